@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the B200 quadrature-point engine.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model vm|heat] [--n QP_PER_GPU]
+    python bench.py --impl reference ...          # the CPU arm (reference algorithm on host cores)
+
+Metric (BASELINE.json): quadrature points per second for stress + consistent tangent +
+internal state, on the von Mises configuration (configs[1]) evaluated on a synthetic batch of
+--n points per GPU (default 1e8 = SURVEY.md section 8d's per-GPU target size).
+
+  value      device-resident: one kernel launch per step over all --n points; inputs (strain
+             increment, committed history) already in HBM; timed with CUDA events on the
+             library's compute stream; max over ranks.
+  e2e        through the public API `VonMises.C_tang_impl` (the callable that
+             `evaluate_external_operators` invokes): strain increment in pinned HOST memory,
+             tangent/stress/dp delivered into pinned HOST arrays, H2D and D2H inside the timed
+             region (history stays resident in HBM, as north_star prescribes).
+  roofline   algorithmic bytes per QP (240 for von Mises: SURVEY.md section 8d) x n / mean kernel time,
+             against MEASURED_PEAKS.json's hbm_gbs.
+  cpu_baseline  the C restatement of the reference's Numba kernel (oracle/, "port") on the
+             box's host cores, bounded sample.
+One JSON line on stdout (rank 0).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_QP = {"vm": 240, "heat": 88}
+METRIC = "quadrature points per second (stress + consistent tangent + internal state)"
+
+
+def _measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------- CPU arm
+def cpu_port_rate(model: str, sample_n: int, min_seconds: float, parallel: bool = True):
+    """Time the oracle's C restatement on host cores over a bounded sample; returns (QP/s, cores, passes)."""
+    from oracle import constitutive as oc
+    from oracle import inputs, native
+
+    native.build()
+    cores = native.num_threads() if parallel else 1
+    if model == "vm":
+        deps, sigma_n, p = inputs.vm_batch(sample_n, seed=0)
+        prm = oc.VonMisesParams()
+        fn = lambda: native.vm_return_mapping(deps, sigma_n, p, prm, parallel=parallel)  # noqa: E731
+    else:
+        T, sigma = inputs.heat_batch(sample_n, seed=0)
+
+        def fn():
+            for w in ("q", "dqdT", "dqdsigma"):
+                native.heat(w, T, sigma, parallel=parallel)
+    fn()  # warm-up (page faults, thread pool)
+    best, passes, t_all = float("inf"), 0, time.perf_counter()
+    while True:
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        best = min(best, dt)
+        passes += 1
+        if time.perf_counter() - t_all >= min_seconds and passes >= 3:
+            break
+    return sample_n / best, cores, passes
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = int(args.cpu_sample)
+    from oracle import constitutive as oc
+    from oracle import inputs, native
+
+    native.build()
+    cores = native.num_threads()
+    deps, sigma_n, p = inputs.vm_batch(sample, seed=0)
+    prm = oc.VonMisesParams()
+    for _ in range(args.warmup):
+        native.vm_return_mapping(deps, sigma_n, p, prm, parallel=True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        native.vm_return_mapping(deps, sigma_n, p, prm, parallel=True)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "QP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "von Mises return mapping (demo_plasticity_von_mises.py:298-332), plane-strain "
+                               "Mandel 4-vectors, ~53% plastic points", "qp_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": "QP/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} QPs per step; C restatement of the reference's Numba kernel "
+                                   f"(the reference kernel itself is serial @numba.njit), OpenMP over {cores} threads"},
+        "e2e": {"value": value, "unit": "QP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------- GPU arm
+def run_gpu_arm(args):
+    import dolfinx_external_operator_b200 as eo
+    from dolfinx_external_operator_b200 import synthetic as inputs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+
+    def barrier():
+        if dist is not None:
+            import torch
+
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    ctx = eo.Context(local_rank)
+    n = int(args.n)
+    model = args.model
+    K, W = args.steps, args.warmup
+
+    # ---- synthetic inputs: a seeded tile (seed = rank) repeated to n points, built on device
+    tile_n = min(n, 1 << 22)
+    reps = (n + tile_n - 1) // tile_n
+
+    def fill(dst: eo.DeviceArray, tile: np.ndarray, width: int):
+        d_tile = ctx.to_device(tile.reshape(-1))
+        for r in range(reps):
+            m = min(tile_n, n - r * tile_n)
+            ctx.copy(dst.ptr + r * tile_n * width * 8, d_tile, m * width * 8)
+        ctx.sync()
+        d_tile.free()
+
+    if model == "vm":
+        vm = eo.VonMises(n_qp=n, ctx=ctx, state_layout=args.state_layout)
+        deps_t, sn_t, p_t = inputs.vm_batch(tile_n, seed=rank)
+        d_deps = ctx.empty((n * 4,))
+        fill(d_deps, deps_t, 4)
+        if args.state_layout == "soa":
+            for c in range(4):
+                col = ctx.to_device(np.ascontiguousarray(sn_t[:, c]))
+                for r in range(reps):
+                    m = min(tile_n, n - r * tile_n)
+                    ctx.copy(vm.sigma_n_dev.ptr + (c * n + r * tile_n) * 8, col, m * 8)
+                ctx.sync()
+                col.free()
+        else:
+            fill(vm.sigma_n_dev, sn_t, 4)
+        fill(vm.p_dev, p_t, 1)
+        d_Ct = ctx.empty((n * 16,))
+
+        def step():
+            vm.eval_device(d_deps, d_Ct)
+    else:
+        T_t, s_t = inputs.heat_batch(tile_n, seed=rank)
+        d_T, d_s = ctx.empty((n,)), ctx.empty((n * 2,))
+        fill(d_T, T_t, 1)
+        fill(d_s, s_t, 2)
+        d_q, d_dT, d_ds = ctx.empty((n * 2,)), ctx.empty((n * 2,)), ctx.empty((n * 4,))
+
+        def step():
+            ctx.check(ctx.lib.eo_heat_eval(ctx.handle, 1.0, 1.0, d_T.ptr, d_s.ptr, None, None, d_q.ptr, d_dT.ptr,
+                                           d_ds.ptr, n))
+
+    def step_with_collective():
+        step()
+        if dist is not None:
+            from dolfinx_external_operator_b200.parallel import allreduce_stats_device
+
+            allreduce_stats_device(ctx)
+
+    # ---- device-resident timing
+    for _ in range(W):
+        step_with_collective()
+    ctx.sync()
+    ctx.stats_reset()
+    ev = [ctx.event() for _ in range(2 * K + 2)]
+    sampler = ClockSampler(local_rank)
+    barrier()
+    ctx.sync()
+    sampler.start()
+    launches0 = ctx.launch_count
+    ctx.record(ev[0])
+    for k in range(K):
+        ctx.record(ev[2 + 2 * k])
+        step()
+        ctx.record(ev[3 + 2 * k])
+        if dist is not None:
+            from dolfinx_external_operator_b200.parallel import allreduce_stats_device
+
+            allreduce_stats_device(ctx)
+    ctx.record(ev[1])
+    ctx.sync()
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count - launches0
+    total_ms = ctx.elapsed_ms(ev[0], ev[1])
+    kernel_ms = [ctx.elapsed_ms(ev[2 + 2 * k], ev[3 + 2 * k]) for k in range(K)]
+    stats = ctx.stats()
+
+    if dist is not None:
+        import torch
+
+        t = torch.tensor([total_ms], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = world * n * K / (total_ms * 1e-3)
+
+    # ---- end-to-end through the public callable (host buffers)
+    e2e = None
+    if model == "vm" and args.e2e_n > 0:
+        ne = int(args.e2e_n)
+        vm_e = eo.VonMises(n_qp=ne, ctx=ctx)
+        deps_h = ctx.pinned_empty((ne, 1, 4))  # (n_cells, n_points, 4), the operand shape of demo_vm:344
+        deps_t2, sn_t2, p_t2 = inputs.vm_batch(min(ne, 1 << 22), seed=rank)
+        flat = deps_h.reshape(-1, 4)
+        for r in range(0, ne, deps_t2.shape[0]):
+            m = min(deps_t2.shape[0], ne - r)
+            flat[r:r + m] = deps_t2[:m]
+        sn_full = np.resize(sn_t2, (ne, 4))
+        p_full = np.resize(p_t2, ne)
+        vm_e.set_history(sn_full, p_full)
+        del sn_full, p_full
+        call = vm_e((1,))
+        Ke = max(2, min(K, 5))
+        for _ in range(2):
+            out = call(deps_h)
+        barrier()
+        t0 = time.perf_counter()
+        checksum = 0.0
+        for _ in range(Ke):
+            Ct_h, sig_h, dp_h = call(deps_h)  # H2D + kernel + D2H, synchronous on return
+            checksum += float(dp_h[0])
+        ctx.sync()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            import torch
+
+            t = torch.tensor([dt], device=f"cuda:{local_rank}", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * ne * Ke / dt, "unit": "QP/s", "h2d_bytes_per_step": 32 * ne,
+               "d2h_bytes_per_step": 168 * ne, "qp_per_step_per_gpu": ne, "steps": Ke,
+               "api": "VonMises((1,))(deps) == external_function(derivatives)(*operands), history resident in HBM"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline for the dominant kernel (the only kernel in a step)
+    peak, peak_src = _measured_peaks()
+    k_ms = float(np.mean(kernel_ms))
+    achieved = BYTES_PER_QP[model] * n / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            tj = json.load(fh).get(model)
+        if tj and tj.get("n") == n:
+            traffic = tj.get("dram_bytes_per_launch")
+
+    # ---- CPU baseline on this box's host cores (bounded sample)
+    cpu = None
+    if args.cpu_seconds > 0:
+        rate, cores, passes = cpu_port_rate(model, int(args.cpu_sample), args.cpu_seconds, parallel=True)
+        rate1, _, _ = cpu_port_rate(model, int(args.cpu_sample) // 4, min(3.0, args.cpu_seconds), parallel=False)
+        cpu = {"value": rate, "unit": "QP/s", "cores": cores, "kind": "port",
+               "sample": f"{int(args.cpu_sample)} QPs x {passes} passes (best pass); C restatement of the reference "
+                         f"kernel, OpenMP; single-thread rate {rate1:.3e} QP/s (the reference's Numba kernel is serial)",
+               "single_thread_value": rate1}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "QP/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": ("von Mises return mapping, plane-strain Mandel 4-vectors (BASELINE configs[1] callable at "
+                         "configs[4] batch size)" if model == "vm" else "nonlinear heat flux q, dq/dT, dq/dsigma fused"),
+            "qp_per_gpu": n, "state_layout": args.state_layout, "plastic_fraction": (
+                stats["n_plastic"] / max(stats["n_points"], 1)),
+            "l2": f"inputs+outputs {BYTES_PER_QP[model] * n / 1e9:.1f} GB per step >> 126 MB L2 (no flush needed)",
+            "partition": "contiguous block of QPs per rank, no halo; one stats all-reduce per step when n_gpus > 1",
+        },
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "bytes_per_qp": BYTES_PER_QP[model],
+                     "kernel_ms": k_ms},
+        "cpu_baseline": cpu,
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="vm", choices=["vm", "heat"])
+    ap.add_argument("--n", type=float, default=1e8, help="quadrature points per GPU (device-resident leg)")
+    ap.add_argument("--e2e-n", type=float, default=1.5e7, help="quadrature points per GPU for the end-to-end leg")
+    ap.add_argument("--state-layout", default="aos", choices=["aos", "soa"])
+    ap.add_argument("--cpu-sample", type=float, default=4e6)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1 and args.gpus > 1 and args.impl == "b200":
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), __file__] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

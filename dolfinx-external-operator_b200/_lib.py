@@ -1,0 +1,112 @@
+"""ctypes binding of libeo_b200.so (C ABI declared in include/eo_b200.h).
+
+There is no fallback: if the shared library is missing, or no sm_100 GPU is
+visible when a context is created, an `EOError` is raised.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libeo_b200.so")
+
+EO_OK = 0
+EO_LAYOUT_AOS = 0
+EO_LAYOUT_SOA = 1
+EO_NITER_BINS = 208
+
+STATUS_NAMES = {
+    0: "EO_OK",
+    -1: "EO_ERR_INVALID",
+    -2: "EO_ERR_CUDA",
+    -3: "EO_ERR_NOMEM",
+    -4: "EO_ERR_UNSUPPORTED",
+    -5: "EO_ERR_NO_DEVICE",
+}
+
+
+class EOError(RuntimeError):
+    def __init__(self, code: int, text: str):
+        super().__init__(f"{STATUS_NAMES.get(code, code)}: {text}")
+        self.code = code
+
+
+class VmParams(C.Structure):
+    _fields_ = [("lmbda", C.c_double), ("mu", C.c_double), ("H", C.c_double), ("sigma_0", C.c_double)]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("n_points", C.c_int64),
+        ("n_plastic", C.c_int64),
+        ("n_nonconverged", C.c_int64),
+        ("n_nonfinite", C.c_int64),
+        ("niter_hist", C.c_int64 * EO_NITER_BINS),
+        ("niter_max", C.c_double),
+        ("f_max", C.c_double),
+        ("res_max", C.c_double),
+        ("reserved", C.c_double),
+    ]
+
+
+_vp = C.c_void_p
+_i64 = C.c_int64
+_dbl = C.c_double
+
+# name -> (restype, argtypes); kept in one table so the CPU test-suite can check
+# that every symbol declared in include/eo_b200.h is exported and bound.
+PROTOTYPES = {
+    "eo_version": (C.c_int, []),
+    "eo_device_count": (C.c_int, []),
+    "eo_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "eo_destroy": (C.c_int, [_vp]),
+    "eo_last_error": (C.c_char_p, [_vp]),
+    "eo_sync": (C.c_int, [_vp]),
+    "eo_stream": (_vp, [_vp]),
+    "eo_set_chunk": (C.c_int, [_vp, _i64]),
+    "eo_launch_count": (_i64, [_vp]),
+    "eo_dev_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
+    "eo_dev_free": (C.c_int, [_vp, _vp]),
+    "eo_dev_memset": (C.c_int, [_vp, _vp, C.c_int, C.c_size_t]),
+    "eo_copy": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+    "eo_host_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
+    "eo_host_free": (C.c_int, [_vp, _vp]),
+    "eo_host_register": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "eo_host_unregister": (C.c_int, [_vp, _vp]),
+    "eo_event_create": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "eo_event_destroy": (C.c_int, [_vp, _vp]),
+    "eo_event_record": (C.c_int, [_vp, _vp]),
+    "eo_event_elapsed_ms": (C.c_int, [_vp, _vp, _vp, C.POINTER(C.c_float)]),
+    "eo_flush_l2": (C.c_int, [_vp, C.c_size_t]),
+    "eo_stats_reset": (C.c_int, [_vp]),
+    "eo_stats_read": (C.c_int, [_vp, C.POINTER(Stats)]),
+    "eo_stats_device_ptr": (_vp, [_vp]),
+    "eo_vm_eval": (C.c_int, [_vp, C.POINTER(VmParams), _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
+    "eo_vm_eval_resident": (C.c_int, [_vp, C.POINTER(VmParams), _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_int]),
+    "eo_commit_history": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, C.c_int]),
+    "eo_heat_eval": (C.c_int, [_vp, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libeo_b200.so and bind every prototype.  Raises EOError if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EOError(
+            -5,
+            f"{LIB_PATH} not found - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback)",
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

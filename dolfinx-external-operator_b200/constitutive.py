@@ -1,0 +1,306 @@
+"""`external_function` factories backed by the sm_100a kernels.
+
+Each class is a drop-in for one of the reference demos' `*_external(derivatives)`
+higher-order functions (protocol: external_operator.py:432 - the outer call
+selects by derivative multi-index, the inner callable receives one array per
+operand, shape `(n_cells, n_points, *operand_shape)`, and returns a flat array or
+a tuple whose element 0 is that array, :435-438).
+
+Differences from the reference callables, all behind the same protocol:
+  * the arithmetic runs in `libeo_b200.so` (C ABI, include/eo_b200.h); the
+    returned arrays live in page-locked host memory owned by the model object
+    (the protocol says the callee keeps ownership - the caller copies, :289-290)
+    or - `bind_outputs` - ARE the coefficient arrays, so no extra copy is made;
+  * operands may be `DeviceArray`s produced by the GPU `evaluate_operands`, in
+    which case nothing is uploaded;
+  * history (`sigma_n`, `p`) may stay resident in HBM (`history="resident"`,
+    committed on device by `commit()` = demo_vm:564-565) instead of being re-read
+    from host `fem.Function`s at every call (`history=` two objects with
+    `.x.array`, the closure style of demo_vm:347-348).
+There is no CPU fallback: without the library / a B200 these raise `EOError`.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import EO_LAYOUT_AOS, EO_LAYOUT_SOA, VmParams
+from .context import Context, DeviceArray, _ptr, default_context
+
+
+def _n_points(arr) -> int:
+    shape = arr.shape
+    return int(np.prod(shape[:-1], dtype=np.int64)) if len(shape) > 1 else int(shape[0])
+
+
+def _as_input(arr):
+    """Borrow an operand without copying when it is already usable."""
+    if isinstance(arr, DeviceArray):
+        return arr
+    a = np.asarray(arr)
+    if a.dtype != np.float64 or not a.flags.c_contiguous:
+        a = np.ascontiguousarray(a, dtype=np.float64)
+    return a
+
+
+class _ModelBase:
+    def __init__(self, ctx: Context | None):
+        self.ctx = ctx or default_context()
+        self._host_out: dict[str, np.ndarray] = {}
+        self._bound: dict[str, np.ndarray] = {}
+
+    def _out(self, name: str, size: int) -> np.ndarray:
+        """Result buffer `name` of `size` f64: a bound coefficient array, or pinned memory we own."""
+        b = self._bound.get(name)
+        if b is not None:
+            if b.size != size:
+                raise ValueError(f"bound output '{name}' has size {b.size}, the evaluation produces {size}")
+            return b
+        a = self._host_out.get(name)
+        if a is None or a.size != size:
+            a = self.ctx.pinned_empty(size)
+            self._host_out[name] = a
+        return a
+
+    def bind_outputs(self, **arrays: np.ndarray):
+        """Let results land directly in long-lived host arrays (e.g.
+        `J_op.ref_coefficient.x.array`): they are page-locked in place and
+        returned by the callable, so `evaluate_external_operators` skips the copy
+        of external_operator.py:289-290."""
+        for name, arr in arrays.items():
+            if not (isinstance(arr, np.ndarray) and arr.dtype == np.float64 and arr.flags.c_contiguous):
+                raise TypeError(f"bind_outputs({name}=...): need a C-contiguous float64 ndarray")
+            self.ctx.register(arr)
+            self._bound[name] = arr
+
+
+# ---------------------------------------------------------------------------------------
+class VonMises(_ModelBase):
+    """von Mises radial return (plane strain, Mandel 4-vectors) with linear isotropic hardening.
+
+    replaces: `return_mapping` + `C_tang_impl` + `sigma_external`,
+    doc/demo/demo_plasticity_von_mises.py:298-368.  Parameters as :185-191.
+    """
+
+    def __init__(
+        self,
+        E: float = 70e3,
+        nu: float = 0.3,
+        E_tangent: float | None = None,
+        sigma_0: float = 250.0,
+        *,
+        history="resident",
+        n_qp: int | None = None,
+        state_layout: str = "aos",
+        ctx: Context | None = None,
+    ):
+        super().__init__(ctx)
+        E_tangent = E / 100.0 if E_tangent is None else E_tangent
+        self.E, self.nu, self.E_tangent, self.sigma_0 = E, nu, E_tangent, sigma_0
+        self.H = E * E_tangent / (E - E_tangent)  # demo_vm:187
+        self.lmbda = E * nu / (1.0 + nu) / (1.0 - 2.0 * nu)  # :190
+        self.mu = E / 2.0 / (1.0 + nu)  # :191
+        self._prm = VmParams(self.lmbda, self.mu, self.H, sigma_0)
+        self.state_layout = {"aos": EO_LAYOUT_AOS, "soa": EO_LAYOUT_SOA}[state_layout]
+        self._resident = isinstance(history, str) and history == "resident"
+        self._history_objs = None if self._resident else tuple(history)  # (sigma_n, p) with .x.array
+        self.n_qp = None
+        self.sigma_n_dev = self.p_dev = self.sigma_dev = self.dp_dev = None
+        if self._resident and n_qp is not None:
+            self._alloc_state(int(n_qp))
+
+    # ------------------------------------------------------------ state
+    def _alloc_state(self, n: int):
+        self.n_qp = n
+        self.sigma_n_dev = self.ctx.zeros((n * 4,))
+        self.p_dev = self.ctx.zeros((n,))
+        self.sigma_dev = self.ctx.zeros((n * 4,))
+        self.dp_dev = self.ctx.zeros((n,))
+
+    def _to_state_layout(self, a: np.ndarray, ncomp: int) -> np.ndarray:
+        a = np.asarray(a, dtype=np.float64).reshape(-1, ncomp)
+        return np.ascontiguousarray(a.T if self.state_layout == EO_LAYOUT_SOA else a)
+
+    def _from_state_layout(self, a: np.ndarray, ncomp: int) -> np.ndarray:
+        if self.state_layout == EO_LAYOUT_SOA:
+            return np.ascontiguousarray(a.reshape(ncomp, -1).T).reshape(-1)
+        return a.reshape(-1)
+
+    def set_history(self, sigma_n: np.ndarray, p: np.ndarray):
+        """Upload history given in the reference's flat layout ([qp][4], [qp])."""
+        n = int(np.asarray(p).size)
+        if self.n_qp != n:
+            self._alloc_state(n)
+        self.sigma_n_dev.copy_from(self._to_state_layout(sigma_n, 4).reshape(-1))
+        self.p_dev.copy_from(np.asarray(p, dtype=np.float64).reshape(-1))
+
+    def get_history(self):
+        """(sigma_n, p) in the reference's flat layout."""
+        return self._from_state_layout(self.sigma_n_dev.to_host(), 4), self.p_dev.to_host()
+
+    def commit(self):
+        """End of a converged load step: p += dp ; sigma_n <- sigma  (demo_vm:564-565), on device."""
+        if not self._resident:
+            raise RuntimeError("commit() is for history='resident'; host history is updated by the caller")
+        c = self.ctx
+        c.check(c.lib.eo_commit_history(c.handle, self.sigma_n_dev.ptr, self.sigma_dev.ptr, self.p_dev.ptr,
+                                        self.dp_dev.ptr, self.n_qp, 4))
+
+    # ------------------------------------------------------------ callable protocol
+    def __call__(self, derivatives):
+        if derivatives == (1,):
+            return self.C_tang_impl
+        raise NotImplementedError(f"No external function is defined for the requested derivative {derivatives}.")
+
+    def C_tang_impl(self, deps):
+        """deps (n_cells, n_pts, 4) -> (C_tang.reshape(-1), sigma.reshape(-1), dp.reshape(-1)), demo_vm:343-352."""
+        deps = _as_input(deps)
+        n = _n_points(deps) if len(deps.shape) > 1 else deps.shape[0] // 4
+        c = self.ctx
+        C_tang = self._out("C_tang", 16 * n)
+        sigma = self._out("sigma", 4 * n)
+        dp = self._out("dp", n)
+        if self._resident:
+            if self.n_qp is None:
+                self._alloc_state(n)
+            if self.n_qp != n:
+                raise ValueError(f"operand has {n} quadrature points, the resident history {self.n_qp}")
+            if self.state_layout == EO_LAYOUT_AOS:
+                # tangent streams to the host through the chunk pipeline; the small
+                # candidates stay in HBM for commit() and are copied out afterwards
+                c.check(c.lib.eo_vm_eval(c.handle, C.byref(self._prm), _ptr(deps), self.sigma_n_dev.ptr,
+                                         self.p_dev.ptr, _ptr(C_tang), self.sigma_dev.ptr, self.dp_dev.ptr, n))
+                self.sigma_dev.to_host(sigma)
+            else:
+                d_deps = deps if isinstance(deps, DeviceArray) else c.to_device(deps.reshape(-1))
+                d_Ct = c.empty((16 * n,))
+                c.check(c.lib.eo_vm_eval_resident(c.handle, C.byref(self._prm), d_deps.ptr, self.sigma_n_dev.ptr,
+                                                  self.p_dev.ptr, d_Ct.ptr, self.sigma_dev.ptr, self.dp_dev.ptr, n,
+                                                  self.state_layout))
+                d_Ct.to_host(C_tang)
+                sigma[:] = self._from_state_layout(self.sigma_dev.to_host(), 4)
+                d_Ct.free()
+                if d_deps is not deps:
+                    d_deps.free()
+            self.dp_dev.to_host(dp)
+        else:
+            sigma_n_f, p_f = self._history_objs
+            sn = _as_input(sigma_n_f.x.array)
+            pp = _as_input(p_f.x.array)
+            if sn.size != 4 * n or pp.size != n:
+                raise ValueError("history arrays do not match the operand's quadrature-point count")
+            c.check(c.lib.eo_vm_eval(c.handle, C.byref(self._prm), _ptr(deps), _ptr(sn), _ptr(pp), _ptr(C_tang),
+                                     _ptr(sigma), _ptr(dp), n))
+        c.sync()
+        return C_tang, sigma, dp
+
+    def eval_device(self, deps: DeviceArray, C_tang: DeviceArray):
+        """All-device evaluation (asynchronous on the ctx stream): the tangent is written to
+        `C_tang`, the candidates to the resident `sigma_dev`/`dp_dev`.  For device-side consumers."""
+        n = deps.size // 4
+        if self.n_qp is None:
+            self._alloc_state(n)
+        c = self.ctx
+        c.check(c.lib.eo_vm_eval_resident(c.handle, C.byref(self._prm), deps.ptr, self.sigma_n_dev.ptr,
+                                          self.p_dev.ptr, C_tang.ptr, self.sigma_dev.ptr, self.dp_dev.ptr, n,
+                                          self.state_layout))
+
+
+# ---------------------------------------------------------------------------------------
+class HeatConductivity(_ModelBase):
+    """k(T) = 1/(A + B T) and its derivative.
+
+    replaces: `k_impl`/`dkdT_impl`/`k_external`, demo_nonlinear_heat_equation_part1.py:247-303."""
+
+    def __init__(self, A: float = 1.0, B: float = 1.0, *, ctx: Context | None = None):
+        super().__init__(ctx)
+        self.A, self.B = float(A), float(B)
+
+    def __call__(self, derivatives):
+        if derivatives == (0,):
+            return self.k_impl
+        elif derivatives == (1,):
+            return self.dkdT_impl
+        raise NotImplementedError(f"No external function is defined for the requested derivative {derivatives}.")
+
+    def _run(self, T, which):
+        T = _as_input(T)
+        n = T.size
+        out = self._out(which, n)
+        c = self.ctx
+        args = {"k": None, "dk": None}
+        args[which] = _ptr(out)
+        c.check(c.lib.eo_heat_eval(c.handle, self.A, self.B, _ptr(T), None, args["k"], args["dk"], None, None, None, n))
+        c.sync()
+        return out
+
+    def k_impl(self, T):
+        return self._run(T, "k")
+
+    def dkdT_impl(self, T):
+        return self._run(T, "dk")
+
+
+class HeatFlux(_ModelBase):
+    """q(T, sigma) = -k(T) sigma and its two derivatives (gdim = 2).
+
+    replaces: `q_impl`/`dqdT_impl`/`dqdsigma_impl`/`q_external`, part2.py:209-284.
+    `fused=True` evaluates all three in ONE kernel launch on the first request of a
+    Newton iteration and serves the other two from the cached results as long as the
+    operand arrays are the same objects (the reference evaluates k(T) three times)."""
+
+    def __init__(self, A: float = 1.0, B: float = 1.0, *, fused: bool = True, ctx: Context | None = None):
+        super().__init__(ctx)
+        self.A, self.B = float(A), float(B)
+        self.fused = fused
+        self._cache_key = None
+
+    def __call__(self, derivatives):
+        if derivatives == (0, 0):
+            return self.q_impl
+        elif derivatives == (1, 0):
+            return self.dqdT_impl
+        elif derivatives == (0, 1):
+            return self.dqdsigma_impl
+        raise NotImplementedError(f"No external function is defined for the requested derivative {derivatives}.")
+
+    def invalidate(self):
+        self._cache_key = None
+
+    def _run(self, T, sigma, want: str):
+        # the cache holds strong references to the operand OBJECTS it was computed from, so a
+        # later array cannot be confused with them by address reuse; in-place mutation of an
+        # operand array between requests needs an explicit invalidate()
+        key = (T, sigma)
+        T = _as_input(T)
+        sigma = _as_input(sigma)
+        n = T.size
+        if sigma.size != 2 * n:
+            raise ValueError("sigma must hold 2 components per quadrature point")
+        c = self.ctx
+        if self.fused:
+            if not (self._cache_key is not None and self._cache_key[0] is key[0] and self._cache_key[1] is key[1]):
+                q, dT, ds = self._out("q", 2 * n), self._out("dqdT", 2 * n), self._out("dqdsigma", 4 * n)
+                c.check(c.lib.eo_heat_eval(c.handle, self.A, self.B, _ptr(T), _ptr(sigma), None, None, _ptr(q),
+                                           _ptr(dT), _ptr(ds), n))
+                c.sync()
+                self._cache_key = key
+            return self._out(want, {"q": 2, "dqdT": 2, "dqdsigma": 4}[want] * n)
+        out = self._out(want, {"q": 2, "dqdT": 2, "dqdsigma": 4}[want] * n)
+        ptrs = {"q": None, "dqdT": None, "dqdsigma": None}
+        ptrs[want] = _ptr(out)
+        c.check(c.lib.eo_heat_eval(c.handle, self.A, self.B, _ptr(T), _ptr(sigma), None, None, ptrs["q"],
+                                   ptrs["dqdT"], ptrs["dqdsigma"], n))
+        c.sync()
+        return out
+
+    def q_impl(self, T, sigma):
+        return self._run(T, sigma, "q")
+
+    def dqdT_impl(self, T, sigma):
+        return self._run(T, sigma, "dqdT")
+
+    def dqdsigma_impl(self, T, sigma):
+        return self._run(T, sigma, "dqdsigma")

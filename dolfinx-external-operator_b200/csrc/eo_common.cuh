@@ -1,0 +1,201 @@
+// eo_common.cuh - internals shared by the translation units of libeo_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "eo_b200.h"
+
+#define EO_NSLOT 3  // pipeline depth of the host-side (staged) path
+
+struct eo_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t s_cmp = nullptr;  // compute stream (== eo_stream)
+  cudaStream_t s_in = nullptr;   // H2D copies
+  cudaStream_t s_out = nullptr;  // D2H copies
+  cudaEvent_t ev_in[EO_NSLOT] = {};
+  cudaEvent_t ev_cmp[EO_NSLOT] = {};
+  cudaEvent_t ev_out[EO_NSLOT] = {};
+  int64_t chunk = int64_t(1) << 20;
+  // staging arena for the host-side path (grown on demand, never shrunk)
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  // L2 flush scratch
+  char* flush = nullptr;
+  size_t flush_bytes = 0;
+  eo_stats* stats = nullptr;  // device
+  int64_t launches = 0;
+  char err[512] = {0};
+};
+
+extern char g_eo_create_error[512];
+
+int eo_fail(eo_ctx* ctx, int code, const char* fmt, ...);
+
+#define EO_CUDA(ctx, call)                                                                         \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return eo_fail(ctx, e__ == cudaErrorMemoryAllocation ? EO_ERR_NOMEM : EO_ERR_CUDA, "%s: %s", \
+                     #call, cudaGetErrorString(e__));                                              \
+  } while (0)
+
+#define EO_REQUIRE(ctx, cond, msg) \
+  do {                             \
+    if (!(cond)) return eo_fail(ctx, EO_ERR_INVALID, "%s", msg); \
+  } while (0)
+
+// true when `p` is memory the GPU kernels can dereference in place
+bool eo_is_device_ptr(const void* p);
+
+// ------------------------------------------------------------------------------------
+// Any-side argument of a per-quadrature-point ("streamed") operation.
+// ------------------------------------------------------------------------------------
+struct eo_arg {
+  const void* ptr;  // host or device, may be nullptr (= absent)
+  size_t bpq;       // bytes per quadrature point
+  bool is_out;
+  bool on_host = false;  // filled by eo_run_streamed
+};
+
+// `launch(ptrs, n_chunk, qp_offset)` must enqueue the kernel(s) on ctx->s_cmp; ptrs[i] is the device
+// address of argument i for this chunk (nullptr when the argument is absent).
+// All-device arguments: one launch over [0, n), asynchronous.  Otherwise chunks of ctx->chunk points
+// flow through EO_NSLOT staging slots: H2D on s_in, kernel on s_cmp, D2H on s_out, chained by events.
+template <class Launch>
+int eo_run_streamed(eo_ctx* ctx, eo_arg* args, int nargs, int64_t n, Launch launch) {
+  if (n == 0) return EO_OK;
+  bool any_host = false;
+  size_t host_bpq = 0;
+  for (int i = 0; i < nargs; ++i) {
+    args[i].on_host = args[i].ptr != nullptr && !eo_is_device_ptr(args[i].ptr);
+    if (args[i].on_host) {
+      any_host = true;
+      host_bpq += (args[i].bpq + 31) / 32 * 32;
+    }
+  }
+  std::vector<void*> ptrs(nargs);
+  if (!any_host) {
+    for (int i = 0; i < nargs; ++i) ptrs[i] = const_cast<void*>(args[i].ptr);
+    int rc = launch(ptrs.data(), n, int64_t(0));
+    if (rc != EO_OK) return rc;
+    EO_CUDA(ctx, cudaGetLastError());
+    return EO_OK;
+  }
+  const int64_t chunk = n < ctx->chunk ? n : ctx->chunk;
+  // every staged array starts on a 256 B boundary inside its slot
+  size_t slot_bytes = 0;
+  for (int i = 0; i < nargs; ++i)
+    if (args[i].on_host) slot_bytes += (size_t(chunk) * args[i].bpq + 255) / 256 * 256;
+  const size_t need = slot_bytes * EO_NSLOT;
+  if (need > ctx->arena_bytes) {
+    EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_cmp));
+    if (ctx->arena) cudaFree(ctx->arena);
+    ctx->arena = nullptr;
+    ctx->arena_bytes = 0;
+    EO_CUDA(ctx, cudaMalloc(&ctx->arena, need));
+    ctx->arena_bytes = need;
+  }
+  // make the copy streams see everything queued on the compute stream so far
+  EO_CUDA(ctx, cudaEventRecord(ctx->ev_cmp[0], ctx->s_cmp));
+  EO_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_cmp[0], 0));
+  EO_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_cmp[0], 0));
+  int64_t c = 0;
+  for (int64_t off = 0; off < n; off += chunk, ++c) {
+    const int slot = int(c % EO_NSLOT);
+    const int64_t m = (n - off) < chunk ? (n - off) : chunk;
+    char* base = ctx->arena + size_t(slot) * slot_bytes;
+    if (c >= EO_NSLOT) {
+      // slot reuse: its previous kernel must have read its inputs, its previous D2H must have drained
+      EO_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_cmp[slot], 0));
+      EO_CUDA(ctx, cudaStreamWaitEvent(ctx->s_cmp, ctx->ev_out[slot], 0));
+    }
+    size_t cur = 0;
+    for (int i = 0; i < nargs; ++i) {
+      if (!args[i].ptr) {
+        ptrs[i] = nullptr;
+      } else if (args[i].on_host) {
+        ptrs[i] = base + cur;
+        cur += (size_t(chunk) * args[i].bpq + 255) / 256 * 256;
+        if (!args[i].is_out)
+          EO_CUDA(ctx, cudaMemcpyAsync(ptrs[i], (const char*)args[i].ptr + size_t(off) * args[i].bpq,
+                                       size_t(m) * args[i].bpq, cudaMemcpyHostToDevice, ctx->s_in));
+      } else {
+        ptrs[i] = (char*)args[i].ptr + size_t(off) * args[i].bpq;
+      }
+    }
+    EO_CUDA(ctx, cudaEventRecord(ctx->ev_in[slot], ctx->s_in));
+    EO_CUDA(ctx, cudaStreamWaitEvent(ctx->s_cmp, ctx->ev_in[slot], 0));
+    int rc = launch(ptrs.data(), m, off);
+    if (rc != EO_OK) return rc;
+    EO_CUDA(ctx, cudaGetLastError());
+    EO_CUDA(ctx, cudaEventRecord(ctx->ev_cmp[slot], ctx->s_cmp));
+    EO_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_cmp[slot], 0));
+    for (int i = 0; i < nargs; ++i)
+      if (args[i].ptr && args[i].on_host && args[i].is_out)
+        EO_CUDA(ctx, cudaMemcpyAsync((char*)args[i].ptr + size_t(off) * args[i].bpq, ptrs[i],
+                                     size_t(m) * args[i].bpq, cudaMemcpyDeviceToHost, ctx->s_out));
+    EO_CUDA(ctx, cudaEventRecord(ctx->ev_out[slot], ctx->s_out));
+  }
+  EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_in));
+  EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_cmp));
+  EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
+  return EO_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// device helpers: 256-bit streaming loads/stores (sm_100: LDG.E.256 / STG.E.256)
+// ------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+struct __align__(32) eo_d4 {
+  double x, y, z, w;
+};
+
+// read-once data: bypass L1 allocation
+__device__ __forceinline__ eo_d4 eo_ld256(const double* p) {
+  eo_d4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void eo_st256(double* p, double x, double y, double z, double w) {
+  asm volatile("st.global.L1::no_allocate.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(x), "d"(y), "d"(z), "d"(w)
+               : "memory");
+}
+__device__ __forceinline__ double2 eo_ld128(const double* p) {
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void eo_st128(double* p, double x, double y) {
+  asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ double eo_ld64(const double* p) {
+  double r;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void eo_st64(double* p, double x) {
+  asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(x) : "memory");
+}
+
+// block-wide sum of a per-thread count, one atomicAdd per CTA
+__device__ __forceinline__ void eo_block_count_add(unsigned long long* dst, int flag) {
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  unsigned m = __ballot_sync(0xffffffffu, flag);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_cnt, __popc(m));
+  __syncthreads();
+  if (threadIdx.x == 0 && s_cnt) atomicAdd(dst, (unsigned long long)s_cnt);
+}
+#endif
+
+static inline bool eo_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }

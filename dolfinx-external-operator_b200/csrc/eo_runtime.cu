@@ -1,0 +1,258 @@
+// eo_runtime.cu - context, memory, events and statistics of libeo_b200.so.
+#include "eo_common.cuh"
+
+char g_eo_create_error[512] = {0};
+
+int eo_fail(eo_ctx* ctx, int code, const char* fmt, ...) {
+  char* dst = ctx ? ctx->err : g_eo_create_error;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(dst, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+bool eo_is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();  // clear
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+__global__ void eo_flush_kernel(float4* buf, size_t n4) {
+  size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (; i < n4; i += stride) buf[i] = make_float4(float(i), 0.f, 0.f, 0.f);
+}
+
+extern "C" {
+
+int eo_version(void) { return EO_B200_VERSION; }
+
+int eo_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    eo_fail(nullptr, EO_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return EO_ERR_NO_DEVICE;
+  }
+  return n;
+}
+
+int eo_create(int device, eo_ctx** out) {
+  if (!out) return eo_fail(nullptr, EO_ERR_INVALID, "eo_create: out is NULL");
+  *out = nullptr;
+  int n = eo_device_count();
+  if (n <= 0) return eo_fail(nullptr, EO_ERR_NO_DEVICE, "eo_create: no CUDA device visible (this library has no CPU path)");
+  if (device < 0 || device >= n) return eo_fail(nullptr, EO_ERR_INVALID, "eo_create: device %d out of range [0,%d)", device, n);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+    return eo_fail(nullptr, EO_ERR_CUDA, "eo_create: cudaGetDeviceProperties failed");
+  if (prop.major != 10)
+    return eo_fail(nullptr, EO_ERR_NO_DEVICE, "eo_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                   device, prop.major, prop.minor);
+  eo_ctx* ctx = new eo_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+#define EO_CREATE_CUDA(call)                                                                      \
+  do {                                                                                            \
+    cudaError_t e__ = (call);                                                                     \
+    if (e__ != cudaSuccess) {                                                                     \
+      eo_fail(nullptr, EO_ERR_CUDA, "eo_create: %s: %s", #call, cudaGetErrorString(e__));         \
+      delete ctx;                                                                                 \
+      return EO_ERR_CUDA;                                                                         \
+    }                                                                                             \
+  } while (0)
+  EO_CREATE_CUDA(cudaSetDevice(device));
+  EO_CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->s_cmp, cudaStreamNonBlocking));
+  EO_CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+  EO_CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < EO_NSLOT; ++i) {
+    EO_CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+    EO_CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_cmp[i], cudaEventDisableTiming));
+    EO_CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
+  }
+  EO_CREATE_CUDA(cudaMalloc(&ctx->stats, sizeof(eo_stats)));
+  EO_CREATE_CUDA(cudaMemset(ctx->stats, 0, sizeof(eo_stats)));
+#undef EO_CREATE_CUDA
+  *out = ctx;
+  return EO_OK;
+}
+
+int eo_destroy(eo_ctx* ctx) {
+  if (!ctx) return EO_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->s_in);
+  cudaStreamSynchronize(ctx->s_cmp);
+  cudaStreamSynchronize(ctx->s_out);
+  for (int i = 0; i < EO_NSLOT; ++i) {
+    if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+    if (ctx->ev_cmp[i]) cudaEventDestroy(ctx->ev_cmp[i]);
+    if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
+  }
+  if (ctx->arena) cudaFree(ctx->arena);
+  if (ctx->flush) cudaFree(ctx->flush);
+  if (ctx->stats) cudaFree(ctx->stats);
+  if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+  if (ctx->s_cmp) cudaStreamDestroy(ctx->s_cmp);
+  if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+  delete ctx;
+  return EO_OK;
+}
+
+const char* eo_last_error(const eo_ctx* ctx) { return ctx ? ctx->err : g_eo_create_error; }
+
+int eo_sync(eo_ctx* ctx) {
+  EO_REQUIRE(ctx, ctx != nullptr, "eo_sync: ctx is NULL");
+  EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_in));
+  EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_cmp));
+  EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
+  return EO_OK;
+}
+
+void* eo_stream(eo_ctx* ctx) { return ctx ? (void*)ctx->s_cmp : nullptr; }
+
+int eo_set_chunk(eo_ctx* ctx, int64_t n) {
+  EO_REQUIRE(ctx, ctx != nullptr, "eo_set_chunk: ctx is NULL");
+  EO_REQUIRE(ctx, n >= 32, "eo_set_chunk: chunk must be >= 32 quadrature points");
+  ctx->chunk = (n + 31) / 32 * 32;  // keeps every chunk start 32 B aligned for every f64 field
+  return EO_OK;
+}
+
+int64_t eo_launch_count(const eo_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------ memory
+int eo_dev_alloc(eo_ctx* ctx, size_t bytes, void** dptr) {
+  EO_REQUIRE(ctx, ctx && dptr, "eo_dev_alloc: NULL argument");
+  *dptr = nullptr;
+  if (bytes == 0) return EO_OK;
+  EO_CUDA(ctx, cudaSetDevice(ctx->device));
+  EO_CUDA(ctx, cudaMalloc(dptr, bytes));
+  return EO_OK;
+}
+
+int eo_dev_free(eo_ctx* ctx, void* dptr) {
+  EO_REQUIRE(ctx, ctx != nullptr, "eo_dev_free: ctx is NULL");
+  if (!dptr) return EO_OK;
+  EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_cmp));
+  EO_CUDA(ctx, cudaFree(dptr));
+  return EO_OK;
+}
+
+int eo_dev_memset(eo_ctx* ctx, void* dptr, int value, size_t bytes) {
+  EO_REQUIRE(ctx, ctx != nullptr, "eo_dev_memset: ctx is NULL");
+  if (bytes == 0) return EO_OK;
+  EO_REQUIRE(ctx, dptr != nullptr, "eo_dev_memset: dptr is NULL");
+  EO_CUDA(ctx, cudaMemsetAsync(dptr, value, bytes, ctx->s_cmp));
+  return EO_OK;
+}
+
+int eo_copy(eo_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  EO_REQUIRE(ctx, ctx != nullptr, "eo_copy: ctx is NULL");
+  if (bytes == 0) return EO_OK;
+  EO_REQUIRE(ctx, dst && src, "eo_copy: NULL pointer");
+  const bool dd = eo_is_device_ptr(dst), sd = eo_is_device_ptr(src);
+  EO_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->s_cmp));
+  if (!(dd && sd)) EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_cmp));
+  return EO_OK;
+}
+
+int eo_host_alloc(eo_ctx* ctx, size_t bytes, void** hptr) {
+  EO_REQUIRE(ctx, ctx && hptr, "eo_host_alloc: NULL argument");
+  *hptr = nullptr;
+  if (bytes == 0) return EO_OK;
+  EO_CUDA(ctx, cudaHostAlloc(hptr, bytes, cudaHostAllocDefault));
+  return EO_OK;
+}
+
+int eo_host_free(eo_ctx* ctx, void* hptr) {
+  EO_REQUIRE(ctx, ctx != nullptr, "eo_host_free: ctx is NULL");
+  if (!hptr) return EO_OK;
+  EO_CUDA(ctx, cudaFreeHost(hptr));
+  return EO_OK;
+}
+
+int eo_host_register(eo_ctx* ctx, void* hptr, size_t bytes) {
+  EO_REQUIRE(ctx, ctx && hptr, "eo_host_register: NULL argument");
+  if (bytes == 0) return EO_OK;
+  cudaError_t e = cudaHostRegister(hptr, bytes, cudaHostRegisterDefault);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    cudaGetLastError();
+    return EO_OK;
+  }
+  EO_CUDA(ctx, e);
+  return EO_OK;
+}
+
+int eo_host_unregister(eo_ctx* ctx, void* hptr) {
+  EO_REQUIRE(ctx, ctx && hptr, "eo_host_unregister: NULL argument");
+  cudaError_t e = cudaHostUnregister(hptr);
+  if (e == cudaErrorHostMemoryNotRegistered) {
+    cudaGetLastError();
+    return EO_OK;
+  }
+  EO_CUDA(ctx, e);
+  return EO_OK;
+}
+
+// ------------------------------------------------------------------ timing
+int eo_event_create(eo_ctx* ctx, void** ev) {
+  EO_REQUIRE(ctx, ctx && ev, "eo_event_create: NULL argument");
+  cudaEvent_t e;
+  EO_CUDA(ctx, cudaEventCreate(&e));
+  *ev = (void*)e;
+  return EO_OK;
+}
+int eo_event_destroy(eo_ctx* ctx, void* ev) {
+  EO_REQUIRE(ctx, ctx != nullptr, "eo_event_destroy: ctx is NULL");
+  if (ev) EO_CUDA(ctx, cudaEventDestroy((cudaEvent_t)ev));
+  return EO_OK;
+}
+int eo_event_record(eo_ctx* ctx, void* ev) {
+  EO_REQUIRE(ctx, ctx && ev, "eo_event_record: NULL argument");
+  EO_CUDA(ctx, cudaEventRecord((cudaEvent_t)ev, ctx->s_cmp));
+  return EO_OK;
+}
+int eo_event_elapsed_ms(eo_ctx* ctx, void* a, void* b, float* ms) {
+  EO_REQUIRE(ctx, ctx && a && b && ms, "eo_event_elapsed_ms: NULL argument");
+  EO_CUDA(ctx, cudaEventSynchronize((cudaEvent_t)b));
+  EO_CUDA(ctx, cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b));
+  return EO_OK;
+}
+
+int eo_flush_l2(eo_ctx* ctx, size_t bytes) {
+  EO_REQUIRE(ctx, ctx != nullptr, "eo_flush_l2: ctx is NULL");
+  if (bytes == 0) return EO_OK;
+  bytes = (bytes + 15) / 16 * 16;
+  if (bytes > ctx->flush_bytes) {
+    EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_cmp));
+    if (ctx->flush) cudaFree(ctx->flush);
+    ctx->flush = nullptr;
+    ctx->flush_bytes = 0;
+    EO_CUDA(ctx, cudaMalloc(&ctx->flush, bytes));
+    ctx->flush_bytes = bytes;
+  }
+  eo_flush_kernel<<<ctx->sm_count * 8, 256, 0, ctx->s_cmp>>>((float4*)ctx->flush, bytes / 16);
+  EO_CUDA(ctx, cudaGetLastError());
+  return EO_OK;
+}
+
+// ------------------------------------------------------------------ statistics
+int eo_stats_reset(eo_ctx* ctx) {
+  EO_REQUIRE(ctx, ctx != nullptr, "eo_stats_reset: ctx is NULL");
+  EO_CUDA(ctx, cudaMemsetAsync(ctx->stats, 0, sizeof(eo_stats), ctx->s_cmp));
+  return EO_OK;
+}
+int eo_stats_read(eo_ctx* ctx, eo_stats* out) {
+  EO_REQUIRE(ctx, ctx && out, "eo_stats_read: NULL argument");
+  EO_CUDA(ctx, cudaMemcpyAsync(out, ctx->stats, sizeof(eo_stats), cudaMemcpyDeviceToHost, ctx->s_cmp));
+  EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_cmp));
+  return EO_OK;
+}
+void* eo_stats_device_ptr(eo_ctx* ctx) { return ctx ? (void*)ctx->stats : nullptr; }
+
+}  // extern "C"

@@ -1,0 +1,79 @@
+"""Multi-GPU plumbing: one process per GPU, quadrature points partitioned along the
+existing cell partition (reference: each rank evaluates its own local+ghost cells,
+external_operator.py:368-370, and `scatter_forward`s afterwards, :445).
+
+For Quadrature spaces every DOF is cell-interior and ghosts are recomputed locally, so the
+hot path needs NO data exchange.  The one collective is the all-reduce of the statistics
+record (plastic / non-converged counts, Newton-iteration histogram: SUM; maxima: MAX) that
+replaces the rank-local prints of demo_plasticity_mohr_coulomb.py:584-591.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from ._lib import EO_NITER_BINS
+
+N_SUM = 4 + EO_NITER_BINS  # int64 entries of eo_stats' SUM block
+N_MAX = 4  # f64 entries of the MAX block
+
+
+def partition(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous block partition of `n` quadrature points (or cells): [start, stop) of `rank`.
+    The first n % world ranks get one extra item - the same rule DOLFINx's index maps use for
+    an unpartitioned range."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world: {rank}/{world}")
+    base, rem = divmod(int(n), world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def stats_to_arrays(stats: dict) -> tuple[np.ndarray, np.ndarray]:
+    s = np.empty(N_SUM, dtype=np.int64)
+    s[0], s[1], s[2], s[3] = stats["n_points"], stats["n_plastic"], stats["n_nonconverged"], stats["n_nonfinite"]
+    s[4:] = stats["niter_hist"]
+    m = np.array([stats["niter_max"], stats["f_max"], stats["res_max"], 0.0])
+    return s, m
+
+
+def arrays_to_stats(s: np.ndarray, m: np.ndarray) -> dict:
+    return {
+        "n_points": int(s[0]), "n_plastic": int(s[1]), "n_nonconverged": int(s[2]), "n_nonfinite": int(s[3]),
+        "niter_hist": np.asarray(s[4:], dtype=np.int64).copy(),
+        "niter_max": float(m[0]), "f_max": float(m[1]), "res_max": float(m[2]),
+    }
+
+
+def allreduce_stats_host(stats: dict, group=None) -> dict:
+    """All-reduce a statistics dict through torch.distributed with host tensors (gloo)."""
+    import torch
+    import torch.distributed as dist
+
+    s, m = stats_to_arrays(stats)
+    ts, tm = torch.from_numpy(s), torch.from_numpy(m)
+    dist.all_reduce(ts, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(tm, op=dist.ReduceOp.MAX, group=group)
+    return arrays_to_stats(ts.numpy(), tm.numpy())
+
+
+class _StatsView:
+    """`__cuda_array_interface__` window on a slice of the device statistics record."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+def allreduce_stats_device(ctx, group=None) -> None:
+    """In-place NCCL all-reduce of ctx's device statistics record, ordered on the ctx compute
+    stream (two tiny collectives: SUM over the int64 block, MAX over the f64 block)."""
+    import torch
+    import torch.distributed as dist
+
+    base = ctx.stats_device_ptr
+    ts = torch.as_tensor(_StatsView(base, N_SUM, "<i8"), device=f"cuda:{ctx.device}")
+    tm = torch.as_tensor(_StatsView(base + 8 * N_SUM, N_MAX, "<f8"), device=f"cuda:{ctx.device}")
+    with torch.cuda.stream(torch.cuda.ExternalStream(ctx.stream, device=f"cuda:{ctx.device}")):
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX, group=group)

@@ -1,0 +1,168 @@
+/* eo_b200.h - C ABI of libeo_b200.so: the B200 (sm_100a) implementation of the
+ * quadrature-point hot path of dolfinx-external-operator.
+ *
+ * The reference has no FFI of its own: its plug-in boundary is the Python
+ * callable protocol `external_function(derivatives)(*operand_arrays)` used at
+ * src/dolfinx_external_operator/external_operator.py:432, and the operand
+ * tabulation `fem.Expression.eval` at external_operator.py:393-402.  Each entry
+ * point below names the reference code it stands in for ("replaces:").  The
+ * ctypes binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C, no C++/torch types; every function returns 0 (EO_OK) or a negative
+ *    eo_status; eo_last_error(ctx) gives the text; nothing throws.
+ *  - one eo_ctx = one GPU = one compute stream (+2 copy streams).  Calls on one
+ *    ctx must come from one thread at a time (the reference is single threaded
+ *    per MPI rank, petsc/petsc.py:60).
+ *  - array arguments are "any-side" pointers unless stated: they may point to
+ *    device memory (used in place, zero copy), to pinned/registered host memory
+ *    or to pageable host memory (both staged through a chunked, double-buffered
+ *    H2D -> kernel -> D2H pipeline).  The side is detected per pointer with
+ *    cudaPointerGetAttributes.  Host-side calls are complete (data landed) on
+ *    return; all-device calls are asynchronous on the ctx stream - use eo_sync.
+ *  - layouts are the reference's flat C-order arrays: a field with value shape S
+ *    at n quadrature points is [n][prod(S)] ("AoS", e.g. demo_vm:352).  Entry
+ *    points with an explicit `layout` argument also accept EO_LAYOUT_SOA
+ *    ([prod(S)][n]) for fields that stay resident in HBM.
+ *  - all floating point data is IEEE binary64 ("f64"); dofmaps are int32.
+ */
+#ifndef EO_B200_H
+#define EO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EO_B200_VERSION 100 /* 0.1.0 */
+
+typedef enum eo_status {
+  EO_OK = 0,
+  EO_ERR_INVALID = -1,     /* bad argument (NULL, negative size, misaligned, unknown enum) */
+  EO_ERR_CUDA = -2,        /* a CUDA runtime call failed; text in eo_last_error */
+  EO_ERR_NOMEM = -3,       /* device or pinned-host allocation failed */
+  EO_ERR_UNSUPPORTED = -4, /* valid request this build does not implement */
+  EO_ERR_NO_DEVICE = -5    /* no CUDA device / not an sm_100 device */
+} eo_status;
+
+typedef enum eo_layout { EO_LAYOUT_AOS = 0, EO_LAYOUT_SOA = 1 } eo_layout;
+
+typedef struct eo_ctx eo_ctx;
+
+/* ---------------------------------------------------------------- lifetime */
+int eo_version(void);
+/* Number of visible CUDA devices, or a negative eo_status. */
+int eo_device_count(void);
+/* Create a context on `device`.  Fails with EO_ERR_NO_DEVICE when there is no
+ * GPU: there is NO CPU fallback in this library. */
+int eo_create(int device, eo_ctx** out);
+int eo_destroy(eo_ctx* ctx);
+/* Text of the last error on this ctx ("" if none).  ctx == NULL returns the
+ * text of the last eo_create failure. */
+const char* eo_last_error(const eo_ctx* ctx);
+/* Block until all work queued on the ctx streams has finished. */
+int eo_sync(eo_ctx* ctx);
+/* The ctx compute stream as a cudaStream_t cast to void* (for interop). */
+void* eo_stream(eo_ctx* ctx);
+/* Quadrature points per pipeline chunk for host-side calls (default 1<<20). */
+int eo_set_chunk(eo_ctx* ctx, int64_t n_qp_per_chunk);
+/* Count of kernel launches issued by this ctx since creation. */
+int64_t eo_launch_count(const eo_ctx* ctx);
+
+/* ---------------------------------------------------------------- memory */
+int eo_dev_alloc(eo_ctx* ctx, size_t bytes, void** dptr);
+int eo_dev_free(eo_ctx* ctx, void* dptr);
+int eo_dev_memset(eo_ctx* ctx, void* dptr, int value, size_t bytes);
+/* Any-side copy (host<->device, device<->device) ordered on the ctx stream;
+ * synchronous on return when either side is host memory. */
+int eo_copy(eo_ctx* ctx, void* dst, const void* src, size_t bytes);
+/* Pinned host memory (the callee-owned result buffers of the callable protocol). */
+int eo_host_alloc(eo_ctx* ctx, size_t bytes, void** hptr);
+int eo_host_free(eo_ctx* ctx, void* hptr);
+/* Page-lock an existing host array in place (e.g. `ref_coefficient.x.array`,
+ * external_operator.py:289-290) so the D2H lands in it at full PCIe rate. */
+int eo_host_register(eo_ctx* ctx, void* hptr, size_t bytes);
+int eo_host_unregister(eo_ctx* ctx, void* hptr);
+
+/* ---------------------------------------------------------------- timing
+ * CUDA events on the ctx compute stream (bench.py times kernels with these). */
+int eo_event_create(eo_ctx* ctx, void** ev);
+int eo_event_destroy(eo_ctx* ctx, void* ev);
+int eo_event_record(eo_ctx* ctx, void* ev);
+int eo_event_elapsed_ms(eo_ctx* ctx, void* ev_start, void* ev_stop, float* ms);
+/* Write `bytes` of device scratch (> L2) on the ctx stream: L2 flush between
+ * timed iterations. */
+int eo_flush_l2(eo_ctx* ctx, size_t bytes);
+
+/* ---------------------------------------------------------------- statistics
+ * Device-resident record that every constitutive kernel accumulates into in its
+ * epilogue (one atomic per CTA).  replaces: the host-side `jnp.unique(niter,
+ * return_counts=True)`, `jnp.max(yielding)`, `jnp.max(norm_res)` of
+ * demo_plasticity_mohr_coulomb.py:584-591, and is the payload of the one
+ * scalar all-reduce of a multi-GPU run (sums and maxima are kept apart so that
+ * two tiny ncclAllReduce calls - SUM over the int64 block, MAX over the f64
+ * block - combine ranks). */
+#define EO_NITER_BINS 208 /* local-Newton iteration histogram, bins 0..Nitermax(200); padded */
+typedef struct eo_stats {
+  /* SUM block: 4 + EO_NITER_BINS int64 */
+  int64_t n_points;       /* quadrature points evaluated */
+  int64_t n_plastic;      /* vm: dp > 0 ; mc: yielding > 0 */
+  int64_t n_nonconverged; /* mc: left the Newton loop by niter == Nitermax */
+  int64_t n_nonfinite;    /* points whose stress is NaN/Inf */
+  int64_t niter_hist[EO_NITER_BINS];
+  /* MAX block: 4 f64 */
+  double niter_max;
+  double f_max;   /* mc: max yielding (demo_mc:590) */
+  double res_max; /* mc: max ||res|| (demo_mc:591) */
+  double reserved;
+} eo_stats;
+int eo_stats_reset(eo_ctx* ctx);
+/* Copies the record to host (synchronises the ctx stream). */
+int eo_stats_read(eo_ctx* ctx, eo_stats* host_out);
+/* Device address of the record (for an in-place NCCL all-reduce). */
+void* eo_stats_device_ptr(eo_ctx* ctx);
+
+/* ---------------------------------------------------------------- von Mises
+ * replaces: `return_mapping`/`_kernel`, doc/demo/demo_plasticity_von_mises.py:298-332,
+ *           and the body of `C_tang_impl` :343-352.
+ * Constants: demo_vm:185-191 (lmbda, mu from E, nu; H = E*Et/(E-Et); sigma_0). */
+typedef struct eo_vm_params {
+  double lmbda, mu, H, sigma_0;
+} eo_vm_params;
+
+/* deps [n][4], sigma_n [n][4], p [n]  ->  C_tang [n][4][4], sigma [n][4], dp [n].
+ * Branch-free like the source; returns, like the reference, NaN where
+ * sigma_eq == 0 or f == 0 exactly.  Algorithmic HBM traffic: 72 B read + 168 B
+ * written per quadrature point.  The number of points with dp > 0 is added to
+ * the ctx statistics record (eo_stats.n_plastic). */
+int eo_vm_eval(eo_ctx* ctx, const eo_vm_params* prm, const double* deps, const double* sigma_n, const double* p,
+               double* C_tang, double* sigma, double* dp, int64_t n);
+
+/* Same computation with the history resident in HBM in the given layout
+ * (device pointers only).  sigma_n/p are the committed history, sigma/dp the
+ * candidates of this Newton iteration; deps and C_tang are AoS. */
+int eo_vm_eval_resident(eo_ctx* ctx, const eo_vm_params* prm, const double* deps, const double* sigma_n,
+                        const double* p, double* C_tang, double* sigma, double* dp, int64_t n, int state_layout);
+
+/* History commit after a converged load step, on device.
+ * replaces: `p.x.petsc_vec.axpy(1.0, dp.x.petsc_vec)` and
+ *           `sigma_n.x.array[:] = sigma.ref_coefficient.x.array`, demo_vm:564-565
+ *           (sigma_n <- sigma alone: demo_mc:728; pass p = dp = NULL). */
+int eo_commit_history(eo_ctx* ctx, double* sigma_n, const double* sigma, double* p, const double* dp, int64_t n,
+                      int ncomp);
+
+/* ---------------------------------------------------------------- heat
+ * replaces: `k_impl`/`dkdT_impl`, demo_nonlinear_heat_equation_part1.py:252-272;
+ *           `q_impl`/`dqdT_impl`/`dqdsigma_impl`, part2.py:219-261 (gdim = 2).
+ * T [n], sigma [n][2] (may be NULL when no q-type output is requested).
+ * Outputs (each may be NULL = not requested; all requested ones are produced by
+ * ONE fused kernel): k [n], dk [n], q [n][2], dqdT [n][2], dqdsigma [n][2][2]. */
+int eo_heat_eval(eo_ctx* ctx, double A, double B, const double* T, const double* sigma, double* k, double* dk,
+                 double* q, double* dqdT, double* dqdsigma, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EO_B200_H */

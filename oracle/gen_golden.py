@@ -1,0 +1,56 @@
+"""TEST INFRASTRUCTURE - writes tests/golden/*.npz by executing the REFERENCE's own
+constitutive source (see oracle/ref_exec.py).  Runs only in the build container, where
+/root/reference exists; the GPU box uses the committed .npz files.
+
+    python -m oracle.gen_golden [vm] [heat] [mc] [isihara]
+"""
+
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+import sys as _sys, os as _os
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+from . import inputs, ref_exec  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def gen_vm():
+    ns = ref_exec.load_von_mises(num_quadrature_points=3)
+    out = {}
+    for kind in ("mixed", "elastic", "plastic"):
+        n = 1026  # 342 cells x 3 points
+        deps, sigma_n, p = inputs.vm_batch(n, seed=0, kind=kind)
+        Ct, sig, dp = ns["return_mapping"](deps.reshape(-1, 3, 4), sigma_n.reshape(-1, 3, 4), p.reshape(-1, 3))
+        out.update({f"{kind}_deps": deps, f"{kind}_sigma_n": sigma_n, f"{kind}_p": p,
+                    f"{kind}_C_tang": Ct.reshape(n, 4, 4), f"{kind}_sigma": sig.reshape(n, 4), f"{kind}_dp": dp.reshape(n)})
+    out["params"] = np.array([ns["E"], 0.3, ns["E_tangent"], ns["sigma_0"], ns["H"], ns["lmbda"], ns["mu"]])
+    np.savez_compressed(os.path.join(GOLDEN, "vm_seed0_n1026.npz"), **out)
+    print("vm golden written; plastic fraction (mixed):", float((out["mixed_dp"] > 0).mean()))
+
+
+def gen_heat():
+    h1 = ref_exec.load_heat_part1()
+    h2 = ref_exec.load_heat_part2()
+    n_cells, n_pts = 1366, 3
+    T, sigma = inputs.heat_batch(n_cells * n_pts, seed=0)
+    T2 = T.reshape(n_cells, n_pts)
+    s2 = sigma.reshape(n_cells, n_pts * 2)
+    np.savez_compressed(
+        os.path.join(GOLDEN, "heat_seed0_n4098.npz"),
+        T=T, sigma=sigma,
+        k=h1["k_impl"](T2), dk=h1["dkdT_impl"](T2),
+        q=h2["q_impl"](T2, s2), dqdT=h2["dqdT_impl"](T2, s2), dqdsigma=h2["dqdsigma_impl"](T2, s2),
+    )
+    print("heat golden written")
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLDEN, exist_ok=True)
+    what = sys.argv[1:] or ["vm", "heat"]
+    for w in what:
+        globals()[f"gen_{w}"]()

@@ -1,0 +1,72 @@
+"""TEST INFRASTRUCTURE - ctypes access to oracle/liboracle.so (the C/C++ restatements).
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this."""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_lib = None
+
+
+class OracleVmParams(C.Structure):
+    _fields_ = [("lmbda", C.c_double), ("mu", C.c_double), ("H", C.c_double), ("sigma_0", C.c_double)]
+
+
+def build(force: bool = False) -> str:
+    if force or not os.path.exists(LIB_PATH):
+        subprocess.check_call(["make", "-C", _HERE] + (["-B"] if force else []), stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.oracle_num_threads.restype = C.c_int
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def num_threads() -> int:
+    return int(load().oracle_num_threads())
+
+
+def vm_return_mapping(deps, sigma_n, p, prm, parallel: bool = False):
+    """C restatement of demo_vm:298-332; arrays in the reference's layout."""
+    lib = load()
+    deps = np.ascontiguousarray(deps, dtype=np.float64).reshape(-1, 4)
+    sigma_n = np.ascontiguousarray(sigma_n, dtype=np.float64).reshape(-1, 4)
+    p = np.ascontiguousarray(p, dtype=np.float64).reshape(-1)
+    n = p.size
+    Ct = np.empty((n, 4, 4))
+    sig = np.empty((n, 4))
+    dp = np.empty(n)
+    q = OracleVmParams(prm.lmbda, prm.mu, prm.H, prm.sigma_0)
+    lib.oracle_vm_return_mapping(C.byref(q), _p(deps), _p(sigma_n), _p(p), _p(Ct), _p(sig), _p(dp), C.c_int64(n),
+                                 C.c_int(int(parallel)))
+    return Ct, sig, dp
+
+
+_HEAT = {"k": (0, 1), "dk": (1, 1), "q": (2, 2), "dqdT": (3, 2), "dqdsigma": (4, 4)}
+
+
+def heat(which: str, T, sigma=None, A=1.0, B=1.0, parallel: bool = False):
+    lib = load()
+    code, width = _HEAT[which]
+    T = np.ascontiguousarray(T, dtype=np.float64).reshape(-1)
+    s = None if sigma is None else np.ascontiguousarray(sigma, dtype=np.float64).reshape(-1)
+    out = np.empty(T.size * width)
+    lib.oracle_heat(C.c_int(code), C.c_double(A), C.c_double(B), _p(T), _p(s), _p(out), C.c_int64(T.size),
+                    C.c_int(int(parallel)))
+    return out
