@@ -70,3 +70,48 @@ def heat(which: str, T, sigma=None, A=1.0, B=1.0, parallel: bool = False):
     lib.oracle_heat(C.c_int(code), C.c_double(A), C.c_double(B), _p(T), _p(s), _p(out), C.c_int64(T.size),
                     C.c_int(int(parallel)))
     return out
+
+
+class OracleMcParams(C.Structure):
+    _fields_ = [("E", C.c_double), ("nu", C.c_double), ("c", C.c_double), ("phi", C.c_double), ("psi", C.c_double),
+                ("theta_T", C.c_double), ("a", C.c_double), ("tol", C.c_double), ("Nitermax", C.c_int32)]
+
+
+def _mc_prm(prm):
+    return OracleMcParams(prm.E, prm.nu, prm.c, prm.phi, prm.psi, prm.theta_T, prm.a, prm.tol, prm.Nitermax)
+
+
+def mc_return_mapping(deps, sigma_n, prm, parallel: bool = False):
+    """C++ dual-number restatement of demo_mc:474-555.  Returns dict(C_tang, sigma, niter, yielding, norm_res, dlambda)."""
+    lib = load()
+    deps = np.ascontiguousarray(deps, dtype=np.float64).reshape(-1, 4)
+    sigma_n = np.ascontiguousarray(sigma_n, dtype=np.float64).reshape(-1, 4)
+    n = deps.shape[0]
+    out = {"C_tang": np.empty((n, 4, 4)), "sigma": np.empty((n, 4)), "niter": np.empty(n, dtype=np.int32),
+           "yielding": np.empty(n), "norm_res": np.empty(n), "dlambda": np.empty(n)}
+    q = _mc_prm(prm)
+    lib.oracle_mc_return_mapping(C.byref(q), _p(deps), _p(sigma_n), _p(out["C_tang"]), _p(out["sigma"]),
+                                 _p(out["niter"]), _p(out["yielding"]), _p(out["norm_res"]), _p(out["dlambda"]),
+                                 C.c_int64(n), C.c_int(int(parallel)))
+    return out
+
+
+def mc_stress(deps, sigma_n, prm, parallel: bool = False):
+    lib = load()
+    deps = np.ascontiguousarray(deps, dtype=np.float64).reshape(-1, 4)
+    sigma_n = np.ascontiguousarray(sigma_n, dtype=np.float64).reshape(-1, 4)
+    n = deps.shape[0]
+    sig, nit, yl = np.empty((n, 4)), np.empty(n, dtype=np.int32), np.empty(n)
+    q = _mc_prm(prm)
+    lib.oracle_mc_stress(C.byref(q), _p(deps), _p(sigma_n), _p(sig), _p(nit), _p(yl), C.c_int64(n),
+                         C.c_int(int(parallel)))
+    return sig, nit, yl
+
+
+def mc_yield(sigma, prm):
+    lib = load()
+    sigma = np.ascontiguousarray(sigma, dtype=np.float64).reshape(-1, 4)
+    f = np.empty(sigma.shape[0])
+    q = _mc_prm(prm)
+    lib.oracle_mc_yield(C.byref(q), _p(sigma), _p(f), C.c_int64(sigma.shape[0]))
+    return f
