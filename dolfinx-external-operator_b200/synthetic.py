@@ -23,3 +23,94 @@ def heat_batch(n: int, seed: int = 0):
     """T ~ U(0,2) (so A + B T > 0), sigma = grad T ~ N(0,1)^2."""
     rng = np.random.default_rng(seed)
     return rng.uniform(0.0, 2.0, n), rng.normal(0.0, 1.0, (n, 2))
+
+
+# ----------------------------------------------------------------------------- Mohr-Coulomb
+MC_E, MC_NU = 6778.0, 0.25  # demo_plasticity_mohr_coulomb.py:110-111
+
+
+def mc_compliance(E: float = MC_E, nu: float = MC_NU) -> np.ndarray:
+    """S_elas = inv(C_elas) of demo_mc:405-416 in closed form (plane-strain Mandel 4x4)."""
+    S = np.zeros((4, 4))
+    S[:3, :3] = -nu / E
+    S[0, 0] = S[1, 1] = S[2, 2] = 1.0 / E
+    S[3, 3] = (1.0 + nu) / E  # 1/(2 mu)
+    return S
+
+
+def mc_rotate(v: np.ndarray, omega: np.ndarray) -> np.ndarray:
+    """Rotate plane-strain Mandel vectors [xx, yy, zz, sqrt2 xy] by the in-plane angle omega
+    (the model is isotropic, so the return mapping commutes with this rotation; it only serves to
+    populate the shear component, which the demo's principal-axes stress paths leave at zero)."""
+    c, s = np.cos(omega), np.sin(omega)
+    xx, yy, zz, xy = v[:, 0], v[:, 1], v[:, 2], v[:, 3] / np.sqrt(2.0)
+    out = np.empty_like(v)
+    out[:, 0] = c * c * xx + s * s * yy - 2.0 * s * c * xy
+    out[:, 1] = s * s * xx + c * c * yy + 2.0 * s * c * xy
+    out[:, 2] = zz
+    out[:, 3] = np.sqrt(2.0) * (s * c * (xx - yy) + (c * c - s * s) * xy)
+    return out
+
+
+def mc_path_increments(theta: np.ndarray, R) -> np.ndarray:
+    """Stress-path increment in principal Haigh-Westergaard coordinates, demo_mc:868-871."""
+    d = np.zeros((theta.size, 4))
+    d[:, 0] = (R / np.sqrt(2)) * (np.cos(theta) + np.sin(theta) / np.sqrt(3))
+    d[:, 1] = (R / np.sqrt(2)) * (-2 * np.sin(theta) / np.sqrt(3))
+    d[:, 2] = (R / np.sqrt(2)) * (np.sin(theta) / np.sqrt(3) - np.cos(theta))
+    return d
+
+
+def mc_batch(n: int, seed: int = 0, stepper=None, max_level: int = 16, rotate: bool = True):
+    """The demo's yield-surface tracing family (demo_mc:853-930), randomised:
+    Lode angle theta ~ U(-pi/6+1e-5, pi/6-1e-5), path radius R ~ U(0.1, 0.7), hydrostatic offset
+    p ~ U(-1, 1), load level k ~ U{0..max_level} (16 -> ~34 % plastic points, 2-5 Newton iterations).  deps = S_elas @ dsigma_path (:903); sigma_n is the
+    stress reached after k increments of the path, each followed by the re-projection onto the
+    deviatoric plane of :921-923.
+
+    `stepper(deps (m,4), sigma_n (m,4)) -> sigma (m,4)` performs one stress update; the tests pass
+    the CPU oracle, bench.py passes the GPU kernel itself.  Returns deps (n,4), sigma_n (n,4)."""
+    if stepper is None:
+        raise ValueError("mc_batch needs a `stepper` (stress update) to walk the stress paths")
+    rng = np.random.default_rng(seed)
+    eps = 1e-5
+    theta = rng.uniform(-np.pi / 6 + eps, np.pi / 6 - eps, n)
+    R = rng.uniform(0.1, 0.7, n)
+    p = rng.uniform(-1.0, 1.0, n)
+    level = rng.integers(0, max_level + 1, n)
+    omega = rng.uniform(0.0, np.pi, n) if rotate else np.zeros(n)
+    dsig = mc_path_increments(theta, R)
+    deps = dsig @ mc_compliance().T
+    sigma_n = np.zeros((n, 4))
+    sigma_n[:, :3] = p[:, None]
+    tr = np.array([1.0, 1.0, 1.0, 0.0])
+    for k in range(max_level):
+        active = level > k
+        if not active.any():
+            break
+        sig = np.asarray(stepper(deps[active], sigma_n[active])).reshape(-1, 4)
+        dpp = sig @ tr / 3.0 - p[active]
+        sigma_n[active] = sig - np.outer(dpp, tr)
+    if rotate:
+        deps, sigma_n = mc_rotate(deps, omega), mc_rotate(sigma_n, omega)
+    return np.ascontiguousarray(deps), np.ascontiguousarray(sigma_n)
+
+
+def mc_demo_path(n_angles: int = 50, n_loads: int = 9, R: float = 0.7, p: float = 0.1, stepper=None):
+    """The demo's tracing driver itself (demo_mc:853-930): returns the (deps, sigma_n) pairs of every
+    (load level, angle), shapes (n_loads*n_angles, 4)."""
+    eps = 1e-5
+    theta = np.linspace(-np.pi / 6 + eps, np.pi / 6 - eps, n_angles)
+    dsig = mc_path_increments(theta, R)
+    deps = dsig @ mc_compliance().T
+    sigma_n = np.zeros((n_angles, 4))
+    sigma_n[:, :3] = p
+    tr = np.array([1.0, 1.0, 1.0, 0.0])
+    D, S = [], []
+    for _ in range(n_loads):
+        D.append(deps.copy())
+        S.append(sigma_n.copy())
+        sig = np.asarray(stepper(deps, sigma_n)).reshape(-1, 4)
+        dpp = sig @ tr / 3.0 - p
+        sigma_n = sig - np.outer(dpp, tr)
+    return np.concatenate(D), np.concatenate(S)

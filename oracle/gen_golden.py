@@ -49,6 +49,58 @@ def gen_heat():
     print("heat golden written")
 
 
+_MC_NS = None
+
+
+def _mc_init():
+    global _MC_NS
+    import torch
+
+    torch.set_num_threads(1)
+    _MC_NS = ref_exec.load_mohr_coulomb()
+
+
+def _mc_one(args):
+    """One quadrature point through the reference's own `dsigma_ddeps` (demo_mc:555)."""
+    import torch
+
+    de, sn = args
+    Ct, aux = _MC_NS["dsigma_ddeps"](torch.as_tensor(de), torch.as_tensor(sn))
+    sig, niter, yielding, norm_res, dlambda = aux
+    return (Ct.numpy(), sig.numpy(), int(niter), float(yielding), float(norm_res), float(dlambda))
+
+
+def _mc_run(deps, sigma_n, procs=8):
+    import multiprocessing as mp
+
+    with mp.get_context("spawn").Pool(procs, initializer=_mc_init) as pool:
+        res = pool.map(_mc_one, [(deps[i], sigma_n[i]) for i in range(deps.shape[0])], chunksize=1)
+    return {
+        "C_tang": np.stack([r[0] for r in res]), "sigma": np.stack([r[1] for r in res]),
+        "niter": np.array([r[2] for r in res], dtype=np.int32), "yielding": np.array([r[3] for r in res]),
+        "norm_res": np.array([r[4] for r in res]), "dlambda": np.array([r[5] for r in res]),
+    }
+
+
+def gen_mc():
+    """Mohr-Coulomb goldens: the reference's source (demo_mc:282-555) executed over the torch.func
+    JAX shim.  ~30 s per plastic point -> small sets.  The stress paths (sigma_n) are walked with the
+    C++ oracle's stress update; every golden point is then evaluated by the reference itself."""
+    from . import constitutive as oc
+    from . import native
+
+    prm = oc.MohrCoulombParams()
+    step = lambda d, s: native.mc_stress(d, s, prm, parallel=True)[0]  # noqa: E731
+    d, s = inputs.mc_demo_path(10, 9, stepper=step)
+    out = _mc_run(d, s)
+    np.savez_compressed(os.path.join(GOLDEN, "mc_path_10x9.npz"), deps=d, sigma_n=s, **out)
+    print("mc path golden written; niter histogram", np.unique(out["niter"], return_counts=True))
+    d, s = inputs.mc_batch(96, seed=0, stepper=step)
+    out = _mc_run(d, s)
+    np.savez_compressed(os.path.join(GOLDEN, "mc_rand_seed0_n96.npz"), deps=d, sigma_n=s, **out)
+    print("mc random golden written; niter histogram", np.unique(out["niter"], return_counts=True))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     what = sys.argv[1:] or ["vm", "heat"]

@@ -79,3 +79,70 @@ def test_vm_oracle_against_live_reference():
     _close(Ct, rC.reshape(-1, 4, 4))
     _close(sig, rs.reshape(-1, 4))
     _close(dp, rdp.reshape(-1))
+
+
+# ----------------------------------------------------------------------------- Mohr-Coulomb
+MC_RTOL = 1e-10  # local-Newton models: north_star tolerance
+MC_PRM = oc.MohrCoulombParams()
+
+
+def _mc_check(o, g, rtol=MC_RTOL):
+    assert np.array_equal(o["niter"], g["niter"])
+    assert np.array_equal(o["yielding"] > 0, g["yielding"] > 0)  # plastic flags bit-exact
+    _close(o["C_tang"], g["C_tang"], rtol)
+    _close(o["sigma"], g["sigma"], rtol)
+    _close(o["dlambda"], g["dlambda"], rtol)
+    _close(o["yielding"], g["yielding"], rtol)
+    # ||res|| at exit is a converged residual (<= 1e-8 ||res0||): rounding-level quantity, absolute check
+    np.testing.assert_allclose(o["norm_res"], g["norm_res"], rtol=0, atol=1e-10 * np.abs(g["sigma"]).max())
+
+
+@pytest.mark.parametrize("name", ["mc_path_10x9.npz", "mc_rand_seed0_n96.npz"])
+def test_mc_oracle_matches_reference_golden(golden_dir, name):
+    """The C++ dual-number restatement against the reference's own source (demo_mc:282-555) executed
+    over the torch.func shim of the JAX API (oracle/gen_golden.py gen_mc)."""
+    g = np.load(os.path.join(golden_dir, name))
+    o = native.mc_return_mapping(g["deps"], g["sigma_n"], MC_PRM)
+    _mc_check(o, g)
+    el = g["yielding"] <= 0
+    C = oc.elastic_stiffness(MC_PRM.lmbda, MC_PRM.mu)
+    assert np.array_equal(o["C_tang"][el], np.broadcast_to(C, (el.sum(), 4, 4)))  # demo_mc:442-443
+    assert np.all(o["niter"][el] == 1) and np.all(o["dlambda"][el] == 0.0)
+    # returned plastic stresses lie on the yield surface: |f| <= tol * ||res0||
+    f = native.mc_yield(o["sigma"][~el], MC_PRM)
+    assert np.abs(f).max() < 1e-6
+
+
+def test_mc_demo_tracing_histogram():
+    """the demo's 50 x 9 tracing driver (demo_mc:853-930) gives 276 elastic points
+    and 99/57/15/3 plastic points with 2/3/4/5 local Newton iterations."""
+    step = lambda d, s: native.mc_stress(d, s, MC_PRM, parallel=True)[0]  # noqa: E731
+    d, s = inputs.mc_demo_path(50, 9, stepper=step)
+    o = native.mc_return_mapping(d, s, MC_PRM, parallel=True)
+    it, cnt = np.unique(o["niter"], return_counts=True)
+    assert dict(zip(it.tolist(), cnt.tolist())) == {1: 276, 2: 99, 3: 57, 4: 15, 5: 3}
+
+
+def test_mc_synthetic_batch_is_isotropic():
+    """The in-plane rotation that populates the shear component must not change invariants."""
+    step = lambda d, s: native.mc_stress(d, s, MC_PRM, parallel=True)[0]  # noqa: E731
+    d0, s0 = inputs.mc_batch(500, 1, step, rotate=False)
+    d1, s1 = inputs.mc_batch(500, 1, step, rotate=True)
+    o0, o1 = native.mc_return_mapping(d0, s0, MC_PRM), native.mc_return_mapping(d1, s1, MC_PRM)
+    assert np.array_equal(o0["niter"], o1["niter"])
+    np.testing.assert_allclose(o0["yielding"], o1["yielding"], atol=1e-12)
+    assert np.abs(d1[:, 3]).max() > 0
+
+
+@pytest.mark.skipif(not ref_exec.reference_available(), reason="/root/reference absent (GPU box)")
+def test_mc_oracle_against_live_reference():
+    import torch
+
+    ns = ref_exec.load_mohr_coulomb()
+    de = np.array([1.1e-4, -2.3e-4, 0.0, 0.7e-4])
+    sn = np.array([-1.0, -1.2, -0.9, 0.1])
+    Ct, aux = ns["dsigma_ddeps"](torch.as_tensor(de), torch.as_tensor(sn))
+    o = native.mc_return_mapping(de[None], sn[None], MC_PRM)
+    assert int(aux[1]) == int(o["niter"][0])
+    _close(o["C_tang"][0], Ct.numpy(), MC_RTOL)
+    _close(o["sigma"][0], aux[0].numpy(), MC_RTOL)
