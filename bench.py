@@ -37,7 +37,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BYTES_PER_QP = {"vm": 240, "heat": 88}
+BYTES_PER_QP = {"vm": 240, "heat": 88, "mc": 252}
 METRIC = "quadrature points per second (stress + consistent tangent + internal state)"
 
 
@@ -113,6 +113,11 @@ def cpu_port_rate(model: str, sample_n: int, min_seconds: float, parallel: bool 
         deps, sigma_n, p = inputs.vm_batch(sample_n, seed=0)
         prm = oc.VonMisesParams()
         fn = lambda: native.vm_return_mapping(deps, sigma_n, p, prm, parallel=parallel)  # noqa: E731
+    elif model == "mc":
+        mprm = oc.MohrCoulombParams()
+        deps, sigma_n = inputs.mc_batch(sample_n, seed=0,
+                                        stepper=lambda d, s: native.mc_stress(d, s, mprm, parallel=True)[0])
+        fn = lambda: native.mc_return_mapping(deps, sigma_n, mprm, parallel=parallel)  # noqa: E731
     else:
         T, sigma = inputs.heat_batch(sample_n, seed=0)
 
@@ -142,24 +147,45 @@ def run_reference_arm(args):
 
     native.build()
     cores = native.num_threads()
-    deps, sigma_n, p = inputs.vm_batch(sample, seed=0)
-    prm = oc.VonMisesParams()
+    if args.model == "mc":
+        sample = min(sample, 200_000)
+        mprm = oc.MohrCoulombParams()
+        deps, sigma_n = inputs.mc_batch(sample, seed=0,
+                                        stepper=lambda d, s: native.mc_stress(d, s, mprm, parallel=True)[0])
+        ref_step = lambda: native.mc_return_mapping(deps, sigma_n, mprm, parallel=True)  # noqa: E731
+        what = ("Mohr-Coulomb return mapping + AD-through-the-loop tangent (demo_plasticity_mohr_coulomb.py:474-555), "
+                "demo stress-path family, ~34% plastic points")
+        port = ("C++ nested-dual-number restatement of the reference's JAX program (JAX is not installable "
+                "offline), OpenMP")
+    elif args.model == "heat":
+        T, sig = inputs.heat_batch(sample, seed=0)
+
+        def ref_step():
+            for w in ("q", "dqdT", "dqdsigma"):
+                native.heat(w, T, sig, parallel=True)
+        what = "nonlinear heat flux q, dq/dT, dq/dsigma (demo_nonlinear_heat_equation_part2.py:219-261)"
+        port = "C restatement of the reference's NumPy functions, OpenMP"
+    else:
+        deps, sigma_n, p = inputs.vm_batch(sample, seed=0)
+        prm = oc.VonMisesParams()
+        ref_step = lambda: native.vm_return_mapping(deps, sigma_n, p, prm, parallel=True)  # noqa: E731
+        what = ("von Mises return mapping (demo_plasticity_von_mises.py:298-332), plane-strain Mandel 4-vectors, "
+                "~53% plastic points")
+        port = "C restatement of the reference's Numba kernel (the reference kernel itself is serial @numba.njit), OpenMP"
     for _ in range(args.warmup):
-        native.vm_return_mapping(deps, sigma_n, p, prm, parallel=True)
+        ref_step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        native.vm_return_mapping(deps, sigma_n, p, prm, parallel=True)
+        ref_step()
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "QP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "von Mises return mapping (demo_plasticity_von_mises.py:298-332), plane-strain "
-                               "Mandel 4-vectors, ~53% plastic points", "qp_per_step": sample},
+        "config": {"workload": what, "qp_per_step": sample},
         "cpu_baseline": {"value": value, "unit": "QP/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} QPs per step; C restatement of the reference's Numba kernel "
-                                   f"(the reference kernel itself is serial @numba.njit), OpenMP over {cores} threads"},
+                         "sample": f"{sample} QPs per step; {port} over {cores} threads"},
         "e2e": {"value": value, "unit": "QP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -167,7 +193,29 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------- GPU arm
+WORKLOADS = {
+    "vm": "von Mises return mapping, plane-strain Mandel 4-vectors (BASELINE configs[1] callable at configs[4] "
+          "batch size)",
+    "heat": "nonlinear heat flux q, dq/dT, dq/dsigma fused (BASELINE configs[0] callables at configs[4] batch size)",
+    "mc": "Mohr-Coulomb return mapping with apex smoothing, local Newton + tangent through the iterations "
+          "(BASELINE configs[2] callable at configs[4] batch size), demo stress-path family",
+}
+
+
+def _tile_to_device(ctx, dst, tile: np.ndarray, n: int, width: int, itemsize: int = 8):
+    """Repeat a seeded host tile into a device array of n rows."""
+    tile_n = tile.shape[0]
+    d_tile = ctx.to_device(np.ascontiguousarray(tile).reshape(-1))
+    for r in range(0, n, tile_n):
+        m = min(tile_n, n - r)
+        ctx.copy(dst.ptr + r * width * itemsize, d_tile, m * width * itemsize)
+    ctx.sync()
+    d_tile.free()
+
+
 def run_gpu_arm(args):
+    import ctypes as C
+
     import dolfinx_external_operator_b200 as eo
     from dolfinx_external_operator_b200 import synthetic as inputs
 
@@ -189,56 +237,75 @@ def run_gpu_arm(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        import torch
+
+        t = torch.tensor([x], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     ctx = eo.Context(local_rank)
     n = int(args.n)
     model = args.model
     K, W = args.steps, args.warmup
-
-    # ---- synthetic inputs: a seeded tile (seed = rank) repeated to n points, built on device
     tile_n = min(n, 1 << 22)
-    reps = (n + tile_n - 1) // tile_n
+    extra_cfg = {}
 
-    def fill(dst: eo.DeviceArray, tile: np.ndarray, width: int):
-        d_tile = ctx.to_device(tile.reshape(-1))
-        for r in range(reps):
-            m = min(tile_n, n - r * tile_n)
-            ctx.copy(dst.ptr + r * tile_n * width * 8, d_tile, m * width * 8)
-        ctx.sync()
-        d_tile.free()
-
+    # ---- synthetic inputs: a seeded tile (seed = rank) repeated to n points, resident in HBM
     if model == "vm":
         vm = eo.VonMises(n_qp=n, ctx=ctx, state_layout=args.state_layout)
         deps_t, sn_t, p_t = inputs.vm_batch(tile_n, seed=rank)
         d_deps = ctx.empty((n * 4,))
-        fill(d_deps, deps_t, 4)
+        _tile_to_device(ctx, d_deps, deps_t, n, 4)
         if args.state_layout == "soa":
             for c in range(4):
                 col = ctx.to_device(np.ascontiguousarray(sn_t[:, c]))
-                for r in range(reps):
-                    m = min(tile_n, n - r * tile_n)
-                    ctx.copy(vm.sigma_n_dev.ptr + (c * n + r * tile_n) * 8, col, m * 8)
+                for r in range(0, n, tile_n):
+                    m = min(tile_n, n - r)
+                    ctx.copy(vm.sigma_n_dev.ptr + (c * n + r) * 8, col, m * 8)
                 ctx.sync()
                 col.free()
         else:
-            fill(vm.sigma_n_dev, sn_t, 4)
-        fill(vm.p_dev, p_t, 1)
+            _tile_to_device(ctx, vm.sigma_n_dev, sn_t, n, 4)
+        _tile_to_device(ctx, vm.p_dev, p_t, n, 1)
         d_Ct = ctx.empty((n * 16,))
 
         def step():
             vm.eval_device(d_deps, d_Ct)
+    elif model == "mc":
+        from dolfinx_external_operator_b200._lib import McParams
+
+        mc = eo.MohrCoulomb(ctx=ctx, history=None)
+        tile_n = min(n, 1 << 20)
+        # the stress paths are walked with the GPU kernel itself as the stress update
+        deps_t, sn_t = inputs.mc_batch(tile_n, seed=rank, stepper=mc.stress_update)
+        d_deps, d_sn = ctx.empty((n * 4,)), ctx.empty((n * 4,))
+        _tile_to_device(ctx, d_deps, deps_t, n, 4)
+        _tile_to_device(ctx, d_sn, sn_t, n, 4)
+        d_Ct, d_sig = ctx.empty((n * 16,)), ctx.empty((n * 4,))
+        d_it = ctx.empty((n,), np.int32)
+        d_yl, d_nr, d_dl = ctx.empty((n,)), ctx.empty((n,)), ctx.empty((n,))
+        prm = McParams(mc.E, mc.nu, mc.c, mc.phi, mc.psi, mc.theta_T, mc.a, mc.tol, mc.Nitermax)
+        scheme = {"queue": 0, "simple": 1}[args.mc_scheme]
+        extra_cfg["mc_scheme"] = args.mc_scheme
+
+        def step():
+            ctx.check(ctx.lib.eo_mc_eval_scheme(ctx.handle, C.byref(prm), d_deps.ptr, d_sn.ptr, d_Ct.ptr, d_sig.ptr,
+                                                d_it.ptr, d_yl.ptr, d_nr.ptr, d_dl.ptr, n, scheme))
     else:
         T_t, s_t = inputs.heat_batch(tile_n, seed=rank)
         d_T, d_s = ctx.empty((n,)), ctx.empty((n * 2,))
-        fill(d_T, T_t, 1)
-        fill(d_s, s_t, 2)
+        _tile_to_device(ctx, d_T, T_t, n, 1)
+        _tile_to_device(ctx, d_s, s_t, n, 2)
         d_q, d_dT, d_ds = ctx.empty((n * 2,)), ctx.empty((n * 2,)), ctx.empty((n * 4,))
 
         def step():
             ctx.check(ctx.lib.eo_heat_eval(ctx.handle, 1.0, 1.0, d_T.ptr, d_s.ptr, None, None, d_q.ptr, d_dT.ptr,
                                            d_ds.ptr, n))
 
-    def step_with_collective():
-        step()
+    def collective():
         if dist is not None:
             from dolfinx_external_operator_b200.parallel import allreduce_stats_device
 
@@ -246,7 +313,8 @@ def run_gpu_arm(args):
 
     # ---- device-resident timing
     for _ in range(W):
-        step_with_collective()
+        step()
+        collective()
     ctx.sync()
     ctx.stats_reset()
     ev = [ctx.event() for _ in range(2 * K + 2)]
@@ -260,43 +328,39 @@ def run_gpu_arm(args):
         ctx.record(ev[2 + 2 * k])
         step()
         ctx.record(ev[3 + 2 * k])
-        if dist is not None:
-            from dolfinx_external_operator_b200.parallel import allreduce_stats_device
-
-            allreduce_stats_device(ctx)
+        collective()
     ctx.record(ev[1])
     ctx.sync()
     barrier()
     clocks = sampler.stop()
     launches = ctx.launch_count - launches0
-    total_ms = ctx.elapsed_ms(ev[0], ev[1])
+    total_ms = max_over_ranks(ctx.elapsed_ms(ev[0], ev[1]))
     kernel_ms = [ctx.elapsed_ms(ev[2 + 2 * k], ev[3 + 2 * k]) for k in range(K)]
-    stats = ctx.stats()
-
-    if dist is not None:
-        import torch
-
-        t = torch.tensor([total_ms], device=f"cuda:{local_rank}", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+    stats = ctx.stats()  # rank-local when world == 1, all-reduced K times otherwise (only ratios are used)
     value = world * n * K / (total_ms * 1e-3)
 
     # ---- end-to-end through the public callable (host buffers)
     e2e = None
-    if model == "vm" and args.e2e_n > 0:
+    if model in ("vm", "mc") and args.e2e_n > 0:
         ne = int(args.e2e_n)
-        vm_e = eo.VonMises(n_qp=ne, ctx=ctx)
         deps_h = ctx.pinned_empty((ne, 1, 4))  # (n_cells, n_points, 4), the operand shape of demo_vm:344
-        deps_t2, sn_t2, p_t2 = inputs.vm_batch(min(ne, 1 << 22), seed=rank)
         flat = deps_h.reshape(-1, 4)
+        if model == "vm":
+            m_e = eo.VonMises(n_qp=ne, ctx=ctx)
+            deps_t2, sn_t2, p_t2 = inputs.vm_batch(min(ne, 1 << 22), seed=rank)
+            m_e.set_history(np.resize(sn_t2, (ne, 4)), np.resize(p_t2, ne))
+            d2h = 168 * ne
+            api = "VonMises((1,))(deps) == external_function(derivatives)(*operands), history resident in HBM"
+        else:
+            m_e = eo.MohrCoulomb(n_qp=ne, ctx=ctx)
+            deps_t2, sn_t2 = deps_t, sn_t
+            m_e.set_history(np.resize(sn_t2, (ne, 4)))
+            d2h = (160 + 28) * ne
+            api = "MohrCoulomb((1,))(deps) == external_function(derivatives)(*operands), history resident in HBM"
         for r in range(0, ne, deps_t2.shape[0]):
             m = min(deps_t2.shape[0], ne - r)
             flat[r:r + m] = deps_t2[:m]
-        sn_full = np.resize(sn_t2, (ne, 4))
-        p_full = np.resize(p_t2, ne)
-        vm_e.set_history(sn_full, p_full)
-        del sn_full, p_full
-        call = vm_e((1,))
+        call = m_e((1,))
         Ke = max(2, min(K, 5))
         for _ in range(2):
             out = call(deps_h)
@@ -304,19 +368,12 @@ def run_gpu_arm(args):
         t0 = time.perf_counter()
         checksum = 0.0
         for _ in range(Ke):
-            Ct_h, sig_h, dp_h = call(deps_h)  # H2D + kernel + D2H, synchronous on return
-            checksum += float(dp_h[0])
+            out = call(deps_h)  # H2D + kernel + D2H, synchronous on return
+            checksum += float(out[1][0])
         ctx.sync()
-        dt = time.perf_counter() - t0
-        if dist is not None:
-            import torch
-
-            t = torch.tensor([dt], device=f"cuda:{local_rank}", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": world * ne * Ke / dt, "unit": "QP/s", "h2d_bytes_per_step": 32 * ne,
-               "d2h_bytes_per_step": 168 * ne, "qp_per_step_per_gpu": ne, "steps": Ke,
-               "api": "VonMises((1,))(deps) == external_function(derivatives)(*operands), history resident in HBM"}
+               "d2h_bytes_per_step": d2h, "qp_per_step_per_gpu": ne, "steps": Ke, "api": api}
 
     if rank != 0:
         if dist is not None:
@@ -324,46 +381,63 @@ def run_gpu_arm(args):
         return
 
     # ---- roofline for the dominant kernel (the only kernel in a step)
-    peak, peak_src = _measured_peaks()
     k_ms = float(np.mean(kernel_ms))
-    achieved = BYTES_PER_QP[model] * n / (k_ms * 1e-3) / 1e9
-    traffic = None
+    tj = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as fh:
             tj = json.load(fh).get(model)
-        if tj and tj.get("n") == n:
-            traffic = tj.get("dram_bytes_per_launch")
+    traffic = tj.get("dram_bytes_per_launch") if (tj and tj.get("n") == n) else None
+    hbm_peak, hbm_src = _measured_peaks()
+    hbm_achieved = BYTES_PER_QP[model] * n / (k_ms * 1e-3) / 1e9
+    if model == "mc":
+        # FP64-pipe bound: flops per QP counted by ncu (DFMA = 2, DADD/DMUL = 1) for this input family,
+        # peak = DFMA micro-benchmark measured now on this GPU
+        fp64_peak = ctx.fp64_peak_tflops()
+        flops_per_qp = tj.get("fp64_flops_per_qp") if tj else None
+        ach = flops_per_qp * n / (k_ms * 1e-3) / 1e12 if flops_per_qp else None
+        roofline = {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": (ach / fp64_peak) if ach else None, "traffic": traffic,
+                    "peak_source": "measured now: eo_fp64_peak DFMA micro-benchmark (8 chains/thread)",
+                    "fp64_flops_per_qp": flops_per_qp, "kernel_ms": k_ms,
+                    "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                            "bytes_per_qp": BYTES_PER_QP[model]}}
+    else:
+        roofline = {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": hbm_achieved / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
+                    "bytes_per_qp": BYTES_PER_QP[model], "kernel_ms": k_ms}
 
     # ---- CPU baseline on this box's host cores (bounded sample)
     cpu = None
     if args.cpu_seconds > 0:
-        rate, cores, passes = cpu_port_rate(model, int(args.cpu_sample), args.cpu_seconds, parallel=True)
-        rate1, _, _ = cpu_port_rate(model, int(args.cpu_sample) // 4, min(3.0, args.cpu_seconds), parallel=False)
+        sample = int(args.cpu_sample) if model != "mc" else min(int(args.cpu_sample), 200_000)
+        rate, cores, passes = cpu_port_rate(model, sample, args.cpu_seconds, parallel=True)
+        rate1, _, _ = cpu_port_rate(model, sample // 4, min(3.0, args.cpu_seconds), parallel=False)
+        what = {"vm": "C restatement of the reference's Numba kernel (serial in the reference)",
+                "heat": "C restatement of the reference's NumPy functions",
+                "mc": "C++ nested-dual-number restatement of the reference's JAX program (JAX not installable offline)"}
         cpu = {"value": rate, "unit": "QP/s", "cores": cores, "kind": "port",
-               "sample": f"{int(args.cpu_sample)} QPs x {passes} passes (best pass); C restatement of the reference "
-                         f"kernel, OpenMP; single-thread rate {rate1:.3e} QP/s (the reference's Numba kernel is serial)",
+               "sample": f"{sample} QPs x {passes} passes (best pass); {what[model]}, OpenMP; single-thread rate "
+                         f"{rate1:.3e} QP/s",
                "single_thread_value": rate1}
 
+    hist = stats["niter_hist"]
+    cfg = {
+        "workload": WORKLOADS[model], "qp_per_gpu": n, "state_layout": args.state_layout,
+        "plastic_fraction": stats["n_plastic"] / max(stats["n_points"], 1),
+        "l2": f"inputs+outputs {BYTES_PER_QP[model] * n / 1e9:.1f} GB per step >> 126 MB L2 (no flush needed)",
+        "partition": "contiguous block of QPs per rank, no halo; one stats all-reduce per step when n_gpus > 1",
+    }
+    if model == "mc":
+        tot = max(int(hist.sum()), 1)
+        cfg["niter_histogram"] = {int(i): float(hist[i]) / tot for i in np.nonzero(hist)[0]}
+        cfg["n_nonconverged"] = stats["n_nonconverged"]
+    cfg.update(extra_cfg)
     line = {
         "metric": METRIC, "value": value, "unit": "QP/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {
-            "workload": ("von Mises return mapping, plane-strain Mandel 4-vectors (BASELINE configs[1] callable at "
-                         "configs[4] batch size)" if model == "vm" else "nonlinear heat flux q, dq/dT, dq/dsigma fused"),
-            "qp_per_gpu": n, "state_layout": args.state_layout, "plastic_fraction": (
-                stats["n_plastic"] / max(stats["n_points"], 1)),
-            "l2": f"inputs+outputs {BYTES_PER_QP[model] * n / 1e9:.1f} GB per step >> 126 MB L2 (no flush needed)",
-            "partition": "contiguous block of QPs per rank, no halo; one stats all-reduce per step when n_gpus > 1",
-        },
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "bytes_per_qp": BYTES_PER_QP[model],
-                     "kernel_ms": k_ms},
-        "cpu_baseline": cpu,
-        "e2e": e2e,
-        "gpu_launches": int(launches),
-        "clocks": clocks,
+        "dtype": "f64", "data": "synthetic", "config": cfg, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -376,7 +450,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--model", default="vm", choices=["vm", "heat"])
+    ap.add_argument("--model", default="vm", choices=["vm", "heat", "mc"])
+    ap.add_argument("--mc-scheme", default="queue", choices=["queue", "simple"])
     ap.add_argument("--n", type=float, default=1e8, help="quadrature points per GPU (device-resident leg)")
     ap.add_argument("--e2e-n", type=float, default=1.5e7, help="quadrature points per GPU for the end-to-end leg")
     ap.add_argument("--state-layout", default="aos", choices=["aos", "soa"])

@@ -37,6 +37,11 @@ class VmParams(C.Structure):
     _fields_ = [("lmbda", C.c_double), ("mu", C.c_double), ("H", C.c_double), ("sigma_0", C.c_double)]
 
 
+class McParams(C.Structure):
+    _fields_ = [("E", C.c_double), ("nu", C.c_double), ("c", C.c_double), ("phi", C.c_double), ("psi", C.c_double),
+                ("theta_T", C.c_double), ("a", C.c_double), ("tol", C.c_double), ("Nitermax", C.c_int32)]
+
+
 class Stats(C.Structure):
     _fields_ = [
         ("n_points", C.c_int64),
@@ -80,6 +85,8 @@ PROTOTYPES = {
     "eo_event_record": (C.c_int, [_vp, _vp]),
     "eo_event_elapsed_ms": (C.c_int, [_vp, _vp, _vp, C.POINTER(C.c_float)]),
     "eo_flush_l2": (C.c_int, [_vp, C.c_size_t]),
+    "eo_debug_counters": (C.c_int, [_vp, _vp]),
+    "eo_fp64_peak": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double)]),
     "eo_stats_reset": (C.c_int, [_vp]),
     "eo_stats_read": (C.c_int, [_vp, C.POINTER(Stats)]),
     "eo_stats_device_ptr": (_vp, [_vp]),
@@ -87,6 +94,8 @@ PROTOTYPES = {
     "eo_vm_eval_resident": (C.c_int, [_vp, C.POINTER(VmParams), _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_int]),
     "eo_commit_history": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, C.c_int]),
     "eo_heat_eval": (C.c_int, [_vp, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
+    "eo_mc_eval": (C.c_int, [_vp, C.POINTER(McParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
+    "eo_mc_eval_scheme": (C.c_int, [_vp, C.POINTER(McParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_int]),
 }
 
 _lib = None

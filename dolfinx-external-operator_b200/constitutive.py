@@ -26,7 +26,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import EO_LAYOUT_AOS, EO_LAYOUT_SOA, VmParams
+from ._lib import EO_LAYOUT_AOS, EO_LAYOUT_SOA, McParams, VmParams
 from .context import Context, DeviceArray, _ptr, default_context
 
 
@@ -206,6 +206,154 @@ class VonMises(_ModelBase):
         c.check(c.lib.eo_vm_eval_resident(c.handle, C.byref(self._prm), deps.ptr, self.sigma_n_dev.ptr,
                                           self.p_dev.ptr, C_tang.ptr, self.sigma_dev.ptr, self.dp_dev.ptr, n,
                                           self.state_layout))
+
+
+# ---------------------------------------------------------------------------------------
+class MohrCoulomb(_ModelBase):
+    """Non-associative Mohr-Coulomb plasticity with Abbo-Sloan rounding and apex smoothing, per-point
+    local Newton solve, tangent = derivative of the Newton iteration (what `jax.jacfwd` through
+    `lax.while_loop` returns).
+
+    replaces: `return_mapping`, `dsigma_ddeps`, `dsigma_ddeps_vec`, `C_tang_impl`, `sigma_external`,
+    doc/demo/demo_plasticity_mohr_coulomb.py:474-533, :555, :574-620.  Parameters as :110-116, :469.
+
+    The callable returns `(C_tang.reshape(-1), sigma.reshape(-1))` exactly like :593.  The aux state of
+    :533 is available afterwards as `.niter`, `.yielding`, `.norm_res`, `.dlambda`, and the per-call
+    summary the reference prints (:584-591) as `.summary()` (computed on the device, one small read).
+    """
+
+    def __init__(
+        self,
+        E: float = 6778.0,
+        nu: float = 0.25,
+        c: float = 3.45,
+        phi: float = 30 * np.pi / 180,
+        psi: float = 30 * np.pi / 180,
+        theta_T: float = 26 * np.pi / 180,
+        a: float | None = None,
+        tol: float = 1e-8,
+        Nitermax: int = 200,
+        *,
+        history="resident",
+        n_qp: int | None = None,
+        aux: bool = True,
+        verbose: bool = False,
+        ctx: Context | None = None,
+    ):
+        super().__init__(ctx)
+        a = 0.26 * c / np.tan(phi) if a is None else a  # demo_mc:116
+        self.E, self.nu, self.c, self.phi, self.psi, self.theta_T, self.a = E, nu, c, phi, psi, theta_T, a
+        self.tol, self.Nitermax = tol, int(Nitermax)
+        self._prm = McParams(E, nu, c, phi, psi, theta_T, a, tol, int(Nitermax))
+        self._resident = isinstance(history, str) and history == "resident"
+        self._history_objs = None if self._resident else (history,)  # sigma_n with .x.array (demo_mc:579)
+        self.want_aux = aux
+        self.verbose = verbose
+        self.n_qp = None
+        self.sigma_n_dev = self.sigma_dev = None
+        self.niter = self.yielding = self.norm_res = self.dlambda = None
+        self._last_stats = None
+        if self._resident and n_qp is not None:
+            self._alloc_state(int(n_qp))
+
+    def _alloc_state(self, n: int):
+        self.n_qp = n
+        self.sigma_n_dev = self.ctx.zeros((n * 4,))
+        self.sigma_dev = self.ctx.zeros((n * 4,))
+
+    def set_history(self, sigma_n: np.ndarray):
+        sigma_n = np.ascontiguousarray(sigma_n, dtype=np.float64).reshape(-1)
+        n = sigma_n.size // 4
+        if self.n_qp != n:
+            self._alloc_state(n)
+        self.sigma_n_dev.copy_from(sigma_n)
+
+    def get_history(self) -> np.ndarray:
+        return self.sigma_n_dev.to_host()
+
+    def commit(self):
+        """End of a converged load step: sigma_n <- sigma (demo_mc:728), on device."""
+        if not self._resident:
+            raise RuntimeError("commit() is for history='resident'; host history is updated by the caller")
+        c = self.ctx
+        c.check(c.lib.eo_commit_history(c.handle, self.sigma_n_dev.ptr, self.sigma_dev.ptr, None, None, self.n_qp, 4))
+
+    def __call__(self, derivatives):
+        if derivatives == (1,):
+            return self.C_tang_impl
+        raise NotImplementedError(f"No external function is defined for the requested derivative {derivatives}.")
+
+    def C_tang_impl(self, deps):
+        """deps (n_cells, n_pts, 4) -> (C_tang.reshape(-1), sigma.reshape(-1)), demo_mc:577-593."""
+        deps = _as_input(deps)
+        n = _n_points(deps) if len(deps.shape) > 1 else deps.shape[0] // 4
+        c = self.ctx
+        C_tang = self._out("C_tang", 16 * n)
+        sigma = self._out("sigma", 4 * n)
+        if self.want_aux:
+            self.niter = self._out_typed("niter", n, np.int32)
+            self.yielding, self.norm_res, self.dlambda = (self._out(k, n) for k in ("yielding", "norm_res", "dlambda"))
+            aux = [_ptr(self.niter), _ptr(self.yielding), _ptr(self.norm_res), _ptr(self.dlambda)]
+        else:
+            aux = [None, None, None, None]
+        c.stats_reset()
+        if self._resident:
+            if self.n_qp is None:
+                self._alloc_state(n)
+            if self.n_qp != n:
+                raise ValueError(f"operand has {n} quadrature points, the resident history {self.n_qp}")
+            c.check(c.lib.eo_mc_eval(c.handle, C.byref(self._prm), _ptr(deps), self.sigma_n_dev.ptr, _ptr(C_tang),
+                                     self.sigma_dev.ptr, *aux, n))
+            self.sigma_dev.to_host(sigma)
+        else:
+            sn = _as_input(self._history_objs[0].x.array)
+            if sn.size != 4 * n:
+                raise ValueError("history array does not match the operand's quadrature-point count")
+            c.check(c.lib.eo_mc_eval(c.handle, C.byref(self._prm), _ptr(deps), _ptr(sn), _ptr(C_tang), _ptr(sigma),
+                                     *aux, n))
+        c.sync()
+        self._last_stats = c.stats()
+        if self.verbose:
+            print(self.summary_text())
+        return C_tang, sigma
+
+    def _out_typed(self, name: str, size: int, dtype) -> np.ndarray:
+        a = self._host_out.get(name)
+        if a is None or a.size != size or a.dtype != np.dtype(dtype):
+            a = self.ctx.pinned_empty(size, dtype)
+            self._host_out[name] = a
+        return a
+
+    def summary(self) -> dict:
+        """The inner-Newton summary of demo_mc:584-591 for the last call (from the device statistics
+        record): unique iteration counts, their counts, max f(trial), max ||res||."""
+        st = self._last_stats
+        if st is None:
+            raise RuntimeError("no evaluation yet")
+        it = np.nonzero(st["niter_hist"])[0]
+        return {"unique_iters": it.astype(np.int32), "counts": st["niter_hist"][it], "max_f": st["f_max"],
+                "max_residual": st["res_max"], "n_plastic": st["n_plastic"], "n_nonconverged": st["n_nonconverged"],
+                "n_nonfinite": st["n_nonfinite"]}
+
+    def summary_text(self) -> str:
+        s = self.summary()
+        return ("\tInner Newton summary:\n"
+                f"\t\tUnique number of iterations: {s['unique_iters']}\n"
+                f"\t\tCounts of unique number of iterations: {s['counts']}\n"
+                f"\t\tMaximum f: {s['max_f']}\n"
+                f"\t\tMaximum residual: {s['max_residual']}")
+
+    def stress_update(self, deps: np.ndarray, sigma_n: np.ndarray) -> np.ndarray:
+        """One stress update with explicit history (host arrays); used to walk stress paths."""
+        deps = np.ascontiguousarray(deps, dtype=np.float64).reshape(-1, 4)
+        sigma_n = np.ascontiguousarray(sigma_n, dtype=np.float64).reshape(-1, 4)
+        n = deps.shape[0]
+        Ct, sig = np.empty(16 * n), np.empty((n, 4))
+        c = self.ctx
+        c.check(c.lib.eo_mc_eval(c.handle, C.byref(self._prm), _ptr(deps), _ptr(sigma_n), _ptr(Ct), _ptr(sig),
+                                 None, None, None, None, n))
+        c.sync()
+        return sig
 
 
 # ---------------------------------------------------------------------------------------

@@ -205,6 +205,12 @@ class Context:
     def flush_l2(self, nbytes: int = 256 << 20):
         self.check(self._lib.eo_flush_l2(self._h, int(nbytes)))
 
+    def fp64_peak_tflops(self, iters: int = 1 << 16) -> float:
+        """Measured FP64 DFMA throughput of this GPU (the roofline denominator of the Newton-bound kernels)."""
+        t = C.c_double()
+        self.check(self._lib.eo_fp64_peak(self._h, int(iters), C.byref(t)))
+        return float(t.value)
+
     # -------------------------------------------------------------- statistics
     def stats_reset(self):
         self.check(self._lib.eo_stats_reset(self._h))

@@ -30,6 +30,7 @@ struct eo_ctx {
   char* flush = nullptr;
   size_t flush_bytes = 0;
   eo_stats* stats = nullptr;  // device
+  unsigned int* work_ctr = nullptr;  // device: tile counter of the persistent kernels
   int64_t launches = 0;
   char err[512] = {0};
 };

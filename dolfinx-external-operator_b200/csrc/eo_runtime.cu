@@ -1,6 +1,8 @@
 // eo_runtime.cu - context, memory, events and statistics of libeo_b200.so.
 #include "eo_common.cuh"
 
+#include <cmath>
+
 char g_eo_create_error[512] = {0};
 
 int eo_fail(eo_ctx* ctx, int code, const char* fmt, ...) {
@@ -26,6 +28,16 @@ __global__ void eo_flush_kernel(float4* buf, size_t n4) {
   size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
   const size_t stride = size_t(gridDim.x) * blockDim.x;
   for (; i < n4; i += stride) buf[i] = make_float4(float(i), 0.f, 0.f, 0.f);
+}
+
+// FP64 roofline denominator: 8 independent DFMA chains per thread, no memory traffic
+__global__ void __launch_bounds__(256) eo_fp64_peak_kernel(double* out, int iters, double b, double c) {
+  double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, c), a1 = fma(a1, b, c), a2 = fma(a2, b, c), a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c), a5 = fma(a5, b, c), a6 = fma(a6, b, c), a7 = fma(a7, b, c);
+  }
+  out[blockIdx.x * size_t(blockDim.x) + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
 extern "C" {
@@ -78,7 +90,10 @@ int eo_create(int device, eo_ctx** out) {
   }
   EO_CREATE_CUDA(cudaMalloc(&ctx->stats, sizeof(eo_stats)));
   EO_CREATE_CUDA(cudaMemset(ctx->stats, 0, sizeof(eo_stats)));
+  EO_CREATE_CUDA(cudaMalloc(&ctx->work_ctr, 256));
+  EO_CREATE_CUDA(cudaMemset(ctx->work_ctr, 0, 256));
 #undef EO_CREATE_CUDA
+  eo_stats_reset(ctx);
   *out = ctx;
   return EO_OK;
 }
@@ -97,6 +112,7 @@ int eo_destroy(eo_ctx* ctx) {
   if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->flush) cudaFree(ctx->flush);
   if (ctx->stats) cudaFree(ctx->stats);
+  if (ctx->work_ctr) cudaFree(ctx->work_ctr);
   if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
   if (ctx->s_cmp) cudaStreamDestroy(ctx->s_cmp);
   if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
@@ -241,10 +257,45 @@ int eo_flush_l2(eo_ctx* ctx, size_t bytes) {
   return EO_OK;
 }
 
+int eo_debug_counters(eo_ctx* ctx, uint32_t* out) {
+  EO_REQUIRE(ctx, ctx && out, "eo_debug_counters: NULL argument");
+  EO_CUDA(ctx, cudaMemcpyAsync(out, ctx->work_ctr, 256, cudaMemcpyDeviceToHost, ctx->s_cmp));
+  EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_cmp));
+  return EO_OK;
+}
+
+int eo_fp64_peak(eo_ctx* ctx, int iters, double* tflops) {
+  EO_REQUIRE(ctx, ctx && tflops && iters > 0, "eo_fp64_peak: bad argument");
+  EO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int grid = ctx->sm_count * 8, block = 256;
+  double* out = nullptr;
+  EO_CUDA(ctx, cudaMalloc(&out, size_t(grid) * block * sizeof(double)));
+  cudaEvent_t e0, e1;
+  EO_CUDA(ctx, cudaEventCreate(&e0));
+  EO_CUDA(ctx, cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {  // first repetition is the warm-up
+    EO_CUDA(ctx, cudaEventRecord(e0, ctx->s_cmp));
+    eo_fp64_peak_kernel<<<grid, block, 0, ctx->s_cmp>>>(out, iters, 0.999999, 1e-6);
+    EO_CUDA(ctx, cudaEventRecord(e1, ctx->s_cmp));
+    EO_CUDA(ctx, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    EO_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops = 2.0 * 8.0 * double(iters) * double(grid) * block / (double(best) * 1e-3) / 1e12;
+  return EO_OK;
+}
+
 // ------------------------------------------------------------------ statistics
 int eo_stats_reset(eo_ctx* ctx) {
   EO_REQUIRE(ctx, ctx != nullptr, "eo_stats_reset: ctx is NULL");
   EO_CUDA(ctx, cudaMemsetAsync(ctx->stats, 0, sizeof(eo_stats), ctx->s_cmp));
+  static const double neg_inf = -INFINITY;  // max yielding may be negative (all points elastic)
+  EO_CUDA(ctx, cudaMemcpyAsync(&ctx->stats->f_max, &neg_inf, sizeof(double), cudaMemcpyHostToDevice, ctx->s_cmp));
   return EO_OK;
 }
 int eo_stats_read(eo_ctx* ctx, eo_stats* out) {

@@ -1,0 +1,428 @@
+// mc.cu - Mohr-Coulomb return mapping with apex smoothing on sm_100a (FP64-pipe bound).
+// reference: doc/demo/demo_plasticity_mohr_coulomb.py:474-533 (return_mapping), :555 (jacfwd through
+// the loop), :574-593 (vectorised C_tang_impl and its per-call statistics).  The per-point algebra is
+// in mc_core.cuh; this file is the execution scheme.
+//
+// The work is irregular: ~2/3 of the points are elastic (a trial-stress test and a 188-byte store),
+// the rest need 2..5 Newton updates of ~2.5 kflop each.  The reference's vmapped while_loop runs every
+// lane until the slowest has finished (:565-571).  Here one persistent CTA per SM runs a small
+// stage scheduler so that a warp always executes ONE kind of step on 32 points that need it:
+//
+//   stage T    32 new points: 256-bit loads, trial stress, yield test (:421-422).  Elastic points are
+//              finished on the spot (tangent = C_elas, :442-443); plastic points get a state slot in
+//              shared memory and are queued for S0.
+//   stage S0   first residual r(y0) and ||res0|| (:500-501)               -> queue U0
+//   stage U0   first Newton update (Y0 = 0: no third-derivative term) + residual + loop test
+//   stage U    Newton update with the full tangent recursion + residual + loop test      -> queue U / exit
+//
+// A point's state (y, Y = dy/d deps, the G-partials and residual at the current iterate: 46 doubles,
+// 51 when phi != psi) stays in its shared-memory slot between stages (structure-of-arrays over slots);
+// queues hold slot numbers.  Warps pick the fullest-priority queue holding >= 32 entries (U > U0 > S0 > T)
+// under one CTA-wide spin lock that is held for a few dozen cycles per ~10^4-cycle stage, so all 32
+// lanes do the same arithmetic although points need different numbers of iterations.  Tiles of
+// MC_TILE points are handed to CTAs by a global atomic counter (plastic zones cluster in real meshes).
+// Statistics (:584-591: histogram of niter, max f, max ||res||) are accumulated in shared memory and
+// flushed once per CTA into the context's eo_stats record.
+#include "eo_common.cuh"
+#include "mc_core.cuh"
+
+#define MC_THREADS 384   // 12 warps, one CTA per SM
+#define MC_NSLOTS 512    // state slots per CTA (power of two: ring-buffer arithmetic)
+#define MC_TILE 4096     // points per work item of the global counter
+#define MC_SIMPLE_THREADS 128
+
+struct mc_ptrs {
+  const double* deps;
+  const double* sigma_n;
+  double* C_tang;
+  double* sigma;
+  int32_t* niter;
+  double* yielding;
+  double* norm_res;
+  double* dlambda;
+};
+
+__device__ __forceinline__ void mc_atomic_max_f64(double* addr, double v) {
+  if (!(v == v)) return;  // NaN never becomes a maximum
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+  unsigned long long old = *a;
+  while (__longlong_as_double((long long)old) < v) {
+    const unsigned long long prev = atomicCAS(a, old, (unsigned long long)__double_as_longlong(v));
+    if (prev == old) break;
+    old = prev;
+  }
+}
+
+__device__ __forceinline__ void mc_store_aux(const mc_ptrs& P, int64_t i, int32_t niter, double yielding,
+                                             double norm_res, double dlambda) {
+  if (P.niter) P.niter[i] = niter;
+  if (P.yielding) eo_st64(P.yielding + i, yielding);
+  if (P.norm_res) eo_st64(P.norm_res + i, norm_res);
+  if (P.dlambda) eo_st64(P.dlambda + i, dlambda);
+}
+
+__device__ __forceinline__ void mc_store_point(const mc_ptrs& P, int64_t i, const double Ct[16], const double sig[4]) {
+  double* C = P.C_tang + 16 * i;
+  eo_st256(C + 0, Ct[0], Ct[1], Ct[2], Ct[3]);
+  eo_st256(C + 4, Ct[4], Ct[5], Ct[6], Ct[7]);
+  eo_st256(C + 8, Ct[8], Ct[9], Ct[10], Ct[11]);
+  eo_st256(C + 12, Ct[12], Ct[13], Ct[14], Ct[15]);
+  eo_st256(P.sigma + 4 * i, sig[0], sig[1], sig[2], sig[3]);
+}
+
+enum { MC_Q_S0 = 0, MC_Q_U0 = 1, MC_Q_U = 2, MC_Q_FREE = 3, MC_STAGE_T = 3, MC_STAGE_WAIT = 4, MC_STAGE_EXIT = 5 };
+#define MC_EMPTY 0xFFFFu
+#define MC_UNITS_PER_TILE (MC_TILE / 32)
+
+// Bounded multi-producer / multi-consumer ring of slot numbers with per-cell full/empty state
+// (a cell holds MC_EMPTY or a slot number).  `cnt` counts fully published entries and is what consumers
+// claim from; `head`/`tail` are free-running positions.  No locks: a consumer that claimed a cell whose
+// producer is still writing spins on the cell for a few cycles, and vice versa.
+struct mc_queue {
+  unsigned int cnt, head, tail, pad;
+};
+
+// leader lane: claim between want_min and 32 published entries; returns the number taken (0: none)
+__device__ __forceinline__ int mc_q_claim(mc_queue* q, unsigned int want_min, unsigned int& base) {
+  for (int tries = 0; tries < 4; ++tries) {
+    const unsigned int c = *(volatile unsigned int*)&q->cnt;
+    if (c < want_min || c == 0) return 0;
+    const unsigned int t = c < 32u ? c : 32u;
+    if (atomicCAS(&q->cnt, c, c - t) == c) {
+      base = atomicAdd(&q->head, t);
+      return (int)t;
+    }
+  }
+  return 0;
+}
+
+__device__ __forceinline__ int mc_q_read(volatile unsigned short* ring, unsigned int pos) {
+  unsigned short v;
+  while ((v = ring[pos & (MC_NSLOTS - 1)]) == MC_EMPTY) {
+  }
+  ring[pos & (MC_NSLOTS - 1)] = MC_EMPTY;
+  return (int)v;
+}
+
+// warp-collective: lanes with slot >= 0 append it
+__device__ __forceinline__ void mc_q_push(mc_queue* q, volatile unsigned short* ring, int slot, int lane) {
+  const unsigned m = __ballot_sync(0xffffffffu, slot >= 0);
+  if (m == 0) return;
+  unsigned int base = 0;
+  if (lane == 0) base = atomicAdd(&q->tail, (unsigned)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (slot >= 0) {
+    const unsigned int pos = (base + __popc(m & ((1u << lane) - 1u))) & (MC_NSLOTS - 1);
+    while (ring[pos] != MC_EMPTY) {
+    }
+    ring[pos] = (unsigned short)slot;
+  }
+  __threadfence_block();
+  __syncwarp();
+  if (lane == 0) atomicAdd(&q->cnt, (unsigned)__popc(m));
+}
+
+template <bool ASSOC>
+__global__ void __launch_bounds__(MC_THREADS, 1) mc_kernel(const mc_consts k, const mc_ptrs P, const int64_t n,
+                                                           eo_stats* __restrict__ stats, unsigned int* tile_ctr) {
+  extern __shared__ double s_slots[];  // [ASSOC ? MC_NF_ASSOC : MC_NF][MC_NSLOTS]
+  __shared__ unsigned short s_ring[4][MC_NSLOTS];
+  __shared__ long long s_pt[MC_NSLOTS];
+  __shared__ int s_it[MC_NSLOTS];
+  __shared__ mc_queue s_q[4];
+  __shared__ unsigned long long s_work;  // (tile index << 16) | next 32-point unit within the tile
+  __shared__ int s_inflight, s_done, s_fetching;  // inflight: plastic points in the system + T stages running
+  __shared__ unsigned int s_hist[EO_NITER_BINS];
+  __shared__ unsigned int s_nonconv, s_nonfinite, s_plastic;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t ntiles = (n + MC_TILE - 1) / MC_TILE;
+  for (int b = tid; b < EO_NITER_BINS; b += MC_THREADS) s_hist[b] = 0;
+  for (int b = tid; b < MC_NSLOTS; b += MC_THREADS) {
+    s_ring[MC_Q_FREE][b] = (unsigned short)b;
+    s_ring[MC_Q_S0][b] = s_ring[MC_Q_U0][b] = s_ring[MC_Q_U][b] = MC_EMPTY;
+  }
+  if (tid == 0) {
+    s_nonconv = s_nonfinite = s_plastic = 0;
+    s_inflight = 0, s_done = 0, s_fetching = 0;
+    for (int q = 0; q < 4; ++q) s_q[q].cnt = 0, s_q[q].head = 0, s_q[q].tail = 0;
+    s_q[MC_Q_FREE].cnt = MC_NSLOTS;
+    s_work = 0xFFFFull;  // "exhausted": the first warp to look fetches a tile
+  }
+  __syncthreads();
+  double max_f = -INFINITY, max_res = 0.0;
+  int max_it = 0;
+
+  for (;;) {
+    // ------------------------------------------------------------------ pick a stage (lane 0, lock-free)
+    int stage = MC_STAGE_WAIT, take = 0;
+    unsigned int qpos = 0;
+    long long in0 = 0;
+    if (lane == 0) {
+      const unsigned int cU = *(volatile unsigned int*)&s_q[MC_Q_U].cnt, cU0 = *(volatile unsigned int*)&s_q[MC_Q_U0].cnt,
+                         cS0 = *(volatile unsigned int*)&s_q[MC_Q_S0].cnt, cF = *(volatile unsigned int*)&s_q[MC_Q_FREE].cnt;
+      unsigned long long w = *(volatile unsigned long long*)&s_work;
+      long long tile = (long long)(w >> 16);
+      long long units = (tile < ntiles) ? (((n - tile * MC_TILE < MC_TILE ? n - tile * MC_TILE : MC_TILE) + 31) / 32) : 0;
+      bool inputs = (long long)(w & 0xFFFFull) < units;
+      if (!inputs && !*(volatile int*)&s_done && atomicCAS(&s_fetching, 0, 1) == 0) {
+        // fetch the next tile (one warp at a time; re-check under the flag)
+        w = *(volatile unsigned long long*)&s_work;
+        tile = (long long)(w >> 16);
+        units = (tile < ntiles) ? (((n - tile * MC_TILE < MC_TILE ? n - tile * MC_TILE : MC_TILE) + 31) / 32) : 0;
+        if (!((long long)(w & 0xFFFFull) < units)) {
+          const unsigned int t = atomicAdd(tile_ctr, 1u);
+          if ((int64_t)t >= ntiles) {
+            *(volatile int*)&s_done = 1;
+          } else {
+            atomicExch(&s_work, (unsigned long long)t << 16);
+            inputs = true;
+          }
+        } else {
+          inputs = true;
+        }
+        __threadfence_block();
+        atomicExch(&s_fetching, 0);
+      }
+      int want = -1;
+      if (cU >= 32) want = MC_Q_U;
+      else if (cU0 >= 32) want = MC_Q_U0;
+      else if (cS0 >= 32) want = MC_Q_S0;
+      else if (inputs && cF >= 32) want = MC_STAGE_T;
+      else if (cU | cU0 | cS0) want = (cU >= cU0 && cU >= cS0) ? MC_Q_U : (cU0 >= cS0 ? MC_Q_U0 : MC_Q_S0);
+      if (want >= 0 && want <= MC_Q_U) {
+        take = mc_q_claim(&s_q[want], 1, qpos);
+        if (take > 0) stage = want;
+      } else if (want == MC_STAGE_T) {
+        take = mc_q_claim(&s_q[MC_Q_FREE], 32, qpos);  // reserve 32 slots; unused ones go back after the stage
+        if (take == 32) {
+          atomicAdd(&s_inflight, 1);  // before the claim: "inflight == 0 and no inputs" then means finished
+          const unsigned long long w2 = atomicAdd(&s_work, 1ull);
+          const long long tile2 = (long long)(w2 >> 16), off = (long long)(w2 & 0xFFFFull);
+          const long long pts = tile2 < ntiles ? (n - tile2 * MC_TILE < MC_TILE ? n - tile2 * MC_TILE : MC_TILE) : 0;
+          if (off * 32 < pts) {
+            stage = MC_STAGE_T;
+            in0 = tile2 * MC_TILE + off * 32;
+            take = (int)(pts - off * 32 < 32 ? pts - off * 32 : 32);
+          } else {
+            stage = MC_STAGE_T;  // lost the race for the last unit: run an empty T stage that returns the slots
+            take = 0;
+          }
+        } else {
+          take = 0;
+        }
+      }
+      if (stage == MC_STAGE_WAIT && *(volatile int*)&s_done && *(volatile int*)&s_inflight == 0) {
+        // nothing claimed, no tile left, no plastic point and no T stage in flight anywhere in the CTA
+        const unsigned long long w3 = *(volatile unsigned long long*)&s_work;
+        const long long tile3 = (long long)(w3 >> 16);
+        const long long pts3 = tile3 < ntiles ? (n - tile3 * MC_TILE < MC_TILE ? n - tile3 * MC_TILE : MC_TILE) : 0;
+        if (!((long long)(w3 & 0xFFFFull) * 32 < pts3)) stage = MC_STAGE_EXIT;
+      }
+    }
+    stage = __shfl_sync(0xffffffffu, stage, 0);
+    if (stage == MC_STAGE_EXIT) break;
+#ifdef MC_DEBUG_COUNTERS
+    if (lane == 0) {
+      if (stage == MC_STAGE_WAIT) atomicAdd(tile_ctr + 9, 1u);
+      else {
+        atomicAdd(tile_ctr + 1 + 2 * (stage == MC_STAGE_T ? 0 : stage + 1), 1u);
+        atomicAdd(tile_ctr + 2 + 2 * (stage == MC_STAGE_T ? 0 : stage + 1), (unsigned)take);
+      }
+    }
+#endif
+    if (stage == MC_STAGE_WAIT) {
+      __nanosleep(100);
+      continue;
+    }
+    take = __shfl_sync(0xffffffffu, take, 0);
+    qpos = __shfl_sync(0xffffffffu, qpos, 0);
+
+    int slotA = -1;  // slot this lane returns to the FREE list after the stage
+    int slotB = -1;  // slot this lane hands on to the next queue
+    if (stage == MC_STAGE_T) {
+      // ---------------------------------------------------------------- stage T
+      in0 = __shfl_sync(0xffffffffu, in0, 0);
+      const int myres = mc_q_read(s_ring[MC_Q_FREE], qpos + lane);  // the lane-th reserved slot
+      bool plastic = false;
+      double yl = 0.0, sn[4], Cde[4];
+      const int64_t i = in0 + lane;
+      if (lane < take) {
+        const eo_d4 e = eo_ld256(P.deps + 4 * i);
+        const eo_d4 sg = eo_ld256(P.sigma_n + 4 * i);
+        const double de[4] = {e.x, e.y, e.z, e.w};
+        sn[0] = sg.x, sn[1] = sg.y, sn[2] = sg.z, sn[3] = sg.w;
+        yl = mc_trial(k, de, sn, Cde);
+        max_f = fmax(max_f, yl);
+        if (yl <= 0.0) {
+          double sig[4], Ct[16], nr, dl;
+          const int32_t it = mc_elastic(k, sn, Cde, sig, Ct, nr, dl);
+          mc_store_point(P, i, Ct, sig);
+          mc_store_aux(P, i, it, yl, nr, dl);
+          max_res = fmax(max_res, nr);
+          max_it = max(max_it, it);
+          atomicAdd(&s_hist[it], 1u);
+          if (!(isfinite(sig[0]) && isfinite(sig[1]) && isfinite(sig[2]) && isfinite(sig[3])))
+            atomicAdd(&s_nonfinite, 1u);
+        } else {
+          plastic = true;  // a NaN predicate takes the plastic branch, like `yielding <= 0.0` being false
+        }
+      }
+      const unsigned pm = __ballot_sync(0xffffffffu, plastic);
+      const int rank = __popc(pm & ((1u << lane) - 1u));
+      const int npl = __popc(pm);
+      // the plastic lane of rank r takes reserved slot r; reserved slots >= npl go back
+      const int got = __shfl_sync(0xffffffffu, myres, plastic ? rank : 0);
+      if (plastic) {
+        slotB = got;
+        const mc_slot sl{s_slots + slotB, MC_NSLOTS};
+        mc_slot_init(sl, sn, Cde, yl);
+        s_pt[slotB] = i;
+        s_it[slotB] = 0;
+      }
+      if (lane >= npl) slotA = myres;
+      if (lane == 0) atomicAdd(&s_inflight, npl - 1);  // the points enter before this T stage leaves
+    } else {
+      // ---------------------------------------------------------------- stages S0 / U0 / U
+      if (lane < take) {
+        const int slot = mc_q_read(s_ring[stage], qpos + lane);
+        const mc_slot sl{s_slots + slot, MC_NSLOTS};
+        int32_t it = s_it[slot];
+        const bool out = mc_stage<ASSOC>(k, stage, sl, it);
+        s_it[slot] = it;
+        if (out) {
+          const int64_t i = s_pt[slot];
+          double Ct[16], sig[4], nr, dl;
+          mc_slot_result(sl, it, Ct, sig, nr, dl);
+          mc_store_point(P, i, Ct, sig);
+          mc_store_aux(P, i, it, sl[MC_F_YIELD], nr, dl);
+          max_res = fmax(max_res, nr);
+          max_it = max(max_it, it);
+          atomicAdd(&s_hist[min(it, EO_NITER_BINS - 1)], 1u);
+          atomicAdd(&s_plastic, 1u);
+          atomicAdd(&s_inflight, -1);
+          if (it >= k.nitermax) atomicAdd(&s_nonconv, 1u);
+          if (!(isfinite(sig[0]) && isfinite(sig[1]) && isfinite(sig[2]) && isfinite(sig[3])))
+            atomicAdd(&s_nonfinite, 1u);
+          slotA = slot;
+        } else {
+          slotB = slot;
+        }
+      }
+    }
+
+    // ------------------------------------------------------------------ hand the slots on
+    const int qB = stage == MC_STAGE_T ? MC_Q_S0 : (stage == MC_Q_S0 ? MC_Q_U0 : MC_Q_U);
+    __syncwarp();
+    mc_q_push(&s_q[qB], s_ring[qB], slotB, lane);
+    mc_q_push(&s_q[MC_Q_FREE], s_ring[MC_Q_FREE], slotA, lane);
+    __syncwarp();
+  }
+
+  // ------------------------------------------------------------------ statistics flush
+  __syncthreads();
+  for (int b = tid; b < EO_NITER_BINS; b += MC_THREADS)
+    if (s_hist[b]) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->niter_hist[b]), (unsigned long long)s_hist[b]);
+  if (tid == 0) {
+    if (s_plastic) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_plastic), (unsigned long long)s_plastic);
+    if (s_nonconv) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_nonconverged), (unsigned long long)s_nonconv);
+    if (s_nonfinite) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_nonfinite), (unsigned long long)s_nonfinite);
+    if (blockIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_points), (unsigned long long)n);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    max_f = fmax(max_f, __shfl_xor_sync(0xffffffffu, max_f, o));
+    max_res = fmax(max_res, __shfl_xor_sync(0xffffffffu, max_res, o));
+    max_it = max(max_it, __shfl_xor_sync(0xffffffffu, max_it, o));
+  }
+  if (lane == 0) {
+    mc_atomic_max_f64(&stats->f_max, max_f);
+    mc_atomic_max_f64(&stats->res_max, max_res);
+    mc_atomic_max_f64(&stats->niter_max, (double)max_it);
+  }
+}
+
+// simple variant: one thread per point, whole Newton loop per thread (divergent).  Kept as the
+// baseline the queue scheme is measured against (bench.py --mc-scheme simple) and as a cross-check.
+template <bool ASSOC>
+__global__ void __launch_bounds__(MC_SIMPLE_THREADS) mc_kernel_simple(const mc_consts k, const mc_ptrs P, const int64_t n) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const eo_d4 e = eo_ld256(P.deps + 4 * i);
+  const eo_d4 s = eo_ld256(P.sigma_n + 4 * i);
+  const double de[4] = {e.x, e.y, e.z, e.w}, sn[4] = {s.x, s.y, s.z, s.w};
+  double Ct[16], sig[4], yl, nr, dl;
+  int32_t it;
+  mc_point(k, de, sn, Ct, sig, it, yl, nr, dl);
+  mc_store_point(P, i, Ct, sig);
+  mc_store_aux(P, i, it, yl, nr, dl);
+}
+
+static bool g_mc_attr_set[2] = {false, false};
+
+static int mc_launch(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, int64_t n, int scheme) {
+  if (scheme == 1) {
+    const int64_t grid64 = (n + MC_SIMPLE_THREADS - 1) / MC_SIMPLE_THREADS;
+    if (grid64 > 2147483647LL) return eo_fail(ctx, EO_ERR_INVALID, "eo_mc_eval: n too large for one launch");
+    if (k.assoc)
+      mc_kernel_simple<true><<<(unsigned)grid64, MC_SIMPLE_THREADS, 0, ctx->s_cmp>>>(k, P, n);
+    else
+      mc_kernel_simple<false><<<(unsigned)grid64, MC_SIMPLE_THREADS, 0, ctx->s_cmp>>>(k, P, n);
+    ctx->launches += 1;
+    return EO_OK;
+  }
+  const int a = k.assoc ? 1 : 0;
+  const size_t smem = size_t(k.assoc ? MC_NF_ASSOC : MC_NF) * MC_NSLOTS * sizeof(double);
+  if (!g_mc_attr_set[a]) {
+    cudaError_t e = k.assoc ? cudaFuncSetAttribute(mc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                            : cudaFuncSetAttribute(mc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return eo_fail(ctx, EO_ERR_CUDA, "eo_mc_eval: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    g_mc_attr_set[a] = true;
+  }
+  const int64_t ntiles = (n + MC_TILE - 1) / MC_TILE;
+  if (ntiles > 4000000000LL) return eo_fail(ctx, EO_ERR_INVALID, "eo_mc_eval: n too large for one launch");
+  const int64_t grid = ntiles < ctx->sm_count ? ntiles : ctx->sm_count;
+  cudaError_t e = cudaMemsetAsync(ctx->work_ctr, 0, 256, ctx->s_cmp);
+  if (e != cudaSuccess) return eo_fail(ctx, EO_ERR_CUDA, "eo_mc_eval: cudaMemsetAsync: %s", cudaGetErrorString(e));
+  if (k.assoc)
+    mc_kernel<true><<<(unsigned)grid, MC_THREADS, smem, ctx->s_cmp>>>(k, P, n, ctx->stats, ctx->work_ctr);
+  else
+    mc_kernel<false><<<(unsigned)grid, MC_THREADS, smem, ctx->s_cmp>>>(k, P, n, ctx->stats, ctx->work_ctr);
+  ctx->launches += 1;
+  return EO_OK;
+}
+
+extern "C" {
+
+int eo_mc_eval(eo_ctx* ctx, const eo_mc_params* prm, const double* deps, const double* sigma_n, double* C_tang,
+               double* sigma, int32_t* niter, double* yielding, double* norm_res, double* dlambda, int64_t n) {
+  return eo_mc_eval_scheme(ctx, prm, deps, sigma_n, C_tang, sigma, niter, yielding, norm_res, dlambda, n, 0);
+}
+
+int eo_mc_eval_scheme(eo_ctx* ctx, const eo_mc_params* prm, const double* deps, const double* sigma_n, double* C_tang,
+                      double* sigma, int32_t* niter, double* yielding, double* norm_res, double* dlambda, int64_t n,
+                      int scheme) {
+  EO_REQUIRE(ctx, ctx != nullptr, "eo_mc_eval: ctx is NULL");
+  EO_REQUIRE(ctx, prm != nullptr, "eo_mc_eval: prm is NULL");
+  EO_REQUIRE(ctx, n >= 0, "eo_mc_eval: n < 0");
+  EO_REQUIRE(ctx, scheme == 0 || scheme == 1, "eo_mc_eval: unknown scheme");
+  EO_REQUIRE(ctx, prm->Nitermax >= 0 && prm->Nitermax <= 200,
+             "eo_mc_eval: Nitermax must be in [0, 200] (histogram bins of eo_stats)");
+  if (n == 0) return EO_OK;
+  EO_REQUIRE(ctx, deps && sigma_n && C_tang && sigma, "eo_mc_eval: NULL array");
+  EO_CUDA(ctx, cudaSetDevice(ctx->device));
+  mc_params_in pin{prm->E, prm->nu, prm->c, prm->phi, prm->psi, prm->theta_T, prm->a, prm->tol, prm->Nitermax};
+  mc_consts k;
+  mc_make_consts(pin, k);
+  eo_arg args[8] = {{deps, 32, false},  {sigma_n, 32, false}, {C_tang, 128, true},  {sigma, 32, true},
+                    {niter, 4, true},   {yielding, 8, true},  {norm_res, 8, true}, {dlambda, 8, true}};
+  return eo_run_streamed(ctx, args, 8, n, [&](void** a, int64_t m, int64_t) {
+    for (int i = 0; i < 4; ++i)
+      if (!eo_aligned(a[i], 32)) return eo_fail(ctx, EO_ERR_INVALID, "eo_mc_eval: deps/sigma_n/C_tang/sigma must be 32-byte aligned");
+    mc_ptrs P{(const double*)a[0], (const double*)a[1], (double*)a[2], (double*)a[3],
+              (int32_t*)a[4],      (double*)a[5],       (double*)a[6], (double*)a[7]};
+    return mc_launch(ctx, k, P, m, scheme);
+  });
+}
+
+}  // extern "C"

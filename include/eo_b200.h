@@ -96,6 +96,15 @@ int eo_event_elapsed_ms(eo_ctx* ctx, void* ev_start, void* ev_stop, float* ms);
  * timed iterations. */
 int eo_flush_l2(eo_ctx* ctx, size_t bytes);
 
+/* Debug: copy the 64 uint32 scheduler counters of the last persistent-kernel launch to `out` (only
+ * meaningful when the library was built with -DMC_DEBUG_COUNTERS; [0] is the tile counter). */
+int eo_debug_counters(eo_ctx* ctx, uint32_t* out);
+
+/* FP64 roofline denominator for the Newton-bound kernels: runs a register-only DFMA micro-benchmark
+ * (8 independent chains per thread, `iters` trips, all SMs) and returns the best of 3 timed launches
+ * in TFLOP/s (2 flops per DFMA). */
+int eo_fp64_peak(eo_ctx* ctx, int iters, double* tflops);
+
 /* ---------------------------------------------------------------- statistics
  * Device-resident record that every constitutive kernel accumulates into in its
  * epilogue (one atomic per CTA).  replaces: the host-side `jnp.unique(niter,
@@ -114,7 +123,7 @@ typedef struct eo_stats {
   int64_t niter_hist[EO_NITER_BINS];
   /* MAX block: 4 f64 */
   double niter_max;
-  double f_max;   /* mc: max yielding (demo_mc:590) */
+  double f_max;   /* mc: max yielding (demo_mc:590); -inf after a reset */
   double res_max; /* mc: max ||res|| (demo_mc:591) */
   double reserved;
 } eo_stats;
@@ -161,6 +170,37 @@ int eo_commit_history(eo_ctx* ctx, double* sigma_n, const double* sigma, double*
  * ONE fused kernel): k [n], dk [n], q [n][2], dqdT [n][2], dqdsigma [n][2][2]. */
 int eo_heat_eval(eo_ctx* ctx, double A, double B, const double* T, const double* sigma, double* k, double* dk,
                  double* q, double* dqdT, double* dqdsigma, int64_t n);
+
+/* ---------------------------------------------------------------- Mohr-Coulomb
+ * replaces: `dsigma_ddeps_vec = jit(vmap(jacfwd(return_mapping, has_aux=True)))` and the body of
+ *           `C_tang_impl`, doc/demo/demo_plasticity_mohr_coulomb.py:474-533, :555, :574-593
+ *           (surface :282-374, residual/Jacobian :405-465).
+ * Constants: demo_mc:110-116 (E, nu, c, phi, psi, theta_T, a) and :469 (tol, Nitermax). */
+typedef struct eo_mc_params {
+  double E, nu, c, phi, psi, theta_T, a, tol;
+  int32_t Nitermax; /* <= 200 */
+} eo_mc_params;
+
+/* deps [n][4], sigma_n [n][4]  ->  C_tang [n][4][4] (the derivative of the Newton ITERATION w.r.t.
+ * deps, i.e. what jacfwd-through-while_loop returns, not the implicit-function tangent), sigma [n][4],
+ * and the aux tuple of demo_mc:533 per point: niter [n] (int32), yielding [n] = f(trial stress),
+ * norm_res [n], dlambda [n] - each of the four aux arrays may be NULL.
+ * Elastic points (yielding <= 0) take one Newton step with J = I: C_tang = C_elas exactly, niter = 1.
+ * IEEE hazards are the reference's: J2 == 0 at a plastic point or ||res0|| == 0 give NaN / zero
+ * iterations, clipped asin arguments give NaN tangents.  The histogram of niter, max yielding,
+ * max norm_res (the per-call prints of demo_mc:584-591) and the counts of plastic / non-converged /
+ * non-finite points are accumulated into the ctx statistics record.
+ * Algorithmic HBM traffic: 64 B read + 160 B (+ 28 B aux) written per point; the kernel is bound by
+ * the FP64 pipe (local Newton + tangent recursion), not by HBM.
+ * deps, sigma_n, C_tang, sigma must be 32-byte aligned when they are device pointers. */
+int eo_mc_eval(eo_ctx* ctx, const eo_mc_params* prm, const double* deps, const double* sigma_n, double* C_tang,
+               double* sigma, int32_t* niter, double* yielding, double* norm_res, double* dlambda, int64_t n);
+/* Same with an explicit execution scheme: 0 = persistent CTAs with a shared-memory queue of plastic
+ * points and lane refill (the default of eo_mc_eval), 1 = one thread per point (divergent baseline;
+ * does not update the statistics record). */
+int eo_mc_eval_scheme(eo_ctx* ctx, const eo_mc_params* prm, const double* deps, const double* sigma_n,
+                      double* C_tang, double* sigma, int32_t* niter, double* yielding, double* norm_res,
+                      double* dlambda, int64_t n, int scheme);
 
 #ifdef __cplusplus
 }
