@@ -16,6 +16,7 @@ EO_OK = 0
 EO_LAYOUT_AOS = 0
 EO_LAYOUT_SOA = 1
 EO_NITER_BINS = 208
+EO_OPERAND_VALUE, EO_OPERAND_GRAD, EO_OPERAND_MANDEL_STRAIN, EO_OPERAND_DEF_GRAD = 0, 1, 2, 3
 
 STATUS_NAMES = {
     0: "EO_OK",
@@ -40,6 +41,13 @@ class VmParams(C.Structure):
 class McParams(C.Structure):
     _fields_ = [("E", C.c_double), ("nu", C.c_double), ("c", C.c_double), ("phi", C.c_double), ("psi", C.c_double),
                 ("theta_T", C.c_double), ("a", C.c_double), ("tol", C.c_double), ("Nitermax", C.c_int32)]
+
+
+class TabDesc(C.Structure):
+    _fields_ = [("gdim", C.c_int32), ("bs", C.c_int32), ("nb", C.c_int32), ("nq", C.c_int32),
+                ("n_cells", C.c_int64), ("n_dofs", C.c_int64), ("n_nodes", C.c_int64),
+                ("dofmap", C.c_void_p), ("x_dofmap", C.c_void_p), ("x", C.c_void_p),
+                ("phi", C.c_void_p), ("dphi", C.c_void_p), ("dpsi", C.c_void_p)]
 
 
 class Stats(C.Structure):
@@ -94,6 +102,11 @@ PROTOTYPES = {
     "eo_vm_eval_resident": (C.c_int, [_vp, C.POINTER(VmParams), _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_int]),
     "eo_commit_history": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, C.c_int]),
     "eo_heat_eval": (C.c_int, [_vp, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
+    "eo_tab_create": (C.c_int, [_vp, C.POINTER(TabDesc), C.POINTER(_vp)]),
+    "eo_tab_destroy": (C.c_int, [_vp]),
+    "eo_tab_ncomp": (C.c_int, [_vp, C.c_int]),
+    "eo_tabulate": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _vp]),
+    "eo_tab_vm_fused": (C.c_int, [_vp, C.POINTER(VmParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "eo_mc_eval": (C.c_int, [_vp, C.POINTER(McParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
     "eo_mc_eval_scheme": (C.c_int, [_vp, C.POINTER(McParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_int]),
 }

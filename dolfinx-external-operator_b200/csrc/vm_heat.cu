@@ -8,14 +8,11 @@
 // aligned, so every access is a single LDG.E.256 / STG.E.256 per thread and a warp instruction
 // covers 1 KB of consecutive, fully used sectors.
 #include "eo_common.cuh"
+#include "vm_core.cuh"
 
 // ------------------------------------------------------------------------------------------
 // von Mises                                   (reference: demo_plasticity_von_mises.py:307-326)
 // ------------------------------------------------------------------------------------------
-struct vm_consts {
-  double l, m, H, s0;
-};
-
 template <bool VEC, int STATE_LAYOUT>
 __global__ void __launch_bounds__(256) vm_kernel(vm_consts q, const double* __restrict__ deps,
                                                  const double* __restrict__ sigma_n, const double* __restrict__ p,
@@ -44,56 +41,20 @@ __global__ void __launch_bounds__(256) vm_kernel(vm_consts q, const double* __re
     }
     const double pi = eo_ld64(p + i);
 
-    const double l = q.l, m = q.m, H = q.H;
-    const double l2m = l + 2.0 * m;
-    // sigma_elastic = sigma_n + C_elas @ deps                                   (:308)
-    const double se0 = n0 + (l2m * e0 + l * e1 + l * e2);
-    const double se1 = n1 + (l * e0 + l2m * e1 + l * e2);
-    const double se2 = n2 + (l * e0 + l * e1 + l2m * e2);
-    const double se3 = n3 + 2.0 * m * e3;
-    // s = deviatoric @ sigma_elastic                                             (:309)
-    const double third = 1.0 / 3.0;
-    const double tt = 1.0 - third;
-    const double s0 = tt * se0 - third * se1 - third * se2;
-    const double s1 = -third * se0 + tt * se1 - third * se2;
-    const double s2 = -third * se0 - third * se1 + tt * se2;
-    const double s3 = se3;
-    const double seq = sqrt(3.0 / 2.0 * (s0 * s0 + s1 * s1 + s2 * s2 + s3 * s3));  // (:310)
-    const double f = seq - q.s0 - H * pi;                                        // (:312)
-    const double fp = (f + sqrt(f * f)) / 2.0;                                   // (:313)
-    const double dp = fp / (3 * m + H);                                          // (:315)
-    const double v0 = s0 / seq * fp / f, v1 = s1 / seq * fp / f, v2 = s2 / seq * fp / f,
-                 v3 = s3 / seq * fp / f;                                         // (:317)
-    const double beta = 3 * m * dp / seq;                                        // (:318)
-    const double g0 = se0 - beta * s0, g1 = se1 - beta * s1, g2 = se2 - beta * s2, g3 = se3 - beta * s3;  // (:320)
-    const double cn = 3 * m * (3 * m / (3 * m + H) - beta);                      // (:323)
-    const double cd = 2 * m * beta;
-    const double Dd = 1.0 - third, Do = 0.0 - third;  // deviatoric diagonal / off-diagonal (3x3 block)
-    plastic = dp > 0.0;
+    vm_point_out o;
+    vm_point(q, e0, e1, e2, e3, n0, n1, n2, n3, pi, o);
+    plastic = o.dp > 0.0;
+    const double g0 = o.g[0], g1 = o.g[1], g2 = o.g[2], g3 = o.g[3], dp = o.dp;
 
     double* Ct = C_tang + 16 * i;
     if (VEC) {
-      eo_st256(Ct + 0, l2m - cn * (v0 * v0) - cd * Dd, l - cn * (v0 * v1) - cd * Do, l - cn * (v0 * v2) - cd * Do,
-               0.0 - cn * (v0 * v3) - cd * 0.0);
-      eo_st256(Ct + 4, l - cn * (v1 * v0) - cd * Do, l2m - cn * (v1 * v1) - cd * Dd, l - cn * (v1 * v2) - cd * Do,
-               0.0 - cn * (v1 * v3) - cd * 0.0);
-      eo_st256(Ct + 8, l - cn * (v2 * v0) - cd * Do, l - cn * (v2 * v1) - cd * Do, l2m - cn * (v2 * v2) - cd * Dd,
-               0.0 - cn * (v2 * v3) - cd * 0.0);
-      eo_st256(Ct + 12, 0.0 - cn * (v3 * v0) - cd * 0.0, 0.0 - cn * (v3 * v1) - cd * 0.0,
-               0.0 - cn * (v3 * v2) - cd * 0.0, 2.0 * m - cn * (v3 * v3) - cd * 1.0);
+      eo_st256(Ct + 0, o.C[0], o.C[1], o.C[2], o.C[3]);
+      eo_st256(Ct + 4, o.C[4], o.C[5], o.C[6], o.C[7]);
+      eo_st256(Ct + 8, o.C[8], o.C[9], o.C[10], o.C[11]);
+      eo_st256(Ct + 12, o.C[12], o.C[13], o.C[14], o.C[15]);
     } else {
-      const double v[4] = {v0, v1, v2, v3};
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          double Cab = 0.0;
-          if (a < 3 && b < 3) Cab = (a == b) ? l2m : l;
-          if (a == 3 && b == 3) Cab = 2.0 * m;
-          double Dab = (a == b) ? 1.0 : 0.0;
-          if (a < 3 && b < 3) Dab -= third;
-          eo_st64(Ct + 4 * a + b, Cab - cn * (v[a] * v[b]) - cd * Dab);
-        }
+      for (int a = 0; a < 16; ++a) eo_st64(Ct + a, o.C[a]);
     }
     if (STATE_LAYOUT == EO_LAYOUT_SOA) {
       eo_st64(sigma + i, g0), eo_st64(sigma + n + i, g1), eo_st64(sigma + 2 * n + i, g2),

@@ -171,6 +171,53 @@ int eo_commit_history(eo_ctx* ctx, double* sigma_n, const double* sigma, double*
 int eo_heat_eval(eo_ctx* ctx, double A, double B, const double* T, const double* sigma, double* k, double* dk,
                  double* q, double* dqdT, double* dqdsigma, int64_t n);
 
+/* ---------------------------------------------------------------- operand tabulation
+ * replaces: `fem.Expression(operand, eval_points, dtype).eval(operand_mesh, entities)` inside
+ *           `evaluate_operands`, src/dolfinx_external_operator/external_operator.py:386-402 (DOLFINx
+ *           tabulate_expression + FFCx kernel + basix tables), for affine simplex cells (triangles,
+ *           tetrahedra) and the operand expressions of the reference demos.
+ * The basis tables are INPUTS (what basix `element.tabulate(1, eval_points)` returns on the host). */
+typedef enum eo_operand_kind {
+  EO_OPERAND_VALUE = 0,         /* f                      (T: part1.py:210, part2.py:136)               [bs]       */
+  EO_OPERAND_GRAD = 1,          /* grad f, row-major      (sigma = grad T: part2.py:137,167)            [bs][gdim] */
+  EO_OPERAND_MANDEL_STRAIN = 2, /* [g00, g11, 0, sqrt2/2 (g01+g10)]  (epsilon(Du): demo_vm:225-227,
+                                   demo_mc:148-157); needs gdim = bs = 2                               [4]        */
+  EO_OPERAND_DEF_GRAD = 3       /* I + grad u, row-major  (F: demo_hyperelasticity.py:479)              [bs][gdim] */
+} eo_operand_kind;
+
+typedef struct eo_tab_desc {
+  int32_t gdim;            /* 2 (triangles) or 3 (tetrahedra); geometry is the affine P1 map              */
+  int32_t bs;              /* block size of the coefficient: dof index = bs * node + comp (:18-26)        */
+  int32_t nb;              /* scalar basis functions per cell                                            */
+  int32_t nq;              /* evaluation points per cell (= element.interpolation_points, :200)          */
+  int64_t n_cells;         /* local + ghost cells (:368-370)                                             */
+  int64_t n_dofs;          /* blocked dofs of the coefficient (its array has bs * n_dofs scalars)         */
+  int64_t n_nodes;         /* geometry nodes                                                             */
+  const int32_t* dofmap;   /* [n_cells][nb]      V.dofmap.list                                           */
+  const int32_t* x_dofmap; /* [n_cells][gdim+1]  mesh.geometry.dofmap                                    */
+  const double* x;         /* [n_nodes][3]       mesh.geometry.x                                         */
+  const double* phi;       /* [nq][nb]           basix tabulate(1, X)[0]                                 */
+  const double* dphi;      /* [gdim][nq][nb]     basix tabulate(1, X)[1:]                                */
+  const double* dpsi;      /* [gdim][gdim+1]     derivatives of the P1 geometry element (constant)       */
+} eo_tab_desc;
+
+typedef struct eo_tab eo_tab;
+/* Uploads the mesh arrays and tables (they stay resident in HBM); index arrays are range-checked here. */
+int eo_tab_create(eo_ctx* ctx, const eo_tab_desc* desc, eo_tab** out);
+int eo_tab_destroy(eo_tab* tab);
+/* Components per evaluation point of an operand kind on this element, or EO_ERR_INVALID. */
+int eo_tab_ncomp(const eo_tab* tab, int kind);
+/* out[n_cells][nq][ncomp] = operand at the evaluation points of `cells` (NULL: cells 0..n_cells-1, the
+ * default entity list of :365-371; otherwise n_cells int32 cell indices = the `entities` argument).
+ * u (bs*n_dofs), cells and out are any-side pointers; with a host `out` the call is complete on return. */
+int eo_tabulate(eo_tab* tab, int kind, const double* u, const int32_t* cells, int64_t n_cells, double* out);
+/* Fused hot path for all cells: Mandel strain of u at every evaluation point -> von Mises radial return
+ * (eo_vm_eval) without the strain ever touching HBM.  Point index = cell * nq + q, as the reference's
+ * flat layout.  sigma_n, p, C_tang, sigma, dp (and `strain`, optional, may be NULL) are device memory;
+ * u is any-side.  Asynchronous on the ctx stream. */
+int eo_tab_vm_fused(eo_tab* tab, const eo_vm_params* prm, const double* u, const double* sigma_n, const double* p,
+                    double* C_tang, double* sigma, double* dp, double* strain);
+
 /* ---------------------------------------------------------------- Mohr-Coulomb
  * replaces: `dsigma_ddeps_vec = jit(vmap(jacfwd(return_mapping, has_aux=True)))` and the body of
  *           `C_tang_impl`, doc/demo/demo_plasticity_mohr_coulomb.py:474-533, :555, :574-593

@@ -3,8 +3,50 @@
 #include <cstdint>
 
 #include "mc_core.cuh"
+#include "tab_core.cuh"
+
+template <int GDIM, int BS, int NB>
+static void tab_cells(const tab_tables& T, int kind, const int32_t* dofmap, const int32_t* x_dofmap, const double* x,
+                      const double* u, int64_t n_cells, double* out) {
+  const int ncomp = tab_ncomp(kind, BS, GDIM);
+  for (int64_t c = 0; c < n_cells; ++c) {
+    double w[NB][BS], xv[GDIM + 1][GDIM], K[GDIM][GDIM];
+    for (int a = 0; a < NB; ++a)
+      for (int k = 0; k < BS; ++k) w[a][k] = u[int64_t(BS) * dofmap[c * NB + a] + k];
+    for (int v = 0; v < GDIM + 1; ++v)
+      for (int i = 0; i < GDIM; ++i) xv[v][i] = x[3 * int64_t(x_dofmap[c * (GDIM + 1) + v]) + i];
+    tab_geometry<GDIM>(T, xv, K);
+    for (int q = 0; q < T.nq; ++q) {
+      double val[BS], grad[BS][GDIM], r[16];
+      tab_point<GDIM, BS, NB>(T, w, K, q, kind == 0, kind != 0, val, grad);
+      tab_operand<GDIM, BS>(kind, val, grad, r);
+      for (int k = 0; k < ncomp; ++k) out[(c * T.nq + q) * ncomp + k] = r[k];
+    }
+  }
+}
 
 extern "C" {
+
+// tables: phi [nq][nb], dphi [gdim][nq][nb], dpsi [gdim][gdim+1]; returns 0 or -1 (unsupported element)
+int hostcheck_tab(int gdim, int bs, int nb, int nq, int kind, const double* phi, const double* dphi, const double* dpsi,
+                  const int32_t* dofmap, const int32_t* x_dofmap, const double* x, const double* u, int64_t n_cells,
+                  double* out) {
+  tab_tables T{};
+  T.nb = nb, T.nq = nq, T.bs = bs, T.gdim = gdim, T.nv = gdim + 1;
+  for (int q = 0; q < nq; ++q)
+    for (int a = 0; a < nb; ++a) {
+      T.phi[q][a] = phi[q * nb + a];
+      for (int k = 0; k < gdim; ++k) T.dphi[k][q][a] = dphi[(k * nq + q) * nb + a];
+    }
+  for (int k = 0; k < gdim; ++k)
+    for (int v = 0; v < gdim + 1; ++v) T.dpsi[k][v] = dpsi[k * (gdim + 1) + v];
+  if (gdim == 2 && bs == 2 && nb == 6) tab_cells<2, 2, 6>(T, kind, dofmap, x_dofmap, x, u, n_cells, out);
+  else if (gdim == 2 && bs == 1 && nb == 3) tab_cells<2, 1, 3>(T, kind, dofmap, x_dofmap, x, u, n_cells, out);
+  else if (gdim == 2 && bs == 2 && nb == 3) tab_cells<2, 2, 3>(T, kind, dofmap, x_dofmap, x, u, n_cells, out);
+  else if (gdim == 3 && bs == 3 && nb == 4) tab_cells<3, 3, 4>(T, kind, dofmap, x_dofmap, x, u, n_cells, out);
+  else return -1;
+  return 0;
+}
 
 void hostcheck_mc(const mc_params_in* prm, const double* deps, const double* sigma_n, double* C_tang, double* sigma,
                   int32_t* niter, double* yielding, double* norm_res, double* dlambda, int64_t n) {
