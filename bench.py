@@ -37,7 +37,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BYTES_PER_QP = {"vm": 240, "heat": 88, "mc": 252}
+BYTES_PER_QP = {"vm": 240, "heat": 88, "mc": 252, "tab": 176.0 / 3.0, "fused": 235}
 METRIC = "quadrature points per second (stress + consistent tangent + internal state)"
 
 
@@ -137,6 +137,40 @@ def cpu_port_rate(model: str, sample_n: int, min_seconds: float, parallel: bool 
     return sample_n / best, cores, passes
 
 
+def cpu_tab_rate(model: str, min_seconds: float):
+    """CPU baseline for the tabulation legs: the NumPy oracle (einsum over all cells) on a bounded mesh."""
+    from dolfinx_external_operator_b200 import elements as el
+    from dolfinx_external_operator_b200 import synthetic as syn
+    from oracle import constitutive as oc
+    from oracle import native
+    from oracle import tabulation as ot
+
+    m = syn.triangle_mesh(400, 400, 2, jitter=0.2, seed=0)
+    phi, dphi = el.lagrange_triangle(2, el.triangle_quadrature(2))
+    dpsi = el.p1_geometry_derivatives(2)
+    u = syn.smooth_displacement(m["dof_coords"], scale=1.5e-3, seed=0).reshape(-1)
+    nq = 3 * m["dofmap"].shape[0]
+    _, sn, p = syn.vm_batch(nq, seed=0)
+
+    def fn():
+        e = ot.tabulate(ot.MANDEL_STRAIN, u, m["dofmap"], 2, m["x"], m["x_dofmap"], phi, dphi, dpsi)
+        if model == "fused":
+            native.vm_return_mapping(e.reshape(-1, 4), sn, p, oc.VonMisesParams(), parallel=True)
+
+    fn()
+    best, passes, t_all = float("inf"), 0, time.perf_counter()
+    while True:
+        t0 = time.perf_counter()
+        fn()
+        best = min(best, time.perf_counter() - t0)
+        passes += 1
+        if time.perf_counter() - t_all >= min_seconds and passes >= 3:
+            break
+    return {"value": nq / best, "unit": "QP/s", "cores": native.num_threads() if model == "fused" else 1, "kind": "port",
+            "sample": f"{nq} QPs x {passes} passes (best pass); NumPy einsum restatement of the DOLFINx/FFCx tabulation "
+                      "(single-threaded)" + (" + OpenMP C restatement of the von Mises kernel" if model == "fused" else "")}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -147,6 +181,16 @@ def run_reference_arm(args):
 
     native.build()
     cores = native.num_threads()
+    if args.model in ("tab", "fused"):
+        r = cpu_tab_rate(args.model, 5.0)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "QP/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": WORKLOADS[args.model]}, "cpu_baseline": r,
+                "e2e": {"value": r["value"], "unit": "QP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
     if args.model == "mc":
         sample = min(sample, 200_000)
         mprm = oc.MohrCoulombParams()
@@ -199,6 +243,10 @@ WORKLOADS = {
     "heat": "nonlinear heat flux q, dq/dT, dq/dsigma fused (BASELINE configs[0] callables at configs[4] batch size)",
     "mc": "Mohr-Coulomb return mapping with apex smoothing, local Newton + tangent through the iterations "
           "(BASELINE configs[2] callable at configs[4] batch size), demo stress-path family",
+    "tab": "operand tabulation: Mandel strain of a P2 vector field at 3 quadrature points per triangle "
+           "(evaluate_operands for the von Mises / Mohr-Coulomb demos), structured jittered mesh",
+    "fused": "operand tabulation fused with the von Mises return mapping (strain never stored), P2 vector field, "
+             "3 quadrature points per triangle",
 }
 
 
@@ -294,6 +342,33 @@ def run_gpu_arm(args):
         def step():
             ctx.check(ctx.lib.eo_mc_eval_scheme(ctx.handle, C.byref(prm), d_deps.ptr, d_sn.ptr, d_Ct.ptr, d_sig.ptr,
                                                 d_it.ptr, d_yl.ptr, d_nr.ptr, d_dl.ptr, n, scheme))
+    elif model in ("tab", "fused"):
+        from dolfinx_external_operator_b200 import elements as el
+
+        nxy = max(2, int(round((n / 6.0) ** 0.5)))
+        mesh = inputs.triangle_mesh(nxy, nxy, 2, jitter=0.2, seed=rank)
+        n_cells = mesh["dofmap"].shape[0]
+        n = 3 * n_cells  # quadrature points actually processed
+        phi, dphi = el.lagrange_triangle(2, el.triangle_quadrature(2))
+        tab = eo.Tabulator(dofmap=mesh["dofmap"], x_dofmap=mesh["x_dofmap"], x=mesh["x"], phi=phi, dphi=dphi, bs=2,
+                           n_dofs=mesh["n_dofs"], ctx=ctx)
+        d_u = ctx.to_device(inputs.smooth_displacement(mesh["dof_coords"], scale=1.5e-3, seed=rank).reshape(-1))
+        extra_cfg.update(n_cells=n_cells, n_dofs=mesh["n_dofs"], element="P2 vector triangle, 3-point rule")
+        del mesh
+        if model == "tab":
+            d_out = ctx.empty((n_cells, 3, 4))
+
+            def step():
+                tab.evaluate("mandel_strain", d_u, out=d_out)
+        else:
+            vm = eo.VonMises(n_qp=n, ctx=ctx)
+            _, sn_t, p_t = inputs.vm_batch(tile_n, seed=rank)
+            _tile_to_device(ctx, vm.sigma_n_dev, sn_t, n, 4)
+            _tile_to_device(ctx, vm.p_dev, p_t, n, 1)
+            d_Ct = ctx.empty((n * 16,))
+
+            def step():
+                tab.vm_fused(vm, d_u, C_tang=d_Ct)
     else:
         T_t, s_t = inputs.heat_batch(tile_n, seed=rank)
         d_T, d_s = ctx.empty((n,)), ctx.empty((n * 2,))
@@ -409,7 +484,9 @@ def run_gpu_arm(args):
 
     # ---- CPU baseline on this box's host cores (bounded sample)
     cpu = None
-    if args.cpu_seconds > 0:
+    if args.cpu_seconds > 0 and model in ("tab", "fused"):
+        cpu = cpu_tab_rate(model, args.cpu_seconds)
+    elif args.cpu_seconds > 0:
         sample = int(args.cpu_sample) if model != "mc" else min(int(args.cpu_sample), 200_000)
         rate, cores, passes = cpu_port_rate(model, sample, args.cpu_seconds, parallel=True)
         rate1, _, _ = cpu_port_rate(model, sample // 4, min(3.0, args.cpu_seconds), parallel=False)
@@ -450,7 +527,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--model", default="vm", choices=["vm", "heat", "mc"])
+    ap.add_argument("--model", default="vm", choices=["vm", "heat", "mc", "tab", "fused"])
     ap.add_argument("--mc-scheme", default="queue", choices=["queue", "simple"])
     ap.add_argument("--n", type=float, default=1e8, help="quadrature points per GPU (device-resident leg)")
     ap.add_argument("--e2e-n", type=float, default=1.5e7, help="quadrature points per GPU for the end-to-end leg")

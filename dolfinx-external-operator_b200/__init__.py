@@ -9,6 +9,7 @@ GPU-backed `external_function` factories (`VonMises`, `HeatConductivity`, `HeatF
 from ._lib import EOError, LIB_PATH  # noqa: F401
 from .context import Context, DeviceArray, default_context  # noqa: F401
 from .constitutive import HeatConductivity, HeatFlux, MohrCoulomb, VonMises  # noqa: F401
+from .isihara import Isihara, register_torch_op  # noqa: F401
 from .tabulation import Tabulator  # noqa: F401
 from .external_operator import (  # noqa: F401
     FEMExternalOperator,

@@ -50,6 +50,11 @@ class TabDesc(C.Structure):
                 ("phi", C.c_void_p), ("dphi", C.c_void_p), ("dpsi", C.c_void_p)]
 
 
+class IsiharaWeights(C.Structure):
+    _fields_ = [("A1", C.c_float * 4 * 64), ("S2", C.c_float * 4 * 64), ("W2", C.c_float * 64 * 64),
+                ("W2T", C.c_float * 64 * 64), ("w3", C.c_float * 64), ("s3", C.c_float * 4), ("H", C.c_double * 4)]
+
+
 class Stats(C.Structure):
     _fields_ = [
         ("n_points", C.c_int64),
@@ -107,6 +112,10 @@ PROTOTYPES = {
     "eo_tab_ncomp": (C.c_int, [_vp, C.c_int]),
     "eo_tabulate": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _vp]),
     "eo_tab_vm_fused": (C.c_int, [_vp, C.POINTER(VmParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "eo_isihara_create": (C.c_int, [_vp, C.POINTER(IsiharaWeights), C.POINTER(_vp)]),
+    "eo_isihara_destroy": (C.c_int, [_vp]),
+    "eo_isihara_set_correction": (C.c_int, [_vp, C.POINTER(C.c_double)]),
+    "eo_isihara_eval": (C.c_int, [_vp, _vp, _vp, _vp, _i64]),
     "eo_mc_eval": (C.c_int, [_vp, C.POINTER(McParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
     "eo_mc_eval_scheme": (C.c_int, [_vp, C.POINTER(McParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_int]),
 }

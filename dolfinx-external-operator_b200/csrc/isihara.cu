@@ -1,0 +1,118 @@
+// isihara.cu - Isihara ICNN hyperelastic model on sm_100a.
+// replaces: `vectorized_stress_and_tangent = vmap(jacfwd(compute_stress_local, has_aux=True))` and
+//           `dP_dF_impl`, doc/demo/demo_hyperelasticity.py:429-456 (network :242-307, corrections :362-381).
+// The per-point arithmetic is in isihara_core.cuh.  One thread per quadrature point; the preprocessed network
+// (isi_weights, 35 KB: the one remaining 64x64 layer in both orientations plus the collapsed layer 1) is staged
+// once per CTA in shared memory and read as warp-wide broadcasts (every lane needs the same weight at the
+// same time), so the inner loops are float32 FMA bound: ~21 k FMA per point in five 64x64 matrix-vector
+// products, the invariants and the chain rule back to F in float64.  Too small and irregular per point for
+// tensor cores (north_star) - and TF32 inputs would not keep the float32 parity of the reference network.
+#include "eo_common.cuh"
+#include "isihara_core.cuh"
+
+struct eo_isihara {
+  eo_ctx* ctx = nullptr;
+  isi_weights* d_w = nullptr;  // device copy
+  isi_weights h_w;
+};
+
+#define ISI_THREADS 128
+
+__global__ void __launch_bounds__(ISI_THREADS) isihara_kernel(const isi_weights* __restrict__ gw,
+                                                              const double* __restrict__ F, double* __restrict__ dP,
+                                                              double* __restrict__ P, int64_t n) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  isi_weights& W = *reinterpret_cast<isi_weights*>(s_raw);
+  {
+    const int nw = int(sizeof(isi_weights) / 16);
+    const float4* src = reinterpret_cast<const float4*>(gw);
+    float4* dst = reinterpret_cast<float4*>(s_raw);
+    for (int t = threadIdx.x; t < nw; t += blockDim.x) dst[t] = src[t];
+  }
+  __syncthreads();
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += stride) {
+    const eo_d4 f = eo_ld256(F + 4 * i);
+    const double Fv[4] = {f.x, f.y, f.z, f.w};
+    double Pv[4], T[16];
+    isi_point(W, Fv, Pv, T);
+    double* o = dP + 16 * i;
+    eo_st256(o + 0, T[0], T[1], T[2], T[3]);
+    eo_st256(o + 4, T[4], T[5], T[6], T[7]);
+    eo_st256(o + 8, T[8], T[9], T[10], T[11]);
+    eo_st256(o + 12, T[12], T[13], T[14], T[15]);
+    eo_st256(P + 4 * i, Pv[0], Pv[1], Pv[2], Pv[3]);
+  }
+}
+
+static bool g_isi_attr = false;
+
+extern "C" {
+
+int eo_isihara_create(eo_ctx* ctx, const eo_isihara_weights* w, eo_isihara** out) {
+  EO_REQUIRE(ctx, ctx != nullptr, "eo_isihara_create: ctx is NULL");
+  EO_REQUIRE(ctx, w && out, "eo_isihara_create: NULL argument");
+  static_assert(sizeof(eo_isihara_weights) == sizeof(isi_weights), "eo_isihara_weights must mirror isi_weights");
+  static_assert(sizeof(isi_weights) % 16 == 0, "isi_weights is copied in 16-byte pieces");
+  *out = nullptr;
+  EO_CUDA(ctx, cudaSetDevice(ctx->device));
+  eo_isihara* m = new eo_isihara();
+  m->ctx = ctx;
+  memcpy(&m->h_w, w, sizeof(isi_weights));
+  cudaError_t e = cudaMalloc(&m->d_w, sizeof(isi_weights));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(m->d_w, &m->h_w, sizeof(isi_weights), cudaMemcpyHostToDevice, ctx->s_cmp);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_cmp);
+  if (e == cudaSuccess && !g_isi_attr) {
+    e = cudaFuncSetAttribute(isihara_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(isi_weights));
+    g_isi_attr = e == cudaSuccess;
+  }
+  if (e != cudaSuccess) {
+    if (m->d_w) cudaFree(m->d_w);
+    delete m;
+    return eo_fail(ctx, e == cudaErrorMemoryAllocation ? EO_ERR_NOMEM : EO_ERR_CUDA, "eo_isihara_create: %s",
+                   cudaGetErrorString(e));
+  }
+  *out = m;
+  return EO_OK;
+}
+
+int eo_isihara_destroy(eo_isihara* m) {
+  if (!m) return EO_OK;
+  cudaSetDevice(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->s_cmp);
+  if (m->d_w) cudaFree(m->d_w);
+  delete m;
+  return EO_OK;
+}
+
+int eo_isihara_set_correction(eo_isihara* m, const double H_flat[4]) {
+  if (!m || !H_flat) return EO_ERR_INVALID;
+  eo_ctx* ctx = m->ctx;
+  for (int i = 0; i < 4; ++i) m->h_w.H[i] = H_flat[i];
+  EO_CUDA(ctx, cudaMemcpyAsync(m->d_w, &m->h_w, sizeof(isi_weights), cudaMemcpyHostToDevice, ctx->s_cmp));
+  EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_cmp));
+  return EO_OK;
+}
+
+int eo_isihara_eval(eo_isihara* m, const double* F, double* dP, double* P, int64_t n) {
+  if (!m) return EO_ERR_INVALID;
+  eo_ctx* ctx = m->ctx;
+  EO_REQUIRE(ctx, n >= 0, "eo_isihara_eval: n < 0");
+  if (n == 0) return EO_OK;
+  EO_REQUIRE(ctx, F && dP && P, "eo_isihara_eval: NULL array");
+  EO_CUDA(ctx, cudaSetDevice(ctx->device));
+  eo_arg args[3] = {{F, 32, false}, {dP, 128, true}, {P, 32, true}};
+  return eo_run_streamed(ctx, args, 3, n, [&](void** a, int64_t cnt, int64_t) {
+    for (int i = 0; i < 3; ++i)
+      if (!eo_aligned(a[i], 32)) return eo_fail(ctx, EO_ERR_INVALID, "eo_isihara_eval: arrays must be 32-byte aligned");
+    int64_t grid = (cnt + ISI_THREADS - 1) / ISI_THREADS;
+    const int64_t cap = int64_t(ctx->sm_count) * 6;  // persistent-ish: amortise the 35 KB weight staging
+    if (grid > cap) grid = cap;
+    isihara_kernel<<<(unsigned)grid, ISI_THREADS, sizeof(isi_weights), ctx->s_cmp>>>(m->d_w, (const double*)a[0],
+                                                                                      (double*)a[1], (double*)a[2], cnt);
+    ctx->launches += 1;
+    return (int)EO_OK;
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,233 @@
+// isihara_core.cuh - per-quadrature-point arithmetic of the Isihara input-convex neural network
+// hyperelastic model (reference: doc/demo/demo_hyperelasticity.py:242-307 network, :362-381 corrections,
+// :429-456 `compute_stress_local` / `dP_dF_impl`; citations ":NNN" are to that file).  Host/device header:
+// isihara.cu builds the sm_100a kernel from it, tests/hostcheck/ compiles it with g++ for CPU checks.
+//
+// What the reference computes:  W_NN(F) = ICNN(K1, K2, K3)(C = F^T F) with the network in float32 and the
+// invariants in the dtype of F (float64), P = dW_NN/dF + F @ H by `torch.func.grad`, tangent = dP/dF by
+// `jacfwd`, batched by `vmap`.  Written out here:
+//   * features x = (K1, K2, K3) and their first and second derivatives w.r.t. the four components of F are
+//     propagated in float64 with a 2nd-order Taylor jet (15 coefficients) - the reference's AD does the same
+//     arithmetic in float64 on that side of the `.float()` cast (:286);
+//   * the network  z0 = L0 x + b0 (no activation, :289) ; a1 = sp(W1)^T z0 + Skip1(x) ; z1 = softplus(a1)^2/12 ;
+//     a2 = sp(W2)^T z1 + Skip2(x) ; z2 = softplus(a2)^2/12 ; y = sp(W3)^T z2 + sp(Ws3)^T x  (:288-300)
+//     runs in float32.  Because z0 is affine in x, layer 1 collapses on the host to a1 = A1 x + c1
+//     (A1 = sp(W1)^T L0 + Skip1, 64x3), leaving ONE 64x64 layer.  Gradient and Hessian of y w.r.t. x:
+//       g_j = w3_j phi'(a2_j),  v = W2^T g,  d_j = da2_j/dx = sum_i W2_ji phi'(a1_i) A1_i + S2_j
+//       dy/dx   = s3 + S2^T g + A1^T (phi'(a1) . v)
+//       d2y/dx2 = sum_j w3_j phi''(a2_j) d_j d_j^T + sum_i v_i phi''(a1_i) A1_i A1_i^T
+//     i.e. five 64x64 matrix-vector products per point instead of differentiating twice through the graph;
+//   * chain rule back to F in float64, plus the constant corrections P += F @ H, tangent += H^T (:436-441).
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define EO_ISI_HD __host__ __device__ __forceinline__
+#else
+#define EO_ISI_HD inline
+#endif
+
+#define ISI_NH 64  // hidden width (n_hidden = [64, 64, 64], :304)
+
+// network constants after the host-side preprocessing (softplus of the convex weights applied once, :238)
+struct isi_weights {
+  float A1[ISI_NH][4];      // a1 = A1 x + c1: columns 0..2 = A1, column 3 = c1
+  float S2[ISI_NH][4];      // skip of layer 2: columns 0..2 = weight, column 3 = bias
+  float W2[ISI_NH][ISI_NH];   // softplus(layers.2.weights): a2_j = sum_i W2[j][i] z1_i + ...
+  float W2T[ISI_NH][ISI_NH];  // its transpose (v_i = sum_j W2T[i][j] g_j)
+  float w3[ISI_NH];         // softplus(layers.3.weights)
+  float s3[4];              // softplus(skip_layers.3.weights), padded
+  double H[4];              // H_flat = -dW_NN/dF at F = I (:367)
+};
+
+// softplus and the activation phi(a) = softplus(a)^2 / 12 with its first two derivatives, float32
+EO_ISI_HD void isi_phi(float a, float& p0, float& p1, float& p2) {
+  // torch.nn.functional.softplus: log1p(exp(a)), linear above the threshold 20
+  float sp, sg;
+  if (a > 20.0f) {
+    sp = a;
+    sg = 1.0f;
+  } else {
+    const float e = expf(a);
+    sp = log1pf(e);
+    sg = e / (1.0f + e);  // sigmoid = d softplus / da
+  }
+  const float sg1 = sg * (1.0f - sg);  // d sigmoid / da
+  p0 = sp * sp * (1.0f / 12.0f);
+  p1 = sp * sg * (1.0f / 6.0f);
+  p2 = (sg * sg + sp * sg1) * (1.0f / 6.0f);
+}
+
+// y(x), dy/dx (3), d2y/dx2 (6: xx, xy, xz, yy, yz, zz) of the network, float32.
+// `W` may live in shared memory (device) or anywhere (host).
+EO_ISI_HD void isi_network(const isi_weights& W, const float x[3], float& y, float gx[3], float hx[6]) {
+  float g[ISI_NH];  // g_j = w3_j phi'(a2_j)
+  float yy = W.s3[0] * x[0] + W.s3[1] * x[1] + W.s3[2] * x[2];
+  float G0 = W.s3[0], G1 = W.s3[1], G2 = W.s3[2];
+  float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f, h4 = 0.f, h5 = 0.f;
+  // ---- pass A: a2_j and d_j = da2_j/dx for blocks of 16 outputs; layer-1 activations recomputed per block
+#pragma unroll 1
+  for (int jb = 0; jb < ISI_NH; jb += 16) {
+    float acc[16][4];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      acc[j][0] = W.S2[jb + j][0] * x[0] + W.S2[jb + j][1] * x[1] + W.S2[jb + j][2] * x[2] + W.S2[jb + j][3];
+      acc[j][1] = W.S2[jb + j][0];
+      acc[j][2] = W.S2[jb + j][1];
+      acc[j][3] = W.S2[jb + j][2];
+    }
+#pragma unroll 2
+    for (int i = 0; i < ISI_NH; ++i) {
+      const float a1 = W.A1[i][0] * x[0] + W.A1[i][1] * x[1] + W.A1[i][2] * x[2] + W.A1[i][3];
+      float p0, p1, p2;
+      isi_phi(a1, p0, p1, p2);
+      const float z0 = p0, z1 = p1 * W.A1[i][0], z2 = p1 * W.A1[i][1], z3 = p1 * W.A1[i][2];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float w = W.W2[jb + j][i];
+        acc[j][0] += w * z0;
+        acc[j][1] += w * z1;
+        acc[j][2] += w * z2;
+        acc[j][3] += w * z3;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float p0, p1, p2;
+      isi_phi(acc[j][0], p0, p1, p2);
+      const float w3 = W.w3[jb + j];
+      yy += w3 * p0;
+      const float gj = w3 * p1;
+      g[jb + j] = gj;
+      G0 += W.S2[jb + j][0] * gj, G1 += W.S2[jb + j][1] * gj, G2 += W.S2[jb + j][2] * gj;
+      const float c = w3 * p2, d0 = acc[j][1], d1 = acc[j][2], d2 = acc[j][3];
+      h0 += c * d0 * d0, h1 += c * d0 * d1, h2 += c * d0 * d2, h3 += c * d1 * d1, h4 += c * d1 * d2, h5 += c * d2 * d2;
+    }
+  }
+  // ---- pass B: v = W2^T g, then the layer-1 contributions
+#pragma unroll 2
+  for (int i = 0; i < ISI_NH; ++i) {
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < ISI_NH; ++j) v += W.W2T[i][j] * g[j];
+    const float a1 = W.A1[i][0] * x[0] + W.A1[i][1] * x[1] + W.A1[i][2] * x[2] + W.A1[i][3];
+    float p0, p1, p2;
+    isi_phi(a1, p0, p1, p2);
+    const float A0 = W.A1[i][0], A1 = W.A1[i][1], A2 = W.A1[i][2];
+    const float t1 = p1 * v, t2 = p2 * v;
+    G0 += A0 * t1, G1 += A1 * t1, G2 += A2 * t1;
+    h0 += t2 * A0 * A0, h1 += t2 * A0 * A1, h2 += t2 * A0 * A2, h3 += t2 * A1 * A1, h4 += t2 * A1 * A2, h5 += t2 * A2 * A2;
+  }
+  y = yy;
+  gx[0] = G0, gx[1] = G1, gx[2] = G2;
+  hx[0] = h0, hx[1] = h1, hx[2] = h2, hx[3] = h3, hx[4] = h4, hx[5] = h5;
+}
+
+// ------------------------------------------------------------------------------------------------
+// float64 2nd-order Taylor jets in the four components of F: value, gradient (4), Hessian (10, i <= j)
+// ------------------------------------------------------------------------------------------------
+#define ISI_SYM(i, j) ((i) <= (j) ? ((i) * (7 - (i)) / 2 + (j)) : ((j) * (7 - (j)) / 2 + (i)))
+
+struct isi_jet {
+  double v, g[4], h[10];
+};
+
+EO_ISI_HD isi_jet isi_var(double val, int k) {
+  isi_jet r;
+  r.v = val;
+  for (int i = 0; i < 4; ++i) r.g[i] = (i == k) ? 1.0 : 0.0;
+  for (int i = 0; i < 10; ++i) r.h[i] = 0.0;
+  return r;
+}
+EO_ISI_HD isi_jet isi_add(const isi_jet& a, const isi_jet& b, double sb = 1.0) {
+  isi_jet r;
+  r.v = a.v + sb * b.v;
+  for (int i = 0; i < 4; ++i) r.g[i] = a.g[i] + sb * b.g[i];
+  for (int i = 0; i < 10; ++i) r.h[i] = a.h[i] + sb * b.h[i];
+  return r;
+}
+EO_ISI_HD isi_jet isi_addc(const isi_jet& a, double c) {
+  isi_jet r = a;
+  r.v += c;
+  return r;
+}
+EO_ISI_HD isi_jet isi_mul(const isi_jet& a, const isi_jet& b) {
+  isi_jet r;
+  r.v = a.v * b.v;
+  for (int i = 0; i < 4; ++i) r.g[i] = a.g[i] * b.v + a.v * b.g[i];
+  for (int i = 0; i < 4; ++i)
+    for (int j = i; j < 4; ++j)
+      r.h[ISI_SYM(i, j)] = a.h[ISI_SYM(i, j)] * b.v + a.v * b.h[ISI_SYM(i, j)] + a.g[i] * b.g[j] + a.g[j] * b.g[i];
+  return r;
+}
+// f(u) with f0 = f(u.v), f1 = f'(u.v), f2 = f''(u.v)
+EO_ISI_HD isi_jet isi_compose(const isi_jet& u, double f0, double f1, double f2) {
+  isi_jet r;
+  r.v = f0;
+  for (int i = 0; i < 4; ++i) r.g[i] = f1 * u.g[i];
+  for (int i = 0; i < 4; ++i)
+    for (int j = i; j < 4; ++j) r.h[ISI_SYM(i, j)] = f2 * u.g[i] * u.g[j] + f1 * u.h[ISI_SYM(i, j)];
+  return r;
+}
+EO_ISI_HD isi_jet isi_pow(const isi_jet& u, double p) {
+  const double f0 = pow(u.v, p);
+  return isi_compose(u, f0, p * f0 / u.v, p * (p - 1.0) * f0 / (u.v * u.v));
+}
+
+// One point: F = [F11, F12, F21, F22] (:263-266)  ->  P (4), tangent dP_i/dF_j (row-major 4x4)
+EO_ISI_HD void isi_point(const isi_weights& W, const double F[4], double P[4], double dP[16]) {
+  const isi_jet F11 = isi_var(F[0], 0), F12 = isi_var(F[1], 1), F21 = isi_var(F[2], 2), F22 = isi_var(F[3], 3);
+  // right Cauchy-Green tensor and invariants (:269-277)
+  const isi_jet C11 = isi_add(isi_mul(F11, F11), isi_mul(F21, F21));
+  const isi_jet C12 = isi_add(isi_mul(F11, F12), isi_mul(F21, F22));
+  const isi_jet C22 = isi_add(isi_mul(F12, F12), isi_mul(F22, F22));
+  const isi_jet C1221 = isi_mul(C12, C12);
+  const isi_jet C1122 = isi_mul(C11, C22);
+  const isi_jet I1 = isi_addc(isi_add(C11, C22), 1.0);
+  const isi_jet I2 = isi_add(isi_add(isi_add(C11, C22), C1221, -1.0), C1122);
+  const isi_jet I3 = isi_add(C1122, C1221, -1.0);
+  // features (:280-283)
+  isi_jet X[3];
+  X[0] = isi_addc(isi_mul(I1, isi_pow(I3, -1.0 / 3.0)), -3.0);
+  X[1] = isi_addc(isi_mul(I2, isi_pow(I3, -2.0 / 3.0)), -3.0);
+  {
+    const isi_jet J = isi_pow(I3, 0.5);
+    const isi_jet Jm1 = isi_addc(J, -1.0);
+    X[2] = isi_mul(Jm1, Jm1);
+  }
+  // network in float32 (:286)
+  const float x[3] = {(float)X[0].v, (float)X[1].v, (float)X[2].v};
+  float y, gx[3], hx[6];
+  isi_network(W, x, y, gx, hx);
+  const double Wx[3] = {(double)gx[0], (double)gx[1], (double)gx[2]};
+  const double Wxx[3][3] = {{(double)hx[0], (double)hx[1], (double)hx[2]},
+                            {(double)hx[1], (double)hx[3], (double)hx[4]},
+                            {(double)hx[2], (double)hx[4], (double)hx[5]}};
+  // chain rule to F, then the corrections P += F @ H, dP += H^T with H the 4x4 block matrix of :368-376
+  for (int i = 0; i < 4; ++i) {
+    double acc = 0.0;
+    for (int k = 0; k < 3; ++k) acc += Wx[k] * X[k].g[i];
+    P[i] = acc;
+  }
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      double acc = 0.0;
+      for (int k = 0; k < 3; ++k) {
+        acc += Wx[k] * X[k].h[ISI_SYM(i, j)];
+        for (int l = 0; l < 3; ++l) acc += Wxx[k][l] * X[k].g[i] * X[l].g[j];
+      }
+      dP[4 * i + j] = acc;
+    }
+  const double h0 = W.H[0], h1 = W.H[1], h2 = W.H[2], h3 = W.H[3];
+  // Hm = [[h0,h1,0,0],[h2,h3,0,0],[0,0,h0,h1],[0,0,h2,h3]];  P_j += sum_i F_i Hm[i][j];  dP[j][i] += Hm[i][j]
+  P[0] += F[0] * h0 + F[1] * h2;
+  P[1] += F[0] * h1 + F[1] * h3;
+  P[2] += F[2] * h0 + F[3] * h2;
+  P[3] += F[2] * h1 + F[3] * h3;
+  dP[4 * 0 + 0] += h0, dP[4 * 0 + 1] += h2;
+  dP[4 * 1 + 0] += h1, dP[4 * 1 + 1] += h3;
+  dP[4 * 2 + 2] += h0, dP[4 * 2 + 3] += h2;
+  dP[4 * 3 + 2] += h1, dP[4 * 3 + 3] += h3;
+}

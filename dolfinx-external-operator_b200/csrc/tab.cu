@@ -85,54 +85,78 @@ __global__ void __launch_bounds__(128) tab_kernel(const __grid_constant__ tab_ta
   }
 }
 
-// tabulate the Mandel strain and feed it to the von Mises radial return, point by point
-template <int NB>
-__global__ void __launch_bounds__(128) tab_vm_kernel(const __grid_constant__ tab_tables T, const vm_consts vq,
+// tabulate the Mandel strain and feed it to the von Mises radial return.
+// Mapping: one thread per QUADRATURE POINT (cell = i / nq), so that the per-point streams (history in, tangent /
+// stress / dp out) are accessed exactly like in vm_kernel - consecutive threads, consecutive 32-byte records.
+// The nq threads of a cell gather the same coefficients (same sectors: one L1 request) and each contracts them
+// with the derivative-table row of its own point, staged in shared memory (the row index is not warp uniform,
+// which the constant bank would serialise).
+template <int NB, int NQ>  // NQ > 0: evaluation points per cell known at compile time (cheap index split)
+__global__ void __launch_bounds__(256, 4) tab_vm_kernel(const __grid_constant__ tab_tables T, const vm_consts vq,
                                                      const int32_t* __restrict__ dofmap,
                                                      const int32_t* __restrict__ x_dofmap, const double* __restrict__ x,
-                                                     const double* __restrict__ u, int64_t n_cells,
+                                                     const double* __restrict__ u, int64_t n_points,
                                                      const double* __restrict__ sigma_n, const double* __restrict__ p,
                                                      double* __restrict__ C_tang, double* __restrict__ sigma,
                                                      double* __restrict__ dp_out, double* __restrict__ strain_out,
                                                      eo_stats* stats) {
-  const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  __shared__ double s_dphi[EO_TAB_MAX_NQ][2][NB];
+  for (int t = threadIdx.x; t < T.nq * 2 * NB; t += blockDim.x) {
+    const int q = t / (2 * NB), k = (t / NB) % 2, a = t % NB;
+    s_dphi[q][k][a] = T.dphi[k][q][a];
+  }
+  __syncthreads();
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   int plastic = 0;
-  if (c < n_cells) {
+  if (i < n_points) {
+    int64_t c;
+    int q;
+    if (NQ > 0) {
+      c = i / NQ;
+      q = int(i - c * NQ);
+    } else if (i < 2147483647LL) {
+      const unsigned ci = unsigned(i) / unsigned(T.nq);
+      c = ci;
+      q = int(unsigned(i) - ci * unsigned(T.nq));
+    } else {
+      c = i / T.nq;
+      q = int(i - c * T.nq);
+    }
+    // history first: these loads are in flight while the gather and the contraction run
+    const eo_d4 s = eo_ld256(sigma_n + 4 * i);
+    const double pi = eo_ld64(p + i);
     double w[NB][2], K[2][2];
     tab_load_cell<2, 2, NB>(T, dofmap, x_dofmap, x, u, c, w, K);
-    for (int q = 0; q < T.nq; ++q) {
-      const int64_t i = c * T.nq + q;
-      double val[2], grad[2][2], e[4];
-      tab_point<2, 2, NB>(T, w, K, q, false, true, val, grad);
-      tab_operand<2, 2>(2, val, grad, e);
-      const eo_d4 s = eo_ld256(sigma_n + 4 * i);
-      const double pi = eo_ld64(p + i);
-      vm_point_out o;
-      vm_point(vq, e[0], e[1], e[2], e[3], s.x, s.y, s.z, s.w, pi, o);
-      plastic += o.dp > 0.0;
-      double* Ct = C_tang + 16 * i;
-      eo_st256(Ct + 0, o.C[0], o.C[1], o.C[2], o.C[3]);
-      eo_st256(Ct + 4, o.C[4], o.C[5], o.C[6], o.C[7]);
-      eo_st256(Ct + 8, o.C[8], o.C[9], o.C[10], o.C[11]);
-      eo_st256(Ct + 12, o.C[12], o.C[13], o.C[14], o.C[15]);
-      eo_st256(sigma + 4 * i, o.g[0], o.g[1], o.g[2], o.g[3]);
-      eo_st64(dp_out + i, o.dp);
-      if (strain_out) eo_st256(strain_out + 4 * i, e[0], e[1], e[2], e[3]);
-    }
-  }
-  // block-wide count of plastic points, one atomic per CTA
-  __shared__ int s_cnt;
-  if (threadIdx.x == 0) s_cnt = 0;
-  __syncthreads();
+    double G[2][2], grad[2][2], val[2] = {0.0, 0.0}, e[4];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) plastic += __shfl_xor_sync(0xffffffffu, plastic, o);
-  if ((threadIdx.x & 31) == 0 && plastic) atomicAdd(&s_cnt, plastic);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    if (s_cnt) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_plastic), (unsigned long long)s_cnt);
-    if (blockIdx.x == 0)
-      atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_points), (unsigned long long)(n_cells * T.nq));
+    for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        double acc = 0.0;
+#pragma unroll
+        for (int a = 0; a < NB; ++a) acc += w[a][cc] * s_dphi[q][k][a];
+        G[cc][k] = acc;
+      }
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) grad[cc][j] = G[cc][0] * K[0][j] + G[cc][1] * K[1][j];
+    tab_operand<2, 2>(2, val, grad, e);
+    vm_point_out o;
+    vm_point(vq, e[0], e[1], e[2], e[3], s.x, s.y, s.z, s.w, pi, o);
+    plastic = o.dp > 0.0;
+    double* Ct = C_tang + 16 * i;
+    eo_st256(Ct + 0, o.C[0], o.C[1], o.C[2], o.C[3]);
+    eo_st256(Ct + 4, o.C[4], o.C[5], o.C[6], o.C[7]);
+    eo_st256(Ct + 8, o.C[8], o.C[9], o.C[10], o.C[11]);
+    eo_st256(Ct + 12, o.C[12], o.C[13], o.C[14], o.C[15]);
+    eo_st256(sigma + 4 * i, o.g[0], o.g[1], o.g[2], o.g[3]);
+    eo_st64(dp_out + i, o.dp);
+    if (strain_out) eo_st256(strain_out + 4 * i, e[0], e[1], e[2], e[3]);
   }
+  eo_block_count_add(reinterpret_cast<unsigned long long*>(&stats->n_plastic), plastic);
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_points), (unsigned long long)n_points);
 }
 
 template <int GDIM, int BS, int NB>
@@ -319,11 +343,17 @@ int eo_tab_vm_fused(eo_tab* t, const eo_vm_params* prm, const double* u, const d
   int rc = tab_stage_u(t, u, &d_u);
   if (rc != EO_OK) return rc;
   const vm_consts q{prm->lmbda, prm->mu, prm->H, prm->sigma_0};
-  const unsigned grid = (unsigned)((t->n_cells + 127) / 128);
-#define EO_FUSED_CASE(N)                                                                                              \
-  if (t->T.nb == N)                                                                                                   \
-    tab_vm_kernel<N><<<grid, 128, 0, ctx->s_cmp>>>(t->T, q, t->dofmap, t->x_dofmap, t->x, d_u, t->n_cells, sigma_n, p, \
-                                                   C_tang, sigma, dp, strain, ctx->stats);
+  const int64_t n_points = t->n_cells * t->T.nq;
+  const unsigned grid = (unsigned)((n_points + 255) / 256);
+#define EO_FUSED_CASE(N)                                                                                                   \
+  if (t->T.nb == N) {                                                                                                      \
+    if (t->T.nq == 3)                                                                                                      \
+      tab_vm_kernel<N, 3><<<grid, 256, 0, ctx->s_cmp>>>(t->T, q, t->dofmap, t->x_dofmap, t->x, d_u, n_points, sigma_n, p, \
+                                                        C_tang, sigma, dp, strain, ctx->stats);                           \
+    else                                                                                                                   \
+      tab_vm_kernel<N, 0><<<grid, 256, 0, ctx->s_cmp>>>(t->T, q, t->dofmap, t->x_dofmap, t->x, d_u, n_points, sigma_n, p, \
+                                                        C_tang, sigma, dp, strain, ctx->stats);                           \
+  }
   EO_FUSED_CASE(3)
   EO_FUSED_CASE(6)
   EO_FUSED_CASE(10)

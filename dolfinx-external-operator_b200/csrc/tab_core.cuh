@@ -36,25 +36,25 @@ struct tab_tables {
 template <int GDIM>
 EO_TAB_HD void tab_inverse(const double J[GDIM][GDIM], double K[GDIM][GDIM]) {
   if constexpr (GDIM == 2) {
-    const double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
-    K[0][0] = J[1][1] / det;
-    K[0][1] = -J[0][1] / det;
-    K[1][0] = -J[1][0] / det;
-    K[1][1] = J[0][0] / det;
+    const double idet = 1.0 / (J[0][0] * J[1][1] - J[0][1] * J[1][0]);
+    K[0][0] = J[1][1] * idet;
+    K[0][1] = -J[0][1] * idet;
+    K[1][0] = -J[1][0] * idet;
+    K[1][1] = J[0][0] * idet;
   } else {
     const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
     const double c10 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
     const double c20 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
-    const double det = J[0][0] * c00 + J[0][1] * c10 + J[0][2] * c20;
-    K[0][0] = c00 / det;
-    K[1][0] = c10 / det;
-    K[2][0] = c20 / det;
-    K[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / det;
-    K[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det;
-    K[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det;
-    K[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
-    K[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
-    K[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+    const double idet = 1.0 / (J[0][0] * c00 + J[0][1] * c10 + J[0][2] * c20);
+    K[0][0] = c00 * idet;
+    K[1][0] = c10 * idet;
+    K[2][0] = c20 * idet;
+    K[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * idet;
+    K[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * idet;
+    K[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * idet;
+    K[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * idet;
+    K[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * idet;
+    K[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * idet;
   }
 }
 

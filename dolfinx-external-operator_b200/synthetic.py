@@ -25,6 +25,15 @@ def heat_batch(n: int, seed: int = 0):
     return rng.uniform(0.0, 2.0, n), rng.normal(0.0, 1.0, (n, 2))
 
 
+def isihara_batch(n: int, seed: int = 0):
+    """Deformation gradients F = I + N(0, 0.05) (det F > 0), flat [F11, F12, F21, F22]."""
+    rng = np.random.default_rng(seed)
+    F = rng.normal(0.0, 0.05, (n, 4))
+    F[:, 0] += 1.0
+    F[:, 3] += 1.0
+    return F
+
+
 # ----------------------------------------------------------------------------- Mohr-Coulomb
 MC_E, MC_NU = 6778.0, 0.25  # demo_plasticity_mohr_coulomb.py:110-111
 

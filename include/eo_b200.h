@@ -249,6 +249,33 @@ int eo_mc_eval_scheme(eo_ctx* ctx, const eo_mc_params* prm, const double* deps, 
                       double* C_tang, double* sigma, int32_t* niter, double* yielding, double* norm_res,
                       double* dlambda, int64_t n, int scheme);
 
+/* ---------------------------------------------------------------- Isihara ICNN hyperelasticity
+ * replaces: `vectorized_stress_and_tangent` / `dP_dF_impl`, doc/demo/demo_hyperelasticity.py:429-456
+ *           (network :242-307 with the state dict Isihara_noise=high.pth, corrections :362-381).
+ * The network constants are passed PREPROCESSED (what the Python host side computes once from the state dict:
+ * softplus applied to the convex weights, :238; layer 1 collapsed onto the affine layer 0):
+ *   a1 = A1 x + c1           A1 = softplus(layers.1.weights) @ layers.0.weight + skip_layers.1.weight   [64][3]
+ *                            c1 = softplus(layers.1.weights) @ layers.0.bias   + skip_layers.1.bias     [64]
+ *   a2 = W2 phi(a1) + S2 x + b2,  y = w3 . phi(a2) + s3 . x,  phi(a) = softplus(a)^2 / 12   (float32, :286-300) */
+typedef struct eo_isihara_weights {
+  float A1[64][4];  /* columns 0..2 = A1, column 3 = c1 */
+  float S2[64][4];  /* columns 0..2 = skip_layers.2.weight, column 3 = skip_layers.2.bias */
+  float W2[64][64]; /* softplus(layers.2.weights), [out][in] */
+  float W2T[64][64];
+  float w3[64];     /* softplus(layers.3.weights) */
+  float s3[4];      /* softplus(skip_layers.3.weights), padded */
+  double H[4];      /* H_flat = -dW_NN/dF at F = I (:362-367); see eo_isihara_set_correction */
+} eo_isihara_weights;
+
+typedef struct eo_isihara eo_isihara;
+int eo_isihara_create(eo_ctx* ctx, const eo_isihara_weights* w, eo_isihara** out);
+int eo_isihara_destroy(eo_isihara* m);
+/* Replace the stress correction H_flat (e.g. by -P_NN(F = I) evaluated with this library and H = 0). */
+int eo_isihara_set_correction(eo_isihara* m, const double H_flat[4]);
+/* F [n][4] = [F11, F12, F21, F22] (:263-266)  ->  dP [n][4][4] (dP_i/dF_j), P [n][4]; float64 in and out,
+ * network arithmetic in float32 like the reference (results are float32-accurate).  Any-side pointers. */
+int eo_isihara_eval(eo_isihara* m, const double* F, double* dP, double* P, int64_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,23 @@ def gen_heat():
     print("heat golden written")
 
 
+def gen_isihara():
+    """Isihara ICNN golden: the reference's own torch code (demo_hyperelasticity.py:221-315, 362-381, 429-456)
+    with the shipped Isihara_noise=high.pth, eager (no torch.compile).  The state dict travels with the golden so
+    that the GPU box (no /root/reference) can build the model."""
+    import torch
+
+    ns = ref_exec.load_isihara()
+    n = 2049
+    F = inputs.isihara_batch(n, seed=0)
+    F[0] = [1.0, 0.0, 0.0, 1.0]  # the undeformed state: P = 0 by construction (:362-381)
+    dP, P = ns["dP_dF_impl"](F)
+    sd = {k: v.numpy() for k, v in ns["model"].state_dict().items()}
+    np.savez_compressed(os.path.join(GOLDEN, "isihara_seed0_n2049.npz"), F=F, dP=dP.reshape(n, 4, 4), P=P.reshape(n, 4),
+                        H_flat=ns["H_flat"].numpy().astype(np.float64), **{"sd/" + k: v for k, v in sd.items()})
+    print("isihara golden written; |P(F=I)| =", float(np.abs(P.reshape(n, 4)[0]).max()))
+
+
 _MC_NS = None
 
 

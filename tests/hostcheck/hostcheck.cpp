@@ -4,6 +4,7 @@
 
 #include "mc_core.cuh"
 #include "tab_core.cuh"
+#include "isihara_core.cuh"
 
 template <int GDIM, int BS, int NB>
 static void tab_cells(const tab_tables& T, int kind, const int32_t* dofmap, const int32_t* x_dofmap, const double* x,
@@ -26,6 +27,11 @@ static void tab_cells(const tab_tables& T, int kind, const int32_t* dofmap, cons
 }
 
 extern "C" {
+
+void hostcheck_isihara(const isi_weights* w, const double* F, double* dP, double* P, int64_t n) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) isi_point(*w, F + 4 * i, P + 4 * i, dP + 16 * i);
+}
 
 // tables: phi [nq][nb], dphi [gdim][nq][nb], dpsi [gdim][gdim+1]; returns 0 or -1 (unsupported element)
 int hostcheck_tab(int gdim, int bs, int nb, int nq, int kind, const double* phi, const double* dphi, const double* dpsi,
