@@ -37,7 +37,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BYTES_PER_QP = {"vm": 240, "heat": 88, "mc": 252, "tab": 176.0 / 3.0, "fused": 235}
+BYTES_PER_QP = {"vm": 240, "heat": 88, "mc": 252, "tab": 176.0 / 3.0, "fused": 235, "isihara": 192}
 METRIC = "quadrature points per second (stress + consistent tangent + internal state)"
 
 
@@ -108,6 +108,7 @@ def cpu_port_rate(model: str, sample_n: int, min_seconds: float, parallel: bool 
     from oracle import inputs, native
 
     native.build()
+    native.use_all_cores()
     cores = native.num_threads() if parallel else 1
     if model == "vm":
         deps, sigma_n, p = inputs.vm_batch(sample_n, seed=0)
@@ -145,6 +146,7 @@ def cpu_tab_rate(model: str, min_seconds: float):
     from oracle import native
     from oracle import tabulation as ot
 
+    native.use_all_cores()
     m = syn.triangle_mesh(400, 400, 2, jitter=0.2, seed=0)
     phi, dphi = el.lagrange_triangle(2, el.triangle_quadrature(2))
     dpsi = el.p1_geometry_derivatives(2)
@@ -180,6 +182,7 @@ def run_reference_arm(args):
     from oracle import inputs, native
 
     native.build()
+    native.use_all_cores()
     cores = native.num_threads()
     if args.model in ("tab", "fused"):
         r = cpu_tab_rate(args.model, 5.0)
@@ -243,6 +246,8 @@ WORKLOADS = {
     "heat": "nonlinear heat flux q, dq/dT, dq/dsigma fused (BASELINE configs[0] callables at configs[4] batch size)",
     "mc": "Mohr-Coulomb return mapping with apex smoothing, local Newton + tangent through the iterations "
           "(BASELINE configs[2] callable at configs[4] batch size), demo stress-path family",
+    "isihara": "Isihara ICNN hyperelasticity (BASELINE configs[3] callable at configs[4] batch size): stress P and "
+               "tangent dP/dF from the 3-64-64-64-1 float32 network, float64 invariants",
     "tab": "operand tabulation: Mandel strain of a P2 vector field at 3 quadrature points per triangle "
            "(evaluate_operands for the von Mises / Mohr-Coulomb demos), structured jittered mesh",
     "fused": "operand tabulation fused with the von Mises return mapping (strain never stored), P2 vector field, "
@@ -342,6 +347,17 @@ def run_gpu_arm(args):
         def step():
             ctx.check(ctx.lib.eo_mc_eval_scheme(ctx.handle, C.byref(prm), d_deps.ptr, d_sn.ptr, d_Ct.ptr, d_sig.ptr,
                                                 d_it.ptr, d_yl.ptr, d_nr.ptr, d_dl.ptr, n, scheme))
+    elif model == "isihara":
+        gpath = os.path.join(ROOT, "tests", "golden", "isihara_seed0_n2049.npz")  # carries the reference's state dict
+        g = np.load(gpath)
+        isi = eo.Isihara({k[3:]: g[k] for k in g.files if k.startswith("sd/")}, ctx=ctx)
+        F_t = inputs.isihara_batch(tile_n, seed=rank)
+        d_F = ctx.empty((n * 4,))
+        _tile_to_device(ctx, d_F, F_t, n, 4)
+        d_dP, d_P = ctx.empty((n * 16,)), ctx.empty((n * 4,))
+
+        def step():
+            isi.eval_device(d_F, d_dP, d_P)
     elif model in ("tab", "fused"):
         from dolfinx_external_operator_b200 import elements as el
 
@@ -367,8 +383,10 @@ def run_gpu_arm(args):
             _tile_to_device(ctx, vm.p_dev, p_t, n, 1)
             d_Ct = ctx.empty((n * 16,))
 
+            extra_cfg["vm_arithmetic"] = "exact" if args.fused_exact else "fast (2 divisions, FMA; identical flags)"
+
             def step():
-                tab.vm_fused(vm, d_u, C_tang=d_Ct)
+                tab.vm_fused(vm, d_u, C_tang=d_Ct, exact=args.fused_exact)
     else:
         T_t, s_t = inputs.heat_batch(tile_n, seed=rank)
         d_T, d_s = ctx.empty((n,)), ctx.empty((n * 2,))
@@ -416,6 +434,22 @@ def run_gpu_arm(args):
 
     # ---- end-to-end through the public callable (host buffers)
     e2e = None
+    if model == "isihara" and args.e2e_n > 0:
+        ne = int(min(args.e2e_n, n))
+        F_h = ctx.pinned_empty((ne, 1, 2, 2))
+        F_h.reshape(-1, 4)[:] = np.resize(F_t, (ne, 4))
+        call = isi((1,))
+        Ke = max(2, min(K, 5))
+        for _ in range(2):
+            out = call(F_h)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            out = call(F_h)
+        ctx.sync()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": world * ne * Ke / dt, "unit": "QP/s", "h2d_bytes_per_step": 32 * ne, "d2h_bytes_per_step": 160 * ne,
+               "qp_per_step_per_gpu": ne, "steps": Ke, "api": "Isihara((1,))(F) == external_function(derivatives)(*operands)"}
     if model in ("vm", "mc") and args.e2e_n > 0:
         ne = int(args.e2e_n)
         deps_h = ctx.pinned_empty((ne, 1, 4))  # (n_cells, n_points, 4), the operand shape of demo_vm:344
@@ -477,6 +511,16 @@ def run_gpu_arm(args):
                     "fp64_flops_per_qp": flops_per_qp, "kernel_ms": k_ms,
                     "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                             "bytes_per_qp": BYTES_PER_QP[model]}}
+    elif model == "isihara":
+        # float32 CUDA-core bound: ~21 k FMA per point in five 64x64 matrix-vector products (isihara_core.cuh)
+        fma_per_qp = 5 * 64 * 64 + 64 * 16
+        ach = 2.0 * fma_per_qp * n / (k_ms * 1e-3) / 1e12
+        f32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+        roofline = {"bound": "fp32", "achieved": ach, "peak": f32_peak, "unit": "TFLOP/s", "frac": ach / f32_peak,
+                    "traffic": traffic, "peak_source": "nominal: 148 SM x 128 FMA/clk x 2 x 1.965 GHz (no measured f32 figure)",
+                    "fma_per_qp": fma_per_qp, "kernel_ms": k_ms,
+                    "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                            "bytes_per_qp": BYTES_PER_QP[model]}}
     else:
         roofline = {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                     "frac": hbm_achieved / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
@@ -484,7 +528,10 @@ def run_gpu_arm(args):
 
     # ---- CPU baseline on this box's host cores (bounded sample)
     cpu = None
-    if args.cpu_seconds > 0 and model in ("tab", "fused"):
+    if model == "isihara":
+        cpu = None  # the CPU implementation is the reference's torch code, which needs /root/reference: timed in the
+        #             build container only (69 k QP/s on 8 threads)
+    elif args.cpu_seconds > 0 and model in ("tab", "fused"):
         cpu = cpu_tab_rate(model, args.cpu_seconds)
     elif args.cpu_seconds > 0:
         sample = int(args.cpu_sample) if model != "mc" else min(int(args.cpu_sample), 200_000)
@@ -527,7 +574,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--model", default="vm", choices=["vm", "heat", "mc", "tab", "fused"])
+    ap.add_argument("--model", default="vm", choices=["vm", "heat", "mc", "tab", "fused", "isihara"])
+    ap.add_argument("--fused-exact", action="store_true")
     ap.add_argument("--mc-scheme", default="queue", choices=["queue", "simple"])
     ap.add_argument("--n", type=float, default=1e8, help="quadrature points per GPU (device-resident leg)")
     ap.add_argument("--e2e-n", type=float, default=1.5e7, help="quadrature points per GPU for the end-to-end leg")

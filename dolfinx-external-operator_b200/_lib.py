@@ -111,7 +111,7 @@ PROTOTYPES = {
     "eo_tab_destroy": (C.c_int, [_vp]),
     "eo_tab_ncomp": (C.c_int, [_vp, C.c_int]),
     "eo_tabulate": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _vp]),
-    "eo_tab_vm_fused": (C.c_int, [_vp, C.POINTER(VmParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "eo_tab_vm_fused": (C.c_int, [_vp, C.POINTER(VmParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
     "eo_isihara_create": (C.c_int, [_vp, C.POINTER(IsiharaWeights), C.POINTER(_vp)]),
     "eo_isihara_destroy": (C.c_int, [_vp]),
     "eo_isihara_set_correction": (C.c_int, [_vp, C.POINTER(C.c_double)]),

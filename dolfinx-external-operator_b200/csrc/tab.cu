@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(128) tab_kernel(const __grid_constant__ tab_ta
 // The nq threads of a cell gather the same coefficients (same sectors: one L1 request) and each contracts them
 // with the derivative-table row of its own point, staged in shared memory (the row index is not warp uniform,
 // which the constant bank would serialise).
-template <int NB, int NQ>  // NQ > 0: evaluation points per cell known at compile time (cheap index split)
+template <int NB, int NQ, bool EXACT>  // NQ > 0: evaluation points per cell known at compile time (cheap index split)
 __global__ void __launch_bounds__(256, 4) tab_vm_kernel(const __grid_constant__ tab_tables T, const vm_consts vq,
                                                      const int32_t* __restrict__ dofmap,
                                                      const int32_t* __restrict__ x_dofmap, const double* __restrict__ x,
@@ -143,7 +143,10 @@ __global__ void __launch_bounds__(256, 4) tab_vm_kernel(const __grid_constant__ 
       for (int j = 0; j < 2; ++j) grad[cc][j] = G[cc][0] * K[0][j] + G[cc][1] * K[1][j];
     tab_operand<2, 2>(2, val, grad, e);
     vm_point_out o;
-    vm_point(vq, e[0], e[1], e[2], e[3], s.x, s.y, s.z, s.w, pi, o);
+    if (EXACT)
+      vm_point(vq, e[0], e[1], e[2], e[3], s.x, s.y, s.z, s.w, pi, o);
+    else
+      vm_point_fast(vq, e[0], e[1], e[2], e[3], s.x, s.y, s.z, s.w, pi, o);
     plastic = o.dp > 0.0;
     double* Ct = C_tang + 16 * i;
     eo_st256(Ct + 0, o.C[0], o.C[1], o.C[2], o.C[3]);
@@ -325,7 +328,7 @@ int eo_tabulate(eo_tab* t, int kind, const double* u, const int32_t* cells, int6
 }
 
 int eo_tab_vm_fused(eo_tab* t, const eo_vm_params* prm, const double* u, const double* sigma_n, const double* p,
-                    double* C_tang, double* sigma, double* dp, double* strain) {
+                    double* C_tang, double* sigma, double* dp, double* strain, int exact) {
   if (!t) return EO_ERR_INVALID;
   eo_ctx* ctx = t->ctx;
   EO_REQUIRE(ctx, prm != nullptr, "eo_tab_vm_fused: prm is NULL");
@@ -345,18 +348,20 @@ int eo_tab_vm_fused(eo_tab* t, const eo_vm_params* prm, const double* u, const d
   const vm_consts q{prm->lmbda, prm->mu, prm->H, prm->sigma_0};
   const int64_t n_points = t->n_cells * t->T.nq;
   const unsigned grid = (unsigned)((n_points + 255) / 256);
-#define EO_FUSED_CASE(N)                                                                                                   \
-  if (t->T.nb == N) {                                                                                                      \
-    if (t->T.nq == 3)                                                                                                      \
-      tab_vm_kernel<N, 3><<<grid, 256, 0, ctx->s_cmp>>>(t->T, q, t->dofmap, t->x_dofmap, t->x, d_u, n_points, sigma_n, p, \
-                                                        C_tang, sigma, dp, strain, ctx->stats);                           \
-    else                                                                                                                   \
-      tab_vm_kernel<N, 0><<<grid, 256, 0, ctx->s_cmp>>>(t->T, q, t->dofmap, t->x_dofmap, t->x, d_u, n_points, sigma_n, p, \
-                                                        C_tang, sigma, dp, strain, ctx->stats);                           \
+#define EO_FUSED_LAUNCH(N, Q, X)                                                                                         \
+  tab_vm_kernel<N, Q, X><<<grid, 256, 0, ctx->s_cmp>>>(t->T, q, t->dofmap, t->x_dofmap, t->x, d_u, n_points, sigma_n, p, \
+                                                       C_tang, sigma, dp, strain, ctx->stats)
+#define EO_FUSED_CASE(N)                          \
+  if (t->T.nb == N) {                             \
+    if (t->T.nq == 3 && exact) EO_FUSED_LAUNCH(N, 3, true);   \
+    else if (t->T.nq == 3) EO_FUSED_LAUNCH(N, 3, false);      \
+    else if (exact) EO_FUSED_LAUNCH(N, 0, true);  \
+    else EO_FUSED_LAUNCH(N, 0, false);            \
   }
   EO_FUSED_CASE(3)
   EO_FUSED_CASE(6)
   EO_FUSED_CASE(10)
+#undef EO_FUSED_LAUNCH
 #undef EO_FUSED_CASE
   ctx->launches += 1;
   EO_CUDA(ctx, cudaGetLastError());

@@ -52,3 +52,48 @@ __device__ __forceinline__ void vm_point(const vm_consts& q, double e0, double e
   o.C[12] = 0.0 - cn * (v3 * v0) - cd * 0.0, o.C[13] = 0.0 - cn * (v3 * v1) - cd * 0.0,
   o.C[14] = 0.0 - cn * (v3 * v2) - cd * 0.0, o.C[15] = 2.0 * m - cn * (v3 * v3) - cd * 1.0;
 }
+
+// Same update with fewer instructions, for kernels that are issue-bound rather than HBM-bound (the fused
+// tabulate + von Mises kernel).  The DECISION path - trial stress, deviator, sigma_eq, f - is the reference's
+// exact statement sequence, so the plastic/elastic flag (dp > 0 <=> f > 0) is bit-identical to vm_point; the
+// downstream algebra uses two divisions instead of nine (n = s * (f+ / (sigma_eq f))), a precomputed
+// 1/(3 mu + H), the symmetry of the tangent and explicit FMAs.  Results agree with vm_point to a few ulp
+// (tests: rtol 1e-12); elastic points still give dp = 0, sigma = sigma_trial and C_t = C_elas exactly.
+__device__ __forceinline__ void vm_point_fast(const vm_consts& q, double e0, double e1, double e2, double e3, double n0,
+                                              double n1, double n2, double n3, double pi, vm_point_out& o) {
+  const double l = q.l, m = q.m, H = q.H;
+  const double l2m = l + 2.0 * m;
+  const double se0 = n0 + (l2m * e0 + l * e1 + l * e2);  // (:308)
+  const double se1 = n1 + (l * e0 + l2m * e1 + l * e2);
+  const double se2 = n2 + (l * e0 + l * e1 + l2m * e2);
+  const double se3 = n3 + 2.0 * m * e3;
+  const double third = 1.0 / 3.0;
+  const double tt = 1.0 - third;
+  const double s0 = tt * se0 - third * se1 - third * se2;  // (:309)
+  const double s1 = -third * se0 + tt * se1 - third * se2;
+  const double s2 = -third * se0 - third * se1 + tt * se2;
+  const double s3 = se3;
+  const double seq = sqrt(3.0 / 2.0 * (s0 * s0 + s1 * s1 + s2 * s2 + s3 * s3));  // (:310)
+  const double f = seq - q.s0 - H * pi;                                        // (:312)
+  const double fp = (f + fabs(f)) * 0.5;  // == (f + sqrt(f*f)) / 2             (:313)
+  const double m3 = 3 * m;
+  const double i3mH = 1.0 / (m3 + H);
+  const double dp = fp * i3mH;                    // (:315)
+  const double r = fp / (seq * f);                // n = s / sigma_eq * f+ / f    (:317)
+  const double v0 = s0 * r, v1 = s1 * r, v2 = s2 * r, v3 = s3 * r;
+  const double beta = m3 * dp / seq;              // (:318)
+  o.dp = dp;
+  o.g[0] = fma(-beta, s0, se0), o.g[1] = fma(-beta, s1, se1), o.g[2] = fma(-beta, s2, se2), o.g[3] = fma(-beta, s3, se3);
+  const double cn = m3 * (m3 * i3mH - beta);      // (:323)
+  const double cd = 2 * m * beta;
+  const double w0 = cn * v0, w1 = cn * v1, w2 = cn * v2, w3 = cn * v3;
+  const double dD = l2m - cd * tt, dO = l + cd * third;  // C - cd * dev on the 3x3 block
+  const double c00 = fma(-w0, v0, dD), c01 = fma(-w0, v1, dO), c02 = fma(-w0, v2, dO), c03 = -(w0 * v3);
+  const double c11 = fma(-w1, v1, dD), c12 = fma(-w1, v2, dO), c13 = -(w1 * v3);
+  const double c22 = fma(-w2, v2, dD), c23 = -(w2 * v3);
+  const double c33 = fma(-w3, v3, 2.0 * m - cd);
+  o.C[0] = c00, o.C[1] = c01, o.C[2] = c02, o.C[3] = c03;
+  o.C[4] = c01, o.C[5] = c11, o.C[6] = c12, o.C[7] = c13;
+  o.C[8] = c02, o.C[9] = c12, o.C[10] = c22, o.C[11] = c23;
+  o.C[12] = c03, o.C[13] = c13, o.C[14] = c23, o.C[15] = c33;
+}

@@ -152,9 +152,12 @@ class Tabulator:
         c.check(c.lib.eo_tabulate(self._h, kind_id, _ptr(u), _ptr(cells), n, _ptr(out)))
         return out
 
-    def vm_fused(self, vm, coefficient=None, C_tang: DeviceArray | None = None, strain: DeviceArray | None = None):
+    def vm_fused(self, vm, coefficient=None, C_tang: DeviceArray | None = None, strain: DeviceArray | None = None,
+                 exact: bool = False):
         """Tabulate the Mandel strain and run the von Mises update in ONE kernel (history resident in `vm`).
-        Returns the tangent DeviceArray; stress / dp candidates land in vm.sigma_dev / vm.dp_dev."""
+        Returns the tangent DeviceArray; stress / dp candidates land in vm.sigma_dev / vm.dp_dev.
+        exact=True reproduces `vm((1,))(tab.evaluate("mandel_strain"))` bit for bit; the default uses the
+        cheaper downstream algebra (same flags, a few ulp in the values)."""
         n = self.n_cells * self.nq
         if vm.n_qp is None:
             vm._alloc_state(n)
@@ -166,7 +169,7 @@ class Tabulator:
         u = self._coeff(coefficient)
         prm = VmParams(vm.lmbda, vm.mu, vm.H, vm.sigma_0)
         c.check(c.lib.eo_tab_vm_fused(self._h, C.byref(prm), _ptr(u), vm.sigma_n_dev.ptr, vm.p_dev.ptr, C_tang.ptr,
-                                      vm.sigma_dev.ptr, vm.dp_dev.ptr, _ptr(strain)))
+                                      vm.sigma_dev.ptr, vm.dp_dev.ptr, _ptr(strain), int(bool(exact))))
         return C_tang
 
 

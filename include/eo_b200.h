@@ -214,9 +214,13 @@ int eo_tabulate(eo_tab* tab, int kind, const double* u, const int32_t* cells, in
 /* Fused hot path for all cells: Mandel strain of u at every evaluation point -> von Mises radial return
  * (eo_vm_eval) without the strain ever touching HBM.  Point index = cell * nq + q, as the reference's
  * flat layout.  sigma_n, p, C_tang, sigma, dp (and `strain`, optional, may be NULL) are device memory;
- * u is any-side.  Asynchronous on the ctx stream. */
+ * u is any-side.  Asynchronous on the ctx stream.
+ * exact != 0: the von Mises arithmetic is the reference's statement sequence (bit-identical to eo_vm_eval on the
+ * tabulated strain); exact == 0: same decision path (identical plastic/elastic flags) but two divisions instead
+ * of nine and explicit FMAs downstream - a few ulp from the exact variant, ~1.3x faster (this kernel is
+ * issue-bound, not HBM-bound). */
 int eo_tab_vm_fused(eo_tab* tab, const eo_vm_params* prm, const double* u, const double* sigma_n, const double* p,
-                    double* C_tang, double* sigma, double* dp, double* strain);
+                    double* C_tang, double* sigma, double* dp, double* strain, int exact);
 
 /* ---------------------------------------------------------------- Mohr-Coulomb
  * replaces: `dsigma_ddeps_vec = jit(vmap(jacfwd(return_mapping, has_aux=True)))` and the body of

@@ -28,6 +28,16 @@ int oracle_num_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU-baseline legs of bench.py run on rank 0 only and
+ * may use all host cores. */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* One quadrature point; mirrors `_kernel` demo_vm:307-326 statement by statement. */
 static void vm_point(const oracle_vm_params* q, const double* deps, const double* sn, double p, double* Ct,
                      double* sig, double* dp_out) {

@@ -42,6 +42,16 @@ def num_threads() -> int:
     return int(load().oracle_num_threads())
 
 
+def use_all_cores() -> int:
+    """Let the OpenMP legs use every host core this process may run on (torchrun sets OMP_NUM_THREADS=1)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    load().oracle_set_num_threads(C.c_int(n))
+    return num_threads()
+
+
 def vm_return_mapping(deps, sigma_n, p, prm, parallel: bool = False):
     """C restatement of demo_vm:298-332; arrays in the reference's layout."""
     lib = load()
