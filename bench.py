@@ -37,7 +37,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BYTES_PER_QP = {"vm": 240, "heat": 88, "mc": 252, "tab": 176.0 / 3.0, "fused": 235, "isihara": 192}
+BYTES_PER_QP = {"vm": 240, "jitvm": 240, "heat": 88, "mc": 252, "tab": 176.0 / 3.0, "fused": 235, "isihara": 192}
 METRIC = "quadrature points per second (stress + consistent tangent + internal state)"
 
 
@@ -248,6 +248,8 @@ WORKLOADS = {
           "(BASELINE configs[2] callable at configs[4] batch size), demo stress-path family",
     "isihara": "Isihara ICNN hyperelasticity (BASELINE configs[3] callable at configs[4] batch size): stress P and "
                "tangent dP/dF from the 3-64-64-64-1 float32 network, float64 invariants",
+    "jitvm": "von Mises return mapping written as a user model for the run-time compiled (NVRTC) generic path: "
+             "stress + tangent by forward-mode dual numbers + plastic multiplier, plane-strain Mandel 4-vectors",
     "tab": "operand tabulation: Mandel strain of a P2 vector field at 3 quadrature points per triangle "
            "(evaluate_operands for the von Mises / Mohr-Coulomb demos), structured jittered mesh",
     "fused": "operand tabulation fused with the von Mises return mapping (strain never stored), P2 vector field, "
@@ -327,6 +329,21 @@ def run_gpu_arm(args):
 
         def step():
             vm.eval_device(d_deps, d_Ct)
+    elif model == "jitvm":
+        from dolfinx_external_operator_b200 import jit_models as jm
+
+        jv = jm.von_mises(ctx=ctx)
+        deps_t, sn_t, p_t = inputs.vm_batch(tile_n, seed=rank)
+        d_deps = ctx.empty((n * 4,))
+        _tile_to_device(ctx, d_deps, deps_t, n, 4)
+        jv.state = [ctx.empty((n * 4,)), ctx.empty((n,))]
+        _tile_to_device(ctx, jv.state[0], sn_t, n, 4)
+        _tile_to_device(ctx, jv.state[1], p_t, n, 1)
+        d_Ct, d_sig, d_dp = ctx.empty((n * 16,)), ctx.empty((n * 4,)), ctx.empty((n,))
+        jv.compile((1,))
+
+        def step():
+            jv.eval_device((1,), [d_deps], d_Ct, d_sig, [d_dp])
     elif model == "mc":
         from dolfinx_external_operator_b200._lib import McParams
 
@@ -535,9 +552,11 @@ def run_gpu_arm(args):
         cpu = cpu_tab_rate(model, args.cpu_seconds)
     elif args.cpu_seconds > 0:
         sample = int(args.cpu_sample) if model != "mc" else min(int(args.cpu_sample), 200_000)
-        rate, cores, passes = cpu_port_rate(model, sample, args.cpu_seconds, parallel=True)
-        rate1, _, _ = cpu_port_rate(model, sample // 4, min(3.0, args.cpu_seconds), parallel=False)
+        cm = "vm" if model == "jitvm" else model
+        rate, cores, passes = cpu_port_rate(cm, sample, args.cpu_seconds, parallel=True)
+        rate1, _, _ = cpu_port_rate(cm, sample // 4, min(3.0, args.cpu_seconds), parallel=False)
         what = {"vm": "C restatement of the reference's Numba kernel (serial in the reference)",
+                "jitvm": "C restatement of the reference's Numba kernel (serial in the reference)",
                 "heat": "C restatement of the reference's NumPy functions",
                 "mc": "C++ nested-dual-number restatement of the reference's JAX program (JAX not installable offline)"}
         cpu = {"value": rate, "unit": "QP/s", "cores": cores, "kind": "port",
@@ -574,7 +593,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--model", default="vm", choices=["vm", "heat", "mc", "tab", "fused", "isihara"])
+    ap.add_argument("--model", default="vm", choices=["vm", "heat", "mc", "tab", "fused", "isihara", "jitvm"])
     ap.add_argument("--fused-exact", action="store_true")
     ap.add_argument("--mc-scheme", default="queue", choices=["queue", "simple"])
     ap.add_argument("--n", type=float, default=1e8, help="quadrature points per GPU (device-resident leg)")

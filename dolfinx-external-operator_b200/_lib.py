@@ -55,6 +55,19 @@ class IsiharaWeights(C.Structure):
                 ("W2T", C.c_float * 64 * 64), ("w3", C.c_float * 64), ("s3", C.c_float * 4), ("H", C.c_double * 4)]
 
 
+EO_JIT_MAX_ARGS = 8
+EO_JIT_MAX_PARAMS = 32
+
+
+class JitDesc(C.Structure):
+    _fields_ = [("source", C.c_char_p), ("entry", C.c_char_p),
+                ("n_operands", C.c_int32), ("operand_size", C.c_int32 * EO_JIT_MAX_ARGS),
+                ("n_state", C.c_int32), ("state_size", C.c_int32 * EO_JIT_MAX_ARGS),
+                ("out_size", C.c_int32),
+                ("n_aux", C.c_int32), ("aux_size", C.c_int32 * EO_JIT_MAX_ARGS),
+                ("n_params", C.c_int32), ("fmad", C.c_int32)]
+
+
 class Stats(C.Structure):
     _fields_ = [
         ("n_points", C.c_int64),
@@ -116,6 +129,14 @@ PROTOTYPES = {
     "eo_isihara_destroy": (C.c_int, [_vp]),
     "eo_isihara_set_correction": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "eo_isihara_eval": (C.c_int, [_vp, _vp, _vp, _vp, _i64]),
+    "eo_jit_create": (C.c_int, [_vp, C.POINTER(JitDesc), C.POINTER(_vp)]),
+    "eo_jit_destroy": (C.c_int, [_vp]),
+    "eo_jit_compile": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
+    "eo_jit_cubin": (C.c_int, [_vp, C.POINTER(C.c_int), _vp, C.c_size_t]),
+    "eo_jit_log": (C.c_char_p, [_vp]),
+    "eo_jit_last_error": (C.c_char_p, [_vp]),
+    "eo_jit_out_width": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "eo_jit_eval": (C.c_int, [_vp, C.POINTER(C.c_int), _vp, C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, C.POINTER(_vp), _i64]),
     "eo_mc_eval": (C.c_int, [_vp, C.POINTER(McParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
     "eo_mc_eval_scheme": (C.c_int, [_vp, C.POINTER(McParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_int]),
 }

@@ -1,0 +1,225 @@
+// eo_jit_device.cuh - device side of the generic (NVRTC) quadrature-point path.  This text is embedded in
+// libeo_b200.so and handed to NVRTC as the header "eo_jit_device.cuh"; jit.cu generates the few lines that
+// instantiate eo_jit_run<Spec> for one model and one derivative multi-index.
+//
+// One thread = one quadrature point (the same mapping as vm_kernel): the point's operand / state components
+// are contiguous in the reference's flat layout [point][component] (external_operator.py:396,
+// demo_vm:344-352), so a thread reads them with the widest access its alignment allows (256-bit when the
+// component count is a multiple of 4, 128-bit for a multiple of 2) through the read-only, no-L1-allocate
+// path, seeds the dual numbers, calls the user's model and streams the results back the same way.
+#pragma once
+#include "eo_dual.h"
+
+#define EO_JIT_MAX_ARGS 8
+#define EO_JIT_MAX_PARAMS 32
+
+struct eo_jit_args {
+  const double* operand[EO_JIT_MAX_ARGS];
+  const double* state[EO_JIT_MAX_ARGS];
+  double* out;    // value (order 0) or derivative (order 1, 2)
+  double* value;  // order >= 1: the operator's value, optional
+  double* aux[EO_JIT_MAX_ARGS];
+  long long n;
+  double prm[EO_JIT_MAX_PARAMS];
+};
+
+namespace eo_jitd {
+
+__device__ __forceinline__ void ld(const double* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+__device__ __forceinline__ void ld(const double* p, double& a, double& b) {
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
+}
+__device__ __forceinline__ void ld(const double* p, double& a) {
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(a) : "l"(p));
+}
+__device__ __forceinline__ void st(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.L1::no_allocate.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void st(double* p, double a, double b) {
+  asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void st(double* p, double a) {
+  asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(a) : "memory");
+}
+
+// S contiguous doubles of one point; the base pointer is 32-byte aligned (checked on the host)
+template <int S>
+__device__ __forceinline__ void load_point(const double* __restrict__ base, long long i, double* r) {
+  const double* p = base + i * S;
+  if (S % 4 == 0) {
+#pragma unroll
+    for (int k = 0; k < S; k += 4) ld(p + k, r[k], r[k + 1], r[k + 2], r[k + 3]);
+  } else if (S % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k < S; k += 2) ld(p + k, r[k], r[k + 1]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < S; ++k) ld(p + k, r[k]);
+  }
+}
+template <int S>
+__device__ __forceinline__ void store_point(double* __restrict__ base, long long i, const double* r) {
+  double* p = base + i * S;
+  if (S % 4 == 0) {
+#pragma unroll
+    for (int k = 0; k < S; k += 4) st(p + k, r[k], r[k + 1], r[k + 2], r[k + 3]);
+  } else if (S % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k < S; k += 2) st(p + k, r[k], r[k + 1]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < S; ++k) st(p + k, r[k]);
+  }
+}
+
+// compile-time table helpers over the Spec's static arrays
+template <class Spec, int K>
+struct op_offset {
+  static constexpr int value = op_offset<Spec, K - 1>::value + Spec::op_size(K - 1);
+};
+template <class Spec>
+struct op_offset<Spec, 0> {
+  static constexpr int value = 0;
+};
+template <class Spec, int K>
+struct st_offset {
+  static constexpr int value = st_offset<Spec, K - 1>::value + Spec::st_size(K - 1);
+};
+template <class Spec>
+struct st_offset<Spec, 0> {
+  static constexpr int value = 0;
+};
+template <class Spec, int K>
+struct aux_offset {
+  static constexpr int value = aux_offset<Spec, K - 1>::value + Spec::aux_size(K - 1);
+};
+template <class Spec>
+struct aux_offset<Spec, 0> {
+  static constexpr int value = 0;
+};
+
+template <class Spec, int K, int NK>
+struct loader {
+  static __device__ __forceinline__ void operands(const eo_jit_args& a, long long i, double* x) {
+    load_point<Spec::op_size(K)>(a.operand[K], i, x + op_offset<Spec, K>::value);
+    loader<Spec, K + 1, NK>::operands(a, i, x);
+  }
+  static __device__ __forceinline__ void states(const eo_jit_args& a, long long i, double* s) {
+    load_point<Spec::st_size(K)>(a.state[K], i, s + st_offset<Spec, K>::value);
+    loader<Spec, K + 1, NK>::states(a, i, s);
+  }
+  static __device__ __forceinline__ void aux(const eo_jit_args& a, long long i, const double* v) {
+    if (a.aux[K]) store_point<Spec::aux_size(K)>(a.aux[K], i, v + aux_offset<Spec, K>::value);
+    loader<Spec, K + 1, NK>::aux(a, i, v);
+  }
+};
+template <class Spec, int NK>
+struct loader<Spec, NK, NK> {
+  static __device__ __forceinline__ void operands(const eo_jit_args&, long long, double*) {}
+  static __device__ __forceinline__ void states(const eo_jit_args&, long long, double*) {}
+  static __device__ __forceinline__ void aux(const eo_jit_args&, long long, const double*) {}
+};
+
+constexpr int at_least_1(int n) { return n > 0 ? n : 1; }
+
+// ---- order 0: the value ----------------------------------------------------------------------
+template <class Spec>
+__device__ __forceinline__ void run0(const eo_jit_args& a, long long i) {
+  double x[at_least_1(Spec::NIN)], s[at_least_1(Spec::NST)], y[at_least_1(Spec::NOUT)], w[at_least_1(Spec::NAUX)];
+  loader<Spec, 0, Spec::N_OPERANDS>::operands(a, i, x);
+  loader<Spec, 0, Spec::N_STATE>::states(a, i, s);
+  Spec::template call<double>(x, s, a.prm, y, w);
+  store_point<Spec::NOUT>(a.out, i, y);
+  loader<Spec, 0, Spec::N_AUX>::aux(a, i, w);
+}
+
+// ---- order 1: d y / d operand[A], layout [point][NOUT][size(A)] --------------------------------
+template <class Spec>
+__device__ __forceinline__ void run1(const eo_jit_args& a, long long i) {
+  constexpr int A = Spec::DA, NA = Spec::op_size(A), OA = op_offset<Spec, A>::value;
+  using T = eo::dual<NA>;
+  double xr[at_least_1(Spec::NIN)], s[at_least_1(Spec::NST)];
+  loader<Spec, 0, Spec::N_OPERANDS>::operands(a, i, xr);
+  loader<Spec, 0, Spec::N_STATE>::states(a, i, s);
+  T x[at_least_1(Spec::NIN)], y[at_least_1(Spec::NOUT)], w[at_least_1(Spec::NAUX)];
+#pragma unroll
+  for (int k = 0; k < Spec::NIN; ++k) {
+    x[k].v = xr[k];
+#pragma unroll
+    for (int j = 0; j < NA; ++j) x[k].d[j] = (k == OA + j) ? 1.0 : 0.0;
+  }
+  Spec::template call<T>(x, s, a.prm, y, w);
+  double D[Spec::NOUT * NA];
+#pragma unroll
+  for (int o = 0; o < Spec::NOUT; ++o)
+#pragma unroll
+    for (int j = 0; j < NA; ++j) D[o * NA + j] = y[o].d[j];
+  store_point<Spec::NOUT * NA>(a.out, i, D);
+  if (a.value) {
+    double yv[at_least_1(Spec::NOUT)];
+#pragma unroll
+    for (int o = 0; o < Spec::NOUT; ++o) yv[o] = y[o].v;
+    store_point<Spec::NOUT>(a.value, i, yv);
+  }
+  double wv[at_least_1(Spec::NAUX)];
+#pragma unroll
+  for (int o = 0; o < Spec::NAUX; ++o) wv[o] = w[o].v;
+  loader<Spec, 0, Spec::N_AUX>::aux(a, i, wv);
+}
+
+// ---- order 2: d2 y / d operand[A] d operand[B] (A <= B), layout [point][NOUT][size(A)][size(B)] --
+template <class Spec>
+__device__ __forceinline__ void run2(const eo_jit_args& a, long long i) {
+  constexpr int A = Spec::DA, B = Spec::DB;
+  constexpr int NA = Spec::op_size(A), OA = op_offset<Spec, A>::value;
+  constexpr int NB = Spec::op_size(B), OB = op_offset<Spec, B>::value;
+  using V = eo::dual<NB>;
+  using T = eo::dual<NA, V>;
+  double xr[at_least_1(Spec::NIN)], s[at_least_1(Spec::NST)];
+  loader<Spec, 0, Spec::N_OPERANDS>::operands(a, i, xr);
+  loader<Spec, 0, Spec::N_STATE>::states(a, i, s);
+  T x[at_least_1(Spec::NIN)], y[at_least_1(Spec::NOUT)], w[at_least_1(Spec::NAUX)];
+#pragma unroll
+  for (int k = 0; k < Spec::NIN; ++k) {
+    x[k].v.v = xr[k];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) x[k].v.d[j] = (k == OB + j) ? 1.0 : 0.0;
+#pragma unroll
+    for (int j = 0; j < NA; ++j) x[k].d[j] = V((k == OA + j) ? 1.0 : 0.0);
+  }
+  Spec::template call<T>(x, s, a.prm, y, w);
+  double D[Spec::NOUT * NA * NB];
+#pragma unroll
+  for (int o = 0; o < Spec::NOUT; ++o)
+#pragma unroll
+    for (int ja = 0; ja < NA; ++ja)
+#pragma unroll
+      for (int jb = 0; jb < NB; ++jb) D[(o * NA + ja) * NB + jb] = y[o].d[ja].d[jb];
+  store_point<Spec::NOUT * NA * NB>(a.out, i, D);
+  if (a.value) {
+    double yv[at_least_1(Spec::NOUT)];
+#pragma unroll
+    for (int o = 0; o < Spec::NOUT; ++o) yv[o] = y[o].v.v;
+    store_point<Spec::NOUT>(a.value, i, yv);
+  }
+  double wv[at_least_1(Spec::NAUX)];
+#pragma unroll
+  for (int o = 0; o < Spec::NAUX; ++o) wv[o] = w[o].v.v;
+  loader<Spec, 0, Spec::N_AUX>::aux(a, i, wv);
+}
+
+template <class Spec>
+__device__ __forceinline__ void run(const eo_jit_args& a) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  if constexpr (Spec::ORDER == 0)
+    run0<Spec>(a, i);
+  else if constexpr (Spec::ORDER == 1)
+    run1<Spec>(a, i);
+  else
+    run2<Spec>(a, i);
+}
+
+}  // namespace eo_jitd

@@ -1,0 +1,350 @@
+// jit.cu - generic per-quadrature-point operators compiled at run time (NVRTC) for sm_100a.
+//
+// replaces: the open-ended `external_function(derivatives)(*operands)` protocol of
+// src/dolfinx_external_operator/external_operator.py:432 for models that are NOT one of the hard-wired
+// kernels: the user hands in the CUDA C++ text of one function template (see include/eo_dual.h) and gets the
+// value, first and second derivatives with respect to any operand by forward-mode dual numbers - what the
+// reference obtains from JAX / torch.func (README.md:16-25, demo_mc:555, demo_hyperelasticity.py:429-456).
+//
+// NVRTC (libnvrtc.so.12) is loaded with dlopen on first use so that the library itself keeps no link-time
+// dependency on it; the CUBIN is loaded with cudaLibraryLoadData and launched with cudaLaunchKernel on the
+// context's compute stream, host-side arguments go through the same chunked pipeline as every other entry point.
+#include <dlfcn.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+
+#include "eo_common.cuh"
+#include "eo_jit_device.cuh"  // eo_jit_args (the same text NVRTC sees)
+
+static const char* k_hdr_dual =
+#include "eo_dual.inc"
+    ;
+static const char* k_hdr_device =
+#include "eo_jit_device.inc"
+    ;
+
+// ---------------------------------------------------------------------------------------------
+// NVRTC through dlopen
+// ---------------------------------------------------------------------------------------------
+namespace {
+typedef struct _nvrtcProgram* nvrtcProgram;
+struct nvrtc_api {
+  void* h = nullptr;
+  int (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*);
+  int (*CompileProgram)(nvrtcProgram, int, const char* const*);
+  int (*DestroyProgram)(nvrtcProgram*);
+  int (*GetCUBINSize)(nvrtcProgram, size_t*);
+  int (*GetCUBIN)(nvrtcProgram, char*);
+  int (*GetProgramLogSize)(nvrtcProgram, size_t*);
+  int (*GetProgramLog)(nvrtcProgram, char*);
+  const char* (*GetErrorString)(int);
+  int (*Version)(int*, int*);
+  std::string err;
+};
+
+nvrtc_api* nvrtc() {
+  static nvrtc_api api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* names[] = {getenv("EO_NVRTC_LIB"),
+                           "libnvrtc.so.12",
+                           "/usr/local/cuda/lib64/libnvrtc.so.12",
+                           "libnvrtc.so.13",
+                           "libnvrtc.so"};
+    for (const char* nm : names) {
+      if (!nm || !*nm) continue;
+      api.h = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+      if (api.h) break;
+    }
+    if (!api.h) {
+      api.err = "libnvrtc.so.12 not found (set EO_NVRTC_LIB to its path)";
+      return;
+    }
+#define EO_SYM(field, name)                                   \
+  *(void**)(&api.field) = dlsym(api.h, name);                 \
+  if (!api.field) {                                           \
+    api.err = std::string("libnvrtc lacks ") + name;          \
+    api.h = nullptr;                                          \
+    return;                                                   \
+  }
+    EO_SYM(CreateProgram, "nvrtcCreateProgram");
+    EO_SYM(CompileProgram, "nvrtcCompileProgram");
+    EO_SYM(DestroyProgram, "nvrtcDestroyProgram");
+    EO_SYM(GetCUBINSize, "nvrtcGetCUBINSize");
+    EO_SYM(GetCUBIN, "nvrtcGetCUBIN");
+    EO_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize");
+    EO_SYM(GetProgramLog, "nvrtcGetProgramLog");
+    EO_SYM(GetErrorString, "nvrtcGetErrorString");
+    EO_SYM(Version, "nvrtcVersion");
+#undef EO_SYM
+  });
+  return &api;
+}
+
+struct jit_variant {
+  std::string cubin;
+  cudaLibrary_t lib = nullptr;
+  cudaKernel_t kernel = nullptr;
+  int order = 0, da = 0, db = 0;
+  int out_width = 0;  // doubles per point of the primary output
+};
+}  // namespace
+
+struct eo_jit {
+  eo_ctx* ctx = nullptr;  // may be nullptr: compile-only object (no GPU needed)
+  std::string source, entry;
+  int n_operands = 0, n_state = 0, n_aux = 0, n_params = 0, out_size = 0, fmad = 1;
+  int operand_size[EO_JIT_MAX_ARGS] = {}, state_size[EO_JIT_MAX_ARGS] = {}, aux_size[EO_JIT_MAX_ARGS] = {};
+  std::map<std::string, jit_variant> variants;
+  std::string log;  // last compile log
+  char err[512] = {0};
+};
+
+static int jit_fail(eo_jit* m, int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(m->err, sizeof m->err, fmt, ap);
+  va_end(ap);
+  if (m->ctx) snprintf(m->ctx->err, sizeof m->ctx->err, "%s", m->err);
+  return code;
+}
+
+static std::string int_list(const int* v, int n) {
+  std::string s = "{";
+  for (int i = 0; i < n; ++i) s += (i ? "," : "") + std::to_string(v[i]);
+  if (n == 0) s += "0";
+  return s + "}";
+}
+
+// The translation unit handed to NVRTC for one derivative multi-index.
+static std::string jit_program(const eo_jit* m, int order, int da, int db) {
+  int nin = 0, nst = 0, naux = 0;
+  for (int i = 0; i < m->n_operands; ++i) nin += m->operand_size[i];
+  for (int i = 0; i < m->n_state; ++i) nst += m->state_size[i];
+  for (int i = 0; i < m->n_aux; ++i) naux += m->aux_size[i];
+  std::string s;
+  s += "#include \"eo_jit_device.cuh\"\n";
+  s += "#line 1 \"model.cu\"\n";
+  s += m->source;
+  s += "\n#line 1 \"eo_jit_entry.cu\"\n";
+  s += "struct eo_jit_spec {\n";
+  s += "  static constexpr int N_OPERANDS = " + std::to_string(m->n_operands) + ", N_STATE = " + std::to_string(m->n_state) +
+       ", N_AUX = " + std::to_string(m->n_aux) + ";\n";
+  s += "  static constexpr int NIN = " + std::to_string(nin) + ", NST = " + std::to_string(nst) +
+       ", NOUT = " + std::to_string(m->out_size) + ", NAUX = " + std::to_string(naux) + ";\n";
+  s += "  static constexpr int ORDER = " + std::to_string(order) + ", DA = " + std::to_string(da) + ", DB = " + std::to_string(db) + ";\n";
+  s += "  static constexpr int op_size(int k) { constexpr int t[] = " + int_list(m->operand_size, m->n_operands) + "; return t[k]; }\n";
+  s += "  static constexpr int st_size(int k) { constexpr int t[] = " + int_list(m->state_size, m->n_state) + "; return t[k]; }\n";
+  s += "  static constexpr int aux_size(int k) { constexpr int t[] = " + int_list(m->aux_size, m->n_aux) + "; return t[k]; }\n";
+  s += "  template <class T> static __device__ __forceinline__ void call(const T* x, const double* s, const double* prm, T* y, T* w) {\n";
+  s += "    " + m->entry + "<T>(x, s, prm, y, w);\n  }\n};\n";
+  s += "extern \"C\" __global__ void __launch_bounds__(256) eo_jit_entry(const __grid_constant__ eo_jit_args a) {\n";
+  s += "  eo_jitd::run<eo_jit_spec>(a);\n}\n";
+  return s;
+}
+
+static int jit_multi_index(eo_jit* m, const int* derivatives, int& order, int& da, int& db) {
+  order = 0, da = 0, db = 0;
+  for (int i = 0; i < m->n_operands; ++i) {
+    const int d = derivatives ? derivatives[i] : 0;
+    if (d < 0) return jit_fail(m, EO_ERR_INVALID, "eo_jit: negative derivative order");
+    for (int r = 0; r < d; ++r) {
+      if (order == 0) da = i;
+      if (order == 1) db = i;
+      ++order;
+    }
+  }
+  if (order > 2) return jit_fail(m, EO_ERR_UNSUPPORTED, "eo_jit: derivative order %d > 2 is not implemented", order);
+  return EO_OK;
+}
+
+static int jit_compile(eo_jit* m, int order, int da, int db, jit_variant** out) {
+  const std::string key = std::to_string(order) + ":" + std::to_string(da) + ":" + std::to_string(db);
+  auto it = m->variants.find(key);
+  if (it != m->variants.end()) {
+    *out = &it->second;
+    return EO_OK;
+  }
+  nvrtc_api* rt = nvrtc();
+  if (!rt->h) return jit_fail(m, EO_ERR_UNSUPPORTED, "eo_jit: %s", rt->err.c_str());
+  const std::string prog_text = jit_program(m, order, da, db);
+  nvrtcProgram prog = nullptr;
+  const char* hdr_src[2] = {k_hdr_device, k_hdr_dual};
+  const char* hdr_name[2] = {"eo_jit_device.cuh", "eo_dual.h"};
+  int rc = rt->CreateProgram(&prog, prog_text.c_str(), "eo_jit_entry.cu", 2, hdr_src, hdr_name);
+  if (rc) return jit_fail(m, EO_ERR_CUDA, "nvrtcCreateProgram: %s", rt->GetErrorString(rc));
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device",
+                        m->fmad ? "--fmad=true" : "--fmad=false"};
+  rc = rt->CompileProgram(prog, 5, opts);
+  size_t ls = 0;
+  rt->GetProgramLogSize(prog, &ls);
+  m->log.assign(ls ? ls : 1, '\0');
+  if (ls) rt->GetProgramLog(prog, &m->log[0]);
+  while (!m->log.empty() && m->log.back() == '\0') m->log.pop_back();
+  if (rc) {
+    rt->DestroyProgram(&prog);
+    return jit_fail(m, EO_ERR_INVALID, "eo_jit: compilation of '%s' (derivatives %s) failed: %s; see eo_jit_log", m->entry.c_str(),
+                    key.c_str(), rt->GetErrorString(rc));
+  }
+  jit_variant v;
+  size_t cs = 0;
+  rt->GetCUBINSize(prog, &cs);
+  v.cubin.assign(cs, '\0');
+  rt->GetCUBIN(prog, &v.cubin[0]);
+  rt->DestroyProgram(&prog);
+  v.order = order, v.da = da, v.db = db;
+  v.out_width = m->out_size;
+  if (order >= 1) v.out_width *= m->operand_size[da];
+  if (order >= 2) v.out_width *= m->operand_size[db];
+  if (m->ctx) {
+    cudaError_t e = cudaLibraryLoadData(&v.lib, v.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e != cudaSuccess) return jit_fail(m, EO_ERR_CUDA, "cudaLibraryLoadData: %s", cudaGetErrorString(e));
+    e = cudaLibraryGetKernel(&v.kernel, v.lib, "eo_jit_entry");
+    if (e != cudaSuccess) return jit_fail(m, EO_ERR_CUDA, "cudaLibraryGetKernel: %s", cudaGetErrorString(e));
+  }
+  auto ins = m->variants.emplace(key, std::move(v));
+  *out = &ins.first->second;
+  return EO_OK;
+}
+
+extern "C" {
+
+int eo_jit_create(eo_ctx* ctx, const eo_jit_desc* d, eo_jit** out) {
+  if (!out) return eo_fail(ctx, EO_ERR_INVALID, "eo_jit_create: out is NULL");
+  *out = nullptr;
+  if (!d || !d->source || !d->entry) return eo_fail(ctx, EO_ERR_INVALID, "eo_jit_create: NULL descriptor / source / entry");
+  if (d->n_operands < 1 || d->n_operands > EO_JIT_MAX_ARGS || d->n_state < 0 || d->n_state > EO_JIT_MAX_ARGS ||
+      d->n_aux < 0 || d->n_aux > EO_JIT_MAX_ARGS || d->n_params < 0 || d->n_params > EO_JIT_MAX_PARAMS)
+    return eo_fail(ctx, EO_ERR_INVALID, "eo_jit_create: operand / state / aux / parameter count out of range");
+  if (d->out_size < 1 || d->out_size > 64) return eo_fail(ctx, EO_ERR_INVALID, "eo_jit_create: out_size must be in [1, 64]");
+  eo_jit* m = new eo_jit();
+  m->ctx = ctx;
+  m->source = d->source;
+  m->entry = d->entry;
+  m->n_operands = d->n_operands, m->n_state = d->n_state, m->n_aux = d->n_aux, m->n_params = d->n_params;
+  m->out_size = d->out_size;
+  m->fmad = d->fmad ? 1 : 0;
+  bool ok = true;
+  for (int i = 0; i < d->n_operands; ++i) ok = ok && (m->operand_size[i] = d->operand_size[i]) >= 1 && d->operand_size[i] <= 16;
+  for (int i = 0; i < d->n_state; ++i) ok = ok && (m->state_size[i] = d->state_size[i]) >= 1 && d->state_size[i] <= 64;
+  for (int i = 0; i < d->n_aux; ++i) ok = ok && (m->aux_size[i] = d->aux_size[i]) >= 1 && d->aux_size[i] <= 64;
+  if (!ok) {
+    delete m;
+    return eo_fail(ctx, EO_ERR_INVALID, "eo_jit_create: a component count is out of range (operands 1..16, state/aux 1..64)");
+  }
+  *out = m;
+  return EO_OK;
+}
+
+int eo_jit_destroy(eo_jit* m) {
+  if (!m) return EO_OK;
+  if (m->ctx) cudaStreamSynchronize(m->ctx->s_cmp);
+  for (auto& kv : m->variants)
+    if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
+  delete m;
+  return EO_OK;
+}
+
+const char* eo_jit_log(const eo_jit* m) { return m ? m->log.c_str() : ""; }
+const char* eo_jit_last_error(const eo_jit* m) { return m ? m->err : "eo_jit: NULL handle"; }
+
+int eo_jit_compile(eo_jit* m, const int* derivatives, size_t* cubin_bytes) {
+  if (!m) return EO_ERR_INVALID;
+  int order, da, db;
+  int rc = jit_multi_index(m, derivatives, order, da, db);
+  if (rc) return rc;
+  jit_variant* v = nullptr;
+  rc = jit_compile(m, order, da, db, &v);
+  if (rc) return rc;
+  if (cubin_bytes) *cubin_bytes = v->cubin.size();
+  return EO_OK;
+}
+
+int eo_jit_cubin(eo_jit* m, const int* derivatives, void* buf, size_t buf_bytes) {
+  if (!m) return EO_ERR_INVALID;
+  int order, da, db;
+  int rc = jit_multi_index(m, derivatives, order, da, db);
+  if (rc) return rc;
+  jit_variant* v = nullptr;
+  rc = jit_compile(m, order, da, db, &v);
+  if (rc) return rc;
+  if (!buf || buf_bytes < v->cubin.size()) return jit_fail(m, EO_ERR_INVALID, "eo_jit_cubin: buffer too small (%zu needed)", v->cubin.size());
+  memcpy(buf, v->cubin.data(), v->cubin.size());
+  return EO_OK;
+}
+
+int eo_jit_out_width(eo_jit* m, const int* derivatives) {
+  if (!m) return EO_ERR_INVALID;
+  int order, da, db;
+  int rc = jit_multi_index(m, derivatives, order, da, db);
+  if (rc) return rc;
+  int w = m->out_size;
+  if (order >= 1) w *= m->operand_size[da];
+  if (order >= 2) w *= m->operand_size[db];
+  return w;
+}
+
+int eo_jit_eval(eo_jit* m, const int* derivatives, const double* params, const double* const* operands,
+                const double* const* state, double* out, double* value, double* const* aux, int64_t n) {
+  if (!m) return EO_ERR_INVALID;
+  eo_ctx* ctx = m->ctx;
+  if (!ctx) return jit_fail(m, EO_ERR_NO_DEVICE, "eo_jit_eval: this model was created without a context (compile-only)");
+  if (n < 0) return jit_fail(m, EO_ERR_INVALID, "eo_jit_eval: n < 0");
+  if (!out || !operands || (m->n_state && !state) || (m->n_params && !params))
+    return jit_fail(m, EO_ERR_INVALID, "eo_jit_eval: NULL out / operands / state / params");
+  int order, da, db;
+  int rc = jit_multi_index(m, derivatives, order, da, db);
+  if (rc) return rc;
+  jit_variant* v = nullptr;
+  rc = jit_compile(m, order, da, db, &v);
+  if (rc) return rc;
+  EO_CUDA(ctx, cudaSetDevice(ctx->device));
+
+  // argument table of the streamed pipeline: operands, state, out, value, aux
+  eo_arg args[3 * EO_JIT_MAX_ARGS + 2];
+  int na = 0;
+  for (int i = 0; i < m->n_operands; ++i) {
+    if (!operands[i]) return jit_fail(m, EO_ERR_INVALID, "eo_jit_eval: operand %d is NULL", i);
+    args[na++] = {operands[i], size_t(m->operand_size[i]) * 8, false};
+  }
+  for (int i = 0; i < m->n_state; ++i) {
+    if (!state[i]) return jit_fail(m, EO_ERR_INVALID, "eo_jit_eval: state field %d is NULL", i);
+    args[na++] = {state[i], size_t(m->state_size[i]) * 8, false};
+  }
+  const int i_out = na;
+  args[na++] = {out, size_t(v->out_width) * 8, true};
+  const int i_val = na;
+  args[na++] = {order >= 1 ? value : nullptr, size_t(m->out_size) * 8, true};
+  const int i_aux = na;
+  for (int i = 0; i < m->n_aux; ++i) args[na++] = {aux ? aux[i] : nullptr, size_t(m->aux_size[i]) * 8, true};
+  for (int i = 0; i < na; ++i)
+    if (args[i].ptr && (reinterpret_cast<uintptr_t>(args[i].ptr) & 7))
+      return jit_fail(m, EO_ERR_INVALID, "eo_jit_eval: argument %d is not 8-byte aligned", i);
+
+  eo_jit_args ka;
+  memset(&ka, 0, sizeof ka);
+  for (int i = 0; i < m->n_params; ++i) ka.prm[i] = params[i];
+  cudaKernel_t kernel = v->kernel;
+  auto launch = [&](void** p, int64_t nn, int64_t) -> int {
+    for (int i = 0; i < na; ++i)
+      if (p[i] && (reinterpret_cast<uintptr_t>(p[i]) & (args[i].bpq % 32 == 0 ? 31 : args[i].bpq % 16 == 0 ? 15 : 7)))
+        return jit_fail(m, EO_ERR_INVALID, "eo_jit_eval: device argument %d is misaligned for its %zu-byte points", i, args[i].bpq);
+    for (int i = 0; i < m->n_operands; ++i) ka.operand[i] = (const double*)p[i];
+    for (int i = 0; i < m->n_state; ++i) ka.state[i] = (const double*)p[m->n_operands + i];
+    ka.out = (double*)p[i_out];
+    ka.value = (double*)p[i_val];
+    for (int i = 0; i < m->n_aux; ++i) ka.aux[i] = (double*)p[i_aux + i];
+    ka.n = nn;
+    void* kargs[1] = {&ka};
+    const unsigned grid = unsigned((nn + 255) / 256);
+    cudaError_t e = cudaLaunchKernel((const void*)kernel, dim3(grid), dim3(256), kargs, 0, ctx->s_cmp);
+    if (e != cudaSuccess) return jit_fail(m, EO_ERR_CUDA, "eo_jit_eval: launch: %s", cudaGetErrorString(e));
+    ++ctx->launches;
+    return EO_OK;
+  };
+  return eo_run_streamed(ctx, args, na, n, launch);
+}
+
+}  // extern "C"

@@ -280,6 +280,51 @@ int eo_isihara_set_correction(eo_isihara* m, const double H_flat[4]);
  * network arithmetic in float32 like the reference (results are float32-accurate).  Any-side pointers. */
 int eo_isihara_eval(eo_isihara* m, const double* F, double* dP, double* P, int64_t n);
 
+/* ---------------------------------------------------------------- generic run-time compiled models
+ * replaces: any user `external_function(derivatives)(*operands)` (external_operator.py:432) that is not one
+ *           of the hard-wired kernels, together with the automatic differentiation the reference demos take
+ *           from their array library (README.md:16-25; jax.jacfwd demo_mc:555; torch.func
+ *           demo_hyperelasticity.py:429-456).
+ * `source` is CUDA C++ text defining
+ *     template <class T> __device__ void ENTRY(const T* x, const double* state, const double* prm, T* y, T* aux);
+ * x = all operands concatenated (operand_size[0] + ... components), state = all per-point state fields
+ * concatenated (read only, not differentiated), prm = n_params doubles, y = out_size results, aux = all
+ * auxiliary outputs concatenated (e.g. the plastic multiplier increment of demo_vm:352).  T is double for the
+ * value and eo::dual<...> (include/eo_dual.h) for derivatives.  One NVRTC compilation (sm_100a) per derivative
+ * multi-index, cached in the handle.  `ctx` may be NULL for a compile-only handle (works without a GPU). */
+#define EO_JIT_MAX_ARGS 8
+#define EO_JIT_MAX_PARAMS 32
+typedef struct eo_jit_desc {
+  const char* source;
+  const char* entry;
+  int32_t n_operands, operand_size[EO_JIT_MAX_ARGS]; /* components per point, 1..16 */
+  int32_t n_state, state_size[EO_JIT_MAX_ARGS];
+  int32_t out_size;                                  /* components of the operator's value */
+  int32_t n_aux, aux_size[EO_JIT_MAX_ARGS];
+  int32_t n_params;
+  int32_t fmad;                                      /* 0: plain IEEE sequence (--fmad=false), 1: contract */
+} eo_jit_desc;
+
+typedef struct eo_jit eo_jit;
+int eo_jit_create(eo_ctx* ctx, const eo_jit_desc* desc, eo_jit** out);
+int eo_jit_destroy(eo_jit* m);
+/* Compile (if not cached) the kernel for `derivatives` (one int per operand, sum <= 2; NULL = value). */
+int eo_jit_compile(eo_jit* m, const int* derivatives, size_t* cubin_bytes);
+/* Copy the compiled sm_100a CUBIN for `derivatives` (size from eo_jit_compile) - for inspection with
+ * cuobjdump / caching by the caller. */
+int eo_jit_cubin(eo_jit* m, const int* derivatives, void* buf, size_t buf_bytes);
+/* NVRTC log of the last compilation / text of the last error on this handle. */
+const char* eo_jit_log(const eo_jit* m);
+const char* eo_jit_last_error(const eo_jit* m);
+/* doubles per point of `out` for `derivatives`: out_size x size(operand a) [x size(operand b)], or < 0. */
+int eo_jit_out_width(eo_jit* m, const int* derivatives);
+/* Evaluate at n points.  operands[i] : [n][operand_size[i]], state[i] : [n][state_size[i]] (any-side).
+ * out : [n][out_width]  - the value, or the derivative laid out [point][out][operand a][operand b] like the
+ *       reference's `space_shape + operand_shape` convention (external_operator.py:117-121);
+ * value (optional, derivative orders >= 1) : [n][out_size];  aux[i] (each optional) : [n][aux_size[i]]. */
+int eo_jit_eval(eo_jit* m, const int* derivatives, const double* params, const double* const* operands,
+                const double* const* state, double* out, double* value, double* const* aux, int64_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,129 @@
+"""CPU tests of the run-time compiled (NVRTC) path: compilation for sm_100a works without a GPU, compile
+errors surface with NVRTC's log, and the model texts + the dual-number algebra (include/eo_dual.h, built with
+g++ by tests/jit_util.py) reproduce the reference's hand-derived tangents stored in the golden vectors."""
+
+import os
+
+import numpy as np
+import pytest
+
+from dolfinx_external_operator_b200 import jit_models as jm
+from dolfinx_external_operator_b200._lib import EOError
+from dolfinx_external_operator_b200.jit import JitModel
+from jit_util import host_eval
+
+
+def _close(a, b, rtol):
+    b = np.asarray(b).reshape(-1)
+    np.testing.assert_allclose(np.asarray(a).reshape(-1), b, rtol=rtol, atol=rtol * np.abs(b).max())
+
+
+def test_compiles_for_sm100a_without_gpu():
+    m = jm.von_mises(compile_only=True)
+    for d in [(0,), (1,), (2,)]:
+        assert m.compile(d) > 1000
+    assert m.out_width((0,)) == 4 and m.out_width((1,)) == 16 and m.out_width((2,)) == 64
+    cubin = m.cubin((1,))
+    assert cubin[:4] == b"\x7fELF"
+    h = jm.heat_flux(compile_only=True)
+    assert [h.out_width(d) for d in [(0, 0), (1, 0), (0, 1), (1, 1), (2, 0), (0, 2)]] == [2, 2, 4, 4, 2, 8]
+    for d in [(0, 0), (1, 0), (0, 1), (1, 1)]:
+        assert h.compile(d) > 1000
+
+
+def test_compile_error_carries_the_nvrtc_log():
+    bad = "template <class T> __device__ void f(const T* x, const double*, const double*, T* y, T*) { y[0] = x[0] +; }"
+    m = JitModel(bad, "f", [()], (), compile_only=True)
+    with pytest.raises(EOError) as e:
+        m.compile((0,))
+    assert "model.cu(1): error" in str(e.value)
+    with pytest.raises(EOError):  # order 3 is not implemented
+        jm.heat_conductivity(compile_only=True).compile((3,))
+    with pytest.raises(EOError):  # evaluation needs a context
+        jm.heat_conductivity(compile_only=True)._evaluate((0,), None, 1, [np.zeros(3)])
+
+
+def test_protocol_errors():
+    m = jm.von_mises(compile_only=True, supported=[(1,)])
+    with pytest.raises(NotImplementedError):  # demo_vm:364-368
+        m((0,))
+    with pytest.raises(ValueError):
+        m((1, 0))
+    with pytest.raises(ValueError):
+        JitModel("", "f", [()] * 9, (), compile_only=True)
+
+
+@pytest.mark.parametrize("kind", ["mixed", "elastic", "plastic"])
+def test_von_mises_ad_tangent_matches_reference_golden(golden_dir, kind):
+    """d sigma / d deps by dual numbers == the reference's closed-form consistent tangent (demo_vm:322-326)."""
+    g = np.load(os.path.join(golden_dir, "vm_seed0_n1026.npz"))
+    m = jm.von_mises(compile_only=True)
+    deps, sn, p = g[f"{kind}_deps"], g[f"{kind}_sigma_n"], g[f"{kind}_p"]
+    Ct, sig, (dp,) = host_eval(m, (1,), [deps], [sn, p])
+    assert np.array_equal(dp > 0, g[f"{kind}_dp"] > 0)
+    _close(Ct, g[f"{kind}_C_tang"], 1e-12)
+    _close(sig, g[f"{kind}_sigma"], 1e-12)
+    _close(dp, g[f"{kind}_dp"], 1e-12)
+    sig0, _, (dp0,) = host_eval(m, (0,), [deps], [sn, p])
+    assert np.array_equal(sig0, sig) and np.array_equal(dp0, dp)
+
+
+def test_heat_ad_derivatives_match_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "heat_seed0_n4098.npz"))
+    T, s = g["T"], g["sigma"]
+    m = jm.heat_flux(compile_only=True)
+    _close(host_eval(m, (0, 0), [T, s])[0], g["q"], 1e-14)
+    _close(host_eval(m, (1, 0), [T, s])[0], g["dqdT"], 1e-14)
+    _close(host_eval(m, (0, 1), [T, s])[0], g["dqdsigma"], 1e-14)
+    k = jm.heat_conductivity(compile_only=True)
+    _close(host_eval(k, (0,), [T])[0], g["k"], 1e-14)
+    _close(host_eval(k, (1,), [T])[0], g["dk"], 1e-14)
+    # second derivatives (no golden in the reference): analytic, k = 1/(A+BT), q = -k sigma, A = B = 1
+    kk = 1.0 / (1.0 + T)
+    _close(host_eval(k, (2,), [T])[0], 2 * kk**3, 1e-13)
+    d2 = host_eval(m, (1, 1), [T, s])[0].reshape(-1, 2, 1, 2)  # d2 q_i / dT dsigma_j = k^2 delta_ij
+    ref = np.einsum("n,ij->nij", kk**2, np.eye(2))
+    _close(d2[:, :, 0, :], ref, 1e-13)
+    _close(host_eval(m, (2, 0), [T, s])[0].reshape(-1, 2), -2 * kk[:, None] ** 3 * s, 1e-13)
+    assert np.all(host_eval(m, (0, 2), [T, s])[0] == 0.0)
+
+
+ELEMENTARY = r"""
+template <class T>
+__device__ void elem(const T* x, const double*, const double* prm, T* y, T*) {
+  const T a = x[0], b = x[1];
+  y[0] = sin(a) * cos(b) + tan(a * 0.25);
+  y[1] = exp(a * b) - log(1.0 + a * a) + expm1(b * 0.1) + log1p(a * a);
+  y[2] = sqrt(a * a + b * b + 1.0) / (2.0 + a) + cbrt(1.0 + b * b);
+  y[3] = atan2(a, 1.5 + b * b) + asin(0.3 * sin(a)) + acos(0.2 * cos(b)) + atan(a - b);
+  y[4] = pow(1.0 + a * a, 1.5) + pow(2.0 + b * b, a) + pow(1.7, a * b);
+  y[5] = tanh(a) + sinh(0.3 * b) * cosh(0.2 * a) + fabs(a - b) + fmax(a, b) * fmin(a * a, 0.5) - a / b + 3 / (2 + a * a);
+  y[6] = eo::select(a > b, a * a * b, b * b * a) + (-a) * prm[0];
+}
+"""
+
+
+def test_dual_algebra_against_complex_step_and_finite_differences():
+    """Every elementary function of eo_dual.h: first derivatives against central differences of the value
+    evaluation, second derivatives against central differences of the first."""
+    rng = np.random.default_rng(3)
+    n = 200
+    x = rng.uniform(0.2, 1.2, (n, 2))
+    x[:, 1] += 0.05 * np.sign(x[:, 1] - x[:, 0])  # keep away from the kinks a == b
+    m = JitModel(ELEMENTARY, "elem", [(2,)], (7,), params=[0.7], compile_only=True)
+    f = lambda z: host_eval(m, (0,), [z])[0].reshape(n, 7)  # noqa: E731
+    J = host_eval(m, (1,), [x])[0].reshape(n, 7, 2)
+    h = 1e-6
+    for j in range(2):
+        e = np.zeros(2)
+        e[j] = h
+        fd = (f(x + e) - f(x - e)) / (2 * h)
+        np.testing.assert_allclose(J[:, :, j], fd, rtol=2e-8, atol=2e-8)
+    H = host_eval(m, (2,), [x])[0].reshape(n, 7, 2, 2)
+    J1 = lambda z: host_eval(m, (1,), [z])[0].reshape(n, 7, 2)  # noqa: E731
+    for j in range(2):
+        e = np.zeros(2)
+        e[j] = h
+        fd = (J1(x + e) - J1(x - e)) / (2 * h)
+        np.testing.assert_allclose(H[:, :, :, j], fd, rtol=5e-7, atol=5e-7)
+    np.testing.assert_allclose(H, H.transpose(0, 1, 3, 2), rtol=1e-12, atol=1e-12)

@@ -1,0 +1,112 @@
+"""GPU parity tests of the run-time compiled (NVRTC) generic path: the sm_100a kernels generated from a user
+model, called through the C ABI / the callable protocol, against (a) the golden vectors made by the
+reference's own code, (b) the hard-wired kernels, (c) the host build of the same model text (jit_util)."""
+
+import os
+
+import numpy as np
+import pytest
+
+import dolfinx_external_operator_b200 as eo
+from dolfinx_external_operator_b200 import jit_models as jm
+from dolfinx_external_operator_b200.jit import JitModel
+from jit_util import host_eval
+from oracle import inputs
+from test_jit_cpu import ELEMENTARY
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(a, b, rtol):
+    b = np.asarray(b).reshape(-1)
+    np.testing.assert_allclose(np.asarray(a).reshape(-1), b, rtol=rtol, atol=rtol * np.abs(b).max())
+
+
+@pytest.mark.parametrize("kind", ["mixed", "elastic", "plastic"])
+def test_jit_von_mises_against_reference_golden(ctx, golden_dir, kind):
+    g = np.load(os.path.join(golden_dir, "vm_seed0_n1026.npz"))
+    deps, sn, p = g[f"{kind}_deps"], g[f"{kind}_sigma_n"], g[f"{kind}_p"]
+    m = jm.von_mises(ctx=ctx)
+    m.set_state(0, sn)
+    m.set_state(1, p)
+    Ct, sig, dp = m((1,))(deps.reshape(-1, 3, 4))  # the protocol call of demo_vm:343-352
+    assert np.array_equal(dp > 0, g[f"{kind}_dp"] > 0)  # plastic flags bit-exact
+    _close(Ct, g[f"{kind}_C_tang"], 1e-12)
+    _close(sig, g[f"{kind}_sigma"], 1e-12)
+    _close(dp, g[f"{kind}_dp"], 1e-12)
+    m0 = jm.von_mises(ctx=ctx, returns=("out", "aux0"))
+    m0.state = m.state
+    sig0, dp0 = m0((0,))(deps)
+    assert np.array_equal(sig0, sig) and np.array_equal(dp0, dp)  # same primal in every instantiation
+
+
+@pytest.mark.parametrize("n", [1, 31, 257, 100_003, 2_500_000])
+def test_jit_von_mises_against_hardwired_kernel(ctx, n):
+    """Generic path vs vm_kernel on the same seeded batch (pageable host arrays -> chunked pipeline for the
+    largest size); the AD tangent and the closed-form tangent agree to 1e-11."""
+    deps, sn, p = inputs.vm_batch(n, seed=n)
+    vm = eo.VonMises(ctx=ctx)
+    vm.set_history(sn, p)
+    rC, rs, rdp = (np.array(a) for a in vm((1,))(deps.reshape(-1, 1, 4)))
+    m = jm.von_mises(ctx=ctx)
+    m.set_state(0, sn)
+    m.set_state(1, p)
+    Ct, sig, dp = m((1,))(deps.reshape(-1, 1, 4))
+    assert np.array_equal(dp > 0, rdp > 0)
+    _close(Ct, rC, 1e-11)
+    _close(sig, rs, 1e-12)
+    _close(dp, rdp, 1e-12)
+
+
+def test_jit_heat_against_reference_golden(ctx, golden_dir):
+    g = np.load(os.path.join(golden_dir, "heat_seed0_n4098.npz"))
+    T, s = g["T"], g["sigma"]
+    m = jm.heat_flux(ctx=ctx)
+    _close(m((0, 0))(T, s), g["q"], 1e-13)
+    _close(m((1, 0))(T, s), g["dqdT"], 1e-13)
+    _close(m((0, 1))(T, s), g["dqdsigma"], 1e-13)
+    k = jm.heat_conductivity(ctx=ctx)
+    _close(k((0,))(T), g["k"], 1e-13)
+    _close(k((1,))(T), g["dk"], 1e-13)
+    _close(k((2,))(T), 2.0 / (1.0 + T) ** 3, 1e-13)
+    _close(m((1, 1))(T, s), host_eval(m, (1, 1), [T, s])[0], 1e-13)
+
+
+def test_jit_elementary_functions_match_host_build(ctx):
+    """Every function of eo_dual.h, orders 0-2, NVRTC/sm_100a vs g++ on the same text."""
+    rng = np.random.default_rng(5)
+    n = 4097
+    x = rng.uniform(0.2, 1.2, (n, 2))
+    x[:, 1] += 0.05 * np.sign(x[:, 1] - x[:, 0])
+    m = JitModel(ELEMENTARY, "elem", [(2,)], (7,), params=[0.7], ctx=ctx)
+    for d, rtol in [((0,), 1e-13), ((1,), 1e-12), ((2,), 1e-11)]:
+        _close(m(d)(x), host_eval(m, d, [x])[0], rtol)
+
+
+def test_jit_device_operands_and_async_eval(ctx):
+    n = 70_001
+    deps, sn, p = inputs.vm_batch(n, seed=11)
+    m = jm.von_mises(ctx=ctx)
+    m.set_state(0, sn)
+    m.set_state(1, p)
+    ref = [np.array(a) for a in m((1,))(deps)]
+    d_deps = ctx.to_device(deps.reshape(-1))
+    got = m((1,))(d_deps)  # DeviceArray operand: nothing uploaded
+    for a, b in zip(got, ref):
+        assert np.array_equal(a, b)
+    d_C, d_s, d_dp = ctx.empty((16 * n,)), ctx.empty((4 * n,)), ctx.empty((n,))
+    l0 = ctx.launch_count
+    m.eval_device((1,), [d_deps], d_C, d_s, [d_dp])
+    ctx.sync()
+    assert ctx.launch_count == l0 + 1
+    assert np.array_equal(d_C.to_host(), ref[0]) and np.array_equal(d_s.to_host(), ref[1])
+    assert np.array_equal(d_dp.to_host(), ref[2])
+
+
+def test_jit_empty_and_errors(ctx):
+    m = jm.heat_conductivity(ctx=ctx)
+    assert m((0,))(np.zeros((0, 3))).size == 0
+    with pytest.raises(ValueError):
+        jm.heat_flux(ctx=ctx)((0, 0))(np.zeros(6), np.zeros(10))  # 6 vs 5 points
+    with pytest.raises(ValueError):
+        jm.von_mises(ctx=ctx)((1,))(np.zeros(8))  # state not set
