@@ -23,19 +23,36 @@ struct eo_jit_args {
   double prm[EO_JIT_MAX_PARAMS];
 };
 
+// widest vector access in doubles: 4 (256-bit, needs the CUDA >= 12.9 ptxas) or 2 (jit.cu passes
+// -DEO_JIT_MAX_VEC=2 when the NVRTC it found is older)
+#ifndef EO_JIT_MAX_VEC
+#define EO_JIT_MAX_VEC 4
+#endif
+
 namespace eo_jitd {
 
+#if EO_JIT_MAX_VEC >= 4
 __device__ __forceinline__ void ld(const double* p, double& a, double& b, double& c, double& d) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
+__device__ __forceinline__ void st(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.L1::no_allocate.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+#else
+__device__ __forceinline__ void ld(const double* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(c), "=d"(d) : "l"(p + 2));
+}
+__device__ __forceinline__ void st(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+  asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(p + 2), "d"(c), "d"(d) : "memory");
+}
+#endif
 __device__ __forceinline__ void ld(const double* p, double& a, double& b) {
   asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
 }
 __device__ __forceinline__ void ld(const double* p, double& a) {
   asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(a) : "l"(p));
-}
-__device__ __forceinline__ void st(double* p, double a, double b, double c, double d) {
-  asm volatile("st.global.L1::no_allocate.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
 __device__ __forceinline__ void st(double* p, double a, double b) {
   asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a), "d"(b) : "memory");
@@ -48,10 +65,10 @@ __device__ __forceinline__ void st(double* p, double a) {
 template <int S>
 __device__ __forceinline__ void load_point(const double* __restrict__ base, long long i, double* r) {
   const double* p = base + i * S;
-  if (S % 4 == 0) {
+  if constexpr (S % 4 == 0 && EO_JIT_MAX_VEC >= 4) {
 #pragma unroll
     for (int k = 0; k < S; k += 4) ld(p + k, r[k], r[k + 1], r[k + 2], r[k + 3]);
-  } else if (S % 2 == 0) {
+  } else if constexpr (S % 2 == 0) {
 #pragma unroll
     for (int k = 0; k < S; k += 2) ld(p + k, r[k], r[k + 1]);
   } else {
@@ -62,10 +79,10 @@ __device__ __forceinline__ void load_point(const double* __restrict__ base, long
 template <int S>
 __device__ __forceinline__ void store_point(double* __restrict__ base, long long i, const double* r) {
   double* p = base + i * S;
-  if (S % 4 == 0) {
+  if constexpr (S % 4 == 0 && EO_JIT_MAX_VEC >= 4) {
 #pragma unroll
     for (int k = 0; k < S; k += 4) st(p + k, r[k], r[k + 1], r[k + 2], r[k + 3]);
-  } else if (S % 2 == 0) {
+  } else if constexpr (S % 2 == 0) {
 #pragma unroll
     for (int k = 0; k < S; k += 2) st(p + k, r[k], r[k + 1]);
   } else {

@@ -42,15 +42,19 @@ struct nvrtc_api {
   const char* (*GetErrorString)(int);
   int (*Version)(int*, int*);
   std::string err;
+  int major = 0, minor = 0;
 };
 
 nvrtc_api* nvrtc() {
   static nvrtc_api api;
   static std::once_flag once;
   std::call_once(once, [] {
+    // The toolkit's NVRTC first, by path: a bare soname would resolve to whichever libnvrtc.so.12 the process has
+    // already loaded (PyTorch ships 12.8, whose ptxas rejects the 256-bit vector accesses of sm_100).
     const char* names[] = {getenv("EO_NVRTC_LIB"),
-                           "libnvrtc.so.12",
                            "/usr/local/cuda/lib64/libnvrtc.so.12",
+                           "/usr/local/cuda/lib64/libnvrtc.so",
+                           "libnvrtc.so.12",
                            "libnvrtc.so.13",
                            "libnvrtc.so"};
     for (const char* nm : names) {
@@ -79,6 +83,7 @@ nvrtc_api* nvrtc() {
     EO_SYM(GetErrorString, "nvrtcGetErrorString");
     EO_SYM(Version, "nvrtcVersion");
 #undef EO_SYM
+    api.Version(&api.major, &api.minor);
   });
   return &api;
 }
@@ -175,9 +180,11 @@ static int jit_compile(eo_jit* m, int order, int da, int db, jit_variant** out) 
   const char* hdr_name[2] = {"eo_jit_device.cuh", "eo_dual.h"};
   int rc = rt->CreateProgram(&prog, prog_text.c_str(), "eo_jit_entry.cu", 2, hdr_src, hdr_name);
   if (rc) return jit_fail(m, EO_ERR_CUDA, "nvrtcCreateProgram: %s", rt->GetErrorString(rc));
+  // 256-bit ld/st.global.v4.f64 need the CUDA >= 12.9 ptxas; older NVRTCs get 128-bit accesses
+  const bool v4 = rt->major > 12 || (rt->major == 12 && rt->minor >= 9);
   const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device",
-                        m->fmad ? "--fmad=true" : "--fmad=false"};
-  rc = rt->CompileProgram(prog, 5, opts);
+                        m->fmad ? "--fmad=true" : "--fmad=false", v4 ? "-DEO_JIT_MAX_VEC=4" : "-DEO_JIT_MAX_VEC=2"};
+  rc = rt->CompileProgram(prog, 6, opts);
   size_t ls = 0;
   rt->GetProgramLogSize(prog, &ls);
   m->log.assign(ls ? ls : 1, '\0');
@@ -245,6 +252,11 @@ int eo_jit_destroy(eo_jit* m) {
     if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
   delete m;
   return EO_OK;
+}
+
+int eo_jit_nvrtc_version(void) {
+  nvrtc_api* rt = nvrtc();
+  return rt->h ? rt->major * 1000 + rt->minor * 10 : EO_ERR_UNSUPPORTED;
 }
 
 const char* eo_jit_log(const eo_jit* m) { return m ? m->log.c_str() : ""; }

@@ -310,6 +310,10 @@ int eo_jit_create(eo_ctx* ctx, const eo_jit_desc* desc, eo_jit** out);
 int eo_jit_destroy(eo_jit* m);
 /* Compile (if not cached) the kernel for `derivatives` (one int per operand, sum <= 2; NULL = value). */
 int eo_jit_compile(eo_jit* m, const int* derivatives, size_t* cubin_bytes);
+/* Version of the NVRTC that was found (major * 1000 + minor * 10, e.g. 12090), or EO_ERR_UNSUPPORTED.  The
+ * toolkit's /usr/local/cuda/lib64/libnvrtc.so.12 is preferred (EO_NVRTC_LIB overrides); NVRTC older than 12.9
+ * cannot assemble 256-bit global accesses, models compiled with it use 128-bit ones. */
+int eo_jit_nvrtc_version(void);
 /* Copy the compiled sm_100a CUBIN for `derivatives` (size from eo_jit_compile) - for inspection with
  * cuobjdump / caching by the caller. */
 int eo_jit_cubin(eo_jit* m, const int* derivatives, void* buf, size_t buf_bytes);

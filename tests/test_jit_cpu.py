@@ -31,6 +31,20 @@ def test_compiles_for_sm100a_without_gpu():
         assert h.compile(d) > 1000
 
 
+def test_toolkit_nvrtc_is_preferred_over_the_one_torch_loads():
+    """PyTorch brings its own libnvrtc.so.12 (12.8) into the process; its ptxas cannot assemble the 256-bit
+    global accesses of sm_100, so the library must pick the toolkit's NVRTC by path (and degrade to 128-bit
+    accesses when only an older one exists)."""
+    import torch  # noqa: F401  - loads the bundled NVRTC first
+
+    from dolfinx_external_operator_b200 import _lib
+
+    v = _lib.load().eo_jit_nvrtc_version()
+    assert v >= 12000
+    m = jm.von_mises(compile_only=True)
+    assert m.compile((1,)) > 1000
+
+
 def test_compile_error_carries_the_nvrtc_log():
     bad = "template <class T> __device__ void f(const T* x, const double*, const double*, T* y, T*) { y[0] = x[0] +; }"
     m = JitModel(bad, "f", [()], (), compile_only=True)
