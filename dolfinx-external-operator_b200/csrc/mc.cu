@@ -122,7 +122,7 @@ __device__ __forceinline__ void mc_q_push(mc_queue* q, volatile unsigned short* 
   if (lane == 0) atomicAdd(&q->cnt, (unsigned)__popc(m));
 }
 
-template <bool ASSOC>
+template <bool ASSOC, int AFF>
 __global__ void __launch_bounds__(MC_THREADS, 1) mc_kernel(const mc_consts k, const mc_ptrs P, const int64_t n,
                                                            eo_stats* __restrict__ stats, unsigned int* tile_ctr) {
   extern __shared__ double s_slots[];  // [ASSOC ? MC_NF_ASSOC : MC_NF][MC_NSLOTS]
@@ -185,7 +185,21 @@ __global__ void __launch_bounds__(MC_THREADS, 1) mc_kernel(const mc_consts k, co
         atomicExch(&s_fetching, 0);
       }
       int want = -1;
-      if (cU >= 32) want = MC_Q_U;
+      if (AFF) {
+        // stage affinity per SM sub-partition (warp w runs on sub-partition w & 3): keeping one kind of stage
+        // on a sub-partition keeps that stage's code in its instruction cache; falls through to the priority
+        // rule when the preferred queue cannot fill a warp
+        const int sp = (tid >> 5) & 3;
+        if (sp == 0) {
+          if (inputs && cF >= 32 && cU < 192) want = MC_STAGE_T;
+          else if (cS0 >= 32) want = MC_Q_S0;
+        } else if (sp == 1) {
+          if (cU0 >= 32) want = MC_Q_U0;
+          else if (cS0 >= 32) want = MC_Q_S0;
+        } else if (cU >= 32) want = MC_Q_U;
+      }
+      if (want >= 0) {
+      } else if (cU >= 32) want = MC_Q_U;
       else if (cU0 >= 32) want = MC_Q_U0;
       else if (cS0 >= 32) want = MC_Q_S0;
       else if (inputs && cF >= 32) want = MC_STAGE_T;
@@ -358,7 +372,19 @@ __global__ void __launch_bounds__(MC_SIMPLE_THREADS) mc_kernel_simple(const mc_c
   mc_store_aux(P, i, it, yl, nr, dl);
 }
 
-static bool g_mc_attr_set[2] = {false, false};
+static bool g_mc_attr_set[4] = {false, false, false, false};
+
+template <bool ASSOC, int AFF>
+static int mc_launch_queue(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, int64_t n, size_t smem, unsigned grid) {
+  const int a = (ASSOC ? 1 : 0) + 2 * AFF;
+  if (!g_mc_attr_set[a]) {
+    cudaError_t e = cudaFuncSetAttribute(mc_kernel<ASSOC, AFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return eo_fail(ctx, EO_ERR_CUDA, "eo_mc_eval: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    g_mc_attr_set[a] = true;
+  }
+  mc_kernel<ASSOC, AFF><<<grid, MC_THREADS, smem, ctx->s_cmp>>>(k, P, n, ctx->stats, ctx->work_ctr);
+  return EO_OK;
+}
 
 static int mc_launch(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, int64_t n, int scheme) {
   if (scheme == 1) {
@@ -371,23 +397,18 @@ static int mc_launch(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, int64_t 
     ctx->launches += 1;
     return EO_OK;
   }
-  const int a = k.assoc ? 1 : 0;
   const size_t smem = size_t(k.assoc ? MC_NF_ASSOC : MC_NF) * MC_NSLOTS * sizeof(double);
-  if (!g_mc_attr_set[a]) {
-    cudaError_t e = k.assoc ? cudaFuncSetAttribute(mc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                            : cudaFuncSetAttribute(mc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return eo_fail(ctx, EO_ERR_CUDA, "eo_mc_eval: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    g_mc_attr_set[a] = true;
-  }
   const int64_t ntiles = (n + MC_TILE - 1) / MC_TILE;
   if (ntiles > 4000000000LL) return eo_fail(ctx, EO_ERR_INVALID, "eo_mc_eval: n too large for one launch");
   const int64_t grid = ntiles < ctx->sm_count ? ntiles : ctx->sm_count;
   cudaError_t e = cudaMemsetAsync(ctx->work_ctr, 0, 256, ctx->s_cmp);
   if (e != cudaSuccess) return eo_fail(ctx, EO_ERR_CUDA, "eo_mc_eval: cudaMemsetAsync: %s", cudaGetErrorString(e));
-  if (k.assoc)
-    mc_kernel<true><<<(unsigned)grid, MC_THREADS, smem, ctx->s_cmp>>>(k, P, n, ctx->stats, ctx->work_ctr);
+  int rc;
+  if (scheme == 2)  // no stage affinity: any warp takes the highest-priority full queue (kept for A/B measurements)
+    rc = k.assoc ? mc_launch_queue<true, 0>(ctx, k, P, n, smem, (unsigned)grid) : mc_launch_queue<false, 0>(ctx, k, P, n, smem, (unsigned)grid);
   else
-    mc_kernel<false><<<(unsigned)grid, MC_THREADS, smem, ctx->s_cmp>>>(k, P, n, ctx->stats, ctx->work_ctr);
+    rc = k.assoc ? mc_launch_queue<true, 1>(ctx, k, P, n, smem, (unsigned)grid) : mc_launch_queue<false, 1>(ctx, k, P, n, smem, (unsigned)grid);
+  if (rc != EO_OK) return rc;
   ctx->launches += 1;
   return EO_OK;
 }
@@ -405,7 +426,7 @@ int eo_mc_eval_scheme(eo_ctx* ctx, const eo_mc_params* prm, const double* deps, 
   EO_REQUIRE(ctx, ctx != nullptr, "eo_mc_eval: ctx is NULL");
   EO_REQUIRE(ctx, prm != nullptr, "eo_mc_eval: prm is NULL");
   EO_REQUIRE(ctx, n >= 0, "eo_mc_eval: n < 0");
-  EO_REQUIRE(ctx, scheme == 0 || scheme == 1, "eo_mc_eval: unknown scheme");
+  EO_REQUIRE(ctx, scheme >= 0 && scheme <= 2, "eo_mc_eval: unknown scheme");
   EO_REQUIRE(ctx, prm->Nitermax >= 0 && prm->Nitermax <= 200,
              "eo_mc_eval: Nitermax must be in [0, 200] (histogram bins of eo_stats)");
   if (n == 0) return EO_OK;

@@ -246,9 +246,9 @@ typedef struct eo_mc_params {
  * deps, sigma_n, C_tang, sigma must be 32-byte aligned when they are device pointers. */
 int eo_mc_eval(eo_ctx* ctx, const eo_mc_params* prm, const double* deps, const double* sigma_n, double* C_tang,
                double* sigma, int32_t* niter, double* yielding, double* norm_res, double* dlambda, int64_t n);
-/* Same with an explicit execution scheme: 0 = persistent CTAs with a shared-memory queue of plastic
- * points and lane refill (the default of eo_mc_eval), 1 = one thread per point (divergent baseline;
- * does not update the statistics record). */
+/* Same with an explicit execution scheme: 0 = persistent CTAs with shared-memory stage queues, stage kinds
+ * pinned to SM sub-partitions (the default of eo_mc_eval), 1 = one thread per point (divergent baseline;
+ * does not update the statistics record), 2 = scheme 0 without the sub-partition affinity (A/B measurements). */
 int eo_mc_eval_scheme(eo_ctx* ctx, const eo_mc_params* prm, const double* deps, const double* sigma_n,
                       double* C_tang, double* sigma, int32_t* niter, double* yielding, double* norm_res,
                       double* dlambda, int64_t n, int scheme);
