@@ -50,6 +50,13 @@ class TabDesc(C.Structure):
                 ("phi", C.c_void_p), ("dphi", C.c_void_p), ("dpsi", C.c_void_p)]
 
 
+class GTabDesc(C.Structure):
+    _fields_ = [("gdim", C.c_int32), ("bs", C.c_int32), ("nb", C.c_int32), ("nq", C.c_int32), ("ng", C.c_int32),
+                ("n_sets", C.c_int32), ("n_cells", C.c_int64), ("n_dofs", C.c_int64), ("n_nodes", C.c_int64),
+                ("dofmap", C.c_void_p), ("x_dofmap", C.c_void_p), ("x", C.c_void_p),
+                ("phi", C.c_void_p), ("dphi", C.c_void_p), ("dgeo", C.c_void_p)]
+
+
 class IsiharaWeights(C.Structure):
     _fields_ = [("A1", C.c_float * 4 * 64), ("S2", C.c_float * 4 * 64), ("W2", C.c_float * 64 * 64),
                 ("W2T", C.c_float * 64 * 64), ("w3", C.c_float * 64), ("s3", C.c_float * 4), ("H", C.c_double * 4)]
@@ -111,6 +118,7 @@ PROTOTYPES = {
     "eo_event_record": (C.c_int, [_vp, _vp]),
     "eo_event_elapsed_ms": (C.c_int, [_vp, _vp, _vp, C.POINTER(C.c_float)]),
     "eo_flush_l2": (C.c_int, [_vp, C.c_size_t]),
+    "eo_assign_gather": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp]),
     "eo_debug_counters": (C.c_int, [_vp, _vp]),
     "eo_fp64_peak": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double)]),
     "eo_stats_reset": (C.c_int, [_vp]),
@@ -125,6 +133,10 @@ PROTOTYPES = {
     "eo_tab_ncomp": (C.c_int, [_vp, C.c_int]),
     "eo_tabulate": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _vp]),
     "eo_tab_vm_fused": (C.c_int, [_vp, C.POINTER(VmParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
+    "eo_gtab_create": (C.c_int, [_vp, C.POINTER(GTabDesc), C.POINTER(_vp)]),
+    "eo_gtab_destroy": (C.c_int, [_vp]),
+    "eo_gtab_ncomp": (C.c_int, [_vp, C.c_int]),
+    "eo_gtab_tabulate": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _i64, _vp]),
     "eo_isihara_create": (C.c_int, [_vp, C.POINTER(IsiharaWeights), C.POINTER(_vp)]),
     "eo_isihara_destroy": (C.c_int, [_vp]),
     "eo_isihara_set_correction": (C.c_int, [_vp, C.POINTER(C.c_double)]),

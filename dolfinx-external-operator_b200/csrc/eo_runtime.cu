@@ -40,6 +40,13 @@ __global__ void __launch_bounds__(256) eo_fp64_peak_kernel(double* out, int iter
   out[blockIdx.x * size_t(blockDim.x) + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
+// out[k] = values[src[k]]: the non-contiguous coefficient assignment turned inside out (see eo_assign_gather)
+__global__ void __launch_bounds__(256) eo_gather_kernel(const double* __restrict__ values, const int64_t* __restrict__ src,
+                                                        double* __restrict__ out, int64_t n_out) {
+  const int64_t k = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (k < n_out) out[k] = __ldg(values + __ldg(src + k));
+}
+
 extern "C" {
 
 int eo_version(void) { return EO_B200_VERSION; }
@@ -255,6 +262,24 @@ int eo_flush_l2(eo_ctx* ctx, size_t bytes) {
   eo_flush_kernel<<<ctx->sm_count * 8, 256, 0, ctx->s_cmp>>>((float4*)ctx->flush, bytes / 16);
   EO_CUDA(ctx, cudaGetLastError());
   return EO_OK;
+}
+
+int eo_assign_gather(eo_ctx* ctx, const double* values, int64_t n_values, const int64_t* src_index, int64_t n_out,
+                     double* out) {
+  EO_REQUIRE(ctx, ctx != nullptr, "eo_assign_gather: ctx is NULL");
+  EO_REQUIRE(ctx, n_out >= 0 && n_values >= 0, "eo_assign_gather: negative size");
+  if (n_out == 0) return EO_OK;
+  EO_REQUIRE(ctx, values && src_index && out, "eo_assign_gather: NULL array");
+  EO_REQUIRE(ctx, eo_is_device_ptr(values) && eo_is_device_ptr(src_index),
+             "eo_assign_gather: values and src_index must be device arrays (the operator's result and the plan)");
+  EO_CUDA(ctx, cudaSetDevice(ctx->device));
+  // streamed over the OUTPUT (dof) index: `out` may be the host coefficient array, src_index stays on the device
+  eo_arg args[2] = {{src_index, 8, false}, {out, 8, true}};
+  return eo_run_streamed(ctx, args, 2, n_out, [&](void** a, int64_t m, int64_t) {
+    eo_gather_kernel<<<unsigned((m + 255) / 256), 256, 0, ctx->s_cmp>>>(values, (const int64_t*)a[0], (double*)a[1], m);
+    ctx->launches += 1;
+    return EO_OK;
+  });
 }
 
 int eo_debug_counters(eo_ctx* ctx, uint32_t* out) {

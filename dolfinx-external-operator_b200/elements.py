@@ -60,3 +60,109 @@ def p1_geometry_derivatives(gdim: int) -> np.ndarray:
     for k in range(gdim):
         d[k, k + 1] = 1.0
     return d
+
+
+# ----------------------------------------------------------------------------- tensor-product cells
+def lagrange_interval(degree: int, t: np.ndarray):
+    """(phi (n, degree+1), dphi (n, degree+1)) of the equispaced Lagrange basis on [0, 1], nodes in increasing order."""
+    nodes = np.linspace(0.0, 1.0, degree + 1)
+    t = np.asarray(t, dtype=np.float64)
+    phi = np.ones((t.size, degree + 1))
+    dphi = np.zeros((t.size, degree + 1))
+    for a in range(degree + 1):
+        for m in range(degree + 1):
+            if m != a:
+                phi[:, a] *= (t - nodes[m]) / (nodes[a] - nodes[m])
+        for m in range(degree + 1):
+            if m == a:
+                continue
+            term = np.full(t.size, 1.0 / (nodes[a] - nodes[m]))
+            for l in range(degree + 1):  # noqa: E741
+                if l != a and l != m:
+                    term *= (t - nodes[l]) / (nodes[a] - nodes[l])
+            dphi[:, a] += term
+    return phi, dphi
+
+
+def lagrange_quadrilateral(degree: int, X: np.ndarray):
+    """(phi (nq, nb), dphi (2, nq, nb)), nb = (degree+1)^2, TENSOR ordering: basis (i, j) -> i * (degree+1) + j with
+    i along x, j along y (NOT basix's ordering: production tables come from basix together with DOLFINx's dofmaps;
+    this closed form is paired with `synthetic.quad_mesh`, whose dofmaps use the same tensor ordering)."""
+    px, dx = lagrange_interval(degree, X[:, 0])
+    py, dy = lagrange_interval(degree, X[:, 1])
+    nq = X.shape[0]
+    phi = np.einsum("qi,qj->qij", px, py).reshape(nq, -1)
+    d0 = np.einsum("qi,qj->qij", dx, py).reshape(nq, -1)
+    d1 = np.einsum("qi,qj->qij", px, dy).reshape(nq, -1)
+    return np.ascontiguousarray(phi), np.ascontiguousarray(np.stack([d0, d1]))
+
+
+def lagrange_hexahedron(degree: int, X: np.ndarray):
+    """(phi (nq, nb), dphi (3, nq, nb)), nb = (degree+1)^3, tensor ordering (i, j, k) -> (i * n + j) * n + k."""
+    px, dx = lagrange_interval(degree, X[:, 0])
+    py, dy = lagrange_interval(degree, X[:, 1])
+    pz, dz = lagrange_interval(degree, X[:, 2])
+    nq = X.shape[0]
+    phi = np.einsum("qi,qj,qk->qijk", px, py, pz).reshape(nq, -1)
+    d0 = np.einsum("qi,qj,qk->qijk", dx, py, pz).reshape(nq, -1)
+    d1 = np.einsum("qi,qj,qk->qijk", px, dy, pz).reshape(nq, -1)
+    d2 = np.einsum("qi,qj,qk->qijk", px, py, dz).reshape(nq, -1)
+    return np.ascontiguousarray(phi), np.ascontiguousarray(np.stack([d0, d1, d2]))
+
+
+# reference vertices (DOLFINx / basix ordering) and the vertices of every local facet
+REFERENCE_VERTICES = {
+    "triangle": np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0]]),
+    "tetrahedron": np.array([[0.0, 0, 0], [1.0, 0, 0], [0, 1.0, 0], [0, 0, 1.0]]),
+    "quadrilateral": np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0], [1.0, 1.0]]),
+    "hexahedron": np.array([[x, y, z] for z in (0.0, 1.0) for y in (0.0, 1.0) for x in (0.0, 1.0)]),
+}
+FACET_VERTICES = {
+    "triangle": [(1, 2), (0, 2), (0, 1)],
+    "tetrahedron": [(1, 2, 3), (0, 2, 3), (0, 1, 3), (0, 1, 2)],
+    "quadrilateral": [(0, 1), (0, 2), (1, 3), (2, 3)],
+    "hexahedron": [(0, 1, 2, 3), (0, 1, 4, 5), (0, 2, 4, 6), (1, 3, 5, 7), (2, 3, 6, 7), (4, 5, 6, 7)],
+}
+
+
+def facet_points(cell: str, Xf: np.ndarray) -> np.ndarray:
+    """Points `Xf` (nq, tdim-1) of the reference FACET mapped onto every local facet of the reference cell:
+    (n_facets, nq, tdim).  This is where `fem.Expression.eval` evaluates for (cell, local_facet) entities
+    (test_codim_external_operator.py:75-109): X = v0 + sum_k s_k (v_{k+1} - v0), with the facet's vertices in the
+    order of the table above (for quadrilateral faces of a hexahedron: the first three vertices span the face)."""
+    V = REFERENCE_VERTICES[cell]
+    Xf = np.asarray(Xf, dtype=np.float64).reshape(len(Xf), -1)
+    out = []
+    for fv in FACET_VERTICES[cell]:
+        v0 = V[fv[0]]
+        X = np.tile(v0, (Xf.shape[0], 1))
+        for k in range(Xf.shape[1]):
+            X = X + Xf[:, k : k + 1] * (V[fv[k + 1]] - v0)
+        out.append(X)
+    return np.stack(out)
+
+
+def tabulate_on(cell: str, degree: int, X: np.ndarray):
+    """Closed-form (phi, dphi) of the Lagrange element of `degree` on `cell` at X - stands in for
+    `basix_element.tabulate(1, X)` in the synthetic tests."""
+    if cell == "triangle":
+        return lagrange_triangle(degree, X)
+    if cell == "tetrahedron":
+        return lagrange_tetrahedron(degree, X)
+    if cell == "quadrilateral":
+        return lagrange_quadrilateral(degree, X)
+    if cell == "hexahedron":
+        return lagrange_hexahedron(degree, X)
+    raise ValueError(cell)
+
+
+def table_sets(cell: str, degree: int, geometry_degree: int, X: np.ndarray, facets: bool = False):
+    """(phi (n_sets, nq, nb), dphi (n_sets, tdim, nq, nb), dgeo (n_sets, tdim, nq, ng)) for `eo_gtab_create`:
+    one set at the cell points X, or one per local facet at the facet points X (facets=True)."""
+    Xs = facet_points(cell, X) if facets else np.asarray(X, dtype=np.float64)[None]
+    phi, dphi, dgeo = [], [], []
+    for Xc in Xs:
+        p, d = tabulate_on(cell, degree, Xc)
+        _, g = tabulate_on(cell, geometry_degree, Xc)
+        phi.append(p), dphi.append(d), dgeo.append(g)
+    return np.ascontiguousarray(np.stack(phi)), np.ascontiguousarray(np.stack(dphi)), np.ascontiguousarray(np.stack(dgeo))

@@ -120,11 +120,76 @@ def _reference_expression_eval(external_operator, operand, entities):
     return expr.eval(operand_mesh, entities)
 
 
+def assignment_pairs(external_operator, n_values: int):
+    """The reference's non-contiguous assignments (:286-335) as index pairs: the statement sequence
+    `x.array[targets[j]] = values.reshape(-1)[sources[j]]` for j = 0, 1, 2, ... is what `_assign_non_mixed`
+    (:286-287), `_assign_mixed_2d` (:292-311) and `_assign_mixed_3d` (:313-335) perform."""
+    if not getattr(external_operator, "_is_mixed", False):
+        targets = np.asarray(external_operator.unrolled_dofmap, dtype=np.int64).reshape(-1)
+        if targets.size != n_values:  # what NumPy raises for x.array[dofmap] = values (:287, re-raised at :440-444)
+            raise ValueError(f"shape mismatch: value array of shape ({n_values},) could not be broadcast to indexing "
+                             f"result of shape ({targets.size},)")
+        return targets, np.arange(n_values, dtype=np.int64)
+    npt = int(external_operator._n_points_total)
+    comp = int(external_operator._comp_size)
+    n_cells = n_values // (npt * comp)
+    if n_cells * npt * comp != n_values:
+        raise ValueError(f"cannot reshape array of size {n_values} into shape ({n_cells},{npt}" + (f",{comp})" if comp > 1 else ")"))
+    cells = np.arange(n_cells, dtype=np.int64)[:, None]
+    targets, sources = [], []
+    for info in external_operator._mixed_subspace_info:
+        offset, n_pts = int(info["offset"]), int(info["n_pts"])
+        flat_dofs = np.asarray(info["flat_dofs"], dtype=np.int64).reshape(-1)
+        pts = np.arange(n_pts, dtype=np.int64)[None, :]
+        if comp == 1:  # :305-311  block = values[:, offset:offset+n_pts]
+            src = (cells * npt + offset + pts).reshape(-1)
+        else:  # :325-335  block = values[:, offset:offset+n_pts, :val_size].reshape(n_cells, dofs_per_cell)
+            vs, dpc = int(info["val_size"]), int(info["dofs_per_cell"])
+            if n_pts * vs != dpc:
+                raise ValueError(f"cannot reshape array of size {n_cells * n_pts * vs} into shape ({n_cells},{dpc})")
+            src = ((cells[:, :, None] * npt + offset + pts[:, :, None]) * comp + np.arange(vs, dtype=np.int64)[None, None, :]).reshape(-1)
+        if flat_dofs.size != src.size:
+            raise ValueError(f"shape mismatch: value array of shape ({src.size},) could not be broadcast to indexing "
+                             f"result of shape ({flat_dofs.size},)")
+        targets.append(flat_dofs)
+        sources.append(src)
+    return np.concatenate(targets), np.concatenate(sources)
+
+
+class AssignPlan:
+    """The scatter of :286-335 turned inside out, once per operator: for every degree of freedom the index of the
+    value that NumPy's last-one-wins fancy assignment would leave there.  `apply` is then a race-free device
+    gather (`eo_assign_gather`) whose output is the compact coefficient array - the only thing that crosses PCIe."""
+
+    def __init__(self, ctx, external_operator, n_values: int):
+        x_array = external_operator.ref_coefficient.x.array
+        targets, sources = assignment_pairs(external_operator, n_values)
+        if targets.size and (targets.min() < 0 or targets.max() >= x_array.size):
+            raise IndexError(f"index {int(targets.max())} is out of bounds for axis 0 with size {x_array.size}")
+        src_for_dof = np.full(x_array.size, -1, dtype=np.int64)
+        src_for_dof[targets] = sources  # NumPy keeps the last assignment for repeated targets - exactly the rule wanted
+        self.ctx, self.n_values, self.n_dofs = ctx, int(n_values), int(x_array.size)
+        self.touched = None
+        if (src_for_dof < 0).any():  # dofs the operator never writes keep their old values
+            self.touched = np.nonzero(src_for_dof >= 0)[0]
+            src_for_dof = src_for_dof[self.touched]
+            self._tmp = ctx.pinned_empty(self.touched.size)
+        self.src = ctx.to_device(np.ascontiguousarray(src_for_dof))
+
+    def apply(self, values: DeviceArray, x_array: np.ndarray) -> None:
+        c = self.ctx
+        out = x_array if self.touched is None else self._tmp
+        c.check(c.lib.eo_assign_gather(c.handle, values.ptr, self.n_values, self.src.ptr, self.src.size, out.ctypes.data))
+        c.sync()
+        if self.touched is not None:
+            x_array[self.touched] = self._tmp
+
+
 def _assign(external_operator, values) -> None:
     """`external_operator._assign_func(values)` (:440-444) with two additions: values that
     already ARE the coefficient array (a model bound with `bind_outputs`) are not copied again,
-    and `DeviceArray` values are downloaded straight into the coefficient array when the
-    assignment is the contiguous one (:289-290)."""
+    `DeviceArray` values are downloaded straight into the coefficient array when the assignment is the
+    contiguous one (:289-290), and go through a cached `AssignPlan` (device gather) when it is not (:286-335)."""
     x_array = external_operator.ref_coefficient.x.array
     if isinstance(values, np.ndarray) and values.ctypes.data == x_array.ctypes.data and values.size == x_array.size:
         return
@@ -138,7 +203,13 @@ def _assign(external_operator, values) -> None:
                 )
             values.to_host(x_array.reshape(values.shape))
             return
-        values = values.to_host().reshape(-1)
+        # continuous / mixed coefficient spaces (:286-335): gather on the device, download the compact dof array
+        plan = getattr(external_operator, "_b200_assign_plan", None)
+        if plan is None or plan.n_values != values.size or plan.n_dofs != x_array.size or plan.ctx is not values.ctx:
+            plan = AssignPlan(values.ctx, external_operator, values.size)
+            external_operator._b200_assign_plan = plan
+        plan.apply(values, x_array)
+        return
     external_operator._assign_func(values)
 
 

@@ -51,13 +51,16 @@ class JitModel:
     params         : up to 32 doubles, passed in the kernel's constant bank
     returns        : what the inner callable returns, names out | value | aux<i> | state<i>;
                      default: ("out",) -> a bare flat array
+    output         : "host" - results in pinned host arrays owned by the model (the protocol's default);
+                     "device" - results stay in HBM as `DeviceArray`s (consumed by
+                     `evaluate_external_operators`, which downloads / gathers them into the coefficient)
     supported      : optional set of derivative tuples to accept; others raise NotImplementedError
                      like the reference demos do (demo_vm:364-368)
     """
 
     def __init__(self, source: str, entry: str, operand_shapes, out_shape=(), *, state_shapes=(), aux_shapes=(),
-                 params=(), fmad: bool = True, returns=("out",), supported=None, ctx: Context | None = None,
-                 compile_only: bool = False):
+                 params=(), fmad: bool = True, returns=("out",), supported=None, output: str = "host",
+                 ctx: Context | None = None, compile_only: bool = False):
         self.lib = _lib.load()
         self.ctx = None if compile_only else (ctx or default_context())
         self.operand_shapes = list(operand_shapes)
@@ -71,6 +74,10 @@ class JitModel:
         if self.params.size > EO_JIT_MAX_PARAMS:
             raise ValueError(f"at most {EO_JIT_MAX_PARAMS} parameters")
         self.returns = tuple(returns)
+        if output not in ("host", "device"):
+            raise ValueError("output must be 'host' or 'device'")
+        self.output = output
+        self._dev_out: dict[str, DeviceArray] = {}
         self.supported = None if supported is None else {tuple(d) for d in supported}
         self._src = source.encode()
         self._entry = entry.encode()
@@ -211,6 +218,12 @@ class JitModel:
             if name in device_out:
                 bufs[name] = device_out[name]
                 return device_out[name].ptr
+            if self.output == "device" and (name == "out" or name in self.returns):
+                a = self._dev_out.get(name)
+                if a is None or a.size != size:
+                    a = self._dev_out[name] = self.ctx.empty((size,))
+                bufs[name] = a
+                return a.ptr
             if name == "out" or name in self.returns:
                 bufs[name] = self._buf(name, size)
                 return _ptr(bufs[name])

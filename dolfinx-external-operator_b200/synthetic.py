@@ -187,3 +187,63 @@ def smooth_displacement(dof_coords: np.ndarray, scale: float = 1e-3, seed: int =
         u[:, c] = scale * (a[c, 0] * x + a[c, 1] * y + a[c, 2] * np.sin(3 * x + a[c, 3]) * np.cos(2 * y) + a[c, 4] * x * y
                            + a[c, 5] * y * y)
     return u
+
+
+def quad_mesh(nx: int, ny: int, degree: int = 1, jitter: float = 0.0, seed: int = 0):
+    """Structured quadrilateral mesh of the unit square with Q1 (bilinear, non-affine when jittered) geometry and a
+    Q`degree` Lagrange space, all in TENSOR ordering (elements.lagrange_quadrilateral): local node (i, j) -> i*(d+1)+j.
+    Returns dict(x, x_dofmap (n_cells, 4), dofmap (n_cells, (d+1)^2), n_dofs, dof_coords)."""
+    nvx, nvy = nx + 1, ny + 1
+    X, Y = np.meshgrid(np.linspace(0.0, 1.0, nvx), np.linspace(0.0, 1.0, nvy), indexing="ij")  # [i][j]
+    if jitter > 0.0:
+        rng = np.random.default_rng(seed)
+        X[1:-1, 1:-1] += jitter / nx * rng.uniform(-1, 1, (nvx - 2, nvy - 2))
+        Y[1:-1, 1:-1] += jitter / ny * rng.uniform(-1, 1, (nvx - 2, nvy - 2))
+    x = np.zeros((nvx * nvy, 3))
+    x[:, 0], x[:, 1] = X.reshape(-1), Y.reshape(-1)
+    ci, cj = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    ci, cj = ci.reshape(-1), cj.reshape(-1)
+    vid = lambda i, j: i * nvy + j  # noqa: E731
+    x_dofmap = np.stack([vid(ci + a, cj + b) for a in (0, 1) for b in (0, 1)], axis=1).astype(np.int32)
+    d = degree
+    ndx, ndy = d * nx + 1, d * ny + 1
+    did = lambda i, j: i * ndy + j  # noqa: E731
+    dofmap = np.stack([did(d * ci + a, d * cj + b) for a in range(d + 1) for b in range(d + 1)], axis=1).astype(np.int32)
+    # dof coordinates: the bilinear geometry map of each cell evaluated at the local node positions
+    from . import elements as el
+
+    t = np.linspace(0.0, 1.0, d + 1)
+    Xn = np.array([[a, b] for a in t for b in t])
+    gphi, _ = el.lagrange_quadrilateral(1, Xn)  # (nb, 4)
+    dof_coords = np.zeros((ndx * ndy, 2))
+    dof_coords[dofmap] = np.einsum("cvi,av->cai", x[x_dofmap][:, :, :2], gphi)
+    return {"x": x, "x_dofmap": x_dofmap, "dofmap": dofmap, "n_dofs": ndx * ndy, "dof_coords": dof_coords}
+
+
+def hex_mesh(n: int, degree: int = 1, jitter: float = 0.0, seed: int = 0):
+    """Structured hexahedral mesh of the unit cube, Q1 geometry (trilinear), Q`degree` space, tensor ordering
+    (i, j, k) -> (i*(d+1) + j)*(d+1) + k."""
+    nv = n + 1
+    g = np.linspace(0.0, 1.0, nv)
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    if jitter > 0.0:
+        rng = np.random.default_rng(seed)
+        for A in (X, Y, Z):
+            A[1:-1, 1:-1, 1:-1] += jitter / n * rng.uniform(-1, 1, (nv - 2,) * 3)
+    x = np.stack([X.reshape(-1), Y.reshape(-1), Z.reshape(-1)], axis=1)
+    ci, cj, ck = (a.reshape(-1) for a in np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij"))
+    vid = lambda i, j, k: (i * nv + j) * nv + k  # noqa: E731
+    x_dofmap = np.stack([vid(ci + a, cj + b, ck + c) for a in (0, 1) for b in (0, 1) for c in (0, 1)], axis=1).astype(np.int32)
+    d = degree
+    nd = d * n + 1
+    did = lambda i, j, k: (i * nd + j) * nd + k  # noqa: E731
+    dofmap = np.stack([did(d * ci + a, d * cj + b, d * ck + c) for a in range(d + 1) for b in range(d + 1)
+                       for c in range(d + 1)], axis=1).astype(np.int32)
+    from . import elements as el
+
+    t = np.linspace(0.0, 1.0, d + 1)
+    Xn = np.array([[a, b, c] for a in t for b in t for c in t])
+    gphi, _ = el.lagrange_hexahedron(1, Xn)
+    dof_coords = np.zeros((nd**3, 3))
+    dof_coords[dofmap] = np.einsum("cvi,av->cai", x[x_dofmap], gphi)
+    return {"x": x, "x_dofmap": x_dofmap, "dofmap": dofmap, "n_dofs": nd**3, "dof_coords": dof_coords}

@@ -179,3 +179,108 @@ class _Plan:
 
     def evaluate(self, entities=None):
         return self.tab.evaluate(self.kind_id, self.coefficient, entities, self.output)
+
+
+class GeneralTabulator(Tabulator):
+    """Tabulation for everything beyond the affine-simplex fast path (`eo_gtab_*`, csrc/tabg.cu): any element given
+    by its tables (quadrilaterals, hexahedra, higher degrees), non-affine geometry (`dgeo`: derivative tables of the
+    geometry element, Jacobian per point) and codimension-1 entities: pass one table set per local facet
+    (`phi.shape == (n_facets, nq, nb)`) and `entities` of shape (n, 2) = (cell, local facet), the form the reference
+    uses for boundary operators (test_codim_external_operator.py:75-109).
+
+        phi (n_sets, nq, nb) | (nq, nb);  dphi (n_sets, gdim, nq, nb) | (gdim, nq, nb);  dgeo likewise with ng columns
+    """
+
+    def __init__(self, *, dofmap, x_dofmap, x, phi, dphi, dgeo, bs: int = 1, n_dofs: int | None = None,
+                 coefficient=None, ctx: Context | None = None):
+        from ._lib import GTabDesc
+
+        self.ctx = ctx or default_context()
+        self.dofmap = np.ascontiguousarray(dofmap, dtype=np.int32)
+        self.x_dofmap = np.ascontiguousarray(x_dofmap, dtype=np.int32)
+        x = np.asarray(x, dtype=np.float64)
+        if x.shape[1] == 2:
+            x = np.concatenate([x, np.zeros((x.shape[0], 1))], axis=1)
+        self.x = np.ascontiguousarray(x)
+        phi, dphi, dgeo = (np.asarray(a, dtype=np.float64) for a in (phi, dphi, dgeo))
+        if phi.ndim == 2:
+            phi, dphi, dgeo = phi[None], dphi[None], dgeo[None]
+        self.phi, self.dphi, self.dgeo = (np.ascontiguousarray(a) for a in (phi, dphi, dgeo))
+        self.n_sets, self.nq, self.nb = (int(s) for s in self.phi.shape)
+        self.gdim = int(self.dphi.shape[1])
+        self.ng = int(self.dgeo.shape[3])
+        self.bs = int(bs)
+        self.n_cells = int(self.dofmap.shape[0])
+        self.n_dofs = int(n_dofs) if n_dofs is not None else (int(self.dofmap.max()) + 1 if self.dofmap.size else 0)
+        if self.dphi.shape != (self.n_sets, self.gdim, self.nq, self.nb) or self.dofmap.shape[1] != self.nb:
+            raise ValueError("table / dofmap shapes are inconsistent")
+        if self.dgeo.shape != (self.n_sets, self.gdim, self.nq, self.ng) or self.x_dofmap.shape != (self.n_cells, self.ng):
+            raise ValueError("geometry table / x_dofmap shapes are inconsistent")
+        d = GTabDesc(self.gdim, self.bs, self.nb, self.nq, self.ng, self.n_sets, self.n_cells, self.n_dofs, self.x.shape[0],
+                     self.dofmap.ctypes.data, self.x_dofmap.ctypes.data, self.x.ctypes.data, self.phi.ctypes.data,
+                     self.dphi.ctypes.data, self.dgeo.ctypes.data)
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.eo_gtab_create(self.ctx.handle, C.byref(d), C.byref(h)))
+        self._h = h
+        self.coefficient = coefficient
+        self._plans = {}
+
+    @classmethod
+    def from_function_space(cls, V, Q, coefficient=None, facets: bool = False, ctx: Context | None = None):
+        """From DOLFINx objects: `Q`'s interpolation points are the evaluation points - points of the cell, or
+        (facets=True, Q on a codim-1 submesh) points of the reference facet, mapped onto every local facet with
+        `elements.facet_points` (basix's sub-entity ordering)."""
+        mesh = V.mesh
+        tdim = mesh.topology.dim
+        pts = np.asarray(Q.element.interpolation_points, dtype=np.float64)
+        cell = mesh.topology.cell_name()
+        Xs = elements.facet_points(cell, pts) if facets else pts[None]
+        phi, dphi, dgeo = [], [], []
+        for X in Xs:
+            t = np.asarray(V.element.basix_element.tabulate(1, X))
+            t = t.reshape(t.shape[0], t.shape[1], -1)
+            g = np.asarray(mesh.geometry.cmap.tabulate(1, X))
+            g = g.reshape(g.shape[0], g.shape[1], -1)
+            phi.append(t[0]), dphi.append(t[1:1 + tdim]), dgeo.append(g[1:1 + tdim])
+        return cls(dofmap=V.dofmap.list, x_dofmap=mesh.geometry.dofmap, x=mesh.geometry.x, phi=np.stack(phi),
+                   dphi=np.stack(dphi), dgeo=np.stack(dgeo), bs=V.dofmap.index_map_bs,
+                   n_dofs=V.dofmap.index_map.size_local + V.dofmap.index_map.num_ghosts, coefficient=coefficient, ctx=ctx)
+
+    def close(self):
+        if self._h is not None:
+            self.ctx.lib.eo_gtab_destroy(self._h)
+            self._h = None
+
+    def ncomp(self, kind) -> int:
+        k = KINDS[kind] if isinstance(kind, str) else int(kind)
+        n = self.ctx.lib.eo_gtab_ncomp(self._h, k)
+        if n < 0:
+            raise ValueError(f"operand kind {kind!r} does not fit this element (gdim={self.gdim}, bs={self.bs})")
+        return n
+
+    def evaluate(self, kind, coefficient=None, entities=None, output: str = "device", out=None):
+        """Operand of `kind` on `entities`: None = all cells (:365-371), (n,) int cells, (n, 2) (cell, local facet)."""
+        kind_id = KINDS[kind] if isinstance(kind, str) else int(kind)
+        ncomp = self.ncomp(kind_id)
+        u = self._coeff(coefficient)
+        ent, width, n = None, 0, self.n_cells
+        if entities is not None:
+            ent = np.ascontiguousarray(entities, dtype=np.int32)
+            if ent.ndim == 1:
+                width = 1
+            elif ent.ndim == 2 and ent.shape[1] == 2:
+                width = 2
+            else:
+                raise ValueError("entities must have shape (n,) or (n, 2)")
+            n = int(ent.shape[0])
+        shape = self._shape(kind_id, n)
+        c = self.ctx
+        if out is None:
+            out = c.empty(shape) if output == "device" else np.empty(shape)
+        elif int(np.prod(out.shape)) != n * self.nq * ncomp:
+            raise ValueError("`out` has the wrong size")
+        c.check(c.lib.eo_gtab_tabulate(self._h, kind_id, _ptr(u), _ptr(ent), width, n, _ptr(out)))
+        return out
+
+    def vm_fused(self, *a, **k):
+        raise NotImplementedError("the fused tabulate + von Mises kernel is the affine-triangle fast path (Tabulator)")

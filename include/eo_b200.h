@@ -86,6 +86,18 @@ int eo_host_free(eo_ctx* ctx, void* hptr);
 int eo_host_register(eo_ctx* ctx, void* hptr, size_t bytes);
 int eo_host_unregister(eo_ctx* ctx, void* hptr);
 
+/* ---------------------------------------------------------------- non-contiguous coefficient assignment
+ * replaces: `_assign_non_mixed` (`x.array[unrolled_dofmap] = values`), `_assign_mixed_2d`, `_assign_mixed_3d`,
+ *           external_operator.py:286-335 - continuous and mixed coefficient spaces, where several evaluation
+ *           points write the same degree of freedom and NumPy's fancy assignment keeps the LAST one.
+ * The host side turns the scatter inside out once per operator (for every dof the index of the value that
+ * wins: `src_index`, device resident); the kernel is then the race-free gather out[k] = values[src_index[k]],
+ * bit-identical to the reference's result.  values : device [n_values]; src_index : device int64 [n_out],
+ * entries in [0, n_values) (checked by the host side when the plan is built); out : any-side [n_out] - e.g.
+ * the host `ref_coefficient.x.array` itself, so only the compact dof array crosses PCIe. */
+int eo_assign_gather(eo_ctx* ctx, const double* values, int64_t n_values, const int64_t* src_index, int64_t n_out,
+                     double* out);
+
 /* ---------------------------------------------------------------- timing
  * CUDA events on the ctx compute stream (bench.py times kernels with these). */
 int eo_event_create(eo_ctx* ctx, void** ev);
@@ -221,6 +233,39 @@ int eo_tabulate(eo_tab* tab, int kind, const double* u, const int32_t* cells, in
  * issue-bound, not HBM-bound). */
 int eo_tab_vm_fused(eo_tab* tab, const eo_vm_params* prm, const double* u, const double* sigma_n, const double* p,
                     double* C_tang, double* sigma, double* dp, double* strain, int exact);
+
+/* ---------------------------------------------------------------- general operand tabulation
+ * replaces: `expr.eval(operand_mesh, entities)`, external_operator.py:365-402, for everything the affine-simplex
+ *           fast path above does not cover: any element given by its tables (higher-degree simplices,
+ *           quadrilaterals, hexahedra), non-affine geometry (the Jacobian is evaluated per point from the geometry
+ *           element's derivative tables) and codimension-1 `entities` of shape (n, 2) = (cell, local facet)
+ *           (test/test_codim_external_operator.py:75-109): one table set per local facet, tabulated by basix on
+ *           the host at the facet's points mapped into the reference cell.
+ * One thread per (entity, point); tables in shared memory when they fit. */
+typedef struct eo_gtab_desc {
+  int32_t gdim;            /* geometric = topological dimension, 2 or 3                                     */
+  int32_t bs;              /* block size of the coefficient, 1..3                                           */
+  int32_t nb;              /* scalar basis functions per cell, 1..125                                       */
+  int32_t nq;              /* evaluation points per entity, 1..125                                          */
+  int32_t ng;              /* geometry nodes per cell (3 triangle, 4 quadrilateral/tetrahedron, 8 hexahedron, 6 P2 triangle ...) */
+  int32_t n_sets;          /* table sets: 1 = points inside the cell; number of local facets for codim-1    */
+  int64_t n_cells, n_dofs, n_nodes;
+  const int32_t* dofmap;   /* [n_cells][nb]                                                                 */
+  const int32_t* x_dofmap; /* [n_cells][ng]                                                                 */
+  const double* x;         /* [n_nodes][3]                                                                  */
+  const double* phi;       /* [n_sets][nq][nb]        basix tabulate(1, X_set)[0]                           */
+  const double* dphi;      /* [n_sets][gdim][nq][nb]  basix tabulate(1, X_set)[1:]                          */
+  const double* dgeo;      /* [n_sets][gdim][nq][ng]  the geometry element's tabulate(1, X_set)[1:]         */
+} eo_gtab_desc;
+
+typedef struct eo_gtab eo_gtab;
+int eo_gtab_create(eo_ctx* ctx, const eo_gtab_desc* desc, eo_gtab** out);
+int eo_gtab_destroy(eo_gtab* tab);
+int eo_gtab_ncomp(const eo_gtab* tab, int kind);
+/* out[n_entities][nq][ncomp].  entity_width 0: entities == NULL, cells 0..n_entities-1 (:365-371);
+ * 1: int32 cell indices; 2: int32 (cell, local facet) pairs.  u, entities and out are any-side pointers. */
+int eo_gtab_tabulate(eo_gtab* tab, int kind, const double* u, const int32_t* entities, int entity_width,
+                     int64_t n_entities, double* out);
 
 /* ---------------------------------------------------------------- Mohr-Coulomb
  * replaces: `dsigma_ddeps_vec = jit(vmap(jacfwd(return_mapping, has_aux=True)))` and the body of

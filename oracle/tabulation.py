@@ -44,3 +44,39 @@ def tabulate(kind, u, dofmap, bs, x, x_dofmap, phi, dphi, dpsi, cells=None):
     if kind == DEF_GRAD:  # demo_hyperelasticity.py:479
         return (g + np.eye(gdim)[None, None]).reshape(nc, nq, bs * gdim)
     raise ValueError(kind)
+
+
+def tabulate_general(kind, u, dofmap, bs, x, x_dofmap, phi, dphi, dgeo, entities=None):
+    """General restatement: any element given by table sets, Jacobian per evaluation point (non-affine cells),
+    `entities` None / (n,) cells / (n, 2) (cell, local facet) pairs (external_operator.py:365-371,
+    test_codim_external_operator.py:75-109).  phi (n_sets, nq, nb); dphi (n_sets, gdim, nq, nb);
+    dgeo (n_sets, gdim, nq, ng) derivatives of the geometry element.  out (n_entities, nq, ncomp).
+    PARITY UNPINNED like `tabulate` (same third-party arithmetic); checked against analytic fields."""
+    gdim = dphi.shape[1]
+    if entities is None:
+        cells = np.arange(dofmap.shape[0])
+        sets = np.zeros(cells.size, dtype=np.int64)
+    else:
+        ent = np.asarray(entities)
+        cells = ent if ent.ndim == 1 else ent[:, 0]
+        sets = np.zeros(cells.size, dtype=np.int64) if ent.ndim == 1 else ent[:, 1]
+    w = np.asarray(u, dtype=np.float64).reshape(-1, bs)[dofmap[cells]]  # (ne, nb, bs)
+    xv = x[x_dofmap[cells]][:, :, :gdim]  # (ne, ng, gdim)
+    J = np.einsum("evi,ejqv->eqij", xv, dgeo[sets])  # J_ij(q) = sum_v x_vi dpsi_v/dX_j (q)
+    K = np.linalg.inv(J)
+    if kind == VALUE:
+        return np.einsum("eab,eqa->eqb", w, phi[sets])
+    G = np.einsum("eab,ekqa->eqbk", w, dphi[sets])
+    g = np.einsum("eqbk,eqkj->eqbj", G, K)
+    ne, nq = g.shape[:2]
+    if kind == GRAD:
+        return g.reshape(ne, nq, bs * gdim)
+    if kind == MANDEL_STRAIN:
+        out = np.zeros((ne, nq, 4))
+        out[:, :, 0] = g[:, :, 0, 0]
+        out[:, :, 1] = g[:, :, 1, 1]
+        out[:, :, 3] = np.sqrt(2.0) * 0.5 * (g[:, :, 0, 1] + g[:, :, 1, 0])
+        return out
+    if kind == DEF_GRAD:
+        return (g + np.eye(gdim)[None, None]).reshape(ne, nq, bs * gdim)
+    raise ValueError(kind)

@@ -36,3 +36,37 @@ def tet_case(n=3, seed=0):
     phi, dphi = el.lagrange_tetrahedron(1, X)
     return {"x": x, "x_dofmap": xd, "dofmap": xd.copy(), "n_dofs": x.shape[0], "phi": phi, "dphi": dphi,
             "dpsi": el.p1_geometry_derivatives(3), "X": X, "dof_coords": x}
+
+
+def general_case(cell: str, degree: int, bs: int, facets: bool = False, seed: int = 0):
+    """Synthetic mesh + consistent table sets for the general tabulation path.  Returns the mesh dict extended with
+    phi / dphi / dgeo (n_sets, ...), the reference points X, the cell name and physical evaluation points `xq`
+    (n_sets, n_cells, nq, gdim)."""
+    if cell == "triangle":
+        m = syn.triangle_mesh(7, 5, degree, jitter=0.3, seed=seed)
+        Xc = el.triangle_quadrature(2)
+        Xf = np.array([[0.2113248654051871], [0.7886751345948129]])
+    elif cell == "quadrilateral":
+        m = syn.quad_mesh(6, 5, degree, jitter=0.3, seed=seed)
+        g = np.array([0.2113248654051871, 0.7886751345948129])
+        Xc = np.array([[a, b] for a in g for b in g])
+        Xf = g[:, None]
+    elif cell == "hexahedron":
+        m = syn.hex_mesh(3, degree, jitter=0.25, seed=seed)
+        g = np.array([0.2113248654051871, 0.7886751345948129])
+        Xc = np.array([[a, b, c] for a in g for b in g for c in g])
+        Xf = np.array([[a, b] for a in g for b in g])
+    elif cell == "tetrahedron":
+        m = tet_case(3, seed)
+        Xc = np.array([[0.25, 0.25, 0.25], [0.1, 0.2, 0.3], [0.5, 0.2, 0.1]])
+        Xf = np.array([[1 / 3, 1 / 3], [0.2, 0.6]])
+    else:
+        raise ValueError(cell)
+    X = Xf if facets else Xc
+    phi, dphi, dgeo = el.table_sets(cell, degree, 1, X, facets=facets)
+    gphi = np.stack([el.tabulate_on(cell, 1, Xs)[0] for Xs in (el.facet_points(cell, X) if facets else X[None])])
+    gdim = dphi.shape[1]
+    m = dict(m)
+    m.update(phi=phi, dphi=dphi, dgeo=dgeo, X=X, cell=cell, bs=bs, gdim=gdim,
+             xq=np.einsum("cvi,sqv->scqi", m["x"][m["x_dofmap"]][:, :, :gdim], gphi))
+    return m
