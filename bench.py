@@ -37,7 +37,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BYTES_PER_QP = {"vm": 240, "jitvm": 240, "heat": 88, "mc": 252, "tab": 176.0 / 3.0, "fused": 235, "isihara": 192}
+BYTES_PER_QP = {"vm": 240, "jitvm": 240, "jitfused": 235, "heat": 88, "mc": 252, "tab": 176.0 / 3.0, "fused": 235, "isihara": 192}
 METRIC = "quadrature points per second (stress + consistent tangent + internal state)"
 
 
@@ -250,6 +250,8 @@ WORKLOADS = {
                "tangent dP/dF from the 3-64-64-64-1 float32 network, float64 invariants",
     "jitvm": "von Mises return mapping written as a user model for the run-time compiled (NVRTC) generic path: "
              "stress + tangent by forward-mode dual numbers + plastic multiplier, plane-strain Mandel 4-vectors",
+    "jitfused": "operand tabulation fused into the run-time compiled (NVRTC) von Mises user model: P2 vector field, 3 points "
+                "per triangle, strain never stored, tangent by dual numbers",
     "tab": "operand tabulation: Mandel strain of a P2 vector field at 3 quadrature points per triangle "
            "(evaluate_operands for the von Mises / Mohr-Coulomb demos), structured jittered mesh",
     "fused": "operand tabulation fused with the von Mises return mapping (strain never stored), P2 vector field, "
@@ -375,7 +377,7 @@ def run_gpu_arm(args):
 
         def step():
             isi.eval_device(d_F, d_dP, d_P)
-    elif model in ("tab", "fused"):
+    elif model in ("tab", "fused", "jitfused"):
         from dolfinx_external_operator_b200 import elements as el
 
         nxy = max(2, int(round((n / 6.0) ** 0.5)))
@@ -393,6 +395,21 @@ def run_gpu_arm(args):
 
             def step():
                 tab.evaluate("mandel_strain", d_u, out=d_out)
+        elif model == "jitfused":
+            from dolfinx_external_operator_b200 import jit_models as jm
+            from dolfinx_external_operator_b200.tabulation import LazyOperand
+
+            jv = jm.von_mises(ctx=ctx)
+            _, sn_t, p_t = inputs.vm_batch(tile_n, seed=rank)
+            jv.state = [ctx.empty((n * 4,)), ctx.empty((n,))]
+            _tile_to_device(ctx, jv.state[0], sn_t, n, 4)
+            _tile_to_device(ctx, jv.state[1], p_t, n, 1)
+            dev = {"out": ctx.empty((n * 16,)), "value": ctx.empty((n * 4,)), "aux0": ctx.empty((n,))}
+            lz = [LazyOperand(tab, 2, d_u)]
+            dd = jv._deriv((1,))[1]
+
+            def step():
+                jv._evaluate_fused((1,), dd, 16, lz, dev)
         else:
             vm = eo.VonMises(n_qp=n, ctx=ctx)
             _, sn_t, p_t = inputs.vm_batch(tile_n, seed=rank)
@@ -548,8 +565,8 @@ def run_gpu_arm(args):
     if model == "isihara":
         cpu = None  # the CPU implementation is the reference's torch code, which needs /root/reference: timed in the
         #             build container only (69 k QP/s on 8 threads)
-    elif args.cpu_seconds > 0 and model in ("tab", "fused"):
-        cpu = cpu_tab_rate(model, args.cpu_seconds)
+    elif args.cpu_seconds > 0 and model in ("tab", "fused", "jitfused"):
+        cpu = cpu_tab_rate("fused" if model == "jitfused" else model, args.cpu_seconds)
     elif args.cpu_seconds > 0:
         sample = int(args.cpu_sample) if model != "mc" else min(int(args.cpu_sample), 200_000)
         cm = "vm" if model == "jitvm" else model
@@ -593,7 +610,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--model", default="vm", choices=["vm", "heat", "mc", "tab", "fused", "isihara", "jitvm"])
+    ap.add_argument("--model", default="vm", choices=["vm", "heat", "mc", "tab", "fused", "isihara", "jitvm", "jitfused"])
     ap.add_argument("--fused-exact", action="store_true")
     ap.add_argument("--mc-scheme", default="queue", choices=["queue", "simple", "queue-noaffinity"])
     ap.add_argument("--n", type=float, default=1e8, help="quadrature points per GPU (device-resident leg)")

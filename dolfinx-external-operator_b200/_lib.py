@@ -150,6 +150,10 @@ PROTOTYPES = {
     "eo_jit_last_error": (C.c_char_p, [_vp]),
     "eo_jit_out_width": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "eo_jit_eval": (C.c_int, [_vp, C.POINTER(C.c_int), _vp, C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, C.POINTER(_vp), _i64]),
+    "eo_jit_eval_tabulated": (C.c_int, [_vp, C.POINTER(C.c_int), _vp, C.POINTER(_vp), C.POINTER(C.c_int), C.POINTER(_vp),
+                                        C.POINTER(_vp), _vp, _vp, C.POINTER(_vp)]),
+    "eo_jit_compile_tabulated": (C.c_int, [_vp, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                           C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     "eo_mc_eval": (C.c_int, [_vp, C.POINTER(McParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
     "eo_mc_eval_scheme": (C.c_int, [_vp, C.POINTER(McParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_int]),
 }

@@ -156,6 +156,12 @@ class VonMises(_ModelBase):
 
     def C_tang_impl(self, deps):
         """deps (n_cells, n_pts, 4) -> (C_tang.reshape(-1), sigma.reshape(-1), dp.reshape(-1)), demo_vm:343-352."""
+        from .tabulation import LazyOperand
+
+        if isinstance(deps, LazyOperand):
+            if self._resident and self.state_layout == EO_LAYOUT_AOS and deps.kind_id == 2:
+                return self._C_tang_fused(deps)
+            deps = deps.materialize()
         deps = _as_input(deps)
         n = _n_points(deps) if len(deps.shape) > 1 else deps.shape[0] // 4
         c = self.ctx
@@ -193,6 +199,22 @@ class VonMises(_ModelBase):
                 raise ValueError("history arrays do not match the operand's quadrature-point count")
             c.check(c.lib.eo_vm_eval(c.handle, C.byref(self._prm), _ptr(deps), _ptr(sn), _ptr(pp), _ptr(C_tang),
                                      _ptr(sigma), _ptr(dp), n))
+        c.sync()
+        return C_tang, sigma, dp
+
+    def _C_tang_fused(self, lazy):
+        """The operand is an un-tabulated Mandel strain: tabulation + radial return in one kernel (eo_tab_vm_fused,
+        exact arithmetic: bit-identical to the two-step path), the strain never touches HBM."""
+        n = lazy.tab.n_cells * lazy.tab.nq
+        c = self.ctx
+        d_Ct = getattr(self, "_fused_Ct", None)
+        if d_Ct is None or d_Ct.size != 16 * n:
+            d_Ct = self._fused_Ct = c.empty((16 * n,))
+        lazy.tab.vm_fused(self, lazy.coefficient, C_tang=d_Ct, exact=True)
+        C_tang, sigma, dp = self._out("C_tang", 16 * n), self._out("sigma", 4 * n), self._out("dp", n)
+        d_Ct.to_host(C_tang)
+        self.sigma_dev.to_host(sigma)
+        self.dp_dev.to_host(dp)
         c.sync()
         return C_tang, sigma, dp
 

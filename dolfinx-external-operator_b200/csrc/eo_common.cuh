@@ -55,6 +55,20 @@ int eo_fail(eo_ctx* ctx, int code, const char* fmt, ...);
 // true when `p` is memory the GPU kernels can dereference in place
 bool eo_is_device_ptr(const void* p);
 
+// what jit.cu needs from an eo_tab (defined in tab.cu)
+struct tab_tables;
+struct eo_tab_view {
+  eo_ctx* ctx;
+  const tab_tables* T_host;
+  const tab_tables* T_dev;
+  const int32_t* dofmap;
+  const int32_t* x_dofmap;
+  const double* x;
+  const double* u;  // device pointer of the (possibly staged) coefficient vector
+  int64_t n_cells, n_dofs;
+};
+int eo_tab_view_get(eo_tab* t, const double* u, eo_tab_view* v);
+
 // ------------------------------------------------------------------------------------
 // Any-side argument of a per-quadrature-point ("streamed") operation.
 // ------------------------------------------------------------------------------------

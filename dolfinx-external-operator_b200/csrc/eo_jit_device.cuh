@@ -9,6 +9,9 @@
 // path, seeds the dual numbers, calls the user's model and streams the results back the same way.
 #pragma once
 #include "eo_dual.h"
+#ifdef EO_JIT_FUSED
+#include "tab_core.cuh"
+#endif
 
 #define EO_JIT_MAX_ARGS 8
 #define EO_JIT_MAX_PARAMS 32
@@ -21,6 +24,18 @@ struct eo_jit_args {
   double* aux[EO_JIT_MAX_ARGS];
   long long n;
   double prm[EO_JIT_MAX_PARAMS];
+};
+
+// Fused variant (operands tabulated in the kernel from DOF coefficients, never stored): one tabulation source
+// per operand.  `operand[]` of the base is unused.
+struct tab_tables;
+struct eo_jit_fused_args : eo_jit_args {
+  const tab_tables* T[EO_JIT_MAX_ARGS];  // device copies of the element tables (staged into shared memory)
+  const int* dofmap[EO_JIT_MAX_ARGS];
+  const int* x_dofmap[EO_JIT_MAX_ARGS];
+  const double* x[EO_JIT_MAX_ARGS];
+  const double* u[EO_JIT_MAX_ARGS];
+  long long point_offset;  // global index of this launch's first point (cell = point / NQ); chunked host pipeline
 };
 
 // widest vector access in doubles: 4 (256-bit, needs the CUDA >= 12.9 ptxas) or 2 (jit.cu passes
@@ -141,11 +156,50 @@ struct loader<Spec, NK, NK> {
 
 constexpr int at_least_1(int n) { return n > 0 ? n : 1; }
 
-// ---- order 0: the value ----------------------------------------------------------------------
+// operands of point i: streamed from HBM ...
 template <class Spec>
-__device__ __forceinline__ void run0(const eo_jit_args& a, long long i) {
-  double x[at_least_1(Spec::NIN)], s[at_least_1(Spec::NST)], y[at_least_1(Spec::NOUT)], w[at_least_1(Spec::NAUX)];
+__device__ __forceinline__ void fetch_operands(const eo_jit_args& a, long long i, double* x) {
   loader<Spec, 0, Spec::N_OPERANDS>::operands(a, i, x);
+}
+
+#ifdef EO_JIT_FUSED
+// ... or tabulated on the fly from the cell's DOF coefficients (tab_core.cuh: the same arithmetic as tab_kernel)
+template <class Spec, int K, int NK>
+struct tabber {
+  static __device__ __forceinline__ void run(const eo_jit_fused_args& f, const tab_tables* sT, long long cell, int q, double* x) {
+    constexpr int G = Spec::tab_gdim(K), B = Spec::tab_bs(K), NB = Spec::tab_nb(K), KIND = Spec::tab_kind(K);
+    const tab_tables& T = sT[K];
+    double w[NB][B], Kinv[G][G];
+    tab_load_cell<G, B, NB>(T, f.dofmap[K], f.x_dofmap[K], f.x[K], f.u[K], cell, w, Kinv);
+    double val[B], grad[B][G], r[B * G > 4 ? B * G : 4];
+    tab_point<G, B, NB>(T, w, Kinv, q, KIND == 0, KIND != 0, val, grad);
+    tab_operand<G, B>(KIND, val, grad, r);
+#pragma unroll
+    for (int c = 0; c < Spec::op_size(K); ++c) x[op_offset<Spec, K>::value + c] = r[c];
+    tabber<Spec, K + 1, NK>::run(f, sT, cell, q, x);
+  }
+};
+template <class Spec, int NK>
+struct tabber<Spec, NK, NK> {
+  static __device__ __forceinline__ void run(const eo_jit_fused_args&, const tab_tables*, long long, int, double*) {}
+};
+
+__shared__ tab_tables eo_jit_s_tables[EO_JIT_N_TABLES];
+
+template <class Spec>
+__device__ __forceinline__ void fetch_operands(const eo_jit_fused_args& f, long long i, double* x) {
+  const long long gp = f.point_offset + i;
+  const long long cell = gp / Spec::NQ;
+  const int q = int(gp - cell * Spec::NQ);
+  tabber<Spec, 0, Spec::N_OPERANDS>::run(f, eo_jit_s_tables, cell, q, x);
+}
+#endif
+
+// ---- order 0: the value ----------------------------------------------------------------------
+template <class Spec, class ARGS>
+__device__ __forceinline__ void run0(const ARGS& a, long long i) {
+  double x[at_least_1(Spec::NIN)], s[at_least_1(Spec::NST)], y[at_least_1(Spec::NOUT)], w[at_least_1(Spec::NAUX)];
+  fetch_operands<Spec>(a, i, x);
   loader<Spec, 0, Spec::N_STATE>::states(a, i, s);
   Spec::template call<double>(x, s, a.prm, y, w);
   store_point<Spec::NOUT>(a.out, i, y);
@@ -153,12 +207,12 @@ __device__ __forceinline__ void run0(const eo_jit_args& a, long long i) {
 }
 
 // ---- order 1: d y / d operand[A], layout [point][NOUT][size(A)] --------------------------------
-template <class Spec>
-__device__ __forceinline__ void run1(const eo_jit_args& a, long long i) {
+template <class Spec, class ARGS>
+__device__ __forceinline__ void run1(const ARGS& a, long long i) {
   constexpr int A = Spec::DA, NA = Spec::op_size(A), OA = op_offset<Spec, A>::value;
   using T = eo::dual<NA>;
   double xr[at_least_1(Spec::NIN)], s[at_least_1(Spec::NST)];
-  loader<Spec, 0, Spec::N_OPERANDS>::operands(a, i, xr);
+  fetch_operands<Spec>(a, i, xr);
   loader<Spec, 0, Spec::N_STATE>::states(a, i, s);
   T x[at_least_1(Spec::NIN)], y[at_least_1(Spec::NOUT)], w[at_least_1(Spec::NAUX)];
 #pragma unroll
@@ -187,15 +241,15 @@ __device__ __forceinline__ void run1(const eo_jit_args& a, long long i) {
 }
 
 // ---- order 2: d2 y / d operand[A] d operand[B] (A <= B), layout [point][NOUT][size(A)][size(B)] --
-template <class Spec>
-__device__ __forceinline__ void run2(const eo_jit_args& a, long long i) {
+template <class Spec, class ARGS>
+__device__ __forceinline__ void run2(const ARGS& a, long long i) {
   constexpr int A = Spec::DA, B = Spec::DB;
   constexpr int NA = Spec::op_size(A), OA = op_offset<Spec, A>::value;
   constexpr int NB = Spec::op_size(B), OB = op_offset<Spec, B>::value;
   using V = eo::dual<NB>;
   using T = eo::dual<NA, V>;
   double xr[at_least_1(Spec::NIN)], s[at_least_1(Spec::NST)];
-  loader<Spec, 0, Spec::N_OPERANDS>::operands(a, i, xr);
+  fetch_operands<Spec>(a, i, xr);
   loader<Spec, 0, Spec::N_STATE>::states(a, i, s);
   T x[at_least_1(Spec::NIN)], y[at_least_1(Spec::NOUT)], w[at_least_1(Spec::NAUX)];
 #pragma unroll
@@ -227,16 +281,27 @@ __device__ __forceinline__ void run2(const eo_jit_args& a, long long i) {
   loader<Spec, 0, Spec::N_AUX>::aux(a, i, wv);
 }
 
-template <class Spec>
-__device__ __forceinline__ void run(const eo_jit_args& a) {
+template <class Spec, class ARGS>
+__device__ __forceinline__ void run(const ARGS& a) {
+#ifdef EO_JIT_FUSED
+  {  // stage the element tables (a few KB per operand) in shared memory: the point index q is not warp uniform
+    const int nw = int(sizeof(tab_tables) / 8);
+    for (int k = 0; k < EO_JIT_N_TABLES; ++k) {
+      const double* src = reinterpret_cast<const double*>(a.T[k]);
+      double* dst = reinterpret_cast<double*>(&eo_jit_s_tables[k]);
+      for (int t = threadIdx.x; t < nw; t += blockDim.x) dst[t] = __ldg(src + t);
+    }
+    __syncthreads();
+  }
+#endif
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
   if constexpr (Spec::ORDER == 0)
-    run0<Spec>(a, i);
+    run0<Spec, ARGS>(a, i);
   else if constexpr (Spec::ORDER == 1)
-    run1<Spec>(a, i);
+    run1<Spec, ARGS>(a, i);
   else
-    run2<Spec>(a, i);
+    run2<Spec, ARGS>(a, i);
 }
 
 }  // namespace eo_jitd

@@ -24,6 +24,10 @@ static const char* k_hdr_dual =
 static const char* k_hdr_device =
 #include "eo_jit_device.inc"
     ;
+static const char* k_hdr_tab =
+#include "tab_core.inc"
+    ;
+#include "tab_core.cuh"  // tab_tables (sizes of the element the fused variants are specialised for)
 
 // ---------------------------------------------------------------------------------------------
 // NVRTC through dlopen
@@ -123,13 +127,19 @@ static std::string int_list(const int* v, int n) {
   return s + "}";
 }
 
-// The translation unit handed to NVRTC for one derivative multi-index.
-static std::string jit_program(const eo_jit* m, int order, int da, int db) {
+// tabulation source of one operand in a fused variant
+struct jit_tab_sig {
+  int gdim, bs, nb, kind;
+};
+
+// The translation unit handed to NVRTC for one derivative multi-index (fused: nq > 0 and one jit_tab_sig per operand).
+static std::string jit_program(const eo_jit* m, int order, int da, int db, int nq = 0, const jit_tab_sig* sig = nullptr) {
   int nin = 0, nst = 0, naux = 0;
   for (int i = 0; i < m->n_operands; ++i) nin += m->operand_size[i];
   for (int i = 0; i < m->n_state; ++i) nst += m->state_size[i];
   for (int i = 0; i < m->n_aux; ++i) naux += m->aux_size[i];
   std::string s;
+  if (sig) s += "#define EO_JIT_FUSED 1\n#define EO_JIT_N_TABLES " + std::to_string(m->n_operands) + "\n";
   s += "#include \"eo_jit_device.cuh\"\n";
   s += "#line 1 \"model.cu\"\n";
   s += m->source;
@@ -143,10 +153,23 @@ static std::string jit_program(const eo_jit* m, int order, int da, int db) {
   s += "  static constexpr int op_size(int k) { constexpr int t[] = " + int_list(m->operand_size, m->n_operands) + "; return t[k]; }\n";
   s += "  static constexpr int st_size(int k) { constexpr int t[] = " + int_list(m->state_size, m->n_state) + "; return t[k]; }\n";
   s += "  static constexpr int aux_size(int k) { constexpr int t[] = " + int_list(m->aux_size, m->n_aux) + "; return t[k]; }\n";
+  if (sig) {
+    int g[EO_JIT_MAX_ARGS], b[EO_JIT_MAX_ARGS], nb[EO_JIT_MAX_ARGS], kd[EO_JIT_MAX_ARGS];
+    for (int i = 0; i < m->n_operands; ++i) g[i] = sig[i].gdim, b[i] = sig[i].bs, nb[i] = sig[i].nb, kd[i] = sig[i].kind;
+    s += "  static constexpr int NQ = " + std::to_string(nq) + ";\n";
+    s += "  static constexpr int tab_gdim(int k) { constexpr int t[] = " + int_list(g, m->n_operands) + "; return t[k]; }\n";
+    s += "  static constexpr int tab_bs(int k) { constexpr int t[] = " + int_list(b, m->n_operands) + "; return t[k]; }\n";
+    s += "  static constexpr int tab_nb(int k) { constexpr int t[] = " + int_list(nb, m->n_operands) + "; return t[k]; }\n";
+    s += "  static constexpr int tab_kind(int k) { constexpr int t[] = " + int_list(kd, m->n_operands) + "; return t[k]; }\n";
+  }
   s += "  template <class T> static __device__ __forceinline__ void call(const T* x, const double* s, const double* prm, T* y, T* w) {\n";
   s += "    " + m->entry + "<T>(x, s, prm, y, w);\n  }\n};\n";
-  s += "extern \"C\" __global__ void __launch_bounds__(256) eo_jit_entry(const __grid_constant__ eo_jit_args a) {\n";
-  s += "  eo_jitd::run<eo_jit_spec>(a);\n}\n";
+  // occupancy hint: the fused kernels hide gather latency with resident warps (tab_vm_kernel uses 4 CTAs/SM too)
+  int min_blocks = sig ? 4 : 1;
+  if (const char* e = getenv("EO_JIT_MIN_BLOCKS")) min_blocks = atoi(e) > 0 ? atoi(e) : min_blocks;
+  s += "extern \"C\" __global__ void __launch_bounds__(256, " + std::to_string(min_blocks) + ") eo_jit_entry(const __grid_constant__ " +
+       std::string(sig ? "eo_jit_fused_args" : "eo_jit_args") + " a) {\n";
+  s += std::string("  eo_jitd::run<eo_jit_spec, ") + (sig ? "eo_jit_fused_args" : "eo_jit_args") + ">(a);\n}\n";
   return s;
 }
 
@@ -165,8 +188,13 @@ static int jit_multi_index(eo_jit* m, const int* derivatives, int& order, int& d
   return EO_OK;
 }
 
-static int jit_compile(eo_jit* m, int order, int da, int db, jit_variant** out) {
-  const std::string key = std::to_string(order) + ":" + std::to_string(da) + ":" + std::to_string(db);
+static int jit_compile(eo_jit* m, int order, int da, int db, jit_variant** out, int nq = 0, const jit_tab_sig* sig = nullptr) {
+  std::string key = std::to_string(order) + ":" + std::to_string(da) + ":" + std::to_string(db);
+  if (sig) {
+    key += ":F" + std::to_string(nq);
+    for (int i = 0; i < m->n_operands; ++i)
+      key += "/" + std::to_string(sig[i].gdim) + "," + std::to_string(sig[i].bs) + "," + std::to_string(sig[i].nb) + "," + std::to_string(sig[i].kind);
+  }
   auto it = m->variants.find(key);
   if (it != m->variants.end()) {
     *out = &it->second;
@@ -174,11 +202,11 @@ static int jit_compile(eo_jit* m, int order, int da, int db, jit_variant** out) 
   }
   nvrtc_api* rt = nvrtc();
   if (!rt->h) return jit_fail(m, EO_ERR_UNSUPPORTED, "eo_jit: %s", rt->err.c_str());
-  const std::string prog_text = jit_program(m, order, da, db);
+  const std::string prog_text = jit_program(m, order, da, db, nq, sig);
   nvrtcProgram prog = nullptr;
-  const char* hdr_src[2] = {k_hdr_device, k_hdr_dual};
-  const char* hdr_name[2] = {"eo_jit_device.cuh", "eo_dual.h"};
-  int rc = rt->CreateProgram(&prog, prog_text.c_str(), "eo_jit_entry.cu", 2, hdr_src, hdr_name);
+  const char* hdr_src[3] = {k_hdr_device, k_hdr_dual, k_hdr_tab};
+  const char* hdr_name[3] = {"eo_jit_device.cuh", "eo_dual.h", "tab_core.cuh"};
+  int rc = rt->CreateProgram(&prog, prog_text.c_str(), "eo_jit_entry.cu", 3, hdr_src, hdr_name);
   if (rc) return jit_fail(m, EO_ERR_CUDA, "nvrtcCreateProgram: %s", rt->GetErrorString(rc));
   // 256-bit ld/st.global.v4.f64 need the CUDA >= 12.9 ptxas; older NVRTCs get 128-bit accesses
   const bool v4 = rt->major > 12 || (rt->major == 12 && rt->minor >= 9);
@@ -201,6 +229,16 @@ static int jit_compile(eo_jit* m, int order, int da, int db, jit_variant** out) 
   v.cubin.assign(cs, '\0');
   rt->GetCUBIN(prog, &v.cubin[0]);
   rt->DestroyProgram(&prog);
+  if (const char* dump = getenv("EO_JIT_DUMP_DIR")) {  // for cuobjdump -sass / -res-usage
+    std::string name = key;
+    for (char& ch : name)
+      if (ch == ':' || ch == '/' || ch == ',') ch = '_';
+    const std::string path = std::string(dump) + "/" + m->entry + "_" + name + ".cubin";
+    if (FILE* f = fopen(path.c_str(), "wb")) {
+      fwrite(v.cubin.data(), 1, v.cubin.size(), f);
+      fclose(f);
+    }
+  }
   v.order = order, v.da = da, v.db = db;
   v.out_width = m->out_size;
   if (order >= 1) v.out_width *= m->operand_size[da];
@@ -357,6 +395,106 @@ int eo_jit_eval(eo_jit* m, const int* derivatives, const double* params, const d
     return EO_OK;
   };
   return eo_run_streamed(ctx, args, na, n, launch);
+}
+
+// Fused evaluation: every operand is tabulated inside the kernel from the DOF coefficients of its eo_tab
+// (kind per operand), so no operand array is ever written to or read from HBM.
+int eo_jit_eval_tabulated(eo_jit* m, const int* derivatives, const double* params, eo_tab* const* tabs, const int* kinds,
+                          const double* const* coefficients, const double* const* state, double* out, double* value,
+                          double* const* aux) {
+  if (!m) return EO_ERR_INVALID;
+  eo_ctx* ctx = m->ctx;
+  if (!ctx) return jit_fail(m, EO_ERR_NO_DEVICE, "eo_jit_eval_tabulated: this model was created without a context (compile-only)");
+  if (!out || !tabs || !kinds || !coefficients || (m->n_state && !state) || (m->n_params && !params))
+    return jit_fail(m, EO_ERR_INVALID, "eo_jit_eval_tabulated: NULL argument");
+  int order, da, db;
+  int rc = jit_multi_index(m, derivatives, order, da, db);
+  if (rc) return rc;
+  EO_CUDA(ctx, cudaSetDevice(ctx->device));
+  eo_tab_view tv[EO_JIT_MAX_ARGS];
+  jit_tab_sig sig[EO_JIT_MAX_ARGS];
+  int nq = 0;
+  int64_t n_cells = 0;
+  for (int i = 0; i < m->n_operands; ++i) {
+    if (!tabs[i] || !coefficients[i]) return jit_fail(m, EO_ERR_INVALID, "eo_jit_eval_tabulated: operand %d has no tabulation source", i);
+    const int nc = eo_tab_ncomp(tabs[i], kinds[i]);
+    if (nc != m->operand_size[i])
+      return jit_fail(m, EO_ERR_INVALID, "eo_jit_eval_tabulated: operand %d has %d components, its tabulation kind gives %d", i,
+                      m->operand_size[i], nc);
+    rc = eo_tab_view_get(tabs[i], coefficients[i], &tv[i]);
+    if (rc) return rc;
+    if (tv[i].ctx != ctx) return jit_fail(m, EO_ERR_INVALID, "eo_jit_eval_tabulated: operand %d lives on another context", i);
+    const tab_tables* T = tv[i].T_host;
+    sig[i] = {T->gdim, T->bs, T->nb, kinds[i]};
+    if (i == 0) nq = T->nq, n_cells = tv[i].n_cells;
+    if (T->nq != nq || tv[i].n_cells != n_cells)
+      return jit_fail(m, EO_ERR_INVALID, "eo_jit_eval_tabulated: all operands must share the cells and the evaluation points");
+  }
+  jit_variant* v = nullptr;
+  rc = jit_compile(m, order, da, db, &v, nq, sig);
+  if (rc) return rc;
+  const int64_t n = n_cells * nq;
+
+  eo_arg args[2 * EO_JIT_MAX_ARGS + 2];
+  int na = 0;
+  for (int i = 0; i < m->n_state; ++i) {
+    if (!state[i]) return jit_fail(m, EO_ERR_INVALID, "eo_jit_eval_tabulated: state field %d is NULL", i);
+    args[na++] = {state[i], size_t(m->state_size[i]) * 8, false};
+  }
+  const int i_out = na;
+  args[na++] = {out, size_t(v->out_width) * 8, true};
+  const int i_val = na;
+  args[na++] = {order >= 1 ? value : nullptr, size_t(m->out_size) * 8, true};
+  const int i_aux = na;
+  for (int i = 0; i < m->n_aux; ++i) args[na++] = {aux ? aux[i] : nullptr, size_t(m->aux_size[i]) * 8, true};
+
+  eo_jit_fused_args ka;
+  memset(&ka, 0, sizeof ka);
+  for (int i = 0; i < m->n_params; ++i) ka.prm[i] = params[i];
+  for (int i = 0; i < m->n_operands; ++i) {
+    ka.T[i] = tv[i].T_dev;
+    ka.dofmap[i] = tv[i].dofmap, ka.x_dofmap[i] = tv[i].x_dofmap, ka.x[i] = tv[i].x, ka.u[i] = tv[i].u;
+  }
+  cudaKernel_t kernel = v->kernel;
+  auto launch = [&](void** p, int64_t nn, int64_t off) -> int {
+    for (int i = 0; i < na; ++i)
+      if (p[i] && (reinterpret_cast<uintptr_t>(p[i]) & (args[i].bpq % 32 == 0 ? 31 : args[i].bpq % 16 == 0 ? 15 : 7)))
+        return jit_fail(m, EO_ERR_INVALID, "eo_jit_eval_tabulated: device argument %d is misaligned for its %zu-byte points", i, args[i].bpq);
+    for (int i = 0; i < m->n_state; ++i) ka.state[i] = (const double*)p[i];
+    ka.out = (double*)p[i_out];
+    ka.value = (double*)p[i_val];
+    for (int i = 0; i < m->n_aux; ++i) ka.aux[i] = (double*)p[i_aux + i];
+    ka.n = nn;
+    ka.point_offset = off;
+    void* kargs[1] = {&ka};
+    cudaError_t e = cudaLaunchKernel((const void*)kernel, dim3(unsigned((nn + 255) / 256)), dim3(256), kargs, 0, ctx->s_cmp);
+    if (e != cudaSuccess) return jit_fail(m, EO_ERR_CUDA, "eo_jit_eval_tabulated: launch: %s", cudaGetErrorString(e));
+    ++ctx->launches;
+    return EO_OK;
+  };
+  return eo_run_streamed(ctx, args, na, n, launch);
+}
+
+// compile-only counterpart (no GPU needed): element signature given explicitly
+int eo_jit_compile_tabulated(eo_jit* m, const int* derivatives, int nq, const int* gdim, const int* bs, const int* nb,
+                             const int* kinds, size_t* cubin_bytes) {
+  if (!m || !gdim || !bs || !nb || !kinds) return EO_ERR_INVALID;
+  int order, da, db;
+  int rc = jit_multi_index(m, derivatives, order, da, db);
+  if (rc) return rc;
+  jit_tab_sig sig[EO_JIT_MAX_ARGS];
+  for (int i = 0; i < m->n_operands; ++i) {
+    sig[i] = {gdim[i], bs[i], nb[i], kinds[i]};
+    if (!((gdim[i] == 2 || gdim[i] == 3) && bs[i] >= 1 && bs[i] <= EO_TAB_MAX_BS && nb[i] >= 1 && nb[i] <= EO_TAB_MAX_NB &&
+          tab_ncomp(kinds[i], bs[i], gdim[i]) == m->operand_size[i]))
+      return jit_fail(m, EO_ERR_INVALID, "eo_jit_compile_tabulated: bad element signature for operand %d", i);
+  }
+  if (nq < 1 || nq > EO_TAB_MAX_NQ) return jit_fail(m, EO_ERR_INVALID, "eo_jit_compile_tabulated: nq out of range");
+  jit_variant* v = nullptr;
+  rc = jit_compile(m, order, da, db, &v, nq, sig);
+  if (rc) return rc;
+  if (cubin_bytes) *cubin_bytes = v->cubin.size();
+  return EO_OK;
 }
 
 }  // extern "C"

@@ -25,39 +25,11 @@ struct eo_tab {
   int32_t* dofmap = nullptr;                     // device [n_cells][nb]
   int32_t* x_dofmap = nullptr;                   // device [n_cells][nv]
   double* x = nullptr;                           // device [n_nodes][3]
+  tab_tables* d_T = nullptr;                     // device copy of T (the fused generic kernels stage it in shared memory)
   double* u_stage = nullptr;                     // device staging copy of a host coefficient vector
   int32_t* cells_stage = nullptr;                // device staging copy of a host entity list
   size_t cells_stage_n = 0;
 };
-
-// gather the cell's coefficients and inverse Jacobian
-template <int GDIM, int BS, int NB>
-__device__ __forceinline__ void tab_load_cell(const tab_tables& T, const int32_t* __restrict__ dofmap,
-                                              const int32_t* __restrict__ x_dofmap, const double* __restrict__ x,
-                                              const double* __restrict__ u, int64_t c, double w[NB][BS],
-                                              double K[GDIM][GDIM]) {
-  int32_t idx[NB];
-#pragma unroll
-  for (int a = 0; a < NB; ++a) idx[a] = __ldg(dofmap + c * NB + a);
-#pragma unroll
-  for (int a = 0; a < NB; ++a) {
-    if constexpr (BS == 2) {
-      const double2 v = __ldg(reinterpret_cast<const double2*>(u) + idx[a]);
-      w[a][0] = v.x, w[a][1] = v.y;
-    } else {
-#pragma unroll
-      for (int k = 0; k < BS; ++k) w[a][k] = __ldg(u + int64_t(BS) * idx[a] + k);
-    }
-  }
-  double xv[GDIM + 1][GDIM];
-#pragma unroll
-  for (int v = 0; v < GDIM + 1; ++v) {
-    const int32_t node = __ldg(x_dofmap + c * (GDIM + 1) + v);
-#pragma unroll
-    for (int i = 0; i < GDIM; ++i) xv[v][i] = __ldg(x + 3 * int64_t(node) + i);
-  }
-  tab_geometry<GDIM>(T, xv, K);
-}
 
 template <int GDIM, int BS, int NB>
 __global__ void __launch_bounds__(128) tab_kernel(const __grid_constant__ tab_tables T, int kind,
@@ -204,6 +176,18 @@ static int tab_stage_u(eo_tab* t, const double* u, const double** d_u) {
   return EO_OK;
 }
 
+// internal: what the fused generic path (jit.cu) needs from a tabulation handle; stages a host coefficient vector
+int eo_tab_view_get(eo_tab* t, const double* u, eo_tab_view* v) {
+  v->ctx = t->ctx;
+  v->T_host = &t->T;
+  v->T_dev = t->d_T;
+  v->dofmap = t->dofmap, v->x_dofmap = t->x_dofmap, v->x = t->x;
+  v->n_cells = t->n_cells, v->n_dofs = t->n_dofs;
+  v->u = nullptr;
+  if (!u) return EO_OK;
+  return tab_stage_u(t, u, &v->u);
+}
+
 extern "C" {
 
 int eo_tab_create(eo_ctx* ctx, const eo_tab_desc* d, eo_tab** out) {
@@ -240,6 +224,7 @@ int eo_tab_create(eo_ctx* ctx, const eo_tab_desc* d, eo_tab** out) {
     if (t->dofmap) cudaFree(t->dofmap);
     if (t->x_dofmap) cudaFree(t->x_dofmap);
     if (t->x) cudaFree(t->x);
+    if (t->d_T) cudaFree(t->d_T);
     const int rc = e == cudaErrorMemoryAllocation ? EO_ERR_NOMEM : EO_ERR_CUDA;
     delete t;
     return rc;
@@ -252,6 +237,8 @@ int eo_tab_create(eo_ctx* ctx, const eo_tab_desc* d, eo_tab** out) {
   if ((e = cudaMemcpyAsync(t->dofmap, d->dofmap, b_dm, cudaMemcpyDefault, ctx->s_cmp)) != cudaSuccess) return fail(e, "copy dofmap");
   if ((e = cudaMemcpyAsync(t->x_dofmap, d->x_dofmap, b_xd, cudaMemcpyDefault, ctx->s_cmp)) != cudaSuccess) return fail(e, "copy x_dofmap");
   if ((e = cudaMemcpyAsync(t->x, d->x, b_x, cudaMemcpyDefault, ctx->s_cmp)) != cudaSuccess) return fail(e, "copy x");
+  if ((e = cudaMalloc(&t->d_T, sizeof(tab_tables))) != cudaSuccess) return fail(e, "cudaMalloc(tables)");
+  if ((e = cudaMemcpyAsync(t->d_T, &t->T, sizeof(tab_tables), cudaMemcpyHostToDevice, ctx->s_cmp)) != cudaSuccess) return fail(e, "copy tables");
   if ((e = cudaStreamSynchronize(ctx->s_cmp)) != cudaSuccess) return fail(e, "sync");
   *out = t;
   return EO_OK;
@@ -264,6 +251,7 @@ int eo_tab_destroy(eo_tab* t) {
   if (t->dofmap) cudaFree(t->dofmap);
   if (t->x_dofmap) cudaFree(t->x_dofmap);
   if (t->x) cudaFree(t->x);
+  if (t->d_T) cudaFree(t->d_T);
   if (t->u_stage) cudaFree(t->u_stage);
   if (t->cells_stage) cudaFree(t->cells_stage);
   delete t;

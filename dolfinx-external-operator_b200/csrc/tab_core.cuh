@@ -12,7 +12,12 @@
 // tab.cu and the CPU test harness (tests/hostcheck/) compile the same source.
 #pragma once
 
+#ifdef __CUDACC_RTC__  // NVRTC has no standard headers (this file is also handed to it for the fused generic path)
+typedef int int32_t;
+typedef long long int64_t;
+#else
 #include <cstdint>
+#endif
 
 #if defined(__CUDACC__)
 #define EO_TAB_HD __host__ __device__ __forceinline__
@@ -138,3 +143,34 @@ EO_TAB_HD void tab_operand(int kind, const double val[BS], const double grad[BS]
       for (int j = 0; j < GDIM; ++j) out[c * GDIM + j] = grad[c][j] + ((kind == 3 && c == j) ? 1.0 : 0.0);
   }
 }
+
+#if defined(__CUDACC__) || defined(__CUDACC_RTC__)
+// gather the cell's coefficients and inverse Jacobian (read-only path; neighbouring cells share nodes: L1/L2 hits)
+template <int GDIM, int BS, int NB>
+__device__ __forceinline__ void tab_load_cell(const tab_tables& T, const int32_t* __restrict__ dofmap,
+                                              const int32_t* __restrict__ x_dofmap, const double* __restrict__ x,
+                                              const double* __restrict__ u, int64_t c, double w[NB][BS],
+                                              double K[GDIM][GDIM]) {
+  int32_t idx[NB];
+#pragma unroll
+  for (int a = 0; a < NB; ++a) idx[a] = __ldg(dofmap + c * NB + a);
+#pragma unroll
+  for (int a = 0; a < NB; ++a) {
+    if constexpr (BS == 2) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(u) + idx[a]);
+      w[a][0] = v.x, w[a][1] = v.y;
+    } else {
+#pragma unroll
+      for (int k = 0; k < BS; ++k) w[a][k] = __ldg(u + int64_t(BS) * idx[a] + k);
+    }
+  }
+  double xv[GDIM + 1][GDIM];
+#pragma unroll
+  for (int v = 0; v < GDIM + 1; ++v) {
+    const int32_t node = __ldg(x_dofmap + c * (GDIM + 1) + v);
+#pragma unroll
+    for (int i = 0; i < GDIM; ++i) xv[v][i] = __ldg(x + 3 * int64_t(node) + i);
+  }
+  tab_geometry<GDIM>(T, xv, K);
+}
+#endif

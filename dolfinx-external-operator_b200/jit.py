@@ -191,6 +191,13 @@ class JitModel:
             raise EOError(-5, "this JitModel was created with compile_only=True")
         if len(operands) != len(self.operand_sizes):
             raise TypeError(f"expected {len(self.operand_sizes)} operand arrays, got {len(operands)}")
+        from .tabulation import LazyOperand
+
+        lazy = [isinstance(a, LazyOperand) for a in operands]
+        if all(lazy) and len({(a.tab.n_cells, a.tab.nq) for a in operands}) == 1:
+            return self._evaluate_fused(derivatives, d, width, operands, device_out)
+        if any(lazy):  # mixed: tabulate the lazy ones after all
+            operands = [a.materialize() if z else a for a, z in zip(operands, lazy)]
         ins, n = [], None
         for a, s in zip(operands, self.operand_sizes):
             if not isinstance(a, DeviceArray):
@@ -211,6 +218,19 @@ class JitModel:
         if n == 0:  # empty partition (a rank without cells): nothing to launch
             res = [np.empty(0) for _ in self.returns]
             return res[0] if len(res) == 1 else tuple(res)
+        out_ptr, bufs = self._out_binder(device_out)
+        p_out, p_val, p_aux = self._out_ptrs(out_ptr, order, width, n)
+        ops = (C.c_void_p * len(ins))(*[_ptr(a) for a in ins])
+        sts = (C.c_void_p * max(1, len(self.state)))(*[s.ptr for s in self.state])
+        aux = (C.c_void_p * max(1, len(p_aux)))(*p_aux)
+        prm = self.params.ctypes.data if self.params.size else None
+        self._check(self.lib.eo_jit_eval(self._h, d, prm, ops, sts, p_out, p_val, aux, n))
+        self.ctx.sync()
+        return self._results(order, bufs)
+
+    def _out_binder(self, device_out):
+        """(out_ptr(name, size) -> void*, bufs): where each result lands - a caller-given DeviceArray, a
+        model-owned DeviceArray (output='device') or a model-owned pinned host array."""
         device_out = device_out or {}
         bufs = {}
 
@@ -229,15 +249,15 @@ class JitModel:
                 return _ptr(bufs[name])
             return None
 
+        return out_ptr, bufs
+
+    def _out_ptrs(self, out_ptr, order, width, n):
         p_out = out_ptr("out", width * n)
         p_val = out_ptr("value", self.out_size * n) if order >= 1 else None
         p_aux = [out_ptr(f"aux{i}", s * n) for i, s in enumerate(self.aux_sizes)]
-        ops = (C.c_void_p * len(ins))(*[_ptr(a) for a in ins])
-        sts = (C.c_void_p * max(1, len(self.state)))(*[s.ptr for s in self.state])
-        aux = (C.c_void_p * max(1, len(p_aux)))(*p_aux)
-        prm = self.params.ctypes.data if self.params.size else None
-        self._check(self.lib.eo_jit_eval(self._h, d, prm, ops, sts, p_out, p_val, aux, n))
-        self.ctx.sync()
+        return p_out, p_val, p_aux
+
+    def _results(self, order, bufs):
         res = []
         for name in self.returns:
             if name == "value" and order == 0:
@@ -247,6 +267,32 @@ class JitModel:
             else:
                 res.append(bufs[name])
         return res[0] if len(res) == 1 else tuple(res)
+
+    def _evaluate_fused(self, derivatives, d, width, operands, device_out=None):
+        """All operands are `LazyOperand`s: tabulate them inside the model's kernel (eo_jit_eval_tabulated)."""
+        n = operands[0].tab.n_cells * operands[0].tab.nq
+        for a, s in zip(operands, self.operand_sizes):
+            if a.tab.ncomp(a.kind_id) != s:
+                raise ValueError("operand kind does not have the number of components the model expects")
+        for i, st in enumerate(self.state):
+            if st is None or st.size != n * self.state_sizes[i]:
+                raise ValueError(f"state field {i} is not set or does not hold {n} points")
+        order = sum(derivatives)
+        if n == 0:
+            res = [np.empty(0) for _ in self.returns]
+            return res[0] if len(res) == 1 else tuple(res)
+        out_ptr, bufs = self._out_binder(device_out)
+        p_out, p_val, p_aux = self._out_ptrs(out_ptr, order, width, n)
+        coeffs = [a.tab._coeff(a.coefficient) for a in operands]  # keep the arrays alive across the call
+        tabs = (C.c_void_p * len(operands))(*[a.tab._h for a in operands])
+        kinds = (C.c_int * len(operands))(*[a.kind_id for a in operands])
+        us = (C.c_void_p * len(operands))(*[_ptr(u) for u in coeffs])
+        sts = (C.c_void_p * max(1, len(self.state)))(*[s.ptr for s in self.state])
+        aux = (C.c_void_p * max(1, len(p_aux)))(*p_aux)
+        prm = self.params.ctypes.data if self.params.size else None
+        self._check(self.lib.eo_jit_eval_tabulated(self._h, d, prm, tabs, kinds, us, sts, p_out, p_val, aux))
+        self.ctx.sync()
+        return self._results(order, bufs)
 
     def eval_device(self, derivatives, operands, out: DeviceArray, value: DeviceArray | None = None, aux=()):
         """All-device evaluation, asynchronous on the ctx stream (for device-side consumers and benchmarks)."""

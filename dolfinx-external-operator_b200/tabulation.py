@@ -86,7 +86,8 @@ class Tabulator:
 
     # ------------------------------------------------------------------ plans (evaluate_operands protocol)
     def register(self, operand, kind: str, coefficient=None, output: str = "device"):
-        """Declare that UFL `operand` is `kind` of `coefficient` (default: the tabulator's)."""
+        """Declare that UFL `operand` is `kind` of `coefficient` (default: the tabulator's).  output: 'device'
+        (DeviceArray), 'host' (ndarray) or 'lazy' (a `LazyOperand`: tabulation fused into the consuming kernel)."""
         if kind not in KINDS:
             raise ValueError(f"unknown operand kind {kind!r}; known: {sorted(KINDS)}")
         self._plans[operand] = _Plan(self, KINDS[kind], coefficient, output)
@@ -173,11 +174,36 @@ class Tabulator:
         return C_tang
 
 
+class LazyOperand:
+    """An operand that has NOT been tabulated: (tabulator, kind, coefficient) for all cells.  `evaluate_operands`
+    returns it for plans registered with output='lazy'; callables that can fuse the tabulation into their own kernel
+    (`JitModel`: eo_jit_eval_tabulated; `VonMises`: eo_tab_vm_fused) consume it as is - the operand array is then
+    never written to HBM - and every other consumer calls `materialize()`."""
+
+    def __init__(self, tab: "Tabulator", kind_id: int, coefficient):
+        self.tab, self.kind_id, self.coefficient = tab, kind_id, coefficient
+
+    @property
+    def shape(self):
+        return self.tab._shape(self.kind_id, self.tab.n_cells)
+
+    @property
+    def size(self) -> int:
+        return int(np.prod(self.shape))
+
+    def materialize(self, output: str = "device"):
+        return self.tab.evaluate(self.kind_id, self.coefficient, None, output)
+
+
 class _Plan:
     def __init__(self, tab: Tabulator, kind_id: int, coefficient, output: str):
         self.tab, self.kind_id, self.coefficient, self.output = tab, kind_id, coefficient, output
 
     def evaluate(self, entities=None):
+        if self.output == "lazy":
+            if entities is None and type(self.tab) is Tabulator:
+                return LazyOperand(self.tab, self.kind_id, self.coefficient)
+            return self.tab.evaluate(self.kind_id, self.coefficient, entities, "device")
         return self.tab.evaluate(self.kind_id, self.coefficient, entities, self.output)
 
 

@@ -373,6 +373,17 @@ int eo_jit_out_width(eo_jit* m, const int* derivatives);
  * value (optional, derivative orders >= 1) : [n][out_size];  aux[i] (each optional) : [n][aux_size[i]]. */
 int eo_jit_eval(eo_jit* m, const int* derivatives, const double* params, const double* const* operands,
                 const double* const* state, double* out, double* value, double* const* aux, int64_t n);
+/* Fused hot path for a run-time compiled model (the general form of eo_tab_vm_fused; SURVEY.md 8b `eo_fused_step`):
+ * operand i is tabulated INSIDE the kernel from coefficient vector coefficients[i] (any-side, bs * n_dofs doubles)
+ * with operand kind kinds[i] on tabs[i] (all tabs: same cells and evaluation points), fed to the model from
+ * registers and never stored.  n = n_cells * nq points, point index = cell * nq + q.  state / out / value / aux as in
+ * eo_jit_eval.  One NVRTC compilation per (derivatives, element signature), cached. */
+int eo_jit_eval_tabulated(eo_jit* m, const int* derivatives, const double* params, eo_tab* const* tabs, const int* kinds,
+                          const double* const* coefficients, const double* const* state, double* out, double* value,
+                          double* const* aux);
+/* Compile such a kernel without a GPU: element signature (gdim, block size, basis functions, kind) per operand. */
+int eo_jit_compile_tabulated(eo_jit* m, const int* derivatives, int nq, const int* gdim, const int* bs, const int* nb,
+                             const int* kinds, size_t* cubin_bytes);
 
 #ifdef __cplusplus
 }

@@ -45,6 +45,23 @@ def test_toolkit_nvrtc_is_preferred_over_the_one_torch_loads():
     assert m.compile((1,)) > 1000
 
 
+def test_fused_tabulation_variants_compile_without_gpu():
+    """eo_jit_compile_tabulated: the model kernel with the operand tabulation fused in (P2 vector triangle -> Mandel
+    strain -> von Mises; P2 scalar triangle -> (T, grad T) -> heat flux; P1 tetrahedron -> grad)."""
+    import ctypes as C
+
+    ints = lambda *a: (C.c_int * len(a))(*a)  # noqa: E731
+    nbytes = C.c_size_t(0)
+    m = jm.von_mises(compile_only=True)
+    assert m.lib.eo_jit_compile_tabulated(m._h, ints(1), 3, ints(2), ints(2), ints(6), ints(2), C.byref(nbytes)) == 0
+    assert nbytes.value > 1000
+    h = jm.heat_flux(compile_only=True)
+    for d in [(0, 0), (1, 0), (0, 1)]:
+        assert h.lib.eo_jit_compile_tabulated(h._h, ints(*d), 3, ints(2, 2), ints(1, 1), ints(6, 6), ints(0, 1), C.byref(nbytes)) == 0
+    # operand size 2 does not match a Mandel strain (4 components): rejected
+    assert h.lib.eo_jit_compile_tabulated(h._h, ints(0, 0), 3, ints(2, 2), ints(1, 2), ints(6, 6), ints(0, 2), C.byref(nbytes)) == -1
+
+
 def test_compile_error_carries_the_nvrtc_log():
     bad = "template <class T> __device__ void f(const T* x, const double*, const double*, T* y, T*) { y[0] = x[0] +; }"
     m = JitModel(bad, "f", [()], (), compile_only=True)

@@ -110,3 +110,77 @@ def test_jit_empty_and_errors(ctx):
         jm.heat_flux(ctx=ctx)((0, 0))(np.zeros(6), np.zeros(10))  # 6 vs 5 points
     with pytest.raises(ValueError):
         jm.von_mises(ctx=ctx)((1,))(np.zeros(8))  # state not set
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fused: operands tabulated inside the model's kernel (eo_jit_eval_tabulated), never stored
+def _p2_setup(ctx):
+    from dolfinx_external_operator_b200 import synthetic as syn
+    from tab_util import tri_case
+
+    m = tri_case(nx=23, ny=17)
+    tab = eo.Tabulator(dofmap=m["dofmap"], x_dofmap=m["x_dofmap"], x=m["x"], phi=m["phi"], dphi=m["dphi"], bs=2,
+                       n_dofs=m["n_dofs"], ctx=ctx)
+    u = syn.smooth_displacement(m["dof_coords"], scale=1.5e-3, seed=2).reshape(-1)
+    return m, tab, u
+
+
+def test_fused_tabulation_von_mises_equals_two_step(ctx):
+    from types import SimpleNamespace
+
+    m, tab, u = _p2_setup(ctx)
+    n = 3 * m["dofmap"].shape[0]
+    _, sn, p = inputs.vm_batch(n, seed=4)
+    jv = jm.von_mises(ctx=ctx, fmad=False)  # like tab_kernel (-fmad=false): fused and two-step strains are the same bits
+    jv.set_state(0, sn)
+    jv.set_state(1, p)
+    strain = tab.evaluate("mandel_strain", u)  # two-step: tabulate, then evaluate
+    ref = [np.array(a) for a in jv((1,))(strain)]
+    # the reference's two calls, with the operand registered as lazy -> one fused kernel
+    tab.coefficient = u
+    tab.register("eps", "mandel_strain", output="lazy")
+    op = SimpleNamespace(ufl_operands=["eps"], derivatives=(1,), external_function=jv, b200_tabulator=tab,
+                         ref_coefficient=SimpleNamespace(x=SimpleNamespace(array=np.zeros(16 * n), scatter_forward=lambda: None)))
+    op._assign_func = lambda values: op.ref_coefficient.x.array.__setitem__(slice(None), values)  # :289-290
+    ops = eo.evaluate_operands([op])
+    assert type(ops["eps"]).__name__ == "LazyOperand"
+    l0 = ctx.launch_count
+    ((Ct, sig, dp),) = eo.evaluate_external_operators([op], ops)
+    assert ctx.launch_count - l0 == (n + (1 << 20) - 1) // (1 << 20)  # one launch per pipeline chunk, no tabulation launch
+    for a, b in zip((Ct, sig, dp), ref):
+        assert np.array_equal(a, b)  # same arithmetic, same bits
+    assert np.array_equal(op.ref_coefficient.x.array, ref[0])
+    # the hard-wired von Mises callable fuses the same way (eo_tab_vm_fused, exact variant)
+    vm = eo.VonMises(ctx=ctx)
+    vm.set_history(sn, p)
+    two = [np.array(a) for a in vm((1,))(strain)]
+    op.external_function = vm
+    ((Ct2, sig2, dp2),) = eo.evaluate_external_operators([op], ops)
+    for a, b in zip((Ct2, sig2, dp2), two):
+        assert np.array_equal(a, b)
+
+
+def test_fused_tabulation_two_operands_heat(ctx):
+    """q(T, grad T): two operands of different kinds tabulated from the same P2 scalar coefficient."""
+    from dolfinx_external_operator_b200 import elements as el
+    from tab_util import tri_case
+
+    m = tri_case(nx=11, ny=13)
+    tab = eo.Tabulator(dofmap=m["dofmap"], x_dofmap=m["x_dofmap"], x=m["x"], phi=m["phi"], dphi=m["dphi"], bs=1,
+                       n_dofs=m["n_dofs"], ctx=ctx)
+    x, y = m["dof_coords"][:, 0], m["dof_coords"][:, 1]
+    T = x * x + y  # part1.py:187
+    h = jm.heat_flux(ctx=ctx, fmad=False)
+    from dolfinx_external_operator_b200.tabulation import LazyOperand
+
+    lz = [LazyOperand(tab, 0, T), LazyOperand(tab, 1, T)]
+    Tq, gq = tab.evaluate("value", T, output="host"), tab.evaluate("grad", T, output="host")
+    for d in [(0, 0), (1, 0), (0, 1), (1, 1)]:
+        fused = np.array(h(d)(*lz))
+        two = np.array(h(d)(Tq, gq))
+        assert np.array_equal(fused, two)
+    # analytic: q = -grad T / (1 + T), grad T = (2x, 1) (P2 reproduces x^2 + y exactly)
+    xq = m["xq"].reshape(-1, 2)
+    k = 1.0 / (1.0 + xq[:, 0] ** 2 + xq[:, 1])
+    np.testing.assert_allclose(np.array(h((0, 0))(*lz)).reshape(-1, 2), -k[:, None] * np.stack([2 * xq[:, 0], np.ones(len(xq))], 1),
+                               rtol=1e-11, atol=1e-12)
