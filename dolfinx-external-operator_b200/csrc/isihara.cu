@@ -12,19 +12,31 @@
 
 struct eo_isihara {
   eo_ctx* ctx = nullptr;
-  isi_weights* d_w = nullptr;  // device copy
+  isi_weights_c* d_w = nullptr;  // device copy (compact: without W2)
   isi_weights h_w;
 };
 
-#define ISI_THREADS 128
+static void isi_compact(const isi_weights& w, isi_weights_c& c) {
+  memcpy(c.A1, w.A1, sizeof c.A1);
+  memcpy(c.S2, w.S2, sizeof c.S2);
+  memcpy(c.W2T, w.W2T, sizeof c.W2T);
+  memcpy(c.w3, w.w3, sizeof c.w3);
+  memcpy(c.s3, w.s3, sizeof c.s3);
+  memcpy(c.H, w.H, sizeof c.H);
+}
 
-__global__ void __launch_bounds__(ISI_THREADS) isihara_kernel(const isi_weights* __restrict__ gw,
+#define ISI_THREADS 256  // one CTA per SM: 19 KB of weights + 192 KB of activation scratch
+#define ISI_SMEM (sizeof(isi_weights_c) + size_t(ISI_NH) * ISI_THREADS * 3 * sizeof(float))
+
+__global__ void __launch_bounds__(ISI_THREADS) isihara_kernel(const isi_weights_c* __restrict__ gw,
                                                               const double* __restrict__ F, double* __restrict__ dP,
                                                               double* __restrict__ P, int64_t n) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  isi_weights& W = *reinterpret_cast<isi_weights*>(s_raw);
+  isi_weights_c& W = *reinterpret_cast<isi_weights_c*>(s_raw);
+  // layer-1 activation scratch: [unit][thread][phi, phi', phi''] - consecutive threads are 3 words apart: conflict free
+  float* zs = reinterpret_cast<float*>(s_raw + sizeof(isi_weights_c)) + 3 * threadIdx.x;
   {
-    const int nw = int(sizeof(isi_weights) / 16);
+    const int nw = int(sizeof(isi_weights_c) / 16);
     const float4* src = reinterpret_cast<const float4*>(gw);
     float4* dst = reinterpret_cast<float4*>(s_raw);
     for (int t = threadIdx.x; t < nw; t += blockDim.x) dst[t] = src[t];
@@ -35,7 +47,7 @@ __global__ void __launch_bounds__(ISI_THREADS) isihara_kernel(const isi_weights*
     const eo_d4 f = eo_ld256(F + 4 * i);
     const double Fv[4] = {f.x, f.y, f.z, f.w};
     double Pv[4], T[16];
-    isi_point(W, Fv, Pv, T);
+    isi_point(W, Fv, Pv, T, zs, 3 * ISI_THREADS);
     double* o = dP + 16 * i;
     eo_st256(o + 0, T[0], T[1], T[2], T[3]);
     eo_st256(o + 4, T[4], T[5], T[6], T[7]);
@@ -53,17 +65,19 @@ int eo_isihara_create(eo_ctx* ctx, const eo_isihara_weights* w, eo_isihara** out
   EO_REQUIRE(ctx, ctx != nullptr, "eo_isihara_create: ctx is NULL");
   EO_REQUIRE(ctx, w && out, "eo_isihara_create: NULL argument");
   static_assert(sizeof(eo_isihara_weights) == sizeof(isi_weights), "eo_isihara_weights must mirror isi_weights");
-  static_assert(sizeof(isi_weights) % 16 == 0, "isi_weights is copied in 16-byte pieces");
+  static_assert(sizeof(isi_weights_c) % 16 == 0, "isi_weights_c is copied in 16-byte pieces");
   *out = nullptr;
   EO_CUDA(ctx, cudaSetDevice(ctx->device));
   eo_isihara* m = new eo_isihara();
   m->ctx = ctx;
   memcpy(&m->h_w, w, sizeof(isi_weights));
-  cudaError_t e = cudaMalloc(&m->d_w, sizeof(isi_weights));
-  if (e == cudaSuccess) e = cudaMemcpyAsync(m->d_w, &m->h_w, sizeof(isi_weights), cudaMemcpyHostToDevice, ctx->s_cmp);
+  isi_weights_c hc;
+  isi_compact(m->h_w, hc);
+  cudaError_t e = cudaMalloc(&m->d_w, sizeof(isi_weights_c));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(m->d_w, &hc, sizeof(isi_weights_c), cudaMemcpyHostToDevice, ctx->s_cmp);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_cmp);
   if (e == cudaSuccess && !g_isi_attr) {
-    e = cudaFuncSetAttribute(isihara_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(isi_weights));
+    e = cudaFuncSetAttribute(isihara_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ISI_SMEM);
     g_isi_attr = e == cudaSuccess;
   }
   if (e != cudaSuccess) {
@@ -89,7 +103,9 @@ int eo_isihara_set_correction(eo_isihara* m, const double H_flat[4]) {
   if (!m || !H_flat) return EO_ERR_INVALID;
   eo_ctx* ctx = m->ctx;
   for (int i = 0; i < 4; ++i) m->h_w.H[i] = H_flat[i];
-  EO_CUDA(ctx, cudaMemcpyAsync(m->d_w, &m->h_w, sizeof(isi_weights), cudaMemcpyHostToDevice, ctx->s_cmp));
+  isi_weights_c hc;
+  isi_compact(m->h_w, hc);
+  EO_CUDA(ctx, cudaMemcpyAsync(m->d_w, &hc, sizeof(isi_weights_c), cudaMemcpyHostToDevice, ctx->s_cmp));
   EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_cmp));
   return EO_OK;
 }
@@ -106,9 +122,9 @@ int eo_isihara_eval(eo_isihara* m, const double* F, double* dP, double* P, int64
     for (int i = 0; i < 3; ++i)
       if (!eo_aligned(a[i], 32)) return eo_fail(ctx, EO_ERR_INVALID, "eo_isihara_eval: arrays must be 32-byte aligned");
     int64_t grid = (cnt + ISI_THREADS - 1) / ISI_THREADS;
-    const int64_t cap = int64_t(ctx->sm_count) * 6;  // persistent-ish: amortise the 35 KB weight staging
+    const int64_t cap = int64_t(ctx->sm_count) * 2;  // persistent: one resident CTA per SM, grid-stride over the points
     if (grid > cap) grid = cap;
-    isihara_kernel<<<(unsigned)grid, ISI_THREADS, sizeof(isi_weights), ctx->s_cmp>>>(m->d_w, (const double*)a[0],
+    isihara_kernel<<<(unsigned)grid, ISI_THREADS, ISI_SMEM, ctx->s_cmp>>>(m->d_w, (const double*)a[0],
                                                                                       (double*)a[1], (double*)a[2], cnt);
     ctx->launches += 1;
     return (int)EO_OK;

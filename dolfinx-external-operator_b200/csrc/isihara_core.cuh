@@ -42,6 +42,16 @@ struct isi_weights {
   double H[4];              // H_flat = -dW_NN/dF at F = I (:367)
 };
 
+// what the kernel keeps in shared memory: the same constants without W2 (both passes read W2T rows)
+struct isi_weights_c {
+  float A1[ISI_NH][4];
+  float S2[ISI_NH][4];
+  float W2T[ISI_NH][ISI_NH];
+  float w3[ISI_NH];
+  float s3[4];
+  double H[4];
+};
+
 // softplus and the activation phi(a) = softplus(a)^2 / 12 with its first two derivatives, float32
 EO_ISI_HD void isi_phi(float a, float& p0, float& p1, float& p2) {
   // torch.nn.functional.softplus: log1p(exp(a)), linear above the threshold 20
@@ -61,13 +71,28 @@ EO_ISI_HD void isi_phi(float a, float& p0, float& p1, float& p2) {
 }
 
 // y(x), dy/dx (3), d2y/dx2 (6: xx, xy, xz, yy, yz, zz) of the network, float32.
-// `W` may live in shared memory (device) or anywhere (host).
-EO_ISI_HD void isi_network(const isi_weights& W, const float x[3], float& y, float gx[3], float hx[6]) {
+// `W` may live in shared memory (device) or anywhere (host).  `zs` is per-point scratch for the layer-1
+// activations (phi, phi', phi'' of the 64 units, computed ONCE): element (i, c) at zs[i * zstride + c], c = 0..2
+// - shared memory on the device (12-byte cells, consecutive threads 3 words apart: conflict free), a local array on
+// the host.  WT: isi_weights or isi_weights_c.
+template <class WT>
+EO_ISI_HD void isi_network(const WT& W, const float x[3], float* zs, int zstride, float& y, float gx[3],
+                           float hx[6]) {
   float g[ISI_NH];  // g_j = w3_j phi'(a2_j)
   float yy = W.s3[0] * x[0] + W.s3[1] * x[1] + W.s3[2] * x[2];
   float G0 = W.s3[0], G1 = W.s3[1], G2 = W.s3[2];
   float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f, h4 = 0.f, h5 = 0.f;
-  // ---- pass A: a2_j and d_j = da2_j/dx for blocks of 16 outputs; layer-1 activations recomputed per block
+  // ---- layer 1 (collapsed onto the affine layer 0): a1 = A1 x + c1, activations kept for both passes
+#pragma unroll 4
+  for (int i = 0; i < ISI_NH; ++i) {
+    const float a1 = W.A1[i][0] * x[0] + W.A1[i][1] * x[1] + W.A1[i][2] * x[2] + W.A1[i][3];
+    float p0, p1, p2;
+    isi_phi(a1, p0, p1, p2);
+    float* z = zs + i * zstride;
+    z[0] = p0, z[1] = p1, z[2] = p2;
+  }
+  // ---- pass A: a2_j and d_j = da2_j/dx for blocks of 16 outputs (64 accumulators in registers);
+  //      weights read as W2T[i][jb .. jb+15]: contiguous, four 128-bit broadcasts per 64 FMA
 #pragma unroll 1
   for (int jb = 0; jb < ISI_NH; jb += 16) {
     float acc[16][4];
@@ -80,13 +105,12 @@ EO_ISI_HD void isi_network(const isi_weights& W, const float x[3], float& y, flo
     }
 #pragma unroll 2
     for (int i = 0; i < ISI_NH; ++i) {
-      const float a1 = W.A1[i][0] * x[0] + W.A1[i][1] * x[1] + W.A1[i][2] * x[2] + W.A1[i][3];
-      float p0, p1, p2;
-      isi_phi(a1, p0, p1, p2);
-      const float z0 = p0, z1 = p1 * W.A1[i][0], z2 = p1 * W.A1[i][1], z3 = p1 * W.A1[i][2];
+      const float* z = zs + i * zstride;
+      const float p1 = z[1];
+      const float z0 = z[0], z1 = p1 * W.A1[i][0], z2 = p1 * W.A1[i][1], z3 = p1 * W.A1[i][2];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const float w = W.W2[jb + j][i];
+        const float w = W.W2T[i][jb + j];
         acc[j][0] += w * z0;
         acc[j][1] += w * z1;
         acc[j][2] += w * z2;
@@ -112,9 +136,8 @@ EO_ISI_HD void isi_network(const isi_weights& W, const float x[3], float& y, flo
     float v = 0.f;
 #pragma unroll
     for (int j = 0; j < ISI_NH; ++j) v += W.W2T[i][j] * g[j];
-    const float a1 = W.A1[i][0] * x[0] + W.A1[i][1] * x[1] + W.A1[i][2] * x[2] + W.A1[i][3];
-    float p0, p1, p2;
-    isi_phi(a1, p0, p1, p2);
+    const float* z = zs + i * zstride;
+    const float p1 = z[1], p2 = z[2];
     const float A0 = W.A1[i][0], A1 = W.A1[i][1], A2 = W.A1[i][2];
     const float t1 = p1 * v, t2 = p2 * v;
     G0 += A0 * t1, G1 += A1 * t1, G2 += A2 * t1;
@@ -177,7 +200,9 @@ EO_ISI_HD isi_jet isi_pow(const isi_jet& u, double p) {
 }
 
 // One point: F = [F11, F12, F21, F22] (:263-266)  ->  P (4), tangent dP_i/dF_j (row-major 4x4)
-EO_ISI_HD void isi_point(const isi_weights& W, const double F[4], double P[4], double dP[16]) {
+// zs / zstride: scratch for isi_network (3 * ISI_NH floats per point when zstride = 3)
+template <class WT>
+EO_ISI_HD void isi_point(const WT& W, const double F[4], double P[4], double dP[16], float* zs, int zstride) {
   const isi_jet F11 = isi_var(F[0], 0), F12 = isi_var(F[1], 1), F21 = isi_var(F[2], 2), F22 = isi_var(F[3], 3);
   // right Cauchy-Green tensor and invariants (:269-277)
   const isi_jet C11 = isi_add(isi_mul(F11, F11), isi_mul(F21, F21));
@@ -200,7 +225,7 @@ EO_ISI_HD void isi_point(const isi_weights& W, const double F[4], double P[4], d
   // network in float32 (:286)
   const float x[3] = {(float)X[0].v, (float)X[1].v, (float)X[2].v};
   float y, gx[3], hx[6];
-  isi_network(W, x, y, gx, hx);
+  isi_network(W, x, zs, zstride, y, gx, hx);
   const double Wx[3] = {(double)gx[0], (double)gx[1], (double)gx[2]};
   const double Wxx[3][3] = {{(double)hx[0], (double)hx[1], (double)hx[2]},
                             {(double)hx[1], (double)hx[3], (double)hx[4]},

@@ -30,7 +30,10 @@ extern "C" {
 
 void hostcheck_isihara(const isi_weights* w, const double* F, double* dP, double* P, int64_t n) {
 #pragma omp parallel for schedule(static)
-  for (int64_t i = 0; i < n; ++i) isi_point(*w, F + 4 * i, P + 4 * i, dP + 16 * i);
+  for (int64_t i = 0; i < n; ++i) {
+    float zs[3 * ISI_NH];
+    isi_point(*w, F + 4 * i, P + 4 * i, dP + 16 * i, zs, 3);
+  }
 }
 
 // tables: phi [nq][nb], dphi [gdim][nq][nb], dpsi [gdim][gdim+1]; returns 0 or -1 (unsupported element)
