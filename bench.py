@@ -360,7 +360,7 @@ def run_gpu_arm(args):
         d_it = ctx.empty((n,), np.int32)
         d_yl, d_nr, d_dl = ctx.empty((n,)), ctx.empty((n,)), ctx.empty((n,))
         prm = McParams(mc.E, mc.nu, mc.c, mc.phi, mc.psi, mc.theta_T, mc.a, mc.tol, mc.Nitermax)
-        scheme = {"queue": 0, "simple": 1, "queue-noaffinity": 2}[args.mc_scheme]
+        scheme = {"queue": 0, "simple": 1, "queue-noaffinity": 2, "queue-onepass": 3}[args.mc_scheme]
         extra_cfg["mc_scheme"] = args.mc_scheme
 
         def step():
@@ -612,7 +612,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="vm", choices=["vm", "heat", "mc", "tab", "fused", "isihara", "jitvm", "jitfused"])
     ap.add_argument("--fused-exact", action="store_true")
-    ap.add_argument("--mc-scheme", default="queue", choices=["queue", "simple", "queue-noaffinity"])
+    ap.add_argument("--mc-scheme", default="queue", choices=["queue", "simple", "queue-noaffinity", "queue-onepass"])
     ap.add_argument("--n", type=float, default=1e8, help="quadrature points per GPU (device-resident leg)")
     ap.add_argument("--e2e-n", type=float, default=1.5e7, help="quadrature points per GPU for the end-to-end leg")
     ap.add_argument("--state-layout", default="aos", choices=["aos", "soa"])

@@ -29,6 +29,9 @@ struct eo_ctx {
   // L2 flush scratch
   char* flush = nullptr;
   size_t flush_bytes = 0;
+  // general device scratch (plastic-point list of the two-pass Mohr-Coulomb scheme), grown on demand
+  char* scratch = nullptr;
+  size_t scratch_bytes = 0;
   eo_stats* stats = nullptr;  // device
   unsigned int* work_ctr = nullptr;  // device: tile counter of the persistent kernels
   int64_t launches = 0;
@@ -51,6 +54,9 @@ int eo_fail(eo_ctx* ctx, int code, const char* fmt, ...);
   do {                             \
     if (!(cond)) return eo_fail(ctx, EO_ERR_INVALID, "%s", msg); \
   } while (0)
+
+// device scratch of at least `bytes` (contents undefined; valid until the next eo_scratch call on this ctx)
+int eo_scratch(eo_ctx* ctx, size_t bytes, void** out);
 
 // true when `p` is memory the GPU kernels can dereference in place
 bool eo_is_device_ptr(const void* p);

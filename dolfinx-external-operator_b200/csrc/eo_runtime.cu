@@ -14,6 +14,18 @@ int eo_fail(eo_ctx* ctx, int code, const char* fmt, ...) {
   return code;
 }
 
+int eo_scratch(eo_ctx* ctx, size_t bytes, void** out) {
+  if (bytes > ctx->scratch_bytes) {
+    EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_cmp));
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    ctx->scratch = nullptr, ctx->scratch_bytes = 0;
+    EO_CUDA(ctx, cudaMalloc(&ctx->scratch, bytes));
+    ctx->scratch_bytes = bytes;
+  }
+  *out = ctx->scratch;
+  return EO_OK;
+}
+
 bool eo_is_device_ptr(const void* p) {
   cudaPointerAttributes a;
   cudaError_t e = cudaPointerGetAttributes(&a, p);
@@ -118,6 +130,7 @@ int eo_destroy(eo_ctx* ctx) {
   }
   if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->flush) cudaFree(ctx->flush);
+  if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->stats) cudaFree(ctx->stats);
   if (ctx->work_ctr) cudaFree(ctx->work_ctr);
   if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
@@ -254,6 +267,7 @@ int eo_flush_l2(eo_ctx* ctx, size_t bytes) {
   if (bytes > ctx->flush_bytes) {
     EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_cmp));
     if (ctx->flush) cudaFree(ctx->flush);
+  if (ctx->scratch) cudaFree(ctx->scratch);
     ctx->flush = nullptr;
     ctx->flush_bytes = 0;
     EO_CUDA(ctx, cudaMalloc(&ctx->flush, bytes));

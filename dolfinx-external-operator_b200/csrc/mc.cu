@@ -30,6 +30,7 @@
 #define MC_NSLOTS 512    // state slots per CTA (power of two: ring-buffer arithmetic)
 #define MC_TILE 4096     // points per work item of the global counter
 #define MC_SIMPLE_THREADS 128
+#define MC_CTR_LIST 32   // word of the context's counter block that holds the length of the plastic-point list
 
 struct mc_ptrs {
   const double* deps;
@@ -122,9 +123,14 @@ __device__ __forceinline__ void mc_q_push(mc_queue* q, volatile unsigned short* 
   if (lane == 0) atomicAdd(&q->cnt, (unsigned)__popc(m));
 }
 
-template <bool ASSOC, int AFF>
-__global__ void __launch_bounds__(MC_THREADS, 1) mc_kernel(const mc_consts k, const mc_ptrs P, const int64_t n,
-                                                           eo_stats* __restrict__ stats, unsigned int* tile_ctr) {
+// LISTED: the yield test has already been done by mc_trial_kernel (two-pass scheme); the T stage then only fetches
+// plastic points from the list (point index + f(trial)) and opens their slots.
+template <bool ASSOC, int AFF, bool LISTED>
+__global__ void __launch_bounds__(MC_THREADS, 1) mc_kernel(const mc_consts k, const mc_ptrs P, const int64_t n_in,
+                                                           eo_stats* __restrict__ stats, unsigned int* tile_ctr,
+                                                           const int32_t* __restrict__ list,
+                                                           const double* __restrict__ list_yl) {
+  const int64_t n = LISTED ? (int64_t)tile_ctr[MC_CTR_LIST] : n_in;
   extern __shared__ double s_slots[];  // [ASSOC ? MC_NF_ASSOC : MC_NF][MC_NSLOTS]
   __shared__ unsigned short s_ring[4][MC_NSLOTS];
   __shared__ long long s_pt[MC_NSLOTS];
@@ -249,6 +255,9 @@ __global__ void __launch_bounds__(MC_THREADS, 1) mc_kernel(const mc_consts k, co
       __nanosleep(100);
       continue;
     }
+#ifdef MC_DEBUG_COUNTERS
+    const long long dbg_t0 = clock64();
+#endif
     take = __shfl_sync(0xffffffffu, take, 0);
     qpos = __shfl_sync(0xffffffffu, qpos, 0);
 
@@ -260,8 +269,19 @@ __global__ void __launch_bounds__(MC_THREADS, 1) mc_kernel(const mc_consts k, co
       const int myres = mc_q_read(s_ring[MC_Q_FREE], qpos + lane);  // the lane-th reserved slot
       bool plastic = false;
       double yl = 0.0, sn[4], Cde[4];
-      const int64_t i = in0 + lane;
-      if (lane < take) {
+      int64_t i = in0 + lane;
+      if (LISTED) {
+        if (lane < take) {
+          yl = list_yl[i];
+          i = list[i];
+          const eo_d4 e = eo_ld256(P.deps + 4 * i);
+          const eo_d4 sg = eo_ld256(P.sigma_n + 4 * i);
+          const double de[4] = {e.x, e.y, e.z, e.w};
+          sn[0] = sg.x, sn[1] = sg.y, sn[2] = sg.z, sn[3] = sg.w;
+          mc_Cmul(k, de, Cde);
+          plastic = true;
+        }
+      } else if (lane < take) {
         const eo_d4 e = eo_ld256(P.deps + 4 * i);
         const eo_d4 sg = eo_ld256(P.sigma_n + 4 * i);
         const double de[4] = {e.x, e.y, e.z, e.w};
@@ -331,6 +351,11 @@ __global__ void __launch_bounds__(MC_THREADS, 1) mc_kernel(const mc_consts k, co
     mc_q_push(&s_q[qB], s_ring[qB], slotB, lane);
     mc_q_push(&s_q[MC_Q_FREE], s_ring[MC_Q_FREE], slotA, lane);
     __syncwarp();
+#ifdef MC_DEBUG_COUNTERS
+    if (lane == 0)  // warp-cycles per stage kind: 64-bit counters at words 16.. (T, S0, U0, U)
+      atomicAdd(reinterpret_cast<unsigned long long*>(tile_ctr + 16) + (stage == MC_STAGE_T ? 0 : stage + 1),
+                (unsigned long long)(clock64() - dbg_t0));
+#endif
   }
 
   // ------------------------------------------------------------------ statistics flush
@@ -341,7 +366,7 @@ __global__ void __launch_bounds__(MC_THREADS, 1) mc_kernel(const mc_consts k, co
     if (s_plastic) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_plastic), (unsigned long long)s_plastic);
     if (s_nonconv) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_nonconverged), (unsigned long long)s_nonconv);
     if (s_nonfinite) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_nonfinite), (unsigned long long)s_nonfinite);
-    if (blockIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_points), (unsigned long long)n);
+    if (blockIdx.x == 0 && !LISTED) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_points), (unsigned long long)n);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -353,6 +378,90 @@ __global__ void __launch_bounds__(MC_THREADS, 1) mc_kernel(const mc_consts k, co
     mc_atomic_max_f64(&stats->f_max, max_f);
     mc_atomic_max_f64(&stats->res_max, max_res);
     mc_atomic_max_f64(&stats->niter_max, (double)max_it);
+  }
+}
+
+// Two-pass scheme, pass 1: one thread per point at full occupancy (HBM-bound for elastic points): trial stress and
+// yield test (:421-422); elastic points are finished here, plastic points are appended (warp-aggregated) to a list
+// that mc_kernel<.., LISTED> works off.  The long dependent FP64 chain of the yield test (asin, sincos, sqrt) is
+// latency-bound at the 12 warps/SM of the persistent kernel; here 8x more warps hide it.
+template <bool ASSOC>
+__global__ void __launch_bounds__(256, 4) mc_trial_kernel(const mc_consts k, const mc_ptrs P, const int64_t n,
+                                                       eo_stats* __restrict__ stats, unsigned int* ctr,
+                                                       int32_t* __restrict__ list, double* __restrict__ list_yl) {
+  __shared__ unsigned int s_hist0, s_hist1, s_histx, s_nonfinite;
+  if (threadIdx.x == 0) s_hist0 = s_hist1 = s_histx = s_nonfinite = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  double max_f = -INFINITY, max_res = 0.0;
+  int max_it = 0;
+  bool plastic = false;
+  double yl = 0.0;
+  if (i < n) {
+    const eo_d4 e = eo_ld256(P.deps + 4 * i);
+    const eo_d4 sg = eo_ld256(P.sigma_n + 4 * i);
+    const double de[4] = {e.x, e.y, e.z, e.w}, sn[4] = {sg.x, sg.y, sg.z, sg.w};
+    double Cde[4];
+    yl = mc_trial(k, de, sn, Cde);
+    max_f = yl;
+    if (yl <= 0.0) {
+      double sig[4], Ct[16], nr, dl;
+      const int32_t it = mc_elastic(k, sn, Cde, sig, Ct, nr, dl);
+      mc_store_point(P, i, Ct, sig);
+      mc_store_aux(P, i, it, yl, nr, dl);
+      max_res = nr;
+      max_it = it;
+      if (it == 0) atomicAdd(&s_hist0, 1u);
+      else if (it == 1) atomicAdd(&s_hist1, 1u);
+      else atomicAdd(reinterpret_cast<unsigned long long*>(&stats->niter_hist[min(it, EO_NITER_BINS - 1)]), 1ull);
+      if (!(isfinite(sig[0]) && isfinite(sig[1]) && isfinite(sig[2]) && isfinite(sig[3]))) atomicAdd(&s_nonfinite, 1u);
+    } else {
+      plastic = true;  // NaN predicate -> plastic branch, like `yielding <= 0.0` being false
+    }
+  }
+  // ---- CTA-aggregated epilogue: ONE list reservation and one set of statistics atomics per CTA (a per-warp
+  //      atomicAdd on the single list counter would serialise 6 x 10^5 same-address atomics per 2 x 10^7 points)
+  __shared__ unsigned int s_wbase[8];
+  __shared__ double s_mf[8], s_mr[8];
+  __shared__ int s_mi[8];
+  const int warp = threadIdx.x >> 5;
+  const unsigned pm = __ballot_sync(0xffffffffu, plastic);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    max_f = fmax(max_f, __shfl_xor_sync(0xffffffffu, max_f, o));
+    max_res = fmax(max_res, __shfl_xor_sync(0xffffffffu, max_res, o));
+    max_it = max(max_it, __shfl_xor_sync(0xffffffffu, max_it, o));
+  }
+  if (lane == 0) s_wbase[warp] = __popc(pm), s_mf[warp] = max_f, s_mr[warp] = max_res, s_mi[warp] = max_it;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int total = 0;
+    double mf = -INFINITY, mr = 0.0;
+    int mi = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const unsigned int c = s_wbase[w];
+      s_wbase[w] = total;
+      total += c;
+      mf = fmax(mf, s_mf[w]), mr = fmax(mr, s_mr[w]), mi = max(mi, s_mi[w]);
+    }
+    const unsigned int base = total ? atomicAdd(ctr + MC_CTR_LIST, total) : 0u;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s_wbase[w] += base;
+    mc_atomic_max_f64(&stats->f_max, mf);
+    mc_atomic_max_f64(&stats->res_max, mr);
+    mc_atomic_max_f64(&stats->niter_max, (double)mi);
+    if (s_hist0) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->niter_hist[0]), (unsigned long long)s_hist0);
+    if (s_hist1) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->niter_hist[1]), (unsigned long long)s_hist1);
+    if (s_nonfinite) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_nonfinite), (unsigned long long)s_nonfinite);
+    if (blockIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_points), (unsigned long long)n);
+  }
+  __syncthreads();
+  if (plastic) {
+    const unsigned int pos = s_wbase[warp] + __popc(pm & ((1u << lane) - 1u));
+    list[pos] = (int32_t)i;
+    list_yl[pos] = yl;
   }
 }
 
@@ -372,17 +481,32 @@ __global__ void __launch_bounds__(MC_SIMPLE_THREADS) mc_kernel_simple(const mc_c
   mc_store_aux(P, i, it, yl, nr, dl);
 }
 
-static bool g_mc_attr_set[4] = {false, false, false, false};
+static bool g_mc_attr_set[8] = {};
 
-template <bool ASSOC, int AFF>
+template <bool ASSOC, int AFF, bool LISTED>
 static int mc_launch_queue(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, int64_t n, size_t smem, unsigned grid) {
-  const int a = (ASSOC ? 1 : 0) + 2 * AFF;
+  const int a = (ASSOC ? 1 : 0) + 2 * AFF + 4 * (LISTED ? 1 : 0);
   if (!g_mc_attr_set[a]) {
-    cudaError_t e = cudaFuncSetAttribute(mc_kernel<ASSOC, AFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mc_kernel<ASSOC, AFF, LISTED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return eo_fail(ctx, EO_ERR_CUDA, "eo_mc_eval: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     g_mc_attr_set[a] = true;
   }
-  mc_kernel<ASSOC, AFF><<<grid, MC_THREADS, smem, ctx->s_cmp>>>(k, P, n, ctx->stats, ctx->work_ctr);
+  int32_t* list = nullptr;
+  double* list_yl = nullptr;
+  if (LISTED) {
+    // pass 1: yield test for every point at full occupancy; plastic points land in the list
+    if (n > 2147483647LL) return eo_fail(ctx, EO_ERR_INVALID, "eo_mc_eval: n too large for one launch");
+    void* sc = nullptr;
+    const size_t yl_off = (size_t(n) * 4 + 255) / 256 * 256;
+    int rc = eo_scratch(ctx, yl_off + size_t(n) * 8, &sc);
+    if (rc != EO_OK) return rc;
+    list = reinterpret_cast<int32_t*>(sc);
+    list_yl = reinterpret_cast<double*>(reinterpret_cast<char*>(sc) + yl_off);
+    mc_trial_kernel<ASSOC><<<unsigned((n + 255) / 256), 256, 0, ctx->s_cmp>>>(k, P, n, ctx->stats, ctx->work_ctr, list, list_yl);
+    ctx->launches += 1;
+    grid = (unsigned)ctx->sm_count;  // the list length is only known on the device
+  }
+  mc_kernel<ASSOC, AFF, LISTED><<<grid, MC_THREADS, smem, ctx->s_cmp>>>(k, P, n, ctx->stats, ctx->work_ctr, list, list_yl);
   return EO_OK;
 }
 
@@ -404,10 +528,12 @@ static int mc_launch(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, int64_t 
   cudaError_t e = cudaMemsetAsync(ctx->work_ctr, 0, 256, ctx->s_cmp);
   if (e != cudaSuccess) return eo_fail(ctx, EO_ERR_CUDA, "eo_mc_eval: cudaMemsetAsync: %s", cudaGetErrorString(e));
   int rc;
-  if (scheme == 2)  // no stage affinity: any warp takes the highest-priority full queue (kept for A/B measurements)
-    rc = k.assoc ? mc_launch_queue<true, 0>(ctx, k, P, n, smem, (unsigned)grid) : mc_launch_queue<false, 0>(ctx, k, P, n, smem, (unsigned)grid);
-  else
-    rc = k.assoc ? mc_launch_queue<true, 1>(ctx, k, P, n, smem, (unsigned)grid) : mc_launch_queue<false, 1>(ctx, k, P, n, smem, (unsigned)grid);
+  if (scheme == 2)  // one pass, no stage affinity: any warp takes the highest-priority full queue (A/B measurements)
+    rc = k.assoc ? mc_launch_queue<true, 0, false>(ctx, k, P, n, smem, (unsigned)grid) : mc_launch_queue<false, 0, false>(ctx, k, P, n, smem, (unsigned)grid);
+  else if (scheme == 3)  // one pass with stage affinity: the yield test is the scheduler's T stage (A/B measurements)
+    rc = k.assoc ? mc_launch_queue<true, 1, false>(ctx, k, P, n, smem, (unsigned)grid) : mc_launch_queue<false, 1, false>(ctx, k, P, n, smem, (unsigned)grid);
+  else  // default: two passes - yield test at full occupancy, then the stage scheduler over the plastic list
+    rc = k.assoc ? mc_launch_queue<true, 1, true>(ctx, k, P, n, smem, (unsigned)grid) : mc_launch_queue<false, 1, true>(ctx, k, P, n, smem, (unsigned)grid);
   if (rc != EO_OK) return rc;
   ctx->launches += 1;
   return EO_OK;
@@ -417,7 +543,11 @@ extern "C" {
 
 int eo_mc_eval(eo_ctx* ctx, const eo_mc_params* prm, const double* deps, const double* sigma_n, double* C_tang,
                double* sigma, int32_t* niter, double* yielding, double* norm_res, double* dlambda, int64_t n) {
-  return eo_mc_eval_scheme(ctx, prm, deps, sigma_n, C_tang, sigma, niter, yielding, norm_res, dlambda, n, 0);
+  static const int def_scheme = [] {  // EO_MC_SCHEME overrides the default execution scheme (A/B runs of the test-suite)
+    const char* e = getenv("EO_MC_SCHEME");
+    return (e && *e >= '0' && *e <= '3') ? *e - '0' : 0;
+  }();
+  return eo_mc_eval_scheme(ctx, prm, deps, sigma_n, C_tang, sigma, niter, yielding, norm_res, dlambda, n, def_scheme);
 }
 
 int eo_mc_eval_scheme(eo_ctx* ctx, const eo_mc_params* prm, const double* deps, const double* sigma_n, double* C_tang,
@@ -426,7 +556,7 @@ int eo_mc_eval_scheme(eo_ctx* ctx, const eo_mc_params* prm, const double* deps, 
   EO_REQUIRE(ctx, ctx != nullptr, "eo_mc_eval: ctx is NULL");
   EO_REQUIRE(ctx, prm != nullptr, "eo_mc_eval: prm is NULL");
   EO_REQUIRE(ctx, n >= 0, "eo_mc_eval: n < 0");
-  EO_REQUIRE(ctx, scheme >= 0 && scheme <= 2, "eo_mc_eval: unknown scheme");
+  EO_REQUIRE(ctx, scheme >= 0 && scheme <= 3, "eo_mc_eval: unknown scheme");
   EO_REQUIRE(ctx, prm->Nitermax >= 0 && prm->Nitermax <= 200,
              "eo_mc_eval: Nitermax must be in [0, 200] (histogram bins of eo_stats)");
   if (n == 0) return EO_OK;

@@ -291,9 +291,12 @@ typedef struct eo_mc_params {
  * deps, sigma_n, C_tang, sigma must be 32-byte aligned when they are device pointers. */
 int eo_mc_eval(eo_ctx* ctx, const eo_mc_params* prm, const double* deps, const double* sigma_n, double* C_tang,
                double* sigma, int32_t* niter, double* yielding, double* norm_res, double* dlambda, int64_t n);
-/* Same with an explicit execution scheme: 0 = persistent CTAs with shared-memory stage queues, stage kinds
- * pinned to SM sub-partitions (the default of eo_mc_eval), 1 = one thread per point (divergent baseline;
- * does not update the statistics record), 2 = scheme 0 without the sub-partition affinity (A/B measurements). */
+/* Same with an explicit execution scheme: 0 = two passes (the default of eo_mc_eval): yield test for every point
+ * at full occupancy, elastic points finished there, plastic points listed; then persistent CTAs with
+ * shared-memory stage queues (stage kinds pinned to SM sub-partitions) run the Newton iterations of the listed
+ * points.  1 = one thread per point (divergent baseline; does not update the statistics record); 2 / 3 = one
+ * pass (the yield test is a stage of the scheduler) without / with the sub-partition affinity - kept for A/B
+ * measurements.  All schemes give the same results. */
 int eo_mc_eval_scheme(eo_ctx* ctx, const eo_mc_params* prm, const double* deps, const double* sigma_n,
                       double* C_tang, double* sigma, int32_t* niter, double* yielding, double* norm_res,
                       double* dlambda, int64_t n, int scheme);

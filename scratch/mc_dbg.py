@@ -25,6 +25,7 @@ for scheme in schemes * 3:
     cnt = np.zeros(64, dtype=np.uint32)
     ctx.check(ctx.lib.eo_debug_counters(ctx.handle, cnt.ctypes.data))
     c64 = cnt.view(np.uint64)
+    c64 = c64[0:]
     tot = float(c64[8] + c64[9] + c64[10] + c64[11]) or 1.0
     print("  cycles share: T %.1f%% S0 %.1f%% U0 %.1f%% U %.1f%%  (sum %.3g warp-cycles; per SM-warp %.3g)" % (100*c64[8]/tot, 100*c64[9]/tot, 100*c64[10]/tot, 100*c64[11]/tot, tot, tot/148/12))
     print(f"scheme={scheme} n={n} {ms:.3f} ms  {n/ms/1e6:.3f} GQP/s  tiles={cnt[0]} T={cnt[1]}/{cnt[2]} S0={cnt[3]}/{cnt[4]} U0={cnt[5]}/{cnt[6]} U={cnt[7]}/{cnt[8]} wait={cnt[9]}")
