@@ -303,6 +303,14 @@ def run_gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    numa_cores = None
+    if world > 1 and not args.no_numa_bind:
+        # one rank per GPU: keep this rank's threads and pinned buffers on the GPU's own NUMA node
+        from dolfinx_external_operator_b200.parallel import bind_to_gpu_numa
+
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(visible.split(",")[local_rank]) if visible and visible.split(",")[local_rank].isdigit() else local_rank
+        numa_cores = bind_to_gpu_numa(phys)
     ctx = eo.Context(local_rank)
     n = int(args.n)
     model = args.model
@@ -562,7 +570,9 @@ def run_gpu_arm(args):
 
     # ---- CPU baseline on this box's host cores (bounded sample)
     cpu = None
-    if model == "isihara":
+    if world > 1:
+        cpu = None  # the CPU baseline is reported at N = 1 only (the reference arm is timed separately at every N)
+    elif model == "isihara":
         cpu = None  # the CPU implementation is the reference's torch code, which needs /root/reference: timed in the
         #             build container only (69 k QP/s on 8 threads)
     elif args.cpu_seconds > 0 and model in ("tab", "fused", "jitfused"):
@@ -593,6 +603,9 @@ def run_gpu_arm(args):
         cfg["niter_histogram"] = {int(i): float(hist[i]) / tot for i in np.nonzero(hist)[0]}
         cfg["n_nonconverged"] = stats["n_nonconverged"]
     cfg.update(extra_cfg)
+    if world > 1:
+        cfg["cpu_binding"] = (f"rank pinned to the {len(numa_cores)} cores local to its GPU (NVML affinity)" if numa_cores
+                              else "none")
     line = {
         "metric": METRIC, "value": value, "unit": "QP/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -618,6 +631,7 @@ def main():
     ap.add_argument("--state-layout", default="aos", choices=["aos", "soa"])
     ap.add_argument("--cpu-sample", type=float, default=4e6)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-numa-bind", action="store_true", help="multi-GPU: do not pin ranks to their GPU's NUMA node")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -77,3 +77,29 @@ def allreduce_stats_device(ctx, group=None) -> None:
     with torch.cuda.stream(torch.cuda.ExternalStream(ctx.stream, device=f"cuda:{ctx.device}")):
         dist.all_reduce(ts, op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(tm, op=dist.ReduceOp.MAX, group=group)
+
+
+def bind_to_gpu_numa(device: int) -> list[int] | None:
+    """Pin the calling process to the CPU cores that are local to `device` (NVML's ideal CPU affinity), so that the
+    page-locked result buffers it allocates afterwards - and the threads that touch them - live on the GPU's own
+    NUMA node.  One rank per GPU (external_operator.py:368-370 under MPI) without this lands every rank's pinned
+    memory wherever the launcher started it, and the D2H of the tangent then crosses the socket interconnect.
+    Returns the core list, or None when NVML / sched_setaffinity are unavailable (nothing is changed then)."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device))
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cores = [64 * w + b for w, mask in enumerate(words) for b in range(64) if (int(mask) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cores = [c for c in cores if c in allowed]
+        if not cores:
+            return None
+        os.sched_setaffinity(0, cores)
+        return cores
+    except Exception:
+        return None

@@ -150,6 +150,14 @@ def test_fused_tabulation_von_mises_equals_two_step(ctx):
     for a, b in zip((Ct, sig, dp), ref):
         assert np.array_equal(a, b)  # same arithmetic, same bits
     assert np.array_equal(op.ref_coefficient.x.array, ref[0])
+    # chunked host pipeline: chunks that are not multiples of nq (the kernel maps global point -> (cell, q))
+    ctx.set_chunk(1000)
+    try:
+        ((Ct3, sig3, dp3),) = eo.evaluate_external_operators([op], ops)
+        for a, b in zip((Ct3, sig3, dp3), ref):
+            assert np.array_equal(a, b)
+    finally:
+        ctx.set_chunk(1 << 20)
     # the hard-wired von Mises callable fuses the same way (eo_tab_vm_fused, exact variant)
     vm = eo.VonMises(ctx=ctx)
     vm.set_history(sn, p)
