@@ -37,7 +37,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BYTES_PER_QP = {"vm": 240, "jitvm": 240, "jitfused": 235, "heat": 88, "mc": 252, "tab": 176.0 / 3.0, "fused": 235, "isihara": 192}
+BYTES_PER_QP = {"vm": 240, "jitvm": 240, "jitfused": 235, "jitvm3d": 448, "heat": 88, "mc": 252, "tab": 176.0 / 3.0, "fused": 235, "isihara": 192}
 METRIC = "quadrature points per second (stress + consistent tangent + internal state)"
 
 
@@ -250,6 +250,9 @@ WORKLOADS = {
                "tangent dP/dF from the 3-64-64-64-1 float32 network, float64 invariants",
     "jitvm": "von Mises return mapping written as a user model for the run-time compiled (NVRTC) generic path: "
              "stress + tangent by forward-mode dual numbers + plastic multiplier, plane-strain Mandel 4-vectors",
+    "jitvm3d": "EXTENSION (BASELINE configs[4] '3D'): von Mises return mapping for 6-component Mandel vectors as a "
+               "run-time compiled user model, 6x6 tangent by dual numbers (no reference implementation: the demos are "
+               "plane strain)",
     "jitfused": "operand tabulation fused into the run-time compiled (NVRTC) von Mises user model: P2 vector field, 3 points "
                 "per triangle, strain never stored, tangent by dual numbers",
     "tab": "operand tabulation: Mandel strain of a P2 vector field at 3 quadrature points per triangle "
@@ -339,6 +342,23 @@ def run_gpu_arm(args):
 
         def step():
             vm.eval_device(d_deps, d_Ct)
+    elif model == "jitvm3d":
+        from dolfinx_external_operator_b200 import jit_models as jm
+
+        jv = jm.von_mises_3d(ctx=ctx)
+        rng = np.random.default_rng(rank)
+        deps_t, sn_t = rng.normal(0.0, 2e-3, (tile_n, 6)), rng.normal(0.0, 100.0, (tile_n, 6))
+        p_t = np.abs(rng.normal(0.0, 1e-3, tile_n))
+        d_deps = ctx.empty((n * 6,))
+        _tile_to_device(ctx, d_deps, deps_t, n, 6)
+        jv.state = [ctx.empty((n * 6,)), ctx.empty((n,))]
+        _tile_to_device(ctx, jv.state[0], sn_t, n, 6)
+        _tile_to_device(ctx, jv.state[1], p_t, n, 1)
+        d_Ct, d_sig, d_dp = ctx.empty((n * 36,)), ctx.empty((n * 6,)), ctx.empty((n,))
+        jv.compile((1,))
+
+        def step():
+            jv.eval_device((1,), [d_deps], d_Ct, d_sig, [d_dp])
     elif model == "jitvm":
         from dolfinx_external_operator_b200 import jit_models as jm
 
@@ -525,6 +545,24 @@ def run_gpu_arm(args):
         dt = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": world * ne * Ke / dt, "unit": "QP/s", "h2d_bytes_per_step": 32 * ne,
                "d2h_bytes_per_step": d2h, "qp_per_step_per_gpu": ne, "steps": Ke, "api": api}
+        # host<->device transfer times on their own (CUDA events, pinned buffers): what bounds the end-to-end figure
+        d_tmp = ctx.empty((16 * ne,))
+        evs = [ctx.event() for _ in range(4)]
+        ctx.copy(d_tmp, deps_h, 32 * ne)  # warm
+        ctx.sync()
+        ctx.record(evs[0])
+        ctx.copy(d_tmp, deps_h, 32 * ne)
+        ctx.record(evs[1])
+        ctx.sync()
+        ctx.record(evs[2])
+        ctx.copy(out[0], d_tmp, 128 * ne)
+        ctx.record(evs[3])
+        ctx.sync()
+        h2d_ms, d2h_ms = ctx.elapsed_ms(evs[0], evs[1]), ctx.elapsed_ms(evs[2], evs[3])
+        e2e.update(h2d_ms_alone=h2d_ms, h2d_gbs_alone=32 * ne / h2d_ms / 1e6, d2h_tangent_ms_alone=d2h_ms,
+                   d2h_gbs_alone=128 * ne / d2h_ms / 1e6, ms_per_step=1e3 * dt / Ke,
+                   bound="PCIe device-to-host: the result is 168-188 B per point, the kernel needs < 10 % of the step")
+        d_tmp.free()
 
     if rank != 0:
         if dist is not None:
@@ -579,11 +617,12 @@ def run_gpu_arm(args):
         cpu = cpu_tab_rate("fused" if model == "jitfused" else model, args.cpu_seconds)
     elif args.cpu_seconds > 0:
         sample = int(args.cpu_sample) if model != "mc" else min(int(args.cpu_sample), 200_000)
-        cm = "vm" if model == "jitvm" else model
+        cm = "vm" if model in ("jitvm", "jitvm3d") else model
         rate, cores, passes = cpu_port_rate(cm, sample, args.cpu_seconds, parallel=True)
         rate1, _, _ = cpu_port_rate(cm, sample // 4, min(3.0, args.cpu_seconds), parallel=False)
         what = {"vm": "C restatement of the reference's Numba kernel (serial in the reference)",
                 "jitvm": "C restatement of the reference's Numba kernel (serial in the reference)",
+                "jitvm3d": "C restatement of the reference's plane-strain Numba kernel (no 3-D CPU implementation exists)",
                 "heat": "C restatement of the reference's NumPy functions",
                 "mc": "C++ nested-dual-number restatement of the reference's JAX program (JAX not installable offline)"}
         cpu = {"value": rate, "unit": "QP/s", "cores": cores, "kind": "port",
@@ -623,7 +662,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--model", default="vm", choices=["vm", "heat", "mc", "tab", "fused", "isihara", "jitvm", "jitfused"])
+    ap.add_argument("--model", default="vm", choices=["vm", "heat", "mc", "tab", "fused", "isihara", "jitvm", "jitfused", "jitvm3d"])
     ap.add_argument("--fused-exact", action="store_true")
     ap.add_argument("--mc-scheme", default="queue", choices=["queue", "simple", "queue-noaffinity", "queue-onepass"])
     ap.add_argument("--n", type=float, default=1e8, help="quadrature points per GPU (device-resident leg)")

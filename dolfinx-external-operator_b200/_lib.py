@@ -124,6 +124,7 @@ PROTOTYPES = {
     "eo_stats_reset": (C.c_int, [_vp]),
     "eo_stats_read": (C.c_int, [_vp, C.POINTER(Stats)]),
     "eo_stats_device_ptr": (_vp, [_vp]),
+    "eo_allreduce_stats": (C.c_int, [_vp, _vp]),
     "eo_vm_eval": (C.c_int, [_vp, C.POINTER(VmParams), _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
     "eo_vm_eval_resident": (C.c_int, [_vp, C.POINTER(VmParams), _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_int]),
     "eo_commit_history": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, C.c_int]),

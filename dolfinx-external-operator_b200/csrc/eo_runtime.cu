@@ -1,7 +1,10 @@
 // eo_runtime.cu - context, memory, events and statistics of libeo_b200.so.
 #include "eo_common.cuh"
 
+#include <dlfcn.h>
+
 #include <cmath>
+#include <cstddef>
 
 char g_eo_create_error[512] = {0};
 
@@ -294,6 +297,38 @@ int eo_assign_gather(eo_ctx* ctx, const double* values, int64_t n_values, const 
     ctx->launches += 1;
     return EO_OK;
   });
+}
+
+// The one collective of the path: in-place all-reduce of the device statistics record over a
+// caller-owned NCCL communicator, ordered on the ctx compute stream.  NCCL is resolved at run time from whatever
+// libnccl.so.2 the process has (PyTorch's bundled one, or the system library): no link-time dependency.
+int eo_allreduce_stats(eo_ctx* ctx, void* nccl_comm) {
+  EO_REQUIRE(ctx, ctx != nullptr, "eo_allreduce_stats: ctx is NULL");
+  EO_REQUIRE(ctx, nccl_comm != nullptr, "eo_allreduce_stats: communicator is NULL");
+  typedef int (*allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  typedef const char* (*errstr_fn)(int);
+  static allreduce_fn allreduce = nullptr;
+  static errstr_fn errstr = nullptr;
+  if (!allreduce) {
+    void* h = nullptr;
+    const char* names[] = {getenv("EO_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      if (!nm || !*nm) continue;
+      if ((h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL))) break;
+    }
+    if (!h) return eo_fail(ctx, EO_ERR_UNSUPPORTED, "eo_allreduce_stats: libnccl.so.2 not found (set EO_NCCL_LIB)");
+    *(void**)(&allreduce) = dlsym(h, "ncclAllReduce");
+    *(void**)(&errstr) = dlsym(h, "ncclGetErrorString");
+    if (!allreduce) return eo_fail(ctx, EO_ERR_UNSUPPORTED, "eo_allreduce_stats: ncclAllReduce not found in libnccl");
+  }
+  EO_CUDA(ctx, cudaSetDevice(ctx->device));
+  static_assert(offsetof(eo_stats, niter_max) == (4 + EO_NITER_BINS) * 8, "SUM block first, MAX block after it");
+  char* base = reinterpret_cast<char*>(ctx->stats);
+  const int NCCL_INT64 = 4, NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2;
+  int rc = allreduce(base, base, 4 + EO_NITER_BINS, NCCL_INT64, NCCL_SUM, nccl_comm, ctx->s_cmp);
+  if (rc == 0) rc = allreduce(base + offsetof(eo_stats, niter_max), base + offsetof(eo_stats, niter_max), 4, NCCL_FLOAT64, NCCL_MAX, nccl_comm, ctx->s_cmp);
+  if (rc != 0) return eo_fail(ctx, EO_ERR_CUDA, "eo_allreduce_stats: ncclAllReduce: %s", errstr ? errstr(rc) : "error");
+  return EO_OK;
 }
 
 int eo_debug_counters(eo_ctx* ctx, uint32_t* out) {

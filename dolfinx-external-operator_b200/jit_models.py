@@ -37,6 +37,36 @@ __device__ void vm_sigma(const T* deps, const double* st, const double* prm, T* 
 }
 """
 
+# EXTENSION (not in the reference, whose demos are plane strain): the same radial return for full 3-D stress states,
+# 6-component Mandel vectors [xx, yy, zz, sqrt2 yz, sqrt2 xz, sqrt2 xy]; tangent 6x6 by dual numbers.
+VON_MISES_3D = r"""
+template <class T>
+__device__ void vm3d_sigma(const T* deps, const double* st, const double* prm, T* sig, T* aux) {
+  const double l = prm[0], m = prm[1], H = prm[2], sig0 = prm[3];
+  const double third = 1.0 / 3.0;
+  const double p = st[6];
+  const T trd = deps[0] + deps[1] + deps[2];
+  T se[6];
+  for (int i = 0; i < 3; ++i) se[i] = st[i] + (l * trd + 2.0 * m * deps[i]);
+  for (int i = 3; i < 6; ++i) se[i] = st[i] + 2.0 * m * deps[i];
+  const T tr = third * (se[0] + se[1] + se[2]);
+  T s[6] = {se[0] - tr, se[1] - tr, se[2] - tr, se[3], se[4], se[5]};
+  T ss = s[0] * s[0];
+  for (int i = 1; i < 6; ++i) ss = ss + s[i] * s[i];
+  const T seq = sqrt(1.5 * ss);
+  const T f = seq - sig0 - H * p;
+  if (f > 0.0) {
+    const T dp = f / (3.0 * m + H);
+    const T beta = 3.0 * m * dp / seq;
+    for (int i = 0; i < 6; ++i) sig[i] = se[i] - beta * s[i];
+    aux[0] = dp;
+  } else {
+    for (int i = 0; i < 6; ++i) sig[i] = se[i];
+    aux[0] = T(0.0);
+  }
+}
+"""
+
 # nonlinear heat flux q(T, sigma) = -k(T) sigma with k = 1 / (A + B T)
 # (doc/demo/demo_nonlinear_heat_equation_part2.py:215-261; derivatives :228-261 come from AD here).
 HEAT_FLUX = r"""
@@ -68,6 +98,19 @@ def von_mises(E=70e3, nu=0.3, E_tangent=None, sigma_0=250.0, **kw):
     mu = E / 2.0 / (1.0 + nu)
     kw.setdefault("returns", ("out", "value", "aux0"))
     return JitModel(VON_MISES, "vm_sigma", [(4,)], (4,), state_shapes=[(4,), ()], aux_shapes=[()],
+                    params=[lmbda, mu, H, sigma_0], **kw)
+
+
+def von_mises_3d(E=70e3, nu=0.3, E_tangent=None, sigma_0=250.0, **kw):
+    """EXTENSION: von Mises for 6-component Mandel vectors; `(1,)` -> (C_tang [qp][6][6], sigma [qp][6], dp [qp])."""
+    from .jit import JitModel
+
+    E_tangent = E / 100.0 if E_tangent is None else E_tangent
+    H = E * E_tangent / (E - E_tangent)
+    lmbda = E * nu / (1.0 + nu) / (1.0 - 2.0 * nu)
+    mu = E / 2.0 / (1.0 + nu)
+    kw.setdefault("returns", ("out", "value", "aux0"))
+    return JitModel(VON_MISES_3D, "vm3d_sigma", [(6,)], (6,), state_shapes=[(6,), ()], aux_shapes=[()],
                     params=[lmbda, mu, H, sigma_0], **kw)
 
 

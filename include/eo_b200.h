@@ -144,6 +144,12 @@ int eo_stats_reset(eo_ctx* ctx);
 int eo_stats_read(eo_ctx* ctx, eo_stats* host_out);
 /* Device address of the record (for an in-place NCCL all-reduce). */
 void* eo_stats_device_ptr(eo_ctx* ctx);
+/* The one collective of the hot path (quadrature points shard along the cell partition, one rank per GPU, no halo):
+ * in-place all-reduce of the record - SUM over the int64 block, MAX over the f64 block - over the caller's
+ * `ncclComm_t` (passed as void*), asynchronous on the ctx stream.  replaces: the rank-local prints of
+ * demo_plasticity_mohr_coulomb.py:584-591 turned into global figures.  NCCL is resolved at run time (libnccl.so.2 of
+ * the process; EO_NCCL_LIB overrides). */
+int eo_allreduce_stats(eo_ctx* ctx, void* nccl_comm);
 
 /* ---------------------------------------------------------------- von Mises
  * replaces: `return_mapping`/`_kernel`, doc/demo/demo_plasticity_von_mises.py:298-332,

@@ -147,3 +147,31 @@ class MohrCoulombParams:
     @property
     def mu(self) -> float:  # :406
         return self.E / (2.0 * (1.0 + self.nu))
+
+
+# ------------------------------------------------------------------ EXTENSION: full 3-D von Mises (6-component Mandel)
+def vm3d_return_mapping(deps, sigma_n, p, prm: VonMisesParams = VonMisesParams()):
+    """EXTENSION, not in the reference (its demos are plane strain, 4-component Mandel vectors: demo_vm:193-204):
+    the SAME statements as `vm_return_mapping` (demo_vm:307-326) written for 6-component Mandel vectors
+    [xx, yy, zz, sqrt2 yz, sqrt2 xz, sqrt2 xy] - BASELINE config 5 asks for a "3D" batch; this restatement is its oracle.
+    deps, sigma_n: (n, 6); p: (n,).  Returns C_tang (n,6,6), sigma (n,6), dp (n,)."""
+    deps = np.asarray(deps, dtype=np.float64).reshape(-1, 6)
+    sigma_n = np.asarray(sigma_n, dtype=np.float64).reshape(-1, 6)
+    p = np.asarray(p, dtype=np.float64).reshape(-1)
+    l, mu, H = prm.lmbda, prm.mu, prm.H
+    tr = np.array([1.0, 1.0, 1.0, 0.0, 0.0, 0.0])
+    C = l * np.outer(tr, tr) + 2.0 * mu * np.eye(6)
+    D = np.eye(6) - np.outer(tr, tr) / 3.0
+    sigma_el = sigma_n + deps @ C.T
+    s = sigma_el @ D.T
+    sigma_eq = np.sqrt(1.5 * np.einsum("ni,ni->n", s, s))
+    f_el = sigma_eq - prm.sigma_0 - H * p
+    f_plus = (f_el + np.sqrt(f_el**2)) / 2.0
+    dp = f_plus / (3 * mu + H)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        n_el = s / sigma_eq[:, None] * f_plus[:, None] / f_el[:, None]
+    beta = 3 * mu * dp / sigma_eq
+    sigma = sigma_el - beta[:, None] * s
+    nn = n_el[:, :, None] * n_el[:, None, :]
+    C_tang = C[None] - (3 * mu * (3 * mu / (3 * mu + H) - beta))[:, None, None] * nn - (2 * mu * beta)[:, None, None] * D[None]
+    return C_tang, sigma, dp

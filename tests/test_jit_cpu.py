@@ -99,6 +99,39 @@ def test_von_mises_ad_tangent_matches_reference_golden(golden_dir, kind):
     assert np.array_equal(sig0, sig) and np.array_equal(dp0, dp)
 
 
+def _vm3d_batch(n, seed):
+    rng = np.random.default_rng(seed)
+    deps = rng.normal(0.0, 2e-3, (n, 6))
+    sn = rng.normal(0.0, 100.0, (n, 6))
+    p = np.abs(rng.normal(0.0, 1e-3, n))
+    return deps, sn, p
+
+
+def test_von_mises_3d_extension_against_its_oracle():
+    """EXTENSION (BASELINE config 5 '3D'): 6-component model text + dual-number tangent vs the NumPy restatement."""
+    from oracle import constitutive as oc
+
+    deps, sn, p = _vm3d_batch(2000, 0)
+    m = jm.von_mises_3d(compile_only=True)
+    assert m.compile((1,)) > 1000 and m.out_width((1,)) == 36
+    Ct, sig, (dp,) = host_eval(m, (1,), [deps], [sn, p])
+    rC, rs, rdp = oc.vm3d_return_mapping(deps, sn, p)
+    assert np.array_equal(dp > 0, rdp > 0) and 0.2 < (rdp > 0).mean() < 0.9
+    _close(Ct, rC, 1e-11)
+    _close(sig, rs, 1e-12)
+    _close(dp, rdp, 1e-12)
+    # plane-strain consistency with the reference's 4-component model: embed [xx, yy, zz, sqrt2 xy]
+    g4 = np.zeros((500, 6)), np.zeros((500, 6))
+    d4, s4, p4 = (a[:500] for a in _vm3d_batch(500, 1))
+    idx = [0, 1, 2, 5]
+    g4[0][:, idx], g4[1][:, idx] = d4[:, :4], s4[:, :4]
+    C6, s6, dp6 = oc.vm3d_return_mapping(g4[0], g4[1], p4)
+    C4, sg4, dpp4 = oc.vm_return_mapping(d4[:, :4], s4[:, :4], p4)
+    _close(s6[:, idx], sg4, 1e-12)
+    _close(dp6, dpp4, 1e-12)
+    _close(C6[:, idx][:, :, idx], C4, 1e-12)
+
+
 def test_heat_ad_derivatives_match_reference_golden(golden_dir):
     g = np.load(os.path.join(golden_dir, "heat_seed0_n4098.npz"))
     T, s = g["T"], g["sigma"]

@@ -192,3 +192,21 @@ def test_fused_tabulation_two_operands_heat(ctx):
     k = 1.0 / (1.0 + xq[:, 0] ** 2 + xq[:, 1])
     np.testing.assert_allclose(np.array(h((0, 0))(*lz)).reshape(-1, 2), -k[:, None] * np.stack([2 * xq[:, 0], np.ones(len(xq))], 1),
                                rtol=1e-11, atol=1e-12)
+
+
+def test_jit_von_mises_3d_extension(ctx):
+    """EXTENSION (6-component Mandel): NVRTC kernel vs the NumPy restatement oracle/constitutive.py::vm3d_return_mapping."""
+    from oracle import constitutive as oc
+    from test_jit_cpu import _vm3d_batch
+
+    n = 100_003
+    deps, sn, p = _vm3d_batch(n, 5)
+    m = jm.von_mises_3d(ctx=ctx)
+    m.set_state(0, sn)
+    m.set_state(1, p)
+    Ct, sig, dp = m((1,))(deps)
+    rC, rs, rdp = oc.vm3d_return_mapping(deps, sn, p)
+    assert np.array_equal(dp > 0, rdp > 0)
+    _close(Ct, rC, 1e-11)
+    _close(sig, rs, 1e-12)
+    _close(dp, rdp, 1e-12)
