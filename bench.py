@@ -311,9 +311,7 @@ def run_gpu_arm(args):
         # one rank per GPU: keep this rank's threads and pinned buffers on the GPU's own NUMA node
         from dolfinx_external_operator_b200.parallel import bind_to_gpu_numa
 
-        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
-        phys = int(visible.split(",")[local_rank]) if visible and visible.split(",")[local_rank].isdigit() else local_rank
-        numa_cores = bind_to_gpu_numa(phys)
+        numa_cores = bind_to_gpu_numa(local_rank)
     ctx = eo.Context(local_rank)
     n = int(args.n)
     model = args.model

@@ -98,6 +98,7 @@ _dbl = C.c_double
 PROTOTYPES = {
     "eo_version": (C.c_int, []),
     "eo_device_count": (C.c_int, []),
+    "eo_device_pci_bus_id": (C.c_int, [C.c_int, C.c_char_p, C.c_int]),
     "eo_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "eo_destroy": (C.c_int, [_vp]),
     "eo_last_error": (C.c_char_p, [_vp]),

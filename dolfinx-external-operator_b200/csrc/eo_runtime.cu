@@ -77,6 +77,16 @@ int eo_device_count(void) {
   return n;
 }
 
+int eo_device_pci_bus_id(int device, char* buf, int len) {
+  if (!buf || len < 16) return EO_ERR_INVALID;
+  cudaError_t e = cudaDeviceGetPCIBusId(buf, len, device);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return eo_fail(nullptr, EO_ERR_CUDA, "cudaDeviceGetPCIBusId: %s", cudaGetErrorString(e));
+  }
+  return EO_OK;
+}
+
 int eo_create(int device, eo_ctx** out) {
   if (!out) return eo_fail(nullptr, EO_ERR_INVALID, "eo_create: out is NULL");
   *out = nullptr;

@@ -77,7 +77,7 @@ class JitModel:
         if output not in ("host", "device"):
             raise ValueError("output must be 'host' or 'device'")
         self.output = output
-        self._dev_out: dict[str, DeviceArray] = {}
+        self._dev_out: dict = {}
         self.supported = None if supported is None else {tuple(d) for d in supported}
         self._src = source.encode()
         self._entry = entry.encode()
@@ -101,7 +101,7 @@ class JitModel:
             raise EOError(rc, (self.lib.eo_last_error(self.ctx.handle if self.ctx else None) or b"").decode())
         self._h = h
         self.state: list[DeviceArray | None] = [None] * len(self.state_sizes)
-        self._host_out: dict[str, np.ndarray] = {}
+        self._host_out: dict = {}
         self.n_qp = None
 
     def __del__(self):
@@ -180,10 +180,12 @@ class JitModel:
         return impl
 
     def _buf(self, name: str, size: int) -> np.ndarray:
-        a = self._host_out.get(name)
-        if a is None or a.size != size:
+        """Pinned result buffer, one per (field, size): a Newton iteration alternates between derivative orders
+        (different `out` widths) and must not re-allocate page-locked memory at every call."""
+        a = self._host_out.get((name, size))
+        if a is None:
             a = self.ctx.pinned_empty(size)
-            self._host_out[name] = a
+            self._host_out[(name, size)] = a
         return a
 
     def _evaluate(self, derivatives, d, width, operands, device_out: dict | None = None):
@@ -239,9 +241,9 @@ class JitModel:
                 bufs[name] = device_out[name]
                 return device_out[name].ptr
             if self.output == "device" and (name == "out" or name in self.returns):
-                a = self._dev_out.get(name)
-                if a is None or a.size != size:
-                    a = self._dev_out[name] = self.ctx.empty((size,))
+                a = self._dev_out.get((name, size))
+                if a is None:
+                    a = self._dev_out[(name, size)] = self.ctx.empty((size,))
                 bufs[name] = a
                 return a.ptr
             if name == "out" or name in self.returns:

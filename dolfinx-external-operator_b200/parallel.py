@@ -80,7 +80,8 @@ def allreduce_stats_device(ctx, group=None) -> None:
 
 
 def bind_to_gpu_numa(device: int) -> list[int] | None:
-    """Pin the calling process to the CPU cores that are local to `device` (NVML's ideal CPU affinity), so that the
+    """Pin the calling process to the CPU cores that are local to CUDA device `device` (NVML's ideal CPU affinity, the
+    GPU being identified by its PCI bus id), so that the
     page-locked result buffers it allocates afterwards - and the threads that touch them - live on the GPU's own
     NUMA node.  One rank per GPU (external_operator.py:368-370 under MPI) without this lands every rank's pinned
     memory wherever the launcher started it, and the D2H of the tangent then crosses the socket interconnect.
@@ -88,10 +89,17 @@ def bind_to_gpu_numa(device: int) -> list[int] | None:
     import os
 
     try:
+        import ctypes as C
+
         import pynvml
 
+        from . import _lib
+
         pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(int(device))
+        buf = C.create_string_buffer(32)
+        if _lib.load().eo_device_pci_bus_id(int(device), buf, 32) != 0:  # `device` is a CUDA ordinal of this process
+            return None
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(buf.value)
         n_cpu = os.cpu_count() or 1
         words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
         cores = [64 * w + b for w, mask in enumerate(words) for b in range(64) if (int(mask) >> b) & 1]

@@ -55,6 +55,9 @@ typedef struct eo_ctx eo_ctx;
 int eo_version(void);
 /* Number of visible CUDA devices, or a negative eo_status. */
 int eo_device_count(void);
+/* PCI bus id ("0000:1b:00.0") of CUDA device `device` - the key that identifies the same GPU to NVML (CPU / NUMA
+ * affinity of a rank, parallel.bind_to_gpu_numa) whatever CUDA_VISIBLE_DEVICES / device ordering is in force. */
+int eo_device_pci_bus_id(int device, char* buf, int len);
 /* Create a context on `device`.  Fails with EO_ERR_NO_DEVICE when there is no
  * GPU: there is NO CPU fallback in this library. */
 int eo_create(int device, eo_ctx** out);

@@ -304,6 +304,32 @@ EO_DUAL_HD dual<N, V> fmin(double a, const dual<N, V>& b) {
   return a <= value(b.v) ? dual<N, V>(a) : b;
 }
 
+/* spellings users reach for: abs / max / min (CUDA defines ::abs, ::max, ::min for double) */
+template <int N, class V>
+EO_DUAL_HD dual<N, V> abs(const dual<N, V>& a) {
+  return fabs(a);
+}
+template <int N, class V>
+EO_DUAL_HD dual<N, V> max(const dual<N, V>& a, const dual<N, V>& b) {
+  return fmax(a, b);
+}
+template <int N, class V>
+EO_DUAL_HD dual<N, V> min(const dual<N, V>& a, const dual<N, V>& b) {
+  return fmin(a, b);
+}
+template <int N, class V>
+EO_DUAL_HD dual<N, V> max(const dual<N, V>& a, double b) {
+  return fmax(a, b);
+}
+template <int N, class V>
+EO_DUAL_HD dual<N, V> min(const dual<N, V>& a, double b) {
+  return fmin(a, b);
+}
+template <int N, class V>
+EO_DUAL_HD dual<N, V> hypot(const dual<N, V>& a, const dual<N, V>& b) {
+  return sqrt(a * a + b * b);
+}
+
 /* `select(c, a, b)`: c ? a : b for any T (the model-side spelling of lax.cond / np.where) */
 template <class T>
 EO_DUAL_HD T select(bool c, const T& a, const T& b) {

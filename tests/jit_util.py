@@ -15,8 +15,13 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 _DRIVER = r"""
+#include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include "eo_dual.h"
+using std::max;  // CUDA declares ::max / ::min / ::abs for double; the host build borrows the std ones
+using std::min;
+using std::abs;
 #define __device__
 #define __forceinline__ inline
 %(source)s

@@ -162,7 +162,7 @@ __device__ void elem(const T* x, const double*, const double* prm, T* y, T*) {
   y[3] = atan2(a, 1.5 + b * b) + asin(0.3 * sin(a)) + acos(0.2 * cos(b)) + atan(a - b);
   y[4] = pow(1.0 + a * a, 1.5) + pow(2.0 + b * b, a) + pow(1.7, a * b);
   y[5] = tanh(a) + sinh(0.3 * b) * cosh(0.2 * a) + fabs(a - b) + fmax(a, b) * fmin(a * a, 0.5) - a / b + 3 / (2 + a * a);
-  y[6] = eo::select(a > b, a * a * b, b * b * a) + (-a) * prm[0];
+  y[6] = eo::select(a > b, a * a * b, b * b * a) + (-a) * prm[0] + abs(a - 2.0 * b) + max(a, 0.1) * min(b, a * 3.0) + hypot(a, b);
 }
 """
 
