@@ -107,10 +107,23 @@ class Context:
         self._dev_ptrs: set[int] = set()
         self._host_ptrs: set[int] = set()
         self._finalizer = weakref.finalize(self, Context._destroy, self._lib, h)
+        # not at interpreter exit: models / tabulators that still hold this context are torn down in arbitrary order
+        # then, and their destroy calls must not find a freed context (process teardown releases the GPU anyway)
+        self._finalizer.atexit = False
+
+    @property
+    def alive(self) -> bool:
+        """False once `close()` has destroyed the native context (handles created on it must not be used any more)."""
+        return self._finalizer.alive
 
     @staticmethod
     def _destroy(lib, h):
         lib.eo_destroy(h)
+
+    @staticmethod
+    def _host_free(lib, ctx_finalizer, h, ptr):
+        if ctx_finalizer.alive:  # a pinned array that outlives an explicitly closed context is left to the process
+            lib.eo_host_free(h, ptr)
 
     def close(self):
         self._finalizer()
@@ -162,7 +175,8 @@ class Context:
         return a
 
     def _dev_free(self, ptr: int):
-        self.check(self._lib.eo_dev_free(self._h, ptr))
+        if self.alive:  # after close() the native context (and its allocations' stream) is gone
+            self.check(self._lib.eo_dev_free(self._h, ptr))
 
     def copy(self, dst, src, nbytes: int):
         self.check(self._lib.eo_copy(self._h, _ptr(dst), _ptr(src), int(nbytes)))
@@ -178,7 +192,7 @@ class Context:
         self.check(self._lib.eo_host_alloc(self._h, nbytes, C.byref(p)))
         buf = (C.c_char * nbytes).from_address(p.value)
         arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
-        weakref.finalize(buf, self._lib.eo_host_free, self._h, p.value)
+        weakref.finalize(buf, Context._host_free, self._lib, self._finalizer, self._h, p.value)
         return arr
 
     def register(self, host: np.ndarray):

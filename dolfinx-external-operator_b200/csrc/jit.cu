@@ -98,6 +98,8 @@ struct jit_variant {
   cudaKernel_t kernel = nullptr;
   int order = 0, da = 0, db = 0;
   int out_width = 0;  // doubles per point of the primary output
+  int tile = 0;       // staged variant: points per CTA (0: direct variant)
+  size_t smem = 0;    // staged variant: dynamic shared memory per CTA
 };
 }  // namespace
 
@@ -133,13 +135,15 @@ struct jit_tab_sig {
 };
 
 // The translation unit handed to NVRTC for one derivative multi-index (fused: nq > 0 and one jit_tab_sig per operand).
-static std::string jit_program(const eo_jit* m, int order, int da, int db, int nq = 0, const jit_tab_sig* sig = nullptr) {
+// tile > 0: the staged (TMA bulk copy) variant with `tile` points per CTA.
+static std::string jit_program(const eo_jit* m, int order, int da, int db, int nq = 0, const jit_tab_sig* sig = nullptr, int tile = 0) {
   int nin = 0, nst = 0, naux = 0;
   for (int i = 0; i < m->n_operands; ++i) nin += m->operand_size[i];
   for (int i = 0; i < m->n_state; ++i) nst += m->state_size[i];
   for (int i = 0; i < m->n_aux; ++i) naux += m->aux_size[i];
   std::string s;
   if (sig) s += "#define EO_JIT_FUSED 1\n#define EO_JIT_N_TABLES " + std::to_string(m->n_operands) + "\n";
+  if (tile) s += "#define EO_JIT_STAGED 1\n";
   s += "#include \"eo_jit_device.cuh\"\n";
   s += "#line 1 \"model.cu\"\n";
   s += m->source;
@@ -149,6 +153,7 @@ static std::string jit_program(const eo_jit* m, int order, int da, int db, int n
        ", N_AUX = " + std::to_string(m->n_aux) + ";\n";
   s += "  static constexpr int NIN = " + std::to_string(nin) + ", NST = " + std::to_string(nst) +
        ", NOUT = " + std::to_string(m->out_size) + ", NAUX = " + std::to_string(naux) + ";\n";
+  if (tile) s += "  static constexpr int TILE = " + std::to_string(tile) + ";\n";
   s += "  static constexpr int ORDER = " + std::to_string(order) + ", DA = " + std::to_string(da) + ", DB = " + std::to_string(db) + ";\n";
   s += "  static constexpr int op_size(int k) { constexpr int t[] = " + int_list(m->operand_size, m->n_operands) + "; return t[k]; }\n";
   s += "  static constexpr int st_size(int k) { constexpr int t[] = " + int_list(m->state_size, m->n_state) + "; return t[k]; }\n";
@@ -167,6 +172,11 @@ static std::string jit_program(const eo_jit* m, int order, int da, int db, int n
   // occupancy hint: the fused kernels hide gather latency with resident warps (tab_vm_kernel uses 4 CTAs/SM too)
   int min_blocks = sig ? 4 : 1;
   if (const char* e = getenv("EO_JIT_MIN_BLOCKS")) min_blocks = atoi(e) > 0 ? atoi(e) : min_blocks;
+  if (tile) {
+    s += "extern \"C\" __global__ void __launch_bounds__(" + std::to_string(tile) + ") eo_jit_entry(const __grid_constant__ eo_jit_args a) {\n";
+    s += "  eo_jitd::run_staged<eo_jit_spec>(a);\n}\n";
+    return s;
+  }
   s += "extern \"C\" __global__ void __launch_bounds__(256, " + std::to_string(min_blocks) + ") eo_jit_entry(const __grid_constant__ " +
        std::string(sig ? "eo_jit_fused_args" : "eo_jit_args") + " a) {\n";
   s += std::string("  eo_jitd::run<eo_jit_spec, ") + (sig ? "eo_jit_fused_args" : "eo_jit_args") + ">(a);\n}\n";
@@ -188,8 +198,10 @@ static int jit_multi_index(eo_jit* m, const int* derivatives, int& order, int& d
   return EO_OK;
 }
 
-static int jit_compile(eo_jit* m, int order, int da, int db, jit_variant** out, int nq = 0, const jit_tab_sig* sig = nullptr) {
+static int jit_compile(eo_jit* m, int order, int da, int db, jit_variant** out, int nq = 0, const jit_tab_sig* sig = nullptr,
+                       int tile = 0) {
   std::string key = std::to_string(order) + ":" + std::to_string(da) + ":" + std::to_string(db);
+  if (tile) key += ":T" + std::to_string(tile);
   if (sig) {
     key += ":F" + std::to_string(nq);
     for (int i = 0; i < m->n_operands; ++i)
@@ -202,7 +214,7 @@ static int jit_compile(eo_jit* m, int order, int da, int db, jit_variant** out, 
   }
   nvrtc_api* rt = nvrtc();
   if (!rt->h) return jit_fail(m, EO_ERR_UNSUPPORTED, "eo_jit: %s", rt->err.c_str());
-  const std::string prog_text = jit_program(m, order, da, db, nq, sig);
+  const std::string prog_text = jit_program(m, order, da, db, nq, sig, tile);
   nvrtcProgram prog = nullptr;
   const char* hdr_src[3] = {k_hdr_device, k_hdr_dual, k_hdr_tab};
   const char* hdr_name[3] = {"eo_jit_device.cuh", "eo_dual.h", "tab_core.cuh"};
@@ -243,15 +255,51 @@ static int jit_compile(eo_jit* m, int order, int da, int db, jit_variant** out, 
   v.out_width = m->out_size;
   if (order >= 1) v.out_width *= m->operand_size[da];
   if (order >= 2) v.out_width *= m->operand_size[db];
+  v.tile = tile;
+  if (tile) {
+    int doubles = v.out_width + m->out_size;
+    for (int i = 0; i < m->n_operands; ++i) doubles += m->operand_size[i];
+    for (int i = 0; i < m->n_state; ++i) doubles += m->state_size[i];
+    for (int i = 0; i < m->n_aux; ++i) doubles += m->aux_size[i];
+    v.smem = 128 + size_t(tile) * 8 * doubles;
+  }
   if (m->ctx) {
     cudaError_t e = cudaLibraryLoadData(&v.lib, v.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
     if (e != cudaSuccess) return jit_fail(m, EO_ERR_CUDA, "cudaLibraryLoadData: %s", cudaGetErrorString(e));
     e = cudaLibraryGetKernel(&v.kernel, v.lib, "eo_jit_entry");
     if (e != cudaSuccess) return jit_fail(m, EO_ERR_CUDA, "cudaLibraryGetKernel: %s", cudaGetErrorString(e));
+    if (v.smem > 48 * 1024) {
+      e = cudaFuncSetAttribute((const void*)v.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem);
+      if (e != cudaSuccess) return jit_fail(m, EO_ERR_CUDA, "cudaFuncSetAttribute(staged kernel, %zu B): %s", v.smem, cudaGetErrorString(e));
+    }
   }
   auto ins = m->variants.emplace(key, std::move(v));
   *out = &ins.first->second;
   return EO_OK;
+}
+
+// Points per CTA (= threads) of the staged variant for one derivative multi-index: the largest power of two <= 1024
+// whose tile (every per-point array of the call) fits in 32 KB - several CTAs per SM, so that the load, compute and
+// store phases of different CTAs overlap - but no smaller than 32; 0 when even 32 points do not fit in 96 KB.
+static int jit_tile_points(const eo_jit* m, int order, int da, int db) {
+  int doubles = m->out_size * (order >= 1 ? m->operand_size[da] : 1) * (order >= 2 ? m->operand_size[db] : 1) + m->out_size;
+  for (int i = 0; i < m->n_operands; ++i) doubles += m->operand_size[i];
+  for (int i = 0; i < m->n_state; ++i) doubles += m->state_size[i];
+  for (int i = 0; i < m->n_aux; ++i) doubles += m->aux_size[i];
+  for (int t = 1024; t >= 32; t /= 2)
+    if (128 + size_t(t) * 8 * doubles <= (t == 32 ? 96u : 32u) * 1024) return t;
+  return 0;
+}
+
+// Is the staged variant worth it?  Per-thread accesses are strided (0.15-0.68 of the HBM roofline measured) when a
+// point has an odd number (>= 3) of components; scalars are contiguous across a warp and even counts vectorise.
+static bool jit_has_odd_array(const eo_jit* m, int out_width, int order) {
+  auto bad = [](int s) { return s >= 3 && (s % 2) != 0; };
+  bool odd = bad(out_width) || (order >= 1 && bad(m->out_size));
+  for (int i = 0; i < m->n_operands; ++i) odd = odd || bad(m->operand_size[i]);
+  for (int i = 0; i < m->n_state; ++i) odd = odd || bad(m->state_size[i]);
+  for (int i = 0; i < m->n_aux; ++i) odd = odd || bad(m->aux_size[i]);
+  return odd;
 }
 
 extern "C" {
@@ -307,6 +355,21 @@ int eo_jit_compile(eo_jit* m, const int* derivatives, size_t* cubin_bytes) {
   if (rc) return rc;
   jit_variant* v = nullptr;
   rc = jit_compile(m, order, da, db, &v);
+  if (rc) return rc;
+  if (cubin_bytes) *cubin_bytes = v->cubin.size();
+  return EO_OK;
+}
+
+int eo_jit_compile_staged(eo_jit* m, const int* derivatives, int* tile_points, size_t* cubin_bytes) {
+  if (!m) return EO_ERR_INVALID;
+  int order, da, db;
+  int rc = jit_multi_index(m, derivatives, order, da, db);
+  if (rc) return rc;
+  const int tile = jit_tile_points(m, order, da, db);
+  if (tile_points) *tile_points = tile;
+  if (!tile) return jit_fail(m, EO_ERR_UNSUPPORTED, "eo_jit_compile_staged: a 32-point tile of this model does not fit in shared memory");
+  jit_variant* v = nullptr;
+  rc = jit_compile(m, order, da, db, &v, 0, nullptr, tile);
   if (rc) return rc;
   if (cubin_bytes) *cubin_bytes = v->cubin.size();
   return EO_OK;
@@ -373,25 +436,50 @@ int eo_jit_eval(eo_jit* m, const int* derivatives, const double* params, const d
     if (args[i].ptr && (reinterpret_cast<uintptr_t>(args[i].ptr) & 7))
       return jit_fail(m, EO_ERR_INVALID, "eo_jit_eval: argument %d is not 8-byte aligned", i);
 
+  // staged (TMA bulk copy) variant: EO_JIT_STAGED=0 never, =1 whenever it fits, default: when a point of some array
+  // has an odd number of components (per-thread accesses would be strided)
+  jit_variant* vs = nullptr;
+  {
+    const char* pol = getenv("EO_JIT_STAGED");
+    const bool want = pol ? (*pol == '1') : jit_has_odd_array(m, v->out_width, order);
+    const int tile = want ? jit_tile_points(m, order, da, db) : 0;
+    if (tile && n >= tile) {
+      rc = jit_compile(m, order, da, db, &vs, 0, nullptr, tile);
+      if (rc) return rc;
+    }
+  }
+
   eo_jit_args ka;
   memset(&ka, 0, sizeof ka);
   for (int i = 0; i < m->n_params; ++i) ka.prm[i] = params[i];
-  cudaKernel_t kernel = v->kernel;
   auto launch = [&](void** p, int64_t nn, int64_t) -> int {
-    for (int i = 0; i < na; ++i)
+    bool a16 = true;
+    for (int i = 0; i < na; ++i) {
       if (p[i] && (reinterpret_cast<uintptr_t>(p[i]) & (args[i].bpq % 32 == 0 ? 31 : args[i].bpq % 16 == 0 ? 15 : 7)))
         return jit_fail(m, EO_ERR_INVALID, "eo_jit_eval: device argument %d is misaligned for its %zu-byte points", i, args[i].bpq);
-    for (int i = 0; i < m->n_operands; ++i) ka.operand[i] = (const double*)p[i];
-    for (int i = 0; i < m->n_state; ++i) ka.state[i] = (const double*)p[m->n_operands + i];
-    ka.out = (double*)p[i_out];
-    ka.value = (double*)p[i_val];
-    for (int i = 0; i < m->n_aux; ++i) ka.aux[i] = (double*)p[i_aux + i];
-    ka.n = nn;
-    void* kargs[1] = {&ka};
-    const unsigned grid = unsigned((nn + 255) / 256);
-    cudaError_t e = cudaLaunchKernel((const void*)kernel, dim3(grid), dim3(256), kargs, 0, ctx->s_cmp);
-    if (e != cudaSuccess) return jit_fail(m, EO_ERR_CUDA, "eo_jit_eval: launch: %s", cudaGetErrorString(e));
-    ++ctx->launches;
+      a16 = a16 && !(reinterpret_cast<uintptr_t>(p[i]) & 15);
+    }
+    // full tiles through the staged kernel (bulk copies need 16-byte aligned addresses), the rest directly
+    const int64_t n_staged = (vs && a16) ? nn / vs->tile * vs->tile : 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      const int64_t first = pass == 0 ? 0 : n_staged, cnt = pass == 0 ? n_staged : nn - n_staged;
+      if (cnt <= 0) continue;
+      auto at = [&](int i) -> char* { return p[i] ? (char*)p[i] + size_t(first) * args[i].bpq : nullptr; };
+      for (int i = 0; i < m->n_operands; ++i) ka.operand[i] = (const double*)at(i);
+      for (int i = 0; i < m->n_state; ++i) ka.state[i] = (const double*)at(m->n_operands + i);
+      ka.out = (double*)at(i_out);
+      ka.value = (double*)at(i_val);
+      for (int i = 0; i < m->n_aux; ++i) ka.aux[i] = (double*)at(i_aux + i);
+      ka.n = cnt;
+      void* kargs[1] = {&ka};
+      cudaError_t e;
+      if (pass == 0)
+        e = cudaLaunchKernel((const void*)vs->kernel, dim3(unsigned(cnt / vs->tile)), dim3(vs->tile), kargs, vs->smem, ctx->s_cmp);
+      else
+        e = cudaLaunchKernel((const void*)v->kernel, dim3(unsigned((cnt + 255) / 256)), dim3(256), kargs, 0, ctx->s_cmp);
+      if (e != cudaSuccess) return jit_fail(m, EO_ERR_CUDA, "eo_jit_eval: launch: %s", cudaGetErrorString(e));
+      ++ctx->launches;
+    }
     return EO_OK;
   };
   return eo_run_streamed(ctx, args, na, n, launch);

@@ -78,7 +78,7 @@ class Isihara(_ModelBase):
         c.check(c.lib.eo_isihara_set_correction(self._h, self.H_flat.ctypes.data_as(C.POINTER(C.c_double))))
 
     def close(self):
-        if self._h is not None:
+        if self._h is not None and self.ctx.alive:
             self.ctx.lib.eo_isihara_destroy(self._h)
             self._h = None
 

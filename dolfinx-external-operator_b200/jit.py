@@ -106,7 +106,7 @@ class JitModel:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and (self.ctx is None or self.ctx.alive):
             try:
                 self.lib.eo_jit_destroy(h)
             except Exception:

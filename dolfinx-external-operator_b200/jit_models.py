@@ -67,6 +67,23 @@ __device__ void vm3d_sigma(const T* deps, const double* st, const double* prm, T
 }
 """
 
+# Compressible neo-Hookean energy W(F) = mu/2 (tr(F^T F) - 3) - mu ln J + lambda/2 (ln J)^2, F row-major 3x3.
+# Only the ENERGY is written down: the first Piola-Kirchhoff stress P = dW/dF is the (1,) derivative and the
+# tangent dP/dF = d2W/dF2 the (2,) derivative (nested dual numbers) - the "torch.func.grad + jacfwd" recipe of
+# doc/demo/demo_hyperelasticity.py:429-456 for a closed-form energy.  prm = [mu, lambda].  Arrays of 9 and 81 doubles
+# per point have odd component counts: this model runs through the staged (TMA bulk copy) variant.
+NEO_HOOKEAN_3D = r"""
+template <class T>
+__device__ void neo_hookean_W(const T* F, const double*, const double* prm, T* W, T*) {
+  const double mu = prm[0], lam = prm[1];
+  T I1 = F[0] * F[0];
+  for (int i = 1; i < 9; ++i) I1 = I1 + F[i] * F[i];
+  const T J = F[0] * (F[4] * F[8] - F[5] * F[7]) - F[1] * (F[3] * F[8] - F[5] * F[6]) + F[2] * (F[3] * F[7] - F[4] * F[6]);
+  const T lnJ = log(J);
+  W[0] = 0.5 * mu * (I1 - 3.0) - mu * lnJ + 0.5 * lam * lnJ * lnJ;
+}
+"""
+
 # nonlinear heat flux q(T, sigma) = -k(T) sigma with k = 1 / (A + B T)
 # (doc/demo/demo_nonlinear_heat_equation_part2.py:215-261; derivatives :228-261 come from AD here).
 HEAT_FLUX = r"""
@@ -112,6 +129,13 @@ def von_mises_3d(E=70e3, nu=0.3, E_tangent=None, sigma_0=250.0, **kw):
     kw.setdefault("returns", ("out", "value", "aux0"))
     return JitModel(VON_MISES_3D, "vm3d_sigma", [(6,)], (6,), state_shapes=[(6,), ()], aux_shapes=[()],
                     params=[lmbda, mu, H, sigma_0], **kw)
+
+
+def neo_hookean_3d(mu=1.0, lmbda=2.0, **kw):
+    """Hyperelastic model from its energy alone: `(0,)` -> W, `(1,)` -> P = dW/dF [qp][9], `(2,)` -> dP/dF [qp][9][9]."""
+    from .jit import JitModel
+
+    return JitModel(NEO_HOOKEAN_3D, "neo_hookean_W", [(3, 3)], (), params=[mu, lmbda], **kw)
 
 
 def heat_flux(A=1.0, B=1.0, **kw):

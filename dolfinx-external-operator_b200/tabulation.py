@@ -74,7 +74,7 @@ class Tabulator:
                    n_dofs=V.dofmap.index_map.size_local + V.dofmap.index_map.num_ghosts, coefficient=coefficient, ctx=ctx)
 
     def close(self):
-        if self._h is not None:
+        if self._h is not None and self.ctx.alive:
             self.ctx.lib.eo_tab_destroy(self._h)
             self._h = None
 
@@ -273,7 +273,7 @@ class GeneralTabulator(Tabulator):
                    n_dofs=V.dofmap.index_map.size_local + V.dofmap.index_map.num_ghosts, coefficient=coefficient, ctx=ctx)
 
     def close(self):
-        if self._h is not None:
+        if self._h is not None and self.ctx.alive:
             self.ctx.lib.eo_gtab_destroy(self._h)
             self._h = None
 

@@ -367,6 +367,11 @@ int eo_jit_create(eo_ctx* ctx, const eo_jit_desc* desc, eo_jit** out);
 int eo_jit_destroy(eo_jit* m);
 /* Compile (if not cached) the kernel for `derivatives` (one int per operand, sum <= 2; NULL = value). */
 int eo_jit_compile(eo_jit* m, const int* derivatives, size_t* cubin_bytes);
+/* The staged variant of the kernel for `derivatives`: one CTA per tile of `*tile_points` points, every per-point
+ * array of the tile moved by 1-D TMA bulk copies (cp.async.bulk + mbarrier) through shared memory - coalesced for
+ * any number of components per point.  eo_jit_eval uses it automatically when some array has an odd component count
+ * (EO_JIT_STAGED=0/1 forces never/always); this entry point only compiles it (works without a GPU). */
+int eo_jit_compile_staged(eo_jit* m, const int* derivatives, int* tile_points, size_t* cubin_bytes);
 /* Version of the NVRTC that was found (major * 1000 + minor * 10, e.g. 12090), or EO_ERR_UNSUPPORTED.  The
  * toolkit's /usr/local/cuda/lib64/libnvrtc.so.12 is preferred (EO_NVRTC_LIB overrides); NVRTC older than 12.9
  * cannot assemble 256-bit global accesses, models compiled with it use 128-bit ones. */

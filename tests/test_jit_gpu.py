@@ -210,3 +210,31 @@ def test_jit_von_mises_3d_extension(ctx):
     _close(Ct, rC, 1e-11)
     _close(sig, rs, 1e-12)
     _close(dp, rdp, 1e-12)
+
+
+def test_jit_staged_variant_odd_component_counts(ctx):
+    """Arrays with 9 and 81 doubles per point go through the staged kernel (TMA bulk copies + mbarrier): full tiles
+    staged, the tail direct, host arrays through the chunk pipeline - all against the closed forms."""
+    from test_jit_cpu import neo_hookean_batch, neo_hookean_reference
+
+    n = 70_003  # not a multiple of any tile size
+    F = neo_hookean_batch(n, 7)
+    W, P, A = neo_hookean_reference(F)
+    m = jm.neo_hookean_3d(ctx=ctx)
+    l0 = ctx.launch_count
+    _close(m((1,))(F.reshape(-1, 1, 3, 3)), P, 1e-12)
+    assert ctx.launch_count - l0 == 2  # staged tiles + direct tail
+    _close(m((2,))(F), A, 1e-11)
+    _close(m((0,))(F), W, 1e-13)
+    ctx.set_chunk(10_000)  # chunks whose sizes are no multiples of the tile
+    try:
+        _close(m((1,))(F), P, 1e-12)
+    finally:
+        ctx.set_chunk(1 << 20)
+    d_F = ctx.to_device(F.reshape(-1))
+    d_P = ctx.empty((9 * n,))
+    m.eval_device((1,), [d_F], d_P)
+    ctx.sync()
+    _close(d_P.to_host(), P, 1e-12)
+    few = m((1,))(F[:17])  # fewer points than a tile: direct kernel only
+    _close(few, P[:17], 1e-12)
