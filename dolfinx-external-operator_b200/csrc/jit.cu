@@ -10,6 +10,7 @@
 // dependency on it; the CUBIN is loaded with cudaLibraryLoadData and launched with cudaLaunchKernel on the
 // context's compute stream, host-side arguments go through the same chunked pipeline as every other entry point.
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <map>
 #include <mutex>
@@ -215,10 +216,45 @@ static int jit_compile(eo_jit* m, int order, int da, int db, jit_variant** out, 
   nvrtc_api* rt = nvrtc();
   if (!rt->h) return jit_fail(m, EO_ERR_UNSUPPORTED, "eo_jit: %s", rt->err.c_str());
   const std::string prog_text = jit_program(m, order, da, db, nq, sig, tile);
+  // on-disk CUBIN cache (EO_JIT_CACHE_DIR): keyed by the full translation unit, both headers, the options and the
+  // NVRTC version, so a process restart does not pay the 0.1-3 s compilation again
+  std::string cache_path;
+  if (const char* dir = getenv("EO_JIT_CACHE_DIR")) {
+    unsigned long long h = 1469598103934665603ull;
+    auto mix = [&](const char* p, size_t n) {
+      for (size_t i = 0; i < n; ++i) h = (h ^ (unsigned char)p[i]) * 1099511628211ull;
+    };
+    mix(prog_text.data(), prog_text.size());
+    mix(k_hdr_device, strlen(k_hdr_device));
+    mix(k_hdr_dual, strlen(k_hdr_dual));
+    mix(k_hdr_tab, strlen(k_hdr_tab));
+    const int sig_opts[3] = {m->fmad, rt->major, rt->minor};
+    mix(reinterpret_cast<const char*>(sig_opts), sizeof sig_opts);
+    char name[64];
+    snprintf(name, sizeof name, "/eo_jit_%016llx.cubin", h);
+    cache_path = std::string(dir) + name;
+  }
   nvrtcProgram prog = nullptr;
   const char* hdr_src[3] = {k_hdr_device, k_hdr_dual, k_hdr_tab};
   const char* hdr_name[3] = {"eo_jit_device.cuh", "eo_dual.h", "tab_core.cuh"};
-  int rc = rt->CreateProgram(&prog, prog_text.c_str(), "eo_jit_entry.cu", 3, hdr_src, hdr_name);
+  jit_variant v;
+  bool cached = false;
+  if (!cache_path.empty()) {
+    if (FILE* f = fopen(cache_path.c_str(), "rb")) {
+      fseek(f, 0, SEEK_END);
+      const long sz = ftell(f);
+      fseek(f, 0, SEEK_SET);
+      if (sz > 64) {
+        v.cubin.assign(size_t(sz), '\0');
+        cached = fread(&v.cubin[0], 1, size_t(sz), f) == size_t(sz) && v.cubin.compare(0, 4, "\x7f" "ELF") == 0;
+      }
+      fclose(f);
+      if (cached) m->log = "loaded from " + cache_path;
+    }
+  }
+  int rc = 0;
+  if (!cached) {
+  rc = rt->CreateProgram(&prog, prog_text.c_str(), "eo_jit_entry.cu", 3, hdr_src, hdr_name);
   if (rc) return jit_fail(m, EO_ERR_CUDA, "nvrtcCreateProgram: %s", rt->GetErrorString(rc));
   // 256-bit ld/st.global.v4.f64 need the CUDA >= 12.9 ptxas; older NVRTCs get 128-bit accesses
   const bool v4 = rt->major > 12 || (rt->major == 12 && rt->minor >= 9);
@@ -235,12 +271,20 @@ static int jit_compile(eo_jit* m, int order, int da, int db, jit_variant** out, 
     return jit_fail(m, EO_ERR_INVALID, "eo_jit: compilation of '%s' (derivatives %s) failed: %s; see eo_jit_log", m->entry.c_str(),
                     key.c_str(), rt->GetErrorString(rc));
   }
-  jit_variant v;
   size_t cs = 0;
   rt->GetCUBINSize(prog, &cs);
   v.cubin.assign(cs, '\0');
   rt->GetCUBIN(prog, &v.cubin[0]);
   rt->DestroyProgram(&prog);
+  if (!cache_path.empty()) {  // write-then-rename: concurrent ranks compile the same model at start-up
+    const std::string tmp = cache_path + "." + std::to_string((long)getpid());
+    if (FILE* f = fopen(tmp.c_str(), "wb")) {
+      const bool ok = fwrite(v.cubin.data(), 1, v.cubin.size(), f) == v.cubin.size();
+      fclose(f);
+      if (!ok || rename(tmp.c_str(), cache_path.c_str()) != 0) remove(tmp.c_str());
+    }
+  }
+  }  // !cached
   if (const char* dump = getenv("EO_JIT_DUMP_DIR")) {  // for cuobjdump -sass / -res-usage
     std::string name = key;
     for (char& ch : name)

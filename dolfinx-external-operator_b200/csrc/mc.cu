@@ -318,6 +318,8 @@ __global__ void __launch_bounds__(MC_THREADS, 1) mc_kernel(const mc_consts k, co
       if (lane == 0) atomicAdd(&s_inflight, npl - 1);  // the points enter before this T stage leaves
     } else {
       // ---------------------------------------------------------------- stages S0 / U0 / U
+      bool fin = false, nonconv = false, nonfin = false;
+      int bin = 0;
       if (lane < take) {
         const int slot = mc_q_read(s_ring[stage], qpos + lane);
         const mc_slot sl{s_slots + slot, MC_NSLOTS};
@@ -332,15 +334,29 @@ __global__ void __launch_bounds__(MC_THREADS, 1) mc_kernel(const mc_consts k, co
           mc_store_aux(P, i, it, sl[MC_F_YIELD], nr, dl);
           max_res = fmax(max_res, nr);
           max_it = max(max_it, it);
-          atomicAdd(&s_hist[min(it, EO_NITER_BINS - 1)], 1u);
-          atomicAdd(&s_plastic, 1u);
-          atomicAdd(&s_inflight, -1);
-          if (it >= k.nitermax) atomicAdd(&s_nonconv, 1u);
-          if (!(isfinite(sig[0]) && isfinite(sig[1]) && isfinite(sig[2]) && isfinite(sig[3])))
-            atomicAdd(&s_nonfinite, 1u);
+          fin = true;
+          bin = min(it, EO_NITER_BINS - 1);
+          nonconv = it >= k.nitermax;
+          nonfin = !(isfinite(sig[0]) && isfinite(sig[1]) && isfinite(sig[2]) && isfinite(sig[3]));
           slotA = slot;
         } else {
           slotB = slot;
+        }
+      }
+      // statistics of the points that left the loop: warp-aggregated (one shared-memory atomic per counter and per
+      // distinct iteration count instead of one per lane)
+      const unsigned fm = __ballot_sync(0xffffffffu, fin);
+      if (fm) {
+        const unsigned ncm = __ballot_sync(0xffffffffu, nonconv), nfm = __ballot_sync(0xffffffffu, nonfin);
+        if (fin) {
+          const unsigned grp = __match_any_sync(fm, bin);
+          if (lane == __ffs(grp) - 1) atomicAdd(&s_hist[bin], (unsigned)__popc(grp));
+        }
+        if (lane == 0) {
+          atomicAdd(&s_plastic, (unsigned)__popc(fm));
+          atomicAdd(&s_inflight, -__popc(fm));
+          if (ncm) atomicAdd(&s_nonconv, (unsigned)__popc(ncm));
+          if (nfm) atomicAdd(&s_nonfinite, (unsigned)__popc(nfm));
         }
       }
     }

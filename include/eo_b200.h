@@ -348,7 +348,9 @@ int eo_isihara_eval(eo_isihara* m, const double* F, double* dP, double* P, int64
  * concatenated (read only, not differentiated), prm = n_params doubles, y = out_size results, aux = all
  * auxiliary outputs concatenated (e.g. the plastic multiplier increment of demo_vm:352).  T is double for the
  * value and eo::dual<...> (include/eo_dual.h) for derivatives.  One NVRTC compilation (sm_100a) per derivative
- * multi-index, cached in the handle.  `ctx` may be NULL for a compile-only handle (works without a GPU). */
+ * multi-index, cached in the handle - and on disk when EO_JIT_CACHE_DIR names a directory (CUBIN files keyed by
+ * the translation unit, the embedded headers, the options and the NVRTC version).  `ctx` may be NULL for a
+ * compile-only handle (works without a GPU). */
 #define EO_JIT_MAX_ARGS 8
 #define EO_JIT_MAX_PARAMS 32
 typedef struct eo_jit_desc {

@@ -62,6 +62,22 @@ def test_fused_tabulation_variants_compile_without_gpu():
     assert h.lib.eo_jit_compile_tabulated(h._h, ints(0, 0), 3, ints(2, 2), ints(1, 2), ints(6, 6), ints(0, 2), C.byref(nbytes)) == -1
 
 
+def test_cubin_cache_on_disk(tmp_path):
+    """EO_JIT_CACHE_DIR: the second process-lifetime of a model loads its CUBIN instead of compiling it."""
+    import subprocess
+    import sys
+
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from dolfinx_external_operator_b200 import jit_models as jm\n"
+            "m = jm.von_mises(compile_only=True); n = m.compile((1,)); print(n, m.log[:11])\n") % str(__import__('conftest').ROOT)
+    env = dict(__import__('os').environ, EO_JIT_CACHE_DIR=str(tmp_path))
+    a = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout.split()
+    b = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout.split()
+    assert int(a[0]) == int(b[0]) > 1000
+    assert a[1:] != ["loaded", "from"] and b[1:] == ["loaded", "from"]
+    assert len(list(tmp_path.glob("eo_jit_*.cubin"))) == 1
+
+
 def test_compile_error_carries_the_nvrtc_log():
     bad = "template <class T> __device__ void f(const T* x, const double*, const double*, T* y, T*) { y[0] = x[0] +; }"
     m = JitModel(bad, "f", [()], (), compile_only=True)
