@@ -148,6 +148,7 @@ PROTOTYPES = {
     "eo_jit_compile": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     "eo_jit_nvrtc_version": (C.c_int, []),
     "eo_jit_compile_staged": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
+    "eo_jit_compile_ppt": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     "eo_jit_cubin": (C.c_int, [_vp, C.POINTER(C.c_int), _vp, C.c_size_t]),
     "eo_jit_log": (C.c_char_p, [_vp]),
     "eo_jit_last_error": (C.c_char_p, [_vp]),

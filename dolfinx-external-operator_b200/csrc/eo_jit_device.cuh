@@ -88,21 +88,10 @@ __device__ __forceinline__ void sts(unsigned a, double x, double y) {
 __device__ __forceinline__ void sts(unsigned a, double x) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(x) : "memory"); }
 #endif
 
-// S contiguous doubles of one point; the base pointer is 32-byte aligned (checked on the host)
+// S contiguous doubles of one point in GLOBAL memory; the base pointer is aligned for the widest access used
 template <int S>
-__device__ __forceinline__ void load_point(const double* __restrict__ base, long long i, double* r) {
+__device__ __forceinline__ void gload_point(const double* __restrict__ base, long long i, double* r) {
   const double* p = base + i * S;
-#ifdef EO_JIT_STAGED
-  const unsigned a = (unsigned)__cvta_generic_to_shared(p);
-  if constexpr (S % 2 == 0) {
-#pragma unroll
-    for (int k = 0; k < S; k += 2) lds(a + 8 * k, r[k], r[k + 1]);
-  } else {
-#pragma unroll
-    for (int k = 0; k < S; ++k) lds(a + 8 * k, r[k]);
-  }
-  return;
-#endif
   if constexpr (S % 4 == 0 && EO_JIT_MAX_VEC >= 4) {
 #pragma unroll
     for (int k = 0; k < S; k += 4) ld(p + k, r[k], r[k + 1], r[k + 2], r[k + 3]);
@@ -115,19 +104,8 @@ __device__ __forceinline__ void load_point(const double* __restrict__ base, long
   }
 }
 template <int S>
-__device__ __forceinline__ void store_point(double* __restrict__ base, long long i, const double* r) {
+__device__ __forceinline__ void gstore_point(double* __restrict__ base, long long i, const double* r) {
   double* p = base + i * S;
-#ifdef EO_JIT_STAGED
-  const unsigned a = (unsigned)__cvta_generic_to_shared(p);
-  if constexpr (S % 2 == 0) {
-#pragma unroll
-    for (int k = 0; k < S; k += 2) sts(a + 8 * k, r[k], r[k + 1]);
-  } else {
-#pragma unroll
-    for (int k = 0; k < S; ++k) sts(a + 8 * k, r[k]);
-  }
-  return;
-#endif
   if constexpr (S % 4 == 0 && EO_JIT_MAX_VEC >= 4) {
 #pragma unroll
     for (int k = 0; k < S; k += 4) st(p + k, r[k], r[k + 1], r[k + 2], r[k + 3]);
@@ -138,6 +116,46 @@ __device__ __forceinline__ void store_point(double* __restrict__ base, long long
 #pragma unroll
     for (int k = 0; k < S; ++k) st(p + k, r[k]);
   }
+}
+
+// Where the per-point code (run0/1/2) finds a point's components: global memory (direct variant), the CTA's
+// shared-memory tile (EO_JIT_STAGED) or the thread's own registers (EO_JIT_PPT: several points per thread, fetched
+// together with wide accesses by run_ppt).
+template <int S>
+__device__ __forceinline__ void load_point(const double* __restrict__ base, long long i, double* r) {
+#if defined(EO_JIT_STAGED)
+  const unsigned a = (unsigned)__cvta_generic_to_shared(base + i * S);
+  if constexpr (S % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k < S; k += 2) lds(a + 8 * k, r[k], r[k + 1]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < S; ++k) lds(a + 8 * k, r[k]);
+  }
+#elif defined(EO_JIT_PPT)
+#pragma unroll
+  for (int k = 0; k < S; ++k) r[k] = base[i * S + k];
+#else
+  gload_point<S>(base, i, r);
+#endif
+}
+template <int S>
+__device__ __forceinline__ void store_point(double* __restrict__ base, long long i, const double* r) {
+#if defined(EO_JIT_STAGED)
+  const unsigned a = (unsigned)__cvta_generic_to_shared(base + i * S);
+  if constexpr (S % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k < S; k += 2) sts(a + 8 * k, r[k], r[k + 1]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < S; ++k) sts(a + 8 * k, r[k]);
+  }
+#elif defined(EO_JIT_PPT)
+#pragma unroll
+  for (int k = 0; k < S; ++k) base[i * S + k] = r[k];
+#else
+  gstore_point<S>(base, i, r);
+#endif
 }
 
 // compile-time table helpers over the Spec's static arrays
@@ -189,6 +207,31 @@ struct loader<Spec, NK, NK> {
 };
 
 constexpr int at_least_1(int n) { return n > 0 ? n : 1; }
+
+#ifdef EO_JIT_PPT
+// wide global accesses of PPT consecutive points per array (run_ppt)
+template <class Spec, int K, int NK>
+struct ppt_io {
+  static __device__ __forceinline__ void load_operands(const eo_jit_args& a, const eo_jit_args& b, long long g) {
+    gload_point<Spec::PPT * Spec::op_size(K)>(a.operand[K], g, const_cast<double*>(b.operand[K]));
+    ppt_io<Spec, K + 1, NK>::load_operands(a, b, g);
+  }
+  static __device__ __forceinline__ void load_states(const eo_jit_args& a, const eo_jit_args& b, long long g) {
+    gload_point<Spec::PPT * Spec::st_size(K)>(a.state[K], g, const_cast<double*>(b.state[K]));
+    ppt_io<Spec, K + 1, NK>::load_states(a, b, g);
+  }
+  static __device__ __forceinline__ void store_aux(const eo_jit_args& a, const eo_jit_args& b, long long g) {
+    if (a.aux[K]) gstore_point<Spec::PPT * Spec::aux_size(K)>(a.aux[K], g, b.aux[K]);
+    ppt_io<Spec, K + 1, NK>::store_aux(a, b, g);
+  }
+};
+template <class Spec, int NK>
+struct ppt_io<Spec, NK, NK> {
+  static __device__ __forceinline__ void load_operands(const eo_jit_args&, const eo_jit_args&, long long) {}
+  static __device__ __forceinline__ void load_states(const eo_jit_args&, const eo_jit_args&, long long) {}
+  static __device__ __forceinline__ void store_aux(const eo_jit_args&, const eo_jit_args&, long long) {}
+};
+#endif
 
 // operands of point i: streamed from HBM ...
 template <class Spec>
@@ -337,6 +380,61 @@ __device__ __forceinline__ void run(const ARGS& a) {
   else
     run2<Spec, ARGS>(a, i);
 }
+
+#ifdef EO_JIT_PPT
+// ------------------------------------------------------------------------------------------------------------
+// Several points per thread, for models with very few bytes per point (scalar fields): a thread fetches PPT
+// consecutive points of every array with one wide access each (more bytes in flight per thread - a scalar model at one
+// point per thread reaches only 0.77 of the HBM roofline), evaluates them one after the other out of registers and
+// writes the PPT results back the same way.  a.n is a multiple of PPT (the host sends the remainder to the direct kernel).
+// ------------------------------------------------------------------------------------------------------------
+template <class Spec>
+__device__ __forceinline__ void run_ppt(const eo_jit_args& a) {
+  constexpr int PPT = Spec::PPT;
+  constexpr int OUTW = Spec::ORDER == 0 ? Spec::NOUT
+                                        : (Spec::ORDER == 1 ? Spec::NOUT * Spec::op_size(Spec::DA)
+                                                            : Spec::NOUT * Spec::op_size(Spec::DA) * Spec::op_size(Spec::DB));
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g * PPT >= a.n) return;
+  double in[PPT * at_least_1(Spec::NIN)], st_[PPT * at_least_1(Spec::NST)], out[PPT * OUTW], val[PPT * Spec::NOUT],
+      aux[PPT * at_least_1(Spec::NAUX)];
+  eo_jit_args b = a;
+  int off = 0;
+#pragma unroll
+  for (int k = 0; k < Spec::N_OPERANDS; ++k) {
+    b.operand[k] = in + off;
+    off += PPT * Spec::op_size(k);
+  }
+  off = 0;
+#pragma unroll
+  for (int k = 0; k < Spec::N_STATE; ++k) {
+    b.state[k] = st_ + off;
+    off += PPT * Spec::st_size(k);
+  }
+  b.out = out;
+  b.value = val;  // always evaluated into registers; written back only when the caller asked for it
+  off = 0;
+#pragma unroll
+  for (int k = 0; k < Spec::N_AUX; ++k) {
+    b.aux[k] = aux + off;
+    off += PPT * Spec::aux_size(k);
+  }
+  ppt_io<Spec, 0, Spec::N_OPERANDS>::load_operands(a, b, g);
+  ppt_io<Spec, 0, Spec::N_STATE>::load_states(a, b, g);
+#pragma unroll
+  for (int p = 0; p < PPT; ++p) {
+    if constexpr (Spec::ORDER == 0)
+      run0<Spec, eo_jit_args>(b, p);
+    else if constexpr (Spec::ORDER == 1)
+      run1<Spec, eo_jit_args>(b, p);
+    else
+      run2<Spec, eo_jit_args>(b, p);
+  }
+  gstore_point<PPT * OUTW>(a.out, g, out);
+  if (a.value) gstore_point<PPT * Spec::NOUT>(a.value, g, val);
+  ppt_io<Spec, 0, Spec::N_AUX>::store_aux(a, b, g);
+}
+#endif
 
 #ifdef EO_JIT_STAGED
 // ------------------------------------------------------------------------------------------------------------

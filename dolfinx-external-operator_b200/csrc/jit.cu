@@ -100,6 +100,7 @@ struct jit_variant {
   int order = 0, da = 0, db = 0;
   int out_width = 0;  // doubles per point of the primary output
   int tile = 0;       // staged variant: points per CTA (0: direct variant)
+  int ppt = 0;        // several-points-per-thread variant: points per thread
   size_t smem = 0;    // staged variant: dynamic shared memory per CTA
 };
 }  // namespace
@@ -137,7 +138,9 @@ struct jit_tab_sig {
 
 // The translation unit handed to NVRTC for one derivative multi-index (fused: nq > 0 and one jit_tab_sig per operand).
 // tile > 0: the staged (TMA bulk copy) variant with `tile` points per CTA.
-static std::string jit_program(const eo_jit* m, int order, int da, int db, int nq = 0, const jit_tab_sig* sig = nullptr, int tile = 0) {
+// ppt > 1: the several-points-per-thread variant (scalar-sized models).
+static std::string jit_program(const eo_jit* m, int order, int da, int db, int nq = 0, const jit_tab_sig* sig = nullptr, int tile = 0,
+                               int ppt = 0) {
   int nin = 0, nst = 0, naux = 0;
   for (int i = 0; i < m->n_operands; ++i) nin += m->operand_size[i];
   for (int i = 0; i < m->n_state; ++i) nst += m->state_size[i];
@@ -145,6 +148,7 @@ static std::string jit_program(const eo_jit* m, int order, int da, int db, int n
   std::string s;
   if (sig) s += "#define EO_JIT_FUSED 1\n#define EO_JIT_N_TABLES " + std::to_string(m->n_operands) + "\n";
   if (tile) s += "#define EO_JIT_STAGED 1\n";
+  if (ppt > 1) s += "#define EO_JIT_PPT 1\n";
   s += "#include \"eo_jit_device.cuh\"\n";
   s += "#line 1 \"model.cu\"\n";
   s += m->source;
@@ -155,6 +159,7 @@ static std::string jit_program(const eo_jit* m, int order, int da, int db, int n
   s += "  static constexpr int NIN = " + std::to_string(nin) + ", NST = " + std::to_string(nst) +
        ", NOUT = " + std::to_string(m->out_size) + ", NAUX = " + std::to_string(naux) + ";\n";
   if (tile) s += "  static constexpr int TILE = " + std::to_string(tile) + ";\n";
+  if (ppt > 1) s += "  static constexpr int PPT = " + std::to_string(ppt) + ";\n";
   s += "  static constexpr int ORDER = " + std::to_string(order) + ", DA = " + std::to_string(da) + ", DB = " + std::to_string(db) + ";\n";
   s += "  static constexpr int op_size(int k) { constexpr int t[] = " + int_list(m->operand_size, m->n_operands) + "; return t[k]; }\n";
   s += "  static constexpr int st_size(int k) { constexpr int t[] = " + int_list(m->state_size, m->n_state) + "; return t[k]; }\n";
@@ -176,6 +181,11 @@ static std::string jit_program(const eo_jit* m, int order, int da, int db, int n
   if (tile) {
     s += "extern \"C\" __global__ void __launch_bounds__(" + std::to_string(tile) + ") eo_jit_entry(const __grid_constant__ eo_jit_args a) {\n";
     s += "  eo_jitd::run_staged<eo_jit_spec>(a);\n}\n";
+    return s;
+  }
+  if (ppt > 1) {
+    s += "extern \"C\" __global__ void __launch_bounds__(256) eo_jit_entry(const __grid_constant__ eo_jit_args a) {\n";
+    s += "  eo_jitd::run_ppt<eo_jit_spec>(a);\n}\n";
     return s;
   }
   s += "extern \"C\" __global__ void __launch_bounds__(256, " + std::to_string(min_blocks) + ") eo_jit_entry(const __grid_constant__ " +
@@ -200,9 +210,10 @@ static int jit_multi_index(eo_jit* m, const int* derivatives, int& order, int& d
 }
 
 static int jit_compile(eo_jit* m, int order, int da, int db, jit_variant** out, int nq = 0, const jit_tab_sig* sig = nullptr,
-                       int tile = 0) {
+                       int tile = 0, int ppt = 0) {
   std::string key = std::to_string(order) + ":" + std::to_string(da) + ":" + std::to_string(db);
   if (tile) key += ":T" + std::to_string(tile);
+  if (ppt > 1) key += ":P" + std::to_string(ppt);
   if (sig) {
     key += ":F" + std::to_string(nq);
     for (int i = 0; i < m->n_operands; ++i)
@@ -215,7 +226,7 @@ static int jit_compile(eo_jit* m, int order, int da, int db, jit_variant** out, 
   }
   nvrtc_api* rt = nvrtc();
   if (!rt->h) return jit_fail(m, EO_ERR_UNSUPPORTED, "eo_jit: %s", rt->err.c_str());
-  const std::string prog_text = jit_program(m, order, da, db, nq, sig, tile);
+  const std::string prog_text = jit_program(m, order, da, db, nq, sig, tile, ppt);
   // on-disk CUBIN cache (EO_JIT_CACHE_DIR): keyed by the full translation unit, both headers, the options and the
   // NVRTC version, so a process restart does not pay the 0.1-3 s compilation again
   std::string cache_path;
@@ -300,6 +311,7 @@ static int jit_compile(eo_jit* m, int order, int da, int db, jit_variant** out, 
   if (order >= 1) v.out_width *= m->operand_size[da];
   if (order >= 2) v.out_width *= m->operand_size[db];
   v.tile = tile;
+  v.ppt = ppt;
   if (tile) {
     int doubles = v.out_width + m->out_size;
     for (int i = 0; i < m->n_operands; ++i) doubles += m->operand_size[i];
@@ -333,6 +345,17 @@ static int jit_tile_points(const eo_jit* m, int order, int da, int db) {
   for (int t = 1024; t >= 32; t /= 2)
     if (128 + size_t(t) * 8 * doubles <= (t == 32 ? 96u : 32u) * 1024) return t;
   return 0;
+}
+
+// Points per thread for scalar-sized models (<= 4 doubles read, <= 8 written per point): >= 32 bytes of loads per thread.
+static int jit_points_per_thread(const eo_jit* m, int out_width) {
+  int in = 0;
+  for (int i = 0; i < m->n_operands; ++i) in += m->operand_size[i];
+  for (int i = 0; i < m->n_state; ++i) in += m->state_size[i];
+  int aux = 0;
+  for (int i = 0; i < m->n_aux; ++i) aux += m->aux_size[i];
+  if (in > 4 || out_width + m->out_size + aux > 8) return 1;
+  return in == 1 ? 4 : 2;
 }
 
 // Is the staged variant worth it?  Per-thread accesses are strided (0.15-0.68 of the HBM roofline measured) when a
@@ -419,6 +442,22 @@ int eo_jit_compile_staged(eo_jit* m, const int* derivatives, int* tile_points, s
   return EO_OK;
 }
 
+int eo_jit_compile_ppt(eo_jit* m, const int* derivatives, int* points_per_thread, size_t* cubin_bytes) {
+  if (!m) return EO_ERR_INVALID;
+  int order, da, db;
+  int rc = jit_multi_index(m, derivatives, order, da, db);
+  if (rc) return rc;
+  const int w = m->out_size * (order >= 1 ? m->operand_size[da] : 1) * (order >= 2 ? m->operand_size[db] : 1);
+  const int ppt = jit_points_per_thread(m, w);
+  if (points_per_thread) *points_per_thread = ppt;
+  if (ppt <= 1) return jit_fail(m, EO_ERR_UNSUPPORTED, "eo_jit_compile_ppt: this model is not scalar-sized (one point per thread is used)");
+  jit_variant* v = nullptr;
+  rc = jit_compile(m, order, da, db, &v, 0, nullptr, 0, ppt);
+  if (rc) return rc;
+  if (cubin_bytes) *cubin_bytes = v->cubin.size();
+  return EO_OK;
+}
+
 int eo_jit_cubin(eo_jit* m, const int* derivatives, void* buf, size_t buf_bytes) {
   if (!m) return EO_ERR_INVALID;
   int order, da, db;
@@ -491,6 +530,12 @@ int eo_jit_eval(eo_jit* m, const int* derivatives, const double* params, const d
       rc = jit_compile(m, order, da, db, &vs, 0, nullptr, tile);
       if (rc) return rc;
     }
+    const char* pp = getenv("EO_JIT_PPT");
+    const int ppt = (vs || (pp && *pp == '0')) ? 1 : jit_points_per_thread(m, v->out_width);
+    if (ppt > 1 && n >= 1024) {  // bulk variant for scalar-sized models: several points per thread
+      rc = jit_compile(m, order, da, db, &vs, 0, nullptr, 0, ppt);
+      if (rc) return rc;
+    }
   }
 
   eo_jit_args ka;
@@ -503,8 +548,12 @@ int eo_jit_eval(eo_jit* m, const int* derivatives, const double* params, const d
         return jit_fail(m, EO_ERR_INVALID, "eo_jit_eval: device argument %d is misaligned for its %zu-byte points", i, args[i].bpq);
       a16 = a16 && !(reinterpret_cast<uintptr_t>(p[i]) & 15);
     }
-    // full tiles through the staged kernel (bulk copies need 16-byte aligned addresses), the rest directly
-    const int64_t n_staged = (vs && a16) ? nn / vs->tile * vs->tile : 0;
+    // full tiles through the staged kernel (bulk copies need 16-byte aligned addresses) or full groups through the
+    // points-per-thread kernel (32-byte aligned wide accesses), the rest directly
+    bool a32 = true;
+    for (int i = 0; i < na; ++i) a32 = a32 && !(reinterpret_cast<uintptr_t>(p[i]) & 31);
+    const int64_t unit = vs ? (vs->tile ? vs->tile : vs->ppt) : 1;
+    const int64_t n_staged = (vs && (vs->tile ? a16 : a32)) ? nn / unit * unit : 0;
     for (int pass = 0; pass < 2; ++pass) {
       const int64_t first = pass == 0 ? 0 : n_staged, cnt = pass == 0 ? n_staged : nn - n_staged;
       if (cnt <= 0) continue;
@@ -517,8 +566,10 @@ int eo_jit_eval(eo_jit* m, const int* derivatives, const double* params, const d
       ka.n = cnt;
       void* kargs[1] = {&ka};
       cudaError_t e;
-      if (pass == 0)
+      if (pass == 0 && vs->tile)
         e = cudaLaunchKernel((const void*)vs->kernel, dim3(unsigned(cnt / vs->tile)), dim3(vs->tile), kargs, vs->smem, ctx->s_cmp);
+      else if (pass == 0)
+        e = cudaLaunchKernel((const void*)vs->kernel, dim3(unsigned((cnt / vs->ppt + 255) / 256)), dim3(256), kargs, 0, ctx->s_cmp);
       else
         e = cudaLaunchKernel((const void*)v->kernel, dim3(unsigned((cnt + 255) / 256)), dim3(256), kargs, 0, ctx->s_cmp);
       if (e != cudaSuccess) return jit_fail(m, EO_ERR_CUDA, "eo_jit_eval: launch: %s", cudaGetErrorString(e));

@@ -374,6 +374,10 @@ int eo_jit_compile(eo_jit* m, const int* derivatives, size_t* cubin_bytes);
  * any number of components per point.  eo_jit_eval uses it automatically when some array has an odd component count
  * (EO_JIT_STAGED=0/1 forces never/always); this entry point only compiles it (works without a GPU). */
 int eo_jit_compile_staged(eo_jit* m, const int* derivatives, int* tile_points, size_t* cubin_bytes);
+/* The several-points-per-thread variant used for scalar-sized models (<= 4 doubles read, <= 8 written per point):
+ * each thread fetches 2 or 4 consecutive points of every array with one wide access (EO_JIT_PPT=0 disables it).
+ * Compile-only entry point, like eo_jit_compile_staged. */
+int eo_jit_compile_ppt(eo_jit* m, const int* derivatives, int* points_per_thread, size_t* cubin_bytes);
 /* Version of the NVRTC that was found (major * 1000 + minor * 10, e.g. 12090), or EO_ERR_UNSUPPORTED.  The
  * toolkit's /usr/local/cuda/lib64/libnvrtc.so.12 is preferred (EO_NVRTC_LIB overrides); NVRTC older than 12.9
  * cannot assemble 256-bit global accesses, models compiled with it use 128-bit ones. */

@@ -62,6 +62,19 @@ def test_fused_tabulation_variants_compile_without_gpu():
     assert h.lib.eo_jit_compile_tabulated(h._h, ints(0, 0), 3, ints(2, 2), ints(1, 2), ints(6, 6), ints(0, 2), C.byref(nbytes)) == -1
 
 
+def test_points_per_thread_variant_compiles_for_scalar_sized_models():
+    import ctypes as C
+
+    ints = lambda *a: (C.c_int * len(a))(*a)  # noqa: E731
+    ppt, nbytes = C.c_int(0), C.c_size_t(0)
+    k = jm.heat_conductivity(compile_only=True)
+    assert k.lib.eo_jit_compile_ppt(k._h, ints(1), C.byref(ppt), C.byref(nbytes)) == 0 and ppt.value == 4
+    q = jm.heat_flux(compile_only=True)
+    assert q.lib.eo_jit_compile_ppt(q._h, ints(0, 1), C.byref(ppt), C.byref(nbytes)) == 0 and ppt.value == 2
+    vm = jm.von_mises(compile_only=True)  # 9 doubles read per point: one point per thread
+    assert vm.lib.eo_jit_compile_ppt(vm._h, ints(1), C.byref(ppt), C.byref(nbytes)) == -4 and ppt.value == 1
+
+
 def test_cubin_cache_on_disk(tmp_path):
     """EO_JIT_CACHE_DIR: the second process-lifetime of a model loads its CUBIN instead of compiling it."""
     import subprocess

@@ -238,3 +238,29 @@ def test_jit_staged_variant_odd_component_counts(ctx):
     _close(d_P.to_host(), P, 1e-12)
     few = m((1,))(F[:17])  # fewer points than a tile: direct kernel only
     _close(few, P[:17], 1e-12)
+
+
+@pytest.mark.parametrize("n", [1023, 1024, 100_003])
+def test_jit_points_per_thread_variant(ctx, n):
+    """Scalar-sized models run 2 or 4 points per thread above 1024 points (bulk) + a direct tail; every variant
+    must give the same bits as the one-point-per-thread kernel (same model code, same IEEE operations)."""
+    import os
+
+    rng = np.random.default_rng(n)
+    T, s = rng.uniform(0.0, 2.0, n), rng.normal(size=(n, 2))
+    q, k = jm.heat_flux(ctx=ctx), jm.heat_conductivity(ctx=ctx)
+    l0 = ctx.launch_count
+    got = {d: np.array(q(d)(T, s)) for d in [(0, 0), (1, 0), (0, 1), (1, 1)]}
+    gk = {d: np.array(k(d)(T)) for d in [(0,), (1,), (2,)]}
+    launches = ctx.launch_count - l0
+    assert launches == (7 if n < 1024 else 7 + sum(1 for ppt in (2, 2, 2, 2, 4, 4, 4) if n % ppt))
+    os.environ["EO_JIT_PPT"] = "0"
+    try:
+        q1, k1 = jm.heat_flux(ctx=ctx), jm.heat_conductivity(ctx=ctx)
+        for d in got:
+            assert np.array_equal(got[d], np.array(q1(d)(T, s))), d
+        for d in gk:
+            assert np.array_equal(gk[d], np.array(k1(d)(T))), d
+    finally:
+        del os.environ["EO_JIT_PPT"]
+    _close(gk[(1,)], -1.0 / (1.0 + T) ** 2, 1e-13)
