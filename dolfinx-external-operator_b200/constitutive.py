@@ -39,6 +39,8 @@ def _as_input(arr):
     """Borrow an operand without copying when it is already usable."""
     if isinstance(arr, DeviceArray):
         return arr
+    if hasattr(arr, "materialize"):  # tabulation.LazyOperand handed to a callable that does not fuse the tabulation
+        return arr.materialize()
     a = np.asarray(arr)
     if a.dtype != np.float64 or not a.flags.c_contiguous:
         a = np.ascontiguousarray(a, dtype=np.float64)

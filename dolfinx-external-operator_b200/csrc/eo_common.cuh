@@ -207,7 +207,18 @@ __device__ __forceinline__ void eo_st64(double* p, double x) {
   asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(x) : "memory");
 }
 
-// block-wide sum of a per-thread count, one atomicAdd per CTA
+// block-wide sum of per-thread counts (grid-stride kernels: a thread may have counted several points)
+__device__ __forceinline__ void eo_block_sum_add(unsigned long long* dst, int count) {
+  __shared__ int s_sum;
+  if (threadIdx.x == 0) s_sum = 0;
+  __syncthreads();
+  const int w = __reduce_add_sync(0xffffffffu, count);
+  if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_sum, w);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_sum) atomicAdd(dst, (unsigned long long)s_sum);
+}
+
+// block-wide sum of a per-thread FLAG (0/1), one atomicAdd per CTA
 __device__ __forceinline__ void eo_block_count_add(unsigned long long* dst, int flag) {
   __shared__ int s_cnt;
   if (threadIdx.x == 0) s_cnt = 0;

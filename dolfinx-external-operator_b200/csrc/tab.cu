@@ -18,6 +18,10 @@
 #include "tab_core.cuh"
 #include "vm_core.cuh"
 
+#ifndef TAB_FUSED_WAVES
+#define TAB_FUSED_WAVES 8
+#endif
+
 struct eo_tab {
   eo_ctx* ctx = nullptr;
   tab_tables T;
@@ -78,9 +82,9 @@ __global__ void __launch_bounds__(256, 4) tab_vm_kernel(const __grid_constant__ 
     s_dphi[q][k][a] = T.dphi[k][q][a];
   }
   __syncthreads();
-  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  // grid-stride over 256-point tiles: the table staging and its barrier are paid once per CTA, not once per tile
   int plastic = 0;
-  if (i < n_points) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n_points; i += int64_t(gridDim.x) * blockDim.x) {
     int64_t c;
     int q;
     if (NQ > 0) {
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(256, 4) tab_vm_kernel(const __grid_constant__ 
       vm_point(vq, e[0], e[1], e[2], e[3], s.x, s.y, s.z, s.w, pi, o);
     else
       vm_point_fast(vq, e[0], e[1], e[2], e[3], s.x, s.y, s.z, s.w, pi, o);
-    plastic = o.dp > 0.0;
+    plastic += o.dp > 0.0;
     double* Ct = C_tang + 16 * i;
     eo_st256(Ct + 0, o.C[0], o.C[1], o.C[2], o.C[3]);
     eo_st256(Ct + 4, o.C[4], o.C[5], o.C[6], o.C[7]);
@@ -129,7 +133,7 @@ __global__ void __launch_bounds__(256, 4) tab_vm_kernel(const __grid_constant__ 
     eo_st64(dp_out + i, o.dp);
     if (strain_out) eo_st256(strain_out + 4 * i, e[0], e[1], e[2], e[3]);
   }
-  eo_block_count_add(reinterpret_cast<unsigned long long*>(&stats->n_plastic), plastic);
+  eo_block_sum_add(reinterpret_cast<unsigned long long*>(&stats->n_plastic), plastic);
   if (blockIdx.x == 0 && threadIdx.x == 0)
     atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_points), (unsigned long long)n_points);
 }
@@ -335,7 +339,9 @@ int eo_tab_vm_fused(eo_tab* t, const eo_vm_params* prm, const double* u, const d
   if (rc != EO_OK) return rc;
   const vm_consts q{prm->lmbda, prm->mu, prm->H, prm->sigma_0};
   const int64_t n_points = t->n_cells * t->T.nq;
-  const unsigned grid = (unsigned)((n_points + 255) / 256);
+  const int64_t tiles = (n_points + 255) / 256;
+  const int64_t cap = int64_t(ctx->sm_count) * 4 * TAB_FUSED_WAVES;  // 4 resident CTAs per SM x a few waves each
+  const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
 #define EO_FUSED_LAUNCH(N, Q, X)                                                                                         \
   tab_vm_kernel<N, Q, X><<<grid, 256, 0, ctx->s_cmp>>>(t->T, q, t->dofmap, t->x_dofmap, t->x, d_u, n_points, sigma_n, p, \
                                                        C_tang, sigma, dp, strain, ctx->stats)

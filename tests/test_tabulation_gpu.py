@@ -180,3 +180,23 @@ def test_drop_in_constitutive_update_flow(ctx):
     _close(J_op.ref_coefficient.x.array, rC, 1e-10)
     _close(sigma_new, rs, 1e-11)
     assert np.array_equal(dp_new > 0, rdp > 0)
+
+
+def test_lazy_operand_is_materialised_by_callables_that_do_not_fuse(ctx):
+    """`register(..., output="lazy")` hands an un-tabulated operand to the callable; a callable without a fused kernel
+    (Mohr-Coulomb) tabulates it after all and gives the same result as with an explicit tabulation."""
+    from dolfinx_external_operator_b200 import synthetic as syn
+    from dolfinx_external_operator_b200.tabulation import LazyOperand
+    from tab_util import tri_case
+
+    m = tri_case(nx=9, ny=8)
+    tab = eo.Tabulator(dofmap=m["dofmap"], x_dofmap=m["x_dofmap"], x=m["x"], phi=m["phi"], dphi=m["dphi"], bs=2,
+                       n_dofs=m["n_dofs"], ctx=ctx)
+    u = syn.smooth_displacement(m["dof_coords"], scale=1e-4, seed=3).reshape(-1)
+    n = 3 * m["dofmap"].shape[0]
+    mc = eo.MohrCoulomb(ctx=ctx)
+    mc.set_history(np.tile([-1.0, -1.2, -0.9, 0.1], (n, 1)))
+    a = [np.array(x) for x in mc((1,))(tab.evaluate("mandel_strain", u))]
+    b = [np.array(x) for x in mc((1,))(LazyOperand(tab, 2, u))]
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
