@@ -37,7 +37,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BYTES_PER_QP = {"vm": 240, "jitvm": 240, "jitfused": 235, "jitvm3d": 448, "heat": 88, "mc": 252, "tab": 176.0 / 3.0, "fused": 235, "isihara": 192}
+BYTES_PER_QP = {"vm": 240, "jitvm": 240, "jitfused": 235, "jitvm3d": 448, "heat": 88, "mc": 252, "tab": 176.0 / 3.0, "fused": 235, "isihara": 192,
+                # device-side consumers (csrc/form.cu): + read-modify-write of the DOF vector (2 nodes x 2 x 8 B per cell, twice)
+                "step": 235 + 64.0 / 3.0, "action": 128 + 80.0 / 3.0 + 64.0 / 3.0}
 METRIC = "quadrature points per second (stress + consistent tangent + internal state)"
 
 
@@ -144,20 +146,34 @@ def cpu_tab_rate(model: str, min_seconds: float):
     from dolfinx_external_operator_b200 import synthetic as syn
     from oracle import constitutive as oc
     from oracle import native
+    from oracle import forms as of
     from oracle import tabulation as ot
 
     native.use_all_cores()
-    m = syn.triangle_mesh(400, 400, 2, jitter=0.2, seed=0)
+    nxy = 150 if model in ("step", "action") else 400  # the forms oracle builds dense per-cell operand matrices
+    m = syn.triangle_mesh(nxy, nxy, 2, jitter=0.2, seed=0)
     phi, dphi = el.lagrange_triangle(2, el.triangle_quadrature(2))
     dpsi = el.p1_geometry_derivatives(2)
     u = syn.smooth_displacement(m["dof_coords"], scale=1.5e-3, seed=0).reshape(-1)
     nq = 3 * m["dofmap"].shape[0]
     _, sn, p = syn.vm_batch(nq, seed=0)
 
+    W3 = el.triangle_quadrature_weights(2)
+    geo = (m["x"], m["x_dofmap"], phi, dphi, dpsi)
+    Ct0 = None
+    if model == "action":
+        e = ot.tabulate(ot.MANDEL_STRAIN, u, m["dofmap"], 2, *geo)
+        Ct0 = native.vm_return_mapping(e.reshape(-1, 4), sn, p, oc.VonMisesParams(), parallel=True)[0]
+
     def fn():
-        e = ot.tabulate(ot.MANDEL_STRAIN, u, m["dofmap"], 2, m["x"], m["x_dofmap"], phi, dphi, dpsi)
-        if model == "fused":
-            native.vm_return_mapping(e.reshape(-1, 4), sn, p, oc.VonMisesParams(), parallel=True)
+        if model == "action":
+            of.apply_action(ot.MANDEL_STRAIN, ot.MANDEL_STRAIN, Ct0, u, W3, m["dofmap"], 2, m["n_dofs"], *geo)
+            return
+        e = ot.tabulate(ot.MANDEL_STRAIN, u, m["dofmap"], 2, *geo)
+        if model in ("fused", "step"):
+            r = native.vm_return_mapping(e.reshape(-1, 4), sn, p, oc.VonMisesParams(), parallel=True)
+            if model == "step":
+                of.assemble_vector(ot.MANDEL_STRAIN, r[1], W3, m["dofmap"], 2, m["n_dofs"], *geo)
 
     fn()
     best, passes, t_all = float("inf"), 0, time.perf_counter()
@@ -168,9 +184,51 @@ def cpu_tab_rate(model: str, min_seconds: float):
         passes += 1
         if time.perf_counter() - t_all >= min_seconds and passes >= 3:
             break
-    return {"value": nq / best, "unit": "QP/s", "cores": native.num_threads() if model == "fused" else 1, "kind": "port",
+    return {"value": nq / best, "unit": "QP/s", "cores": native.num_threads() if model in ("fused", "step") else 1, "kind": "port",
             "sample": f"{nq} QPs x {passes} passes (best pass); NumPy einsum restatement of the DOLFINx/FFCx tabulation "
-                      "(single-threaded)" + (" + OpenMP C restatement of the von Mises kernel" if model == "fused" else "")}
+                      "(single-threaded)" + (" + OpenMP C restatement of the von Mises kernel" if model in ("fused", "step") else "")
+                      + (" + NumPy restatement of the element loop of assemble_vector" if model == "step" else "")
+                      + ("; NumPy restatement of the element loop (tangent action)" if model == "action" else "")}
+
+
+def e2e_device_consumers(ctx, eo, inputs, ne, rank, world, max_over_ranks, barrier):
+    """Supplementary end-to-end figure of the default (von Mises) line: the same constitutive update consumed ON the
+    device - host displacement vector in, host residual vector out, tangent resident for the
+    matrix-free action - instead of shipping 168 B per point back to DOLFINx's assembler."""
+    from dolfinx_external_operator_b200 import elements as el
+
+    nxy = max(2, int(round((ne / 6.0) ** 0.5)))
+    mesh = inputs.triangle_mesh(nxy, nxy, 2, jitter=0.2, seed=rank)
+    nq = 3 * mesh["dofmap"].shape[0]
+    phi, dphi = el.lagrange_triangle(2, el.triangle_quadrature(2))
+    tab = eo.Tabulator(dofmap=mesh["dofmap"], x_dofmap=mesh["x_dofmap"], x=mesh["x"], phi=phi, dphi=dphi, bs=2,
+                       n_dofs=mesh["n_dofs"], ctx=ctx)
+    forms = eo.QuadratureForms(tab, el.triangle_quadrature_weights(2))
+    vm = eo.VonMises(n_qp=nq, ctx=ctx)
+    _, sn_t, p_t = inputs.vm_batch(min(nq, 1 << 22), seed=rank)
+    _tile_to_device(ctx, vm.sigma_n_dev, sn_t, nq, 4)
+    _tile_to_device(ctx, vm.p_dev, p_t, nq, 1)
+    nd = 2 * tab.n_dofs
+    u_h, b_h, y_h = ctx.pinned_empty((nd,)), ctx.pinned_empty((nd,)), ctx.pinned_empty((nd,))
+    u_h[:] = inputs.smooth_displacement(mesh["dof_coords"], scale=1.5e-3, seed=rank).reshape(-1)
+    del mesh
+    out = {}
+    for name, call in (("residual", lambda: forms.vm_residual(vm, u_h, out=b_h)),
+                       ("tangent_action", lambda: forms.action("mandel_strain", "mandel_strain", forms.C_tang, u_h, out=y_h))):
+        for _ in range(2):
+            call()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            call()
+        ctx.sync()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        out[name] = {"value": world * nq * 5 / dt, "unit": "QP/s", "ms_per_step": 1e3 * dt / 5}
+    out.update(h2d_bytes_per_step=8 * nd, d2h_bytes_per_step=8 * nd, qp_per_step_per_gpu=nq,
+               api="QuadratureForms.vm_residual(vm, u_host, out=b_host) / .action(..., x_host, out=y_host): eo_form_vm_step, "
+                   "eo_form_action; P2 vector triangles, 3 points per cell; boundary terms, lifting and the solve stay with "
+                   "the caller")
+    return out
 
 
 def run_reference_arm(args):
@@ -184,7 +242,7 @@ def run_reference_arm(args):
     native.build()
     native.use_all_cores()
     cores = native.num_threads()
-    if args.model in ("tab", "fused"):
+    if args.model in ("tab", "fused", "step", "action"):
         r = cpu_tab_rate(args.model, 5.0)
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "QP/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
@@ -259,6 +317,11 @@ WORKLOADS = {
            "(evaluate_operands for the von Mises / Mohr-Coulomb demos), structured jittered mesh",
     "fused": "operand tabulation fused with the von Mises return mapping (strain never stored), P2 vector field, "
              "3 quadrature points per triangle",
+    "step": "one Newton residual evaluation on the device (SURVEY.md 8f rank 1): Mandel strain of a P2 vector field -> "
+            "von Mises return mapping (tangent / stress / dp stored in HBM) -> b = int sigma . epsilon(v) dx, ONE kernel; "
+            "3 quadrature points per triangle",
+    "action": "matrix-free tangent action y = J x with J = int (C_tang epsilon(u_hat)) . epsilon(v) dx, tangent resident "
+              "in HBM (what a Krylov method needs from assemble_matrix); P2 vector field, 3 points per triangle",
 }
 
 
@@ -403,7 +466,7 @@ def run_gpu_arm(args):
 
         def step():
             isi.eval_device(d_F, d_dP, d_P)
-    elif model in ("tab", "fused", "jitfused"):
+    elif model in ("tab", "fused", "jitfused", "step", "action"):
         from dolfinx_external_operator_b200 import elements as el
 
         nxy = max(2, int(round((n / 6.0) ** 0.5)))
@@ -421,6 +484,24 @@ def run_gpu_arm(args):
 
             def step():
                 tab.evaluate("mandel_strain", d_u, out=d_out)
+        elif model in ("step", "action"):
+            forms = eo.QuadratureForms(tab, el.triangle_quadrature_weights(2))
+            vm = eo.VonMises(n_qp=n, ctx=ctx)
+            _, sn_t, p_t = inputs.vm_batch(tile_n, seed=rank)
+            _tile_to_device(ctx, vm.sigma_n_dev, sn_t, n, 4)
+            _tile_to_device(ctx, vm.p_dev, p_t, n, 1)
+            d_b = ctx.empty((2 * tab.n_dofs,))
+            extra_cfg["vm_arithmetic"] = "exact" if args.fused_exact else "fast (2 divisions, FMA; identical flags)"
+            extra_cfg["scatter"] = "fp64 RED.ADD per element-vector entry (12 per cell)"
+            if model == "step":
+                def step():
+                    forms.vm_residual(vm, d_u, out=d_b, exact=args.fused_exact)
+            else:
+                forms.vm_residual(vm, d_u, out=d_b, exact=args.fused_exact)  # fills forms.C_tang
+                d_y = ctx.empty((2 * tab.n_dofs,))
+
+                def step():
+                    forms.action("mandel_strain", "mandel_strain", forms.C_tang, d_u, out=d_y)
         elif model == "jitfused":
             from dolfinx_external_operator_b200 import jit_models as jm
             from dolfinx_external_operator_b200.tabulation import LazyOperand
@@ -562,6 +643,34 @@ def run_gpu_arm(args):
                    bound="PCIe device-to-host: the result is 168-188 B per point, the kernel needs < 10 % of the step")
         d_tmp.free()
 
+    e2e_dc = None
+    if model in ("step", "action"):
+        # end to end through QuadratureForms with HOST vectors: only DOF vectors cross the link
+        nd = 2 * tab.n_dofs
+        u_h, b_h = ctx.pinned_empty((nd,)), ctx.pinned_empty((nd,))
+        d_u.to_host(u_h)
+        if model == "step":
+            call = lambda: forms.vm_residual(vm, u_h, out=b_h, exact=args.fused_exact)  # noqa: E731
+            api = "QuadratureForms.vm_residual(vm, u_host, out=b_host): eo_form_vm_step, history / tangent resident in HBM"
+        else:
+            call = lambda: forms.action("mandel_strain", "mandel_strain", forms.C_tang, u_h, out=b_h)  # noqa: E731
+            api = "QuadratureForms.action(..., C_tang_resident, x_host, out=y_host): eo_form_action"
+        Ke = max(2, min(K, 5))
+        for _ in range(2):
+            call()
+        barrier()
+        t0 = time.perf_counter()
+        checksum = 0.0
+        for _ in range(Ke):
+            call()  # H2D + kernel + D2H, synchronous on return
+            checksum += float(b_h[0])
+        ctx.sync()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": world * n * Ke / dt, "unit": "QP/s", "h2d_bytes_per_step": 8 * nd, "d2h_bytes_per_step": 8 * nd,
+               "qp_per_step_per_gpu": n, "steps": Ke, "api": api, "ms_per_step": 1e3 * dt / Ke}
+    elif model == "vm" and args.e2e_n > 0 and not args.no_device_consumers:
+        e2e_dc = e2e_device_consumers(ctx, eo, inputs, int(args.e2e_n), rank, world, max_over_ranks, barrier)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -611,8 +720,8 @@ def run_gpu_arm(args):
     elif model == "isihara":
         cpu = None  # the CPU implementation is the reference's torch code, which needs /root/reference: timed in the
         #             build container only (69 k QP/s on 8 threads)
-    elif args.cpu_seconds > 0 and model in ("tab", "fused", "jitfused"):
-        cpu = cpu_tab_rate("fused" if model == "jitfused" else model, args.cpu_seconds)
+    elif args.cpu_seconds > 0 and model in ("tab", "fused", "jitfused", "step", "action"):
+        cpu = cpu_tab_rate({"jitfused": "fused"}.get(model, model), args.cpu_seconds)
     elif args.cpu_seconds > 0:
         sample = int(args.cpu_sample) if model != "mc" else min(int(args.cpu_sample), 200_000)
         cm = "vm" if model in ("jitvm", "jitvm3d") else model
@@ -649,6 +758,8 @@ def run_gpu_arm(args):
         "dtype": "f64", "data": "synthetic", "config": cfg, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    if e2e_dc is not None:
+        line["e2e_device_consumers"] = e2e_dc
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -660,7 +771,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--model", default="vm", choices=["vm", "heat", "mc", "tab", "fused", "isihara", "jitvm", "jitfused", "jitvm3d"])
+    ap.add_argument("--model", default="vm", choices=["vm", "heat", "mc", "tab", "fused", "isihara", "jitvm", "jitfused", "jitvm3d", "step", "action"])
     ap.add_argument("--fused-exact", action="store_true")
     ap.add_argument("--mc-scheme", default="queue", choices=["queue", "simple", "queue-noaffinity", "queue-onepass"])
     ap.add_argument("--n", type=float, default=1e8, help="quadrature points per GPU (device-resident leg)")
@@ -668,6 +779,8 @@ def main():
     ap.add_argument("--state-layout", default="aos", choices=["aos", "soa"])
     ap.add_argument("--cpu-sample", type=float, default=4e6)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-device-consumers", action="store_true",
+                    help="vm: skip the supplementary end-to-end leg through the device-side consumers (QuadratureForms)")
     ap.add_argument("--no-numa-bind", action="store_true", help="multi-GPU: do not pin ranks to their GPU's NUMA node")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -11,6 +11,7 @@ from .context import Context, DeviceArray, default_context  # noqa: F401
 from .constitutive import HeatConductivity, HeatFlux, MohrCoulomb, VonMises  # noqa: F401
 from .isihara import Isihara, register_torch_op  # noqa: F401
 from .tabulation import GeneralTabulator, Tabulator  # noqa: F401
+from .forms import QuadratureForms  # noqa: F401
 from .jit import JitModel  # noqa: F401
 from . import jit_models  # noqa: F401
 from .external_operator import (  # noqa: F401

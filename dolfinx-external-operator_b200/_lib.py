@@ -135,6 +135,14 @@ PROTOTYPES = {
     "eo_tab_ncomp": (C.c_int, [_vp, C.c_int]),
     "eo_tabulate": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _vp]),
     "eo_tab_vm_fused": (C.c_int, [_vp, C.POINTER(VmParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
+    "eo_form_create": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "eo_form_destroy": (C.c_int, [_vp]),
+    "eo_form_vector": (C.c_int, [_vp, C.c_int, _vp, _i64, _vp, C.c_int]),
+    "eo_form_action": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _i64, _vp, C.c_int]),
+    "eo_form_vm_step": (C.c_int, [_vp, C.POINTER(VmParams), _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, C.c_int, C.c_int]),
+    "eo_form_set_pattern": (C.c_int, [_vp, _vp, _vp, _i64]),
+    "eo_form_nnz": (_i64, [_vp]),
+    "eo_form_matrix": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _i64, _vp, C.c_int]),
     "eo_gtab_create": (C.c_int, [_vp, C.POINTER(GTabDesc), C.POINTER(_vp)]),
     "eo_gtab_destroy": (C.c_int, [_vp]),
     "eo_gtab_ncomp": (C.c_int, [_vp, C.c_int]),

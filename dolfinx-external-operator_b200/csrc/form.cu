@@ -1,0 +1,637 @@
+// form.cu - device-side CONSUMERS of the external-operator values: the two integrals the
+// reference hands to DOLFINx right after `evaluate_external_operators`, evaluated where the stress and the
+// tangent already live (HBM), so that only DOF vectors cross the PCIe link instead of 168 B per point.
+// replaces: `assemble_vector(b, F)` with F = inner(sigma, epsilon(v)) dx         (demo_plasticity_von_mises.py:253,
+//             petsc/petsc.py:64; heat: inner(q, grad(v)) dx, part2.py:181)
+//           the ACTION of `assemble_matrix(A, J)` with J = derivative(F, Du, u_hat) =
+//             inner(C_tang epsilon(u_hat), epsilon(v)) dx                         (demo_vm:390-398, petsc/petsc.py:88)
+//           on a vector (what a Krylov method needs from A), and A itself as CSR values.
+// The test/trial "operand kinds" are the ones of the tabulation (tab_core.cuh): the residual is the weighted
+// TRANSPOSE of the operand tabulation, b = B^T W s, and the tangent action is y = B^T W D B x.
+//
+// Mapping: one thread per cell.  The thread gathers its cell's geometry (and, for the action, the nb*bs entries
+// of x) through the read-only path, walks the cell's quadrature points - each point's record (stress 32 B,
+// tangent 128 B) is read once with 256-bit loads; the three records of a P2 triangle are contiguous - and
+// accumulates the nb*bs element-vector entries in registers; the tables sit in the constant bank (the point index
+// is warp-uniform: broadcast).  The scatter is one fp64 RED.ADD per element entry (each DOF of a P2 triangle mesh
+// is touched by 2-6 cells: low contention, resolved in L2).  Summation order over cells is therefore not fixed:
+// results agree with the oracle to rounding (tests: rtol 1e-12 of the vector norm), not bit for bit.
+// HBM-bound: residual 32 B/point + ~45 B/cell of index/geometry traffic; action 128 B/point + the same.
+#include "eo_common.cuh"
+#include "tab_core.cuh"
+#include "tab_handle.cuh"
+#include "vm_core.cuh"
+
+struct eo_form {
+  eo_tab* tab = nullptr;
+  double w[EO_TAB_MAX_NQ];   // quadrature weights on the reference cell
+  double* x_stage = nullptr; // device copy of a host input vector
+  double* y_stage = nullptr; // device result when the caller's vector is host memory
+  // CSR pattern of the assembled matrix (scalar rows/cols = bs * node + comp), built once on request
+  int64_t nnz = 0;
+  int32_t* row_ptr = nullptr;  // device [bs*n_dofs + 1]
+  int32_t* col = nullptr;      // device [nnz], sorted within a row
+};
+
+struct form_weights {
+  double w[EO_TAB_MAX_NQ];
+};
+
+// inverse Jacobian AND |det J| of one affine cell
+template <int GDIM>
+__device__ __forceinline__ double form_geometry(const tab_tables& T, const int32_t* __restrict__ x_dofmap,
+                                                const double* __restrict__ x, int64_t c, double K[GDIM][GDIM]) {
+  double xv[GDIM + 1][GDIM];
+#pragma unroll
+  for (int v = 0; v < GDIM + 1; ++v) {
+    const int32_t node = __ldg(x_dofmap + c * (GDIM + 1) + v);
+#pragma unroll
+    for (int i = 0; i < GDIM; ++i) xv[v][i] = __ldg(x + 3 * int64_t(node) + i);
+  }
+  double J[GDIM][GDIM];
+#pragma unroll
+  for (int i = 0; i < GDIM; ++i)
+#pragma unroll
+    for (int j = 0; j < GDIM; ++j) {
+      double acc = 0.0;
+#pragma unroll
+      for (int v = 0; v < GDIM + 1; ++v) acc += xv[v][i] * T.dpsi[j][v];
+      J[i][j] = acc;
+    }
+  tab_inverse<GDIM>(J, K);
+  double det;
+  if constexpr (GDIM == 2)
+    det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+  else
+    det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) + J[0][1] * (J[1][2] * J[2][0] - J[1][0] * J[2][2]) +
+          J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+  return fabs(det);
+}
+
+// transpose of tab_operand: the point value s (ncomp of `kind`) as a cotangent of (value, gradient)
+template <int GDIM, int BS>
+__device__ __forceinline__ void form_cotangent(int kind, const double* s, double Vs[BS], double Gs[BS][GDIM]) {
+#pragma unroll
+  for (int c = 0; c < BS; ++c) {
+    Vs[c] = 0.0;
+#pragma unroll
+    for (int j = 0; j < GDIM; ++j) Gs[c][j] = 0.0;
+  }
+  if (kind == 0) {
+#pragma unroll
+    for (int c = 0; c < BS; ++c) Vs[c] = s[c];
+  } else if (kind == 2) {
+    if constexpr (GDIM == 2 && BS == 2) {
+      const double h = 1.4142135623730951 * 0.5 * s[3];
+      Gs[0][0] = s[0], Gs[1][1] = s[1], Gs[0][1] = h, Gs[1][0] = h;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < BS; ++c)
+#pragma unroll
+      for (int j = 0; j < GDIM; ++j) Gs[c][j] = s[c * GDIM + j];
+  }
+}
+
+// fe[a][c] += scale * ( Vs[c] phi[q][a] + sum_k (sum_j Gs[c][j] K[k][j]) dphi[k][q][a] )   - transpose of tab_point
+template <int GDIM, int BS, int NB>
+__device__ __forceinline__ void form_accumulate(const tab_tables& T, int kind, int q, double scale, const double Vs[BS],
+                                                const double Gs[BS][GDIM], const double K[GDIM][GDIM],
+                                                double fe[NB][BS]) {
+  if (kind == 0) {
+#pragma unroll
+    for (int a = 0; a < NB; ++a) {
+      const double ph = scale * T.phi[q][a];
+#pragma unroll
+      for (int c = 0; c < BS; ++c) fe[a][c] += Vs[c] * ph;
+    }
+    return;
+  }
+  double H[BS][GDIM];
+#pragma unroll
+  for (int c = 0; c < BS; ++c)
+#pragma unroll
+    for (int k = 0; k < GDIM; ++k) {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < GDIM; ++j) acc += Gs[c][j] * K[k][j];
+      H[c][k] = scale * acc;
+    }
+#pragma unroll
+  for (int a = 0; a < NB; ++a)
+#pragma unroll
+    for (int c = 0; c < BS; ++c) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < GDIM; ++k) acc += H[c][k] * T.dphi[k][q][a];
+      fe[a][c] += acc;
+    }
+}
+
+template <int BS, int NB>
+__device__ __forceinline__ void form_scatter(const int32_t idx[NB], const double fe[NB][BS], double* __restrict__ b) {
+#pragma unroll
+  for (int a = 0; a < NB; ++a)
+#pragma unroll
+    for (int c = 0; c < BS; ++c) atomicAdd(b + int64_t(BS) * idx[a] + c, fe[a][c]);
+}
+
+// b += sum_q w_q |det J| B_q^T coef[c][q]
+template <int GDIM, int BS, int NB>
+__global__ void __launch_bounds__(128) form_vector_kernel(const __grid_constant__ tab_tables T,
+                                                          const __grid_constant__ form_weights W, int kind,
+                                                          const int32_t* __restrict__ dofmap,
+                                                          const int32_t* __restrict__ x_dofmap,
+                                                          const double* __restrict__ x, const double* __restrict__ coef,
+                                                          int64_t n_cells, double* __restrict__ b) {
+  const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (c >= n_cells) return;
+  double K[GDIM][GDIM];
+  const double adet = form_geometry<GDIM>(T, x_dofmap, x, c, K);
+  int32_t idx[NB];
+#pragma unroll
+  for (int a = 0; a < NB; ++a) idx[a] = __ldg(dofmap + c * NB + a);
+  const int ncomp = tab_ncomp(kind, BS, GDIM);
+  const bool vec4 = ncomp == 4 && (reinterpret_cast<uintptr_t>(coef) % 32) == 0;
+  double fe[NB][BS];
+#pragma unroll
+  for (int a = 0; a < NB; ++a)
+#pragma unroll
+    for (int k = 0; k < BS; ++k) fe[a][k] = 0.0;
+  const double* s_ptr = coef + c * int64_t(T.nq) * ncomp;
+  for (int q = 0; q < T.nq; ++q) {
+    double s[BS * GDIM > 4 ? BS * GDIM : 4];
+    if (vec4) {
+      const eo_d4 v = eo_ld256(s_ptr + 4 * q);
+      s[0] = v.x, s[1] = v.y, s[2] = v.z, s[3] = v.w;
+    } else {
+      for (int k = 0; k < ncomp; ++k) s[k] = eo_ld64(s_ptr + q * ncomp + k);
+    }
+    double Vs[BS], Gs[BS][GDIM];
+    form_cotangent<GDIM, BS>(kind, s, Vs, Gs);
+    form_accumulate<GDIM, BS, NB>(T, kind, q, W.w[q] * adet, Vs, Gs, K, fe);
+  }
+  form_scatter<BS, NB>(idx, fe, b);
+}
+
+// y += sum_q w_q |det J| B_test,q^T ( D[c][q] (B_trial,q x) ),   D row-major (ncomp_test, ncomp_trial) per point
+template <int GDIM, int BS, int NB>
+__global__ void __launch_bounds__(128) form_action_kernel(const __grid_constant__ tab_tables T,
+                                                          const __grid_constant__ form_weights W, int kind_test,
+                                                          int kind_trial, const int32_t* __restrict__ dofmap,
+                                                          const int32_t* __restrict__ x_dofmap,
+                                                          const double* __restrict__ x, const double* __restrict__ D,
+                                                          const double* __restrict__ xin, int64_t n_cells,
+                                                          double* __restrict__ y) {
+  const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (c >= n_cells) return;
+  double K[GDIM][GDIM];
+  const double adet = form_geometry<GDIM>(T, x_dofmap, x, c, K);
+  int32_t idx[NB];
+#pragma unroll
+  for (int a = 0; a < NB; ++a) idx[a] = __ldg(dofmap + c * NB + a);
+  double w[NB][BS];
+#pragma unroll
+  for (int a = 0; a < NB; ++a) {
+    if constexpr (BS == 2) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(xin) + idx[a]);
+      w[a][0] = v.x, w[a][1] = v.y;
+    } else {
+#pragma unroll
+      for (int k = 0; k < BS; ++k) w[a][k] = __ldg(xin + int64_t(BS) * idx[a] + k);
+    }
+  }
+  constexpr int MAXC = BS * GDIM > 4 ? BS * GDIM : 4;
+  const int nt = tab_ncomp(kind_test, BS, GDIM), ni = tab_ncomp(kind_trial, BS, GDIM);
+  const bool vec44 = nt == 4 && ni == 4 && (reinterpret_cast<uintptr_t>(D) % 32) == 0;
+  double fe[NB][BS];
+#pragma unroll
+  for (int a = 0; a < NB; ++a)
+#pragma unroll
+    for (int k = 0; k < BS; ++k) fe[a][k] = 0.0;
+  const double* D_ptr = D + c * int64_t(T.nq) * nt * ni;
+  for (int q = 0; q < T.nq; ++q) {
+    double val[BS], grad[BS][GDIM], e[MAXC], tau[MAXC];
+    tab_point<GDIM, BS, NB>(T, w, K, q, kind_trial == 0, kind_trial != 0, val, grad);
+    tab_operand<GDIM, BS>(kind_trial, val, grad, e);
+    if (vec44) {
+      const double* Dq = D_ptr + 16 * q;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const eo_d4 d = eo_ld256(Dq + 4 * r);
+        tau[r] = d.x * e[0] + d.y * e[1] + d.z * e[2] + d.w * e[3];
+      }
+    } else {
+      const double* Dq = D_ptr + int64_t(q) * nt * ni;
+      for (int r = 0; r < nt; ++r) {
+        double acc = 0.0;
+        for (int l = 0; l < ni; ++l) acc += eo_ld64(Dq + r * ni + l) * e[l];
+        tau[r] = acc;
+      }
+    }
+    double Vs[BS], Gs[BS][GDIM];
+    form_cotangent<GDIM, BS>(kind_test, tau, Vs, Gs);
+    form_accumulate<GDIM, BS, NB>(T, kind_test, q, W.w[q] * adet, Vs, Gs, K, fe);
+  }
+  form_scatter<BS, NB>(idx, fe, y);
+}
+
+// One Newton residual evaluation of the von Mises problem without leaving the device:
+// Mandel strain of u -> radial return (C_tang, sigma, dp stored for the tangent action / the history commit)
+// -> b += int sigma . epsilon(v) dx.  The per-point arithmetic and its results are those of eo_tab_vm_fused.
+template <int NB, bool EXACT>
+__global__ void __launch_bounds__(128) form_vm_step_kernel(const __grid_constant__ tab_tables T,
+                                                           const __grid_constant__ form_weights W, const vm_consts vq,
+                                                           const int32_t* __restrict__ dofmap,
+                                                           const int32_t* __restrict__ x_dofmap,
+                                                           const double* __restrict__ x, const double* __restrict__ u,
+                                                           int64_t n_cells, const double* __restrict__ sigma_n,
+                                                           const double* __restrict__ p, double* __restrict__ C_tang,
+                                                           double* __restrict__ sigma, double* __restrict__ dp_out,
+                                                           double* __restrict__ b, eo_stats* stats) {
+  const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  int plastic = 0;
+  if (c < n_cells) {
+    double K[2][2];
+    const double adet = form_geometry<2>(T, x_dofmap, x, c, K);
+    int32_t idx[NB];
+#pragma unroll
+    for (int a = 0; a < NB; ++a) idx[a] = __ldg(dofmap + c * NB + a);
+    double w[NB][2];
+#pragma unroll
+    for (int a = 0; a < NB; ++a) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(u) + idx[a]);
+      w[a][0] = v.x, w[a][1] = v.y;
+    }
+    double fe[NB][2];
+#pragma unroll
+    for (int a = 0; a < NB; ++a) fe[a][0] = 0.0, fe[a][1] = 0.0;
+    const int64_t i0 = c * T.nq;
+    for (int q = 0; q < T.nq; ++q) {
+      const int64_t i = i0 + q;
+      const eo_d4 s = eo_ld256(sigma_n + 4 * i);
+      const double pi = eo_ld64(p + i);
+      double val[2] = {0.0, 0.0}, grad[2][2], e[4];
+      tab_point<2, 2, NB>(T, w, K, q, false, true, val, grad);
+      tab_operand<2, 2>(2, val, grad, e);
+      vm_point_out o;
+      if (EXACT)
+        vm_point(vq, e[0], e[1], e[2], e[3], s.x, s.y, s.z, s.w, pi, o);
+      else
+        vm_point_fast(vq, e[0], e[1], e[2], e[3], s.x, s.y, s.z, s.w, pi, o);
+      plastic += o.dp > 0.0;
+      double* Ct = C_tang + 16 * i;
+      eo_st256(Ct + 0, o.C[0], o.C[1], o.C[2], o.C[3]);
+      eo_st256(Ct + 4, o.C[4], o.C[5], o.C[6], o.C[7]);
+      eo_st256(Ct + 8, o.C[8], o.C[9], o.C[10], o.C[11]);
+      eo_st256(Ct + 12, o.C[12], o.C[13], o.C[14], o.C[15]);
+      eo_st256(sigma + 4 * i, o.g[0], o.g[1], o.g[2], o.g[3]);
+      eo_st64(dp_out + i, o.dp);
+      double Vs[2], Gs[2][2];
+      form_cotangent<2, 2>(2, o.g, Vs, Gs);
+      form_accumulate<2, 2, NB>(T, 2, q, W.w[q] * adet, Vs, Gs, K, fe);
+    }
+    form_scatter<2, NB>(idx, fe, b);
+  }
+  eo_block_sum_add(reinterpret_cast<unsigned long long*>(&stats->n_plastic), plastic);
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_points), (unsigned long long)(n_cells * T.nq));
+}
+
+// A[pos] += element matrix entries; the position of (row, col) is found by bisection in the sorted CSR row
+// (rows of a P2 triangle mesh hold <= ~40 entries: <= 6 probes, all L1/L2 hits on the pattern).
+template <int GDIM, int BS, int NB>
+__global__ void __launch_bounds__(128) form_matrix_kernel(const __grid_constant__ tab_tables T,
+                                                          const __grid_constant__ form_weights W, int kind_test,
+                                                          int kind_trial, const int32_t* __restrict__ dofmap,
+                                                          const int32_t* __restrict__ x_dofmap,
+                                                          const double* __restrict__ x, const double* __restrict__ D,
+                                                          int64_t n_cells, const int32_t* __restrict__ row_ptr,
+                                                          const int32_t* __restrict__ col, double* __restrict__ vals) {
+  const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (c >= n_cells) return;
+  double K[GDIM][GDIM];
+  const double adet = form_geometry<GDIM>(T, x_dofmap, x, c, K);
+  int32_t idx[NB];
+#pragma unroll
+  for (int a = 0; a < NB; ++a) idx[a] = __ldg(dofmap + c * NB + a);
+  constexpr int MAXC = BS * GDIM > 4 ? BS * GDIM : 4;
+  const int nt = tab_ncomp(kind_test, BS, GDIM), ni = tab_ncomp(kind_trial, BS, GDIM);
+  const double* D_ptr = D + c * int64_t(T.nq) * nt * ni;
+  // one trial basis function (bj, cj) at a time: its element-matrix COLUMN is the action on a unit vector
+  for (int bj = 0; bj < NB; ++bj)
+    for (int cj = 0; cj < BS; ++cj) {
+      double fe[NB][BS];
+#pragma unroll
+      for (int a = 0; a < NB; ++a)
+#pragma unroll
+        for (int k = 0; k < BS; ++k) fe[a][k] = 0.0;
+      for (int q = 0; q < T.nq; ++q) {
+        double val[BS], grad[BS][GDIM], e[MAXC], tau[MAXC];
+#pragma unroll
+        for (int k = 0; k < BS; ++k) {
+          val[k] = (k == cj) ? T.phi[q][bj] : 0.0;
+#pragma unroll
+          for (int j = 0; j < GDIM; ++j) {
+            double acc = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < GDIM; ++kk) acc += T.dphi[kk][q][bj] * K[kk][j];
+            grad[k][j] = (k == cj) ? acc : 0.0;
+          }
+        }
+        tab_operand<GDIM, BS>(kind_trial, val, grad, e);
+        const double* Dq = D_ptr + int64_t(q) * nt * ni;
+        for (int r = 0; r < nt; ++r) {
+          double acc = 0.0;
+          for (int l = 0; l < ni; ++l) acc += __ldg(Dq + r * ni + l) * e[l];
+          tau[r] = acc;
+        }
+        double Vs[BS], Gs[BS][GDIM];
+        form_cotangent<GDIM, BS>(kind_test, tau, Vs, Gs);
+        form_accumulate<GDIM, BS, NB>(T, kind_test, q, W.w[q] * adet, Vs, Gs, K, fe);
+      }
+      const int32_t gcol = BS * __ldg(dofmap + c * NB + bj) + cj;
+#pragma unroll
+      for (int a = 0; a < NB; ++a)
+#pragma unroll
+        for (int k = 0; k < BS; ++k) {
+          const int32_t grow = BS * idx[a] + k;
+          int32_t lo = __ldg(row_ptr + grow), hi = __ldg(row_ptr + grow + 1) - 1;
+          while (lo < hi) {
+            const int32_t mid = (lo + hi) >> 1;
+            if (__ldg(col + mid) < gcol) lo = mid + 1; else hi = mid;
+          }
+          atomicAdd(vals + lo, fe[a][k]);
+        }
+    }
+}
+
+static int form_kind(int kind) { return kind == EO_OPERAND_DEF_GRAD ? EO_OPERAND_GRAD : kind; }  // d(I + grad u) = grad du
+
+#define EO_FORM_CASES(X) \
+  X(2, 1, 3) X(2, 1, 6) X(2, 2, 3) X(2, 2, 6) X(2, 1, 10) X(2, 2, 10) X(3, 1, 4) X(3, 3, 4) X(3, 1, 10) X(3, 3, 10)
+
+// result vector on the device side: the caller's (device) or the staging copy (host); zeroed unless accumulating
+static int form_result(eo_form* f, double* y, int accumulate, double** d_y) {
+  eo_tab* t = f->tab;
+  eo_ctx* ctx = t->ctx;
+  const size_t bytes = size_t(t->n_dofs) * t->T.bs * sizeof(double);
+  if (eo_is_device_ptr(y)) {
+    *d_y = y;
+  } else {
+    if (!f->y_stage) EO_CUDA(ctx, cudaMalloc(&f->y_stage, bytes ? bytes : 8));
+    *d_y = f->y_stage;
+    if (accumulate) EO_CUDA(ctx, cudaMemcpyAsync(f->y_stage, y, bytes, cudaMemcpyHostToDevice, ctx->s_cmp));
+  }
+  if (!accumulate) EO_CUDA(ctx, cudaMemsetAsync(*d_y, 0, bytes, ctx->s_cmp));
+  return EO_OK;
+}
+
+static int form_finish(eo_form* f, double* y, double* d_y) {
+  eo_ctx* ctx = f->tab->ctx;
+  EO_CUDA(ctx, cudaGetLastError());
+  if (d_y != y) {
+    const size_t bytes = size_t(f->tab->n_dofs) * f->tab->T.bs * sizeof(double);
+    EO_CUDA(ctx, cudaMemcpyAsync(y, d_y, bytes, cudaMemcpyDeviceToHost, ctx->s_cmp));
+    EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_cmp));
+  }
+  return EO_OK;
+}
+
+static int form_stage_x(eo_form* f, const double* x, const double** d_x) {
+  eo_ctx* ctx = f->tab->ctx;
+  if (eo_is_device_ptr(x)) {
+    *d_x = x;
+    return EO_OK;
+  }
+  const size_t bytes = size_t(f->tab->n_dofs) * f->tab->T.bs * sizeof(double);
+  if (!f->x_stage) EO_CUDA(ctx, cudaMalloc(&f->x_stage, bytes ? bytes : 8));
+  EO_CUDA(ctx, cudaMemcpyAsync(f->x_stage, x, bytes, cudaMemcpyHostToDevice, ctx->s_cmp));
+  *d_x = f->x_stage;
+  return EO_OK;
+}
+
+static int form_check_kind(eo_form* f, int kind, const char* what) {
+  if (kind < 0 || kind > 3 || eo_tab_ncomp(f->tab, kind) <= 0)
+    return eo_fail(f->tab->ctx, EO_ERR_INVALID, "%s: operand kind %d does not fit this element", what, kind);
+  return EO_OK;
+}
+
+extern "C" {
+
+int eo_form_create(eo_tab* tab, const double* weights, eo_form** out) {
+  if (!tab) return EO_ERR_INVALID;
+  eo_ctx* ctx = tab->ctx;
+  EO_REQUIRE(ctx, weights && out, "eo_form_create: NULL argument");
+  eo_form* f = new eo_form();
+  f->tab = tab;
+  memset(f->w, 0, sizeof(f->w));
+  for (int q = 0; q < tab->T.nq; ++q) f->w[q] = weights[q];
+  *out = f;
+  return EO_OK;
+}
+
+int eo_form_destroy(eo_form* f) {
+  if (!f) return EO_OK;
+  cudaSetDevice(f->tab->ctx->device);
+  cudaStreamSynchronize(f->tab->ctx->s_cmp);
+  if (f->x_stage) cudaFree(f->x_stage);
+  if (f->y_stage) cudaFree(f->y_stage);
+  if (f->row_ptr) cudaFree(f->row_ptr);
+  if (f->col) cudaFree(f->col);
+  delete f;
+  return EO_OK;
+}
+
+int eo_form_vector(eo_form* f, int kind_test, const double* coef, int64_t n_cells, double* b, int accumulate) {
+  if (!f) return EO_ERR_INVALID;
+  eo_tab* t = f->tab;
+  eo_ctx* ctx = t->ctx;
+  int rc = form_check_kind(f, kind_test, "eo_form_vector");
+  if (rc != EO_OK) return rc;
+  if (n_cells < 0) n_cells = t->n_cells;
+  EO_REQUIRE(ctx, n_cells <= t->n_cells, "eo_form_vector: more cells requested than the mesh has");
+  EO_REQUIRE(ctx, b != nullptr, "eo_form_vector: b is NULL");
+  EO_REQUIRE(ctx, n_cells == 0 || (coef && eo_is_device_ptr(coef)), "eo_form_vector: the point values must be device memory");
+  EO_CUDA(ctx, cudaSetDevice(ctx->device));
+  double* d_b = nullptr;
+  rc = form_result(f, b, accumulate, &d_b);
+  if (rc != EO_OK) return rc;
+  const int kind = form_kind(kind_test);
+  if (n_cells > 0) {
+    const unsigned grid = (unsigned)((n_cells + 127) / 128);
+    form_weights W;
+    memcpy(W.w, f->w, sizeof(W.w));
+    bool done = false;
+#define X(G, B, N)                                                                                              \
+  if (!done && t->T.gdim == G && t->T.bs == B && t->T.nb == N) {                                                \
+    form_vector_kernel<G, B, N><<<grid, 128, 0, ctx->s_cmp>>>(t->T, W, kind, t->dofmap, t->x_dofmap, t->x, coef, \
+                                                              n_cells, d_b);                                    \
+    done = true;                                                                                                \
+  }
+    EO_FORM_CASES(X)
+#undef X
+    if (!done) return eo_fail(ctx, EO_ERR_UNSUPPORTED, "eo_form_vector: no kernel for this element");
+    ctx->launches += 1;
+  }
+  return form_finish(f, b, d_b);
+}
+
+int eo_form_action(eo_form* f, int kind_test, int kind_trial, const double* D, const double* x, int64_t n_cells,
+                   double* y, int accumulate) {
+  if (!f) return EO_ERR_INVALID;
+  eo_tab* t = f->tab;
+  eo_ctx* ctx = t->ctx;
+  int rc = form_check_kind(f, kind_test, "eo_form_action");
+  if (rc != EO_OK) return rc;
+  rc = form_check_kind(f, kind_trial, "eo_form_action");
+  if (rc != EO_OK) return rc;
+  if (n_cells < 0) n_cells = t->n_cells;
+  EO_REQUIRE(ctx, n_cells <= t->n_cells, "eo_form_action: more cells requested than the mesh has");
+  EO_REQUIRE(ctx, x && y, "eo_form_action: NULL vector");
+  EO_REQUIRE(ctx, n_cells == 0 || (D && eo_is_device_ptr(D)), "eo_form_action: the point values must be device memory");
+  EO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const double* d_x = nullptr;
+  rc = form_stage_x(f, x, &d_x);
+  if (rc != EO_OK) return rc;
+  double* d_y = nullptr;
+  rc = form_result(f, y, accumulate, &d_y);
+  if (rc != EO_OK) return rc;
+  EO_REQUIRE(ctx, d_x != d_y, "eo_form_action: x and y must not alias");
+  const int kt = form_kind(kind_test), ki = form_kind(kind_trial);
+  if (n_cells > 0) {
+    const unsigned grid = (unsigned)((n_cells + 127) / 128);
+    form_weights W;
+    memcpy(W.w, f->w, sizeof(W.w));
+    bool done = false;
+#define X(G, B, N)                                                                                               \
+  if (!done && t->T.gdim == G && t->T.bs == B && t->T.nb == N) {                                                 \
+    form_action_kernel<G, B, N><<<grid, 128, 0, ctx->s_cmp>>>(t->T, W, kt, ki, t->dofmap, t->x_dofmap, t->x, D, d_x, \
+                                                              n_cells, d_y);                                     \
+    done = true;                                                                                                 \
+  }
+    EO_FORM_CASES(X)
+#undef X
+    if (!done) return eo_fail(ctx, EO_ERR_UNSUPPORTED, "eo_form_action: no kernel for this element");
+    ctx->launches += 1;
+  }
+  return form_finish(f, y, d_y);
+}
+
+int eo_form_vm_step(eo_form* f, const eo_vm_params* prm, const double* u, const double* sigma_n, const double* p,
+                    double* C_tang, double* sigma, double* dp, int64_t n_cells, double* b, int accumulate, int exact) {
+  if (!f) return EO_ERR_INVALID;
+  eo_tab* t = f->tab;
+  eo_ctx* ctx = t->ctx;
+  EO_REQUIRE(ctx, prm != nullptr, "eo_form_vm_step: prm is NULL");
+  EO_REQUIRE(ctx, t->T.gdim == 2 && t->T.bs == 2, "eo_form_vm_step: needs a 2-d vector field (plane-strain Mandel strain)");
+  EO_REQUIRE(ctx, t->T.nb == 3 || t->T.nb == 6 || t->T.nb == 10, "eo_form_vm_step: P1/P2/P3 triangles only");
+  if (n_cells < 0) n_cells = t->n_cells;
+  EO_REQUIRE(ctx, n_cells <= t->n_cells, "eo_form_vm_step: more cells requested than the mesh has");
+  EO_REQUIRE(ctx, u && b, "eo_form_vm_step: NULL vector");
+  EO_REQUIRE(ctx, n_cells == 0 || (sigma_n && p && C_tang && sigma && dp), "eo_form_vm_step: NULL array");
+  EO_REQUIRE(ctx, n_cells == 0 || (eo_is_device_ptr(sigma_n) && eo_is_device_ptr(p) && eo_is_device_ptr(C_tang) &&
+                                   eo_is_device_ptr(sigma) && eo_is_device_ptr(dp)),
+             "eo_form_vm_step: history and point outputs must be device memory (u and b may be host memory)");
+  EO_REQUIRE(ctx, eo_aligned(sigma_n, 32) && eo_aligned(C_tang, 32) && eo_aligned(sigma, 32),
+             "eo_form_vm_step: arrays must be 32-byte aligned");
+  EO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const double* d_u = nullptr;
+  int rc = eo_tab_stage_u(t, u, &d_u);
+  if (rc != EO_OK) return rc;
+  double* d_b = nullptr;
+  rc = form_result(f, b, accumulate, &d_b);
+  if (rc != EO_OK) return rc;
+  if (n_cells > 0) {
+    const vm_consts q{prm->lmbda, prm->mu, prm->H, prm->sigma_0};
+    const unsigned grid = (unsigned)((n_cells + 127) / 128);
+    form_weights W;
+    memcpy(W.w, f->w, sizeof(W.w));
+#define EO_STEP(N)                                                                                                     \
+  if (t->T.nb == N) {                                                                                                  \
+    if (exact)                                                                                                         \
+      form_vm_step_kernel<N, true><<<grid, 128, 0, ctx->s_cmp>>>(t->T, W, q, t->dofmap, t->x_dofmap, t->x, d_u, n_cells, \
+                                                                 sigma_n, p, C_tang, sigma, dp, d_b, ctx->stats);      \
+    else                                                                                                               \
+      form_vm_step_kernel<N, false><<<grid, 128, 0, ctx->s_cmp>>>(t->T, W, q, t->dofmap, t->x_dofmap, t->x, d_u,        \
+                                                                  n_cells, sigma_n, p, C_tang, sigma, dp, d_b, ctx->stats); \
+  }
+    EO_STEP(3)
+    EO_STEP(6)
+    EO_STEP(10)
+#undef EO_STEP
+    ctx->launches += 1;
+  }
+  return form_finish(f, b, d_b);
+}
+
+int eo_form_set_pattern(eo_form* f, const int32_t* row_ptr, const int32_t* col, int64_t nnz) {
+  if (!f) return EO_ERR_INVALID;
+  eo_tab* t = f->tab;
+  eo_ctx* ctx = t->ctx;
+  const int64_t n_rows = t->n_dofs * t->T.bs;
+  EO_REQUIRE(ctx, row_ptr && (col || nnz == 0) && nnz >= 0, "eo_form_set_pattern: bad argument");
+  EO_REQUIRE(ctx, nnz < 2147483647LL, "eo_form_set_pattern: more than 2^31 - 1 entries (int32 CSR)");
+  EO_REQUIRE(ctx, row_ptr[0] == 0 && row_ptr[n_rows] == nnz, "eo_form_set_pattern: row_ptr does not span [0, nnz]");
+  for (int64_t r = 0; r < n_rows; ++r) {
+    if (row_ptr[r + 1] < row_ptr[r]) return eo_fail(ctx, EO_ERR_INVALID, "eo_form_set_pattern: row_ptr not monotone");
+    for (int32_t k = row_ptr[r]; k < row_ptr[r + 1]; ++k) {
+      if (col[k] < 0 || col[k] >= n_rows) return eo_fail(ctx, EO_ERR_INVALID, "eo_form_set_pattern: column out of range");
+      if (k > row_ptr[r] && col[k] <= col[k - 1])
+        return eo_fail(ctx, EO_ERR_INVALID, "eo_form_set_pattern: columns must be strictly increasing within a row");
+    }
+  }
+  EO_CUDA(ctx, cudaSetDevice(ctx->device));
+  EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_cmp));
+  if (f->row_ptr) cudaFree(f->row_ptr);
+  if (f->col) cudaFree(f->col);
+  f->row_ptr = nullptr, f->col = nullptr, f->nnz = 0;
+  EO_CUDA(ctx, cudaMalloc(&f->row_ptr, size_t(n_rows + 1) * 4));
+  EO_CUDA(ctx, cudaMalloc(&f->col, size_t(nnz ? nnz : 1) * 4));
+  EO_CUDA(ctx, cudaMemcpyAsync(f->row_ptr, row_ptr, size_t(n_rows + 1) * 4, cudaMemcpyHostToDevice, ctx->s_cmp));
+  EO_CUDA(ctx, cudaMemcpyAsync(f->col, col, size_t(nnz) * 4, cudaMemcpyHostToDevice, ctx->s_cmp));
+  EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_cmp));
+  f->nnz = nnz;
+  return EO_OK;
+}
+
+int eo_form_matrix(eo_form* f, int kind_test, int kind_trial, const double* D, int64_t n_cells, double* vals,
+                   int accumulate) {
+  if (!f) return EO_ERR_INVALID;
+  eo_tab* t = f->tab;
+  eo_ctx* ctx = t->ctx;
+  int rc = form_check_kind(f, kind_test, "eo_form_matrix");
+  if (rc != EO_OK) return rc;
+  rc = form_check_kind(f, kind_trial, "eo_form_matrix");
+  if (rc != EO_OK) return rc;
+  EO_REQUIRE(ctx, f->row_ptr != nullptr, "eo_form_matrix: no sparsity pattern (call eo_form_set_pattern first)");
+  if (n_cells < 0) n_cells = t->n_cells;
+  EO_REQUIRE(ctx, n_cells <= t->n_cells, "eo_form_matrix: more cells requested than the mesh has");
+  EO_REQUIRE(ctx, vals && eo_is_device_ptr(vals), "eo_form_matrix: the CSR values must be device memory");
+  EO_REQUIRE(ctx, n_cells == 0 || (D && eo_is_device_ptr(D)), "eo_form_matrix: the point values must be device memory");
+  EO_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!accumulate) EO_CUDA(ctx, cudaMemsetAsync(vals, 0, size_t(f->nnz) * sizeof(double), ctx->s_cmp));
+  const int kt = form_kind(kind_test), ki = form_kind(kind_trial);
+  if (n_cells > 0) {
+    const unsigned grid = (unsigned)((n_cells + 127) / 128);
+    form_weights W;
+    memcpy(W.w, f->w, sizeof(W.w));
+    bool done = false;
+#define X(G, B, N)                                                                                                  \
+  if (!done && t->T.gdim == G && t->T.bs == B && t->T.nb == N) {                                                    \
+    form_matrix_kernel<G, B, N><<<grid, 128, 0, ctx->s_cmp>>>(t->T, W, kt, ki, t->dofmap, t->x_dofmap, t->x, D, n_cells, \
+                                                              f->row_ptr, f->col, vals);                            \
+    done = true;                                                                                                    \
+  }
+    EO_FORM_CASES(X)
+#undef X
+    if (!done) return eo_fail(ctx, EO_ERR_UNSUPPORTED, "eo_form_matrix: no kernel for this element");
+    ctx->launches += 1;
+  }
+  EO_CUDA(ctx, cudaGetLastError());
+  return EO_OK;
+}
+
+int64_t eo_form_nnz(const eo_form* f) { return f ? f->nnz : -1; }
+
+}  // extern "C"

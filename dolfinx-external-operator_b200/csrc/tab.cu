@@ -16,24 +16,13 @@
 // Compiled with -fmad=false like vm_heat.cu (the fused and the two-step paths then agree bit for bit).
 #include "eo_common.cuh"
 #include "tab_core.cuh"
+#include "tab_handle.cuh"
 #include "vm_core.cuh"
 
 #ifndef TAB_FUSED_WAVES
 #define TAB_FUSED_WAVES 8
 #endif
 
-struct eo_tab {
-  eo_ctx* ctx = nullptr;
-  tab_tables T;
-  int64_t n_cells = 0, n_dofs = 0, n_nodes = 0;  // n_dofs counts blocked dofs (x bs scalars)
-  int32_t* dofmap = nullptr;                     // device [n_cells][nb]
-  int32_t* x_dofmap = nullptr;                   // device [n_cells][nv]
-  double* x = nullptr;                           // device [n_nodes][3]
-  tab_tables* d_T = nullptr;                     // device copy of T (the fused generic kernels stage it in shared memory)
-  double* u_stage = nullptr;                     // device staging copy of a host coefficient vector
-  int32_t* cells_stage = nullptr;                // device staging copy of a host entity list
-  size_t cells_stage_n = 0;
-};
 
 template <int GDIM, int BS, int NB>
 __global__ void __launch_bounds__(128) tab_kernel(const __grid_constant__ tab_tables T, int kind,
@@ -167,7 +156,7 @@ static int tab_launch(eo_tab* t, int kind, const double* u, const int32_t* cells
 }
 
 // device pointer for a coefficient vector given on either side
-static int tab_stage_u(eo_tab* t, const double* u, const double** d_u) {
+int eo_tab_stage_u(eo_tab* t, const double* u, const double** d_u) {
   eo_ctx* ctx = t->ctx;
   if (eo_is_device_ptr(u)) {
     *d_u = u;
@@ -189,7 +178,7 @@ int eo_tab_view_get(eo_tab* t, const double* u, eo_tab_view* v) {
   v->n_cells = t->n_cells, v->n_dofs = t->n_dofs;
   v->u = nullptr;
   if (!u) return EO_OK;
-  return tab_stage_u(t, u, &v->u);
+  return eo_tab_stage_u(t, u, &v->u);
 }
 
 extern "C" {
@@ -280,7 +269,7 @@ int eo_tabulate(eo_tab* t, int kind, const double* u, const int32_t* cells, int6
   EO_REQUIRE(ctx, u && out, "eo_tabulate: NULL array");
   EO_CUDA(ctx, cudaSetDevice(ctx->device));
   const double* d_u = nullptr;
-  int rc = tab_stage_u(t, u, &d_u);
+  int rc = eo_tab_stage_u(t, u, &d_u);
   if (rc != EO_OK) return rc;
   const int32_t* d_cells = cells;
   if (cells && !eo_is_device_ptr(cells)) {
@@ -335,7 +324,7 @@ int eo_tab_vm_fused(eo_tab* t, const eo_vm_params* prm, const double* u, const d
              "eo_tab_vm_fused: arrays must be 32-byte aligned");
   EO_CUDA(ctx, cudaSetDevice(ctx->device));
   const double* d_u = nullptr;
-  int rc = tab_stage_u(t, u, &d_u);
+  int rc = eo_tab_stage_u(t, u, &d_u);
   if (rc != EO_OK) return rc;
   const vm_consts q{prm->lmbda, prm->mu, prm->H, prm->sigma_0};
   const int64_t n_points = t->n_cells * t->T.nq;

@@ -1,0 +1,21 @@
+// tab_handle.cuh - the tabulation handle (device-resident mesh arrays + element tables), shared by tab.cu and
+// form.cu (the device-side consumers integrate over the same cells with the same tables).
+#pragma once
+#include "eo_common.cuh"
+#include "tab_core.cuh"
+
+struct eo_tab {
+  eo_ctx* ctx = nullptr;
+  tab_tables T;
+  int64_t n_cells = 0, n_dofs = 0, n_nodes = 0;  // n_dofs counts blocked dofs (x bs scalars)
+  int32_t* dofmap = nullptr;                     // device [n_cells][nb]
+  int32_t* x_dofmap = nullptr;                   // device [n_cells][nv]
+  double* x = nullptr;                           // device [n_nodes][3]
+  tab_tables* d_T = nullptr;                     // device copy of T (the fused generic kernels stage it in shared memory)
+  double* u_stage = nullptr;                     // device staging copy of a host coefficient vector
+  int32_t* cells_stage = nullptr;                // device staging copy of a host entity list
+  size_t cells_stage_n = 0;
+};
+
+// device pointer for a coefficient vector given on either side (host vectors are copied into t->u_stage)
+int eo_tab_stage_u(eo_tab* t, const double* u, const double** d_u);

@@ -23,6 +23,15 @@ def triangle_quadrature(degree: int) -> np.ndarray:
     raise NotImplementedError("only the 1- and 3-point triangle rules are tabulated here; pass basix points")
 
 
+def triangle_quadrature_weights(degree: int) -> np.ndarray:
+    """Weights of `triangle_quadrature(degree)` on the reference triangle (they sum to its area, 1/2)."""
+    if degree <= 1:
+        return np.array([0.5])
+    if degree == 2:
+        return np.full(3, 1.0 / 6.0)
+    raise NotImplementedError("only the 1- and 3-point triangle rules are tabulated here; pass basix weights")
+
+
 def lagrange_triangle(degree: int, X: np.ndarray):
     """(phi (nq, nb), dphi (2, nq, nb)) of P1 / P2 on the reference triangle at points X (nq, 2)."""
     x, y = X[:, 0], X[:, 1]

@@ -1,0 +1,179 @@
+"""Device-side consumers of the external-operator values (C ABI `eo_form_*`, csrc/form.cu).
+
+In the reference, `evaluate_external_operators` copies stress and tangent into `ref_coefficient.x.array`
+(external_operator.py:289-290) and DOLFINx then integrates them - `assemble_vector(b, F)` / `assemble_matrix(A, J)`
+inside the SNES callbacks (petsc/petsc.py:60-64, 86-88; forms at demo_plasticity_von_mises.py:253, 390-398).  At
+168 B per point that copy across PCIe is the end-to-end bottleneck once the kernels run at the HBM roofline
+(DESIGN.md section 8).  `QuadratureForms` evaluates those two integrals on the device, where the values already
+are, so only DOF vectors cross the link:
+
+    forms = QuadratureForms(tab, weights)                    # tab: the Tabulator of the displacement space
+    b = forms.vm_residual(vm, Du)                            # constitutive update + int sigma . eps(v) dx, one kernel
+    y = forms.action("mandel_strain", "mandel_strain", forms.C_tang, x)     # J @ x for a Krylov method
+    A = forms.matrix("mandel_strain", "mandel_strain", forms.C_tang)        # CSR values on the device
+
+Boundary terms (the pressure load of demo_vm:253), Dirichlet lifting and the linear solve stay with the caller.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import VmParams
+from .context import DeviceArray, _ptr
+from .tabulation import KINDS, Tabulator
+
+
+class QuadratureForms:
+    def __init__(self, tab: Tabulator, weights):
+        if type(tab) is not Tabulator:
+            raise TypeError("QuadratureForms needs the affine-simplex Tabulator (eo_tab) of the test/trial space")
+        self.tab, self.ctx = tab, tab.ctx
+        self.weights = np.ascontiguousarray(weights, dtype=np.float64).reshape(-1)
+        if self.weights.size != tab.nq:
+            raise ValueError(f"{self.weights.size} quadrature weights for {tab.nq} evaluation points per cell")
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.eo_form_create(tab._h, self.weights.ctypes.data, C.byref(h)))
+        self._h = h
+        self.n_scalar_dofs = tab.bs * tab.n_dofs
+        self.C_tang: DeviceArray | None = None  # tangent of the last vm_residual call, resident
+        self.row_ptr = self.col = None
+
+    def close(self):
+        if self._h is not None and self.ctx.alive:
+            self.ctx.lib.eo_form_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _kind(self, kind) -> int:
+        k = KINDS[kind] if isinstance(kind, str) else int(kind)
+        self.tab.ncomp(k)  # raises for kinds that do not fit the element
+        return k
+
+    def _vec_in(self, x):
+        if isinstance(x, DeviceArray):
+            if x.size != self.n_scalar_dofs:
+                raise ValueError("vector size does not match the dofmap")
+            return x
+        a = x.x.array if hasattr(x, "x") else x
+        a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+        if a.size != self.n_scalar_dofs:
+            raise ValueError(f"vector has {a.size} entries, the dofmap addresses {self.n_scalar_dofs}")
+        return a
+
+    def _vec_out(self, out, output):
+        if out is None:
+            return self.ctx.empty((self.n_scalar_dofs,)) if output == "device" else np.empty(self.n_scalar_dofs)
+        if isinstance(out, np.ndarray) and (out.dtype != np.float64 or not out.flags.c_contiguous):
+            raise ValueError("`out` must be a C-contiguous float64 array")
+        if out.size != self.n_scalar_dofs:
+            raise ValueError("`out` has the wrong size")
+        return out
+
+    def _points(self, a, ncomp, n_cells):
+        if not isinstance(a, DeviceArray):
+            raise TypeError("point values must be a DeviceArray (they are consumed where the operator kernels wrote them)")
+        if a.size != self.tab.n_cells * self.tab.nq * ncomp:
+            raise ValueError(f"point-value array has {a.size} entries, expected {self.tab.n_cells * self.tab.nq * ncomp}")
+        return a
+
+    def _cells(self, n_cells):
+        n = self.tab.n_cells if n_cells is None else int(n_cells)
+        if not 0 <= n <= self.tab.n_cells:
+            raise ValueError("n_cells out of range")
+        return n
+
+    # ------------------------------------------------------------------ the integrals
+    def vector(self, kind_test, coef: DeviceArray, out=None, n_cells=None, accumulate=False, output="host"):
+        """b = assemble_vector(inner(coef, OP_test(v)) dx) over cells 0..n_cells-1 (default: all)."""
+        k = self._kind(kind_test)
+        coef = self._points(coef, self.tab.ncomp(k), n_cells)
+        out = self._vec_out(out, output)
+        c = self.ctx
+        c.check(c.lib.eo_form_vector(self._h, k, coef.ptr, self._cells(n_cells), _ptr(out), int(bool(accumulate))))
+        return out
+
+    def action(self, kind_test, kind_trial, D: DeviceArray, x, out=None, n_cells=None, accumulate=False, output="host"):
+        """y = A x with A = assemble_matrix(inner(D OP_trial(u_hat), OP_test(v)) dx), never formed."""
+        kt, ki = self._kind(kind_test), self._kind(kind_trial)
+        D = self._points(D, self.tab.ncomp(kt) * self.tab.ncomp(ki), n_cells)
+        x = self._vec_in(x)
+        out = self._vec_out(out, output)
+        c = self.ctx
+        c.check(c.lib.eo_form_action(self._h, kt, ki, D.ptr, _ptr(x), self._cells(n_cells), _ptr(out),
+                                     int(bool(accumulate))))
+        return out
+
+    def vm_residual(self, vm, u=None, out=None, n_cells=None, accumulate=False, exact=False, output="host"):
+        """Constitutive update of the von Mises demo + residual in ONE kernel: the Mandel strain of `u` (default: the
+        tabulator's coefficient) goes through the radial return (`vm`: a resident-history `VonMises`), tangent /
+        stress / dp stay in HBM (`self.C_tang`, `vm.sigma_dev`, `vm.dp_dev`) and b = int sigma . eps(v) dx comes back."""
+        t = self.tab
+        n = t.n_cells * t.nq
+        if vm.n_qp is None:
+            vm._alloc_state(n)
+        if vm.n_qp != n:
+            raise ValueError(f"mesh has {n} quadrature points, the resident history {vm.n_qp}")
+        c = self.ctx
+        if self.C_tang is None or self.C_tang.size != 16 * n:
+            self.C_tang = c.empty((16 * n,))
+        u = t._coeff(u)
+        out = self._vec_out(out, output)
+        prm = VmParams(vm.lmbda, vm.mu, vm.H, vm.sigma_0)
+        c.check(c.lib.eo_form_vm_step(self._h, C.byref(prm), _ptr(u), vm.sigma_n_dev.ptr, vm.p_dev.ptr, self.C_tang.ptr,
+                                      vm.sigma_dev.ptr, vm.dp_dev.ptr, self._cells(n_cells), _ptr(out),
+                                      int(bool(accumulate)), int(bool(exact))))
+        return out
+
+    # ------------------------------------------------------------------ assembled matrix (CSR on the device)
+    def set_pattern(self, row_ptr=None, col=None):
+        """CSR pattern over scalar dofs; default: every pair of dofs sharing a cell (what DOLFINx's
+        `create_sparsity_pattern` gives for a cell integral), built on the host once."""
+        if row_ptr is None:
+            row_ptr, col = cell_sparsity(self.tab.dofmap, self.tab.bs, self.tab.n_dofs)
+        self.row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int32)
+        self.col = np.ascontiguousarray(col, dtype=np.int32)
+        if self.row_ptr.size != self.n_scalar_dofs + 1:
+            raise ValueError("row_ptr must have bs * n_dofs + 1 entries")
+        c = self.ctx
+        c.check(c.lib.eo_form_set_pattern(self._h, self.row_ptr.ctypes.data, self.col.ctypes.data, int(self.col.size)))
+        return self.row_ptr, self.col
+
+    def matrix(self, kind_test, kind_trial, D: DeviceArray, vals: DeviceArray | None = None, n_cells=None,
+               accumulate=False):
+        """CSR values (DeviceArray, nnz) of assemble_matrix(inner(D OP_trial(u_hat), OP_test(v)) dx)."""
+        if self.row_ptr is None:
+            self.set_pattern()
+        kt, ki = self._kind(kind_test), self._kind(kind_trial)
+        D = self._points(D, self.tab.ncomp(kt) * self.tab.ncomp(ki), n_cells)
+        c = self.ctx
+        if vals is None:
+            vals = c.empty((int(self.col.size),))
+        elif vals.size != self.col.size:
+            raise ValueError("`vals` does not match the pattern")
+        c.check(c.lib.eo_form_matrix(self._h, kt, ki, D.ptr, self._cells(n_cells), vals.ptr, int(bool(accumulate))))
+        return vals
+
+
+def cell_sparsity(dofmap: np.ndarray, bs: int, n_dofs: int):
+    """(row_ptr, col) int32 of the scalar-dof CSR pattern in which two dofs are coupled iff they share a cell."""
+    dofmap = np.asarray(dofmap)
+    nc, nb = dofmap.shape
+    nd = nb * bs
+    sd = (bs * dofmap[:, :, None].astype(np.int64) + np.arange(bs)[None, None, :]).reshape(nc, nd)
+    n = bs * n_dofs
+    key = np.unique((sd[:, :, None] * n + sd[:, None, :]).reshape(-1))
+    if key.size >= 2**31 - 1:
+        raise ValueError("pattern too large for int32 CSR")
+    rows, col = key // n, key % n
+    row_ptr = np.zeros(n + 1, dtype=np.int64)
+    np.add.at(row_ptr, rows + 1, 1)
+    return np.cumsum(row_ptr).astype(np.int32), col.astype(np.int32)

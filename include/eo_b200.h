@@ -243,6 +243,45 @@ int eo_tabulate(eo_tab* tab, int kind, const double* u, const int32_t* cells, in
 int eo_tab_vm_fused(eo_tab* tab, const eo_vm_params* prm, const double* u, const double* sigma_n, const double* p,
                     double* C_tang, double* sigma, double* dp, double* strain, int exact);
 
+/* ---------------------------------------------------------------- device-side consumers of the operator values
+ *  - what the reference hands to DOLFINx right after `evaluate_external_operators`:
+ * replaces: `assemble_vector(b, F)`, petsc/petsc.py:64, for F = inner(N, OP(v)) dx with N the external operator's
+ *             quadrature coefficient - inner(sigma, epsilon(v)) dx (demo_plasticity_von_mises.py:253),
+ *             inner(q, grad(v)) dx (demo_nonlinear_heat_equation_part2.py:181);
+ *           `assemble_matrix(A, J)`, petsc/petsc.py:88, for J = derivative(F, u, u_hat) after
+ *             `replace_external_operators` = inner(dN OP_trial(u_hat), OP_test(v)) dx (demo_vm:390-398), as the
+ *             ACTION on a vector (matrix-free Krylov) and as CSR values.
+ * The point values stay in HBM; only DOF vectors (about 11 B per point for P2 triangles) cross the PCIe link
+ * instead of the 168 B per point of the tangent.  OP_test / OP_trial are eo_operand_kind values of the element the
+ * eo_tab was built for (test space = trial space = the coefficient's space; DEF_GRAD acts as GRAD).  Cells 0..n_cells-1
+ * are integrated (n_cells < 0: all; DOLFINx integrates the owned cells, which come first, :368-370 lists owned +
+ * ghosts).  Scatter by fp64 atomics: cell order of the sums is not fixed, results are reproducible to rounding only.
+ * Vectors (bs * n_dofs doubles) are any-side pointers - with a host result the call is complete on return;
+ * point-value arrays must be device memory, laid out exactly as the operator kernels write them
+ * ([cell][point][comp], tangents row-major (ncomp_test, ncomp_trial)). */
+typedef struct eo_form eo_form;
+/* weights[nq]: quadrature weights of the reference cell at the eo_tab's evaluation points
+ * (basix.make_quadrature(cell, degree)[1]); the eo_tab must outlive the form. */
+int eo_form_create(eo_tab* tab, const double* weights, eo_form** out);
+int eo_form_destroy(eo_form* form);
+/* b (+)= sum_cells sum_q w_q |det J| coef[cell][q] . OP_test(phi_i)(x_q)      accumulate == 0: b is zeroed first */
+int eo_form_vector(eo_form* form, int kind_test, const double* coef, int64_t n_cells, double* b, int accumulate);
+/* y (+)= A x with A_ij = sum_cells sum_q w_q |det J| OP_test(phi_i) . D[cell][q] OP_trial(phi_j);  x, y distinct */
+int eo_form_action(eo_form* form, int kind_test, int kind_trial, const double* D, const double* x, int64_t n_cells,
+                   double* y, int accumulate);
+/* One Newton residual evaluation of the von Mises demo on the device (demo_vm:500-513: external_callback +
+ * assemble_vector): Mandel strain of u -> radial return (results identical to eo_tab_vm_fused, stored for
+ * eo_form_action / eo_commit_history) -> b (+)= int sigma . epsilon(v) dx.  One kernel; u, b any-side. */
+int eo_form_vm_step(eo_form* form, const eo_vm_params* prm, const double* u, const double* sigma_n, const double* p,
+                    double* C_tang, double* sigma, double* dp, int64_t n_cells, double* b, int accumulate, int exact);
+/* CSR pattern of the assembled matrix over scalar dofs (row = bs * node + comp): host arrays row_ptr[bs*n_dofs + 1],
+ * col[nnz] (strictly increasing within a row - what `fem.create_sparsity_pattern` + finalize gives); validated and
+ * uploaded once.  eo_form_matrix then adds every element matrix into vals[nnz] (device memory). */
+int eo_form_set_pattern(eo_form* form, const int32_t* row_ptr, const int32_t* col, int64_t nnz);
+int64_t eo_form_nnz(const eo_form* form);
+int eo_form_matrix(eo_form* form, int kind_test, int kind_trial, const double* D, int64_t n_cells, double* vals,
+                   int accumulate);
+
 /* ---------------------------------------------------------------- general operand tabulation
  * replaces: `expr.eval(operand_mesh, entities)`, external_operator.py:365-402, for everything the affine-simplex
  *           fast path above does not cover: any element given by its tables (higher-degree simplices,

@@ -1,0 +1,126 @@
+"""Known-answer anchors of the forms oracle (oracle/forms.py - parity unpinned against DOLFINx, see its header):
+adjointness with the analytically checked tabulation, exactly integrable fields, rigid-body modes and symmetry of
+the elastic stiffness, CSR assembly == action, and the reference's Taylor test of residual vs tangent
+(demo_plasticity_mohr_coulomb.py:1203-1235) with the von Mises oracle."""
+
+import numpy as np
+import pytest
+
+from dolfinx_external_operator_b200 import elements as el
+from dolfinx_external_operator_b200 import forms as pkg_forms
+from dolfinx_external_operator_b200 import synthetic as syn
+from oracle import constitutive as oc
+from oracle import forms as of
+from oracle import tabulation as ot
+from tab_util import tet_case, tri_case
+
+W3 = el.triangle_quadrature_weights(2)
+
+
+def _geo(m):
+    return (m["x"], m["x_dofmap"], m["phi"], m["dphi"], m["dpsi"])
+
+
+@pytest.mark.parametrize("kind", [ot.VALUE, ot.GRAD, ot.MANDEL_STRAIN, ot.DEF_GRAD])
+def test_vector_is_the_weighted_transpose_of_the_tabulation(kind):
+    m = tri_case(nx=7, ny=5)
+    rng = np.random.default_rng(0)
+    u = rng.normal(size=2 * m["n_dofs"])
+    op = ot.tabulate(kind, u, m["dofmap"], 2, *_geo(m))
+    if kind == ot.DEF_GRAD:
+        op = op - np.eye(2).reshape(-1)[None, None]
+    s = rng.normal(size=op.shape)
+    b = of.assemble_vector(kind, s, W3, m["dofmap"], 2, m["n_dofs"], *_geo(m))
+    _, adet = of.operand_matrix(kind, m["dofmap"], 2, *_geo(m))
+    lhs = np.einsum("cqk,cqk,q,c->", op, s, W3, adet)
+    assert abs(lhs - u @ b) <= 1e-12 * abs(lhs)
+
+
+def test_exact_integrals_on_the_unit_square():
+    m = tri_case(nx=6, ny=4, degree=2)  # jittered interior, the domain is still [0,1]^2
+    xq = m["xq"]
+    one = np.ones(xq.shape[:2] + (1,))
+    b = of.assemble_vector(ot.VALUE, one, W3, m["dofmap"], 1, m["n_dofs"], *_geo(m))
+    assert abs(b.sum() - 1.0) < 1e-14  # sum_i int phi_i = |domain|
+    N = (xq[..., 0] * xq[..., 1] + xq[..., 1] ** 2)[..., None]  # degree 2: the 3-point rule is exact for sum_i b_i
+    b = of.assemble_vector(ot.VALUE, N, W3, m["dofmap"], 1, m["n_dofs"], *_geo(m))
+    assert abs(b.sum() - (0.25 + 1.0 / 3.0)) < 1e-14
+    # int grad(v) . c over the domain against v = a P1 field interpolated into P2: = int c . grad(x) dx
+    c = np.broadcast_to(np.array([0.3, -1.1]), xq.shape[:2] + (2,))
+    b = of.assemble_vector(ot.GRAD, c, W3, m["dofmap"], 1, m["n_dofs"], *_geo(m))
+    assert abs(b @ m["dof_coords"][:, 0] - 0.3) < 1e-14 and abs(b @ m["dof_coords"][:, 1] + 1.1) < 1e-14
+
+
+def test_elastic_stiffness_rigid_modes_symmetry_and_csr():
+    m = tri_case(nx=5, ny=4)
+    nc = m["dofmap"].shape[0]
+    Ce = oc.elastic_stiffness(oc.VonMisesParams().lmbda, oc.VonMisesParams().mu)
+    D = np.broadcast_to(Ce.reshape(-1), (nc, 3, 16)).copy()
+    args = (W3, m["dofmap"], 2, m["n_dofs"], *_geo(m))
+    xy = m["dof_coords"]
+    scale = None
+    rng = np.random.default_rng(1)
+    xr, yr = rng.normal(size=2 * m["n_dofs"]), rng.normal(size=2 * m["n_dofs"])
+    Ax, Ay = (of.apply_action(ot.MANDEL_STRAIN, ot.MANDEL_STRAIN, D, v, *args) for v in (xr, yr))
+    scale = np.abs(Ax).max()
+    for mode in (np.stack([np.ones(len(xy)), np.zeros(len(xy))], 1), np.stack([np.zeros(len(xy)), np.ones(len(xy))], 1),
+                 np.stack([-xy[:, 1], xy[:, 0]], 1)):
+        y = of.apply_action(ot.MANDEL_STRAIN, ot.MANDEL_STRAIN, D, mode.reshape(-1), *args)
+        assert np.abs(y).max() < 1e-12 * scale
+    assert abs(yr @ Ax - xr @ Ay) < 1e-12 * abs(yr @ Ax)
+    assert xr @ Ax > 0
+    # assembled CSR == action; the package's pattern builder == the oracle's
+    rp, col = of.sparsity_pattern(m["dofmap"], 2, m["n_dofs"])
+    rp2, col2 = pkg_forms.cell_sparsity(m["dofmap"], 2, m["n_dofs"])
+    assert np.array_equal(rp, rp2) and np.array_equal(col, col2)
+    vals = of.assemble_matrix(ot.MANDEL_STRAIN, ot.MANDEL_STRAIN, D, *args, rp, col)
+    rows = np.repeat(np.arange(rp.size - 1), np.diff(rp))
+    y = np.zeros(2 * m["n_dofs"])
+    np.add.at(y, rows, vals * xr[col])
+    np.testing.assert_allclose(y, Ax, rtol=0, atol=1e-12 * scale)
+
+
+def test_tets_and_cell_subset():
+    m = tet_case(2)
+    w = np.array([0.1, 1.0 / 6.0 - 0.1])
+    rng = np.random.default_rng(2)
+    nc = m["dofmap"].shape[0]
+    s = rng.normal(size=(nc, 2, 9))
+    u = rng.normal(size=3 * m["n_dofs"])
+    b = of.assemble_vector(ot.GRAD, s, w, m["dofmap"], 3, m["n_dofs"], *_geo(m))
+    op = ot.tabulate(ot.GRAD, u, m["dofmap"], 3, *_geo(m))
+    _, adet = of.operand_matrix(ot.GRAD, m["dofmap"], 3, *_geo(m))
+    lhs = np.einsum("cqk,cqk,q,c->", op, s, w, adet)
+    assert abs(lhs - u @ b) <= 1e-12 * abs(lhs)
+    b_half = of.assemble_vector(ot.GRAD, s, w, m["dofmap"], 3, m["n_dofs"], *_geo(m), n_cells=nc // 2)
+    b_rest = of.assemble_vector(ot.GRAD, s[nc // 2:], w, m["dofmap"][nc // 2:], 3, m["n_dofs"], m["x"],
+                                m["x_dofmap"][nc // 2:], m["phi"], m["dphi"], m["dpsi"])
+    np.testing.assert_allclose(b_half + b_rest, b, rtol=0, atol=1e-13 * np.abs(b).max())
+
+
+def test_taylor_remainder_of_residual_vs_tangent_has_slope_two():
+    """demo_mc:1203-1235 for the von Mises demo: |F(u + h du) - F(u) - h J(u) du| = O(h^2)."""
+    m = tri_case(nx=8, ny=6)
+    prm = oc.VonMisesParams()
+    nq = m["dofmap"].shape[0] * 3
+    rng = np.random.default_rng(5)
+    sigma_n = rng.normal(0.0, 30.0, (nq, 4))
+    p = np.abs(rng.normal(0.0, 1e-3, nq))
+    u = syn.smooth_displacement(m["dof_coords"], scale=2e-2, seed=3).reshape(-1)  # deep in the plastic range
+    du = syn.smooth_displacement(m["dof_coords"], scale=2e-2, seed=4).reshape(-1)
+    args = (W3, m["dofmap"], 2, m["n_dofs"], *_geo(m))
+
+    def residual(v):
+        eps = ot.tabulate(ot.MANDEL_STRAIN, v, m["dofmap"], 2, *_geo(m)).reshape(-1, 4)
+        Ct, sig, dp = oc.vm_return_mapping(eps, sigma_n, p, prm)
+        return of.assemble_vector(ot.MANDEL_STRAIN, sig, *args), Ct, dp
+
+    F0, Ct, dp = residual(u)
+    assert (dp > 0).mean() > 0.9
+    Jdu = of.apply_action(ot.MANDEL_STRAIN, ot.MANDEL_STRAIN, Ct, du, *args)
+    hs = np.array([1e-2, 5e-3, 2.5e-3, 1.25e-3])
+    r0 = np.array([np.linalg.norm(residual(u + h * du)[0] - F0) for h in hs])
+    r1 = np.array([np.linalg.norm(residual(u + h * du)[0] - F0 - h * Jdu) for h in hs])
+    slope0 = np.polyfit(np.log(hs), np.log(r0), 1)[0]
+    slope1 = np.polyfit(np.log(hs), np.log(r1), 1)[0]
+    assert abs(slope0 - 1.0) < 0.05 and slope1 > 1.9

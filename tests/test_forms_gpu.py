@@ -1,0 +1,204 @@
+"""GPU parity tests of the device-side consumers (csrc/form.cu, C ABI eo_form_*, `QuadratureForms`) against the
+NumPy oracle (oracle/forms.py).  Floating point with an order-free atomic scatter: rtol 1e-12 of the vector's
+largest entry (north_star: 1e-12 for closed-form paths).  The per-point results of the fused residual step are
+bit-identical to the fused tabulate + von Mises kernel."""
+
+import numpy as np
+import pytest
+
+import dolfinx_external_operator_b200 as eo
+from dolfinx_external_operator_b200 import elements as el
+from dolfinx_external_operator_b200 import synthetic as syn
+from oracle import constitutive as oc
+from oracle import forms as of
+from oracle import tabulation as ot
+from tab_util import tet_case, tri_case
+
+pytestmark = pytest.mark.gpu
+KIND = {"value": ot.VALUE, "grad": ot.GRAD, "mandel_strain": ot.MANDEL_STRAIN, "def_grad": ot.DEF_GRAD}
+W3 = el.triangle_quadrature_weights(2)
+
+
+def _mk(ctx, m, bs, weights=W3):
+    tab = eo.Tabulator(dofmap=m["dofmap"], x_dofmap=m["x_dofmap"], x=m["x"], phi=m["phi"], dphi=m["dphi"], bs=bs,
+                       n_dofs=m["n_dofs"], ctx=ctx)
+    return tab, eo.QuadratureForms(tab, weights)
+
+
+def _geo(m):
+    return (m["x"], m["x_dofmap"], m["phi"], m["dphi"], m["dpsi"])
+
+
+def _close(a, b, rtol=1e-12):
+    a, b = np.asarray(a).reshape(-1), np.asarray(b).reshape(-1)
+    np.testing.assert_allclose(a, b, rtol=0, atol=rtol * max(np.abs(b).max(), 1e-300))
+
+
+@pytest.mark.parametrize("kind", ["value", "grad", "mandel_strain", "def_grad"])
+@pytest.mark.parametrize("degree", [1, 2])
+def test_vector_p1_p2_vector_triangle(ctx, kind, degree):
+    m = tri_case(nx=37, ny=23, degree=degree)
+    tab, forms = _mk(ctx, m, 2)
+    nc = m["dofmap"].shape[0]
+    s = np.random.default_rng(0).normal(size=(nc, 3, tab.ncomp(kind)))
+    d_s = ctx.to_device(s)
+    ref = of.assemble_vector(KIND[kind], s, W3, m["dofmap"], 2, m["n_dofs"], *_geo(m))
+    _close(forms.vector(kind, d_s), ref)
+    d_b = forms.vector(kind, d_s, output="device")
+    _close(d_b.to_host(), ref)
+    # accumulate on top of an existing host vector; owned-cell prefix
+    b0 = np.random.default_rng(1).normal(size=ref.size)
+    b = b0.copy()
+    forms.vector(kind, d_s, out=b, accumulate=True)
+    _close(b - b0, ref, rtol=1e-11)
+    half = of.assemble_vector(KIND[kind], s, W3, m["dofmap"], 2, m["n_dofs"], *_geo(m), n_cells=nc // 3)
+    _close(forms.vector(kind, d_s, n_cells=nc // 3), half)
+
+
+def test_vector_scalar_space_and_exact_integral(ctx):
+    m = tri_case(nx=20, ny=15, degree=2)
+    tab, forms = _mk(ctx, m, 1)
+    xq = m["xq"]
+    N = (xq[..., 0] * xq[..., 1] + xq[..., 1] ** 2)[..., None]
+    b = forms.vector("value", ctx.to_device(N))
+    assert abs(b.sum() - (0.25 + 1.0 / 3.0)) < 1e-13
+    _close(b, of.assemble_vector(ot.VALUE, N, W3, m["dofmap"], 1, m["n_dofs"], *_geo(m)))
+    q = np.random.default_rng(3).normal(size=xq.shape[:2] + (2,))  # heat flux against grad(v), part2.py:181
+    _close(forms.vector("grad", ctx.to_device(q)), of.assemble_vector(ot.GRAD, q, W3, m["dofmap"], 1, m["n_dofs"], *_geo(m)))
+
+
+def test_vector_and_action_tetrahedra(ctx):
+    m = tet_case(4)
+    w = np.array([0.1, 1.0 / 6.0 - 0.1])
+    tab, forms = _mk(ctx, m, 3, w)
+    nc = m["dofmap"].shape[0]
+    rng = np.random.default_rng(2)
+    s = rng.normal(size=(nc, 2, 9))
+    _close(forms.vector("grad", ctx.to_device(s)), of.assemble_vector(ot.GRAD, s, w, m["dofmap"], 3, m["n_dofs"], *_geo(m)))
+    D = rng.normal(size=(nc, 2, 81))
+    x = rng.normal(size=3 * m["n_dofs"])
+    ref = of.apply_action(ot.GRAD, ot.GRAD, D, x, w, m["dofmap"], 3, m["n_dofs"], *_geo(m))
+    _close(forms.action("grad", "def_grad", ctx.to_device(D), x), ref)
+
+
+@pytest.mark.parametrize("pair", [("mandel_strain", "mandel_strain"), ("grad", "value"), ("value", "grad"), ("grad", "grad")])
+def test_action_p2_triangle(ctx, pair):
+    kt, ki = pair
+    bs = 2 if "mandel_strain" in pair else 1  # (grad, value) = dq/dT, (grad, grad) = dq/dsigma of the heat demo
+    m = tri_case(nx=31, ny=17)
+    tab, forms = _mk(ctx, m, bs)
+    nc = m["dofmap"].shape[0]
+    rng = np.random.default_rng(4)
+    D = rng.normal(size=(nc, 3, tab.ncomp(kt) * tab.ncomp(ki)))
+    x = rng.normal(size=bs * m["n_dofs"])
+    ref = of.apply_action(KIND[kt], KIND[ki], D, x, W3, m["dofmap"], bs, m["n_dofs"], *_geo(m))
+    d_D = ctx.to_device(D)
+    _close(forms.action(kt, ki, d_D, x), ref)
+    d_y = forms.action(kt, ki, d_D, ctx.to_device(x), output="device")
+    _close(d_y.to_host(), ref)
+    part = of.apply_action(KIND[kt], KIND[ki], D, x, W3, m["dofmap"], bs, m["n_dofs"], *_geo(m), n_cells=nc // 2)
+    _close(forms.action(kt, ki, d_D, x, n_cells=nc // 2), part)
+
+
+def test_matrix_csr(ctx):
+    m = tri_case(nx=13, ny=9)
+    tab, forms = _mk(ctx, m, 2)
+    nc = m["dofmap"].shape[0]
+    rng = np.random.default_rng(6)
+    D = rng.normal(size=(nc, 3, 16))
+    rp, col = forms.set_pattern()
+    ref = of.assemble_matrix(ot.MANDEL_STRAIN, ot.MANDEL_STRAIN, D, W3, m["dofmap"], 2, m["n_dofs"], *_geo(m), rp, col)
+    d_D = ctx.to_device(D)
+    vals = forms.matrix("mandel_strain", "mandel_strain", d_D)
+    _close(vals.to_host(), ref)
+    forms.matrix("mandel_strain", "mandel_strain", d_D, vals=vals, accumulate=True)
+    _close(vals.to_host(), 2 * ref)
+    # the assembled matrix and the matrix-free action are the same operator
+    x = rng.normal(size=2 * m["n_dofs"])
+    rows = np.repeat(np.arange(rp.size - 1), np.diff(rp))
+    y = np.zeros_like(x)
+    np.add.at(y, rows, 0.5 * vals.to_host() * x[col])
+    _close(forms.action("mandel_strain", "mandel_strain", d_D, x), y, rtol=1e-11)
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_vm_residual_step(ctx, exact):
+    m = tri_case(nx=41, ny=29)
+    tab, forms = _mk(ctx, m, 2)
+    n = m["dofmap"].shape[0] * 3
+    rng = np.random.default_rng(7)
+    sigma_n, p = rng.normal(0.0, 100.0, (n, 4)), np.abs(rng.normal(0.0, 1e-3, n))
+    u = syn.smooth_displacement(m["dof_coords"], scale=3e-3, seed=3).reshape(-1)
+    vm = eo.VonMises(ctx=ctx, n_qp=n)
+    vm.set_history(sigma_n, p)
+    ctx.stats_reset()
+    b = forms.vm_residual(vm, u, exact=exact)
+    Ct, sig, dp = forms.C_tang.to_host(), vm.sigma_dev.to_host(), vm.dp_dev.to_host()
+    st = ctx.stats()
+    # per-point results: identical to the fused tabulate + von Mises kernel
+    vm2 = eo.VonMises(ctx=ctx, n_qp=n)
+    vm2.set_history(sigma_n, p)
+    Ct2 = tab.vm_fused(vm2, u, exact=exact).to_host()
+    assert np.array_equal(Ct, Ct2) and np.array_equal(sig, vm2.sigma_dev.to_host()) and np.array_equal(dp, vm2.dp_dev.to_host())
+    # ... and within 1e-12 of the oracle, flags bit-exact
+    eps = ot.tabulate(ot.MANDEL_STRAIN, u, m["dofmap"], 2, *_geo(m)).reshape(-1, 4)
+    rCt, rsig, rdp = oc.vm_return_mapping(eps, sigma_n, p)
+    assert np.array_equal(dp > 0, np.asarray(rdp).reshape(-1) > 0) and 0.2 < (dp > 0).mean() < 0.8
+    assert st["n_plastic"] == int((dp > 0).sum()) and st["n_points"] == n
+    _close(Ct, rCt, 1e-12), _close(sig, rsig, 1e-12)
+    _close(b, of.assemble_vector(ot.MANDEL_STRAIN, rsig, W3, m["dofmap"], 2, m["n_dofs"], *_geo(m)))
+    # residual step == separate stress integral; tangent action against the oracle with the kernel's own tangent
+    _close(forms.vector("mandel_strain", vm.sigma_dev), b)
+    x = rng.normal(size=u.size)
+    _close(forms.action("mandel_strain", "mandel_strain", forms.C_tang, x),
+           of.apply_action(ot.MANDEL_STRAIN, ot.MANDEL_STRAIN, Ct, x, W3, m["dofmap"], 2, m["n_dofs"], *_geo(m)))
+
+
+def test_errors_and_empty(ctx):
+    m = tri_case(nx=4, ny=3)
+    tab, forms = _mk(ctx, m, 2)
+    nc = m["dofmap"].shape[0]
+    with pytest.raises(ValueError):
+        eo.QuadratureForms(tab, np.ones(2))
+    with pytest.raises(TypeError):
+        forms.vector("grad", np.zeros((nc, 3, 4)))  # point values must be resident
+    with pytest.raises(ValueError):
+        forms.vector("grad", ctx.zeros((nc, 3, 3)))
+    with pytest.raises(ValueError):
+        forms.action("grad", "grad", ctx.zeros((nc, 3, 16)), np.zeros(5))
+    x = ctx.zeros((2 * m["n_dofs"],))
+    with pytest.raises(eo.EOError):
+        forms.action("grad", "grad", ctx.zeros((nc, 3, 16)), x, out=x)  # aliasing
+    with pytest.raises(eo.EOError):
+        ctx.check(ctx.lib.eo_form_matrix(forms._h, 1, 1, ctx.zeros((nc, 3, 16)).ptr, -1, x.ptr, 0))  # no pattern yet
+    b = forms.vector("grad", ctx.zeros((nc, 3, 4)), n_cells=0)
+    assert b.shape == (2 * m["n_dofs"],) and not b.any()
+    mt, ft = _mk(ctx, tri_case(nx=4, ny=3, degree=1), 1)
+    with pytest.raises(ValueError):
+        ft.vector("mandel_strain", ctx.zeros((10,)))
+
+
+def test_full_size_properties(ctx):
+    """1e7 points: adjointness with the tabulation kernel, rigid-body modes of the elastic stiffness."""
+    m = syn.triangle_mesh(1291, 1291, 2)  # 3 333 362 cells, 1.0e7 points
+    X = el.triangle_quadrature(2)
+    phi, dphi = el.lagrange_triangle(2, X)
+    m.update(phi=phi, dphi=dphi)
+    tab, forms = _mk(ctx, m, 2)
+    nc = m["dofmap"].shape[0]
+    n = nc * 3
+    rng = np.random.default_rng(8)
+    u = rng.normal(size=2 * m["n_dofs"])
+    s = rng.normal(size=(n, 4))
+    d_s = ctx.to_device(s)
+    eps = tab.evaluate("mandel_strain", u, output="host").reshape(n, 4)
+    area = 1.0 / (2 * 1291 * 1291)  # |det J| / 2 ... every cell is congruent: w_q |det J| = area / 3
+    lhs = (eps * s).sum() * area / 3.0
+    b = forms.vector("mandel_strain", d_s)
+    assert abs(lhs - u @ b) < 1e-11 * abs(lhs)
+    Ce = oc.elastic_stiffness(oc.VonMisesParams().lmbda, oc.VonMisesParams().mu)
+    d_D = ctx.to_device(np.broadcast_to(Ce.reshape(-1), (n, 16)).copy())
+    xy = m["dof_coords"]
+    scale = np.abs(forms.action("mandel_strain", "mandel_strain", d_D, u)).max()
+    rot = np.stack([-xy[:, 1], xy[:, 0]], 1).reshape(-1)
+    assert np.abs(forms.action("mandel_strain", "mandel_strain", d_D, rot)).max() < 1e-11 * scale
