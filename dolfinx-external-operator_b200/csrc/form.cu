@@ -68,6 +68,25 @@ __device__ __forceinline__ double form_geometry(const tab_tables& T, const int32
   return fabs(det);
 }
 
+// the cell's coefficients through the dofmap (read-only path; neighbouring cells / points share nodes: L1/L2 hits)
+template <int BS, int NB>
+__device__ __forceinline__ void form_gather(const int32_t* __restrict__ dofmap, const double* __restrict__ u, int64_t c,
+                                            double w[NB][BS]) {
+  int32_t idx[NB];
+#pragma unroll
+  for (int a = 0; a < NB; ++a) idx[a] = __ldg(dofmap + c * NB + a);
+#pragma unroll
+  for (int a = 0; a < NB; ++a) {
+    if constexpr (BS == 2) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(u) + idx[a]);
+      w[a][0] = v.x, w[a][1] = v.y;
+    } else {
+#pragma unroll
+      for (int k = 0; k < BS; ++k) w[a][k] = __ldg(u + int64_t(BS) * idx[a] + k);
+    }
+  }
+}
+
 // transpose of tab_operand: the point value s (ncomp of `kind`) as a cotangent of (value, gradient)
 template <int GDIM, int BS>
 __device__ __forceinline__ void form_cotangent(int kind, const double* s, double Vs[BS], double Gs[BS][GDIM]) {
@@ -93,15 +112,25 @@ __device__ __forceinline__ void form_cotangent(int kind, const double* s, double
   }
 }
 
+// table access for either home of the tables (constant bank: warp-uniform q; shared memory: per-thread q)
+__device__ __forceinline__ double form_phi(const tab_tables& T, int q, int a) { return T.phi[q][a]; }
+__device__ __forceinline__ double form_dphi(const tab_tables& T, int k, int q, int a) { return T.dphi[k][q][a]; }
+template <int GDIM, int NB>
+struct form_tabs;
+template <int GDIM, int NB>
+__device__ __forceinline__ double form_phi(const form_tabs<GDIM, NB>& S, int q, int a);
+template <int GDIM, int NB>
+__device__ __forceinline__ double form_dphi(const form_tabs<GDIM, NB>& S, int k, int q, int a);
+
 // fe[a][c] += scale * ( Vs[c] phi[q][a] + sum_k (sum_j Gs[c][j] K[k][j]) dphi[k][q][a] )   - transpose of tab_point
-template <int GDIM, int BS, int NB>
-__device__ __forceinline__ void form_accumulate(const tab_tables& T, int kind, int q, double scale, const double Vs[BS],
+template <int GDIM, int BS, int NB, class Tables>
+__device__ __forceinline__ void form_accumulate(const Tables& T, int kind, int q, double scale, const double Vs[BS],
                                                 const double Gs[BS][GDIM], const double K[GDIM][GDIM],
                                                 double fe[NB][BS]) {
   if (kind == 0) {
 #pragma unroll
     for (int a = 0; a < NB; ++a) {
-      const double ph = scale * T.phi[q][a];
+      const double ph = scale * form_phi(T, q, a);
 #pragma unroll
       for (int c = 0; c < BS; ++c) fe[a][c] += Vs[c] * ph;
     }
@@ -123,156 +152,243 @@ __device__ __forceinline__ void form_accumulate(const tab_tables& T, int kind, i
     for (int c = 0; c < BS; ++c) {
       double acc = 0.0;
 #pragma unroll
-      for (int k = 0; k < GDIM; ++k) acc += H[c][k] * T.dphi[k][q][a];
+      for (int k = 0; k < GDIM; ++k) acc += H[c][k] * form_dphi(T, k, q, a);
       fe[a][c] += acc;
     }
 }
 
-template <int BS, int NB>
-__device__ __forceinline__ void form_scatter(const int32_t idx[NB], const double fe[NB][BS], double* __restrict__ b) {
+// ------------------------------------------------------------------------------------------------------------
+// Mapping of the three integrals: one thread per QUADRATURE POINT, a CTA of FORM_THREADS threads covers
+// FORM_THREADS / nq consecutive cells (a cell never straddles CTAs).  The per-point streams (stress 32 B, tangent
+// 128 B, history, outputs) are then read and written exactly like in the streaming kernels - consecutive threads,
+// consecutive records, two dependent memory round trips per thread - and the nq threads of a cell gather the same
+// coefficients / geometry (same sectors: one L1 request).  Each thread turns its point's cotangent into its
+// contribution to the cell's nb*bs element-vector entries, parks it in shared memory (row stride nb*bs + 1: no bank
+// conflicts), and after a barrier the CTA's threads sum the nq contributions of each entry and issue ONE fp64
+// RED.ADD per element-vector entry (each DOF of a P2 triangle mesh is touched by 2-6 cells: low contention,
+// resolved in L2).  The CTA grid-strides over tiles of cells.
+// ------------------------------------------------------------------------------------------------------------
+#define FORM_THREADS 256
+
+// Element tables staged in shared memory: the point index differs between the threads of a warp, which the
+// constant bank would serialise (one pass per distinct address).
+template <int GDIM, int NB>
+struct form_tabs {
+  double phi[EO_TAB_MAX_NQ][NB];
+  double dphi[EO_TAB_MAX_NQ][GDIM][NB];
+};
+
+template <int GDIM, int NB>
+__device__ __forceinline__ void form_stage_tables(const tab_tables& T, form_tabs<GDIM, NB>& S) {
+  for (int t = threadIdx.x; t < T.nq * NB; t += blockDim.x) {
+    const int q = t / NB, a = t - q * NB;
+    S.phi[q][a] = T.phi[q][a];
 #pragma unroll
-  for (int a = 0; a < NB; ++a)
+    for (int k = 0; k < GDIM; ++k) S.dphi[q][k][a] = T.dphi[k][q][a];
+  }
+  __syncthreads();
+}
+
+template <int GDIM, int NB>
+__device__ __forceinline__ double form_phi(const form_tabs<GDIM, NB>& S, int q, int a) { return S.phi[q][a]; }
+template <int GDIM, int NB>
+__device__ __forceinline__ double form_dphi(const form_tabs<GDIM, NB>& S, int k, int q, int a) { return S.dphi[q][k][a]; }
+
+// tab_point with the tables in shared memory (same statement order: identical results)
+template <int GDIM, int BS, int NB>
+__device__ __forceinline__ void form_point(const form_tabs<GDIM, NB>& S, const double w[NB][BS], const double K[GDIM][GDIM],
+                                           int q, bool want_value, bool want_grad, double val[BS], double grad[BS][GDIM]) {
+  if (want_value) {
 #pragma unroll
-    for (int c = 0; c < BS; ++c) atomicAdd(b + int64_t(BS) * idx[a] + c, fe[a][c]);
+    for (int c = 0; c < BS; ++c) {
+      double acc = 0.0;
+#pragma unroll
+      for (int a = 0; a < NB; ++a) acc += w[a][c] * S.phi[q][a];
+      val[c] = acc;
+    }
+  }
+  if (want_grad) {
+    double G[BS][GDIM];
+#pragma unroll
+    for (int c = 0; c < BS; ++c)
+#pragma unroll
+      for (int k = 0; k < GDIM; ++k) {
+        double acc = 0.0;
+#pragma unroll
+        for (int a = 0; a < NB; ++a) acc += w[a][c] * S.dphi[q][k][a];
+        G[c][k] = acc;
+      }
+#pragma unroll
+    for (int c = 0; c < BS; ++c)
+#pragma unroll
+      for (int j = 0; j < GDIM; ++j) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < GDIM; ++k) acc += G[c][k] * K[k][j];
+        grad[c][j] = acc;
+      }
+  }
+}
+
+struct form_tile {
+  int64_t c;    // this thread's cell
+  int q;        // its point within the cell
+  bool active;  // false for the <= nq - 1 spare threads of the CTA and past the last cell
+};
+
+__device__ __forceinline__ form_tile form_locate(int nq, int cpb, int64_t tile, int64_t n_cells) {
+  const unsigned l = unsigned(threadIdx.x) / unsigned(nq);
+  form_tile t;
+  t.q = int(unsigned(threadIdx.x) - l * unsigned(nq));
+  t.c = tile * cpb + l;
+  t.active = int(l) < cpb && t.c < n_cells;
+  return t;
+}
+
+// this thread's contribution (cotangent tau of `kind` at point q, scaled) -> shared -> one RED per element entry
+template <int GDIM, int BS, int NB>
+__device__ __forceinline__ void form_reduce_scatter(const form_tabs<GDIM, NB>& S, int nq, int kind, const form_tile& t, double scale,
+                                                    const double* tau, const double K[GDIM][GDIM],
+                                                    const int32_t* __restrict__ dofmap, int64_t tile, int cpb,
+                                                    int64_t n_cells, double* __restrict__ b, double* s_fe) {
+  constexpr int ND = NB * BS;
+  if (t.active) {
+    double Vs[BS], Gs[BS][GDIM], fe[NB][BS];
+#pragma unroll
+    for (int a = 0; a < NB; ++a)
+#pragma unroll
+      for (int k = 0; k < BS; ++k) fe[a][k] = 0.0;
+    form_cotangent<GDIM, BS>(kind, tau, Vs, Gs);
+    form_accumulate<GDIM, BS, NB>(S, kind, t.q, scale, Vs, Gs, K, fe);
+    double* row = s_fe + threadIdx.x * (ND + 1);
+#pragma unroll
+    for (int a = 0; a < NB; ++a)
+#pragma unroll
+      for (int k = 0; k < BS; ++k) row[a * BS + k] = fe[a][k];
+  }
+  __syncthreads();
+  const int64_t c0 = tile * cpb;
+  const int cells_here = int((n_cells - c0) < cpb ? (n_cells - c0) : cpb);
+  for (int j = threadIdx.x; j < cells_here * ND; j += FORM_THREADS) {
+    const int l = j / ND, e = j - l * ND;
+    const double* row = s_fe + (l * nq) * (ND + 1) + e;
+    double acc = row[0];
+    for (int q = 1; q < nq; ++q) acc += row[q * (ND + 1)];
+    const int32_t node = __ldg(dofmap + (c0 + l) * NB + e / BS);
+    atomicAdd(b + int64_t(BS) * node + (e % BS), acc);
+  }
+  __syncthreads();  // the rows are rewritten by the next tile
 }
 
 // b += sum_q w_q |det J| B_q^T coef[c][q]
 template <int GDIM, int BS, int NB>
-__global__ void __launch_bounds__(128) form_vector_kernel(const __grid_constant__ tab_tables T,
-                                                          const __grid_constant__ form_weights W, int kind,
-                                                          const int32_t* __restrict__ dofmap,
-                                                          const int32_t* __restrict__ x_dofmap,
-                                                          const double* __restrict__ x, const double* __restrict__ coef,
-                                                          int64_t n_cells, double* __restrict__ b) {
-  const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-  if (c >= n_cells) return;
-  double K[GDIM][GDIM];
-  const double adet = form_geometry<GDIM>(T, x_dofmap, x, c, K);
-  int32_t idx[NB];
-#pragma unroll
-  for (int a = 0; a < NB; ++a) idx[a] = __ldg(dofmap + c * NB + a);
+__global__ void __launch_bounds__(FORM_THREADS) form_vector_kernel(const __grid_constant__ tab_tables T,
+                                                                   const __grid_constant__ form_weights W, int kind,
+                                                                   const int32_t* __restrict__ dofmap,
+                                                                   const int32_t* __restrict__ x_dofmap,
+                                                                   const double* __restrict__ x,
+                                                                   const double* __restrict__ coef, int64_t n_cells,
+                                                                   double* __restrict__ b) {
+  extern __shared__ double s_fe[];
+  __shared__ form_tabs<GDIM, NB> S;
+  form_stage_tables<GDIM, NB>(T, S);
+  const int cpb = FORM_THREADS / T.nq;
+  const int64_t tiles = (n_cells + cpb - 1) / cpb;
   const int ncomp = tab_ncomp(kind, BS, GDIM);
   const bool vec4 = ncomp == 4 && (reinterpret_cast<uintptr_t>(coef) % 32) == 0;
-  double fe[NB][BS];
-#pragma unroll
-  for (int a = 0; a < NB; ++a)
-#pragma unroll
-    for (int k = 0; k < BS; ++k) fe[a][k] = 0.0;
-  const double* s_ptr = coef + c * int64_t(T.nq) * ncomp;
-  for (int q = 0; q < T.nq; ++q) {
-    double s[BS * GDIM > 4 ? BS * GDIM : 4];
-    if (vec4) {
-      const eo_d4 v = eo_ld256(s_ptr + 4 * q);
-      s[0] = v.x, s[1] = v.y, s[2] = v.z, s[3] = v.w;
-    } else {
-      for (int k = 0; k < ncomp; ++k) s[k] = eo_ld64(s_ptr + q * ncomp + k);
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const form_tile t = form_locate(T.nq, cpb, tile, n_cells);
+    double K[GDIM][GDIM], s[BS * GDIM > 4 ? BS * GDIM : 4], scale = 0.0;
+    if (t.active) {
+      const double* sp = coef + (t.c * T.nq + t.q) * ncomp;
+      if (vec4) {
+        const eo_d4 v = eo_ld256(sp);
+        s[0] = v.x, s[1] = v.y, s[2] = v.z, s[3] = v.w;
+      } else {
+        for (int k = 0; k < ncomp; ++k) s[k] = eo_ld64(sp + k);
+      }
+      scale = W.w[t.q] * form_geometry<GDIM>(T, x_dofmap, x, t.c, K);
     }
-    double Vs[BS], Gs[BS][GDIM];
-    form_cotangent<GDIM, BS>(kind, s, Vs, Gs);
-    form_accumulate<GDIM, BS, NB>(T, kind, q, W.w[q] * adet, Vs, Gs, K, fe);
+    form_reduce_scatter<GDIM, BS, NB>(S, T.nq, kind, t, scale, s, K, dofmap, tile, cpb, n_cells, b, s_fe);
   }
-  form_scatter<BS, NB>(idx, fe, b);
 }
 
 // y += sum_q w_q |det J| B_test,q^T ( D[c][q] (B_trial,q x) ),   D row-major (ncomp_test, ncomp_trial) per point
 template <int GDIM, int BS, int NB>
-__global__ void __launch_bounds__(128) form_action_kernel(const __grid_constant__ tab_tables T,
-                                                          const __grid_constant__ form_weights W, int kind_test,
-                                                          int kind_trial, const int32_t* __restrict__ dofmap,
-                                                          const int32_t* __restrict__ x_dofmap,
-                                                          const double* __restrict__ x, const double* __restrict__ D,
-                                                          const double* __restrict__ xin, int64_t n_cells,
-                                                          double* __restrict__ y) {
-  const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-  if (c >= n_cells) return;
-  double K[GDIM][GDIM];
-  const double adet = form_geometry<GDIM>(T, x_dofmap, x, c, K);
-  int32_t idx[NB];
-#pragma unroll
-  for (int a = 0; a < NB; ++a) idx[a] = __ldg(dofmap + c * NB + a);
-  double w[NB][BS];
-#pragma unroll
-  for (int a = 0; a < NB; ++a) {
-    if constexpr (BS == 2) {
-      const double2 v = __ldg(reinterpret_cast<const double2*>(xin) + idx[a]);
-      w[a][0] = v.x, w[a][1] = v.y;
-    } else {
-#pragma unroll
-      for (int k = 0; k < BS; ++k) w[a][k] = __ldg(xin + int64_t(BS) * idx[a] + k);
-    }
-  }
+__global__ void __launch_bounds__(FORM_THREADS, (NB * BS <= 12 ? 3 : 1)) form_action_kernel(const __grid_constant__ tab_tables T,
+                                                                   const __grid_constant__ form_weights W, int kind_test,
+                                                                   int kind_trial, const int32_t* __restrict__ dofmap,
+                                                                   const int32_t* __restrict__ x_dofmap,
+                                                                   const double* __restrict__ x,
+                                                                   const double* __restrict__ D,
+                                                                   const double* __restrict__ xin, int64_t n_cells,
+                                                                   double* __restrict__ y) {
+  extern __shared__ double s_fe[];
+  __shared__ form_tabs<GDIM, NB> S;
+  form_stage_tables<GDIM, NB>(T, S);
   constexpr int MAXC = BS * GDIM > 4 ? BS * GDIM : 4;
+  const int cpb = FORM_THREADS / T.nq;
+  const int64_t tiles = (n_cells + cpb - 1) / cpb;
   const int nt = tab_ncomp(kind_test, BS, GDIM), ni = tab_ncomp(kind_trial, BS, GDIM);
   const bool vec44 = nt == 4 && ni == 4 && (reinterpret_cast<uintptr_t>(D) % 32) == 0;
-  double fe[NB][BS];
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const form_tile t = form_locate(T.nq, cpb, tile, n_cells);
+    double K[GDIM][GDIM], tau[MAXC], scale = 0.0;
+    if (t.active) {
+      const double* Dq = D + (t.c * T.nq + t.q) * int64_t(nt * ni);
+      double w[NB][BS];
+      form_gather<BS, NB>(dofmap, xin, t.c, w);
+      scale = W.w[t.q] * form_geometry<GDIM>(T, x_dofmap, x, t.c, K);
+      double val[BS], grad[BS][GDIM], e[MAXC];
+      form_point<GDIM, BS, NB>(S, w, K, t.q, kind_trial == 0, kind_trial != 0, val, grad);
+      tab_operand<GDIM, BS>(kind_trial, val, grad, e);
+      if (vec44) {
 #pragma unroll
-  for (int a = 0; a < NB; ++a)
-#pragma unroll
-    for (int k = 0; k < BS; ++k) fe[a][k] = 0.0;
-  const double* D_ptr = D + c * int64_t(T.nq) * nt * ni;
-  for (int q = 0; q < T.nq; ++q) {
-    double val[BS], grad[BS][GDIM], e[MAXC], tau[MAXC];
-    tab_point<GDIM, BS, NB>(T, w, K, q, kind_trial == 0, kind_trial != 0, val, grad);
-    tab_operand<GDIM, BS>(kind_trial, val, grad, e);
-    if (vec44) {
-      const double* Dq = D_ptr + 16 * q;
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const eo_d4 d = eo_ld256(Dq + 4 * r);
-        tau[r] = d.x * e[0] + d.y * e[1] + d.z * e[2] + d.w * e[3];
-      }
-    } else {
-      const double* Dq = D_ptr + int64_t(q) * nt * ni;
-      for (int r = 0; r < nt; ++r) {
-        double acc = 0.0;
-        for (int l = 0; l < ni; ++l) acc += eo_ld64(Dq + r * ni + l) * e[l];
-        tau[r] = acc;
+        for (int r = 0; r < 4; ++r) {
+          const eo_d4 d = eo_ld256(Dq + 4 * r);
+          tau[r] = d.x * e[0] + d.y * e[1] + d.z * e[2] + d.w * e[3];
+        }
+      } else {
+        for (int r = 0; r < nt; ++r) {
+          double acc = 0.0;
+          for (int l = 0; l < ni; ++l) acc += eo_ld64(Dq + r * ni + l) * e[l];
+          tau[r] = acc;
+        }
       }
     }
-    double Vs[BS], Gs[BS][GDIM];
-    form_cotangent<GDIM, BS>(kind_test, tau, Vs, Gs);
-    form_accumulate<GDIM, BS, NB>(T, kind_test, q, W.w[q] * adet, Vs, Gs, K, fe);
+    form_reduce_scatter<GDIM, BS, NB>(S, T.nq, kind_test, t, scale, tau, K, dofmap, tile, cpb, n_cells, y, s_fe);
   }
-  form_scatter<BS, NB>(idx, fe, y);
 }
 
 // One Newton residual evaluation of the von Mises problem without leaving the device:
 // Mandel strain of u -> radial return (C_tang, sigma, dp stored for the tangent action / the history commit)
 // -> b += int sigma . epsilon(v) dx.  The per-point arithmetic and its results are those of eo_tab_vm_fused.
 template <int NB, bool EXACT>
-__global__ void __launch_bounds__(128) form_vm_step_kernel(const __grid_constant__ tab_tables T,
-                                                           const __grid_constant__ form_weights W, const vm_consts vq,
-                                                           const int32_t* __restrict__ dofmap,
-                                                           const int32_t* __restrict__ x_dofmap,
-                                                           const double* __restrict__ x, const double* __restrict__ u,
-                                                           int64_t n_cells, const double* __restrict__ sigma_n,
-                                                           const double* __restrict__ p, double* __restrict__ C_tang,
-                                                           double* __restrict__ sigma, double* __restrict__ dp_out,
-                                                           double* __restrict__ b, eo_stats* stats) {
-  const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+__global__ void __launch_bounds__(FORM_THREADS, 3) form_vm_step_kernel(
+    const __grid_constant__ tab_tables T, const __grid_constant__ form_weights W, const vm_consts vq,
+    const int32_t* __restrict__ dofmap, const int32_t* __restrict__ x_dofmap, const double* __restrict__ x,
+    const double* __restrict__ u, int64_t n_cells, const double* __restrict__ sigma_n, const double* __restrict__ p,
+    double* __restrict__ C_tang, double* __restrict__ sigma, double* __restrict__ dp_out, double* __restrict__ b,
+    eo_stats* stats) {
+  extern __shared__ double s_fe[];
+  __shared__ form_tabs<2, NB> S;
+  form_stage_tables<2, NB>(T, S);
+  const int cpb = FORM_THREADS / T.nq;
+  const int64_t tiles = (n_cells + cpb - 1) / cpb;
   int plastic = 0;
-  if (c < n_cells) {
-    double K[2][2];
-    const double adet = form_geometry<2>(T, x_dofmap, x, c, K);
-    int32_t idx[NB];
-#pragma unroll
-    for (int a = 0; a < NB; ++a) idx[a] = __ldg(dofmap + c * NB + a);
-    double w[NB][2];
-#pragma unroll
-    for (int a = 0; a < NB; ++a) {
-      const double2 v = __ldg(reinterpret_cast<const double2*>(u) + idx[a]);
-      w[a][0] = v.x, w[a][1] = v.y;
-    }
-    double fe[NB][2];
-#pragma unroll
-    for (int a = 0; a < NB; ++a) fe[a][0] = 0.0, fe[a][1] = 0.0;
-    const int64_t i0 = c * T.nq;
-    for (int q = 0; q < T.nq; ++q) {
-      const int64_t i = i0 + q;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const form_tile t = form_locate(T.nq, cpb, tile, n_cells);
+    double K[2][2], g[4], scale = 0.0;
+    if (t.active) {
+      const int64_t i = t.c * T.nq + t.q;
+      // history first: these loads are in flight while the gather and the contraction run
       const eo_d4 s = eo_ld256(sigma_n + 4 * i);
       const double pi = eo_ld64(p + i);
+      double w[NB][2];
+      form_gather<2, NB>(dofmap, u, t.c, w);
+      scale = W.w[t.q] * form_geometry<2>(T, x_dofmap, x, t.c, K);
       double val[2] = {0.0, 0.0}, grad[2][2], e[4];
-      tab_point<2, 2, NB>(T, w, K, q, false, true, val, grad);
+      form_point<2, 2, NB>(S, w, K, t.q, false, true, val, grad);
       tab_operand<2, 2>(2, val, grad, e);
       vm_point_out o;
       if (EXACT)
@@ -287,11 +403,9 @@ __global__ void __launch_bounds__(128) form_vm_step_kernel(const __grid_constant
       eo_st256(Ct + 12, o.C[12], o.C[13], o.C[14], o.C[15]);
       eo_st256(sigma + 4 * i, o.g[0], o.g[1], o.g[2], o.g[3]);
       eo_st64(dp_out + i, o.dp);
-      double Vs[2], Gs[2][2];
-      form_cotangent<2, 2>(2, o.g, Vs, Gs);
-      form_accumulate<2, 2, NB>(T, 2, q, W.w[q] * adet, Vs, Gs, K, fe);
+      g[0] = o.g[0], g[1] = o.g[1], g[2] = o.g[2], g[3] = o.g[3];
     }
-    form_scatter<2, NB>(idx, fe, b);
+    form_reduce_scatter<2, 2, NB>(S, T.nq, 2, t, scale, g, K, dofmap, tile, cpb, n_cells, b, s_fe);
   }
   eo_block_sum_add(reinterpret_cast<unsigned long long*>(&stats->n_plastic), plastic);
   if (blockIdx.x == 0 && threadIdx.x == 0)
@@ -370,6 +484,25 @@ static int form_kind(int kind) { return kind == EO_OPERAND_DEF_GRAD ? EO_OPERAND
 
 #define EO_FORM_CASES(X) \
   X(2, 1, 3) X(2, 1, 6) X(2, 2, 3) X(2, 2, 6) X(2, 1, 10) X(2, 2, 10) X(3, 1, 4) X(3, 3, 4) X(3, 1, 10) X(3, 3, 10)
+
+#ifndef FORM_WAVES
+#define FORM_WAVES 8
+#endif
+// persistent-ish grid: a few waves of the resident CTAs, each grid-striding over tiles of FORM_THREADS / nq cells
+static unsigned form_grid(eo_ctx* ctx, const eo_tab* t, int64_t n_cells) {
+  const int cpb = FORM_THREADS / t->T.nq;
+  const int64_t tiles = (n_cells + cpb - 1) / cpb;
+  const int64_t cap = int64_t(ctx->sm_count) * 4 * FORM_WAVES;
+  return (unsigned)(tiles < cap ? tiles : cap);
+}
+
+// dynamic shared memory of the element-vector rows (FORM_THREADS rows of nd + 1 doubles); opt in above 48 KB
+template <class Kernel>
+static size_t form_smem(eo_ctx* ctx, Kernel k, int nd) {
+  const size_t bytes = size_t(FORM_THREADS) * (nd + 1) * sizeof(double);
+  if (bytes > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+  return bytes;
+}
 
 // result vector on the device side: the caller's (device) or the staging copy (host); zeroed unless accumulating
 static int form_result(eo_form* f, double* y, int accumulate, double** d_y) {
@@ -459,15 +592,16 @@ int eo_form_vector(eo_form* f, int kind_test, const double* coef, int64_t n_cell
   if (rc != EO_OK) return rc;
   const int kind = form_kind(kind_test);
   if (n_cells > 0) {
-    const unsigned grid = (unsigned)((n_cells + 127) / 128);
+    const unsigned grid = form_grid(ctx, t, n_cells);
     form_weights W;
     memcpy(W.w, f->w, sizeof(W.w));
     bool done = false;
-#define X(G, B, N)                                                                                              \
-  if (!done && t->T.gdim == G && t->T.bs == B && t->T.nb == N) {                                                \
-    form_vector_kernel<G, B, N><<<grid, 128, 0, ctx->s_cmp>>>(t->T, W, kind, t->dofmap, t->x_dofmap, t->x, coef, \
-                                                              n_cells, d_b);                                    \
-    done = true;                                                                                                \
+#define X(G, B, N)                                                                                                     \
+  if (!done && t->T.gdim == G && t->T.bs == B && t->T.nb == N) {                                                       \
+    const size_t sm = form_smem(ctx, form_vector_kernel<G, B, N>, N * B);                                              \
+    form_vector_kernel<G, B, N><<<grid, FORM_THREADS, sm, ctx->s_cmp>>>(t->T, W, kind, t->dofmap, t->x_dofmap, t->x, coef, \
+                                                                        n_cells, d_b);                                 \
+    done = true;                                                                                                       \
   }
     EO_FORM_CASES(X)
 #undef X
@@ -500,15 +634,16 @@ int eo_form_action(eo_form* f, int kind_test, int kind_trial, const double* D, c
   EO_REQUIRE(ctx, d_x != d_y, "eo_form_action: x and y must not alias");
   const int kt = form_kind(kind_test), ki = form_kind(kind_trial);
   if (n_cells > 0) {
-    const unsigned grid = (unsigned)((n_cells + 127) / 128);
+    const unsigned grid = form_grid(ctx, t, n_cells);
     form_weights W;
     memcpy(W.w, f->w, sizeof(W.w));
     bool done = false;
-#define X(G, B, N)                                                                                               \
-  if (!done && t->T.gdim == G && t->T.bs == B && t->T.nb == N) {                                                 \
-    form_action_kernel<G, B, N><<<grid, 128, 0, ctx->s_cmp>>>(t->T, W, kt, ki, t->dofmap, t->x_dofmap, t->x, D, d_x, \
-                                                              n_cells, d_y);                                     \
-    done = true;                                                                                                 \
+#define X(G, B, N)                                                                                                        \
+  if (!done && t->T.gdim == G && t->T.bs == B && t->T.nb == N) {                                                          \
+    const size_t sm = form_smem(ctx, form_action_kernel<G, B, N>, N * B);                                                 \
+    form_action_kernel<G, B, N><<<grid, FORM_THREADS, sm, ctx->s_cmp>>>(t->T, W, kt, ki, t->dofmap, t->x_dofmap, t->x, D, d_x, \
+                                                                        n_cells, d_y);                                    \
+    done = true;                                                                                                          \
   }
     EO_FORM_CASES(X)
 #undef X
@@ -544,17 +679,22 @@ int eo_form_vm_step(eo_form* f, const eo_vm_params* prm, const double* u, const 
   if (rc != EO_OK) return rc;
   if (n_cells > 0) {
     const vm_consts q{prm->lmbda, prm->mu, prm->H, prm->sigma_0};
-    const unsigned grid = (unsigned)((n_cells + 127) / 128);
+    const unsigned grid = form_grid(ctx, t, n_cells);
     form_weights W;
     memcpy(W.w, f->w, sizeof(W.w));
-#define EO_STEP(N)                                                                                                     \
-  if (t->T.nb == N) {                                                                                                  \
-    if (exact)                                                                                                         \
-      form_vm_step_kernel<N, true><<<grid, 128, 0, ctx->s_cmp>>>(t->T, W, q, t->dofmap, t->x_dofmap, t->x, d_u, n_cells, \
-                                                                 sigma_n, p, C_tang, sigma, dp, d_b, ctx->stats);      \
-    else                                                                                                               \
-      form_vm_step_kernel<N, false><<<grid, 128, 0, ctx->s_cmp>>>(t->T, W, q, t->dofmap, t->x_dofmap, t->x, d_u,        \
-                                                                  n_cells, sigma_n, p, C_tang, sigma, dp, d_b, ctx->stats); \
+#define EO_STEP(N)                                                                                                        \
+  if (t->T.nb == N) {                                                                                                     \
+    if (exact) {                                                                                                          \
+      const size_t sm = form_smem(ctx, form_vm_step_kernel<N, true>, N * 2);                                              \
+      form_vm_step_kernel<N, true><<<grid, FORM_THREADS, sm, ctx->s_cmp>>>(t->T, W, q, t->dofmap, t->x_dofmap, t->x, d_u,  \
+                                                                           n_cells, sigma_n, p, C_tang, sigma, dp, d_b,   \
+                                                                           ctx->stats);                                   \
+    } else {                                                                                                              \
+      const size_t sm = form_smem(ctx, form_vm_step_kernel<N, false>, N * 2);                                             \
+      form_vm_step_kernel<N, false><<<grid, FORM_THREADS, sm, ctx->s_cmp>>>(t->T, W, q, t->dofmap, t->x_dofmap, t->x, d_u, \
+                                                                            n_cells, sigma_n, p, C_tang, sigma, dp, d_b,  \
+                                                                            ctx->stats);                                  \
+    }                                                                                                                     \
   }
     EO_STEP(3)
     EO_STEP(6)

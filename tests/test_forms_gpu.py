@@ -128,7 +128,7 @@ def test_vm_residual_step(ctx, exact):
     n = m["dofmap"].shape[0] * 3
     rng = np.random.default_rng(7)
     sigma_n, p = rng.normal(0.0, 100.0, (n, 4)), np.abs(rng.normal(0.0, 1e-3, n))
-    u = syn.smooth_displacement(m["dof_coords"], scale=3e-3, seed=3).reshape(-1)
+    u = syn.smooth_displacement(m["dof_coords"], scale=6e-4, seed=3).reshape(-1)  # ~50 % plastic points
     vm = eo.VonMises(ctx=ctx, n_qp=n)
     vm.set_history(sigma_n, p)
     ctx.stats_reset()
