@@ -22,6 +22,8 @@
 #include "tab_handle.cuh"
 #include "vm_core.cuh"
 
+#include <cstdlib>
+
 struct eo_form {
   eo_tab* tab = nullptr;
   double w[EO_TAB_MAX_NQ];   // quadrature weights on the reference cell
@@ -313,56 +315,165 @@ __global__ void __launch_bounds__(FORM_THREADS) form_vector_kernel(const __grid_
   }
 }
 
-// y += sum_q w_q |det J| B_test,q^T ( D[c][q] (B_trial,q x) ),   D row-major (ncomp_test, ncomp_trial) per point
-template <int GDIM, int BS, int NB>
-__global__ void __launch_bounds__(FORM_THREADS, (NB * BS <= 12 ? 3 : 1)) form_action_kernel(const __grid_constant__ tab_tables T,
-                                                                   const __grid_constant__ form_weights W, int kind_test,
-                                                                   int kind_trial, const int32_t* __restrict__ dofmap,
-                                                                   const int32_t* __restrict__ x_dofmap,
-                                                                   const double* __restrict__ x,
-                                                                   const double* __restrict__ D,
-                                                                   const double* __restrict__ xin, int64_t n_cells,
-                                                                   double* __restrict__ y) {
-  extern __shared__ double s_fe[];
-  __shared__ form_tabs<GDIM, NB> S;
-  form_stage_tables<GDIM, NB>(T, S);
+// y += sum_q w_q |det J| B_test,q^T ( D[c][q] (B_trial,q x) ),   D row-major (ncomp_test, ncomp_trial) per point.
+// One thread per CELL: it gathers once and walks its nq points (NQ > 0: unrolled, all tangent loads of the cell are
+// issued up front).  Measured against the per-point mapping of the other two integrals (which gathers nq times and
+// pays the shared-memory reduction): 3.8 ms vs 4.8 ms per 1e8 points - both are bound by the LSU wavefront rate
+// (~0.7 / clk / SM), not by HBM.  General fallback of the TMA-staged kernel below.
+template <int GDIM, int BS, int NB, int NQ>
+__global__ void __launch_bounds__(128) form_action_cell_kernel(const __grid_constant__ tab_tables T,
+                                                               const __grid_constant__ form_weights W, int kind_test,
+                                                               int kind_trial, const int32_t* __restrict__ dofmap,
+                                                               const int32_t* __restrict__ x_dofmap,
+                                                               const double* __restrict__ x, const double* __restrict__ D,
+                                                               const double* __restrict__ xin, int64_t n_cells,
+                                                               double* __restrict__ y) {
+  const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (c >= n_cells) return;
   constexpr int MAXC = BS * GDIM > 4 ? BS * GDIM : 4;
-  const int cpb = FORM_THREADS / T.nq;
-  const int64_t tiles = (n_cells + cpb - 1) / cpb;
+  const int nq = NQ > 0 ? NQ : T.nq;
   const int nt = tab_ncomp(kind_test, BS, GDIM), ni = tab_ncomp(kind_trial, BS, GDIM);
   const bool vec44 = nt == 4 && ni == 4 && (reinterpret_cast<uintptr_t>(D) % 32) == 0;
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const form_tile t = form_locate(T.nq, cpb, tile, n_cells);
-    double K[GDIM][GDIM], tau[MAXC], scale = 0.0;
-    if (t.active) {
-      const double* Dq = D + (t.c * T.nq + t.q) * int64_t(nt * ni);
-      double w[NB][BS];
-      form_gather<BS, NB>(dofmap, xin, t.c, w);
-      scale = W.w[t.q] * form_geometry<GDIM>(T, x_dofmap, x, t.c, K);
-      double val[BS], grad[BS][GDIM], e[MAXC];
-      form_point<GDIM, BS, NB>(S, w, K, t.q, kind_trial == 0, kind_trial != 0, val, grad);
-      tab_operand<GDIM, BS>(kind_trial, val, grad, e);
-      if (vec44) {
+  const double* D_ptr = D + c * int64_t(nq) * nt * ni;
+  eo_d4 d[NQ > 0 ? NQ : 1][4];
+  if (NQ > 0 && vec44) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const eo_d4 d = eo_ld256(Dq + 4 * r);
-          tau[r] = d.x * e[0] + d.y * e[1] + d.z * e[2] + d.w * e[3];
-        }
-      } else {
-        for (int r = 0; r < nt; ++r) {
-          double acc = 0.0;
-          for (int l = 0; l < ni; ++l) acc += eo_ld64(Dq + r * ni + l) * e[l];
-          tau[r] = acc;
-        }
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) d[q][r] = eo_ld256(D_ptr + 16 * q + 4 * r);
+  }
+  double K[GDIM][GDIM];
+  const double adet = form_geometry<GDIM>(T, x_dofmap, x, c, K);
+  int32_t idx[NB];
+#pragma unroll
+  for (int a = 0; a < NB; ++a) idx[a] = __ldg(dofmap + c * NB + a);
+  double w[NB][BS];
+#pragma unroll
+  for (int a = 0; a < NB; ++a) {
+    if constexpr (BS == 2) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(xin) + idx[a]);
+      w[a][0] = v.x, w[a][1] = v.y;
+    } else {
+#pragma unroll
+      for (int k = 0; k < BS; ++k) w[a][k] = __ldg(xin + int64_t(BS) * idx[a] + k);
+    }
+  }
+  double fe[NB][BS];
+#pragma unroll
+  for (int a = 0; a < NB; ++a)
+#pragma unroll
+    for (int k = 0; k < BS; ++k) fe[a][k] = 0.0;
+#pragma unroll
+  for (int q = 0; q < nq; ++q) {
+    double val[BS], grad[BS][GDIM], e[MAXC], tau[MAXC];
+    tab_point<GDIM, BS, NB>(T, w, K, q, kind_trial == 0, kind_trial != 0, val, grad);
+    tab_operand<GDIM, BS>(kind_trial, val, grad, e);
+    if (vec44) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const eo_d4 dd = NQ > 0 ? d[NQ > 0 ? q : 0][r] : eo_ld256(D_ptr + 16 * q + 4 * r);
+        tau[r] = dd.x * e[0] + dd.y * e[1] + dd.z * e[2] + dd.w * e[3];
+      }
+    } else {
+      const double* Dq = D_ptr + int64_t(q) * nt * ni;
+      for (int r = 0; r < nt; ++r) {
+        double acc = 0.0;
+        for (int l = 0; l < ni; ++l) acc += eo_ld64(Dq + r * ni + l) * e[l];
+        tau[r] = acc;
       }
     }
-    form_reduce_scatter<GDIM, BS, NB>(S, T.nq, kind_test, t, scale, tau, K, dofmap, tile, cpb, n_cells, y, s_fe);
+    double Vs[BS], Gs[BS][GDIM];
+    form_cotangent<GDIM, BS>(kind_test, tau, Vs, Gs);
+    form_accumulate<GDIM, BS, NB>(T, kind_test, q, W.w[q] * adet, Vs, Gs, K, fe);
   }
+#pragma unroll
+  for (int a = 0; a < NB; ++a)
+#pragma unroll
+    for (int k = 0; k < BS; ++k) atomicAdd(y + int64_t(BS) * idx[a] + k, fe[a][k]);
+}
+
+// Per-cell action with the tangent staged by the TMA unit: every thread asks for ITS cell's NQ contiguous 4x4 tangents
+// (NQ * 128 B) with one 1-D bulk copy into a padded shared-memory row (row stride NQ * 128 + 16 B: the 16-byte reads
+// of 8 consecutive lanes then cover all 32 banks), completion on one mbarrier per CTA.  The copies bypass the LSU - whose
+// wavefront rate, not HBM, bounds the register-path kernels: a warp-wide 256-bit load of 128-byte records touches 32
+// lines per instruction - and are in flight while the thread gathers its coefficients and geometry.
+template <int NB, int NQ>
+__global__ void __launch_bounds__(128) form_action_tma_kernel(const __grid_constant__ tab_tables T,
+                                                              const __grid_constant__ form_weights W,
+                                                              const int32_t* __restrict__ dofmap,
+                                                              const int32_t* __restrict__ x_dofmap,
+                                                              const double* __restrict__ x, const double* __restrict__ D,
+                                                              const double* __restrict__ xin, int64_t n_cells,
+                                                              double* __restrict__ y) {
+  extern __shared__ __align__(128) unsigned char form_smem_raw[];
+  constexpr unsigned CELL_B = NQ * 128, ROW_B = CELL_B + 16;
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(form_smem_raw);
+  const unsigned rows = bar + 128;
+  const int64_t c0 = blockIdx.x * int64_t(128);
+  const int64_t c = c0 + threadIdx.x;
+  const unsigned cells_here = (unsigned)((n_cells - c0) < 128 ? (n_cells - c0) : 128);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (c < n_cells)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     rows + threadIdx.x * ROW_B),
+                 "l"(D + c * int64_t(NQ) * 16), "r"(CELL_B), "r"(bar)
+                 : "memory");
+  if (threadIdx.x == 0)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(cells_here * CELL_B) : "memory");
+  double K[2][2], w[NB][2], adet = 0.0;
+  int32_t idx[NB];
+  if (c < n_cells) {
+    adet = form_geometry<2>(T, x_dofmap, x, c, K);
+#pragma unroll
+    for (int a = 0; a < NB; ++a) idx[a] = __ldg(dofmap + c * NB + a);
+#pragma unroll
+    for (int a = 0; a < NB; ++a) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(xin) + idx[a]);
+      w[a][0] = v.x, w[a][1] = v.y;
+    }
+  }
+  unsigned done = 0;
+  while (!done)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done)
+                 : "r"(bar)
+                 : "memory");
+  if (c >= n_cells) return;
+  double fe[NB][2];
+#pragma unroll
+  for (int a = 0; a < NB; ++a) fe[a][0] = 0.0, fe[a][1] = 0.0;
+  const unsigned my = rows + threadIdx.x * ROW_B;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    double val[2] = {0.0, 0.0}, grad[2][2], e[4], tau[4];
+    tab_point<2, 2, NB>(T, w, K, q, false, true, val, grad);
+    tab_operand<2, 2>(2, val, grad, e);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      double d0, d1, d2, d3;
+      asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(d0), "=d"(d1) : "r"(my + q * 128 + r * 32));
+      asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(d2), "=d"(d3) : "r"(my + q * 128 + r * 32 + 16));
+      tau[r] = d0 * e[0] + d1 * e[1] + d2 * e[2] + d3 * e[3];
+    }
+    double Vs[2], Gs[2][2];
+    form_cotangent<2, 2>(2, tau, Vs, Gs);
+    form_accumulate<2, 2, NB>(T, 2, q, W.w[q] * adet, Vs, Gs, K, fe);
+  }
+#pragma unroll
+  for (int a = 0; a < NB; ++a)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) atomicAdd(y + 2 * int64_t(idx[a]) + k, fe[a][k]);
 }
 
 // One Newton residual evaluation of the von Mises problem without leaving the device:
 // Mandel strain of u -> radial return (C_tang, sigma, dp stored for the tangent action / the history commit)
 // -> b += int sigma . epsilon(v) dx.  The per-point arithmetic and its results are those of eo_tab_vm_fused.
+// (A per-cell variant with TMA bulk stores of tangent and stress - the analogue of form_action_tma_kernel - was measured
+// slower, 6.6 vs 5.8 ms per 1e8 points: 160 registers leave 12 warps per SM for the division-heavy radial return.)
 template <int NB, bool EXACT>
 __global__ void __launch_bounds__(FORM_THREADS, 3) form_vm_step_kernel(
     const __grid_constant__ tab_tables T, const __grid_constant__ form_weights W, const vm_consts vq,
@@ -484,6 +595,12 @@ static int form_kind(int kind) { return kind == EO_OPERAND_DEF_GRAD ? EO_OPERAND
 
 #define EO_FORM_CASES(X) \
   X(2, 1, 3) X(2, 1, 6) X(2, 2, 3) X(2, 2, 6) X(2, 1, 10) X(2, 2, 10) X(3, 1, 4) X(3, 3, 4) X(3, 1, 10) X(3, 3, 10)
+
+// tuning switches (A/B measurements; defaults are the measured best)
+static int form_env(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
 
 #ifndef FORM_WAVES
 #define FORM_WAVES 8
@@ -634,16 +751,28 @@ int eo_form_action(eo_form* f, int kind_test, int kind_trial, const double* D, c
   EO_REQUIRE(ctx, d_x != d_y, "eo_form_action: x and y must not alias");
   const int kt = form_kind(kind_test), ki = form_kind(kind_trial);
   if (n_cells > 0) {
-    const unsigned grid = form_grid(ctx, t, n_cells);
     form_weights W;
     memcpy(W.w, f->w, sizeof(W.w));
     bool done = false;
-#define X(G, B, N)                                                                                                        \
-  if (!done && t->T.gdim == G && t->T.bs == B && t->T.nb == N) {                                                          \
-    const size_t sm = form_smem(ctx, form_action_kernel<G, B, N>, N * B);                                                 \
-    form_action_kernel<G, B, N><<<grid, FORM_THREADS, sm, ctx->s_cmp>>>(t->T, W, kt, ki, t->dofmap, t->x_dofmap, t->x, D, d_x, \
-                                                                        n_cells, d_y);                                    \
-    done = true;                                                                                                          \
+    // TMA-staged kernel for the 4x4 tangent of the plasticity demos (EO_FORM_ACTION_TMA=0: register-path kernel, for A/B)
+    const bool tma = form_env("EO_FORM_ACTION_TMA", 1) && t->T.gdim == 2 && t->T.bs == 2 && t->T.nq == 3 && kt == 2 && ki == 2 &&
+                     eo_aligned(D, 32);
+    const unsigned gc = (unsigned)((n_cells + 127) / 128);
+#define X(G, B, N)                                                                                                       \
+  if (!done && t->T.gdim == G && t->T.bs == B && t->T.nb == N) {                                                         \
+    if (tma) {                                                                                                           \
+      const size_t sm = 128 + 128 * (3 * 128 + 16);                                                                      \
+      auto kfn = form_action_tma_kernel<(G == 2 && B == 2 ? N : 3), 3>;                                                  \
+      cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm));                                   \
+      kfn<<<gc, 128, sm, ctx->s_cmp>>>(t->T, W, t->dofmap, t->x_dofmap, t->x, D, d_x, n_cells, d_y);                     \
+    } else if (t->T.nq == 3) {                                                                                           \
+      form_action_cell_kernel<G, B, N, 3><<<gc, 128, 0, ctx->s_cmp>>>(t->T, W, kt, ki, t->dofmap, t->x_dofmap, t->x, D,   \
+                                                                      d_x, n_cells, d_y);                                \
+    } else {                                                                                                             \
+      form_action_cell_kernel<G, B, N, 0><<<gc, 128, 0, ctx->s_cmp>>>(t->T, W, kt, ki, t->dofmap, t->x_dofmap, t->x, D,   \
+                                                                      d_x, n_cells, d_y);                                \
+    }                                                                                                                    \
+    done = true;                                                                                                         \
   }
     EO_FORM_CASES(X)
 #undef X
