@@ -127,7 +127,10 @@ def solve(mesh, backend, n_steps: int = 20, max_load: float = 1.1, rtol: float =
     out = {"load": loads / Q_LIM, "u_probe": np.zeros(n_steps), "newton_iterations": np.zeros(n_steps, dtype=int),
            "residual_histories": [], "plastic_fraction": np.zeros(n_steps)}
     for k, q in enumerate(loads):
-        Du = np.full(n, np.finfo(np.float64).eps)  # :551 (sigma_eq = 0 would be 0/0 in the radial return, :317)
+        # :551 sets Du = eps so that sigma_eq != 0 (0/0 in the radial return, :317).  A CONSTANT field has zero strain in
+        # exact arithmetic - the demo lives on the rounding residue of sum_a dphi_a - so the seed here is eps * (1 + x):
+        # strain eps * I whatever the summation order.
+        Du = np.finfo(np.float64).eps * (1.0 + mesh["dof_coords"]).reshape(-1)
         Du[mesh["fixed"]] = 0.0
         hist = []
         for it in range(max_it + 1):
@@ -138,6 +141,8 @@ def solve(mesh, backend, n_steps: int = 20, max_load: float = 1.1, rtol: float =
                 break
             if it == max_it:
                 raise RuntimeError(f"Newton did not converge at load step {k}: {hist}")
+            if not np.isfinite(nrm):
+                raise RuntimeError(f"non-finite residual at load step {k}, iteration {it}")
             A = sp.csr_matrix((backend.tangent_csr(), col, row_ptr), shape=(n, n))
             Du[free] -= splu(A[free][:, free].tocsc()).solve(r[free])
         out["plastic_fraction"][k] = backend.plastic_fraction()
