@@ -133,6 +133,28 @@ class QuadratureForms:
                                       int(bool(accumulate)), int(bool(exact))))
         return out
 
+    def mc_residual(self, mc, u=None, out=None, n_cells=None, accumulate=False, output="host"):
+        """The Mohr-Coulomb counterpart of `vm_residual` (demo_plasticity_mohr_coulomb.py:679-688 + assemble_vector):
+        Mandel strain of `u` -> local Newton return mapping (`mc`: a resident-history `MohrCoulomb`; tangent and stress
+        stay in HBM as `self.C_tang`, `mc.sigma_dev`) -> b = int sigma . eps(v) dx.  Three launches (tabulation, the
+        two-pass Mohr-Coulomb kernels, the stress integral): the model is FP64-pipe bound, fusing would not pay."""
+        t = self.tab
+        n = t.n_cells * t.nq
+        if mc.n_qp is None:
+            mc._alloc_state(n)
+        if mc.n_qp != n:
+            raise ValueError(f"mesh has {n} quadrature points, the resident history {mc.n_qp}")
+        c = self.ctx
+        if self.C_tang is None or self.C_tang.size != 16 * n:
+            self.C_tang = c.empty((16 * n,))
+        if getattr(self, "_strain", None) is None or self._strain.size != 4 * n:
+            self._strain = c.empty((t.n_cells, t.nq, 4))
+        t.evaluate("mandel_strain", u, out=self._strain)
+        c.stats_reset()
+        c.check(c.lib.eo_mc_eval(c.handle, C.byref(mc._prm), self._strain.ptr, mc.sigma_n_dev.ptr, self.C_tang.ptr,
+                                 mc.sigma_dev.ptr, None, None, None, None, n))
+        return self.vector("mandel_strain", mc.sigma_dev, out=out, n_cells=n_cells, accumulate=accumulate, output=output)
+
     # ------------------------------------------------------------------ assembled matrix (CSR on the device)
     def set_pattern(self, row_ptr=None, col=None):
         """CSR pattern over scalar dofs; default: every pair of dofs sharing a cell (what DOLFINx's

@@ -1,2 +1,1 @@
 python -m pytest tests/test_forms_gpu.py tests/test_cylinder_gpu.py -m gpu -q 2>&1 | tail -5
-python examples/thick_walled_cylinder.py 20 64 2>&1 | tail -24

@@ -154,6 +154,32 @@ def test_vm_residual_step(ctx, exact):
            of.apply_action(ot.MANDEL_STRAIN, ot.MANDEL_STRAIN, Ct, x, W3, m["dofmap"], 2, m["n_dofs"], *_geo(m)))
 
 
+def test_mc_residual_step(ctx):
+    """Mohr-Coulomb: tabulate -> local Newton -> stress integral on the device vs the oracle chain (1e-10: Newton model)."""
+    from oracle import native
+
+    m = tri_case(nx=23, ny=17)
+    tab, forms = _mk(ctx, m, 2)
+    n = m["dofmap"].shape[0] * 3
+    mprm = oc.MohrCoulombParams()
+    _, sigma_n = syn.mc_batch(n, seed=5, stepper=lambda d, s: native.mc_stress(d, s, mprm, parallel=True)[0])
+    u = syn.smooth_displacement(m["dof_coords"], scale=2e-6, seed=3).reshape(-1)
+    mc = eo.MohrCoulomb(ctx=ctx, n_qp=n)
+    mc.set_history(sigma_n)
+    b = forms.mc_residual(mc, u)
+    eps = ot.tabulate(ot.MANDEL_STRAIN, u, m["dofmap"], 2, *_geo(m)).reshape(-1, 4)
+    ref = native.mc_return_mapping(eps, sigma_n, mprm, parallel=True)
+    assert 0.05 < (np.asarray(ref["yielding"]) > 0).mean() < 0.95 and int(np.max(ref["niter"])) < 20
+    _close(mc.sigma_dev.to_host(), ref["sigma"], 1e-10)
+    _close(b, of.assemble_vector(ot.MANDEL_STRAIN, ref["sigma"], W3, m["dofmap"], 2, m["n_dofs"], *_geo(m)), 1e-10)
+    x = np.random.default_rng(1).normal(size=u.size)
+    Ct = forms.C_tang.to_host()
+    _close(forms.action("mandel_strain", "mandel_strain", forms.C_tang, x),
+           of.apply_action(ot.MANDEL_STRAIN, ot.MANDEL_STRAIN, Ct, x, W3, m["dofmap"], 2, m["n_dofs"], *_geo(m)))
+    mc.commit()
+    _close(mc.sigma_n_dev.to_host(), ref["sigma"], 1e-10)
+
+
 def test_errors_and_empty(ctx):
     m = tri_case(nx=4, ny=3)
     tab, forms = _mk(ctx, m, 2)
