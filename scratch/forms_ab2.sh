@@ -1,7 +1,7 @@
 #!/bin/bash
 B="--n 1e8 --steps 10 --cpu-seconds 0 --e2e-n 0"
 run() { name=$1; model=$2; shift 2
-  extra=""; if [ "${@: -2:1}" = "--" ]; then extra="${@: -1}"; set -- "${@:1:$#-2}"; fi; env "$@" python bench.py --model $model $B $extra > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err
+  env "$@" python bench.py --model $model $B > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err
   python - <<PY
 import json
 try:
@@ -11,9 +11,6 @@ except Exception as e:
     print("$name ERR", e, open('gpurun_out/ab_$name.err').read()[-400:])
 PY
 }
-timeout 300 python -m pytest tests/test_forms_gpu.py -m gpu -q 2>&1 | tail -3
-EO_FORM_STEP_TMA=0 EO_FORM_ACTION_TMA=0 timeout 300 python -m pytest tests/test_forms_gpu.py -m gpu -q 2>&1 | tail -3
-run step_tma step EO_FORM_STEP_TMA=1
-run step_tma_exact step EO_FORM_STEP_TMA=1 -- --fused-exact
-run step_point step EO_FORM_STEP_TMA=0
-run action_tma action EO_FORM_ACTION_TMA=1
+timeout 300 python -m pytest tests/test_forms_gpu.py tests/test_cylinder_gpu.py -m gpu -q 2>&1 | tail -3
+run action_tma2 action EO_FORM_ACTION_TMA2=1
+run action_tma1 action EO_FORM_ACTION_TMA2=0
