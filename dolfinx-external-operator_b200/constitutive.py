@@ -468,6 +468,17 @@ class HeatFlux(_ModelBase):
         c.sync()
         return out
 
+    def eval_device(self, T: DeviceArray, sigma: DeviceArray, q: DeviceArray | None = None,
+                    dqdT: DeviceArray | None = None, dqdsigma: DeviceArray | None = None):
+        """All-device evaluation (asynchronous on the ctx stream) of any subset of q (2/pt), dq/dT (2/pt), dq/dsigma
+        (4/pt, row-major 2x2) - for device-side consumers (`QuadratureForms.vector / .action / .matrix`)."""
+        n = T.size
+        if sigma.size != 2 * n:
+            raise ValueError("sigma must hold 2 components per quadrature point")
+        c = self.ctx
+        c.check(c.lib.eo_heat_eval(c.handle, self.A, self.B, T.ptr, sigma.ptr, None, None, _ptr(q), _ptr(dqdT),
+                                   _ptr(dqdsigma), n))
+
     def q_impl(self, T, sigma):
         return self._run(T, sigma, "q")
 

@@ -180,6 +180,36 @@ def test_mc_residual_step(ctx):
     _close(mc.sigma_n_dev.to_host(), ref["sigma"], 1e-10)
 
 
+def test_heat_demo_forms_match_the_explicit_forms(ctx):
+    """demo_nonlinear_heat_equation_part2.py:283-300 on the device: tabulate T and grad T, evaluate q / dq/dT / dq/dsigma
+    (eo_heat_eval), integrate b = int q . grad(v) and assemble J (test grad x trial value + test grad x trial grad) into
+    CSR; compared like the reference does with the explicit ("pure UFL") forms, and with the oracle chain."""
+    from heat_util import explicit_heat_forms
+    from test_heat_forms_cpu import dense, heat_case, oracle_heat_forms
+
+    m, T = heat_case()
+    tab, forms = _mk(ctx, m, 1)
+    nc = m["dofmap"].shape[0]
+    d_T = ctx.to_device(T)
+    Tq, sq = tab.evaluate("value", d_T), tab.evaluate("grad", d_T)
+    q, dT, ds = ctx.empty((nc, 3, 2)), ctx.empty((nc, 3, 2)), ctx.empty((nc, 3, 4))
+    eo.HeatFlux(ctx=ctx).eval_device(Tq, sq, q, dT, ds)
+    b = forms.vector("grad", q)
+    rp, col = forms.set_pattern()
+    vals = forms.matrix("grad", "value", dT)
+    forms.matrix("grad", "grad", ds, vals=vals, accumulate=True)
+    b_ex, A_ex = explicit_heat_forms(m, T)
+    _close(b, b_ex), _close(dense(vals.to_host(), rp, col), A_ex)
+    b_or, v_or, rp2, col2 = oracle_heat_forms(m, T)
+    assert np.array_equal(rp, rp2) and np.array_equal(col, col2)
+    _close(b, b_or), _close(vals.to_host(), v_or)
+    # the same Jacobian matrix-free: two accumulated actions
+    x = np.random.default_rng(2).normal(size=T.size)
+    y = forms.action("grad", "value", dT, x)
+    forms.action("grad", "grad", ds, x, out=y, accumulate=True)
+    _close(y, A_ex @ x, 1e-11)
+
+
 def test_errors_and_empty(ctx):
     m = tri_case(nx=4, ny=3)
     tab, forms = _mk(ctx, m, 2)
