@@ -19,6 +19,7 @@
 // HBM-bound: residual 32 B/point + ~45 B/cell of index/geometry traffic; action 128 B/point + the same.
 #include "eo_common.cuh"
 #include "tab_core.cuh"
+#include "form_core.cuh"
 #include "tab_handle.cuh"
 #include "vm_core.cuh"
 
@@ -39,7 +40,7 @@ struct form_weights {
   double w[EO_TAB_MAX_NQ];
 };
 
-// inverse Jacobian AND |det J| of one affine cell
+// inverse Jacobian AND |det J| of one affine cell (vertex coordinates through the read-only path)
 template <int GDIM>
 __device__ __forceinline__ double form_geometry(const tab_tables& T, const int32_t* __restrict__ x_dofmap,
                                                 const double* __restrict__ x, int64_t c, double K[GDIM][GDIM]) {
@@ -50,24 +51,7 @@ __device__ __forceinline__ double form_geometry(const tab_tables& T, const int32
 #pragma unroll
     for (int i = 0; i < GDIM; ++i) xv[v][i] = __ldg(x + 3 * int64_t(node) + i);
   }
-  double J[GDIM][GDIM];
-#pragma unroll
-  for (int i = 0; i < GDIM; ++i)
-#pragma unroll
-    for (int j = 0; j < GDIM; ++j) {
-      double acc = 0.0;
-#pragma unroll
-      for (int v = 0; v < GDIM + 1; ++v) acc += xv[v][i] * T.dpsi[j][v];
-      J[i][j] = acc;
-    }
-  tab_inverse<GDIM>(J, K);
-  double det;
-  if constexpr (GDIM == 2)
-    det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
-  else
-    det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) + J[0][1] * (J[1][2] * J[2][0] - J[1][0] * J[2][2]) +
-          J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
-  return fabs(det);
+  return form_geometry_xv<GDIM>(T, xv, K);
 }
 
 // the cell's coefficients through the dofmap (read-only path; neighbouring cells / points share nodes: L1/L2 hits)
@@ -87,76 +71,6 @@ __device__ __forceinline__ void form_gather(const int32_t* __restrict__ dofmap, 
       for (int k = 0; k < BS; ++k) w[a][k] = __ldg(u + int64_t(BS) * idx[a] + k);
     }
   }
-}
-
-// transpose of tab_operand: the point value s (ncomp of `kind`) as a cotangent of (value, gradient)
-template <int GDIM, int BS>
-__device__ __forceinline__ void form_cotangent(int kind, const double* s, double Vs[BS], double Gs[BS][GDIM]) {
-#pragma unroll
-  for (int c = 0; c < BS; ++c) {
-    Vs[c] = 0.0;
-#pragma unroll
-    for (int j = 0; j < GDIM; ++j) Gs[c][j] = 0.0;
-  }
-  if (kind == 0) {
-#pragma unroll
-    for (int c = 0; c < BS; ++c) Vs[c] = s[c];
-  } else if (kind == 2) {
-    if constexpr (GDIM == 2 && BS == 2) {
-      const double h = 1.4142135623730951 * 0.5 * s[3];
-      Gs[0][0] = s[0], Gs[1][1] = s[1], Gs[0][1] = h, Gs[1][0] = h;
-    }
-  } else {
-#pragma unroll
-    for (int c = 0; c < BS; ++c)
-#pragma unroll
-      for (int j = 0; j < GDIM; ++j) Gs[c][j] = s[c * GDIM + j];
-  }
-}
-
-// table access for either home of the tables (constant bank: warp-uniform q; shared memory: per-thread q)
-__device__ __forceinline__ double form_phi(const tab_tables& T, int q, int a) { return T.phi[q][a]; }
-__device__ __forceinline__ double form_dphi(const tab_tables& T, int k, int q, int a) { return T.dphi[k][q][a]; }
-template <int GDIM, int NB>
-struct form_tabs;
-template <int GDIM, int NB>
-__device__ __forceinline__ double form_phi(const form_tabs<GDIM, NB>& S, int q, int a);
-template <int GDIM, int NB>
-__device__ __forceinline__ double form_dphi(const form_tabs<GDIM, NB>& S, int k, int q, int a);
-
-// fe[a][c] += scale * ( Vs[c] phi[q][a] + sum_k (sum_j Gs[c][j] K[k][j]) dphi[k][q][a] )   - transpose of tab_point
-template <int GDIM, int BS, int NB, class Tables>
-__device__ __forceinline__ void form_accumulate(const Tables& T, int kind, int q, double scale, const double Vs[BS],
-                                                const double Gs[BS][GDIM], const double K[GDIM][GDIM],
-                                                double fe[NB][BS]) {
-  if (kind == 0) {
-#pragma unroll
-    for (int a = 0; a < NB; ++a) {
-      const double ph = scale * form_phi(T, q, a);
-#pragma unroll
-      for (int c = 0; c < BS; ++c) fe[a][c] += Vs[c] * ph;
-    }
-    return;
-  }
-  double H[BS][GDIM];
-#pragma unroll
-  for (int c = 0; c < BS; ++c)
-#pragma unroll
-    for (int k = 0; k < GDIM; ++k) {
-      double acc = 0.0;
-#pragma unroll
-      for (int j = 0; j < GDIM; ++j) acc += Gs[c][j] * K[k][j];
-      H[c][k] = scale * acc;
-    }
-#pragma unroll
-  for (int a = 0; a < NB; ++a)
-#pragma unroll
-    for (int c = 0; c < BS; ++c) {
-      double acc = 0.0;
-#pragma unroll
-      for (int k = 0; k < GDIM; ++k) acc += H[c][k] * form_dphi(T, k, q, a);
-      fe[a][c] += acc;
-    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -192,9 +106,9 @@ __device__ __forceinline__ void form_stage_tables(const tab_tables& T, form_tabs
 }
 
 template <int GDIM, int NB>
-__device__ __forceinline__ double form_phi(const form_tabs<GDIM, NB>& S, int q, int a) { return S.phi[q][a]; }
+EO_TAB_HD double form_phi(const form_tabs<GDIM, NB>& S, int q, int a) { return S.phi[q][a]; }
 template <int GDIM, int NB>
-__device__ __forceinline__ double form_dphi(const form_tabs<GDIM, NB>& S, int k, int q, int a) { return S.dphi[q][k][a]; }
+EO_TAB_HD double form_dphi(const form_tabs<GDIM, NB>& S, int k, int q, int a) { return S.dphi[q][k][a]; }
 
 // tab_point with the tables in shared memory (same statement order: identical results)
 template <int GDIM, int BS, int NB>

@@ -4,6 +4,7 @@
 
 #include "mc_core.cuh"
 #include "tab_core.cuh"
+#include "form_core.cuh"
 #include "isihara_core.cuh"
 
 template <int GDIM, int BS, int NB>
@@ -26,7 +27,76 @@ static void tab_cells(const tab_tables& T, int kind, const int32_t* dofmap, cons
   }
 }
 
+// serial restatement of the form kernels' cell loop on top of form_core.cuh:
+//   x == nullptr: y += B^T W D            (eo_form_vector; D = point values, ncomp(kind_test) per point)
+//   x != nullptr: y += B^T W D (B x)      (eo_form_action; D row-major (ncomp_test, ncomp_trial) per point)
+template <int GDIM, int BS, int NB>
+static void form_cells(const tab_tables& T, const double* wq, int kind_test, int kind_trial, const int32_t* dofmap,
+                       const int32_t* x_dofmap, const double* xg, const double* D, const double* x, int64_t n_cells,
+                       double* y) {
+  const int nt = tab_ncomp(kind_test, BS, GDIM), ni = x ? tab_ncomp(kind_trial, BS, GDIM) : 1;
+  for (int64_t c = 0; c < n_cells; ++c) {
+    double w[NB][BS], xv[GDIM + 1][GDIM], K[GDIM][GDIM], fe[NB][BS];
+    for (int a = 0; a < NB; ++a)
+      for (int k = 0; k < BS; ++k) {
+        w[a][k] = x ? x[int64_t(BS) * dofmap[c * NB + a] + k] : 0.0;
+        fe[a][k] = 0.0;
+      }
+    for (int v = 0; v < GDIM + 1; ++v)
+      for (int i = 0; i < GDIM; ++i) xv[v][i] = xg[3 * int64_t(x_dofmap[c * (GDIM + 1) + v]) + i];
+    const double adet = form_geometry_xv<GDIM>(T, xv, K);
+    for (int q = 0; q < T.nq; ++q) {
+      double tau[16];
+      const double* Dq = D + (c * T.nq + q) * int64_t(nt * ni);
+      if (x) {
+        double val[BS], grad[BS][GDIM], e[16];
+        tab_point<GDIM, BS, NB>(T, w, K, q, kind_trial == 0, kind_trial != 0, val, grad);
+        tab_operand<GDIM, BS>(kind_trial, val, grad, e);
+        for (int r = 0; r < nt; ++r) {
+          double acc = 0.0;
+          for (int l = 0; l < ni; ++l) acc += Dq[r * ni + l] * e[l];
+          tau[r] = acc;
+        }
+      } else {
+        for (int r = 0; r < nt; ++r) tau[r] = Dq[r];
+      }
+      double Vs[BS], Gs[BS][GDIM];
+      form_cotangent<GDIM, BS>(kind_test, tau, Vs, Gs);
+      form_accumulate<GDIM, BS, NB>(T, kind_test, q, wq[q] * adet, Vs, Gs, K, fe);
+    }
+    for (int a = 0; a < NB; ++a)
+      for (int k = 0; k < BS; ++k) y[int64_t(BS) * dofmap[c * NB + a] + k] += fe[a][k];
+  }
+}
+
+static void fill_tables(tab_tables& T, int gdim, int bs, int nb, int nq, const double* phi, const double* dphi,
+                        const double* dpsi) {
+  T.nb = nb, T.nq = nq, T.bs = bs, T.gdim = gdim, T.nv = gdim + 1;
+  for (int q = 0; q < nq; ++q)
+    for (int a = 0; a < nb; ++a) {
+      T.phi[q][a] = phi[q * nb + a];
+      for (int k = 0; k < gdim; ++k) T.dphi[k][q][a] = dphi[(k * nq + q) * nb + a];
+    }
+  for (int k = 0; k < gdim; ++k)
+    for (int v = 0; v < gdim + 1; ++v) T.dpsi[k][v] = dpsi[k * (gdim + 1) + v];
+}
+
 extern "C" {
+
+// y (bs * n_dofs, zeroed by the caller) += form vector (x == NULL) or form action; kinds as eo_operand_kind with DEF_GRAD
+// already mapped to GRAD; returns 0 or -1 (unsupported element)
+int hostcheck_form(int gdim, int bs, int nb, int nq, int kind_test, int kind_trial, const double* phi, const double* dphi,
+                   const double* dpsi, const double* weights, const int32_t* dofmap, const int32_t* x_dofmap,
+                   const double* xg, const double* D, const double* x, int64_t n_cells, double* y) {
+  tab_tables T{};
+  fill_tables(T, gdim, bs, nb, nq, phi, dphi, dpsi);
+  if (gdim == 2 && bs == 2 && nb == 6) form_cells<2, 2, 6>(T, weights, kind_test, kind_trial, dofmap, x_dofmap, xg, D, x, n_cells, y);
+  else if (gdim == 2 && bs == 1 && nb == 3) form_cells<2, 1, 3>(T, weights, kind_test, kind_trial, dofmap, x_dofmap, xg, D, x, n_cells, y);
+  else if (gdim == 2 && bs == 1 && nb == 6) form_cells<2, 1, 6>(T, weights, kind_test, kind_trial, dofmap, x_dofmap, xg, D, x, n_cells, y);
+  else if (gdim == 3 && bs == 3 && nb == 4) form_cells<3, 3, 4>(T, weights, kind_test, kind_trial, dofmap, x_dofmap, xg, D, x, n_cells, y);
+  else return -1;
+  return 0;
+}
 
 void hostcheck_isihara(const isi_weights* w, const double* F, double* dP, double* P, int64_t n) {
 #pragma omp parallel for schedule(static)

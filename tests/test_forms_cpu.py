@@ -124,3 +124,61 @@ def test_taylor_remainder_of_residual_vs_tangent_has_slope_two():
     slope0 = np.polyfit(np.log(hs), np.log(r0), 1)[0]
     slope1 = np.polyfit(np.log(hs), np.log(r1), 1)[0]
     assert abs(slope0 - 1.0) < 0.05 and slope1 > 1.9
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the kernels' own per-cell algebra (csrc/form_core.cuh, compiled for the host by tests/hostcheck/) against the oracle
+@pytest.fixture(scope="module")
+def hc():
+    import ctypes as C
+    import os
+    import subprocess
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    subprocess.check_call(["make", "-C", os.path.join(here, "hostcheck")], stdout=subprocess.DEVNULL)
+    return C.CDLL(os.path.join(here, "hostcheck", "libhostcheck.so"))
+
+
+def _host_form(hc, m, bs, weights, kind_test, kind_trial, D, x=None):
+    import ctypes as C
+
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    gdim, (nq, nb) = m["dphi"].shape[0], m["phi"].shape
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (m["phi"], m["dphi"], m["dpsi"], weights)]
+    dm, xd = np.ascontiguousarray(m["dofmap"], dtype=np.int32), np.ascontiguousarray(m["x_dofmap"], dtype=np.int32)
+    xg, D = np.ascontiguousarray(m["x"]), np.ascontiguousarray(D, dtype=np.float64)
+    xin = None if x is None else np.ascontiguousarray(x, dtype=np.float64)
+    y = np.zeros(bs * m["n_dofs"])
+    fk = lambda k: ot.GRAD if k == ot.DEF_GRAD else k  # noqa: E731  (form.cu: form_kind)
+    rc = hc.hostcheck_form(gdim, bs, nb, nq, fk(kind_test), fk(kind_trial), *(p(a) for a in arrs), p(dm), p(xd), p(xg), p(D),
+                           p(xin), C.c_int64(dm.shape[0]), p(y))
+    assert rc == 0
+    return y
+
+
+@pytest.mark.parametrize("kind", [ot.VALUE, ot.GRAD, ot.MANDEL_STRAIN, ot.DEF_GRAD])
+def test_form_core_vector_against_oracle(hc, kind):
+    m = tri_case(nx=9, ny=7)
+    s = np.random.default_rng(0).normal(size=(m["dofmap"].shape[0], 3, of.ncomp(kind, 2, 2)))
+    got = _host_form(hc, m, 2, W3, kind, 0, s)
+    ref = of.assemble_vector(kind, s, W3, m["dofmap"], 2, m["n_dofs"], *_geo(m))
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-13 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("case", [("tri2", ot.MANDEL_STRAIN, ot.MANDEL_STRAIN), ("tri1s", ot.GRAD, ot.VALUE),
+                                  ("tri1s", ot.GRAD, ot.GRAD), ("tet", ot.GRAD, ot.DEF_GRAD)])
+def test_form_core_action_against_oracle(hc, case):
+    name, kt, ki = case
+    if name == "tri2":
+        m, bs, w = tri_case(nx=9, ny=7), 2, W3
+    elif name == "tri1s":
+        m, bs, w = tri_case(nx=9, ny=7, degree=1), 1, W3
+    else:
+        m, bs, w = tet_case(2), 3, np.array([0.1, 1.0 / 6.0 - 0.1])
+    gdim = m["dphi"].shape[0]
+    rng = np.random.default_rng(1)
+    D = rng.normal(size=(m["dofmap"].shape[0], m["phi"].shape[0], of.ncomp(kt, bs, gdim) * of.ncomp(ki, bs, gdim)))
+    x = rng.normal(size=bs * m["n_dofs"])
+    got = _host_form(hc, m, bs, w, kt, ki, D, x)
+    ref = of.apply_action(kt, ki, D, x, w, m["dofmap"], bs, m["n_dofs"], *_geo(m))
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-13 * np.abs(ref).max())
