@@ -29,6 +29,35 @@ def partition(n: int, rank: int, world: int) -> tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
+def local_submesh(dofmap: np.ndarray, x_dofmap: np.ndarray, x: np.ndarray, rank: int, world: int) -> dict:
+    """The cell block of `rank` as a self-contained mesh for `Tabulator` / `QuadratureForms`: cells [start, stop) of the
+    contiguous partition, dofs and geometry nodes renumbered locally in order of first use.  Returns dict(cells (start,
+    stop), dofmap, x_dofmap, x, n_dofs, dof_l2g, node_l2g).  Every local cell is an OWNED cell (cell integrals run over
+    owned cells only, like DOLFINx's assemblers); dofs on the block interface appear on both ranks and their contributions
+    are summed afterwards - `b.ghostUpdate(ADD, REVERSE)` in the reference's callbacks (demo_vm:512), `sum_shared` here."""
+    start, stop = partition(dofmap.shape[0], rank, world)
+    dm, xd = np.asarray(dofmap)[start:stop], np.asarray(x_dofmap)[start:stop]
+    dof_l2g, dm_loc = np.unique(dm.reshape(-1), return_inverse=True)
+    node_l2g, xd_loc = np.unique(xd.reshape(-1), return_inverse=True)
+    return {"cells": (start, stop), "dofmap": dm_loc.reshape(dm.shape).astype(np.int32),
+            "x_dofmap": xd_loc.reshape(xd.shape).astype(np.int32), "x": np.ascontiguousarray(np.asarray(x)[node_l2g]),
+            "n_dofs": int(dof_l2g.size), "dof_l2g": dof_l2g, "node_l2g": node_l2g}
+
+
+def sum_shared(b_local: np.ndarray, dof_l2g: np.ndarray, n_dofs_global: int, bs: int = 1, group=None) -> np.ndarray:
+    """Global vector (bs * n_dofs_global) = sum over ranks of the local cell-integral vectors (host tensors; gloo or
+    nccl-with-host-staging).  A dense all-reduce: fine for tests and moderate sizes; production codes exchange only the
+    interface dofs with their neighbours (what PETSc's ghostUpdate does)."""
+    import torch
+    import torch.distributed as dist
+
+    g = np.zeros((n_dofs_global, bs))
+    g[dof_l2g] = np.asarray(b_local, dtype=np.float64).reshape(-1, bs)
+    t = torch.from_numpy(g)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.numpy().reshape(-1)
+
+
 def stats_to_arrays(stats: dict) -> tuple[np.ndarray, np.ndarray]:
     s = np.empty(N_SUM, dtype=np.int64)
     s[0], s[1], s[2], s[3] = stats["n_points"], stats["n_plastic"], stats["n_nonconverged"], stats["n_nonfinite"]

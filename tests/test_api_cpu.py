@@ -168,3 +168,48 @@ def test_stats_allreduce_world2_gloo(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert res.stdout.count("ok") == 2
+
+
+_GLOO_FORMS_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np, torch.distributed as dist
+from dolfinx_external_operator_b200 import elements as el, parallel as par
+from oracle import forms as of, tabulation as ot
+from tab_util import tri_case
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+m = tri_case(nx=9, ny=7)
+W3 = el.triangle_quadrature_weights(2)
+s = np.random.default_rng(0).normal(size=(m["dofmap"].shape[0], 3, 4))      # the same "stress" on every rank
+x = np.random.default_rng(1).normal(size=2 * m["n_dofs"])
+loc = par.local_submesh(m["dofmap"], m["x_dofmap"], m["x"], r, w)
+a, b = loc["cells"]
+geo = (loc["x"], loc["x_dofmap"], m["phi"], m["dphi"], m["dpsi"])
+b_loc = of.assemble_vector(ot.MANDEL_STRAIN, s[a:b], W3, loc["dofmap"], 2, loc["n_dofs"], *geo)
+y_loc = of.apply_action(ot.MANDEL_STRAIN, ot.MANDEL_STRAIN, np.tile(np.eye(4).reshape(-1), (b - a, 3, 1)),
+                        x.reshape(-1, 2)[loc["dof_l2g"]].reshape(-1), W3, loc["dofmap"], 2, loc["n_dofs"], *geo)
+gb = par.sum_shared(b_loc, loc["dof_l2g"], m["n_dofs"], bs=2)
+gy = par.sum_shared(y_loc, loc["dof_l2g"], m["n_dofs"], bs=2)
+G = (m["x"], m["x_dofmap"], m["phi"], m["dphi"], m["dpsi"])
+ref_b = of.assemble_vector(ot.MANDEL_STRAIN, s, W3, m["dofmap"], 2, m["n_dofs"], *G)
+ref_y = of.apply_action(ot.MANDEL_STRAIN, ot.MANDEL_STRAIN, np.tile(np.eye(4).reshape(-1), (m["dofmap"].shape[0], 3, 1)), x,
+                        W3, m["dofmap"], 2, m["n_dofs"], *G)
+assert np.abs(gb - ref_b).max() <= 1e-13 * np.abs(ref_b).max()
+assert np.abs(gy - ref_y).max() <= 1e-13 * np.abs(ref_y).max()
+assert loc["n_dofs"] < m["n_dofs"] and (b - a) in (m["dofmap"].shape[0] // 2, m["dofmap"].shape[0] - m["dofmap"].shape[0] // 2)
+dist.destroy_process_group()
+print("rank", r, "ok")
+"""
+
+
+def test_cell_partitioned_forms_world2_gloo(tmp_path):
+    """The device-side consumers shard by cells: each rank integrates its owned block on a locally numbered sub-mesh and
+    the interface dofs are summed afterwards (the reference's ghostUpdate(ADD, REVERSE)); the sum equals the global vector."""
+    script = tmp_path / "wf.py"
+    script.write_text(_GLOO_FORMS_WORKER.format(root=ROOT))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", str(29900 + os.getpid() % 90), str(script)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.count("ok") == 2
