@@ -9,14 +9,17 @@
 // The test/trial "operand kinds" are the ones of the tabulation (tab_core.cuh): the residual is the weighted
 // TRANSPOSE of the operand tabulation, b = B^T W s, and the tangent action is y = B^T W D B x.
 //
-// Mapping: one thread per cell.  The thread gathers its cell's geometry (and, for the action, the nb*bs entries
-// of x) through the read-only path, walks the cell's quadrature points - each point's record (stress 32 B,
-// tangent 128 B) is read once with 256-bit loads; the three records of a P2 triangle are contiguous - and
-// accumulates the nb*bs element-vector entries in registers; the tables sit in the constant bank (the point index
-// is warp-uniform: broadcast).  The scatter is one fp64 RED.ADD per element entry (each DOF of a P2 triangle mesh
-// is touched by 2-6 cells: low contention, resolved in L2).  Summation order over cells is therefore not fixed:
-// results agree with the oracle to rounding (tests: rtol 1e-12 of the vector norm), not bit for bit.
-// HBM-bound: residual 32 B/point + ~45 B/cell of index/geometry traffic; action 128 B/point + the same.
+// Kernels (P2 vector triangle, 3 points per cell, measured at 1e8 points on B200 - profiles/r1_forms_ncu_summary.md):
+//   form_vector_kernel / form_vm_step_kernel   one thread per POINT, per-CTA shared-memory reduction of the nq
+//                                              contributions, one fp64 RED.ADD per element-vector entry   (step: 0.68)
+//   form_action_tma_kernel                     one thread per CELL, its nq 4x4 tangents staged by a per-thread TMA bulk copy
+//                                              into a padded shared row                                   (0.81-0.82)
+//   form_action_cell_kernel                    general fallback of the action (any kinds / nq / element)
+//   form_matrix_kernel                         element matrices column by column into CSR values (bisection in the row)
+// Each DOF of a P2 triangle mesh is touched by 2-6 cells: the REDs see low contention and resolve in L2.  Summation
+// order over cells is not fixed: results agree with the oracle to rounding (tests: 1e-12 of the vector scale), not bit
+// for bit.  What bounds the register-path kernels is the LSU wavefront rate, not HBM (see the table in the summary).
+// The per-cell arithmetic lives in form_core.cuh (host/device; also compiled by the CPU test harness).
 #include "eo_common.cuh"
 #include "tab_core.cuh"
 #include "form_core.cuh"
