@@ -774,7 +774,9 @@ def main():
     ap.add_argument("--model", default="vm", choices=["vm", "heat", "mc", "tab", "fused", "isihara", "jitvm", "jitfused", "jitvm3d", "step", "action"])
     ap.add_argument("--fused-exact", action="store_true")
     ap.add_argument("--mc-scheme", default="queue", choices=["queue", "simple", "queue-noaffinity", "queue-onepass"])
-    ap.add_argument("--n", type=float, default=1e8, help="quadrature points per GPU (device-resident leg)")
+    ap.add_argument("--n", "--qp-per-gpu", dest="n", type=float, default=1e8,
+                    help="quadrature points per GPU (device-resident leg); under torchrun spell it --qp-per-gpu "
+                         "(torchrun's own parser rejects --n as an ambiguous abbreviation)")
     ap.add_argument("--e2e-n", type=float, default=1.5e7, help="quadrature points per GPU for the end-to-end leg")
     ap.add_argument("--state-layout", default="aos", choices=["aos", "soa"])
     ap.add_argument("--cpu-sample", type=float, default=4e6)

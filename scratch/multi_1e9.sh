@@ -3,8 +3,8 @@
 N=2
 P=29711
 run() { timeout 700 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P bench.py --gpus $N "$@"; P=$((P+1)); }
-run --n 5e8 --steps 5 --warmup 3 --cpu-seconds 0 --no-device-consumers > gpurun_out/bench_1e9_vm_n$N.json 2> gpurun_out/bench_1e9_vm_n$N.err
-run --model mc --n 5e8 --steps 3 --warmup 3 --cpu-seconds 0 --e2e-n 0 > gpurun_out/bench_1e9_mc_n$N.json 2> gpurun_out/bench_1e9_mc_n$N.err
+run --qp-per-gpu 5e8 --steps 5 --warmup 3 --cpu-seconds 0 --no-device-consumers > gpurun_out/bench_1e9_vm_n$N.json 2> gpurun_out/bench_1e9_vm_n$N.err
+run --model mc --qp-per-gpu 5e8 --steps 3 --warmup 3 --cpu-seconds 0 --e2e-n 0 > gpurun_out/bench_1e9_mc_n$N.json 2> gpurun_out/bench_1e9_mc_n$N.err
 python - <<PY
 import json
 for f in ['vm','mc']:
