@@ -318,8 +318,8 @@ __global__ void __launch_bounds__(128) form_action_cell_kernel(const __grid_cons
 // slower - 4.4 vs 3.3 ms per 1e8 points at 8 warps per SM - and is not kept.)
 template <int NB, int NQ>
 __global__ void __launch_bounds__(128) form_action_tma_kernel(const __grid_constant__ tab_tables T,
-                                                              const __grid_constant__ form_weights W,
-                                                              const int32_t* __restrict__ dofmap,
+                                                              const __grid_constant__ form_weights W, int kind_test,
+                                                              int kind_trial, const int32_t* __restrict__ dofmap,
                                                               const int32_t* __restrict__ x_dofmap,
                                                               const double* __restrict__ x, const double* __restrict__ D,
                                                               const double* __restrict__ xin, int64_t n_cells,
@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(128) form_action_tma_kernel(const __grid_const
   for (int q = 0; q < NQ; ++q) {
     double val[2] = {0.0, 0.0}, grad[2][2], e[4], tau[4];
     tab_point<2, 2, NB>(T, w, K, q, false, true, val, grad);
-    tab_operand<2, 2>(2, val, grad, e);
+    tab_operand<2, 2>(kind_trial, val, grad, e);
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       double d0, d1, d2, d3;
@@ -378,8 +378,8 @@ __global__ void __launch_bounds__(128) form_action_tma_kernel(const __grid_const
       tau[r] = d0 * e[0] + d1 * e[1] + d2 * e[2] + d3 * e[3];
     }
     double Vs[2], Gs[2][2];
-    form_cotangent<2, 2>(2, tau, Vs, Gs);
-    form_accumulate<2, 2, NB>(T, 2, q, W.w[q] * adet, Vs, Gs, K, fe);
+    form_cotangent<2, 2>(kind_test, tau, Vs, Gs);
+    form_accumulate<2, 2, NB>(T, kind_test, q, W.w[q] * adet, Vs, Gs, K, fe);
   }
 #pragma unroll
   for (int a = 0; a < NB; ++a)
@@ -672,8 +672,9 @@ int eo_form_action(eo_form* f, int kind_test, int kind_trial, const double* D, c
     form_weights W;
     memcpy(W.w, f->w, sizeof(W.w));
     bool done = false;
-    // TMA-staged kernel for the 4x4 tangent of the plasticity demos (EO_FORM_ACTION_TMA=0: register-path kernel, for A/B)
-    const bool tma = form_env("EO_FORM_ACTION_TMA", 1) && t->T.gdim == 2 && t->T.bs == 2 && t->T.nq == 3 && kt == 2 && ki == 2 &&
+    // TMA-staged kernel for 4x4 tangents on 2-d vector fields: C_tang of the plasticity demos (Mandel strain both sides),
+    // dP/dF of the hyperelasticity demo (gradient both sides)   (EO_FORM_ACTION_TMA=0: register-path kernel, for A/B)
+    const bool tma = form_env("EO_FORM_ACTION_TMA", 1) && t->T.gdim == 2 && t->T.bs == 2 && t->T.nq == 3 && kt != 0 && ki != 0 &&
                      eo_aligned(D, 32);
     const unsigned gc = (unsigned)((n_cells + 127) / 128);
 #define X(G, B, N)                                                                                                       \
@@ -682,7 +683,7 @@ int eo_form_action(eo_form* f, int kind_test, int kind_trial, const double* D, c
       const size_t sm = 128 + 128 * (3 * 128 + 16);                                                                      \
       auto kfn = form_action_tma_kernel<(G == 2 && B == 2 ? N : 3), 3>;                                                  \
       cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm));                                   \
-      kfn<<<gc, 128, sm, ctx->s_cmp>>>(t->T, W, t->dofmap, t->x_dofmap, t->x, D, d_x, n_cells, d_y);                     \
+      kfn<<<gc, 128, sm, ctx->s_cmp>>>(t->T, W, kt, ki, t->dofmap, t->x_dofmap, t->x, D, d_x, n_cells, d_y);             \
     } else if (t->T.nq == 3) {                                                                                           \
       form_action_cell_kernel<G, B, N, 3><<<gc, 128, 0, ctx->s_cmp>>>(t->T, W, kt, ki, t->dofmap, t->x_dofmap, t->x, D,   \
                                                                       d_x, n_cells, d_y);                                \

@@ -1,0 +1,8 @@
+timeout 600 python -m pytest tests/test_forms_gpu.py -m gpu -q 2>&1 | tail -4
+timeout 200 python bench.py --model action --n 1e8 --steps 10 --cpu-seconds 0 --e2e-n 0 2>&1 | python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('action', d['config']['qp_per_gpu'], round(d['ms_per_step'],3), 'ms frac', round(d['roofline']['frac'],3))
+    elif 'rror' in l: print(l.strip()[:300])
+"

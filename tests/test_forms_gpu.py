@@ -81,10 +81,13 @@ def test_vector_and_action_tetrahedra(ctx):
     _close(forms.action("grad", "def_grad", ctx.to_device(D), x), ref)
 
 
-@pytest.mark.parametrize("pair", [("mandel_strain", "mandel_strain"), ("grad", "value"), ("value", "grad"), ("grad", "grad")])
+@pytest.mark.parametrize("pair", [("mandel_strain", "mandel_strain"), ("grad", "value"), ("value", "grad"), ("grad", "grad"),
+                                  ("grad", "def_grad", 2), ("mandel_strain", "grad", 2), ("value", "mandel_strain", 2)])
 def test_action_p2_triangle(ctx, pair):
-    kt, ki = pair
-    bs = 2 if "mandel_strain" in pair else 1  # (grad, value) = dq/dT, (grad, grad) = dq/dsigma of the heat demo
+    kt, ki = pair[:2]
+    # (grad, value) = dq/dT, (grad, grad) = dq/dsigma of the heat demo; (grad, def_grad) on a vector field = dP/dF of the
+    # hyperelasticity demo (demo_hyperelasticity.py:479-500), 4x4 like C_tang
+    bs = pair[2] if len(pair) > 2 else (2 if "mandel_strain" in pair else 1)
     m = tri_case(nx=31, ny=17)
     tab, forms = _mk(ctx, m, bs)
     nc = m["dofmap"].shape[0]
