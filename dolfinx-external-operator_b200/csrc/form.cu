@@ -10,8 +10,9 @@
 // TRANSPOSE of the operand tabulation, b = B^T W s, and the tangent action is y = B^T W D B x.
 //
 // Kernels (P2 vector triangle, 3 points per cell, measured at 1e8 points on B200 - profiles/r1_forms_ncu_summary.md):
-//   form_vector_kernel / form_vm_step_kernel   one thread per POINT, per-CTA shared-memory reduction of the nq
-//                                              contributions, one fp64 RED.ADD per element-vector entry   (step: 0.68)
+//   form_vector_cell_kernel                    one thread per CELL, nb*bs fp64 RED.ADDs                            (0.68)
+//   form_vm_step_kernel                        one thread per POINT, per-CTA shared-memory reduction of the nq
+//                                              contributions, one fp64 RED.ADD per element-vector entry   (0.68)
 //   form_action_tma_kernel                     one thread per CELL, its nq 4x4 tangents staged by a per-thread TMA bulk copy
 //                                              into a padded shared row                                   (0.81-0.82)
 //   form_action_cell_kernel                    general fallback of the action (any kinds / nq / element)
@@ -77,7 +78,7 @@ __device__ __forceinline__ void form_gather(const int32_t* __restrict__ dofmap, 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Mapping of the three integrals: one thread per QUADRATURE POINT, a CTA of FORM_THREADS threads covers
+// Mapping of the fused residual step: one thread per QUADRATURE POINT, a CTA of FORM_THREADS threads covers
 // FORM_THREADS / nq consecutive cells (a cell never straddles CTAs).  The per-point streams (stress 32 B, tangent
 // 128 B, history, outputs) are then read and written exactly like in the streaming kernels - consecutive threads,
 // consecutive records, two dependent memory round trips per thread - and the nq threads of a cell gather the same
@@ -199,37 +200,48 @@ __device__ __forceinline__ void form_reduce_scatter(const form_tabs<GDIM, NB>& S
   __syncthreads();  // the rows are rewritten by the next tile
 }
 
-// b += sum_q w_q |det J| B_q^T coef[c][q]
+// b += sum_q w_q |det J| B_q^T coef[c][q].  One thread per CELL: geometry once, nq point records (contiguous per cell),
+// nb*bs REDs.  For this light kernel (32 B of stream per point) the per-cell mapping beats the per-point mapping of the
+// step kernel, whose nq-fold geometry and shared-memory reduction would dominate: 1.57 vs 2.94 ms per 1e8 points.
 template <int GDIM, int BS, int NB>
-__global__ void __launch_bounds__(FORM_THREADS) form_vector_kernel(const __grid_constant__ tab_tables T,
-                                                                   const __grid_constant__ form_weights W, int kind,
-                                                                   const int32_t* __restrict__ dofmap,
-                                                                   const int32_t* __restrict__ x_dofmap,
-                                                                   const double* __restrict__ x,
-                                                                   const double* __restrict__ coef, int64_t n_cells,
-                                                                   double* __restrict__ b) {
-  extern __shared__ double s_fe[];
-  __shared__ form_tabs<GDIM, NB> S;
-  form_stage_tables<GDIM, NB>(T, S);
-  const int cpb = FORM_THREADS / T.nq;
-  const int64_t tiles = (n_cells + cpb - 1) / cpb;
+__global__ void __launch_bounds__(128) form_vector_cell_kernel(const __grid_constant__ tab_tables T,
+                                                               const __grid_constant__ form_weights W, int kind,
+                                                               const int32_t* __restrict__ dofmap,
+                                                               const int32_t* __restrict__ x_dofmap,
+                                                               const double* __restrict__ x,
+                                                               const double* __restrict__ coef, int64_t n_cells,
+                                                               double* __restrict__ b) {
+  const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (c >= n_cells) return;
   const int ncomp = tab_ncomp(kind, BS, GDIM);
   const bool vec4 = ncomp == 4 && (reinterpret_cast<uintptr_t>(coef) % 32) == 0;
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const form_tile t = form_locate(T.nq, cpb, tile, n_cells);
-    double K[GDIM][GDIM], s[BS * GDIM > 4 ? BS * GDIM : 4], scale = 0.0;
-    if (t.active) {
-      const double* sp = coef + (t.c * T.nq + t.q) * ncomp;
-      if (vec4) {
-        const eo_d4 v = eo_ld256(sp);
-        s[0] = v.x, s[1] = v.y, s[2] = v.z, s[3] = v.w;
-      } else {
-        for (int k = 0; k < ncomp; ++k) s[k] = eo_ld64(sp + k);
-      }
-      scale = W.w[t.q] * form_geometry<GDIM>(T, x_dofmap, x, t.c, K);
+  const double* s_ptr = coef + c * int64_t(T.nq) * ncomp;
+  double K[GDIM][GDIM];
+  const double adet = form_geometry<GDIM>(T, x_dofmap, x, c, K);
+  int32_t idx[NB];
+#pragma unroll
+  for (int a = 0; a < NB; ++a) idx[a] = __ldg(dofmap + c * NB + a);
+  double fe[NB][BS];
+#pragma unroll
+  for (int a = 0; a < NB; ++a)
+#pragma unroll
+    for (int k = 0; k < BS; ++k) fe[a][k] = 0.0;
+  for (int q = 0; q < T.nq; ++q) {
+    double s[BS * GDIM > 4 ? BS * GDIM : 4];
+    if (vec4) {
+      const eo_d4 v = eo_ld256(s_ptr + 4 * q);
+      s[0] = v.x, s[1] = v.y, s[2] = v.z, s[3] = v.w;
+    } else {
+      for (int k = 0; k < ncomp; ++k) s[k] = eo_ld64(s_ptr + q * ncomp + k);
     }
-    form_reduce_scatter<GDIM, BS, NB>(S, T.nq, kind, t, scale, s, K, dofmap, tile, cpb, n_cells, b, s_fe);
+    double Vs[BS], Gs[BS][GDIM];
+    form_cotangent<GDIM, BS>(kind, s, Vs, Gs);
+    form_accumulate<GDIM, BS, NB>(T, kind, q, W.w[q] * adet, Vs, Gs, K, fe);
   }
+#pragma unroll
+  for (int a = 0; a < NB; ++a)
+#pragma unroll
+    for (int k = 0; k < BS; ++k) atomicAdd(b + int64_t(BS) * idx[a] + k, fe[a][k]);
 }
 
 // y += sum_q w_q |det J| B_test,q^T ( D[c][q] (B_trial,q x) ),   D row-major (ncomp_test, ncomp_trial) per point.
@@ -627,15 +639,13 @@ int eo_form_vector(eo_form* f, int kind_test, const double* coef, int64_t n_cell
   if (rc != EO_OK) return rc;
   const int kind = form_kind(kind_test);
   if (n_cells > 0) {
-    const unsigned grid = form_grid(ctx, t, n_cells);
     form_weights W;
     memcpy(W.w, f->w, sizeof(W.w));
     bool done = false;
 #define X(G, B, N)                                                                                                     \
   if (!done && t->T.gdim == G && t->T.bs == B && t->T.nb == N) {                                                       \
-    const size_t sm = form_smem(ctx, form_vector_kernel<G, B, N>, N * B);                                              \
-    form_vector_kernel<G, B, N><<<grid, FORM_THREADS, sm, ctx->s_cmp>>>(t->T, W, kind, t->dofmap, t->x_dofmap, t->x, coef, \
-                                                                        n_cells, d_b);                                 \
+    form_vector_cell_kernel<G, B, N><<<(unsigned)((n_cells + 127) / 128), 128, 0, ctx->s_cmp>>>(                       \
+        t->T, W, kind, t->dofmap, t->x_dofmap, t->x, coef, n_cells, d_b);                                              \
     done = true;                                                                                                       \
   }
     EO_FORM_CASES(X)
