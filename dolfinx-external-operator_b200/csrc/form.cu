@@ -31,6 +31,7 @@
 
 struct eo_form {
   eo_tab* tab = nullptr;
+  eo_ctx* ctx = nullptr;     // = tab->ctx, kept so that destroying the form never touches the (possibly gone) eo_tab
   double w[EO_TAB_MAX_NQ];   // quadrature weights on the reference cell
   double* x_stage = nullptr; // device copy of a host input vector
   double* y_stage = nullptr; // device result when the caller's vector is host memory
@@ -605,6 +606,7 @@ int eo_form_create(eo_tab* tab, const double* weights, eo_form** out) {
   EO_REQUIRE(ctx, weights && out, "eo_form_create: NULL argument");
   eo_form* f = new eo_form();
   f->tab = tab;
+  f->ctx = ctx;
   memset(f->w, 0, sizeof(f->w));
   for (int q = 0; q < tab->T.nq; ++q) f->w[q] = weights[q];
   *out = f;
@@ -613,8 +615,8 @@ int eo_form_create(eo_tab* tab, const double* weights, eo_form** out) {
 
 int eo_form_destroy(eo_form* f) {
   if (!f) return EO_OK;
-  cudaSetDevice(f->tab->ctx->device);
-  cudaStreamSynchronize(f->tab->ctx->s_cmp);
+  cudaSetDevice(f->ctx->device);
+  cudaStreamSynchronize(f->ctx->s_cmp);
   if (f->x_stage) cudaFree(f->x_stage);
   if (f->y_stage) cudaFree(f->y_stage);
   if (f->row_ptr) cudaFree(f->row_ptr);
