@@ -39,6 +39,10 @@ struct eo_form {
   int64_t nnz = 0;
   int32_t* row_ptr = nullptr;  // device [bs*n_dofs + 1]
   int32_t* col = nullptr;      // device [nnz], sorted within a row
+  // position of every element-matrix entry in the CSR values, [nd*nd][n_cells] (coalesced over cells), filled by
+  // bisection at the first eo_form_matrix after eo_form_set_pattern when memory allows; -1 = not in the pattern
+  int32_t* pos = nullptr;
+  unsigned* missing = nullptr;  // device counter of element entries the pattern does not hold
 };
 
 struct form_weights {
@@ -454,8 +458,40 @@ __global__ void __launch_bounds__(FORM_THREADS, 3) form_vm_step_kernel(
     atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_points), (unsigned long long)(n_cells * T.nq));
 }
 
-// A[pos] += element matrix entries; the position of (row, col) is found by bisection in the sorted CSR row
-// (rows of a P2 triangle mesh hold <= ~40 entries: <= 6 probes, all L1/L2 hits on the pattern).
+// position of (row, col) in the CSR values by bisection in the sorted row, or -1
+__device__ __forceinline__ int32_t form_csr_find(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
+                                                 int32_t grow, int32_t gcol) {
+  int32_t lo = __ldg(row_ptr + grow);
+  const int32_t end = __ldg(row_ptr + grow + 1);
+  int32_t hi = end - 1;
+  if (hi < lo) return -1;
+  while (lo < hi) {
+    const int32_t mid = (lo + hi) >> 1;
+    if (__ldg(col + mid) < gcol) lo = mid + 1; else hi = mid;
+  }
+  return __ldg(col + lo) == gcol ? lo : -1;
+}
+
+// the positions of all (nb*bs)^2 element-matrix entries of every cell, once per pattern
+template <int BS, int NB>
+__global__ void __launch_bounds__(128) form_positions_kernel(const int32_t* __restrict__ dofmap, int64_t n_cells,
+                                                             const int32_t* __restrict__ row_ptr,
+                                                             const int32_t* __restrict__ col, int32_t* __restrict__ pos) {
+  constexpr int ND = NB * BS;
+  const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (c >= n_cells) return;
+  for (int r = 0; r < ND; ++r) {
+    const int32_t grow = BS * __ldg(dofmap + c * NB + r / BS) + r % BS;
+    for (int cc = 0; cc < ND; ++cc) {
+      const int32_t gcol = BS * __ldg(dofmap + c * NB + cc / BS) + cc % BS;
+      pos[(int64_t(r) * ND + cc) * n_cells + c] = form_csr_find(row_ptr, col, grow, gcol);
+    }
+  }
+}
+
+// A[pos] += element matrix entries; positions from the cache above, or found by bisection in the sorted CSR row
+// (rows of a P2 triangle mesh hold <= ~40 entries: <= 6 probes, all L1/L2 hits on the pattern); entries the pattern does
+// not hold are dropped and counted.
 template <int GDIM, int BS, int NB>
 __global__ void __launch_bounds__(128) form_matrix_kernel(const __grid_constant__ tab_tables T,
                                                           const __grid_constant__ form_weights W, int kind_test,
@@ -463,9 +499,12 @@ __global__ void __launch_bounds__(128) form_matrix_kernel(const __grid_constant_
                                                           const int32_t* __restrict__ x_dofmap,
                                                           const double* __restrict__ x, const double* __restrict__ D,
                                                           int64_t n_cells, const int32_t* __restrict__ row_ptr,
-                                                          const int32_t* __restrict__ col, double* __restrict__ vals) {
+                                                          const int32_t* __restrict__ col, double* __restrict__ vals,
+                                                          const int32_t* __restrict__ pos, int64_t pos_stride,
+                                                          unsigned* __restrict__ missing) {
   const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (c >= n_cells) return;
+  constexpr int ND = NB * BS;
   double K[GDIM][GDIM];
   const double adet = form_geometry<GDIM>(T, x_dofmap, x, c, K);
   int32_t idx[NB];
@@ -474,6 +513,7 @@ __global__ void __launch_bounds__(128) form_matrix_kernel(const __grid_constant_
   constexpr int MAXC = BS * GDIM > 4 ? BS * GDIM : 4;
   const int nt = tab_ncomp(kind_test, BS, GDIM), ni = tab_ncomp(kind_trial, BS, GDIM);
   const double* D_ptr = D + c * int64_t(T.nq) * nt * ni;
+  unsigned miss = 0;
   // one trial basis function (bj, cj) at a time: its element-matrix COLUMN is the action on a unit vector
   for (int bj = 0; bj < NB; ++bj)
     for (int cj = 0; cj < BS; ++cj) {
@@ -511,15 +551,15 @@ __global__ void __launch_bounds__(128) form_matrix_kernel(const __grid_constant_
       for (int a = 0; a < NB; ++a)
 #pragma unroll
         for (int k = 0; k < BS; ++k) {
-          const int32_t grow = BS * idx[a] + k;
-          int32_t lo = __ldg(row_ptr + grow), hi = __ldg(row_ptr + grow + 1) - 1;
-          while (lo < hi) {
-            const int32_t mid = (lo + hi) >> 1;
-            if (__ldg(col + mid) < gcol) lo = mid + 1; else hi = mid;
-          }
-          atomicAdd(vals + lo, fe[a][k]);
+          const int32_t at = pos ? __ldg(pos + (int64_t(a * BS + k) * ND + (bj * BS + cj)) * pos_stride + c)
+                                 : form_csr_find(row_ptr, col, BS * idx[a] + k, gcol);
+          if (at >= 0)
+            atomicAdd(vals + at, fe[a][k]);
+          else
+            ++miss;
         }
     }
+  if (miss) atomicAdd(missing, miss);
 }
 
 static int form_kind(int kind) { return kind == EO_OPERAND_DEF_GRAD ? EO_OPERAND_GRAD : kind; }  // d(I + grad u) = grad du
@@ -621,6 +661,8 @@ int eo_form_destroy(eo_form* f) {
   if (f->y_stage) cudaFree(f->y_stage);
   if (f->row_ptr) cudaFree(f->row_ptr);
   if (f->col) cudaFree(f->col);
+  if (f->pos) cudaFree(f->pos);
+  if (f->missing) cudaFree(f->missing);
   delete f;
   return EO_OK;
 }
@@ -785,7 +827,8 @@ int eo_form_set_pattern(eo_form* f, const int32_t* row_ptr, const int32_t* col, 
   EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_cmp));
   if (f->row_ptr) cudaFree(f->row_ptr);
   if (f->col) cudaFree(f->col);
-  f->row_ptr = nullptr, f->col = nullptr, f->nnz = 0;
+  if (f->pos) cudaFree(f->pos);
+  f->row_ptr = nullptr, f->col = nullptr, f->pos = nullptr, f->nnz = 0;
   EO_CUDA(ctx, cudaMalloc(&f->row_ptr, size_t(n_rows + 1) * 4));
   EO_CUDA(ctx, cudaMalloc(&f->col, size_t(nnz ? nnz : 1) * 4));
   EO_CUDA(ctx, cudaMemcpyAsync(f->row_ptr, row_ptr, size_t(n_rows + 1) * 4, cudaMemcpyHostToDevice, ctx->s_cmp));
@@ -816,17 +859,54 @@ int eo_form_matrix(eo_form* f, int kind_test, int kind_trial, const double* D, i
     const unsigned grid = (unsigned)((n_cells + 127) / 128);
     form_weights W;
     memcpy(W.w, f->w, sizeof(W.w));
+    if (!f->missing) {
+      EO_CUDA(ctx, cudaMalloc(&f->missing, sizeof(unsigned)));
+      EO_CUDA(ctx, cudaMemsetAsync(f->missing, 0, sizeof(unsigned), ctx->s_cmp));
+    }
+    // position cache, built for ALL cells at the first assembly after eo_form_set_pattern when it fits in a quarter of the
+    // free memory (P2 vector triangle: 576 B per cell); EO_FORM_MATRIX_POS=0: bisection in every assembly
+    const int nd = t->T.nb * t->T.bs;
     bool done = false;
+    if (!f->pos && form_env("EO_FORM_MATRIX_POS", 1)) {
+      size_t free_b = 0, total_b = 0;
+      const size_t need = size_t(nd) * nd * size_t(t->n_cells) * sizeof(int32_t);
+      EO_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+      if (need <= free_b / 4 && cudaMalloc(&f->pos, need) == cudaSuccess) {
+        const unsigned gp = (unsigned)((t->n_cells + 127) / 128);
+#define X(G, B, N)                                                                                                   \
+  if (!done && t->T.gdim == G && t->T.bs == B && t->T.nb == N) {                                                     \
+    form_positions_kernel<B, N><<<gp, 128, 0, ctx->s_cmp>>>(t->dofmap, t->n_cells, f->row_ptr, f->col, f->pos);             \
+    done = true;                                                                                                     \
+  }
+        EO_FORM_CASES(X)
+#undef X
+        ctx->launches += 1;
+      } else {
+        cudaGetLastError();  // a failed cudaMalloc is not an error of this call: fall back to bisection
+        f->pos = nullptr;
+      }
+    }
+    done = false;
 #define X(G, B, N)                                                                                                  \
   if (!done && t->T.gdim == G && t->T.bs == B && t->T.nb == N) {                                                    \
     form_matrix_kernel<G, B, N><<<grid, 128, 0, ctx->s_cmp>>>(t->T, W, kt, ki, t->dofmap, t->x_dofmap, t->x, D, n_cells, \
-                                                              f->row_ptr, f->col, vals);                            \
+                                                              f->row_ptr, f->col, vals, f->pos, t->n_cells, f->missing); \
     done = true;                                                                                                    \
   }
     EO_FORM_CASES(X)
 #undef X
     if (!done) return eo_fail(ctx, EO_ERR_UNSUPPORTED, "eo_form_matrix: no kernel for this element");
     ctx->launches += 1;
+    // element entries outside the pattern are a caller error (a pattern that is not the cell-coupling pattern of this mesh)
+    unsigned miss = 0;
+    EO_CUDA(ctx, cudaMemcpyAsync(&miss, f->missing, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->s_cmp));
+    EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_cmp));
+    if (miss) {
+      EO_CUDA(ctx, cudaMemsetAsync(f->missing, 0, sizeof(unsigned), ctx->s_cmp));
+      if (f->pos) cudaFree(f->pos);
+      f->pos = nullptr;
+      return eo_fail(ctx, EO_ERR_INVALID, "eo_form_matrix: %u element-matrix entries are not in the sparsity pattern", miss);
+    }
   }
   EO_CUDA(ctx, cudaGetLastError());
   return EO_OK;

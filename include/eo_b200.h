@@ -278,6 +278,10 @@ int eo_form_vm_step(eo_form* form, const eo_vm_params* prm, const double* u, con
  * col[nnz] (strictly increasing within a row - what `fem.create_sparsity_pattern` + finalize gives); validated and
  * uploaded once.  eo_form_matrix then adds every element matrix into vals[nnz] (device memory). */
 int eo_form_set_pattern(eo_form* form, const int32_t* row_ptr, const int32_t* col, int64_t nnz);
+/* eo_form_matrix is complete on return (it reads back a miss counter): element entries of the integrated cells that the
+ * pattern does not hold are an error (EO_ERR_INVALID).  The CSR position of every element entry is cached on the device
+ * at the first assembly after eo_form_set_pattern when it fits in a quarter of the free memory ((nb*bs)^2 int32 per
+ * cell); later assemblies then neither search nor touch the pattern. */
 int64_t eo_form_nnz(const eo_form* form);
 int eo_form_matrix(eo_form* form, int kind_test, int kind_trial, const double* D, int64_t n_cells, double* vals,
                    int accumulate);

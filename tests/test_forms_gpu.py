@@ -116,6 +116,17 @@ def test_matrix_csr(ctx):
     _close(vals.to_host(), ref)
     forms.matrix("mandel_strain", "mandel_strain", d_D, vals=vals, accumulate=True)
     _close(vals.to_host(), 2 * ref)
+    # subset of cells on the cached positions; a pattern that misses an element entry is an error
+    part = of.assemble_matrix(ot.MANDEL_STRAIN, ot.MANDEL_STRAIN, D[:nc // 2], W3, m["dofmap"][:nc // 2], 2, m["n_dofs"],
+                              m["x"], m["x_dofmap"][:nc // 2], m["phi"], m["dphi"], m["dpsi"], rp, col)
+    _close(forms.matrix("mandel_strain", "mandel_strain", d_D, n_cells=nc // 2).to_host(), part)
+    tab2, forms2 = _mk(ctx, m, 2)
+    keep = np.ones(col.size, dtype=bool)
+    keep[rp[5] + 1] = False  # drop one off-diagonal entry of row 5
+    rp_bad = np.concatenate([[0], np.cumsum(np.add.reduceat(keep.astype(np.int64), rp[:-1]))]).astype(np.int32)
+    forms2.set_pattern(rp_bad, col[keep])
+    with pytest.raises(eo.EOError):
+        forms2.matrix("mandel_strain", "mandel_strain", d_D)
     # the assembled matrix and the matrix-free action are the same operator
     x = rng.normal(size=2 * m["n_dofs"])
     rows = np.repeat(np.arange(rp.size - 1), np.diff(rp))
