@@ -20,6 +20,8 @@
 // Each DOF of a P2 triangle mesh is touched by 2-6 cells: the REDs see low contention and resolve in L2.  Summation
 // order over cells is not fixed: results agree with the oracle to rounding (tests: 1e-12 of the vector scale), not bit
 // for bit.  What bounds the register-path kernels is the LSU wavefront rate, not HBM (see the table in the summary).
+// This file is compiled with -fmad=false for the step kernel (its per-point results are bit-identical to tab.cu's fused
+// kernel); the vector / action / matrix integrals, compared at a tolerance only, contract with explicit FMAs.
 // The per-cell arithmetic lives in form_core.cuh (host/device; also compiled by the CPU test harness).
 #include "eo_common.cuh"
 #include "tab_core.cuh"
@@ -241,7 +243,7 @@ __global__ void __launch_bounds__(128) form_vector_cell_kernel(const __grid_cons
     }
     double Vs[BS], Gs[BS][GDIM];
     form_cotangent<GDIM, BS>(kind, s, Vs, Gs);
-    form_accumulate<GDIM, BS, NB>(T, kind, q, W.w[q] * adet, Vs, Gs, K, fe);
+    form_accumulate<GDIM, BS, NB, true>(T, kind, q, W.w[q] * adet, Vs, Gs, K, fe);
   }
 #pragma unroll
   for (int a = 0; a < NB; ++a)
@@ -300,25 +302,25 @@ __global__ void __launch_bounds__(128) form_action_cell_kernel(const __grid_cons
 #pragma unroll
   for (int q = 0; q < nq; ++q) {
     double val[BS], grad[BS][GDIM], e[MAXC], tau[MAXC];
-    tab_point<GDIM, BS, NB>(T, w, K, q, kind_trial == 0, kind_trial != 0, val, grad);
+    tab_point<GDIM, BS, NB, true>(T, w, K, q, kind_trial == 0, kind_trial != 0, val, grad);
     tab_operand<GDIM, BS>(kind_trial, val, grad, e);
     if (vec44) {
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const eo_d4 dd = NQ > 0 ? d[NQ > 0 ? q : 0][r] : eo_ld256(D_ptr + 16 * q + 4 * r);
-        tau[r] = dd.x * e[0] + dd.y * e[1] + dd.z * e[2] + dd.w * e[3];
+        tau[r] = fma(dd.w, e[3], fma(dd.z, e[2], fma(dd.y, e[1], dd.x * e[0])));
       }
     } else {
       const double* Dq = D_ptr + int64_t(q) * nt * ni;
       for (int r = 0; r < nt; ++r) {
         double acc = 0.0;
-        for (int l = 0; l < ni; ++l) acc += eo_ld64(Dq + r * ni + l) * e[l];
+        for (int l = 0; l < ni; ++l) acc = fma(eo_ld64(Dq + r * ni + l), e[l], acc);
         tau[r] = acc;
       }
     }
     double Vs[BS], Gs[BS][GDIM];
     form_cotangent<GDIM, BS>(kind_test, tau, Vs, Gs);
-    form_accumulate<GDIM, BS, NB>(T, kind_test, q, W.w[q] * adet, Vs, Gs, K, fe);
+    form_accumulate<GDIM, BS, NB, true>(T, kind_test, q, W.w[q] * adet, Vs, Gs, K, fe);
   }
 #pragma unroll
   for (int a = 0; a < NB; ++a)
@@ -385,18 +387,18 @@ __global__ void __launch_bounds__(128) form_action_tma_kernel(const __grid_const
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
     double val[2] = {0.0, 0.0}, grad[2][2], e[4], tau[4];
-    tab_point<2, 2, NB>(T, w, K, q, false, true, val, grad);
+    tab_point<2, 2, NB, true>(T, w, K, q, false, true, val, grad);
     tab_operand<2, 2>(kind_trial, val, grad, e);
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       double d0, d1, d2, d3;
       asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(d0), "=d"(d1) : "r"(my + q * 128 + r * 32));
       asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(d2), "=d"(d3) : "r"(my + q * 128 + r * 32 + 16));
-      tau[r] = d0 * e[0] + d1 * e[1] + d2 * e[2] + d3 * e[3];
+      tau[r] = fma(d3, e[3], fma(d2, e[2], fma(d1, e[1], d0 * e[0])));
     }
     double Vs[2], Gs[2][2];
     form_cotangent<2, 2>(kind_test, tau, Vs, Gs);
-    form_accumulate<2, 2, NB>(T, kind_test, q, W.w[q] * adet, Vs, Gs, K, fe);
+    form_accumulate<2, 2, NB, true>(T, kind_test, q, W.w[q] * adet, Vs, Gs, K, fe);
   }
 #pragma unroll
   for (int a = 0; a < NB; ++a)
@@ -539,12 +541,12 @@ __global__ void __launch_bounds__(128) form_matrix_kernel(const __grid_constant_
         const double* Dq = D_ptr + int64_t(q) * nt * ni;
         for (int r = 0; r < nt; ++r) {
           double acc = 0.0;
-          for (int l = 0; l < ni; ++l) acc += __ldg(Dq + r * ni + l) * e[l];
+          for (int l = 0; l < ni; ++l) acc = fma(__ldg(Dq + r * ni + l), e[l], acc);
           tau[r] = acc;
         }
         double Vs[BS], Gs[BS][GDIM];
         form_cotangent<GDIM, BS>(kind_test, tau, Vs, Gs);
-        form_accumulate<GDIM, BS, NB>(T, kind_test, q, W.w[q] * adet, Vs, Gs, K, fe);
+        form_accumulate<GDIM, BS, NB, true>(T, kind_test, q, W.w[q] * adet, Vs, Gs, K, fe);
       }
       const int32_t gcol = BS * __ldg(dofmap + c * NB + bj) + cj;
 #pragma unroll

@@ -66,7 +66,7 @@ template <int GDIM, int NB>
 EO_TAB_HD double form_dphi(const form_tabs<GDIM, NB>& S, int k, int q, int a);
 
 // fe[a][c] += scale * ( Vs[c] phi[q][a] + sum_k (sum_j Gs[c][j] K[k][j]) dphi[k][q][a] )   - transpose of tab_point
-template <int GDIM, int BS, int NB, class Tables>
+template <int GDIM, int BS, int NB, bool FMA = false, class Tables>
 EO_TAB_HD void form_accumulate(const Tables& T, int kind, int q, double scale, const double Vs[BS],
                                                 const double Gs[BS][GDIM], const double K[GDIM][GDIM],
                                                 double fe[NB][BS]) {
@@ -75,7 +75,7 @@ EO_TAB_HD void form_accumulate(const Tables& T, int kind, int q, double scale, c
     for (int a = 0; a < NB; ++a) {
       const double ph = scale * form_phi(T, q, a);
 #pragma unroll
-      for (int c = 0; c < BS; ++c) fe[a][c] += Vs[c] * ph;
+      for (int c = 0; c < BS; ++c) fe[a][c] = tab_madd<FMA>(Vs[c], ph, fe[a][c]);
     }
     return;
   }
@@ -86,7 +86,7 @@ EO_TAB_HD void form_accumulate(const Tables& T, int kind, int q, double scale, c
     for (int k = 0; k < GDIM; ++k) {
       double acc = 0.0;
 #pragma unroll
-      for (int j = 0; j < GDIM; ++j) acc += Gs[c][j] * K[k][j];
+      for (int j = 0; j < GDIM; ++j) acc = tab_madd<FMA>(Gs[c][j], K[k][j], acc);
       H[c][k] = scale * acc;
     }
 #pragma unroll
@@ -95,7 +95,7 @@ EO_TAB_HD void form_accumulate(const Tables& T, int kind, int q, double scale, c
     for (int c = 0; c < BS; ++c) {
       double acc = 0.0;
 #pragma unroll
-      for (int k = 0; k < GDIM; ++k) acc += H[c][k] * form_dphi(T, k, q, a);
+      for (int k = 0; k < GDIM; ++k) acc = tab_madd<FMA>(H[c][k], form_dphi(T, k, q, a), acc);
       fe[a][c] += acc;
     }
 }

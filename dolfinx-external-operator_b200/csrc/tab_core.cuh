@@ -16,6 +16,7 @@
 typedef int int32_t;
 typedef long long int64_t;
 #else
+#include <cmath>
 #include <cstdint>
 #endif
 
@@ -79,8 +80,19 @@ EO_TAB_HD void tab_geometry(const tab_tables& T, const double xv[GDIM + 1][GDIM]
   tab_inverse<GDIM>(J, K);
 }
 
+// acc + a * b, as two roundings (the files that include this header are compiled with -fmad=false so that the
+// tabulation kernels agree bit for bit among themselves) or as one fused operation (FMA = true: consumers that are
+// compared at a tolerance only - the form kernels' action / vector / matrix integrals)
+template <bool FMA>
+EO_TAB_HD double tab_madd(double a, double b, double acc) {
+  if constexpr (FMA)
+    return fma(a, b, acc);
+  else
+    return acc + a * b;
+}
+
 // function value and physical gradient at evaluation point q:  w[a][c] gathered coefficients
-template <int GDIM, int BS, int NB>
+template <int GDIM, int BS, int NB, bool FMA = false>
 EO_TAB_HD void tab_point(const tab_tables& T, const double w[NB][BS], const double K[GDIM][GDIM], int q, bool want_value,
                          bool want_grad, double val[BS], double grad[BS][GDIM]) {
   if (want_value) {
@@ -88,7 +100,7 @@ EO_TAB_HD void tab_point(const tab_tables& T, const double w[NB][BS], const doub
     for (int c = 0; c < BS; ++c) {
       double acc = 0.0;
 #pragma unroll
-      for (int a = 0; a < NB; ++a) acc += w[a][c] * T.phi[q][a];
+      for (int a = 0; a < NB; ++a) acc = tab_madd<FMA>(w[a][c], T.phi[q][a], acc);
       val[c] = acc;
     }
   }
@@ -100,7 +112,7 @@ EO_TAB_HD void tab_point(const tab_tables& T, const double w[NB][BS], const doub
       for (int k = 0; k < GDIM; ++k) {
         double acc = 0.0;
 #pragma unroll
-        for (int a = 0; a < NB; ++a) acc += w[a][c] * T.dphi[k][q][a];
+        for (int a = 0; a < NB; ++a) acc = tab_madd<FMA>(w[a][c], T.dphi[k][q][a], acc);
         G[c][k] = acc;
       }
 #pragma unroll
@@ -109,7 +121,7 @@ EO_TAB_HD void tab_point(const tab_tables& T, const double w[NB][BS], const doub
       for (int j = 0; j < GDIM; ++j) {
         double acc = 0.0;
 #pragma unroll
-        for (int k = 0; k < GDIM; ++k) acc += G[c][k] * K[k][j];
+        for (int k = 0; k < GDIM; ++k) acc = tab_madd<FMA>(G[c][k], K[k][j], acc);
         grad[c][j] = acc;
       }
   }
