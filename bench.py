@@ -40,6 +40,10 @@ sys.path.insert(0, ROOT)
 BYTES_PER_QP = {"vm": 240, "jitvm": 240, "jitfused": 235, "jitvm3d": 448, "heat": 88, "mc": 252, "tab": 176.0 / 3.0, "fused": 235, "isihara": 192,
                 # device-side consumers (csrc/form.cu): + read-modify-write of the DOF vector (2 nodes x 2 x 8 B per cell, twice)
                 "step": 235 + 64.0 / 3.0, "action": 128 + 80.0 / 3.0 + 64.0 / 3.0}
+# per P2-triangle cell: dofmap 24 + x_dofmap 12 + 6 gathered dofs x 16 + 3 gathered vertices x 16 = 180 B (vs 80 B unique)
+_CELL_GATHER = (24 + 12 + 96 + 48) / 3.0
+GATHERED_BYTES_PER_QP = {"tab": _CELL_GATHER + 32, "fused": _CELL_GATHER + 40 + 168, "jitfused": _CELL_GATHER + 40 + 168,
+                         "step": _CELL_GATHER + 40 + 168 + 12 * 16 / 3.0, "action": _CELL_GATHER + 128 + 12 * 16 / 3.0}
 METRIC = "quadrature points per second (stress + consistent tangent + internal state)"
 
 
@@ -712,6 +716,13 @@ def run_gpu_arm(args):
         roofline = {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                     "frac": hbm_achieved / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
                     "bytes_per_qp": BYTES_PER_QP[model], "kernel_ms": k_ms}
+        if model in GATHERED_BYTES_PER_QP:
+            # the gather-limited kernels report the unique-byte fraction (above: what must cross HBM once)
+            # and the gathered-byte fraction (what the threads request: every cell's own copy of its dofs / vertices)
+            gb = GATHERED_BYTES_PER_QP[model]
+            ga = gb * n / (k_ms * 1e-3) / 1e9
+            roofline["gathered"] = {"bytes_per_qp": gb, "achieved": ga, "unit": "GB/s", "frac_of_hbm_peak": ga / hbm_peak,
+                                    "note": "requested bytes (per-cell copies of shared dofs / vertices served by L1/L2)"}
 
     # ---- CPU baseline on this box's host cores (bounded sample)
     cpu = None
