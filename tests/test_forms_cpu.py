@@ -182,3 +182,30 @@ def test_form_core_action_against_oracle(hc, case):
     got = _host_form(hc, m, bs, w, kt, ki, D, x)
     ref = of.apply_action(kt, ki, D, x, w, m["dofmap"], bs, m["n_dofs"], *_geo(m))
     np.testing.assert_allclose(got, ref, rtol=0, atol=1e-13 * np.abs(ref).max())
+
+
+def test_three_point_rule_is_exact_for_the_p2_stiffness():
+    """Known answer independent of the 3-point rule: on affine cells the P2 strain-displacement products are quadratic, so
+    the demos' 3-point rule integrates the constant-tangent stiffness exactly - compare with the 6-point degree-4
+    Dunavant rule on the same tables machinery (different points, different weights)."""
+    a1, b1, w1 = 0.445948490915965, 0.108103018168070, 0.223381589678011
+    a2, b2, w2 = 0.091576213509771, 0.816847572980459, 0.109951743655322
+    X6 = np.array([[a1, a1], [a1, b1], [b1, a1], [a2, a2], [a2, b2], [b2, a2]])
+    W6 = 0.5 * np.array([w1, w1, w1, w2, w2, w2])
+    m = tri_case(nx=6, ny=5)
+    phi6, dphi6 = el.lagrange_triangle(2, X6)
+    Ce = oc.elastic_stiffness(oc.VonMisesParams().lmbda, oc.VonMisesParams().mu)
+    nc = m["dofmap"].shape[0]
+    K3 = of.element_matrices(ot.MANDEL_STRAIN, ot.MANDEL_STRAIN, np.broadcast_to(Ce.reshape(-1), (nc, 3, 16)), W3, m["dofmap"], 2,
+                             m["x"], m["x_dofmap"], m["phi"], m["dphi"], m["dpsi"])
+    K6 = of.element_matrices(ot.MANDEL_STRAIN, ot.MANDEL_STRAIN, np.broadcast_to(Ce.reshape(-1), (nc, 6, 16)), W6, m["dofmap"], 2,
+                             m["x"], m["x_dofmap"], phi6, dphi6, m["dpsi"])
+    np.testing.assert_allclose(K3, K6, rtol=0, atol=1e-12 * np.abs(K6).max())
+    # and the mass-like integral of a product of two P2 functions (degree 4) is NOT exact with 3 points: the check above
+    # is a statement about the rule, not a tautology of the machinery
+    M3 = of.element_matrices(ot.VALUE, ot.VALUE, np.broadcast_to(np.eye(2).reshape(-1), (nc, 3, 4)), W3, m["dofmap"], 2,
+                             m["x"], m["x_dofmap"], m["phi"], m["dphi"], m["dpsi"])
+    M6 = of.element_matrices(ot.VALUE, ot.VALUE, np.broadcast_to(np.eye(2).reshape(-1), (nc, 6, 4)), W6, m["dofmap"], 2,
+                             m["x"], m["x_dofmap"], phi6, dphi6, m["dpsi"])
+    assert np.abs(M3 - M6).max() > 1e-3 * np.abs(M6).max()
+    assert abs(M6.sum() - 2 * 1.0) < 1e-12  # sum_ij int phi_i phi_j = |domain| per component
