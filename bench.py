@@ -145,39 +145,31 @@ def cpu_port_rate(model: str, sample_n: int, min_seconds: float, parallel: bool 
 
 
 def cpu_tab_rate(model: str, min_seconds: float):
-    """CPU baseline for the tabulation legs: the NumPy oracle (einsum over all cells) on a bounded mesh."""
+    """CPU baseline for the cell-loop legs (tab / fused / step / action): the OpenMP C restatement of the von Mises demo's
+    cell loop (oracle/csrc/forms_oracle.c: tabulation of the Mandel strain, radial return, residual scatter, tangent
+    action) on all host cores, on a bounded mesh (1.28 M cells = 3.84 M quadrature points)."""
     from dolfinx_external_operator_b200 import elements as el
     from dolfinx_external_operator_b200 import synthetic as syn
     from oracle import constitutive as oc
     from oracle import native
-    from oracle import forms as of
-    from oracle import tabulation as ot
 
-    native.use_all_cores()
-    nxy = 150 if model in ("step", "action") else 400  # the forms oracle builds dense per-cell operand matrices
-    m = syn.triangle_mesh(nxy, nxy, 2, jitter=0.2, seed=0)
-    phi, dphi = el.lagrange_triangle(2, el.triangle_quadrature(2))
-    dpsi = el.p1_geometry_derivatives(2)
+    cores = native.use_all_cores()
+    m = syn.triangle_mesh(800, 800, 2, jitter=0.2, seed=0)
+    m["phi"], m["dphi"] = el.lagrange_triangle(2, el.triangle_quadrature(2))
+    m["dpsi"] = el.p1_geometry_derivatives(2)
     u = syn.smooth_displacement(m["dof_coords"], scale=1.5e-3, seed=0).reshape(-1)
     nq = 3 * m["dofmap"].shape[0]
     _, sn, p = syn.vm_batch(nq, seed=0)
-
     W3 = el.triangle_quadrature_weights(2)
-    geo = (m["x"], m["x_dofmap"], phi, dphi, dpsi)
-    Ct0 = None
-    if model == "action":
-        e = ot.tabulate(ot.MANDEL_STRAIN, u, m["dofmap"], 2, *geo)
-        Ct0 = native.vm_return_mapping(e.reshape(-1, 4), sn, p, oc.VonMisesParams(), parallel=True)[0]
+    prm = oc.VonMisesParams()
+    mode = {"tab": "tab", "fused": "fused", "jitfused": "fused", "step": "step", "action": "action"}[model]
+    Ct0 = native.forms_p2_cells("fused", m, W3, u, prm, sn, p)[0] if mode == "action" else None
 
     def fn():
-        if model == "action":
-            of.apply_action(ot.MANDEL_STRAIN, ot.MANDEL_STRAIN, Ct0, u, W3, m["dofmap"], 2, m["n_dofs"], *geo)
-            return
-        e = ot.tabulate(ot.MANDEL_STRAIN, u, m["dofmap"], 2, *geo)
-        if model in ("fused", "step"):
-            r = native.vm_return_mapping(e.reshape(-1, 4), sn, p, oc.VonMisesParams(), parallel=True)
-            if model == "step":
-                of.assemble_vector(ot.MANDEL_STRAIN, r[1], W3, m["dofmap"], 2, m["n_dofs"], *geo)
+        if mode == "action":
+            native.forms_p2_cells("action", m, W3, u, C_tang=Ct0)
+        else:
+            native.forms_p2_cells(mode, m, W3, u, prm, sn, p)
 
     fn()
     best, passes, t_all = float("inf"), 0, time.perf_counter()
@@ -188,11 +180,13 @@ def cpu_tab_rate(model: str, min_seconds: float):
         passes += 1
         if time.perf_counter() - t_all >= min_seconds and passes >= 3:
             break
-    return {"value": nq / best, "unit": "QP/s", "cores": native.num_threads() if model in ("fused", "step") else 1, "kind": "port",
-            "sample": f"{nq} QPs x {passes} passes (best pass); NumPy einsum restatement of the DOLFINx/FFCx tabulation "
-                      "(single-threaded)" + (" + OpenMP C restatement of the von Mises kernel" if model in ("fused", "step") else "")
-                      + (" + NumPy restatement of the element loop of assemble_vector" if model == "step" else "")
-                      + ("; NumPy restatement of the element loop (tangent action)" if model == "action" else "")}
+    what = {"tab": "tabulation of the Mandel strain", "fused": "tabulation + von Mises radial return",
+            "step": "tabulation + von Mises radial return + residual scatter",
+            "action": "tangent action (tabulate x, contract with the stored tangent, scatter)"}[mode]
+    return {"value": nq / best, "unit": "QP/s", "cores": cores, "kind": "port",
+            "sample": f"{nq} QPs x {passes} passes (best pass, includes allocating the result arrays); OpenMP C restatement "
+                      f"of the demo's cell loop ({what}; the reference runs it serially per MPI rank through DOLFINx/FFCx "
+                      "and Numba)"}
 
 
 def e2e_device_consumers(ctx, eo, inputs, ne, rank, world, max_over_ranks, barrier):

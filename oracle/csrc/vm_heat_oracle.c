@@ -80,6 +80,12 @@ static void vm_point(const oracle_vm_params* q, const double* deps, const double
   *dp_out = dp;
 }
 
+/* the same point update for the cell loop of forms_oracle.c */
+void oracle_vm_point(const oracle_vm_params* q, const double* deps, const double* sn, double p, double* Ct, double* sig,
+                     double* dp_out) {
+  vm_point(q, deps, sn, p, Ct, sig, dp_out);
+}
+
 /* AoS layouts exactly as the reference returns them (demo_vm:352):
  * deps/sigma_n/sigma [n][4], p/dp [n], C_tang [n][4][4]. */
 void oracle_vm_return_mapping(const oracle_vm_params* q, const double* deps, const double* sigma_n, const double* p,

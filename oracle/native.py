@@ -125,3 +125,41 @@ def mc_yield(sigma, prm):
     q = _mc_prm(prm)
     lib.oracle_mc_yield(C.byref(q), _p(sigma), _p(f), C.c_int64(sigma.shape[0]))
     return f
+
+
+def forms_p2_cells(mode: str, m: dict, weights, u, prm=None, sigma_n=None, p=None, C_tang=None):
+    """OpenMP C restatement of the von Mises demo's cell loop on a 2-d vector Lagrange mesh dict `m` (dofmap, x_dofmap, x,
+    dphi (2, nq, nb), dpsi): mode 'tab' -> strain (n_cells, nq, 4); 'fused' -> (C_tang, sigma, dp); 'step' -> (b, C_tang,
+    sigma, dp); 'action' -> y = A u with the given C_tang.  CPU baseline of the corresponding bench legs."""
+    lib = load()
+    code = {"tab": 0, "fused": 1, "step": 2, "action": 3}[mode]
+    dm = np.ascontiguousarray(m["dofmap"], dtype=np.int32)
+    xd = np.ascontiguousarray(m["x_dofmap"], dtype=np.int32)
+    x = np.ascontiguousarray(m["x"], dtype=np.float64)
+    dphi = np.ascontiguousarray(m["dphi"], dtype=np.float64)
+    dpsi = np.ascontiguousarray(m["dpsi"], dtype=np.float64)
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1)
+    nc, nb = dm.shape
+    nq = dphi.shape[1]
+    n = nc * nq
+    if nb > 10 or nq > 16 or dphi.shape[0] != 2:
+        raise ValueError("forms_p2_cells: 2-d elements with nb <= 10, nq <= 16")
+    strain = np.empty((nc, nq, 4)) if code == 0 else None
+    if code in (1, 2):
+        C_tang, sigma, dp = np.empty((n, 4, 4)), np.empty((n, 4)), np.empty(n)
+        sigma_n = np.ascontiguousarray(sigma_n, dtype=np.float64).reshape(-1, 4)
+        p = np.ascontiguousarray(p, dtype=np.float64).reshape(-1)
+        q = OracleVmParams(prm.lmbda, prm.mu, prm.H, prm.sigma_0)
+    else:
+        sigma = dp = None
+        q = OracleVmParams(0.0, 0.0, 0.0, 0.0)
+        if code == 3:
+            C_tang = np.ascontiguousarray(C_tang, dtype=np.float64).reshape(-1, 16)
+    vec = np.zeros(2 * m["n_dofs"]) if code >= 2 else None
+    lib.oracle_forms_p2_cells(C.c_int(code), C.c_int(nb), C.c_int(nq), _p(dphi), _p(dpsi), _p(w), _p(dm), _p(xd), _p(x), _p(u),
+                              C.byref(q), None if sigma_n is None else _p(sigma_n), None if p is None else _p(p),
+                              None if strain is None else _p(strain), None if C_tang is None else _p(C_tang),
+                              None if sigma is None else _p(sigma), None if dp is None else _p(dp),
+                              None if vec is None else _p(vec), C.c_int64(nc))
+    return {"tab": strain, "fused": (C_tang, sigma, dp), "step": (vec, C_tang, sigma, dp), "action": vec}[mode]

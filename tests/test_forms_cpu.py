@@ -209,3 +209,32 @@ def test_three_point_rule_is_exact_for_the_p2_stiffness():
                              m["x"], m["x_dofmap"], phi6, dphi6, m["dpsi"])
     assert np.abs(M3 - M6).max() > 1e-3 * np.abs(M6).max()
     assert abs(M6.sum() - 2 * 1.0) < 1e-12  # sum_ij int phi_i phi_j = |domain| per component
+
+
+def test_c_cell_loop_against_the_numpy_oracles():
+    """oracle/csrc/forms_oracle.c (the OpenMP CPU baseline of the tab / fused / step / action bench legs) reproduces the
+    NumPy oracles: strain, radial return (bit-exact flags), residual and tangent action."""
+    from oracle import native
+
+    m = tri_case(nx=11, ny=8)
+    n = m["dofmap"].shape[0] * 3
+    rng = np.random.default_rng(3)
+    sigma_n, p = rng.normal(0.0, 100.0, (n, 4)), np.abs(rng.normal(0.0, 1e-3, n))
+    u = syn.smooth_displacement(m["dof_coords"], scale=6e-4, seed=3).reshape(-1)
+    prm = oc.VonMisesParams()
+    eps_ref = ot.tabulate(ot.MANDEL_STRAIN, u, m["dofmap"], 2, *_geo(m))
+    eps = native.forms_p2_cells("tab", m, W3, u)
+    np.testing.assert_allclose(eps, eps_ref, rtol=0, atol=1e-13 * np.abs(eps_ref).max())
+    rCt, rsig, rdp = oc.vm_return_mapping(eps_ref.reshape(-1, 4), sigma_n, p, prm)
+    b, Ct, sig, dp = native.forms_p2_cells("step", m, W3, u, prm, sigma_n, p)
+    assert np.array_equal(dp > 0, np.asarray(rdp).reshape(-1) > 0) and 0.2 < (dp > 0).mean() < 0.8
+    np.testing.assert_allclose(Ct, rCt, rtol=0, atol=1e-11 * np.abs(rCt).max())
+    np.testing.assert_allclose(sig, rsig, rtol=0, atol=1e-12 * np.abs(rsig).max())
+    b_ref = of.assemble_vector(ot.MANDEL_STRAIN, rsig, W3, m["dofmap"], 2, m["n_dofs"], *_geo(m))
+    np.testing.assert_allclose(b, b_ref, rtol=0, atol=1e-12 * np.abs(b_ref).max())
+    Ct2, sig2, dp2 = native.forms_p2_cells("fused", m, W3, u, prm, sigma_n, p)
+    assert np.array_equal(Ct2, Ct) and np.array_equal(sig2, sig) and np.array_equal(dp2, dp)
+    x = rng.normal(size=u.size)
+    y = native.forms_p2_cells("action", m, W3, x, C_tang=Ct)
+    y_ref = of.apply_action(ot.MANDEL_STRAIN, ot.MANDEL_STRAIN, Ct, x, W3, m["dofmap"], 2, m["n_dofs"], *_geo(m))
+    np.testing.assert_allclose(y, y_ref, rtol=0, atol=1e-12 * np.abs(y_ref).max())
