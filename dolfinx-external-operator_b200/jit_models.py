@@ -5,7 +5,6 @@ golden vectors)."""
 
 from __future__ import annotations
 
-import numpy as np
 
 # von Mises radial return, plane-strain Mandel 4-vectors: sigma(deps; sigma_n, p) and aux = dp.
 # Statements follow doc/demo/demo_plasticity_von_mises.py:307-320; the tangent of :322-326 is NOT written
