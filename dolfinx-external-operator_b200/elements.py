@@ -33,7 +33,7 @@ def triangle_quadrature_weights(degree: int) -> np.ndarray:
 
 
 def lagrange_triangle(degree: int, X: np.ndarray):
-    """(phi (nq, nb), dphi (2, nq, nb)) of P1 / P2 on the reference triangle at points X (nq, 2)."""
+    """(phi (nq, nb), dphi (2, nq, nb)) of P1 / P2 / P3 on the reference triangle at points X (nq, 2)."""
     x, y = X[:, 0], X[:, 1]
     one, zero = np.ones_like(x), np.zeros_like(x)
     if degree == 1:
@@ -45,9 +45,50 @@ def lagrange_triangle(degree: int, X: np.ndarray):
         phi = np.stack([l0 * (2 * l0 - 1), x * (2 * x - 1), y * (2 * y - 1), 4 * x * y, 4 * y * l0, 4 * x * l0], axis=1)
         dx = np.stack([-(4 * l0 - 1), 4 * x - 1, zero, 4 * y, -4 * y, 4 * (l0 - x)], axis=1)
         dy = np.stack([-(4 * l0 - 1), zero, 4 * y - 1, 4 * x, 4 * (l0 - y), -4 * x], axis=1)
+    elif degree == 3:
+        # equispaced P3: vertices, two nodes per edge (edge0=(v1,v2), edge1=(v0,v2), edge2=(v0,v1), from the lower to the
+        # higher local vertex), interior node.  (DOLFINx's default P3 variant is GLL-warped: production tables come from
+        # basix; this closed form only has to be consistent with the dofmaps of the synthetic meshes.)
+        l = [1 - x - y, x, y]  # noqa: E741
+        dl = [(-one, -one), (one, zero), (zero, one)]
+        funcs = []  # (value, d/dx, d/dy) built from barycentric products
+
+        def vert(i):
+            li = l[i]
+            v = 0.5 * li * (3 * li - 1) * (3 * li - 2)
+            dv = 0.5 * ((3 * li - 1) * (3 * li - 2) + 3 * li * (3 * li - 2) + 3 * li * (3 * li - 1))
+            return v, dv * dl[i][0], dv * dl[i][1]
+
+        def edge(i, j):  # node at 1/3 from vertex i towards vertex j
+            li, lj = l[i], l[j]
+            v = 4.5 * li * lj * (3 * li - 1)
+            dvi, dvj = 4.5 * lj * (6 * li - 1), 4.5 * li * (3 * li - 1)
+            return v, dvi * dl[i][0] + dvj * dl[j][0], dvi * dl[i][1] + dvj * dl[j][1]
+
+        funcs += [vert(0), vert(1), vert(2)]
+        funcs += [edge(1, 2), edge(2, 1), edge(0, 2), edge(2, 0), edge(0, 1), edge(1, 0)]
+        b = 27.0 * l[0] * l[1] * l[2]
+        db = [27.0 * (l[1] * l[2] * dl[0][k] + l[0] * l[2] * dl[1][k] + l[0] * l[1] * dl[2][k]) for k in (0, 1)]
+        funcs.append((b, db[0], db[1]))
+        phi = np.stack([f[0] for f in funcs], axis=1)
+        dx = np.stack([f[1] for f in funcs], axis=1)
+        dy = np.stack([f[2] for f in funcs], axis=1)
     else:
-        raise NotImplementedError("closed-form tables for P1 and P2 only; pass basix tables for higher degrees")
+        raise NotImplementedError("closed-form tables for P1, P2 and P3; pass basix tables for higher degrees")
     return np.ascontiguousarray(phi), np.ascontiguousarray(np.stack([dx, dy]))
+
+
+def lagrange_triangle_nodes(degree: int) -> np.ndarray:
+    """Reference coordinates of the nodes of `lagrange_triangle(degree, .)`, in its ordering."""
+    if degree == 1:
+        return np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0]])
+    if degree == 2:
+        return np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0], [0.5, 0.5], [0.0, 0.5], [0.5, 0.0]])
+    if degree == 3:
+        t = 1.0 / 3.0
+        return np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0], [2 * t, t], [t, 2 * t], [0.0, t], [0.0, 2 * t], [t, 0.0],
+                         [2 * t, 0.0], [t, t]])
+    raise NotImplementedError
 
 
 def lagrange_tetrahedron(degree: int, X: np.ndarray):

@@ -93,6 +93,8 @@ int hostcheck_form(int gdim, int bs, int nb, int nq, int kind_test, int kind_tri
   if (gdim == 2 && bs == 2 && nb == 6) form_cells<2, 2, 6>(T, weights, kind_test, kind_trial, dofmap, x_dofmap, xg, D, x, n_cells, y);
   else if (gdim == 2 && bs == 1 && nb == 3) form_cells<2, 1, 3>(T, weights, kind_test, kind_trial, dofmap, x_dofmap, xg, D, x, n_cells, y);
   else if (gdim == 2 && bs == 1 && nb == 6) form_cells<2, 1, 6>(T, weights, kind_test, kind_trial, dofmap, x_dofmap, xg, D, x, n_cells, y);
+  else if (gdim == 2 && bs == 2 && nb == 10) form_cells<2, 2, 10>(T, weights, kind_test, kind_trial, dofmap, x_dofmap, xg, D, x, n_cells, y);
+  else if (gdim == 2 && bs == 1 && nb == 10) form_cells<2, 1, 10>(T, weights, kind_test, kind_trial, dofmap, x_dofmap, xg, D, x, n_cells, y);
   else if (gdim == 3 && bs == 3 && nb == 4) form_cells<3, 3, 4>(T, weights, kind_test, kind_trial, dofmap, x_dofmap, xg, D, x, n_cells, y);
   else return -1;
   return 0;
@@ -122,6 +124,8 @@ int hostcheck_tab(int gdim, int bs, int nb, int nq, int kind, const double* phi,
   if (gdim == 2 && bs == 2 && nb == 6) tab_cells<2, 2, 6>(T, kind, dofmap, x_dofmap, x, u, n_cells, out);
   else if (gdim == 2 && bs == 1 && nb == 3) tab_cells<2, 1, 3>(T, kind, dofmap, x_dofmap, x, u, n_cells, out);
   else if (gdim == 2 && bs == 2 && nb == 3) tab_cells<2, 2, 3>(T, kind, dofmap, x_dofmap, x, u, n_cells, out);
+  else if (gdim == 2 && bs == 2 && nb == 10) tab_cells<2, 2, 10>(T, kind, dofmap, x_dofmap, x, u, n_cells, out);
+  else if (gdim == 2 && bs == 1 && nb == 10) tab_cells<2, 1, 10>(T, kind, dofmap, x_dofmap, x, u, n_cells, out);
   else if (gdim == 3 && bs == 3 && nb == 4) tab_cells<3, 3, 4>(T, kind, dofmap, x_dofmap, x, u, n_cells, out);
   else return -1;
   return 0;

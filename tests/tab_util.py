@@ -16,6 +16,24 @@ def tri_case(nx=9, ny=7, degree=2, qdeg=2, jitter=0.3, seed=1):
     return m
 
 
+def tri_case_discontinuous(degree=3, nx=5, ny=4, jitter=0.3, seed=1, qdeg=2):
+    """Jittered triangles with a cell-wise (discontinuous) numbering of a degree-`degree` Lagrange space: every cell owns
+    its nb nodes, dofmap = arange.  Enough to exercise gather / contraction / scatter of elements the structured
+    generators do not number globally (P3: nb = 10)."""
+    g = syn.triangle_mesh(nx, ny, 1, jitter=jitter, seed=seed)
+    X = el.triangle_quadrature(qdeg)
+    phi, dphi = el.lagrange_triangle(degree, X)
+    nodes = el.lagrange_triangle_nodes(degree)
+    P1n, _ = el.lagrange_triangle(1, nodes)  # affine map of the reference nodes
+    nc, nb = g["x_dofmap"].shape[0], nodes.shape[0]
+    xv = g["x"][g["x_dofmap"]][:, :, :2]
+    dof_coords = np.einsum("cvi,av->cai", xv, P1n).reshape(nc * nb, 2)
+    P1phi, _ = el.lagrange_triangle(1, X)
+    return {"x": g["x"], "x_dofmap": g["x_dofmap"], "dofmap": np.arange(nc * nb, dtype=np.int32).reshape(nc, nb),
+            "n_dofs": nc * nb, "dof_coords": dof_coords, "phi": phi, "dphi": dphi, "dpsi": el.p1_geometry_derivatives(2),
+            "X": X, "xq": np.einsum("cvi,qv->cqi", xv, P1phi)}
+
+
 def tet_case(n=3, seed=0):
     """A few P1 tetrahedra: the 6-tet split of each cube of an n^3 grid (jittered)."""
     rng = np.random.default_rng(seed)

@@ -238,3 +238,25 @@ def test_c_cell_loop_against_the_numpy_oracles():
     y = native.forms_p2_cells("action", m, W3, x, C_tang=Ct)
     y_ref = of.apply_action(ot.MANDEL_STRAIN, ot.MANDEL_STRAIN, Ct, x, W3, m["dofmap"], 2, m["n_dofs"], *_geo(m))
     np.testing.assert_allclose(y, y_ref, rtol=0, atol=1e-12 * np.abs(y_ref).max())
+
+
+def test_form_core_p3_against_oracle(hc):
+    """nb = 10 (P3 triangles, cell-wise numbering): the kernels' core vs the oracle for vector and action, and the adjoint
+    identity with the P3 tabulation."""
+    from tab_util import tri_case_discontinuous
+
+    m = tri_case_discontinuous(degree=3)
+    rng = np.random.default_rng(4)
+    nc = m["dofmap"].shape[0]
+    for bs, kt, ki in ((2, ot.MANDEL_STRAIN, ot.MANDEL_STRAIN), (1, ot.GRAD, ot.VALUE)):
+        s = rng.normal(size=(nc, 3, of.ncomp(kt, bs, 2)))
+        ref = of.assemble_vector(kt, s, W3, m["dofmap"], bs, m["n_dofs"], *_geo(m))
+        np.testing.assert_allclose(_host_form(hc, m, bs, W3, kt, 0, s), ref, rtol=0, atol=1e-13 * np.abs(ref).max())
+        u = rng.normal(size=bs * m["n_dofs"])
+        op = ot.tabulate(kt, u, m["dofmap"], bs, *_geo(m))
+        _, adet = of.operand_matrix(kt, m["dofmap"], bs, *_geo(m))
+        lhs = np.einsum("cqk,cqk,q,c->", op, s, W3, adet)
+        assert abs(lhs - u @ ref) <= 1e-12 * abs(lhs)
+        D = rng.normal(size=(nc, 3, of.ncomp(kt, bs, 2) * of.ncomp(ki, bs, 2)))
+        yref = of.apply_action(kt, ki, D, u, W3, m["dofmap"], bs, m["n_dofs"], *_geo(m))
+        np.testing.assert_allclose(_host_form(hc, m, bs, W3, kt, ki, D, u), yref, rtol=0, atol=1e-13 * np.abs(yref).max())

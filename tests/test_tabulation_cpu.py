@@ -103,3 +103,26 @@ def test_tab_core_against_oracle_p1_scalar_and_tets(hc):
     u = np.random.default_rng(0).normal(size=t["n_dofs"] * 3)
     ref = ot.tabulate(ot.GRAD, u, t["dofmap"], 3, t["x"], t["x_dofmap"], t["phi"], t["dphi"], t["dpsi"])
     np.testing.assert_allclose(_hc_tab(hc, t, ot.GRAD, u, 3, 3, 9), ref, rtol=1e-11, atol=1e-11 * np.abs(ref).max())
+
+
+def test_p3_triangle_reproduces_cubic_fields(hc):
+    """P3 (nb = 10, the largest element of the fast path): a cubic field and its gradient are reproduced exactly by the
+    oracle and by the kernels' core (tab_core.cuh, instantiation <2, bs, 10>)."""
+    from tab_util import tri_case_discontinuous
+
+    m = tri_case_discontinuous(degree=3)
+    x, y = m["dof_coords"][:, 0], m["dof_coords"][:, 1]
+    xq, yq = m["xq"][..., 0], m["xq"][..., 1]
+    f = lambda x, y: x**3 - 2 * x * x * y + 0.5 * y**3 + x * y - 0.3 * y  # noqa: E731
+    fx = lambda x, y: 3 * x * x - 4 * x * y + y  # noqa: E731
+    fy = lambda x, y: -2 * x * x + 1.5 * y * y + x - 0.3  # noqa: E731
+    T = f(x, y)
+    val, grad = _tab(m, ot.VALUE, T, 1), _tab(m, ot.GRAD, T, 1)
+    np.testing.assert_allclose(val[..., 0], f(xq, yq), atol=1e-13)
+    np.testing.assert_allclose(grad, np.stack([fx(xq, yq), fy(xq, yq)], -1), atol=1e-11)
+    np.testing.assert_allclose(_hc_tab(hc, m, ot.VALUE, T, 1, 2, 1), val, rtol=0, atol=1e-13)
+    np.testing.assert_allclose(_hc_tab(hc, m, ot.GRAD, T, 1, 2, 2), grad, rtol=0, atol=1e-12)
+    u = np.stack([f(x, y), fy(x, y)], 1).reshape(-1)  # vector field, bs = 2
+    ref = _tab(m, ot.MANDEL_STRAIN, u, 2)
+    np.testing.assert_allclose(ref[..., 0], fx(xq, yq), atol=1e-11)
+    np.testing.assert_allclose(_hc_tab(hc, m, ot.MANDEL_STRAIN, u, 2, 2, 4), ref, rtol=0, atol=1e-12 * np.abs(ref).max())
