@@ -91,16 +91,40 @@ def lagrange_triangle_nodes(degree: int) -> np.ndarray:
     raise NotImplementedError
 
 
+_TET_EDGES = ((2, 3), (1, 3), (1, 2), (0, 3), (0, 2), (0, 1))  # basix sub-entity order of the reference tetrahedron
+
+
 def lagrange_tetrahedron(degree: int, X: np.ndarray):
-    """(phi (nq, 4), dphi (3, nq, 4)) of P1 on the reference tetrahedron."""
-    if degree != 1:
-        raise NotImplementedError("closed-form tetrahedron tables for P1 only; pass basix tables")
+    """(phi (nq, nb), dphi (3, nq, nb)) of P1 (nb = 4) / P2 (nb = 10: vertices, then the edge midpoints in the order
+    (v2,v3), (v1,v3), (v1,v2), (v0,v3), (v0,v2), (v0,v1)) on the reference tetrahedron."""
     x, y, z = X[:, 0], X[:, 1], X[:, 2]
     one, zero = np.ones_like(x), np.zeros_like(x)
-    phi = np.stack([1 - x - y - z, x, y, z], axis=1)
-    d = np.stack([np.stack([-one, one, zero, zero], 1), np.stack([-one, zero, one, zero], 1),
-                  np.stack([-one, zero, zero, one], 1)])
+    lam = [1 - x - y - z, x, y, z]
+    dlam = [(-one, -one, -one), (one, zero, zero), (zero, one, zero), (zero, zero, one)]
+    if degree == 1:
+        phi = np.stack(lam, axis=1)
+        d = np.stack([np.stack([dlam[a][k] for a in range(4)], 1) for k in range(3)])
+    elif degree == 2:
+        vals = [lam[i] * (2 * lam[i] - 1) for i in range(4)] + [4 * lam[i] * lam[j] for i, j in _TET_EDGES]
+        ders = []
+        for k in range(3):
+            dk = [(4 * lam[i] - 1) * dlam[i][k] for i in range(4)]
+            dk += [4 * (lam[i] * dlam[j][k] + lam[j] * dlam[i][k]) for i, j in _TET_EDGES]
+            ders.append(np.stack(dk, 1))
+        phi, d = np.stack(vals, axis=1), np.stack(ders)
+    else:
+        raise NotImplementedError("closed-form tetrahedron tables for P1 and P2; pass basix tables")
     return np.ascontiguousarray(phi), np.ascontiguousarray(d)
+
+
+def lagrange_tetrahedron_nodes(degree: int) -> np.ndarray:
+    """Reference coordinates of the nodes of `lagrange_tetrahedron(degree, .)`, in its ordering."""
+    v = np.array([[0.0, 0, 0], [1.0, 0, 0], [0.0, 1, 0], [0.0, 0, 1]])
+    if degree == 1:
+        return v
+    if degree == 2:
+        return np.concatenate([v, np.array([0.5 * (v[i] + v[j]) for i, j in _TET_EDGES])])
+    raise NotImplementedError
 
 
 def p1_geometry_derivatives(gdim: int) -> np.ndarray:

@@ -96,6 +96,8 @@ int hostcheck_form(int gdim, int bs, int nb, int nq, int kind_test, int kind_tri
   else if (gdim == 2 && bs == 2 && nb == 10) form_cells<2, 2, 10>(T, weights, kind_test, kind_trial, dofmap, x_dofmap, xg, D, x, n_cells, y);
   else if (gdim == 2 && bs == 1 && nb == 10) form_cells<2, 1, 10>(T, weights, kind_test, kind_trial, dofmap, x_dofmap, xg, D, x, n_cells, y);
   else if (gdim == 3 && bs == 3 && nb == 4) form_cells<3, 3, 4>(T, weights, kind_test, kind_trial, dofmap, x_dofmap, xg, D, x, n_cells, y);
+  else if (gdim == 3 && bs == 3 && nb == 10) form_cells<3, 3, 10>(T, weights, kind_test, kind_trial, dofmap, x_dofmap, xg, D, x, n_cells, y);
+  else if (gdim == 3 && bs == 1 && nb == 10) form_cells<3, 1, 10>(T, weights, kind_test, kind_trial, dofmap, x_dofmap, xg, D, x, n_cells, y);
   else return -1;
   return 0;
 }
@@ -127,6 +129,8 @@ int hostcheck_tab(int gdim, int bs, int nb, int nq, int kind, const double* phi,
   else if (gdim == 2 && bs == 2 && nb == 10) tab_cells<2, 2, 10>(T, kind, dofmap, x_dofmap, x, u, n_cells, out);
   else if (gdim == 2 && bs == 1 && nb == 10) tab_cells<2, 1, 10>(T, kind, dofmap, x_dofmap, x, u, n_cells, out);
   else if (gdim == 3 && bs == 3 && nb == 4) tab_cells<3, 3, 4>(T, kind, dofmap, x_dofmap, x, u, n_cells, out);
+  else if (gdim == 3 && bs == 3 && nb == 10) tab_cells<3, 3, 10>(T, kind, dofmap, x_dofmap, x, u, n_cells, out);
+  else if (gdim == 3 && bs == 1 && nb == 10) tab_cells<3, 1, 10>(T, kind, dofmap, x_dofmap, x, u, n_cells, out);
   else return -1;
   return 0;
 }

@@ -56,6 +56,22 @@ def tet_case(n=3, seed=0):
             "dpsi": el.p1_geometry_derivatives(3), "X": X, "dof_coords": x}
 
 
+def tet_case_discontinuous(degree=2, n=2, seed=0):
+    """Jittered tetrahedra (the 6-tet cube split of `tet_case`) with a cell-wise numbering of a degree-`degree` Lagrange
+    space (P2: nb = 10)."""
+    g = tet_case(n, seed)
+    X = np.array([[0.25, 0.25, 0.25], [0.1, 0.2, 0.3], [0.5, 0.2, 0.1], [0.15, 0.6, 0.2]])
+    phi, dphi = el.lagrange_tetrahedron(degree, X)
+    nodes = el.lagrange_tetrahedron_nodes(degree)
+    P1n, _ = el.lagrange_tetrahedron(1, nodes)
+    nc, nb = g["x_dofmap"].shape[0], nodes.shape[0]
+    xv = g["x"][g["x_dofmap"]]
+    P1phi, _ = el.lagrange_tetrahedron(1, X)
+    return {"x": g["x"], "x_dofmap": g["x_dofmap"], "dofmap": np.arange(nc * nb, dtype=np.int32).reshape(nc, nb),
+            "n_dofs": nc * nb, "dof_coords": np.einsum("cvi,av->cai", xv, P1n).reshape(nc * nb, 3), "phi": phi, "dphi": dphi,
+            "dpsi": el.p1_geometry_derivatives(3), "X": X, "xq": np.einsum("cvi,qv->cqi", xv, P1phi)}
+
+
 def general_case(cell: str, degree: int, bs: int, facets: bool = False, seed: int = 0):
     """Synthetic mesh + consistent table sets for the general tabulation path.  Returns the mesh dict extended with
     phi / dphi / dgeo (n_sets, ...), the reference points X, the cell name and physical evaluation points `xq`

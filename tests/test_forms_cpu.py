@@ -260,3 +260,20 @@ def test_form_core_p3_against_oracle(hc):
         D = rng.normal(size=(nc, 3, of.ncomp(kt, bs, 2) * of.ncomp(ki, bs, 2)))
         yref = of.apply_action(kt, ki, D, u, W3, m["dofmap"], bs, m["n_dofs"], *_geo(m))
         np.testing.assert_allclose(_host_form(hc, m, bs, W3, kt, ki, D, u), yref, rtol=0, atol=1e-13 * np.abs(yref).max())
+
+
+def test_form_core_p2_tetrahedra_against_oracle(hc):
+    """nb = 10, gdim = 3 (P2 tetrahedra): P : grad(v) and the dP/dF action of a 3-d hyperelastic residual / Jacobian."""
+    from tab_util import tet_case_discontinuous
+
+    m = tet_case_discontinuous()
+    w = np.array([0.05, 0.04, 0.03, 1.0 / 6.0 - 0.12])
+    rng = np.random.default_rng(5)
+    nc, nq = m["dofmap"].shape[0], m["phi"].shape[0]
+    P = rng.normal(size=(nc, nq, 9))
+    ref = of.assemble_vector(ot.GRAD, P, w, m["dofmap"], 3, m["n_dofs"], *_geo(m))
+    np.testing.assert_allclose(_host_form(hc, m, 3, w, ot.GRAD, 0, P), ref, rtol=0, atol=1e-13 * np.abs(ref).max())
+    D = rng.normal(size=(nc, nq, 81))
+    x = rng.normal(size=3 * m["n_dofs"])
+    yref = of.apply_action(ot.GRAD, ot.DEF_GRAD, D, x, w, m["dofmap"], 3, m["n_dofs"], *_geo(m))
+    np.testing.assert_allclose(_host_form(hc, m, 3, w, ot.GRAD, ot.DEF_GRAD, D, x), yref, rtol=0, atol=1e-13 * np.abs(yref).max())

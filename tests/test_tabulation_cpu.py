@@ -126,3 +126,27 @@ def test_p3_triangle_reproduces_cubic_fields(hc):
     ref = _tab(m, ot.MANDEL_STRAIN, u, 2)
     np.testing.assert_allclose(ref[..., 0], fx(xq, yq), atol=1e-11)
     np.testing.assert_allclose(_hc_tab(hc, m, ot.MANDEL_STRAIN, u, 2, 2, 4), ref, rtol=0, atol=1e-12 * np.abs(ref).max())
+
+
+def test_p2_tetrahedra_reproduce_quadratic_fields(hc):
+    """P2 tetrahedra (nb = 10, gdim = 3): quadratic fields and F = I + grad u reproduced exactly by the oracle and by the
+    kernels' core (instantiations <3, 1, 10>, <3, 3, 10>)."""
+    from tab_util import tet_case_discontinuous
+
+    m = tet_case_discontinuous()
+    X = m["dof_coords"]
+    xq = m["xq"]
+    f = lambda p: p[..., 0] ** 2 - p[..., 0] * p[..., 2] + 0.5 * p[..., 1] * p[..., 2] + p[..., 1]  # noqa: E731
+    gf = lambda p: np.stack([2 * p[..., 0] - p[..., 2], 0.5 * p[..., 2] + 1.0, -p[..., 0] + 0.5 * p[..., 1]], -1)  # noqa: E731
+    T = f(X)
+    geo = (m["x"], m["x_dofmap"], m["phi"], m["dphi"], m["dpsi"])
+    val = ot.tabulate(ot.VALUE, T, m["dofmap"], 1, *geo)
+    grad = ot.tabulate(ot.GRAD, T, m["dofmap"], 1, *geo)
+    np.testing.assert_allclose(val[..., 0], f(xq), atol=1e-13)
+    np.testing.assert_allclose(grad, gf(xq), atol=1e-11)
+    np.testing.assert_allclose(_hc_tab(hc, m, ot.VALUE, T, 1, 3, 1), val, rtol=0, atol=1e-13)
+    np.testing.assert_allclose(_hc_tab(hc, m, ot.GRAD, T, 1, 3, 3), grad, rtol=0, atol=1e-12)
+    u = np.stack([f(X), 0.3 * X[:, 0] * X[:, 1], X[:, 2] ** 2], 1).reshape(-1)
+    F = ot.tabulate(ot.DEF_GRAD, u, m["dofmap"], 3, *geo)
+    np.testing.assert_allclose(F[..., 0:3], gf(xq) + np.array([1.0, 0, 0]), atol=1e-11)
+    np.testing.assert_allclose(_hc_tab(hc, m, ot.DEF_GRAD, u, 3, 3, 9), F, rtol=0, atol=1e-12 * np.abs(F).max())
