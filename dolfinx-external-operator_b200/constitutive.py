@@ -27,7 +27,7 @@ import ctypes as C
 import numpy as np
 
 from ._lib import EO_LAYOUT_AOS, EO_LAYOUT_SOA, McParams, VmParams
-from .context import Context, DeviceArray, _ptr, default_context
+from .context import Context, DeviceArray, _ptr, default_context, evaluation_round
 
 
 def _n_points(arr) -> int:
@@ -444,8 +444,10 @@ class HeatFlux(_ModelBase):
     def _run(self, T, sigma, want: str):
         # the cache holds strong references to the operand OBJECTS it was computed from, so a
         # later array cannot be confused with them by address reuse; in-place mutation of an
-        # operand array between requests needs an explicit invalidate()
-        key = (T, sigma)
+        # operand array between requests of ONE evaluate_external_operators round needs an explicit invalidate()
+        # (a new round - context.new_evaluation_round - always recomputes).  The returned arrays are model-owned
+        # buffers that the next evaluation overwrites; the reference copies them into the coefficient (:289-290).
+        key = (T, sigma, evaluation_round())
         T = _as_input(T)
         sigma = _as_input(sigma)
         n = T.size
@@ -453,7 +455,8 @@ class HeatFlux(_ModelBase):
             raise ValueError("sigma must hold 2 components per quadrature point")
         c = self.ctx
         if self.fused:
-            if not (self._cache_key is not None and self._cache_key[0] is key[0] and self._cache_key[1] is key[1]):
+            if not (self._cache_key is not None and self._cache_key[0] is key[0] and self._cache_key[1] is key[1]
+                    and self._cache_key[2] == key[2]):
                 q, dT, ds = self._out("q", 2 * n), self._out("dqdT", 2 * n), self._out("dqdsigma", 4 * n)
                 c.check(c.lib.eo_heat_eval(c.handle, self.A, self.B, _ptr(T), _ptr(sigma), None, None, _ptr(q),
                                            _ptr(dT), _ptr(ds), n))

@@ -32,14 +32,21 @@ def _ptr(a):
 
 
 class DeviceArray:
-    """A typed view of device memory owned by a Context (freed with it or by .free())."""
+    """A typed view of device memory allocated through a Context.  An owning array returns its memory to the device
+    when it is garbage collected (or earlier, by .free()); views made by .reshape() keep their owner alive.  Memory
+    that outlives an explicitly closed context is left to the process."""
 
-    def __init__(self, ctx: "Context", ptr: int, shape, dtype, owner: bool = True):
+    def __init__(self, ctx: "Context", ptr: int, shape, dtype, owner: bool = True, base: "DeviceArray | None" = None):
         self.ctx = ctx
         self.ptr = ptr
         self.shape = tuple(int(s) for s in shape)
         self.dtype = np.dtype(dtype)
         self._owner = owner
+        self._base = base  # keeps the owning array (and with it the allocation) alive
+        self._release = None
+        if owner and ptr:
+            self._release = weakref.finalize(self, Context._dev_release, ctx._lib, ctx._finalizer, ctx._h, ptr)
+            self._release.atexit = False
 
     @property
     def size(self) -> int:
@@ -69,7 +76,7 @@ class DeviceArray:
             shape = tuple(self.size // max(known, 1) if s == -1 else s for s in shape)
         if int(np.prod(shape, dtype=np.int64)) != self.size:
             raise ValueError(f"cannot reshape device array of size {self.size} into {shape}")
-        return DeviceArray(self.ctx, self.ptr, shape, self.dtype, owner=False)
+        return DeviceArray(self.ctx, self.ptr, shape, self.dtype, owner=False, base=self)
 
     def copy_from(self, src) -> "DeviceArray":
         if isinstance(src, np.ndarray):
@@ -89,6 +96,8 @@ class DeviceArray:
 
     def free(self):
         if self._owner and self.ptr:
+            if self._release is not None:
+                self._release.detach()
             self.ctx._dev_free(self.ptr)
             self.ptr = None
 
@@ -104,8 +113,6 @@ class Context:
             raise EOError(rc, (self._lib.eo_last_error(None) or b"").decode())
         self._h = h
         self.device = int(device)
-        self._dev_ptrs: set[int] = set()
-        self._host_ptrs: set[int] = set()
         self._finalizer = weakref.finalize(self, Context._destroy, self._lib, h)
         # not at interpreter exit: models / tabulators that still hold this context are torn down in arbitrary order
         # then, and their destroy calls must not find a freed context (process teardown releases the GPU anyway)
@@ -119,6 +126,11 @@ class Context:
     @staticmethod
     def _destroy(lib, h):
         lib.eo_destroy(h)
+
+    @staticmethod
+    def _dev_release(lib, ctx_finalizer, h, ptr):
+        if ctx_finalizer.alive:
+            lib.eo_dev_free(h, ptr)
 
     @staticmethod
     def _host_free(lib, ctx_finalizer, h, ptr):
@@ -250,6 +262,21 @@ class Context:
 
 
 _default_ctx: Context | None = None
+
+# Counter of evaluate_operands / evaluate_external_operators rounds: callables that cache results across the requests
+# of ONE round (HeatFlux: q, dq/dT, dq/dsigma from one launch) key their cache on it, so operand buffers that are
+# refilled in place between rounds are never served stale.
+_round = 0
+
+
+def new_evaluation_round() -> int:
+    global _round
+    _round += 1
+    return _round
+
+
+def evaluation_round() -> int:
+    return _round
 
 
 def default_context() -> Context:

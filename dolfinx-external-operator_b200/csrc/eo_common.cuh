@@ -73,7 +73,8 @@ struct eo_tab_view {
   const double* u;  // device pointer of the (possibly staged) coefficient vector
   int64_t n_cells, n_dofs;
 };
-int eo_tab_view_get(eo_tab* t, const double* u, eo_tab_view* v);
+// `slot`: staging buffer of the handle used when `u` is a host vector (one per operand of a fused launch)
+int eo_tab_view_get(eo_tab* t, const double* u, eo_tab_view* v, int slot);
 
 // ------------------------------------------------------------------------------------
 // Any-side argument of a per-quadrature-point ("streamed") operation.

@@ -280,7 +280,6 @@ int eo_flush_l2(eo_ctx* ctx, size_t bytes) {
   if (bytes > ctx->flush_bytes) {
     EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_cmp));
     if (ctx->flush) cudaFree(ctx->flush);
-  if (ctx->scratch) cudaFree(ctx->scratch);
     ctx->flush = nullptr;
     ctx->flush_bytes = 0;
     EO_CUDA(ctx, cudaMalloc(&ctx->flush, bytes));

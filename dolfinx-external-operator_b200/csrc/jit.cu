@@ -604,7 +604,7 @@ int eo_jit_eval_tabulated(eo_jit* m, const int* derivatives, const double* param
     if (nc != m->operand_size[i])
       return jit_fail(m, EO_ERR_INVALID, "eo_jit_eval_tabulated: operand %d has %d components, its tabulation kind gives %d", i,
                       m->operand_size[i], nc);
-    rc = eo_tab_view_get(tabs[i], coefficients[i], &tv[i]);
+    rc = eo_tab_view_get(tabs[i], coefficients[i], &tv[i], i);
     if (rc) return rc;
     if (tv[i].ctx != ctx) return jit_fail(m, EO_ERR_INVALID, "eo_jit_eval_tabulated: operand %d lives on another context", i);
     const tab_tables* T = tv[i].T_host;

@@ -156,21 +156,22 @@ static int tab_launch(eo_tab* t, int kind, const double* u, const int32_t* cells
 }
 
 // device pointer for a coefficient vector given on either side
-int eo_tab_stage_u(eo_tab* t, const double* u, const double** d_u) {
+int eo_tab_stage_u(eo_tab* t, const double* u, const double** d_u, int slot) {
   eo_ctx* ctx = t->ctx;
+  EO_REQUIRE(ctx, slot >= 0 && slot < EO_JIT_MAX_ARGS, "eo_tab_stage_u: staging slot out of range");
   if (eo_is_device_ptr(u)) {
     *d_u = u;
     return EO_OK;
   }
   const size_t bytes = size_t(t->n_dofs) * t->T.bs * sizeof(double);
-  if (!t->u_stage) EO_CUDA(ctx, cudaMalloc(&t->u_stage, bytes));
-  EO_CUDA(ctx, cudaMemcpyAsync(t->u_stage, u, bytes, cudaMemcpyHostToDevice, ctx->s_cmp));
-  *d_u = t->u_stage;
+  if (!t->u_stage[slot]) EO_CUDA(ctx, cudaMalloc(&t->u_stage[slot], bytes ? bytes : 8));
+  EO_CUDA(ctx, cudaMemcpyAsync(t->u_stage[slot], u, bytes, cudaMemcpyHostToDevice, ctx->s_cmp));
+  *d_u = t->u_stage[slot];
   return EO_OK;
 }
 
 // internal: what the fused generic path (jit.cu) needs from a tabulation handle; stages a host coefficient vector
-int eo_tab_view_get(eo_tab* t, const double* u, eo_tab_view* v) {
+int eo_tab_view_get(eo_tab* t, const double* u, eo_tab_view* v, int slot) {
   v->ctx = t->ctx;
   v->T_host = &t->T;
   v->T_dev = t->d_T;
@@ -178,7 +179,7 @@ int eo_tab_view_get(eo_tab* t, const double* u, eo_tab_view* v) {
   v->n_cells = t->n_cells, v->n_dofs = t->n_dofs;
   v->u = nullptr;
   if (!u) return EO_OK;
-  return eo_tab_stage_u(t, u, &v->u);
+  return eo_tab_stage_u(t, u, &v->u, slot);
 }
 
 extern "C" {
@@ -245,7 +246,8 @@ int eo_tab_destroy(eo_tab* t) {
   if (t->x_dofmap) cudaFree(t->x_dofmap);
   if (t->x) cudaFree(t->x);
   if (t->d_T) cudaFree(t->d_T);
-  if (t->u_stage) cudaFree(t->u_stage);
+  for (double* s : t->u_stage)
+    if (s) cudaFree(s);
   if (t->cells_stage) cudaFree(t->cells_stage);
   delete t;
   return EO_OK;

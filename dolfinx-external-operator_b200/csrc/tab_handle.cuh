@@ -12,10 +12,11 @@ struct eo_tab {
   int32_t* x_dofmap = nullptr;                   // device [n_cells][nv]
   double* x = nullptr;                           // device [n_nodes][3]
   tab_tables* d_T = nullptr;                     // device copy of T (the fused generic kernels stage it in shared memory)
-  double* u_stage = nullptr;                     // device staging copy of a host coefficient vector
+  double* u_stage[EO_JIT_MAX_ARGS] = {};         // device staging copies of host coefficient vectors, one per operand slot
   int32_t* cells_stage = nullptr;                // device staging copy of a host entity list
   size_t cells_stage_n = 0;
 };
 
-// device pointer for a coefficient vector given on either side (host vectors are copied into t->u_stage)
-int eo_tab_stage_u(eo_tab* t, const double* u, const double** d_u);
+// device pointer for a coefficient vector given on either side (host vectors are copied into t->u_stage[slot];
+// calls that tabulate several operands on one handle in ONE launch give every operand its own slot)
+int eo_tab_stage_u(eo_tab* t, const double* u, const double** d_u, int slot = 0);

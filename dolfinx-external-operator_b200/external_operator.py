@@ -22,7 +22,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .context import DeviceArray
+from .context import DeviceArray, new_evaluation_round
 
 try:  # pragma: no cover - needs the FEniCS stack
     from dolfinx_external_operator import FEMExternalOperator, replace_external_operators  # noqa: F401
@@ -215,12 +215,18 @@ def _assign(external_operator, values) -> None:
 
 def evaluate_external_operators(external_operators, evaluated_operands):
     """Evaluate external operators and update their coefficients (reference :407-448)."""
+    return _evaluate_external_operators(external_operators, evaluated_operands, 0)
+
+
+def _evaluate_external_operators(external_operators, evaluated_operands, depth):
+    if depth == 0:
+        new_evaluation_round()  # results cached by a callable for the requests of one round end here
     evaluated_operators = []
     for external_operator in external_operators:
         ufl_operands_eval = []
         for operand in external_operator.ufl_operands:
             if _is_external_operator(operand):  # :427-428
-                ufl_operands_eval.extend(evaluate_external_operators([operand], evaluated_operands[operand]))
+                ufl_operands_eval.extend(_evaluate_external_operators([operand], evaluated_operands[operand], depth + 1))
             else:
                 ufl_operands_eval.append(evaluated_operands[operand])
 

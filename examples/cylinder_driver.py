@@ -24,8 +24,8 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import elements as el
-from . import synthetic as syn
+from dolfinx_external_operator_b200 import elements as el
+from dolfinx_external_operator_b200 import synthetic as syn
 
 R_E, R_I = 1.3, 1.0  # demo_vm:183
 E, NU, SIGMA_0 = 70e3, 0.3, 250.0  # :185-188
@@ -88,7 +88,7 @@ class GpuBackend:
     """The product path: Tabulator + VonMises (history resident) + QuadratureForms on one B200."""
 
     def __init__(self, mesh, ctx=None, exact: bool = True):
-        from . import QuadratureForms, Tabulator, VonMises
+        from dolfinx_external_operator_b200 import QuadratureForms, Tabulator, VonMises
 
         self.tab = Tabulator(dofmap=mesh["dofmap"], x_dofmap=mesh["x_dofmap"], x=mesh["x"], phi=mesh["phi"],
                              dphi=mesh["dphi"], bs=2, n_dofs=mesh["n_dofs"], ctx=ctx)

@@ -18,8 +18,8 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import elements as el
-from . import synthetic as syn
+from dolfinx_external_operator_b200 import elements as el
+from dolfinx_external_operator_b200 import synthetic as syn
 
 L, H = 1.2, 1.0  # demo_mc:119
 C_COHESION = 3.45  # :112
@@ -45,7 +45,7 @@ class GpuBackend:
     """The product path: Tabulator + MohrCoulomb (history resident) + QuadratureForms on one B200."""
 
     def __init__(self, mesh, ctx=None):
-        from . import MohrCoulomb, QuadratureForms, Tabulator
+        from dolfinx_external_operator_b200 import MohrCoulomb, QuadratureForms, Tabulator
 
         self.tab = Tabulator(dofmap=mesh["dofmap"], x_dofmap=mesh["x_dofmap"], x=mesh["x"], phi=mesh["phi"],
                              dphi=mesh["dphi"], bs=2, n_dofs=mesh["n_dofs"], ctx=ctx)

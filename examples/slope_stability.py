@@ -9,10 +9,11 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 import numpy as np  # noqa: E402
 
-from dolfinx_external_operator_b200 import slope_stability as ss  # noqa: E402
+import slope_driver as ss  # noqa: E402
 
 if __name__ == "__main__":
     nx, ny = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (25, 25)

@@ -9,8 +9,9 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
-from dolfinx_external_operator_b200 import thick_walled_cylinder as twc  # noqa: E402
+import cylinder_driver as twc  # noqa: E402
 
 if __name__ == "__main__":
     n_r, n_t = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (20, 64)

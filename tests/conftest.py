@@ -9,6 +9,9 @@ if ROOT not in sys.path:
 if os.path.join(ROOT, "tests") not in sys.path:
     sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+if os.path.join(ROOT, "examples") not in sys.path:  # the demo drivers (known-answer problems) live with the examples
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 

@@ -6,7 +6,7 @@ consistent tangent, plastic zone reaching the outer radius at the analytic colla
 import numpy as np
 
 from cylinder_util import OracleBackend
-from dolfinx_external_operator_b200 import thick_walled_cylinder as twc
+import cylinder_driver as twc
 
 
 def test_boundary_data_of_the_quarter_ring():

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from cylinder_util import OracleBackend
-from dolfinx_external_operator_b200 import thick_walled_cylinder as twc
+import cylinder_driver as twc
 
 pytestmark = pytest.mark.gpu
 

@@ -264,3 +264,22 @@ def test_jit_points_per_thread_variant(ctx, n):
     finally:
         del os.environ["EO_JIT_PPT"]
     _close(gk[(1,)], -1.0 / (1.0 + T) ** 2, 1e-13)
+
+
+def test_fused_tabulation_two_coefficients_on_one_tabulator(ctx):
+    """Regression: two lazy operands of ONE tabulator with DIFFERENT host coefficients (u and u_old on one space) each
+    get their own staging buffer - q(T_a, grad T_b) must not be tabulated from a single coefficient."""
+    from dolfinx_external_operator_b200.tabulation import LazyOperand
+    from tab_util import tri_case
+
+    m = tri_case(nx=9, ny=7)
+    tab = eo.Tabulator(dofmap=m["dofmap"], x_dofmap=m["x_dofmap"], x=m["x"], phi=m["phi"], dphi=m["dphi"], bs=1,
+                       n_dofs=m["n_dofs"], ctx=ctx)
+    x, y = m["dof_coords"][:, 0], m["dof_coords"][:, 1]
+    Ta, Tb = x * x + y, 0.5 * x * y + 0.25 * y * y
+    h = jm.heat_flux(ctx=ctx, fmad=False)
+    fused = np.array(h((0, 0))(LazyOperand(tab, 0, Ta), LazyOperand(tab, 1, Tb)))
+    two = np.array(h((0, 0))(tab.evaluate("value", Ta, output="host"), tab.evaluate("grad", Tb, output="host")))
+    assert np.array_equal(fused, two)
+    same = np.array(h((0, 0))(tab.evaluate("value", Tb, output="host"), tab.evaluate("grad", Tb, output="host")))
+    assert not np.array_equal(fused, same)

@@ -172,3 +172,17 @@ def test_mc_device_resident_and_bad_arguments(ctx):
     assert ctx.lib.eo_mc_eval(ctx.handle, C.byref(bad), dd.ptr, ds.ptr, dC.ptr, dsig.ptr, None, None, None, None, n) == -1
     for a in (dd, ds, dC, dsig):
         a.free()
+
+
+def test_mc_scratch_survives_l2_flush(ctx):
+    """Regression: eo_flush_l2 growing its buffer must not touch the Mohr-Coulomb scratch (plastic-point list)."""
+    d, s = inputs.mc_batch(20_000, seed=5, stepper=_stepper())
+    ref = native.mc_return_mapping(d, s, PRM, parallel=True)
+    _check(_abi(ctx, d, s), ref, d, s)  # allocates the scratch of the two-pass scheme
+    ctx.flush_l2(300 << 20)             # grows the flush buffer
+    ctx.flush_l2(400 << 20)
+    tmp = [ctx.empty((1 << 20,)) for _ in range(4)]  # would reuse a freed scratch block
+    for t in tmp:
+        ctx.check(ctx.lib.eo_dev_memset(ctx.handle, t.ptr, 0xFF, t.nbytes))
+    _check(_abi(ctx, d[:15_000], s[:15_000]), {k: v[:15_000] for k, v in ref.items()}, d[:15_000], s[:15_000])
+    ctx.sync()

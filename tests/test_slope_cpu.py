@@ -5,7 +5,7 @@ of the crest point reaches its plateau at the slope stability factor l_lim = gam
 
 import numpy as np
 
-from dolfinx_external_operator_b200 import slope_stability as ss
+import slope_driver as ss
 from slope_util import OracleBackend
 
 STEPS = np.concatenate([np.linspace(2, 22.9, 50), [22.96, 22.99], np.linspace(23.2, 27, 20)])  # demo_mc:708-710, extended

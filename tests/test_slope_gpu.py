@@ -4,7 +4,7 @@
 import numpy as np
 import pytest
 
-from dolfinx_external_operator_b200 import slope_stability as ss
+import slope_driver as ss
 from slope_util import OracleBackend
 from test_slope_cpu import STEPS, check_collapse
 

@@ -236,3 +236,40 @@ def test_heat_argument_errors(ctx):
     out = np.empty(8)
     assert ctx.lib.eo_heat_eval(ctx.handle, 1.0, 1.0, T.ctypes.data, None, None, None, out.ctypes.data, None, None, 4) == -1
     assert b"sigma" in ctx.lib.eo_last_error(ctx.handle)
+
+
+def test_device_arrays_return_their_memory(ctx):
+    """Owning DeviceArrays free their allocation when collected (the default drop-in path allocates one operand
+    array per evaluate_operands call); views keep the owner alive."""
+    import gc
+
+    import torch
+
+    ctx.sync()
+    gc.collect()
+    free0 = torch.cuda.mem_get_info(ctx.device)[0]
+    for _ in range(40):
+        a = ctx.empty((1 << 24,))  # 128 MB each: 5 GB in total if leaked
+        v = a.reshape(-1, 4)
+        del a
+        assert v._base is not None and v.ptr
+        ctx.check(ctx.lib.eo_dev_memset(ctx.handle, v.ptr, 0, v.nbytes))  # still valid through the view
+        del v
+    gc.collect()
+    free1 = torch.cuda.mem_get_info(ctx.device)[0]
+    assert free0 - free1 < (512 << 20)
+
+
+def test_heat_flux_cache_is_per_evaluation_round(ctx):
+    """An operand buffer refilled in place between two evaluate_external_operators rounds is never served stale."""
+    from dolfinx_external_operator_b200.context import new_evaluation_round
+
+    hf = eo.HeatFlux(ctx=ctx)
+    T, g = inputs.heat_batch(999, seed=3)
+    Tb, gb = T.reshape(-1, 3).copy(), g.reshape(-1, 6).copy()
+    q1 = np.array(hf((0, 0))(Tb, gb))
+    Tb += 0.5
+    new_evaluation_round()
+    q2 = np.array(hf((0, 0))(Tb, gb))
+    np.testing.assert_allclose(q2, native.heat("q", Tb.reshape(-1), gb.reshape(-1, 2)).reshape(-1), rtol=1e-12)
+    assert not np.array_equal(q1, q2)
