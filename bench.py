@@ -323,6 +323,15 @@ WORKLOADS = {
 }
 
 
+def _nanmax(vals):
+    v = [x for x in vals if x == x]
+    return max(v) if v else float("nan")
+
+
+def _same(a, b):
+    return a == b or (a != a and b != b)
+
+
 def _tile_to_device(ctx, dst, tile: np.ndarray, n: int, width: int, itemsize: int = 8):
     """Repeat a seeded host tile into a device array of n rows."""
     tile_n = tile.shape[0]
@@ -568,7 +577,35 @@ def run_gpu_arm(args):
     launches = ctx.launch_count - launches0
     total_ms = max_over_ranks(ctx.elapsed_ms(ev[0], ev[1]))
     kernel_ms = [ctx.elapsed_ms(ev[2 + 2 * k], ev[3 + 2 * k]) for k in range(K)]
-    stats = ctx.stats()  # rank-local when world == 1, all-reduced K times otherwise (only ratios are used)
+    stats = ctx.stats()  # this rank's record over the K timed steps (the collective never modifies it)
+    collective_check = None
+    if dist is not None:
+        # the K-th collective left the GLOBAL record of the K steps: it must equal the sum of the local records,
+        # gathered here a second, independent way (host tensors through the store-backed object collective)
+        import torch
+
+        gstats = ctx.stats_global()
+        loc = [None] * world
+        dist.all_gather_object(loc, {k: (v.tolist() if isinstance(v, np.ndarray) else v) for k, v in stats.items()})
+        want_points = sum(l["n_points"] for l in loc)
+        want_plastic = sum(l["n_plastic"] for l in loc)
+        want_hist = np.sum([np.asarray(l["niter_hist"], dtype=np.int64) for l in loc], axis=0)
+        counted = model not in ("heat", "isihara", "tab", "action", "jitvm", "jitvm3d", "jitfused")
+        ok = (gstats["n_points"] == want_points and gstats["n_plastic"] == want_plastic
+              and np.array_equal(gstats["niter_hist"], want_hist)
+              and _same(gstats["f_max"], _nanmax(l["f_max"] for l in loc))
+              and _same(gstats["res_max"], _nanmax(l["res_max"] for l in loc))
+              and (not counted or want_points == world * n * K))
+        collective_check = {"ok": bool(ok), "n_points": gstats["n_points"], "expected_n_points": want_points,
+                            "n_plastic": gstats["n_plastic"], "sum_of_local_n_plastic": want_plastic,
+                            "what": "eo_stats global record after the last step == sum / max over the ranks' local records "
+                                    "(one NCCL all-gather of the 1.7 KB record + combine kernel per step, on the "
+                                    "collective stream, overlapping the next step)"}
+        if not ok:
+            print(f"[rank {rank}] statistics collective mismatch: {collective_check}", file=sys.stderr, flush=True)
+            dist.destroy_process_group()
+            sys.exit(3)
+        stats = gstats
     value = world * n * K / (total_ms * 1e-3)
 
     # ---- end-to-end through the public callable (host buffers)
@@ -747,7 +784,8 @@ def run_gpu_arm(args):
         "workload": WORKLOADS[model], "qp_per_gpu": n, "state_layout": args.state_layout,
         "plastic_fraction": stats["n_plastic"] / max(stats["n_points"], 1),
         "l2": f"inputs+outputs {BYTES_PER_QP[model] * n / 1e9:.1f} GB per step >> 126 MB L2 (no flush needed)",
-        "partition": "contiguous block of QPs per rank, no halo; one stats all-reduce per step when n_gpus > 1",
+        "partition": "contiguous block of QPs per rank, no halo; one statistics collective per step when n_gpus > 1 "
+                     "(plastic_fraction / niter histogram are then the global figures)",
     }
     if model == "mc":
         tot = max(int(hist.sum()), 1)
@@ -765,6 +803,8 @@ def run_gpu_arm(args):
     }
     if e2e_dc is not None:
         line["e2e_device_consumers"] = e2e_dc
+    if collective_check is not None:
+        line["collective"] = collective_check
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -126,6 +126,9 @@ PROTOTYPES = {
     "eo_stats_read": (C.c_int, [_vp, C.POINTER(Stats)]),
     "eo_stats_device_ptr": (_vp, [_vp]),
     "eo_allreduce_stats": (C.c_int, [_vp, _vp]),
+    "eo_stats_read_global": (C.c_int, [_vp, C.POINTER(Stats)]),
+    "eo_stats_collective_begin": (C.c_int, [_vp, C.c_int, C.POINTER(Stats), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "eo_stats_collective_end": (C.c_int, [_vp, C.c_int]),
     "eo_vm_eval": (C.c_int, [_vp, C.POINTER(VmParams), _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
     "eo_vm_eval_resident": (C.c_int, [_vp, C.POINTER(VmParams), _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_int]),
     "eo_commit_history": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, C.c_int]),

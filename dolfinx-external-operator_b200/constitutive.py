@@ -52,6 +52,29 @@ class _ModelBase:
         self.ctx = ctx or default_context()
         self._host_out: dict[str, np.ndarray] = {}
         self._bound: dict[str, np.ndarray] = {}
+        self._last_stats = None
+
+    def local_stats(self) -> dict:
+        """Statistics record of this rank's last evaluation (points, plastic / non-converged / non-finite counts,
+        Newton-iteration histogram, maxima) - what the reference prints per call, demo_mc:584-591."""
+        if self._last_stats is None:
+            raise RuntimeError("no evaluation yet")
+        return self._last_stats
+
+    def global_stats(self, group=None) -> dict:
+        """The same record over ALL ranks of the torch.distributed `group` (default: the world group; one rank per
+        GPU along the cell partition, external_operator.py:368-370): counts summed, maxima maximised - the one
+        collective of the hot path (`parallel.allreduce_stats`: NCCL all-gather of the 1.7 KB record on the device,
+        host tensors for gloo).  Collective call: every rank of the group must make it after its evaluation.
+        Without an initialised process group it is the local record."""
+        import torch.distributed as dist
+
+        st = self.local_stats()
+        if not (dist.is_available() and dist.is_initialized()):
+            return st
+        from .parallel import allreduce_stats
+
+        return allreduce_stats(self.ctx, st, group)
 
     def _out(self, name: str, size: int) -> np.ndarray:
         """Result buffer `name` of `size` f64: a bound coefficient array, or pinned memory we own."""
@@ -170,6 +193,7 @@ class VonMises(_ModelBase):
         C_tang = self._out("C_tang", 16 * n)
         sigma = self._out("sigma", 4 * n)
         dp = self._out("dp", n)
+        c.stats_reset()
         if self._resident:
             if self.n_qp is None:
                 self._alloc_state(n)
@@ -201,7 +225,7 @@ class VonMises(_ModelBase):
                 raise ValueError("history arrays do not match the operand's quadrature-point count")
             c.check(c.lib.eo_vm_eval(c.handle, C.byref(self._prm), _ptr(deps), _ptr(sn), _ptr(pp), _ptr(C_tang),
                                      _ptr(sigma), _ptr(dp), n))
-        c.sync()
+        self._last_stats = c.stats()  # synchronises
         return C_tang, sigma, dp
 
     def _C_tang_fused(self, lazy):
@@ -212,12 +236,13 @@ class VonMises(_ModelBase):
         d_Ct = getattr(self, "_fused_Ct", None)
         if d_Ct is None or d_Ct.size != 16 * n:
             d_Ct = self._fused_Ct = c.empty((16 * n,))
+        c.stats_reset()
         lazy.tab.vm_fused(self, lazy.coefficient, C_tang=d_Ct, exact=True)
         C_tang, sigma, dp = self._out("C_tang", 16 * n), self._out("sigma", 4 * n), self._out("dp", n)
         d_Ct.to_host(C_tang)
         self.sigma_dev.to_host(sigma)
         self.dp_dev.to_host(dp)
-        c.sync()
+        self._last_stats = c.stats()  # synchronises
         return C_tang, sigma, dp
 
     def eval_device(self, deps: DeviceArray, C_tang: DeviceArray):
@@ -276,7 +301,6 @@ class MohrCoulomb(_ModelBase):
         self.n_qp = None
         self.sigma_n_dev = self.sigma_dev = None
         self.niter = self.yielding = self.norm_res = self.dlambda = None
-        self._last_stats = None
         if self._resident and n_qp is not None:
             self._alloc_state(int(n_qp))
 
@@ -348,16 +372,18 @@ class MohrCoulomb(_ModelBase):
             self._host_out[name] = a
         return a
 
-    def summary(self) -> dict:
+    def summary(self, group=None, *, reduce: bool | None = None) -> dict:
         """The inner-Newton summary of demo_mc:584-591 for the last call (from the device statistics
-        record): unique iteration counts, their counts, max f(trial), max ||res||."""
-        st = self._last_stats
-        if st is None:
-            raise RuntimeError("no evaluation yet")
+        record): unique iteration counts, their counts, max f(trial), max ||res||.  Under torch.distributed (one rank
+        per GPU) pass `group` or `reduce=True` for the figures of ALL ranks - the scalar all-reduce that turns the
+        reference's rank-local prints into global ones (collective call, see `global_stats`)."""
+        if reduce is None:
+            reduce = group is not None
+        st = self.global_stats(group) if reduce else self.local_stats()
         it = np.nonzero(st["niter_hist"])[0]
         return {"unique_iters": it.astype(np.int32), "counts": st["niter_hist"][it], "max_f": st["f_max"],
-                "max_residual": st["res_max"], "n_plastic": st["n_plastic"], "n_nonconverged": st["n_nonconverged"],
-                "n_nonfinite": st["n_nonfinite"]}
+                "max_residual": st["res_max"], "n_points": st["n_points"], "n_plastic": st["n_plastic"],
+                "n_nonconverged": st["n_nonconverged"], "n_nonfinite": st["n_nonfinite"]}
 
     def summary_text(self) -> str:
         s = self.summary()

@@ -242,8 +242,20 @@ class Context:
         self.check(self._lib.eo_stats_reset(self._h))
 
     def stats(self) -> dict:
+        """The LOCAL record (this GPU's points since the last stats_reset)."""
         s = Stats()
         self.check(self._lib.eo_stats_read(self._h, C.byref(s)))
+        return self._stats_dict(s)
+
+    def stats_global(self) -> dict:
+        """The GLOBAL record written by the last statistics collective (`parallel.allreduce_stats_device`,
+        `eo_allreduce_stats`); waits for that collective."""
+        s = Stats()
+        self.check(self._lib.eo_stats_read_global(self._h, C.byref(s)))
+        return self._stats_dict(s)
+
+    @staticmethod
+    def _stats_dict(s) -> dict:
         hist = np.array(s.niter_hist[:], dtype=np.int64)
         return {
             "n_points": int(s.n_points),

@@ -32,7 +32,15 @@ struct eo_ctx {
   // general device scratch (plastic-point list of the two-pass Mohr-Coulomb scheme), grown on demand
   char* scratch = nullptr;
   size_t scratch_bytes = 0;
-  eo_stats* stats = nullptr;  // device
+  eo_stats* stats = nullptr;  // device: the LOCAL record the kernels accumulate into
+  // the one collective (eo_allreduce_stats): snapshot of the local record, the gathered records of all ranks and
+  // their combination; the collective runs on its own stream so that it overlaps the next evaluation
+  cudaStream_t s_coll = nullptr;
+  cudaEvent_t ev_coll_ready = nullptr, ev_coll_done = nullptr;
+  eo_stats* stats_send = nullptr;    // device [1]
+  eo_stats* stats_recv = nullptr;    // device [stats_recv_world]
+  int stats_recv_world = 0;
+  eo_stats* stats_global = nullptr;  // device [1]
   unsigned int* work_ctr = nullptr;  // device: tile counter of the persistent kernels
   int64_t launches = 0;
   char err[512] = {0};

@@ -62,6 +62,26 @@ __global__ void __launch_bounds__(256) eo_gather_kernel(const double* __restrict
   if (k < n_out) out[k] = __ldg(values + __ldg(src + k));
 }
 
+// global record = SUM over ranks of the int64 block, MAX over ranks of the f64 block of the gathered records
+__global__ void __launch_bounds__(256) eo_stats_combine_kernel(const eo_stats* __restrict__ recv, int world,
+                                                               eo_stats* __restrict__ out) {
+  constexpr int NS = 4 + EO_NITER_BINS, NM = 4;
+  const int j = threadIdx.x;
+  if (j < NS) {
+    long long acc = 0;
+    for (int r = 0; r < world; ++r) acc += reinterpret_cast<const long long*>(recv + r)[j];
+    reinterpret_cast<long long*>(out)[j] = acc;
+  } else if (j < NS + NM) {
+    const int k = j - NS;
+    double m = (&recv[0].niter_max)[k];
+    for (int r = 1; r < world; ++r) {
+      const double v = (&recv[r].niter_max)[k];
+      m = (v > m || m != m) ? v : m;  // NaN-free maximum unless every rank holds NaN
+    }
+    (&out->niter_max)[k] = m;
+  }
+}
+
 extern "C" {
 
 int eo_version(void) { return EO_B200_VERSION; }
@@ -120,8 +140,14 @@ int eo_create(int device, eo_ctx** out) {
     EO_CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_cmp[i], cudaEventDisableTiming));
     EO_CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
   }
+  EO_CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->s_coll, cudaStreamNonBlocking));
+  EO_CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_coll_ready, cudaEventDisableTiming));
+  EO_CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_coll_done, cudaEventDisableTiming));
   EO_CREATE_CUDA(cudaMalloc(&ctx->stats, sizeof(eo_stats)));
   EO_CREATE_CUDA(cudaMemset(ctx->stats, 0, sizeof(eo_stats)));
+  EO_CREATE_CUDA(cudaMalloc(&ctx->stats_send, sizeof(eo_stats)));
+  EO_CREATE_CUDA(cudaMalloc(&ctx->stats_global, sizeof(eo_stats)));
+  EO_CREATE_CUDA(cudaMemset(ctx->stats_global, 0, sizeof(eo_stats)));
   EO_CREATE_CUDA(cudaMalloc(&ctx->work_ctr, 256));
   EO_CREATE_CUDA(cudaMemset(ctx->work_ctr, 0, 256));
 #undef EO_CREATE_CUDA
@@ -136,6 +162,13 @@ int eo_destroy(eo_ctx* ctx) {
   cudaStreamSynchronize(ctx->s_in);
   cudaStreamSynchronize(ctx->s_cmp);
   cudaStreamSynchronize(ctx->s_out);
+  if (ctx->s_coll) cudaStreamSynchronize(ctx->s_coll);
+  if (ctx->ev_coll_ready) cudaEventDestroy(ctx->ev_coll_ready);
+  if (ctx->ev_coll_done) cudaEventDestroy(ctx->ev_coll_done);
+  if (ctx->stats_send) cudaFree(ctx->stats_send);
+  if (ctx->stats_recv) cudaFree(ctx->stats_recv);
+  if (ctx->stats_global) cudaFree(ctx->stats_global);
+  if (ctx->s_coll) cudaStreamDestroy(ctx->s_coll);
   for (int i = 0; i < EO_NSLOT; ++i) {
     if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
     if (ctx->ev_cmp[i]) cudaEventDestroy(ctx->ev_cmp[i]);
@@ -160,6 +193,7 @@ int eo_sync(eo_ctx* ctx) {
   EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_in));
   EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_cmp));
   EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
+  EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_coll));
   return EO_OK;
 }
 
@@ -308,17 +342,58 @@ int eo_assign_gather(eo_ctx* ctx, const double* values, int64_t n_values, const 
   });
 }
 
-// The one collective of the path: in-place all-reduce of the device statistics record over a
-// caller-owned NCCL communicator, ordered on the ctx compute stream.  NCCL is resolved at run time from whatever
-// libnccl.so.2 the process has (PyTorch's bundled one, or the system library): no link-time dependency.
+// The one collective of the path.  The local record is never modified: it is snapshot on the compute
+// stream, the snapshots of all ranks are gathered with ONE ncclAllGather on the collective stream, and a combine kernel
+// writes the global record (SUM over the int64 block, MAX over the f64 block).  Calling it after every evaluation on a
+// record that keeps accumulating therefore never counts anything twice, and the next evaluation overlaps it.
+int eo_stats_collective_begin(eo_ctx* ctx, int world, const eo_stats* host_record, void** send, void** recv, void** stream) {
+  EO_REQUIRE(ctx, ctx != nullptr, "eo_stats_collective_begin: ctx is NULL");
+  EO_REQUIRE(ctx, world >= 1 && world <= 4096, "eo_stats_collective_begin: world size out of range");
+  EO_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (world > ctx->stats_recv_world) {
+    EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_coll));
+    if (ctx->stats_recv) cudaFree(ctx->stats_recv);
+    ctx->stats_recv = nullptr, ctx->stats_recv_world = 0;
+    EO_CUDA(ctx, cudaMalloc(&ctx->stats_recv, size_t(world) * sizeof(eo_stats)));
+    ctx->stats_recv_world = world;
+  }
+  // the previous collective must have read the snapshot before it is overwritten
+  EO_CUDA(ctx, cudaStreamWaitEvent(ctx->s_cmp, ctx->ev_coll_done, 0));
+  if (host_record)
+    EO_CUDA(ctx, cudaMemcpyAsync(ctx->stats_send, host_record, sizeof(eo_stats), cudaMemcpyHostToDevice, ctx->s_cmp));
+  else
+    EO_CUDA(ctx, cudaMemcpyAsync(ctx->stats_send, ctx->stats, sizeof(eo_stats), cudaMemcpyDeviceToDevice, ctx->s_cmp));
+  EO_CUDA(ctx, cudaEventRecord(ctx->ev_coll_ready, ctx->s_cmp));
+  EO_CUDA(ctx, cudaStreamWaitEvent(ctx->s_coll, ctx->ev_coll_ready, 0));
+  if (send) *send = ctx->stats_send;
+  if (recv) *recv = ctx->stats_recv;
+  if (stream) *stream = (void*)ctx->s_coll;
+  return EO_OK;
+}
+
+int eo_stats_collective_end(eo_ctx* ctx, int world) {
+  EO_REQUIRE(ctx, ctx != nullptr, "eo_stats_collective_end: ctx is NULL");
+  EO_REQUIRE(ctx, world >= 1 && world <= ctx->stats_recv_world, "eo_stats_collective_end: no matching eo_stats_collective_begin");
+  EO_CUDA(ctx, cudaSetDevice(ctx->device));
+  eo_stats_combine_kernel<<<1, 256, 0, ctx->s_coll>>>(ctx->stats_recv, world, ctx->stats_global);
+  EO_CUDA(ctx, cudaGetLastError());
+  EO_CUDA(ctx, cudaEventRecord(ctx->ev_coll_done, ctx->s_coll));
+  ctx->launches += 1;
+  return EO_OK;
+}
+
+// NCCL is resolved at run time from whatever libnccl.so.2 the process has (PyTorch's bundled one, or the system
+// library): no link-time dependency.
 int eo_allreduce_stats(eo_ctx* ctx, void* nccl_comm) {
   EO_REQUIRE(ctx, ctx != nullptr, "eo_allreduce_stats: ctx is NULL");
   EO_REQUIRE(ctx, nccl_comm != nullptr, "eo_allreduce_stats: communicator is NULL");
-  typedef int (*allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  typedef int (*allgather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
+  typedef int (*count_fn)(void*, int*);
   typedef const char* (*errstr_fn)(int);
-  static allreduce_fn allreduce = nullptr;
+  static allgather_fn allgather = nullptr;
+  static count_fn comm_count = nullptr;
   static errstr_fn errstr = nullptr;
-  if (!allreduce) {
+  if (!allgather) {
     void* h = nullptr;
     const char* names[] = {getenv("EO_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
     for (const char* nm : names) {
@@ -326,17 +401,31 @@ int eo_allreduce_stats(eo_ctx* ctx, void* nccl_comm) {
       if ((h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL))) break;
     }
     if (!h) return eo_fail(ctx, EO_ERR_UNSUPPORTED, "eo_allreduce_stats: libnccl.so.2 not found (set EO_NCCL_LIB)");
-    *(void**)(&allreduce) = dlsym(h, "ncclAllReduce");
+    *(void**)(&comm_count) = dlsym(h, "ncclCommCount");
     *(void**)(&errstr) = dlsym(h, "ncclGetErrorString");
-    if (!allreduce) return eo_fail(ctx, EO_ERR_UNSUPPORTED, "eo_allreduce_stats: ncclAllReduce not found in libnccl");
+    *(void**)(&allgather) = dlsym(h, "ncclAllGather");
+    if (!allgather || !comm_count) {
+      allgather = nullptr;
+      return eo_fail(ctx, EO_ERR_UNSUPPORTED, "eo_allreduce_stats: ncclAllGather / ncclCommCount not found in libnccl");
+    }
   }
-  EO_CUDA(ctx, cudaSetDevice(ctx->device));
-  static_assert(offsetof(eo_stats, niter_max) == (4 + EO_NITER_BINS) * 8, "SUM block first, MAX block after it");
-  char* base = reinterpret_cast<char*>(ctx->stats);
-  const int NCCL_INT64 = 4, NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2;
-  int rc = allreduce(base, base, 4 + EO_NITER_BINS, NCCL_INT64, NCCL_SUM, nccl_comm, ctx->s_cmp);
-  if (rc == 0) rc = allreduce(base + offsetof(eo_stats, niter_max), base + offsetof(eo_stats, niter_max), 4, NCCL_FLOAT64, NCCL_MAX, nccl_comm, ctx->s_cmp);
-  if (rc != 0) return eo_fail(ctx, EO_ERR_CUDA, "eo_allreduce_stats: ncclAllReduce: %s", errstr ? errstr(rc) : "error");
+  int world = 0;
+  int rc = comm_count(nccl_comm, &world);
+  if (rc != 0) return eo_fail(ctx, EO_ERR_CUDA, "eo_allreduce_stats: ncclCommCount: %s", errstr ? errstr(rc) : "error");
+  rc = eo_stats_collective_begin(ctx, world, nullptr, nullptr, nullptr, nullptr);
+  if (rc != EO_OK) return rc;
+  static_assert(sizeof(eo_stats) % 8 == 0 && offsetof(eo_stats, niter_max) == (4 + EO_NITER_BINS) * 8,
+                "SUM block first, MAX block after it, whole record a multiple of 8 bytes");
+  const int NCCL_INT64 = 4;
+  rc = allgather(ctx->stats_send, ctx->stats_recv, sizeof(eo_stats) / 8, NCCL_INT64, nccl_comm, ctx->s_coll);
+  if (rc != 0) return eo_fail(ctx, EO_ERR_CUDA, "eo_allreduce_stats: ncclAllGather: %s", errstr ? errstr(rc) : "error");
+  return eo_stats_collective_end(ctx, world);
+}
+
+int eo_stats_read_global(eo_ctx* ctx, eo_stats* out) {
+  EO_REQUIRE(ctx, ctx && out, "eo_stats_read_global: NULL argument");
+  EO_CUDA(ctx, cudaMemcpyAsync(out, ctx->stats_global, sizeof(eo_stats), cudaMemcpyDeviceToHost, ctx->s_coll));
+  EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_coll));
   return EO_OK;
 }
 

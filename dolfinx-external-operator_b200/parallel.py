@@ -5,7 +5,9 @@ external_operator.py:368-370, and `scatter_forward`s afterwards, :445).
 For Quadrature spaces every DOF is cell-interior and ghosts are recomputed locally, so the
 hot path needs NO data exchange.  The one collective is the all-reduce of the statistics
 record (plastic / non-converged counts, Newton-iteration histogram: SUM; maxima: MAX) that
-replaces the rank-local prints of demo_plasticity_mohr_coulomb.py:584-591.
+replaces the rank-local prints of demo_plasticity_mohr_coulomb.py:584-591: one all-gather of
+the 1.7 KB record + a local combine, into a record SEPARATE from the one the kernels
+accumulate into (`allreduce_stats`, C ABI `eo_allreduce_stats`).
 """
 
 from __future__ import annotations
@@ -58,15 +60,23 @@ def sum_shared(b_local: np.ndarray, dof_l2g: np.ndarray, n_dofs_global: int, bs:
     return t.numpy().reshape(-1)
 
 
-def stats_to_arrays(stats: dict) -> tuple[np.ndarray, np.ndarray]:
-    s = np.empty(N_SUM, dtype=np.int64)
-    s[0], s[1], s[2], s[3] = stats["n_points"], stats["n_plastic"], stats["n_nonconverged"], stats["n_nonfinite"]
-    s[4:] = stats["niter_hist"]
-    m = np.array([stats["niter_max"], stats["f_max"], stats["res_max"], 0.0])
-    return s, m
+def stats_to_record(stats: dict) -> np.ndarray:
+    """The statistics dict packed like `eo_stats` (include/eo_b200.h): N_SUM int64 then N_MAX float64, as one int64
+    vector (the float64 block bit-cast) - the payload of the collective on either backend."""
+    rec = np.zeros(N_SUM + N_MAX, dtype=np.int64)
+    rec[0], rec[1], rec[2], rec[3] = stats["n_points"], stats["n_plastic"], stats["n_nonconverged"], stats["n_nonfinite"]
+    rec[4:N_SUM] = stats["niter_hist"]
+    rec[N_SUM:].view(np.float64)[:] = [stats["niter_max"], stats["f_max"], stats["res_max"], 0.0]
+    return rec
 
 
-def arrays_to_stats(s: np.ndarray, m: np.ndarray) -> dict:
+def combine_records(records: np.ndarray) -> dict:
+    """records (world, N_SUM + N_MAX) int64 -> the global statistics dict: SUM over the int64 block, MAX over the float64
+    block (what `eo_stats_combine_kernel` does on the device)."""
+    records = np.ascontiguousarray(records, dtype=np.int64).reshape(-1, N_SUM + N_MAX)
+    s = records[:, :N_SUM].sum(axis=0)
+    m = np.ascontiguousarray(records[:, N_SUM:]).view(np.float64).reshape(-1, N_MAX)
+    m = np.where(np.isnan(m).all(axis=0), np.nan, np.nanmax(np.where(np.isnan(m), -np.inf, m), axis=0))
     return {
         "n_points": int(s[0]), "n_plastic": int(s[1]), "n_nonconverged": int(s[2]), "n_nonfinite": int(s[3]),
         "niter_hist": np.asarray(s[4:], dtype=np.int64).copy(),
@@ -75,37 +85,66 @@ def arrays_to_stats(s: np.ndarray, m: np.ndarray) -> dict:
 
 
 def allreduce_stats_host(stats: dict, group=None) -> dict:
-    """All-reduce a statistics dict through torch.distributed with host tensors (gloo)."""
+    """Global statistics from every rank's dict through torch.distributed with host tensors (gloo): ONE all-gather of
+    the packed record, combined locally.  The input is not modified."""
     import torch
     import torch.distributed as dist
 
-    s, m = stats_to_arrays(stats)
-    ts, tm = torch.from_numpy(s), torch.from_numpy(m)
-    dist.all_reduce(ts, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(tm, op=dist.ReduceOp.MAX, group=group)
-    return arrays_to_stats(ts.numpy(), tm.numpy())
+    rec = torch.from_numpy(stats_to_record(stats))
+    out = [torch.empty_like(rec) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(out, rec, group=group)
+    return combine_records(torch.stack(out).numpy())
 
 
-class _StatsView:
-    """`__cuda_array_interface__` window on a slice of the device statistics record."""
+class _DevView:
+    """`__cuda_array_interface__` window on device memory owned by the library."""
 
-    def __init__(self, ptr: int, n: int, typestr: str):
+    def __init__(self, ptr: int, n: int, typestr: str = "<i8"):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3,
                                          "strides": None}
 
 
-def allreduce_stats_device(ctx, group=None) -> None:
-    """In-place NCCL all-reduce of ctx's device statistics record, ordered on the ctx compute
-    stream (two tiny collectives: SUM over the int64 block, MAX over the f64 block)."""
+def allreduce_stats_device(ctx, group=None, stats: dict | None = None) -> None:
+    """The one collective of the hot path on a torch.distributed NCCL group: ctx's LOCAL statistics record (or `stats`,
+    a dict read earlier) of every rank -> ctx's GLOBAL record (`ctx.stats_global()`).  One `all_gather_into_tensor` of
+    the 1.7 KB record on the ctx's collective stream plus the library's combine kernel; asynchronous - it is ordered
+    after the work queued on the compute stream so far and overlaps whatever is queued next.  The local record is not
+    modified, so this may follow every evaluation of a record that keeps accumulating."""
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
 
-    base = ctx.stats_device_ptr
-    ts = torch.as_tensor(_StatsView(base, N_SUM, "<i8"), device=f"cuda:{ctx.device}")
-    tm = torch.as_tensor(_StatsView(base + 8 * N_SUM, N_MAX, "<f8"), device=f"cuda:{ctx.device}")
-    with torch.cuda.stream(torch.cuda.ExternalStream(ctx.stream, device=f"cuda:{ctx.device}")):
-        dist.all_reduce(ts, op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX, group=group)
+    from ._lib import Stats
+
+    world = dist.get_world_size(group)
+    send, recv, stream = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    host = None
+    if stats is not None:
+        host = Stats.from_buffer_copy(stats_to_record(stats).tobytes())
+    ctx.check(ctx.lib.eo_stats_collective_begin(ctx.handle, world, C.byref(host) if host is not None else None,
+                                                C.byref(send), C.byref(recv), C.byref(stream)))
+    nrec = N_SUM + N_MAX
+    dev = f"cuda:{ctx.device}"
+    t_send = torch.as_tensor(_DevView(send.value, nrec), device=dev)
+    t_recv = torch.as_tensor(_DevView(recv.value, nrec * world), device=dev)
+    with torch.cuda.stream(torch.cuda.ExternalStream(stream.value, device=dev)):
+        dist.all_gather_into_tensor(t_recv, t_send, group=group)
+    ctx.check(ctx.lib.eo_stats_collective_end(ctx.handle, world))
+
+
+def allreduce_stats(ctx, stats: dict | None = None, group=None) -> dict:
+    """Global statistics of all ranks of `group` (default: the world group), whatever its backend: NCCL -> on the
+    device (`allreduce_stats_device`, then one 1.7 KB read), anything else -> host tensors.  `stats` defaults to the
+    ctx's current local record.  Every rank of the group must call it."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("allreduce_stats needs an initialised torch.distributed process group (one rank per GPU)")
+    if "nccl" in str(dist.get_backend(group)):
+        allreduce_stats_device(ctx, group, stats)
+        return ctx.stats_global()
+    return allreduce_stats_host(stats if stats is not None else ctx.stats(), group)
 
 
 def bind_to_gpu_numa(device: int) -> list[int] | None:

@@ -125,9 +125,8 @@ int eo_fp64_peak(eo_ctx* ctx, int iters, double* tflops);
  * epilogue (one atomic per CTA).  replaces: the host-side `jnp.unique(niter,
  * return_counts=True)`, `jnp.max(yielding)`, `jnp.max(norm_res)` of
  * demo_plasticity_mohr_coulomb.py:584-591, and is the payload of the one
- * scalar all-reduce of a multi-GPU run (sums and maxima are kept apart so that
- * two tiny ncclAllReduce calls - SUM over the int64 block, MAX over the f64
- * block - combine ranks). */
+ * scalar all-reduce of a multi-GPU run (eo_allreduce_stats: sums over the int64
+ * block, maxima over the f64 block). */
 #define EO_NITER_BINS 208 /* local-Newton iteration histogram, bins 0..Nitermax(200); padded */
 typedef struct eo_stats {
   /* SUM block: 4 + EO_NITER_BINS int64 */
@@ -145,14 +144,25 @@ typedef struct eo_stats {
 int eo_stats_reset(eo_ctx* ctx);
 /* Copies the record to host (synchronises the ctx stream). */
 int eo_stats_read(eo_ctx* ctx, eo_stats* host_out);
-/* Device address of the record (for an in-place NCCL all-reduce). */
+/* Device address of the local record. */
 void* eo_stats_device_ptr(eo_ctx* ctx);
 /* The one collective of the hot path (quadrature points shard along the cell partition, one rank per GPU, no halo):
- * in-place all-reduce of the record - SUM over the int64 block, MAX over the f64 block - over the caller's
- * `ncclComm_t` (passed as void*), asynchronous on the ctx stream.  replaces: the rank-local prints of
- * demo_plasticity_mohr_coulomb.py:584-591 turned into global figures.  NCCL is resolved at run time (libnccl.so.2 of
- * the process; EO_NCCL_LIB overrides). */
+ * the records of all ranks of the caller's `ncclComm_t` (passed as void*) are combined - SUM over the int64 block, MAX
+ * over the f64 block - into a separate GLOBAL record; the local record is left untouched, so the call can follow every
+ * evaluation of a record that keeps accumulating without counting anything twice.  ONE ncclAllGather of the 1.7 KB
+ * record plus a combine kernel, on the ctx's collective stream: ordered after everything queued on the compute stream
+ * so far, overlapping whatever is queued afterwards; eo_stats_read_global / eo_sync wait for it.
+ * replaces: the rank-local prints of demo_plasticity_mohr_coulomb.py:584-591 turned into global figures.  NCCL is
+ * resolved at run time (libnccl.so.2 of the process; EO_NCCL_LIB overrides). */
 int eo_allreduce_stats(eo_ctx* ctx, void* nccl_comm);
+/* Copies the global record to host (synchronises the collective stream). */
+int eo_stats_read_global(eo_ctx* ctx, eo_stats* host_out);
+/* The same collective for callers whose communicator is not an ncclComm_t (torch.distributed process groups):
+ * _begin snapshots the local record (or uploads `host_record` when it is not NULL) and returns the send buffer (one
+ * record), the receive buffer (`world` records) and the collective stream (cudaStream_t as void*); the caller all-gathers
+ * send -> recv on that stream; _end launches the combine kernel there. */
+int eo_stats_collective_begin(eo_ctx* ctx, int world, const eo_stats* host_record, void** send, void** recv, void** stream);
+int eo_stats_collective_end(eo_ctx* ctx, int world);
 
 /* ---------------------------------------------------------------- von Mises
  * replaces: `return_mapping`/`_kernel`, doc/demo/demo_plasticity_von_mises.py:298-332,

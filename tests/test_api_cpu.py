@@ -152,6 +152,11 @@ hist = np.zeros(par.N_SUM - 4, dtype=np.int64); hist[1 + r] = 10 * (r + 1)
 st = dict(n_points=b - a, n_plastic=r + 1, n_nonconverged=r, n_nonfinite=0, niter_hist=hist,
           niter_max=float(3 + r), f_max=0.5 * (r + 1), res_max=1e-9 / (r + 1))
 out = par.allreduce_stats_host(st)
+assert st["n_points"] == b - a and st["n_plastic"] == r + 1          # the input is not modified
+assert par.allreduce_stats_host(st)["n_points"] == out["n_points"]   # ... so repeating the collective changes nothing
+assert par.allreduce_stats(None, st)["n_plastic"] == 3               # backend dispatch (gloo -> host tensors)
+rec = par.stats_to_record(st); back = par.combine_records(rec[None])
+assert back["n_points"] == st["n_points"] and back["f_max"] == st["f_max"] and np.array_equal(back["niter_hist"], hist)
 assert out["n_points"] == 1001 and out["n_plastic"] == 3 and out["n_nonconverged"] == 1
 assert out["niter_hist"][1] == 10 and out["niter_hist"][2] == 20
 assert out["niter_max"] == 4.0 and out["f_max"] == 1.0 and out["res_max"] == 1e-9
