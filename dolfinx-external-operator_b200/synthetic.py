@@ -177,6 +177,57 @@ def triangle_mesh(nx: int, ny: int, degree: int = 2, lx: float = 1.0, ly: float 
     return {"x": x, "x_dofmap": x_dofmap, "dofmap": dofmap, "n_dofs": int(n_dofs), "dof_coords": dof_coords}
 
 
+def renumber(mesh: dict, order: str = "shuffled", seed: int = 0) -> dict:
+    """The same mesh under another numbering of cells, dofs and geometry nodes - the structured generators number
+    everything row-major, which is the best case for the per-cell gathers of the tabulation / form kernels.
+
+    order = "shuffled": independent random permutations of cells, dofs and nodes (worst case: no two neighbouring cells
+            share a cache line);
+            "rcm": reverse Cuthill-McKee on the dof connectivity of a SHUFFLED mesh (nothing of the structured order
+            survives), cells sorted by their lowest dof - the locality an unstructured (gmsh) mesh has after the graph
+            reordering DOLFINx applies to dofs and cells when it builds a mesh / function space.
+    Returns a new dict with permuted x, x_dofmap, dofmap, dof_coords, plus `dof_new` (old dof -> new dof), `node_new`
+    and `cell_old` (new cell k is old cell cell_old[k]): per-cell results are the old ones in the order cell_old, bit
+    for bit; a dof vector maps as u_new[dof_new] = u_old (rows of bs components)."""
+    rng = np.random.default_rng(seed)
+    dofmap, x_dofmap, x = np.asarray(mesh["dofmap"]), np.asarray(mesh["x_dofmap"]), np.asarray(mesh["x"])
+    nc, n_dofs, n_nodes = dofmap.shape[0], int(mesh["n_dofs"]), x.shape[0]
+    dof_new, node_new, cell_old = rng.permutation(n_dofs), rng.permutation(n_nodes), rng.permutation(nc)
+    if order == "rcm":
+        from scipy.sparse import coo_matrix
+        from scipy.sparse.csgraph import reverse_cuthill_mckee
+
+        def rcm(conn, n, pre):
+            c = pre[conn].astype(np.int64)  # shuffled labels
+            k = c.shape[1]
+            rows, cols = np.repeat(c, k, axis=1).reshape(-1), np.tile(c, (1, k)).reshape(-1)
+            A = coo_matrix((np.ones(rows.size, dtype=np.int8), (rows, cols)), shape=(n, n)).tocsr()
+            perm = reverse_cuthill_mckee(A, symmetric_mode=True)  # position k holds shuffled label perm[k]
+            inv = np.empty(n, dtype=np.int64)
+            inv[perm] = np.arange(n)
+            return inv[pre]  # old label -> new label
+
+        dof_new = rcm(dofmap, n_dofs, dof_new)
+        node_new = rcm(x_dofmap, n_nodes, node_new)
+        cell_old = np.argsort(dof_new[dofmap].min(axis=1), kind="stable")
+    elif order != "shuffled":
+        raise ValueError(f"unknown numbering {order!r}")
+    out = dict(mesh)
+    out["dofmap"] = np.ascontiguousarray(dof_new[dofmap][cell_old], dtype=np.int32)
+    out["x_dofmap"] = np.ascontiguousarray(node_new[x_dofmap][cell_old], dtype=np.int32)
+    xn = np.empty_like(x)
+    xn[node_new] = x
+    out["x"] = xn
+    if "dof_coords" in mesh:
+        dc = np.empty_like(mesh["dof_coords"])
+        dc[dof_new] = mesh["dof_coords"]
+        out["dof_coords"] = dc
+    if "xq" in mesh:
+        out["xq"] = np.asarray(mesh["xq"])[cell_old]
+    out.update(dof_new=dof_new, node_new=node_new, cell_old=cell_old, order=order)
+    return out
+
+
 def smooth_displacement(dof_coords: np.ndarray, scale: float = 1e-3, seed: int = 0) -> np.ndarray:
     """A smooth random vector field sampled at the dof coordinates, blocked layout [node][comp]."""
     rng = np.random.default_rng(seed)

@@ -272,3 +272,93 @@ def test_full_size_properties(ctx):
     scale = np.abs(forms.action("mandel_strain", "mandel_strain", d_D, u)).max()
     rot = np.stack([-xy[:, 1], xy[:, 0]], 1).reshape(-1)
     assert np.abs(forms.action("mandel_strain", "mandel_strain", d_D, rot)).max() < 1e-11 * scale
+
+
+# ------------------------------------------------------------------ nb = 10 instantiations, renumbered meshes
+def test_forms_p3_triangles(ctx):
+    """form kernels <2,1,10> / <2,2,10>: vector, action (general + 4x4 TMA path), residual step vs the oracle."""
+    from tab_util import tri_case_discontinuous
+
+    m = tri_case_discontinuous(degree=3, nx=11, ny=8)
+    nc = m["dofmap"].shape[0]
+    rng = np.random.default_rng(4)
+    for bs, kt, ki in ((2, "mandel_strain", "mandel_strain"), (1, "grad", "value"), (2, "grad", "def_grad")):
+        tab, forms = _mk(ctx, m, bs)
+        s = rng.normal(size=(nc, 3, tab.ncomp(kt)))
+        _close(forms.vector(kt, ctx.to_device(s)), of.assemble_vector(KIND[kt], s, W3, m["dofmap"], bs, m["n_dofs"], *_geo(m)))
+        D = rng.normal(size=(nc, 3, tab.ncomp(kt) * tab.ncomp(ki)))
+        x = rng.normal(size=bs * m["n_dofs"])
+        ref = of.apply_action(KIND[kt], KIND[ki], D, x, W3, m["dofmap"], bs, m["n_dofs"], *_geo(m))
+        _close(forms.action(kt, ki, ctx.to_device(D), x), ref)
+    # residual step on P3: per-point results identical to the fused kernel, vector vs oracle
+    tab, forms = _mk(ctx, m, 2)
+    n = 3 * nc
+    u = syn.smooth_displacement(m["dof_coords"], scale=1.5e-3, seed=1).reshape(-1)
+    _, sn, p = syn.vm_batch(n, seed=2)
+    vm_a, vm_b = eo.VonMises(ctx=ctx), eo.VonMises(ctx=ctx)
+    vm_a.set_history(sn, p)
+    vm_b.set_history(sn, p)
+    b = forms.vm_residual(vm_a, u, exact=True)
+    Ct = tab.vm_fused(vm_b, u, exact=True)
+    assert np.array_equal(forms.C_tang.to_host(), Ct.to_host()) and np.array_equal(vm_a.sigma_dev.to_host(), vm_b.sigma_dev.to_host())
+    ref = of.assemble_vector(ot.MANDEL_STRAIN, vm_b.sigma_dev.to_host().reshape(nc, 3, 4), W3, m["dofmap"], 2, m["n_dofs"], *_geo(m))
+    _close(b, ref)
+
+
+def test_forms_p2_tetrahedra(ctx):
+    """form kernels <3,1,10> / <3,3,10>: P : grad(v) and the dP/dF action of a 3-d residual / Jacobian."""
+    from tab_util import tet_case_discontinuous
+
+    m = tet_case_discontinuous(n=3)
+    w = np.array([0.05, 0.04, 0.03, 1.0 / 6.0 - 0.12])
+    rng = np.random.default_rng(5)
+    nc, nq = m["dofmap"].shape[0], m["phi"].shape[0]
+    tab, forms = _mk(ctx, m, 3, w)
+    P = rng.normal(size=(nc, nq, 9))
+    _close(forms.vector("grad", ctx.to_device(P)), of.assemble_vector(ot.GRAD, P, w, m["dofmap"], 3, m["n_dofs"], *_geo(m)))
+    D = rng.normal(size=(nc, nq, 81))
+    x = rng.normal(size=3 * m["n_dofs"])
+    _close(forms.action("grad", "def_grad", ctx.to_device(D), x),
+           of.apply_action(ot.GRAD, ot.DEF_GRAD, D, x, w, m["dofmap"], 3, m["n_dofs"], *_geo(m)))
+    tab1, forms1 = _mk(ctx, m, 1, w)
+    q = rng.normal(size=(nc, nq, 3))
+    _close(forms1.vector("grad", ctx.to_device(q)), of.assemble_vector(ot.GRAD, q, w, m["dofmap"], 1, m["n_dofs"], *_geo(m)))
+    K = rng.normal(size=(nc, nq, 9))
+    T = rng.normal(size=m["n_dofs"])
+    _close(forms1.action("grad", "grad", ctx.to_device(K), T),
+           of.apply_action(ot.GRAD, ot.GRAD, K, T, w, m["dofmap"], 1, m["n_dofs"], *_geo(m)))
+
+
+@pytest.mark.parametrize("order", ["shuffled", "rcm"])
+def test_forms_on_renumbered_mesh(ctx, order):
+    """Residual step and tangent action under a random / RCM numbering: vectors equal the structured ones up to the dof
+    permutation (atomic scatter: to rounding), per-point results bit for bit."""
+    m = tri_case(nx=29, ny=31)
+    r = syn.renumber(m, order, seed=5)
+    nc = m["dofmap"].shape[0]
+    n = 3 * nc
+    u = syn.smooth_displacement(m["dof_coords"], scale=1.5e-3, seed=3)
+    ur = np.empty_like(u)
+    ur[r["dof_new"]] = u
+    _, sn, p = syn.vm_batch(n, seed=6)
+    co = r["cell_old"]
+    sn_r = sn.reshape(nc, 3, 4)[co].reshape(-1, 4)
+    p_r = p.reshape(nc, 3)[co].reshape(-1)
+    tab_s, forms_s = _mk(ctx, m, 2)
+    tab_r, forms_r = _mk(ctx, r, 2)
+    vm_s, vm_r = eo.VonMises(ctx=ctx), eo.VonMises(ctx=ctx)
+    vm_s.set_history(sn, p)
+    vm_r.set_history(sn_r, p_r)
+    b_s = forms_s.vm_residual(vm_s, u.reshape(-1), exact=True).copy()
+    b_r = forms_r.vm_residual(vm_r, ur.reshape(-1), exact=True).copy()
+    assert np.array_equal(forms_r.C_tang.to_host().reshape(nc, -1), forms_s.C_tang.to_host().reshape(nc, -1)[co])
+    _close(b_r.reshape(-1, 2), b_s.reshape(-1, 2)[np.argsort(r["dof_new"])], 1e-12)
+    x = np.random.default_rng(7).normal(size=u.shape)
+    xr = np.empty_like(x)
+    xr[r["dof_new"]] = x
+    y_s = forms_s.action("mandel_strain", "mandel_strain", forms_s.C_tang, x.reshape(-1)).copy()
+    y_r = forms_r.action("mandel_strain", "mandel_strain", forms_r.C_tang, xr.reshape(-1)).copy()
+    _close(y_r.reshape(-1, 2), y_s.reshape(-1, 2)[np.argsort(r["dof_new"])], 1e-12)
+    ref = of.apply_action(ot.MANDEL_STRAIN, ot.MANDEL_STRAIN, forms_r.C_tang.to_host().reshape(nc, 3, 16), xr.reshape(-1), W3,
+                          r["dofmap"], 2, r["n_dofs"], r["x"], r["x_dofmap"], r["phi"], r["dphi"], r["dpsi"])
+    _close(y_r, ref)

@@ -150,3 +150,23 @@ def test_p2_tetrahedra_reproduce_quadratic_fields(hc):
     F = ot.tabulate(ot.DEF_GRAD, u, m["dofmap"], 3, *geo)
     np.testing.assert_allclose(F[..., 0:3], gf(xq) + np.array([1.0, 0, 0]), atol=1e-11)
     np.testing.assert_allclose(_hc_tab(hc, m, ot.DEF_GRAD, u, 3, 3, 9), F, rtol=0, atol=1e-12 * np.abs(F).max())
+
+
+@pytest.mark.parametrize("order", ["shuffled", "rcm"])
+def test_renumbered_mesh_is_the_same_mesh(order):
+    """synthetic.renumber permutes cells / dofs / nodes consistently: the oracle returns the same per-cell values in the
+    new cell order, and RCM restores locality (small dof spread per cell) where the shuffle destroys it."""
+    from dolfinx_external_operator_b200 import synthetic as syn
+
+    m = tri_case(nx=12, ny=9)
+    r = syn.renumber(m, order, seed=2)
+    u = syn.smooth_displacement(m["dof_coords"], seed=3)
+    ur = np.empty_like(u)
+    ur[r["dof_new"]] = u
+    a = _tab(m, ot.MANDEL_STRAIN, u.reshape(-1), 2)
+    b = _tab(r, ot.MANDEL_STRAIN, ur.reshape(-1), 2)
+    assert np.array_equal(b, a[r["cell_old"]])
+    assert sorted(r["dof_new"]) == list(range(m["n_dofs"])) and sorted(r["cell_old"]) == list(range(m["dofmap"].shape[0]))
+    spread = lambda d: (d.max(axis=1) - d.min(axis=1)).mean()  # noqa: E731
+    if order == "rcm":
+        assert spread(r["dofmap"]) < 0.5 * spread(syn.renumber(m, "shuffled", seed=2)["dofmap"])

@@ -200,3 +200,91 @@ def test_lazy_operand_is_materialised_by_callables_that_do_not_fuse(ctx):
     b = [np.array(x) for x in mc((1,))(LazyOperand(tab, 2, u))]
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+# ------------------------------------------------------------------ nb = 10 instantiations of the fast path
+def test_p3_triangles_fast_path(ctx):
+    """tab_kernel<2,1,10> / <2,2,10> (P3 triangles, reference/test/test_nested_ex_op.py:93-105 sweeps these element
+    families): kernel vs oracle, and a cubic field reproduced exactly."""
+    from tab_util import tri_case_discontinuous
+
+    m = tri_case_discontinuous(degree=3, nx=13, ny=9)
+    x, y = m["dof_coords"][:, 0], m["dof_coords"][:, 1]
+    xq, yq = m["xq"][..., 0], m["xq"][..., 1]
+    f = lambda x, y: x**3 - 2 * x * x * y + 0.5 * y**3 + x * y - 0.3 * y  # noqa: E731
+    fx = lambda x, y: 3 * x * x - 4 * x * y + y  # noqa: E731
+    fy = lambda x, y: -2 * x * x + 1.5 * y * y + x - 0.3  # noqa: E731
+    T = f(x, y)
+    tab1 = _mk(ctx, m, 1)
+    val, grad = tab1.evaluate("value", T, output="host"), tab1.evaluate("grad", T, output="host")
+    _close(val, _ref(m, "value", T, 1))
+    _close(grad, _ref(m, "grad", T, 1), 1e-11)
+    np.testing.assert_allclose(val, f(xq, yq), atol=1e-13)
+    np.testing.assert_allclose(grad, np.stack([fx(xq, yq), fy(xq, yq)], -1), atol=1e-11)
+    u = np.stack([f(x, y), fy(x, y)], 1).reshape(-1)
+    tab2 = _mk(ctx, m, 2)
+    for kind in ("value", "grad", "mandel_strain", "def_grad"):
+        _close(tab2.evaluate(kind, u, output="host"), _ref(m, kind, u, 2), 1e-11)
+    cells = np.array([7, 0, 3, 3, m["dofmap"].shape[0] - 1], dtype=np.int32)
+    _close(tab2.evaluate("mandel_strain", u, entities=cells, output="host"), _ref(m, "mandel_strain", u, 2, cells), 1e-11)
+    # fused tabulate + von Mises on P3 (tab_vm_kernel<10, 3, *>) == two steps, bit for bit
+    n = m["dofmap"].shape[0] * 3
+    us = 2e-3 * u
+    _, sn, p = syn.vm_batch(n, seed=4)
+    vm_a, vm_b = eo.VonMises(ctx=ctx), eo.VonMises(ctx=ctx)
+    vm_a.set_history(sn, p)
+    vm_b.set_history(sn, p)
+    Ct_a, sig_a, dp_a = vm_a((1,))(tab2.evaluate("mandel_strain", us))
+    Ct_b = tab2.vm_fused(vm_b, us, exact=True)
+    assert np.array_equal(Ct_b.to_host(), Ct_a) and np.array_equal(vm_b.sigma_dev.to_host(), sig_a)
+    assert np.array_equal(vm_b.dp_dev.to_host(), dp_a) and 0.02 < (dp_a > 0).mean() < 0.98
+
+
+def test_p2_tetrahedra_fast_path(ctx):
+    """tab_kernel<3,1,10> / <3,3,10> (P2 tetrahedra): kernel vs oracle, quadratic fields reproduced exactly."""
+    from tab_util import tet_case_discontinuous
+
+    m = tet_case_discontinuous(n=3)
+    X, xq = m["dof_coords"], m["xq"]
+    f = lambda p: p[..., 0] ** 2 - p[..., 0] * p[..., 2] + 0.5 * p[..., 1] * p[..., 2] + p[..., 1]  # noqa: E731
+    gf = lambda p: np.stack([2 * p[..., 0] - p[..., 2], 0.5 * p[..., 2] + 1.0, -p[..., 0] + 0.5 * p[..., 1]], -1)  # noqa: E731
+    T = f(X)
+    tab1 = _mk(ctx, m, 1)
+    val, grad = tab1.evaluate("value", T, output="host"), tab1.evaluate("grad", T, output="host")
+    _close(val, _ref(m, "value", T, 1))
+    _close(grad, _ref(m, "grad", T, 1), 1e-11)
+    np.testing.assert_allclose(val, f(xq), atol=1e-13)
+    np.testing.assert_allclose(grad, gf(xq), atol=1e-11)
+    u = np.stack([f(X), 0.3 * X[:, 0] * X[:, 1], X[:, 2] ** 2], 1).reshape(-1)
+    tab3 = _mk(ctx, m, 3)
+    for kind in ("value", "grad", "def_grad"):
+        out = tab3.evaluate(kind, u, output="device")
+        _close(out.to_host(), _ref(m, kind, u, 3), 1e-11)
+    F = tab3.evaluate("def_grad", u, output="host")
+    np.testing.assert_allclose(F[..., 0, :], gf(xq) + np.array([1.0, 0, 0]), atol=1e-11)
+
+
+# ------------------------------------------------------------------ numbering-independent results
+@pytest.mark.parametrize("order", ["shuffled", "rcm"])
+def test_renumbered_mesh_gives_the_same_bits(ctx, order):
+    """The structured generators number dofs row-major (best case for the gathers).  Under a random / RCM numbering of
+    cells, dofs and nodes the kernels must return the SAME per-cell bits (in the new cell order) and agree with the oracle
+    evaluated on the renumbered mesh."""
+    m = tri_case(nx=33, ny=29)
+    r = syn.renumber(m, order, seed=2)
+    u = syn.smooth_displacement(m["dof_coords"], scale=1.5e-3, seed=3)
+    ur = np.empty_like(u)
+    ur[r["dof_new"]] = u
+    base = _mk(ctx, m, 2).evaluate("mandel_strain", u.reshape(-1), output="host")
+    tab = _mk(ctx, r, 2)
+    got = tab.evaluate("mandel_strain", ur.reshape(-1), output="host")
+    assert np.array_equal(got, base[r["cell_old"]])
+    _close(got, _ref(r, "mandel_strain", ur.reshape(-1), 2))
+    n = 3 * m["dofmap"].shape[0]
+    _, sn, p = syn.vm_batch(n, seed=9)
+    vm_a, vm_b = eo.VonMises(ctx=ctx), eo.VonMises(ctx=ctx)
+    vm_a.set_history(sn, p)
+    vm_b.set_history(sn, p)
+    Ct_a, _, dp_a = vm_a((1,))(got)
+    Ct_b = tab.vm_fused(vm_b, ur.reshape(-1), exact=True)
+    assert np.array_equal(Ct_b.to_host(), Ct_a) and np.array_equal(vm_b.dp_dev.to_host(), dp_a)
