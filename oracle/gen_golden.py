@@ -118,6 +118,21 @@ def gen_mc():
     print("mc random golden written; niter histogram", np.unique(out["niter"], return_counts=True))
 
 
+def gen_mc_big(n: int = 2048, seed: int = 1, procs: int | None = None):
+    """A larger random Mohr-Coulomb golden (>= 2000 points so that the Lode-corner set is populated):
+    same recipe as gen_mc, seed 1.  About 30 s of CPU per plastic point: run it in the background
+    (`nice python -m oracle.gen_golden mc_big`)."""
+    from . import constitutive as oc
+    from . import native
+
+    prm = oc.MohrCoulombParams()
+    step = lambda d, s: native.mc_stress(d, s, prm, parallel=True)[0]  # noqa: E731
+    d, s = inputs.mc_batch(n, seed=seed, stepper=step)
+    out = _mc_run(d, s, procs or int(os.environ.get("GEN_PROCS", "6")))
+    np.savez_compressed(os.path.join(GOLDEN, f"mc_rand_seed{seed}_n{n}.npz"), deps=d, sigma_n=s, **out)
+    print("mc big golden written; niter histogram", np.unique(out["niter"], return_counts=True))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     what = sys.argv[1:] or ["vm", "heat"]

@@ -146,3 +146,30 @@ def test_mc_oracle_against_live_reference():
     assert int(aux[1]) == int(o["niter"][0])
     _close(o["C_tang"][0], Ct.numpy(), MC_RTOL)
     _close(o["sigma"][0], aux[0].numpy(), MC_RTOL)
+
+
+def test_numba_restatement_is_bit_identical_to_the_reference_golden(golden_dir):
+    """oracle/numba_vm.py (the serial-Numba execution model bench.py times as the reference's own CPU callable) against
+    the golden made by the reference's Numba kernel."""
+    numba = pytest.importorskip("numba")  # noqa: F841
+    from oracle import numba_vm
+
+    g = np.load(os.path.join(golden_dir, "vm_seed0_n1026.npz"))
+    f = numba_vm.make_return_mapping()
+    for kind in ("mixed", "elastic", "plastic"):
+        Ct, s, dp = f(*(np.ascontiguousarray(g[f"{kind}_{k}"]) for k in ("deps", "sigma_n", "p")))
+        assert np.array_equal(Ct.reshape(-1), g[f"{kind}_C_tang"].reshape(-1))
+        assert np.array_equal(s.reshape(-1), g[f"{kind}_sigma"].reshape(-1)) and np.array_equal(dp, g[f"{kind}_dp"])
+
+
+def test_isihara_torch_restatement_against_the_reference_golden(golden_dir):
+    """oracle/isihara_torch.py (functional torch restatement, the CPU baseline of the Isihara bench leg) against the
+    golden made by the reference's own module: same float32 network, so agreement is far below the 2e-6 parity bound."""
+    from oracle import isihara_torch as it
+
+    g = np.load(os.path.join(golden_dir, "isihara_seed0_n2049.npz"))
+    sd = {k[3:]: g[k] for k in g.files if k.startswith("sd/")}
+    dP, P = it.dP_dF(g["F"][:300], sd)
+    assert np.abs(dP - g["dP"][:300]).max() <= 1e-8 * np.abs(g["dP"]).max()
+    assert np.abs(P - g["P"][:300]).max() <= 1e-8 * np.abs(g["P"]).max()
+    np.testing.assert_allclose(it.stress_correction(it._sd_tensors(sd)).numpy(), g["H_flat"], rtol=0, atol=1e-12)
