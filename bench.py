@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py - headline benchmark of the B200 quadrature-point engine.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--model vm|heat] [--n QP_PER_GPU]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model vm|heat|mc|...] [--n QP_PER_GPU]
     python bench.py --impl reference ...          # the CPU arm (reference algorithm on host cores)
 
 Metric (BASELINE.json): quadrature points per second for stress + consistent tangent +
@@ -18,19 +18,27 @@ internal state, on the von Mises configuration (configs[1]) evaluated on a synth
   roofline   algorithmic bytes per QP (240 for von Mises: SURVEY.md section 8d) x n / mean kernel time,
              against MEASURED_PEAKS.json's hbm_gbs.
   cpu_baseline  the C restatement of the reference's Numba kernel (oracle/, "port") on the
-             box's host cores, bounded sample.
+             box's host cores, bounded sample; plus the serial Numba kernel itself (`numba_serial`).
+  models     (default line only) every other kernel of the hot path timed the same way in the same run - Mohr-Coulomb,
+             heat, operand tabulation, fused tabulate + von Mises, residual step, tangent action, Isihara - each with
+             kernel_ms, its roofline fraction (HBM, or the FP64 / FP32 pipe peak measured in this run) and a short CPU
+             leg; `peaks` carries the measured denominators.
+  e2e_device_consumers  the same constitutive update consumed on the device (host DOF vector in, host residual out)
+             with its own CPU baseline (the C cell loop: tabulate + radial return + residual scatter).
 One JSON line on stdout (rank 0).
 """
 
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
 import sys
 import threading
 import time
+from types import SimpleNamespace
 
 import numpy as np
 
@@ -44,6 +52,13 @@ BYTES_PER_QP = {"vm": 240, "jitvm": 240, "jitfused": 235, "jitvm3d": 448, "heat"
 _CELL_GATHER = (24 + 12 + 96 + 48) / 3.0
 GATHERED_BYTES_PER_QP = {"tab": _CELL_GATHER + 32, "fused": _CELL_GATHER + 40 + 168, "jitfused": _CELL_GATHER + 40 + 168,
                          "step": _CELL_GATHER + 40 + 168 + 12 * 16 / 3.0, "action": _CELL_GATHER + 128 + 12 * 16 / 3.0}
+# ALGORITHMIC FP64 work of the Mohr-Coulomb path per point for the demo stress-path family (34 % plastic points, 2-5
+# Newton iterations): 2 x DFMA + DADD + DMUL thread instructions counted by ncu: yield test 245 +
+# Newton / tangent recursion 1768.  Fixed: a faster kernel that needs fewer instructions does not shrink it.
+MC_FLOPS_PER_QP = 2014.0
+# FP32 FMAs of the Isihara network per point: five 64x64 matrix-vector products + the 3->64 / 64->1 layers (isihara_core.cuh)
+ISIHARA_FMA_PER_QP = 5 * 64 * 64 + 64 * 16
+MESH_MODELS = ("tab", "fused", "jitfused", "step", "action")
 METRIC = "quadrature points per second (stress + consistent tangent + internal state)"
 
 
@@ -107,7 +122,20 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# ------------------------------------------------------------------------------- CPU arm
+# ------------------------------------------------------------------------------- CPU legs (oracle/ = the checker, timed)
+def _best_of(fn, min_seconds: float, min_passes: int = 3):
+    fn()  # warm-up (page faults, thread pool, JIT)
+    best, passes, t_all = float("inf"), 0, time.perf_counter()
+    while True:
+        t0 = time.perf_counter()
+        fn()
+        best = min(best, time.perf_counter() - t0)
+        passes += 1
+        if time.perf_counter() - t_all >= min_seconds and passes >= min_passes:
+            break
+    return best, passes
+
+
 def cpu_port_rate(model: str, sample_n: int, min_seconds: float, parallel: bool = True):
     """Time the oracle's C restatement on host cores over a bounded sample; returns (QP/s, cores, passes)."""
     from oracle import constitutive as oc
@@ -131,30 +159,60 @@ def cpu_port_rate(model: str, sample_n: int, min_seconds: float, parallel: bool 
         def fn():
             for w in ("q", "dqdT", "dqdsigma"):
                 native.heat(w, T, sigma, parallel=parallel)
-    fn()  # warm-up (page faults, thread pool)
-    best, passes, t_all = float("inf"), 0, time.perf_counter()
-    while True:
-        t0 = time.perf_counter()
-        fn()
-        dt = time.perf_counter() - t0
-        best = min(best, dt)
-        passes += 1
-        if time.perf_counter() - t_all >= min_seconds and passes >= 3:
-            break
+    best, passes = _best_of(fn, min_seconds)
     return sample_n / best, cores, passes
 
 
-def cpu_tab_rate(model: str, min_seconds: float):
+def cpu_numba_rate(sample_n: int, min_seconds: float):
+    """The reference's own CPU callable as it executes: serial @numba.njit loop (oracle/numba_vm.py, bit-identical to
+    the golden made by the reference's kernel).  None when numba is not importable."""
+    try:
+        from oracle import inputs, numba_vm
+
+        f = numba_vm.make_return_mapping()
+    except Exception:  # numba absent / unusable: reported as unavailable, never fatal
+        return None
+    deps, sigma_n, p = inputs.vm_batch(sample_n, seed=0)
+    best, passes = _best_of(lambda: f(deps, sigma_n, p), min_seconds, 2)
+    return {"value": sample_n / best, "unit": "QP/s", "cores": 1, "kind": "port",
+            "sample": f"{sample_n} QPs x {passes} passes (best pass): serial @numba.njit loop with per-point NumPy algebra and "
+                      "three fresh result arrays per call - the execution model of the reference's return_mapping "
+                      "(demo_plasticity_von_mises.py:298-332), restated in oracle/numba_vm.py and bit-identical to the golden made "
+                      "by the reference's kernel"}
+
+
+def cpu_isihara_rate(sample_n: int, min_seconds: float):
+    """The reference's torch evaluation (vmap(jacfwd(grad)) through the ICNN), restated in oracle/isihara_torch.py and
+    pinned to the golden made by the reference's module; eager ATen on torch.get_num_threads() threads."""
+    import torch
+
+    from oracle import inputs
+    from oracle import isihara_torch as it
+
+    try:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except (AttributeError, RuntimeError):
+        pass
+    g = np.load(os.path.join(ROOT, "tests", "golden", "isihara_seed0_n2049.npz"))
+    sd = {k[3:]: g[k] for k in g.files if k.startswith("sd/")}
+    F = inputs.isihara_batch(sample_n, seed=0)
+    best, passes = _best_of(lambda: it.dP_dF(F, sd, g["H_flat"]), min_seconds, 2)
+    return {"value": sample_n / best, "unit": "QP/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{sample_n} QPs x {passes} passes (best pass): torch.func vmap(jacfwd(grad)) through the float32 ICNN "
+                      "(demo_hyperelasticity.py:429-456), functional restatement pinned to the reference's golden"}
+
+
+def cpu_tab_rate(model: str, min_seconds: float, nxy: int = 800):
     """CPU baseline for the cell-loop legs (tab / fused / step / action): the OpenMP C restatement of the von Mises demo's
     cell loop (oracle/csrc/forms_oracle.c: tabulation of the Mandel strain, radial return, residual scatter, tangent
-    action) on all host cores, on a bounded mesh (1.28 M cells = 3.84 M quadrature points)."""
+    action) on all host cores, on a bounded mesh (nxy = 800: 1.28 M cells = 3.84 M quadrature points)."""
     from dolfinx_external_operator_b200 import elements as el
     from dolfinx_external_operator_b200 import synthetic as syn
     from oracle import constitutive as oc
     from oracle import native
 
     cores = native.use_all_cores()
-    m = syn.triangle_mesh(800, 800, 2, jitter=0.2, seed=0)
+    m = syn.triangle_mesh(nxy, nxy, 2, jitter=0.2, seed=0)
     m["phi"], m["dphi"] = el.lagrange_triangle(2, el.triangle_quadrature(2))
     m["dpsi"] = el.p1_geometry_derivatives(2)
     u = syn.smooth_displacement(m["dof_coords"], scale=1.5e-3, seed=0).reshape(-1)
@@ -171,15 +229,7 @@ def cpu_tab_rate(model: str, min_seconds: float):
         else:
             native.forms_p2_cells(mode, m, W3, u, prm, sn, p)
 
-    fn()
-    best, passes, t_all = float("inf"), 0, time.perf_counter()
-    while True:
-        t0 = time.perf_counter()
-        fn()
-        best = min(best, time.perf_counter() - t0)
-        passes += 1
-        if time.perf_counter() - t_all >= min_seconds and passes >= 3:
-            break
+    best, passes = _best_of(fn, min_seconds)
     what = {"tab": "tabulation of the Mandel strain", "fused": "tabulation + von Mises radial return",
             "step": "tabulation + von Mises radial return + residual scatter",
             "action": "tangent action (tabulate x, contract with the stored tangent, scatter)"}[mode]
@@ -189,44 +239,24 @@ def cpu_tab_rate(model: str, min_seconds: float):
                       "and Numba)"}
 
 
-def e2e_device_consumers(ctx, eo, inputs, ne, rank, world, max_over_ranks, barrier):
-    """Supplementary end-to-end figure of the default (von Mises) line: the same constitutive update consumed ON the
-    device (SURVEY.md 8f rank 1) - host displacement vector in, host residual vector out, tangent resident for the
-    matrix-free action - instead of shipping 168 B per point back to DOLFINx's assembler."""
-    from dolfinx_external_operator_b200 import elements as el
-
-    nxy = max(2, int(round((ne / 6.0) ** 0.5)))
-    mesh = inputs.triangle_mesh(nxy, nxy, 2, jitter=0.2, seed=rank)
-    nq = 3 * mesh["dofmap"].shape[0]
-    phi, dphi = el.lagrange_triangle(2, el.triangle_quadrature(2))
-    tab = eo.Tabulator(dofmap=mesh["dofmap"], x_dofmap=mesh["x_dofmap"], x=mesh["x"], phi=phi, dphi=dphi, bs=2,
-                       n_dofs=mesh["n_dofs"], ctx=ctx)
-    forms = eo.QuadratureForms(tab, el.triangle_quadrature_weights(2))
-    vm = eo.VonMises(n_qp=nq, ctx=ctx)
-    _, sn_t, p_t = inputs.vm_batch(min(nq, 1 << 22), seed=rank)
-    _tile_to_device(ctx, vm.sigma_n_dev, sn_t, nq, 4)
-    _tile_to_device(ctx, vm.p_dev, p_t, nq, 1)
-    nd = 2 * tab.n_dofs
-    u_h, b_h, y_h = ctx.pinned_empty((nd,)), ctx.pinned_empty((nd,)), ctx.pinned_empty((nd,))
-    u_h[:] = inputs.smooth_displacement(mesh["dof_coords"], scale=1.5e-3, seed=rank).reshape(-1)
-    del mesh
-    out = {}
-    for name, call in (("residual", lambda: forms.vm_residual(vm, u_h, out=b_h)),
-                       ("tangent_action", lambda: forms.action("mandel_strain", "mandel_strain", forms.C_tang, u_h, out=y_h))):
-        for _ in range(2):
-            call()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(5):
-            call()
-        ctx.sync()
-        dt = max_over_ranks(time.perf_counter() - t0)
-        out[name] = {"value": world * nq * 5 / dt, "unit": "QP/s", "ms_per_step": 1e3 * dt / 5}
-    out.update(h2d_bytes_per_step=8 * nd, d2h_bytes_per_step=8 * nd, qp_per_step_per_gpu=nq,
-               api="QuadratureForms.vm_residual(vm, u_host, out=b_host) / .action(..., x_host, out=y_host): eo_form_vm_step, "
-                   "eo_form_action; P2 vector triangles, 3 points per cell; boundary terms, lifting and the solve stay with "
-                   "the caller")
-    return out
+def cpu_leg(model: str, seconds: float, sample: float | None = None):
+    """The CPU baseline object of one bench leg (bounded sample, `seconds` of timed work at least)."""
+    if model == "isihara":
+        return cpu_isihara_rate(int(sample or 4096), seconds)
+    if model in MESH_MODELS:
+        return cpu_tab_rate(model, seconds, 800 if seconds >= 5 else 400)
+    cm = "vm" if model in ("jitvm", "jitvm3d") else model
+    n_s = int(sample or 4e6)
+    if model == "mc":
+        n_s = min(n_s, 200_000 if seconds >= 5 else 40_000)
+    rate, cores, passes = cpu_port_rate(cm, n_s, seconds, parallel=True)
+    what = {"vm": "C restatement of the reference's Numba kernel (serial in the reference)",
+            "jitvm": "C restatement of the reference's Numba kernel (serial in the reference)",
+            "jitvm3d": "C restatement of the reference's plane-strain Numba kernel (no 3-D CPU implementation exists)",
+            "heat": "C restatement of the reference's NumPy functions",
+            "mc": "C++ nested-dual-number restatement of the reference's JAX program (JAX not installable offline)"}
+    return {"value": rate, "unit": "QP/s", "cores": cores, "kind": "port",
+            "sample": f"{n_s} QPs x {passes} passes (best pass); {what[model]}, OpenMP"}
 
 
 def run_reference_arm(args):
@@ -240,8 +270,8 @@ def run_reference_arm(args):
     native.build()
     native.use_all_cores()
     cores = native.num_threads()
-    if args.model in ("tab", "fused", "step", "action"):
-        r = cpu_tab_rate(args.model, 5.0)
+    if args.model in ("tab", "fused", "step", "action", "isihara"):
+        r = cpu_tab_rate(args.model, 5.0) if args.model != "isihara" else cpu_isihara_rate(8192, 5.0)
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "QP/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -292,6 +322,10 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "QP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if args.model == "vm" and args.cpu_seconds > 0:
+        nb = cpu_numba_rate(min(sample, 1_000_000), 3.0)
+        if nb is not None:
+            line["cpu_baseline"]["numba_serial"] = nb
     print(json.dumps(line), flush=True)
 
 
@@ -312,7 +346,7 @@ WORKLOADS = {
     "jitfused": "operand tabulation fused into the run-time compiled (NVRTC) von Mises user model: P2 vector field, 3 points "
                 "per triangle, strain never stored, tangent by dual numbers",
     "tab": "operand tabulation: Mandel strain of a P2 vector field at 3 quadrature points per triangle "
-           "(evaluate_operands for the von Mises / Mohr-Coulomb demos), structured jittered mesh",
+           "(evaluate_operands for the von Mises / Mohr-Coulomb demos), jittered triangle mesh",
     "fused": "operand tabulation fused with the von Mises return mapping (strain never stored), P2 vector field, "
              "3 quadrature points per triangle",
     "step": "one Newton residual evaluation on the device (SURVEY.md 8f rank 1): Mandel strain of a P2 vector field -> "
@@ -343,9 +377,317 @@ def _tile_to_device(ctx, dst, tile: np.ndarray, n: int, width: int, itemsize: in
     d_tile.free()
 
 
-def run_gpu_arm(args):
+def build_mesh(ctx, eo, inputs, n, rank, order="structured"):
+    """P2 vector triangle mesh with ~n quadrature points (3 per cell), resident tabulator + forms + displacement."""
+    from dolfinx_external_operator_b200 import elements as el
+
+    nxy = max(2, int(round((n / 6.0) ** 0.5)))
+    mesh = inputs.triangle_mesh(nxy, nxy, 2, jitter=0.2, seed=rank)
+    if order != "structured":
+        mesh = inputs.renumber(mesh, order, seed=rank)
+    n_cells = mesh["dofmap"].shape[0]
+    phi, dphi = el.lagrange_triangle(2, el.triangle_quadrature(2))
+    tab = eo.Tabulator(dofmap=mesh["dofmap"], x_dofmap=mesh["x_dofmap"], x=mesh["x"], phi=phi, dphi=dphi, bs=2,
+                       n_dofs=mesh["n_dofs"], ctx=ctx)
+    d_u = ctx.to_device(inputs.smooth_displacement(mesh["dof_coords"], scale=1.5e-3, seed=rank).reshape(-1))
+    forms = eo.QuadratureForms(tab, el.triangle_quadrature_weights(2))
+    cfg = {"n_cells": n_cells, "n_dofs": mesh["n_dofs"], "element": "P2 vector triangle, 3-point rule", "mesh_order": order}
+    return SimpleNamespace(tab=tab, forms=forms, d_u=d_u, n_cells=n_cells, n=3 * n_cells, cfg=cfg, vm=None)
+
+
+def build_workload(model, ctx, eo, inputs, n, rank, args, mesh=None):
+    """Allocate the device-resident synthetic inputs of one leg (a seeded tile, seed = rank, repeated to n points) and
+    return a namespace with `step()` (one pass of the hot path over the batch), the point count `n`, config extras and
+    the objects the end-to-end legs reuse."""
     import ctypes as C
 
+    w = SimpleNamespace(model=model, n=int(n), cfg={}, keep=[])
+    tile_n = min(w.n, 1 << 22)
+    if model == "vm":
+        vm = eo.VonMises(n_qp=w.n, ctx=ctx, state_layout=args.state_layout)
+        deps_t, sn_t, p_t = inputs.vm_batch(tile_n, seed=rank)
+        d_deps = ctx.empty((w.n * 4,))
+        _tile_to_device(ctx, d_deps, deps_t, w.n, 4)
+        if args.state_layout == "soa":
+            for c in range(4):
+                col = ctx.to_device(np.ascontiguousarray(sn_t[:, c]))
+                for r in range(0, w.n, tile_n):
+                    m = min(tile_n, w.n - r)
+                    ctx.copy(vm.sigma_n_dev.ptr + (c * w.n + r) * 8, col, m * 8)
+                ctx.sync()
+                col.free()
+        else:
+            _tile_to_device(ctx, vm.sigma_n_dev, sn_t, w.n, 4)
+        _tile_to_device(ctx, vm.p_dev, p_t, w.n, 1)
+        d_Ct = ctx.empty((w.n * 16,))
+        w.keep += [vm, d_deps, d_Ct]
+        w.step = lambda: vm.eval_device(d_deps, d_Ct)
+    elif model in ("jitvm", "jitvm3d"):
+        from dolfinx_external_operator_b200 import jit_models as jm
+
+        nc = 6 if model == "jitvm3d" else 4
+        jv = jm.von_mises_3d(ctx=ctx) if model == "jitvm3d" else jm.von_mises(ctx=ctx)
+        if model == "jitvm3d":
+            rng = np.random.default_rng(rank)
+            deps_t, sn_t = rng.normal(0.0, 2e-3, (tile_n, 6)), rng.normal(0.0, 100.0, (tile_n, 6))
+            p_t = np.abs(rng.normal(0.0, 1e-3, tile_n))
+        else:
+            deps_t, sn_t, p_t = inputs.vm_batch(tile_n, seed=rank)
+        d_deps = ctx.empty((w.n * nc,))
+        _tile_to_device(ctx, d_deps, deps_t, w.n, nc)
+        jv.state = [ctx.empty((w.n * nc,)), ctx.empty((w.n,))]
+        _tile_to_device(ctx, jv.state[0], sn_t, w.n, nc)
+        _tile_to_device(ctx, jv.state[1], p_t, w.n, 1)
+        d_Ct, d_sig, d_dp = ctx.empty((w.n * nc * nc,)), ctx.empty((w.n * nc,)), ctx.empty((w.n,))
+        jv.compile((1,))
+        w.keep += [jv, d_deps, d_Ct, d_sig, d_dp]
+        w.step = lambda: jv.eval_device((1,), [d_deps], d_Ct, d_sig, [d_dp])
+    elif model == "mc":
+        from dolfinx_external_operator_b200._lib import McParams
+
+        mc = eo.MohrCoulomb(ctx=ctx, history=None)
+        tile_n = min(w.n, 1 << 20)
+        # the stress paths are walked with the GPU kernel itself as the stress update (SURVEY.md 8d)
+        deps_t, sn_t = inputs.mc_batch(tile_n, seed=rank, stepper=mc.stress_update)
+        d_deps, d_sn = ctx.empty((w.n * 4,)), ctx.empty((w.n * 4,))
+        _tile_to_device(ctx, d_deps, deps_t, w.n, 4)
+        _tile_to_device(ctx, d_sn, sn_t, w.n, 4)
+        d_Ct, d_sig = ctx.empty((w.n * 16,)), ctx.empty((w.n * 4,))
+        d_it = ctx.empty((w.n,), np.int32)
+        d_yl, d_nr, d_dl = ctx.empty((w.n,)), ctx.empty((w.n,)), ctx.empty((w.n,))
+        prm = McParams(mc.E, mc.nu, mc.c, mc.phi, mc.psi, mc.theta_T, mc.a, mc.tol, mc.Nitermax)
+        scheme = {"queue": 0, "simple": 1, "queue-noaffinity": 2, "queue-onepass": 3}[args.mc_scheme]
+        w.cfg["mc_scheme"] = args.mc_scheme
+        w.deps_t, w.sn_t = deps_t, sn_t
+        w.keep += [mc, d_deps, d_sn, d_Ct, d_sig, d_it, d_yl, d_nr, d_dl]
+        n_ = w.n
+        w.step = lambda: ctx.check(ctx.lib.eo_mc_eval_scheme(ctx.handle, C.byref(prm), d_deps.ptr, d_sn.ptr, d_Ct.ptr, d_sig.ptr,
+                                                             d_it.ptr, d_yl.ptr, d_nr.ptr, d_dl.ptr, n_, scheme))
+    elif model == "isihara":
+        gpath = os.path.join(ROOT, "tests", "golden", "isihara_seed0_n2049.npz")  # carries the reference's state dict
+        g = np.load(gpath)
+        isi = eo.Isihara({k[3:]: g[k] for k in g.files if k.startswith("sd/")}, ctx=ctx)
+        F_t = inputs.isihara_batch(tile_n, seed=rank)
+        d_F = ctx.empty((w.n * 4,))
+        _tile_to_device(ctx, d_F, F_t, w.n, 4)
+        d_dP, d_P = ctx.empty((w.n * 16,)), ctx.empty((w.n * 4,))
+        w.isi, w.F_t = isi, F_t
+        w.keep += [d_F, d_dP, d_P]
+        w.step = lambda: isi.eval_device(d_F, d_dP, d_P)
+    elif model in MESH_MODELS:
+        M = mesh if mesh is not None else build_mesh(ctx, eo, inputs, w.n, rank, args.mesh_order)
+        w.mesh = M
+        w.n = M.n
+        w.cfg.update(M.cfg)
+        tab, forms, d_u = M.tab, M.forms, M.d_u
+        tile_n = min(w.n, 1 << 22)
+        if model == "tab":
+            d_out = ctx.empty((M.n_cells, 3, 4))
+            w.keep.append(d_out)
+            w.step = lambda: tab.evaluate("mandel_strain", d_u, out=d_out)
+        elif model == "jitfused":
+            from dolfinx_external_operator_b200 import jit_models as jm
+            from dolfinx_external_operator_b200.tabulation import LazyOperand
+
+            jv = jm.von_mises(ctx=ctx)
+            _, sn_t, p_t = inputs.vm_batch(tile_n, seed=rank)
+            jv.state = [ctx.empty((w.n * 4,)), ctx.empty((w.n,))]
+            _tile_to_device(ctx, jv.state[0], sn_t, w.n, 4)
+            _tile_to_device(ctx, jv.state[1], p_t, w.n, 1)
+            dev = {"out": ctx.empty((w.n * 16,)), "value": ctx.empty((w.n * 4,)), "aux0": ctx.empty((w.n,))}
+            lz = [LazyOperand(tab, 2, d_u)]
+            dd = jv._deriv((1,))[1]
+            w.keep += [jv, dev]
+            w.step = lambda: jv._evaluate_fused((1,), dd, 16, lz, dev)
+        else:
+            vm = M.vm
+            if vm is None:
+                vm = M.vm = eo.VonMises(n_qp=w.n, ctx=ctx)
+                _, sn_t, p_t = inputs.vm_batch(tile_n, seed=rank)
+                _tile_to_device(ctx, vm.sigma_n_dev, sn_t, w.n, 4)
+                _tile_to_device(ctx, vm.p_dev, p_t, w.n, 1)
+            w.vm = vm
+            w.cfg["vm_arithmetic"] = "exact" if args.fused_exact else "fast (2 divisions, FMA; identical flags)"
+            if model == "fused":
+                if forms.C_tang is None or forms.C_tang.size != 16 * w.n:
+                    forms.C_tang = ctx.empty((16 * w.n,))
+                w.step = lambda: tab.vm_fused(vm, d_u, C_tang=forms.C_tang, exact=args.fused_exact)
+            else:
+                w.cfg["scatter"] = "fp64 RED.ADD per element-vector entry (12 per cell)"
+                d_b = ctx.empty((2 * tab.n_dofs,))
+                w.keep.append(d_b)
+                if model == "step":
+                    w.step = lambda: forms.vm_residual(vm, d_u, out=d_b, exact=args.fused_exact)
+                else:
+                    forms.vm_residual(vm, d_u, out=d_b, exact=args.fused_exact)  # fills forms.C_tang
+                    d_y = ctx.empty((2 * tab.n_dofs,))
+                    w.keep.append(d_y)
+                    w.step = lambda: forms.action("mandel_strain", "mandel_strain", forms.C_tang, d_u, out=d_y)
+    elif model == "heat":
+        T_t, s_t = inputs.heat_batch(tile_n, seed=rank)
+        d_T, d_s = ctx.empty((w.n,)), ctx.empty((w.n * 2,))
+        _tile_to_device(ctx, d_T, T_t, w.n, 1)
+        _tile_to_device(ctx, d_s, s_t, w.n, 2)
+        d_q, d_dT, d_ds = ctx.empty((w.n * 2,)), ctx.empty((w.n * 2,)), ctx.empty((w.n * 4,))
+        w.keep += [d_T, d_s, d_q, d_dT, d_ds]
+        n_ = w.n
+        w.step = lambda: ctx.check(ctx.lib.eo_heat_eval(ctx.handle, 1.0, 1.0, d_T.ptr, d_s.ptr, None, None, d_q.ptr, d_dT.ptr,
+                                                        d_ds.ptr, n_))
+    else:
+        raise ValueError(model)
+    return w
+
+
+def time_steps(ctx, step, K, W, barrier, max_over_ranks, collective=None, sampler=None):
+    """W untimed warm-up steps, then K steps bracketed by barrier + sync; CUDA events on the library's compute stream
+    around the whole region and around every step's kernel(s).  Returns (total_ms max over ranks, [kernel_ms], launches)."""
+    for _ in range(W):
+        step()
+        if collective:
+            collective()
+    ctx.sync()
+    ctx.stats_reset()
+    ev = [ctx.event() for _ in range(2 * K + 2)]
+    barrier()
+    ctx.sync()
+    if sampler:
+        sampler.start()
+    launches0 = ctx.launch_count
+    ctx.record(ev[0])
+    for k in range(K):
+        ctx.record(ev[2 + 2 * k])
+        step()
+        ctx.record(ev[3 + 2 * k])
+        if collective:
+            collective()
+    ctx.record(ev[1])
+    ctx.sync()  # all streams of the context, the collective stream included
+    barrier()
+    total_ms = max_over_ranks(ctx.elapsed_ms(ev[0], ev[1]))
+    kernel_ms = [ctx.elapsed_ms(ev[2 + 2 * k], ev[3 + 2 * k]) for k in range(K)]
+    for e in ev:
+        ctx.lib.eo_event_destroy(ctx.handle, e)
+    return total_ms, kernel_ms, ctx.launch_count - launches0
+
+
+def roofline_for(model, n, k_ms, peaks, traffic=None):
+    hbm_peak, hbm_src = peaks["hbm_gbs"], peaks["hbm_source"]
+    hbm_achieved = BYTES_PER_QP[model] * n / (k_ms * 1e-3) / 1e9
+    hbm = {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+           "bytes_per_qp": BYTES_PER_QP[model]}
+    if model == "mc":
+        ach = MC_FLOPS_PER_QP * n / (k_ms * 1e-3) / 1e12
+        return {"bound": "fp64", "achieved": ach, "peak": peaks["fp64_tflops"], "unit": "TFLOP/s",
+                "frac": ach / peaks["fp64_tflops"], "traffic": traffic,
+                "peak_source": "measured in this run: eo_fp64_peak DFMA micro-benchmark (8 chains/thread, all SMs)",
+                "fp64_flops_per_qp": MC_FLOPS_PER_QP, "kernel_ms": k_ms, "hbm": hbm}
+    if model == "isihara":
+        ach = 2.0 * ISIHARA_FMA_PER_QP * n / (k_ms * 1e-3) / 1e12
+        return {"bound": "fp32", "achieved": ach, "peak": peaks["fp32_tflops"], "unit": "TFLOP/s",
+                "frac": ach / peaks["fp32_tflops"], "traffic": traffic,
+                "peak_source": "measured in this run: eo_fp32_peak FFMA micro-benchmark (8 chains/thread, all SMs)",
+                "fma_per_qp": ISIHARA_FMA_PER_QP, "kernel_ms": k_ms, "hbm": hbm}
+    r = {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+         "traffic": traffic, "peak_source": hbm_src, "bytes_per_qp": BYTES_PER_QP[model], "kernel_ms": k_ms}
+    if model in GATHERED_BYTES_PER_QP:
+        # SURVEY.md 8d: the gather-limited kernels report the unique-byte fraction (above: what must cross HBM once)
+        # and the gathered-byte fraction (what the threads request: every cell's own copy of its dofs / vertices)
+        gb = GATHERED_BYTES_PER_QP[model]
+        ga = gb * n / (k_ms * 1e-3) / 1e9
+        r["gathered"] = {"bytes_per_qp": gb, "achieved": ga, "unit": "GB/s", "frac_of_hbm_peak": ga / hbm_peak,
+                         "note": "requested bytes (per-cell copies of shared dofs / vertices served by L1/L2)"}
+    return r
+
+
+def _traffic(model, n):
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(tpath):
+        return None
+    with open(tpath) as fh:
+        tj = json.load(fh).get(model)
+    return tj.get("dram_bytes_per_launch") if (tj and tj.get("n") == n) else None
+
+
+def _stats_cfg(model, stats):
+    out = {"plastic_fraction": stats["n_plastic"] / max(stats["n_points"], 1)}
+    if model == "mc":
+        hist = stats["niter_hist"]
+        tot = max(int(hist.sum()), 1)
+        out["niter_histogram"] = {int(i): float(hist[i]) / tot for i in np.nonzero(hist)[0]}
+        out["n_nonconverged"] = stats["n_nonconverged"]
+    return out
+
+
+def models_block(ctx, eo, inputs, args, rank, world, peaks, barrier, max_over_ranks, collective):
+    """Every other kernel of the hot path, timed like the headline leg (W >= 3 warm-ups, K steps, CUDA events, max over
+    ranks, the statistics collective after every step when n_gpus > 1), one after the other with its buffers freed in
+    between.  Inputs + outputs of every leg are far larger than L2 (no flush needed)."""
+    K, W = args.models_steps, 3
+    out = {}
+    names = [m for m in args.models.split(",") if m]
+    n_for = {"isihara": min(args.n, int(args.models_isihara_n))}
+    mesh_names = [m for m in names if m in MESH_MODELS]
+    mesh = None
+    for name in names:
+        if name in MESH_MODELS and mesh is None:
+            mesh = build_mesh(ctx, eo, inputs, int(args.n), rank, args.mesh_order)
+        wl = build_workload(name, ctx, eo, inputs, n_for.get(name, args.n), rank, args, mesh=mesh)
+        total_ms, k_ms, launches = time_steps(ctx, wl.step, K, W, barrier, max_over_ranks, collective)
+        stats = ctx.stats()
+        km = float(np.mean(k_ms))
+        entry = {"workload": WORKLOADS[name], "qp_per_gpu": wl.n, "steps": K, "warmup": W, "kernel_ms": km,
+                 "ms_per_step": total_ms / K, "value": world * wl.n * K / (total_ms * 1e-3), "unit": "QP/s",
+                 "gpu_launches": int(launches), "roofline": roofline_for(name, wl.n, km, peaks, _traffic(name, wl.n))}
+        if name in ("mc", "fused", "step"):
+            entry.update(_stats_cfg(name, stats))
+        entry.update(wl.cfg)
+        if rank == 0 and world == 1 and args.models_cpu_seconds > 0:
+            entry["cpu_baseline"] = cpu_leg(name, args.models_cpu_seconds)
+        out[name] = entry
+        del wl
+        if name in MESH_MODELS and name == mesh_names[-1]:
+            mesh = None
+        gc.collect()
+    return out
+
+
+def e2e_device_consumers(ctx, eo, inputs, ne, rank, world, max_over_ranks, barrier, cpu_seconds):
+    """Supplementary end-to-end figure of the default (von Mises) line: the same constitutive update consumed ON the
+    device (SURVEY.md 8f rank 1) - host displacement vector in, host residual vector out, tangent resident for the
+    matrix-free action - instead of shipping 168 B per point back to DOLFINx's assembler."""
+    M = build_mesh(ctx, eo, inputs, ne, rank)
+    tab, forms, nq = M.tab, M.forms, M.n
+    vm = eo.VonMises(n_qp=nq, ctx=ctx)
+    _, sn_t, p_t = inputs.vm_batch(min(nq, 1 << 22), seed=rank)
+    _tile_to_device(ctx, vm.sigma_n_dev, sn_t, nq, 4)
+    _tile_to_device(ctx, vm.p_dev, p_t, nq, 1)
+    nd = 2 * tab.n_dofs
+    u_h, b_h, y_h = ctx.pinned_empty((nd,)), ctx.pinned_empty((nd,)), ctx.pinned_empty((nd,))
+    M.d_u.to_host(u_h)
+    out = {}
+    for name, call in (("residual", lambda: forms.vm_residual(vm, u_h, out=b_h)),
+                       ("tangent_action", lambda: forms.action("mandel_strain", "mandel_strain", forms.C_tang, u_h, out=y_h))):
+        for _ in range(3):
+            call()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            call()
+        ctx.sync()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        out[name] = {"value": world * nq * 5 / dt, "unit": "QP/s", "ms_per_step": 1e3 * dt / 5}
+    out.update(h2d_bytes_per_step=8 * nd, d2h_bytes_per_step=8 * nd, qp_per_step_per_gpu=nq,
+               api="QuadratureForms.vm_residual(vm, u_host, out=b_host) / .action(..., x_host, out=y_host): eo_form_vm_step, "
+                   "eo_form_action; P2 vector triangles, 3 points per cell; boundary terms, lifting and the solve stay with "
+                   "the caller")
+    if rank == 0 and world == 1 and cpu_seconds > 0:
+        # the reference-side counterpart of `residual`: host u in, host b out (+ tangent / stress / dp in host memory)
+        out["residual"]["cpu_baseline"] = cpu_tab_rate("step", min(cpu_seconds, 5.0))
+        out["tangent_action"]["cpu_baseline"] = cpu_tab_rate("action", min(cpu_seconds, 3.0), 400)
+    return out
+
+
+def run_gpu_arm(args):
     import dolfinx_external_operator_b200 as eo
     from dolfinx_external_operator_b200 import synthetic as inputs
 
@@ -383,168 +725,14 @@ def run_gpu_arm(args):
 
         numa_cores = bind_to_gpu_numa(local_rank)
     ctx = eo.Context(local_rank)
-    n = int(args.n)
     model = args.model
     K, W = args.steps, args.warmup
-    tile_n = min(n, 1 << 22)
-    extra_cfg = {}
 
-    # ---- synthetic inputs: a seeded tile (seed = rank) repeated to n points, resident in HBM
-    if model == "vm":
-        vm = eo.VonMises(n_qp=n, ctx=ctx, state_layout=args.state_layout)
-        deps_t, sn_t, p_t = inputs.vm_batch(tile_n, seed=rank)
-        d_deps = ctx.empty((n * 4,))
-        _tile_to_device(ctx, d_deps, deps_t, n, 4)
-        if args.state_layout == "soa":
-            for c in range(4):
-                col = ctx.to_device(np.ascontiguousarray(sn_t[:, c]))
-                for r in range(0, n, tile_n):
-                    m = min(tile_n, n - r)
-                    ctx.copy(vm.sigma_n_dev.ptr + (c * n + r) * 8, col, m * 8)
-                ctx.sync()
-                col.free()
-        else:
-            _tile_to_device(ctx, vm.sigma_n_dev, sn_t, n, 4)
-        _tile_to_device(ctx, vm.p_dev, p_t, n, 1)
-        d_Ct = ctx.empty((n * 16,))
-
-        def step():
-            vm.eval_device(d_deps, d_Ct)
-    elif model == "jitvm3d":
-        from dolfinx_external_operator_b200 import jit_models as jm
-
-        jv = jm.von_mises_3d(ctx=ctx)
-        rng = np.random.default_rng(rank)
-        deps_t, sn_t = rng.normal(0.0, 2e-3, (tile_n, 6)), rng.normal(0.0, 100.0, (tile_n, 6))
-        p_t = np.abs(rng.normal(0.0, 1e-3, tile_n))
-        d_deps = ctx.empty((n * 6,))
-        _tile_to_device(ctx, d_deps, deps_t, n, 6)
-        jv.state = [ctx.empty((n * 6,)), ctx.empty((n,))]
-        _tile_to_device(ctx, jv.state[0], sn_t, n, 6)
-        _tile_to_device(ctx, jv.state[1], p_t, n, 1)
-        d_Ct, d_sig, d_dp = ctx.empty((n * 36,)), ctx.empty((n * 6,)), ctx.empty((n,))
-        jv.compile((1,))
-
-        def step():
-            jv.eval_device((1,), [d_deps], d_Ct, d_sig, [d_dp])
-    elif model == "jitvm":
-        from dolfinx_external_operator_b200 import jit_models as jm
-
-        jv = jm.von_mises(ctx=ctx)
-        deps_t, sn_t, p_t = inputs.vm_batch(tile_n, seed=rank)
-        d_deps = ctx.empty((n * 4,))
-        _tile_to_device(ctx, d_deps, deps_t, n, 4)
-        jv.state = [ctx.empty((n * 4,)), ctx.empty((n,))]
-        _tile_to_device(ctx, jv.state[0], sn_t, n, 4)
-        _tile_to_device(ctx, jv.state[1], p_t, n, 1)
-        d_Ct, d_sig, d_dp = ctx.empty((n * 16,)), ctx.empty((n * 4,)), ctx.empty((n,))
-        jv.compile((1,))
-
-        def step():
-            jv.eval_device((1,), [d_deps], d_Ct, d_sig, [d_dp])
-    elif model == "mc":
-        from dolfinx_external_operator_b200._lib import McParams
-
-        mc = eo.MohrCoulomb(ctx=ctx, history=None)
-        tile_n = min(n, 1 << 20)
-        # the stress paths are walked with the GPU kernel itself as the stress update
-        deps_t, sn_t = inputs.mc_batch(tile_n, seed=rank, stepper=mc.stress_update)
-        d_deps, d_sn = ctx.empty((n * 4,)), ctx.empty((n * 4,))
-        _tile_to_device(ctx, d_deps, deps_t, n, 4)
-        _tile_to_device(ctx, d_sn, sn_t, n, 4)
-        d_Ct, d_sig = ctx.empty((n * 16,)), ctx.empty((n * 4,))
-        d_it = ctx.empty((n,), np.int32)
-        d_yl, d_nr, d_dl = ctx.empty((n,)), ctx.empty((n,)), ctx.empty((n,))
-        prm = McParams(mc.E, mc.nu, mc.c, mc.phi, mc.psi, mc.theta_T, mc.a, mc.tol, mc.Nitermax)
-        scheme = {"queue": 0, "simple": 1, "queue-noaffinity": 2, "queue-onepass": 3}[args.mc_scheme]
-        extra_cfg["mc_scheme"] = args.mc_scheme
-
-        def step():
-            ctx.check(ctx.lib.eo_mc_eval_scheme(ctx.handle, C.byref(prm), d_deps.ptr, d_sn.ptr, d_Ct.ptr, d_sig.ptr,
-                                                d_it.ptr, d_yl.ptr, d_nr.ptr, d_dl.ptr, n, scheme))
-    elif model == "isihara":
-        gpath = os.path.join(ROOT, "tests", "golden", "isihara_seed0_n2049.npz")  # carries the reference's state dict
-        g = np.load(gpath)
-        isi = eo.Isihara({k[3:]: g[k] for k in g.files if k.startswith("sd/")}, ctx=ctx)
-        F_t = inputs.isihara_batch(tile_n, seed=rank)
-        d_F = ctx.empty((n * 4,))
-        _tile_to_device(ctx, d_F, F_t, n, 4)
-        d_dP, d_P = ctx.empty((n * 16,)), ctx.empty((n * 4,))
-
-        def step():
-            isi.eval_device(d_F, d_dP, d_P)
-    elif model in ("tab", "fused", "jitfused", "step", "action"):
-        from dolfinx_external_operator_b200 import elements as el
-
-        nxy = max(2, int(round((n / 6.0) ** 0.5)))
-        mesh = inputs.triangle_mesh(nxy, nxy, 2, jitter=0.2, seed=rank)
-        n_cells = mesh["dofmap"].shape[0]
-        n = 3 * n_cells  # quadrature points actually processed
-        phi, dphi = el.lagrange_triangle(2, el.triangle_quadrature(2))
-        tab = eo.Tabulator(dofmap=mesh["dofmap"], x_dofmap=mesh["x_dofmap"], x=mesh["x"], phi=phi, dphi=dphi, bs=2,
-                           n_dofs=mesh["n_dofs"], ctx=ctx)
-        d_u = ctx.to_device(inputs.smooth_displacement(mesh["dof_coords"], scale=1.5e-3, seed=rank).reshape(-1))
-        extra_cfg.update(n_cells=n_cells, n_dofs=mesh["n_dofs"], element="P2 vector triangle, 3-point rule")
-        del mesh
-        if model == "tab":
-            d_out = ctx.empty((n_cells, 3, 4))
-
-            def step():
-                tab.evaluate("mandel_strain", d_u, out=d_out)
-        elif model in ("step", "action"):
-            forms = eo.QuadratureForms(tab, el.triangle_quadrature_weights(2))
-            vm = eo.VonMises(n_qp=n, ctx=ctx)
-            _, sn_t, p_t = inputs.vm_batch(tile_n, seed=rank)
-            _tile_to_device(ctx, vm.sigma_n_dev, sn_t, n, 4)
-            _tile_to_device(ctx, vm.p_dev, p_t, n, 1)
-            d_b = ctx.empty((2 * tab.n_dofs,))
-            extra_cfg["vm_arithmetic"] = "exact" if args.fused_exact else "fast (2 divisions, FMA; identical flags)"
-            extra_cfg["scatter"] = "fp64 RED.ADD per element-vector entry (12 per cell)"
-            if model == "step":
-                def step():
-                    forms.vm_residual(vm, d_u, out=d_b, exact=args.fused_exact)
-            else:
-                forms.vm_residual(vm, d_u, out=d_b, exact=args.fused_exact)  # fills forms.C_tang
-                d_y = ctx.empty((2 * tab.n_dofs,))
-
-                def step():
-                    forms.action("mandel_strain", "mandel_strain", forms.C_tang, d_u, out=d_y)
-        elif model == "jitfused":
-            from dolfinx_external_operator_b200 import jit_models as jm
-            from dolfinx_external_operator_b200.tabulation import LazyOperand
-
-            jv = jm.von_mises(ctx=ctx)
-            _, sn_t, p_t = inputs.vm_batch(tile_n, seed=rank)
-            jv.state = [ctx.empty((n * 4,)), ctx.empty((n,))]
-            _tile_to_device(ctx, jv.state[0], sn_t, n, 4)
-            _tile_to_device(ctx, jv.state[1], p_t, n, 1)
-            dev = {"out": ctx.empty((n * 16,)), "value": ctx.empty((n * 4,)), "aux0": ctx.empty((n,))}
-            lz = [LazyOperand(tab, 2, d_u)]
-            dd = jv._deriv((1,))[1]
-
-            def step():
-                jv._evaluate_fused((1,), dd, 16, lz, dev)
-        else:
-            vm = eo.VonMises(n_qp=n, ctx=ctx)
-            _, sn_t, p_t = inputs.vm_batch(tile_n, seed=rank)
-            _tile_to_device(ctx, vm.sigma_n_dev, sn_t, n, 4)
-            _tile_to_device(ctx, vm.p_dev, p_t, n, 1)
-            d_Ct = ctx.empty((n * 16,))
-
-            extra_cfg["vm_arithmetic"] = "exact" if args.fused_exact else "fast (2 divisions, FMA; identical flags)"
-
-            def step():
-                tab.vm_fused(vm, d_u, C_tang=d_Ct, exact=args.fused_exact)
-    else:
-        T_t, s_t = inputs.heat_batch(tile_n, seed=rank)
-        d_T, d_s = ctx.empty((n,)), ctx.empty((n * 2,))
-        _tile_to_device(ctx, d_T, T_t, n, 1)
-        _tile_to_device(ctx, d_s, s_t, n, 2)
-        d_q, d_dT, d_ds = ctx.empty((n * 2,)), ctx.empty((n * 2,)), ctx.empty((n * 4,))
-
-        def step():
-            ctx.check(ctx.lib.eo_heat_eval(ctx.handle, 1.0, 1.0, d_T.ptr, d_s.ptr, None, None, d_q.ptr, d_dT.ptr,
-                                           d_ds.ptr, n))
+    hbm_peak, hbm_src = _measured_peaks()
+    peaks = {"hbm_gbs": hbm_peak, "hbm_source": hbm_src, "fp64_tflops": ctx.fp64_peak_tflops(),
+             "fp32_tflops": ctx.fp32_peak_tflops(),
+             "how": "FP64 / FP32: register-only DFMA / FFMA micro-benchmarks of this library (8 independent chains per thread, "
+                    "all SMs, best of 3) run at the start of this bench"}
 
     def collective():
         if dist is not None:
@@ -552,45 +740,26 @@ def run_gpu_arm(args):
 
             allreduce_stats_device(ctx)
 
+    wl = build_workload(model, ctx, eo, inputs, int(args.n), rank, args)
+    n = wl.n
+    extra_cfg = wl.cfg
+
     # ---- device-resident timing
-    for _ in range(W):
-        step()
-        collective()
-    ctx.sync()
-    ctx.stats_reset()
-    ev = [ctx.event() for _ in range(2 * K + 2)]
     sampler = ClockSampler(local_rank)
-    barrier()
-    ctx.sync()
-    sampler.start()
-    launches0 = ctx.launch_count
-    ctx.record(ev[0])
-    for k in range(K):
-        ctx.record(ev[2 + 2 * k])
-        step()
-        ctx.record(ev[3 + 2 * k])
-        collective()
-    ctx.record(ev[1])
-    ctx.sync()
-    barrier()
+    total_ms, kernel_ms, launches = time_steps(ctx, wl.step, K, W, barrier, max_over_ranks, collective, sampler)
     clocks = sampler.stop()
-    launches = ctx.launch_count - launches0
-    total_ms = max_over_ranks(ctx.elapsed_ms(ev[0], ev[1]))
-    kernel_ms = [ctx.elapsed_ms(ev[2 + 2 * k], ev[3 + 2 * k]) for k in range(K)]
     stats = ctx.stats()  # this rank's record over the K timed steps (the collective never modifies it)
     collective_check = None
     if dist is not None:
         # the K-th collective left the GLOBAL record of the K steps: it must equal the sum of the local records,
-        # gathered here a second, independent way (host tensors through the store-backed object collective)
-        import torch
-
+        # gathered here a second, independent way (Python objects through the object collective)
         gstats = ctx.stats_global()
         loc = [None] * world
         dist.all_gather_object(loc, {k: (v.tolist() if isinstance(v, np.ndarray) else v) for k, v in stats.items()})
         want_points = sum(l["n_points"] for l in loc)
         want_plastic = sum(l["n_plastic"] for l in loc)
         want_hist = np.sum([np.asarray(l["niter_hist"], dtype=np.int64) for l in loc], axis=0)
-        counted = model not in ("heat", "isihara", "tab", "action", "jitvm", "jitvm3d", "jitfused")
+        counted = model in ("vm", "mc", "fused", "step")
         ok = (gstats["n_points"] == want_points and gstats["n_plastic"] == want_plastic
               and np.array_equal(gstats["niter_hist"], want_hist)
               and _same(gstats["f_max"], _nanmax(l["f_max"] for l in loc))
@@ -613,10 +782,10 @@ def run_gpu_arm(args):
     if model == "isihara" and args.e2e_n > 0:
         ne = int(min(args.e2e_n, n))
         F_h = ctx.pinned_empty((ne, 1, 2, 2))
-        F_h.reshape(-1, 4)[:] = np.resize(F_t, (ne, 4))
-        call = isi((1,))
+        F_h.reshape(-1, 4)[:] = np.resize(wl.F_t, (ne, 4))
+        call = wl.isi((1,))
         Ke = max(2, min(K, 5))
-        for _ in range(2):
+        for _ in range(3):
             out = call(F_h)
         barrier()
         t0 = time.perf_counter()
@@ -626,6 +795,7 @@ def run_gpu_arm(args):
         dt = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": world * ne * Ke / dt, "unit": "QP/s", "h2d_bytes_per_step": 32 * ne, "d2h_bytes_per_step": 160 * ne,
                "qp_per_step_per_gpu": ne, "steps": Ke, "api": "Isihara((1,))(F) == external_function(derivatives)(*operands)"}
+        del call, out, F_h
     if model in ("vm", "mc") and args.e2e_n > 0:
         ne = int(args.e2e_n)
         deps_h = ctx.pinned_empty((ne, 1, 4))  # (n_cells, n_points, 4), the operand shape of demo_vm:344
@@ -638,7 +808,7 @@ def run_gpu_arm(args):
             api = "VonMises((1,))(deps) == external_function(derivatives)(*operands), history resident in HBM"
         else:
             m_e = eo.MohrCoulomb(n_qp=ne, ctx=ctx)
-            deps_t2, sn_t2 = deps_t, sn_t
+            deps_t2, sn_t2 = wl.deps_t, wl.sn_t
             m_e.set_history(np.resize(sn_t2, (ne, 4)))
             d2h = (160 + 28) * ne
             api = "MohrCoulomb((1,))(deps) == external_function(derivatives)(*operands), history resident in HBM"
@@ -647,7 +817,7 @@ def run_gpu_arm(args):
             flat[r:r + m] = deps_t2[:m]
         call = m_e((1,))
         Ke = max(2, min(K, 5))
-        for _ in range(2):
+        for _ in range(3):
             out = call(deps_h)
         barrier()
         t0 = time.perf_counter()
@@ -677,13 +847,13 @@ def run_gpu_arm(args):
                    d2h_gbs_alone=128 * ne / d2h_ms / 1e6, ms_per_step=1e3 * dt / Ke,
                    bound="PCIe device-to-host: the result is 168-188 B per point, the kernel needs < 10 % of the step")
         d_tmp.free()
-
-    e2e_dc = None
+        del m_e, call, out, deps_h, flat
     if model in ("step", "action"):
         # end to end through QuadratureForms with HOST vectors: only DOF vectors cross the link
+        tab, forms, vm = wl.mesh.tab, wl.mesh.forms, wl.vm
         nd = 2 * tab.n_dofs
         u_h, b_h = ctx.pinned_empty((nd,)), ctx.pinned_empty((nd,))
-        d_u.to_host(u_h)
+        wl.mesh.d_u.to_host(u_h)
         if model == "step":
             call = lambda: forms.vm_residual(vm, u_h, out=b_h, exact=args.fused_exact)  # noqa: E731
             api = "QuadratureForms.vm_residual(vm, u_host, out=b_host): eo_form_vm_step, history / tangent resident in HBM"
@@ -691,7 +861,7 @@ def run_gpu_arm(args):
             call = lambda: forms.action("mandel_strain", "mandel_strain", forms.C_tang, u_h, out=b_h)  # noqa: E731
             api = "QuadratureForms.action(..., C_tang_resident, x_host, out=y_host): eo_form_action"
         Ke = max(2, min(K, 5))
-        for _ in range(2):
+        for _ in range(3):
             call()
         barrier()
         t0 = time.perf_counter()
@@ -703,8 +873,21 @@ def run_gpu_arm(args):
         dt = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": world * n * Ke / dt, "unit": "QP/s", "h2d_bytes_per_step": 8 * nd, "d2h_bytes_per_step": 8 * nd,
                "qp_per_step_per_gpu": n, "steps": Ke, "api": api, "ms_per_step": 1e3 * dt / Ke}
-    elif model == "vm" and args.e2e_n > 0 and not args.no_device_consumers:
-        e2e_dc = e2e_device_consumers(ctx, eo, inputs, int(args.e2e_n), rank, world, max_over_ranks, barrier)
+        del call, tab, forms, vm
+
+    # the headline leg's buffers are no longer needed: free them before the other legs allocate theirs
+    wl_cfg_stats = _stats_cfg(model, stats)
+    del wl
+    gc.collect()
+
+    e2e_dc = None
+    if model == "vm" and args.e2e_n > 0 and not args.no_device_consumers:
+        e2e_dc = e2e_device_consumers(ctx, eo, inputs, int(args.e2e_n), rank, world, max_over_ranks, barrier, args.cpu_seconds)
+        gc.collect()
+
+    models = None
+    if model == "vm" and args.models:
+        models = models_block(ctx, eo, inputs, args, rank, world, peaks, barrier, max_over_ranks, collective)
 
     if rank != 0:
         if dist is not None:
@@ -713,84 +896,30 @@ def run_gpu_arm(args):
 
     # ---- roofline for the dominant kernel (the only kernel in a step)
     k_ms = float(np.mean(kernel_ms))
-    tj = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as fh:
-            tj = json.load(fh).get(model)
-    traffic = tj.get("dram_bytes_per_launch") if (tj and tj.get("n") == n) else None
-    hbm_peak, hbm_src = _measured_peaks()
-    hbm_achieved = BYTES_PER_QP[model] * n / (k_ms * 1e-3) / 1e9
-    if model == "mc":
-        # FP64-pipe bound: flops per QP counted by ncu (DFMA = 2, DADD/DMUL = 1) for this input family,
-        # peak = DFMA micro-benchmark measured now on this GPU
-        fp64_peak = ctx.fp64_peak_tflops()
-        flops_per_qp = tj.get("fp64_flops_per_qp") if tj else None
-        ach = flops_per_qp * n / (k_ms * 1e-3) / 1e12 if flops_per_qp else None
-        roofline = {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
-                    "frac": (ach / fp64_peak) if ach else None, "traffic": traffic,
-                    "peak_source": "measured now: eo_fp64_peak DFMA micro-benchmark (8 chains/thread)",
-                    "fp64_flops_per_qp": flops_per_qp, "kernel_ms": k_ms,
-                    "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
-                            "bytes_per_qp": BYTES_PER_QP[model]}}
-    elif model == "isihara":
-        # float32 CUDA-core bound: ~21 k FMA per point in five 64x64 matrix-vector products (isihara_core.cuh)
-        fma_per_qp = 5 * 64 * 64 + 64 * 16
-        ach = 2.0 * fma_per_qp * n / (k_ms * 1e-3) / 1e12
-        f32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
-        roofline = {"bound": "fp32", "achieved": ach, "peak": f32_peak, "unit": "TFLOP/s", "frac": ach / f32_peak,
-                    "traffic": traffic, "peak_source": "nominal: 148 SM x 128 FMA/clk x 2 x 1.965 GHz (no measured f32 figure)",
-                    "fma_per_qp": fma_per_qp, "kernel_ms": k_ms,
-                    "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
-                            "bytes_per_qp": BYTES_PER_QP[model]}}
-    else:
-        roofline = {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": hbm_achieved / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
-                    "bytes_per_qp": BYTES_PER_QP[model], "kernel_ms": k_ms}
-        if model in GATHERED_BYTES_PER_QP:
-            # the gather-limited kernels report the unique-byte fraction (above: what must cross HBM once)
-            # and the gathered-byte fraction (what the threads request: every cell's own copy of its dofs / vertices)
-            gb = GATHERED_BYTES_PER_QP[model]
-            ga = gb * n / (k_ms * 1e-3) / 1e9
-            roofline["gathered"] = {"bytes_per_qp": gb, "achieved": ga, "unit": "GB/s", "frac_of_hbm_peak": ga / hbm_peak,
-                                    "note": "requested bytes (per-cell copies of shared dofs / vertices served by L1/L2)"}
+    roofline = roofline_for(model, n, k_ms, peaks, _traffic(model, n))
 
     # ---- CPU baseline on this box's host cores (bounded sample)
     cpu = None
-    if world > 1:
-        cpu = None  # the CPU baseline is reported at N = 1 only (the reference arm is timed separately at every N)
-    elif model == "isihara":
-        cpu = None  # the CPU implementation is the reference's torch code, which needs /root/reference: timed in the
-        #             build container only (69 k QP/s on 8 threads)
-    elif args.cpu_seconds > 0 and model in ("tab", "fused", "jitfused", "step", "action"):
-        cpu = cpu_tab_rate({"jitfused": "fused"}.get(model, model), args.cpu_seconds)
-    elif args.cpu_seconds > 0:
-        sample = int(args.cpu_sample) if model != "mc" else min(int(args.cpu_sample), 200_000)
-        cm = "vm" if model in ("jitvm", "jitvm3d") else model
-        rate, cores, passes = cpu_port_rate(cm, sample, args.cpu_seconds, parallel=True)
-        rate1, _, _ = cpu_port_rate(cm, sample // 4, min(3.0, args.cpu_seconds), parallel=False)
-        what = {"vm": "C restatement of the reference's Numba kernel (serial in the reference)",
-                "jitvm": "C restatement of the reference's Numba kernel (serial in the reference)",
-                "jitvm3d": "C restatement of the reference's plane-strain Numba kernel (no 3-D CPU implementation exists)",
-                "heat": "C restatement of the reference's NumPy functions",
-                "mc": "C++ nested-dual-number restatement of the reference's JAX program (JAX not installable offline)"}
-        cpu = {"value": rate, "unit": "QP/s", "cores": cores, "kind": "port",
-               "sample": f"{sample} QPs x {passes} passes (best pass); {what[model]}, OpenMP; single-thread rate "
-                         f"{rate1:.3e} QP/s",
-               "single_thread_value": rate1}
+    if world == 1 and args.cpu_seconds > 0:  # reported at N = 1 only (the reference arm is timed separately at every N)
+        cpu = cpu_leg(model, args.cpu_seconds, args.cpu_sample if model != "isihara" else None)
+        if model in ("vm", "jitvm", "jitvm3d", "heat", "mc"):
+            cm = "vm" if model in ("jitvm", "jitvm3d") else model
+            n1 = int(args.cpu_sample) // 4 if model != "mc" else 20_000
+            rate1, _, _ = cpu_port_rate(cm, n1, min(3.0, args.cpu_seconds), parallel=False)
+            cpu["single_thread_value"] = rate1
+            cpu["sample"] += f"; single-thread rate {rate1:.3e} QP/s"
+        if model == "vm":
+            nb = cpu_numba_rate(1_000_000, min(3.0, args.cpu_seconds))
+            if nb is not None:
+                cpu["numba_serial"] = nb
 
-    hist = stats["niter_hist"]
     cfg = {
         "workload": WORKLOADS[model], "qp_per_gpu": n, "state_layout": args.state_layout,
-        "plastic_fraction": stats["n_plastic"] / max(stats["n_points"], 1),
         "l2": f"inputs+outputs {BYTES_PER_QP[model] * n / 1e9:.1f} GB per step >> 126 MB L2 (no flush needed)",
         "partition": "contiguous block of QPs per rank, no halo; one statistics collective per step when n_gpus > 1 "
                      "(plastic_fraction / niter histogram are then the global figures)",
     }
-    if model == "mc":
-        tot = max(int(hist.sum()), 1)
-        cfg["niter_histogram"] = {int(i): float(hist[i]) / tot for i in np.nonzero(hist)[0]}
-        cfg["n_nonconverged"] = stats["n_nonconverged"]
+    cfg.update(wl_cfg_stats)
     cfg.update(extra_cfg)
     if world > 1:
         cfg["cpu_binding"] = (f"rank pinned to the {len(numa_cores)} cores local to its GPU (NVML affinity)" if numa_cores
@@ -799,12 +928,14 @@ def run_gpu_arm(args):
         "metric": METRIC, "value": value, "unit": "QP/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": cfg, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-        "gpu_launches": int(launches), "clocks": clocks,
+        "gpu_launches": int(launches), "clocks": clocks, "peaks": peaks,
     }
     if e2e_dc is not None:
         line["e2e_device_consumers"] = e2e_dc
     if collective_check is not None:
         line["collective"] = collective_check
+    if models is not None:
+        line["models"] = models
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -824,13 +955,22 @@ def main():
                          "(torchrun's own parser rejects --n as an ambiguous abbreviation)")
     ap.add_argument("--e2e-n", type=float, default=1.5e7, help="quadrature points per GPU for the end-to-end leg")
     ap.add_argument("--state-layout", default="aos", choices=["aos", "soa"])
+    ap.add_argument("--mesh-order", default="structured", choices=["structured", "shuffled", "rcm"],
+                    help="numbering of cells / dofs / nodes of the synthetic mesh (tab, fused, step, action): the row-major "
+                         "structured numbering, a random permutation, or reverse Cuthill-McKee of a shuffled mesh")
     ap.add_argument("--cpu-sample", type=float, default=4e6)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--models", default="mc,heat,tab,fused,step,action,isihara",
+                    help="vm (default) line: comma-separated legs of the `models` block ('' = none)")
+    ap.add_argument("--models-steps", type=int, default=5)
+    ap.add_argument("--models-cpu-seconds", type=float, default=2.0)
+    ap.add_argument("--models-isihara-n", type=float, default=2e7)
     ap.add_argument("--no-device-consumers", action="store_true",
                     help="vm: skip the supplementary end-to-end leg through the device-side consumers (QuadratureForms)")
     ap.add_argument("--no-numa-bind", action="store_true", help="multi-GPU: do not pin ranks to their GPU's NUMA node")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    args.n = int(args.n)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world == 1 and args.gpus > 1 and args.impl == "b200":
         # convenience: re-launch under torchrun, one rank per GPU

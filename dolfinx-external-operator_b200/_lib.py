@@ -122,6 +122,7 @@ PROTOTYPES = {
     "eo_assign_gather": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp]),
     "eo_debug_counters": (C.c_int, [_vp, _vp]),
     "eo_fp64_peak": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double)]),
+    "eo_fp32_peak": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double)]),
     "eo_stats_reset": (C.c_int, [_vp]),
     "eo_stats_read": (C.c_int, [_vp, C.POINTER(Stats)]),
     "eo_stats_device_ptr": (_vp, [_vp]),

@@ -237,6 +237,12 @@ class Context:
         self.check(self._lib.eo_fp64_peak(self._h, int(iters), C.byref(t)))
         return float(t.value)
 
+    def fp32_peak_tflops(self, iters: int = 1 << 16) -> float:
+        """Measured FP32 FFMA throughput of this GPU (the roofline denominator of the Isihara network kernel)."""
+        t = C.c_double()
+        self.check(self._lib.eo_fp32_peak(self._h, int(iters), C.byref(t)))
+        return float(t.value)
+
     # -------------------------------------------------------------- statistics
     def stats_reset(self):
         self.check(self._lib.eo_stats_reset(self._h))

@@ -55,6 +55,16 @@ __global__ void __launch_bounds__(256) eo_fp64_peak_kernel(double* out, int iter
   out[blockIdx.x * size_t(blockDim.x) + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
+// FP32 roofline denominator (Isihara network): 8 independent FFMA chains per thread
+__global__ void __launch_bounds__(256) eo_fp32_peak_kernel(float* out, int iters, float b, float c) {
+  float a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fmaf(a0, b, c), a1 = fmaf(a1, b, c), a2 = fmaf(a2, b, c), a3 = fmaf(a3, b, c);
+    a4 = fmaf(a4, b, c), a5 = fmaf(a5, b, c), a6 = fmaf(a6, b, c), a7 = fmaf(a7, b, c);
+  }
+  out[blockIdx.x * size_t(blockDim.x) + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
 // out[k] = values[src[k]]: the non-contiguous coefficient assignment turned inside out (see eo_assign_gather)
 __global__ void __launch_bounds__(256) eo_gather_kernel(const double* __restrict__ values, const int64_t* __restrict__ src,
                                                         double* __restrict__ out, int64_t n_out) {
@@ -449,6 +459,32 @@ int eo_fp64_peak(eo_ctx* ctx, int iters, double* tflops) {
   for (int rep = 0; rep < 4; ++rep) {  // first repetition is the warm-up
     EO_CUDA(ctx, cudaEventRecord(e0, ctx->s_cmp));
     eo_fp64_peak_kernel<<<grid, block, 0, ctx->s_cmp>>>(out, iters, 0.999999, 1e-6);
+    EO_CUDA(ctx, cudaEventRecord(e1, ctx->s_cmp));
+    EO_CUDA(ctx, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    EO_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops = 2.0 * 8.0 * double(iters) * double(grid) * block / (double(best) * 1e-3) / 1e12;
+  return EO_OK;
+}
+
+int eo_fp32_peak(eo_ctx* ctx, int iters, double* tflops) {
+  EO_REQUIRE(ctx, ctx && tflops && iters > 0, "eo_fp32_peak: bad argument");
+  EO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int grid = ctx->sm_count * 8, block = 256;
+  float* out = nullptr;
+  EO_CUDA(ctx, cudaMalloc(&out, size_t(grid) * block * sizeof(float)));
+  cudaEvent_t e0, e1;
+  EO_CUDA(ctx, cudaEventCreate(&e0));
+  EO_CUDA(ctx, cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {  // first repetition is the warm-up
+    EO_CUDA(ctx, cudaEventRecord(e0, ctx->s_cmp));
+    eo_fp32_peak_kernel<<<grid, block, 0, ctx->s_cmp>>>(out, iters, 0.999999f, 1e-6f);
     EO_CUDA(ctx, cudaEventRecord(e1, ctx->s_cmp));
     EO_CUDA(ctx, cudaEventSynchronize(e1));
     float ms = 0.f;

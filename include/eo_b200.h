@@ -119,6 +119,8 @@ int eo_debug_counters(eo_ctx* ctx, uint32_t* out);
  * (8 independent chains per thread, `iters` trips, all SMs) and returns the best of 3 timed launches
  * in TFLOP/s (2 flops per DFMA). */
 int eo_fp64_peak(eo_ctx* ctx, int iters, double* tflops);
+/* The same for FP32 FFMA: roofline denominator of the Isihara network kernel (float32 CUDA cores). */
+int eo_fp32_peak(eo_ctx* ctx, int iters, double* tflops);
 
 /* ---------------------------------------------------------------- statistics
  * Device-resident record that every constitutive kernel accumulates into in its
