@@ -456,7 +456,7 @@ def build_workload(model, ctx, eo, inputs, n, rank, args, mesh=None):
         d_it = ctx.empty((w.n,), np.int32)
         d_yl, d_nr, d_dl = ctx.empty((w.n,)), ctx.empty((w.n,)), ctx.empty((w.n,))
         prm = McParams(mc.E, mc.nu, mc.c, mc.phi, mc.psi, mc.theta_T, mc.a, mc.tol, mc.Nitermax)
-        scheme = {"queue": 0, "simple": 1, "queue-noaffinity": 2, "queue-onepass": 3}[args.mc_scheme]
+        scheme = {"classes": 0, "simple": 1, "queue-noaffinity": 2, "queue-onepass": 3, "ring": 4}[args.mc_scheme]
         w.cfg["mc_scheme"] = args.mc_scheme
         w.deps_t, w.sn_t = deps_t, sn_t
         w.keep += [mc, d_deps, d_sn, d_Ct, d_sig, d_it, d_yl, d_nr, d_dl]
@@ -949,7 +949,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="vm", choices=["vm", "heat", "mc", "tab", "fused", "isihara", "jitvm", "jitfused", "jitvm3d", "step", "action"])
     ap.add_argument("--fused-exact", action="store_true")
-    ap.add_argument("--mc-scheme", default="queue", choices=["queue", "simple", "queue-noaffinity", "queue-onepass"])
+    ap.add_argument("--mc-scheme", default="classes", choices=["classes", "simple", "queue-noaffinity", "queue-onepass", "ring"])
     ap.add_argument("--n", "--qp-per-gpu", dest="n", type=float, default=1e8,
                     help="quadrature points per GPU (device-resident leg); under torchrun spell it --qp-per-gpu "
                          "(torchrun's own parser rejects --n as an ambiguous abbreviation)")

@@ -31,6 +31,12 @@
 #define MC_TILE 4096     // points per work item of the global counter
 #define MC_SIMPLE_THREADS 128
 #define MC_CTR_LIST 32   // word of the context's counter block that holds the length of the plastic-point list
+#ifndef MCN_WARPS
+#define MCN_WARPS 12     // warps per persistent CTA of the lane-class Newton kernel
+#endif
+#ifndef MCN_DEPTH
+#define MCN_DEPTH 16     // slots per lane class (32 classes): 512 slots per CTA
+#endif
 
 struct mc_ptrs {
   const double* deps;
@@ -481,6 +487,223 @@ __global__ void __launch_bounds__(256, 4) mc_trial_kernel(const mc_consts k, con
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Two-pass scheme, pass 2 (default): persistent CTAs work off the plastic-point list with LANE-CLASS slots.
+//
+// A point's Newton state lives in a shared-memory slot for its whole life, like in mc_kernel, but slot (b, l) =
+// b * 32 + l belongs to lane class l: only lane l of whichever warp ever touches it.  Field f of slot (b, l) sits at
+// s_slots[f * NSLOT + b * 32 + l], so the 32 lanes of a warp always access 32 consecutive doubles - no shared-memory
+// bank conflicts by construction (the ring scheduler hands arbitrary slots to lanes: 58 % of its shared-memory
+// wavefronts are conflict replays, profiles/r2_mc_ncu_summary.md).  Scheduling state is two words per class:
+// s_free[l] / s_ready[l], bit b = slot (b, l) is unused / waits for its next Newton update.  A lane allocates and
+// hands on slots with one atomicAnd / atomicOr on its own class word (32 consecutive words per warp instruction); there
+// are no queues, no ring positions and no leader-lane lock.
+//
+// Stages (one inlined copy of mc_stage serves both):
+//   F  first visit of up to 32 listed points: load, first residual, first update, residual, loop test  (kinds 0 + 1)
+//   U  one further Newton update with the full tangent recursion + residual + loop test                (kind 2)
+// A warp takes U when at least MCN_FULL classes have a waiting point, else F when that many classes have a free slot
+// and list entries remain, else whichever fills more lanes.  Points that left the loop are written out from the slot.
+#define MCN_FULL 28
+
+template <bool ASSOC, int NWARPS, int DEPTH>
+__global__ void __launch_bounds__(NWARPS * 32, 1) mc_newton_kernel(const mc_consts k, const mc_ptrs P, eo_stats* __restrict__ stats,
+                                                                   unsigned int* ctr, const int32_t* __restrict__ list,
+                                                                   const double* __restrict__ list_yl) {
+  constexpr int NSLOT = 32 * DEPTH;
+  constexpr unsigned ALL = DEPTH == 32 ? 0xffffffffu : ((1u << DEPTH) - 1u);
+  const int64_t n = (int64_t)ctr[MC_CTR_LIST];
+  extern __shared__ double s_slots[];  // [ASSOC ? MC_NF_ASSOC : MC_NF][NSLOT]
+  __shared__ unsigned int s_free[32], s_ready[32];
+  __shared__ int s_pt[NSLOT];
+  __shared__ int s_it[NSLOT];
+  __shared__ unsigned long long s_work;  // (tile index << 16) | next list entry within the tile
+  __shared__ int s_inflight, s_done, s_fetching;
+  __shared__ unsigned int s_hist[EO_NITER_BINS];
+  __shared__ unsigned int s_nonconv, s_nonfinite, s_plastic;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t ntiles = (n + MC_TILE - 1) / MC_TILE;
+  for (int b = tid; b < EO_NITER_BINS; b += NWARPS * 32) s_hist[b] = 0;
+  if (tid < 32) s_free[tid] = ALL, s_ready[tid] = 0;
+  if (tid == 0) {
+    s_nonconv = s_nonfinite = s_plastic = 0;
+    s_inflight = 0, s_done = 0, s_fetching = 0;
+    s_work = 0xFFFFull;  // "exhausted": the first warp to look fetches a tile
+  }
+  __syncthreads();
+  double max_res = 0.0;
+  int max_it = 0;
+  auto tile_points = [&](long long tile) -> long long {
+    return tile < ntiles ? (n - tile * MC_TILE < MC_TILE ? n - tile * MC_TILE : MC_TILE) : 0;
+  };
+
+  for (;;) {
+    // ------------------------------------------------------------------ what could this warp do?
+    const unsigned rdy = *(volatile unsigned int*)&s_ready[lane], fre = *(volatile unsigned int*)&s_free[lane];
+    const int nU = __popc(__ballot_sync(0xffffffffu, rdy != 0)), nF = __popc(__ballot_sync(0xffffffffu, fre != 0));
+    int stage = MC_STAGE_WAIT;
+    if (lane == 0) {
+      unsigned long long w = *(volatile unsigned long long*)&s_work;
+      bool inputs = (long long)(w & 0xFFFFull) < tile_points((long long)(w >> 16));
+      if (!inputs && !*(volatile int*)&s_done && nF > 0 && atomicCAS(&s_fetching, 0, 1) == 0) {
+        w = *(volatile unsigned long long*)&s_work;  // one warp at a time fetches the next tile; re-check under the flag
+        if (!((long long)(w & 0xFFFFull) < tile_points((long long)(w >> 16)))) {
+          const unsigned int t = atomicAdd(ctr, 1u);
+          if ((int64_t)t >= ntiles) {
+            *(volatile int*)&s_done = 1;
+          } else {
+            atomicExch(&s_work, (unsigned long long)t << 16);
+            inputs = true;
+          }
+        } else {
+          inputs = true;
+        }
+        __threadfence_block();
+        atomicExch(&s_fetching, 0);
+      }
+      const int f = inputs ? nF : 0;
+      if (nU >= MCN_FULL) stage = MC_Q_U;
+      else if (f >= MCN_FULL) stage = MC_STAGE_T;
+      else if (nU > 0 && nU >= f) stage = MC_Q_U;
+      else if (f > 0) stage = MC_STAGE_T;
+      else if (*(volatile int*)&s_done && *(volatile int*)&s_inflight == 0) {
+        const unsigned long long w3 = *(volatile unsigned long long*)&s_work;
+        if (!((long long)(w3 & 0xFFFFull) < tile_points((long long)(w3 >> 16)))) stage = MC_STAGE_EXIT;
+      }
+    }
+    stage = __shfl_sync(0xffffffffu, stage, 0);
+    if (stage == MC_STAGE_EXIT) break;
+    if (stage == MC_STAGE_WAIT) {
+      __nanosleep(200);
+      continue;
+    }
+
+    // ------------------------------------------------------------------ take a slot of this lane's class
+    int slot = -1;
+    {
+      volatile unsigned int* word = stage == MC_Q_U ? &s_ready[lane] : &s_free[lane];
+      for (;;) {
+        const unsigned m = *word;
+        if (m == 0) break;
+        const unsigned bit = m & (0u - m);
+        if (atomicAnd(const_cast<unsigned int*>(word), ~bit) & bit) {
+          slot = (__ffs(bit) - 1) * 32 + lane;
+          break;
+        }
+      }
+    }
+    int kind0 = 2, kind1 = 2;
+    if (stage == MC_STAGE_T) {
+      // ---------------------------------------------------------------- stage F: claim list entries for the lanes that
+      //                                                                  hold a slot, load the points, open the slots
+      kind0 = 0, kind1 = 1;
+      const unsigned sm = __ballot_sync(0xffffffffu, slot >= 0);
+      const int want = __popc(sm);
+      long long e0 = 0;
+      int got = 0;
+      if (lane == 0 && want > 0) {
+        atomicAdd(&s_inflight, want);  // before the claim: "done and inflight == 0" then means finished
+        const unsigned long long w2 = atomicAdd(&s_work, (unsigned long long)want);
+        const long long tile2 = (long long)(w2 >> 16), off = (long long)(w2 & 0xFFFFull), pts = tile_points(tile2);
+        if (off < pts) {
+          e0 = tile2 * MC_TILE + off;
+          got = (int)(pts - off < want ? pts - off : want);
+        }
+        if (got < want) atomicAdd(&s_inflight, got - want);
+      }
+      e0 = __shfl_sync(0xffffffffu, e0, 0);
+      got = __shfl_sync(0xffffffffu, got, 0);
+      const int rank = __popc(sm & ((1u << lane) - 1u));
+      if (slot >= 0 && rank >= got) {  // no list entry for this slot: hand it back
+        atomicOr(&s_free[lane], 1u << (slot >> 5));
+        slot = -1;
+      }
+      if (slot >= 0) {
+        const int64_t e = e0 + rank;
+        const double yl = list_yl[e];
+        const int i = list[e];
+        const eo_d4 de4 = eo_ld256(P.deps + 4 * (int64_t)i);
+        const eo_d4 sg = eo_ld256(P.sigma_n + 4 * (int64_t)i);
+        const double de[4] = {de4.x, de4.y, de4.z, de4.w}, sn[4] = {sg.x, sg.y, sg.z, sg.w};
+        double Cde[4];
+        mc_Cmul(k, de, Cde);
+        const mc_slot sl{s_slots + slot, NSLOT};
+        mc_slot_init(sl, sn, Cde, yl);
+        s_pt[slot] = i;
+        s_it[slot] = 0;
+      }
+    }
+
+    // ------------------------------------------------------------------ Newton stage(s) on the slot
+    bool fin = false, nonconv = false, nonfin = false;
+    int bin = 0;
+    if (slot >= 0) {
+      const mc_slot sl{s_slots + slot, NSLOT};
+      int32_t it = s_it[slot];
+      bool out = false;
+#pragma unroll 1
+      for (int kind = kind0;; ++kind) {
+        out = mc_stage<ASSOC>(k, kind, sl, it);
+        if (out || kind >= kind1) break;
+      }
+      if (out) {
+        const int64_t i = s_pt[slot];
+        double Ct[16], sig[4], nr, dl;
+        mc_slot_result(sl, it, Ct, sig, nr, dl);
+        mc_store_point(P, i, Ct, sig);
+        mc_store_aux(P, i, it, sl[MC_F_YIELD], nr, dl);
+        max_res = fmax(max_res, nr);
+        max_it = max(max_it, it);
+        fin = true;
+        bin = min(it, EO_NITER_BINS - 1);
+        nonconv = it >= k.nitermax;
+        nonfin = !(isfinite(sig[0]) && isfinite(sig[1]) && isfinite(sig[2]) && isfinite(sig[3]));
+        atomicOr(&s_free[lane], 1u << (slot >> 5));  // the slot's contents are dead: no ordering needed
+      } else {
+        s_it[slot] = it;
+        __threadfence_block();  // the slot is complete before another warp's lane of this class can see the bit
+        atomicOr(&s_ready[lane], 1u << (slot >> 5));
+      }
+    }
+    // statistics of the points that left the loop: warp-aggregated
+    const unsigned fm = __ballot_sync(0xffffffffu, fin);
+    if (fm) {
+      const unsigned ncm = __ballot_sync(0xffffffffu, nonconv), nfm = __ballot_sync(0xffffffffu, nonfin);
+      if (fin) {
+        const unsigned grp = __match_any_sync(fm, bin);
+        if (lane == __ffs(grp) - 1) atomicAdd(&s_hist[bin], (unsigned)__popc(grp));
+      }
+      if (lane == 0) {
+        atomicAdd(&s_plastic, (unsigned)__popc(fm));
+        atomicAdd(&s_inflight, -__popc(fm));
+        if (ncm) atomicAdd(&s_nonconv, (unsigned)__popc(ncm));
+        if (nfm) atomicAdd(&s_nonfinite, (unsigned)__popc(nfm));
+      }
+    }
+    __syncwarp();
+  }
+
+  // ------------------------------------------------------------------ statistics flush
+  __syncthreads();
+  for (int b = tid; b < EO_NITER_BINS; b += NWARPS * 32)
+    if (s_hist[b]) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->niter_hist[b]), (unsigned long long)s_hist[b]);
+  if (tid == 0) {
+    if (s_plastic) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_plastic), (unsigned long long)s_plastic);
+    if (s_nonconv) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_nonconverged), (unsigned long long)s_nonconv);
+    if (s_nonfinite) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_nonfinite), (unsigned long long)s_nonfinite);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    max_res = fmax(max_res, __shfl_xor_sync(0xffffffffu, max_res, o));
+    max_it = max(max_it, __shfl_xor_sync(0xffffffffu, max_it, o));
+  }
+  if (lane == 0) {
+    mc_atomic_max_f64(&stats->res_max, max_res);
+    mc_atomic_max_f64(&stats->niter_max, (double)max_it);
+  }
+}
+
 // simple variant: one thread per point, whole Newton loop per thread (divergent).  Kept as the
 // baseline the queue scheme is measured against (bench.py --mc-scheme simple) and as a cross-check.
 template <bool ASSOC>
@@ -526,6 +749,30 @@ static int mc_launch_queue(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, in
   return EO_OK;
 }
 
+// default scheme: pass 1 (mc_trial_kernel) + the lane-class Newton kernel over the plastic list
+template <bool ASSOC>
+static int mc_launch_classes(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, int64_t n) {
+  constexpr int NWARPS = MCN_WARPS, DEPTH = MCN_DEPTH;
+  const size_t smem = size_t(ASSOC ? MC_NF_ASSOC : MC_NF) * (32 * DEPTH) * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(mc_newton_kernel<ASSOC, NWARPS, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return eo_fail(ctx, EO_ERR_CUDA, "eo_mc_eval: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  if (n > 2147483647LL) return eo_fail(ctx, EO_ERR_INVALID, "eo_mc_eval: n too large for one launch");
+  void* sc = nullptr;
+  const size_t yl_off = (size_t(n) * 4 + 255) / 256 * 256;
+  int rc = eo_scratch(ctx, yl_off + size_t(n) * 8, &sc);
+  if (rc != EO_OK) return rc;
+  int32_t* list = reinterpret_cast<int32_t*>(sc);
+  double* list_yl = reinterpret_cast<double*>(reinterpret_cast<char*>(sc) + yl_off);
+  mc_trial_kernel<ASSOC><<<unsigned((n + 255) / 256), 256, 0, ctx->s_cmp>>>(k, P, n, ctx->stats, ctx->work_ctr, list, list_yl);
+  mc_newton_kernel<ASSOC, NWARPS, DEPTH><<<(unsigned)ctx->sm_count, NWARPS * 32, smem, ctx->s_cmp>>>(k, P, ctx->stats, ctx->work_ctr, list, list_yl);
+  ctx->launches += 2;
+  return EO_OK;
+}
+
 static int mc_launch(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, int64_t n, int scheme) {
   if (scheme == 1) {
     const int64_t grid64 = (n + MC_SIMPLE_THREADS - 1) / MC_SIMPLE_THREADS;
@@ -543,12 +790,13 @@ static int mc_launch(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, int64_t 
   const int64_t grid = ntiles < ctx->sm_count ? ntiles : ctx->sm_count;
   cudaError_t e = cudaMemsetAsync(ctx->work_ctr, 0, 256, ctx->s_cmp);
   if (e != cudaSuccess) return eo_fail(ctx, EO_ERR_CUDA, "eo_mc_eval: cudaMemsetAsync: %s", cudaGetErrorString(e));
+  if (scheme == 0) return k.assoc ? mc_launch_classes<true>(ctx, k, P, n) : mc_launch_classes<false>(ctx, k, P, n);
   int rc;
   if (scheme == 2)  // one pass, no stage affinity: any warp takes the highest-priority full queue (A/B measurements)
     rc = k.assoc ? mc_launch_queue<true, 0, false>(ctx, k, P, n, smem, (unsigned)grid) : mc_launch_queue<false, 0, false>(ctx, k, P, n, smem, (unsigned)grid);
   else if (scheme == 3)  // one pass with stage affinity: the yield test is the scheduler's T stage (A/B measurements)
     rc = k.assoc ? mc_launch_queue<true, 1, false>(ctx, k, P, n, smem, (unsigned)grid) : mc_launch_queue<false, 1, false>(ctx, k, P, n, smem, (unsigned)grid);
-  else  // default: two passes - yield test at full occupancy, then the stage scheduler over the plastic list
+  else  // scheme 4: two passes with the ring scheduler of round 1 (A/B measurements)
     rc = k.assoc ? mc_launch_queue<true, 1, true>(ctx, k, P, n, smem, (unsigned)grid) : mc_launch_queue<false, 1, true>(ctx, k, P, n, smem, (unsigned)grid);
   if (rc != EO_OK) return rc;
   ctx->launches += 1;
@@ -561,7 +809,7 @@ int eo_mc_eval(eo_ctx* ctx, const eo_mc_params* prm, const double* deps, const d
                double* sigma, int32_t* niter, double* yielding, double* norm_res, double* dlambda, int64_t n) {
   static const int def_scheme = [] {  // EO_MC_SCHEME overrides the default execution scheme (A/B runs of the test-suite)
     const char* e = getenv("EO_MC_SCHEME");
-    return (e && *e >= '0' && *e <= '3') ? *e - '0' : 0;
+    return (e && *e >= '0' && *e <= '4') ? *e - '0' : 0;
   }();
   return eo_mc_eval_scheme(ctx, prm, deps, sigma_n, C_tang, sigma, niter, yielding, norm_res, dlambda, n, def_scheme);
 }
@@ -572,7 +820,7 @@ int eo_mc_eval_scheme(eo_ctx* ctx, const eo_mc_params* prm, const double* deps, 
   EO_REQUIRE(ctx, ctx != nullptr, "eo_mc_eval: ctx is NULL");
   EO_REQUIRE(ctx, prm != nullptr, "eo_mc_eval: prm is NULL");
   EO_REQUIRE(ctx, n >= 0, "eo_mc_eval: n < 0");
-  EO_REQUIRE(ctx, scheme >= 0 && scheme <= 3, "eo_mc_eval: unknown scheme");
+  EO_REQUIRE(ctx, scheme >= 0 && scheme <= 4, "eo_mc_eval: unknown scheme");
   EO_REQUIRE(ctx, prm->Nitermax >= 0 && prm->Nitermax <= 200,
              "eo_mc_eval: Nitermax must be in [0, 200] (histogram bins of eo_stats)");
   if (n == 0) return EO_OK;

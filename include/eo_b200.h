@@ -356,11 +356,13 @@ typedef struct eo_mc_params {
 int eo_mc_eval(eo_ctx* ctx, const eo_mc_params* prm, const double* deps, const double* sigma_n, double* C_tang,
                double* sigma, int32_t* niter, double* yielding, double* norm_res, double* dlambda, int64_t n);
 /* Same with an explicit execution scheme: 0 = two passes (the default of eo_mc_eval): yield test for every point
- * at full occupancy, elastic points finished there, plastic points listed; then persistent CTAs with
- * shared-memory stage queues (stage kinds pinned to SM sub-partitions) run the Newton iterations of the listed
- * points.  1 = one thread per point (divergent baseline; does not update the statistics record); 2 / 3 = one
- * pass (the yield test is a stage of the scheduler) without / with the sub-partition affinity - kept for A/B
- * measurements.  All schemes give the same results. */
+ * at full occupancy, elastic points finished there, plastic points listed; then persistent CTAs run the Newton
+ * iterations of the listed points out of shared-memory state slots that are partitioned by lane ("lane classes":
+ * conflict-free slot accesses, one bit mask per class instead of queues), a warp always executing one kind of stage.
+ * 1 = one thread per point (divergent baseline; does not update the statistics record); 2 / 3 = one pass with the
+ * ring-queue scheduler of round 1 (the yield test is a stage of the scheduler) without / with sub-partition affinity;
+ * 4 = two passes with that ring-queue scheduler - all kept for A/B measurements.  All schemes give the same results
+ * (2, 3, 4 bit for bit; 0 and 1 to rounding: the same per-point source inlined into different kernels). */
 int eo_mc_eval_scheme(eo_ctx* ctx, const eo_mc_params* prm, const double* deps, const double* sigma_n,
                       double* C_tang, double* sigma, int32_t* niter, double* yielding, double* norm_res,
                       double* dlambda, int64_t n, int scheme);

@@ -48,7 +48,7 @@ def _stepper(prm=PRM):
     return lambda d, s: native.mc_stress(d, s, prm, parallel=True)[0]
 
 
-@pytest.mark.parametrize("scheme", [0, 1, 2, 3])
+@pytest.mark.parametrize("scheme", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("name", ["mc_path_10x9.npz", "mc_rand_seed0_n96.npz"])
 def test_mc_against_reference_golden(ctx, golden_dir, name, scheme):
     g = np.load(os.path.join(golden_dir, name))
@@ -73,20 +73,26 @@ def test_mc_schemes_agree(ctx):
     a, b = _abi(ctx, d, s, scheme=0), _abi(ctx, d, s, scheme=1)
     assert np.array_equal(a["niter"], b["niter"]) and np.array_equal(a["yielding"] > 0, b["yielding"] > 0)
     _check(a, b, d, s)
-    # two-pass (0), one-pass without (2) / with (3) sub-partition affinity: the same stage code, only scheduled
-    # differently -> bit-identical stresses, tangents and aux outputs; the statistics records agree too
+    # ring scheduler in two passes (4), in one pass without (2) / with (3) sub-partition affinity: the same kernel
+    # template, only scheduled differently -> bit-identical stresses, tangents and aux outputs; the lane-class kernel
+    # (0, default) inlines the same stage code in another kernel: equal to rounding; the statistics records agree
     st = {}
-    for scheme in (0, 2, 3):
+    ring = _abi(ctx, d, s, scheme=4)
+    _check(a, ring, d, s)
+    assert np.array_equal(a["niter"], ring["niter"])
+    for scheme in (0, 2, 3, 4):
         ctx.stats_reset()
         o = _abi(ctx, d, s, scheme=scheme)
         ctx.sync()
         st[scheme] = ctx.stats()
+        ref = a if scheme == 0 else ring
         for key in ("C_tang", "sigma", "niter", "dlambda", "norm_res"):
-            assert np.array_equal(o[key], a[key], equal_nan=True), (scheme, key)
+            assert np.array_equal(o[key], ref[key], equal_nan=True), (scheme, key)
         np.testing.assert_allclose(o["yielding"], a["yielding"], rtol=1e-13, atol=1e-13)
-    for scheme in (2, 3):
-        for key in ("n_points", "n_plastic", "n_nonconverged", "n_nonfinite", "niter_max", "f_max", "res_max"):
+    for scheme in (2, 3, 4):
+        for key in ("n_points", "n_plastic", "n_nonconverged", "n_nonfinite", "niter_max", "f_max"):
             assert st[scheme][key] == st[0][key], (scheme, key)
+        assert abs(st[scheme]["res_max"] - st[0]["res_max"]) <= 1e-10 * max(st[0]["res_max"], 1e-300)
         assert np.array_equal(st[scheme]["niter_hist"], st[0]["niter_hist"])
 
 
