@@ -31,11 +31,8 @@
 #define MC_TILE 4096     // points per work item of the global counter
 #define MC_SIMPLE_THREADS 128
 #define MC_CTR_LIST 32   // word of the context's counter block that holds the length of the plastic-point list
-#ifndef MCN_WARPS
-#define MCN_WARPS 12     // warps per persistent CTA of the lane-class Newton kernel
-#endif
-#ifndef MCN_DEPTH
-#define MCN_DEPTH 16     // slots per lane class (32 classes): 512 slots per CTA
+#ifndef MCN_DEFAULT_CONFIG
+#define MCN_DEFAULT_CONFIG 0  // CTA shape of the lane-class Newton kernel, see mc_launch_classes
 #endif
 
 struct mc_ptrs {
@@ -750,9 +747,8 @@ static int mc_launch_queue(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, in
 }
 
 // default scheme: pass 1 (mc_trial_kernel) + the lane-class Newton kernel over the plastic list
-template <bool ASSOC>
-static int mc_launch_classes(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, int64_t n) {
-  constexpr int NWARPS = MCN_WARPS, DEPTH = MCN_DEPTH;
+template <bool ASSOC, int NWARPS, int DEPTH>
+static int mc_launch_newton(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, const int32_t* list, const double* list_yl) {
   const size_t smem = size_t(ASSOC ? MC_NF_ASSOC : MC_NF) * (32 * DEPTH) * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
@@ -760,6 +756,18 @@ static int mc_launch_classes(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, 
     if (e != cudaSuccess) return eo_fail(ctx, EO_ERR_CUDA, "eo_mc_eval: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
+  mc_newton_kernel<ASSOC, NWARPS, DEPTH><<<(unsigned)ctx->sm_count, NWARPS * 32, smem, ctx->s_cmp>>>(k, P, ctx->stats, ctx->work_ctr, list, list_yl);
+  return EO_OK;
+}
+
+template <bool ASSOC>
+static int mc_launch_classes(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, int64_t n) {
+  // EO_MC_CONFIG selects the CTA shape of pass 2 for A/B runs: 0 = 12 warps x 512 slots, 1 = 16 warps (128 registers) x
+  // 512 slots, 2 = 16 warps x 576 slots (associative flow rule only: 51 fields per slot do not fit otherwise)
+  static const int cfg = [] {
+    const char* e = getenv("EO_MC_CONFIG");
+    return (e && *e >= '0' && *e <= '2') ? *e - '0' : MCN_DEFAULT_CONFIG;
+  }();
   if (n > 2147483647LL) return eo_fail(ctx, EO_ERR_INVALID, "eo_mc_eval: n too large for one launch");
   void* sc = nullptr;
   const size_t yl_off = (size_t(n) * 4 + 255) / 256 * 256;
@@ -768,7 +776,10 @@ static int mc_launch_classes(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, 
   int32_t* list = reinterpret_cast<int32_t*>(sc);
   double* list_yl = reinterpret_cast<double*>(reinterpret_cast<char*>(sc) + yl_off);
   mc_trial_kernel<ASSOC><<<unsigned((n + 255) / 256), 256, 0, ctx->s_cmp>>>(k, P, n, ctx->stats, ctx->work_ctr, list, list_yl);
-  mc_newton_kernel<ASSOC, NWARPS, DEPTH><<<(unsigned)ctx->sm_count, NWARPS * 32, smem, ctx->s_cmp>>>(k, P, ctx->stats, ctx->work_ctr, list, list_yl);
+  if (cfg == 2 && ASSOC) rc = mc_launch_newton<ASSOC, 16, ASSOC ? 18 : 16>(ctx, k, P, list, list_yl);
+  else if (cfg >= 1) rc = mc_launch_newton<ASSOC, 16, 16>(ctx, k, P, list, list_yl);
+  else rc = mc_launch_newton<ASSOC, 12, 16>(ctx, k, P, list, list_yl);
+  if (rc != EO_OK) return rc;
   ctx->launches += 2;
   return EO_OK;
 }

@@ -50,6 +50,7 @@ struct mc_consts {
   double lam, mu2, l2m;  // lmbda, 2 mu, lmbda + 2 mu                        (:405-415)
   double s_d, s_tr;      // S_elas = C_elas^{-1}: S v = s_d v - s_tr tr(v) [1,1,1,0]  (:416)
   double theta_T;        //                                                  (:115)
+  double x_T;            // sin(3 theta_T): |theta| > theta_T  <=>  |sin 3 theta| > x_T   (:334, theta_T < 30 deg)
   double tol;            //                                                  (:469)
   int32_t nitermax;      //                                                  (:469)
   int32_t assoc;         // phi == psi: f and g coincide, evaluate once
@@ -90,6 +91,7 @@ inline void mc_make_consts(const mc_params_in& p, mc_consts& k) {
   k.s_d = 1.0 / (2 * mu);
   k.s_tr = lmbda / (2 * mu * (3 * lmbda + 2 * mu));
   k.theta_T = p.theta_T;
+  k.x_T = std::sin(3.0 * p.theta_T);
   k.tol = p.tol;
   k.nitermax = p.nitermax;
   k.assoc = (p.phi == p.psi) ? 1 : 0;
@@ -107,6 +109,27 @@ EO_HD void mc_sincos(double x, double& s, double& c) {
   s = std::sin(x);
   c = std::cos(x);
 #endif
+}
+
+EO_HD double mc_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(x);
+#else
+  return 1.0 / std::sqrt(x);
+#endif
+}
+
+// sin(theta) for theta = asin(x) / 3 (:294) WITHOUT asin / sin in double precision: sin(theta) is the root of
+// 4 s^3 - 3 s + x = 0 (sin 3 theta = 3 s - 4 s^3) in [-1/2, 1/2].  Single-precision start (FP32 pipe), one Newton step and
+// one chord step with the same reciprocal: error 1e-7 -> 1e-13 -> below rounding; |h'| = 3 cos(3 theta) / cos(theta) >=
+// 0.69 on the unrounded range |theta| <= theta_T = 26 deg.  Agrees with sin(asin(x) / 3) to 1 ulp over that range
+// (tests/test_hostcheck_cpu.py).  NaN propagates.
+EO_HD double mc_sin_third_asin(double x) {
+  const float t0 = asinf((float)x) * (1.0f / 3.0f);
+  const double s0 = (double)sinf(t0);
+  const double r = 1.0 / (12.0 * s0 * s0 - 3.0);
+  const double s1 = s0 - ((4.0 * s0 * s0 - 3.0) * s0 + x) * r;
+  return s1 - ((4.0 * s1 * s1 - 3.0) * s1 + x) * r;
 }
 
 // C_elas @ v                                                                    (:407-415)
@@ -189,13 +212,14 @@ EO_HD void mc_surface(const mc_consts& k, const mc_angle& ac, const double sig[4
     const double m[4] = {s2 * s1, s2 * s0, s0 * s1 - 0.5 * s3 * s3, -s2 * s3};
     mc_dev(m, o.t);
   }
-  // arg = -(3 sqrt3 J3) / (2 sqrt(J2^3)), clipped to [-1, 1]                     (:292-293)
+  // arg = -(3 sqrt3 J3) / (2 sqrt(J2^3)), clipped to [-1, 1]                     (:292-293); one reciprocal square
+  // root serves 1 / J2 and J2^(-3/2)
   const double c33 = 5.196152422706632;  // 3 sqrt(3)
-  const double rP = sqrt(J2 * J2 * J2);
-  const double hh = -c33 / (2.0 * rP);
+  const double rJ = mc_rsqrt(J2);
+  const double iJ2 = rJ * rJ;
+  const double hh = -0.5 * c33 * (iJ2 * rJ);
   mc_jet a;
-  a.v = -(c33 * J3) / (2.0 * rP);
-  const double iJ2 = 1.0 / J2;
+  a.v = hh * J3;
   a.x = -1.5 * a.v * iJ2;
   a.y = hh;
   a.xx = 3.75 * a.v * iJ2 * iJ2;
@@ -209,18 +233,20 @@ EO_HD void mc_surface(const mc_consts& k, const mc_angle& ac, const double sig[4
     a.v = a.v < 0.0 ? -1.0 : 1.0;
     a.x = a.y = a.xx = a.xy = a.xxx = a.xxy = 0.0;
   }
-  const double th = (1.0 / 3.0) * asin(a.v);  // :294
+  // theta = asin(arg) / 3 (:294) enters only through sin / cos of theta (unrounded) or of 3 theta (rounded), and
+  // sin 3 theta = arg: neither asin nor sincos is evaluated in double precision
+  const double w2 = 1.0 - a.v * a.v;  // cos^2(3 theta)
   // K(theta) and its derivatives wrt theta                                      (:334-345)
   double K0, K1 = 0, K2 = 0, K3 = 0;
   {
-    const bool rounded = fabs(th) > k.theta_T;
-    double S, Cs;
-    mc_sincos(rounded ? 3.0 * th : th, S, Cs);  // one sincos serves both branches
+    const bool rounded = fabs(a.v) > k.x_T;  // |theta| > theta_T
     if (rounded) {
-      const int sgi = th < 0.0 ? 1 : 0;  // sign(0) = +1 (:298-299)
+      const double S = a.v;
+      const int sgi = a.v < 0.0 ? 1 : 0;  // sign(0) = +1 (:298-299)
       const double Ac = ac.Ar[sgi], Bc = ac.Br[sgi], Cc = ac.Cr[sgi];
       K0 = Ac + Bc * S + Cc * S * S;  // :338-343
       if (ORD >= 1) {
+        const double Cs = sqrt(w2);
         const double S1 = 3.0 * Cs, S2 = -9.0 * S, S3 = -27.0 * Cs;
         const double b2 = Bc + 2.0 * Cc * S;
         K1 = b2 * S1;
@@ -228,6 +254,8 @@ EO_HD void mc_surface(const mc_consts& k, const mc_angle& ac, const double sig[4
         K3 = 6.0 * Cc * S1 * S2 + b2 * S3;
       }
     } else {
+      const double S = mc_sin_third_asin(a.v);
+      const double Cs = sqrt(1.0 - S * S);
       K0 = Cs - ac.kappa * S;  // :335-336
       K1 = -S - ac.kappa * Cs;
       K2 = -K0;
@@ -240,8 +268,7 @@ EO_HD void mc_surface(const mc_consts& k, const mc_angle& ac, const double sig[4
   o.h = (o.I1 / 3.0 * ac.sa) + G0 - ac.ccos;  // :368-374
   if (ORD >= 1) {
     // theta as a function of arg, then K as a function of arg
-    const double w2 = 1.0 - a.v * a.v;
-    const double iw = 1.0 / sqrt(w2);
+    const double iw = mc_rsqrt(w2);
     const double t1 = (1.0 / 3.0) * iw;
     double k1 = K1 * t1, k2 = 0, k3 = 0;
     if (ORD >= 2) {
@@ -555,17 +582,17 @@ EO_HD bool mc_stage(const mc_consts& k, int kind, const mc_slot& sl, int32_t& ni
       M[MC_SYM(0, 1)] -= k.s_tr, M[MC_SYM(0, 2)] -= k.s_tr, M[MC_SYM(1, 2)] -= k.s_tr;
       mc_ldl_factor(M, lf);
     }
-    double z[4], q[4];
+    double z[4], q_[4];  // z = M^{-1} n, q_ = M^{-1} df
 #pragma unroll
     for (int i = 0; i < 4; ++i) z[i] = n[i];
     mc_ldl_solve(lf, z);
     if (ASSOC) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) q[i] = z[i];
+      for (int i = 0; i < 4; ++i) q_[i] = z[i];
     } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) q[i] = df[i];
-      mc_ldl_solve(lf, q);
+      for (int i = 0; i < 4; ++i) q_[i] = df[i];
+      mc_ldl_solve(lf, q_);
     }
     const double idenom = 1.0 / mc_dot4(df, z);
     // Newton step  J delta = -r                                                   (:511-512)
@@ -574,16 +601,21 @@ EO_HD bool mc_stage(const mc_consts& k, int kind, const mc_slot& sl, int32_t& ni
       const double rs[4] = {-sl[MC_F_R + 0], -sl[MC_F_R + 1], -sl[MC_F_R + 2], -sl[MC_F_R + 3]};
       double w[4];
       mc_Smul(k, rs, w);
-      d[4] = (mc_dot4(q, w) + sl[MC_F_R + 4]) * idenom;
+      d[4] = (mc_dot4(q_, w) + sl[MC_F_R + 4]) * idenom;
       mc_ldl_solve(lf, w);
 #pragma unroll
       for (int i = 0; i < 4; ++i) d[i] = w[i] - z[i] * d[4];
     }
 
     // tangent recursion  Y[:,j] <- J^{-1} ( [C e_j; 0] - (DJ[Y[:,j]]) delta ), column by column:
-    // in the symmetric form the right-hand side is  w = e_j - v_j,  rho = -(Hf Y_sig[:,j]) . delta_sig
-    const double Gxxx = sl[MC_F_G + 5], Gxxy = sl[MC_F_G + 6], Gxyy = sl[MC_F_G + 7], Gyyy = sl[MC_F_G + 8];
-    double Hd[4], db[4], Nb[4], Hfd[4];
+    // in the symmetric form the right-hand side is  w = e_j - (al Hd + Nm a),  rho = -(Hf a) . delta_sig  with
+    // a = Y_sig[:,j], al = Y_lam[j] and the SYMMETRIC matrix  Nm = dl D(Hess g)[delta_sig] + delta_lam Hess g:
+    // the third derivative of g contracted with delta_sig is assembled ONCE per update (10 entries) instead of being
+    // contracted with every column.  With b = delta_sig, db = dev b, Nb = N(s) b, J2b = s.b, J3b = t.b:
+    //   D(Hess g)[b] = alb dev + beb N(s) + Gy N(db) + (s p^T + p s^T) + (t q^T + q t^T)
+    //   p = c1/2 s + Gxx db + c2 t + Gxy Nb,   q = Gxy db + c3/2 t + Gyy Nb,
+    //   c1 = Gxxx J2b + Gxxy J3b,  c2 = Gxxy J2b + Gxyy J3b,  c3 = Gxyy J2b + Gyyy J3b
+    double Hd[4], Hfd[4], Nm[10];
     mc_symmul(H, d, Hd);
     if (ASSOC) {
 #pragma unroll
@@ -591,47 +623,57 @@ EO_HD bool mc_stage(const mc_consts& k, int kind, const mc_slot& sl, int32_t& ni
     } else {
       mc_symmul(Hf, d, Hfd);
     }
-    mc_dev(d, db);
-    {
-      double Mb[4];
-      mc_Mmul(s, db, Mb);
-      mc_dev(Mb, Nb);
+    if (kind == 2) {  // Y0 = 0: the first update has no DJ term
+      const double Gxxx = sl[MC_F_G + 5], Gxxy = sl[MC_F_G + 6], Gxyy = sl[MC_F_G + 7], Gyyy = sl[MC_F_G + 8];
+      double db[4], Nb[4], p[4], q[4];
+      mc_dev(d, db);
+      {
+        double Mb[4];
+        mc_Mmul(s, db, Mb);
+        mc_dev(Mb, Nb);
+      }
+      const double J2b = mc_dot4(s, d), J3b = mc_dot4(t, d);
+      const double alb = Gxx * J2b + Gxy * J3b, beb = Gxy * J2b + Gyy * J3b;
+      const double c1 = 0.5 * (Gxxx * J2b + Gxxy * J3b), c2 = Gxxy * J2b + Gxyy * J3b, c3 = 0.5 * (Gxyy * J2b + Gyyy * J3b);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        p[i] = c1 * s[i] + Gxx * db[i] + c2 * t[i] + Gxy * Nb[i];
+        q[i] = Gxy * db[i] + c3 * t[i] + Gyy * Nb[i];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double e[4] = {0, 0, 0, 0}, de[4], Ms[4], Ns[4], Md[4], Nd[4];
+        e[j] = 1.0;
+        mc_dev(e, de);
+        mc_Mmul(s, de, Ms);
+        mc_dev(Ms, Ns);
+        mc_Mmul(db, de, Md);
+        mc_dev(Md, Nd);
+#pragma unroll
+        for (int i = 0; i <= j; ++i) {
+          const double DH = alb * de[i] + beb * Ns[i] + Gy * Nd[i] + (s[i] * p[j] + p[i] * s[j]) + (t[i] * q[j] + q[i] * t[j]);
+          Nm[MC_SYM(i, j)] = dl * DH + d[4] * H[MC_SYM(i, j)];
+        }
+      }
     }
-    const double J2b = mc_dot4(s, d), J3b = mc_dot4(t, d);
-    const double alb = Gxx * J2b + Gxy * J3b, beb = Gxy * J2b + Gyy * J3b;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
     for (int j = 0; j < 4; ++j) {
       double w[4] = {0.0, 0.0, 0.0, 0.0};
       double rho = 0.0;
-      if (kind == 2) {  // Y0 = 0: the first update has no DJ term
-        double a[4];
+      if (kind == 2) {
+        double a[4], Na[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) a[i] = sl[MC_F_YY + 4 * i + j];
         const double al = sl[MC_F_YY + 16 + j];
-        // third derivative of g contracted with a and delta_sigma (see mc_third_mul)
-        double da[4], Ma[4], Na[4], Mab[4], Nab[4], Ha[4];
-        mc_dev(a, da);
-        mc_Mmul(s, da, Ma);
-        mc_dev(Ma, Na);
-        mc_Mmul(da, db, Mab);
-        mc_dev(Mab, Nab);
-        mc_symmul(H, a, Ha);
-        const double J2a = mc_dot4(s, a), J3a = mc_dot4(t, a);
-        const double J2ab = mc_dot4(a, db), J3ab = mc_dot4(a, Nb);
-        const double cs = Gxxx * J2a * J2b + Gxxy * (J2a * J3b + J3a * J2b) + Gxyy * J3a * J3b + Gxx * J2ab + Gxy * J3ab;
-        const double ct = Gxxy * J2a * J2b + Gxyy * (J2a * J3b + J3a * J2b) + Gyyy * J3a * J3b + Gxy * J2ab + Gyy * J3ab;
-        const double ala = Gxx * J2a + Gxy * J3a, bea = Gxy * J2a + Gyy * J3a;
+        mc_symmul(Nm, a, Na);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const double Ta = cs * s[i] + ala * db[i] + alb * da[i] + ct * t[i] + bea * Nb[i] + beb * Na[i] + Gy * Nab[i];
-          w[i] = -(al * Hd[i] + dl * Ta + d[4] * Ha[i]);
-        }
+        for (int i = 0; i < 4; ++i) w[i] = -(al * Hd[i] + Na[i]);
         rho = -mc_dot4(a, Hfd);
       }
       w[0] += (j == 0 ? 1.0 : 0.0), w[1] += (j == 1 ? 1.0 : 0.0), w[2] += (j == 2 ? 1.0 : 0.0), w[3] += (j == 3 ? 1.0 : 0.0);
-      const double yl = (mc_dot4(q, w) - rho) * idenom;
+      const double yl = (mc_dot4(q_, w) - rho) * idenom;
       mc_ldl_solve(lf, w);
 #pragma unroll
       for (int i = 0; i < 4; ++i) sl[MC_F_YY + 4 * i + j] = w[i] - z[i] * yl;
