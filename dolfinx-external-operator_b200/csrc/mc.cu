@@ -31,6 +31,9 @@
 #define MC_TILE 4096     // points per work item of the global counter
 #define MC_SIMPLE_THREADS 128
 #define MC_CTR_LIST 32   // word of the context's counter block that holds the length of the plastic-point list
+#define MCN_FULL_DEFAULT 28
+#define MCN_MIN_ACTIVE_DEFAULT 99  // 99: never wait (a warp starts with whatever lanes it can fill)
+#define MCN_FIRST_LAST_DEFAULT 2
 #ifndef MCN_DEFAULT_CONFIG
 #define MCN_DEFAULT_CONFIG 0  // CTA shape of the lane-class Newton kernel, see mc_launch_classes
 #endif
@@ -497,16 +500,23 @@ __global__ void __launch_bounds__(256, 4) mc_trial_kernel(const mc_consts k, con
 // are no queues, no ring positions and no leader-lane lock.
 //
 // Stages (one inlined copy of mc_stage serves both):
-//   F  first visit of up to 32 listed points: load, first residual, first update, residual, loop test  (kinds 0 + 1)
+//   F  first visit of up to 32 listed points: load, first residual, first update, residual, loop test (kinds 0 + 1) and -
+//      by default - one full update more (kind 2): 63 % of the plastic points of the demo's stress paths converge with
+//      their second update and so never leave the warp that loaded them
 //   U  one further Newton update with the full tangent recursion + residual + loop test                (kind 2)
 // A warp takes U when at least MCN_FULL classes have a waiting point, else F when that many classes have a free slot
 // and list entries remain, else whichever fills more lanes.  Points that left the loop are written out from the slot.
-#define MCN_FULL 28
+struct mcn_policy {
+  int full;         // lanes a stage must fill to start at once
+  int min_active;   // ... unless fewer than this many warps of the CTA are inside a stage
+  int first_last;   // last stage kind of a point's FIRST visit: 0 = first residual only, 1 = + first update, 2 = + second update
+  unsigned sleep_ns;
+};
 
 template <bool ASSOC, int NWARPS, int DEPTH>
 __global__ void __launch_bounds__(NWARPS * 32, 1) mc_newton_kernel(const mc_consts k, const mc_ptrs P, eo_stats* __restrict__ stats,
                                                                    unsigned int* ctr, const int32_t* __restrict__ list,
-                                                                   const double* __restrict__ list_yl) {
+                                                                   const double* __restrict__ list_yl, const mcn_policy pol) {
   constexpr int NSLOT = 32 * DEPTH;
   constexpr unsigned ALL = DEPTH == 32 ? 0xffffffffu : ((1u << DEPTH) - 1u);
   const int64_t n = (int64_t)ctr[MC_CTR_LIST];
@@ -515,7 +525,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) mc_newton_kernel(const mc_cons
   __shared__ int s_pt[NSLOT];
   __shared__ int s_it[NSLOT];
   __shared__ unsigned long long s_work;  // (tile index << 16) | next list entry within the tile
-  __shared__ int s_inflight, s_done, s_fetching;
+  __shared__ int s_inflight, s_done, s_fetching, s_active;  // s_active: warps inside a stage
   __shared__ unsigned int s_hist[EO_NITER_BINS];
   __shared__ unsigned int s_nonconv, s_nonfinite, s_plastic;
 
@@ -525,7 +535,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) mc_newton_kernel(const mc_cons
   if (tid < 32) s_free[tid] = ALL, s_ready[tid] = 0;
   if (tid == 0) {
     s_nonconv = s_nonfinite = s_plastic = 0;
-    s_inflight = 0, s_done = 0, s_fetching = 0;
+    s_inflight = 0, s_done = 0, s_fetching = 0, s_active = 0;
     s_work = 0xFFFFull;  // "exhausted": the first warp to look fetches a tile
   }
   __syncthreads();
@@ -560,8 +570,12 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) mc_newton_kernel(const mc_cons
         atomicExch(&s_fetching, 0);
       }
       const int f = inputs ? nF : 0;
-      if (nU >= MCN_FULL) stage = MC_Q_U;
-      else if (f >= MCN_FULL) stage = MC_STAGE_T;
+      // a partly filled warp occupies the FP64 pipe like a full one: while enough other warps are inside a stage (they
+      // will hand on / free slots within microseconds) it is cheaper to look again than to start with idle lanes
+      const bool patient = *(volatile int*)&s_active >= pol.min_active;
+      if (nU >= pol.full) stage = MC_Q_U;
+      else if (f >= pol.full) stage = MC_STAGE_T;
+      else if (patient && (nU | f)) stage = MC_STAGE_WAIT;
       else if (nU > 0 && nU >= f) stage = MC_Q_U;
       else if (f > 0) stage = MC_STAGE_T;
       else if (*(volatile int*)&s_done && *(volatile int*)&s_inflight == 0) {
@@ -572,9 +586,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) mc_newton_kernel(const mc_cons
     stage = __shfl_sync(0xffffffffu, stage, 0);
     if (stage == MC_STAGE_EXIT) break;
     if (stage == MC_STAGE_WAIT) {
-      __nanosleep(200);
+      __nanosleep(pol.sleep_ns);
       continue;
     }
+    if (lane == 0) atomicAdd(&s_active, 1);
 
     // ------------------------------------------------------------------ take a slot of this lane's class
     int slot = -1;
@@ -594,7 +609,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) mc_newton_kernel(const mc_cons
     if (stage == MC_STAGE_T) {
       // ---------------------------------------------------------------- stage F: claim list entries for the lanes that
       //                                                                  hold a slot, load the points, open the slots
-      kind0 = 0, kind1 = 1;
+      kind0 = 0, kind1 = pol.first_last;
       const unsigned sm = __ballot_sync(0xffffffffu, slot >= 0);
       const int want = __popc(sm);
       long long e0 = 0;
@@ -638,6 +653,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) mc_newton_kernel(const mc_cons
     if (slot >= 0) {
       const mc_slot sl{s_slots + slot, NSLOT};
       int32_t it = s_it[slot];
+      if (stage == MC_Q_U && it == 0) kind0 = kind1 = 1;  // first_last == 0: the first update runs in its own visit
       bool out = false;
 #pragma unroll 1
       for (int kind = kind0;; ++kind) {
@@ -678,6 +694,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) mc_newton_kernel(const mc_cons
         if (nfm) atomicAdd(&s_nonfinite, (unsigned)__popc(nfm));
       }
     }
+    if (lane == 0) atomicAdd(&s_active, -1);
     __syncwarp();
   }
 
@@ -756,7 +773,12 @@ static int mc_launch_newton(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, c
     if (e != cudaSuccess) return eo_fail(ctx, EO_ERR_CUDA, "eo_mc_eval: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  mc_newton_kernel<ASSOC, NWARPS, DEPTH><<<(unsigned)ctx->sm_count, NWARPS * 32, smem, ctx->s_cmp>>>(k, P, ctx->stats, ctx->work_ctr, list, list_yl);
+  static const mcn_policy pol = [] {  // EO_MC_POLICY="full,min_active,first_last,sleep_ns" overrides (A/B runs)
+    mcn_policy p{MCN_FULL_DEFAULT, MCN_MIN_ACTIVE_DEFAULT, MCN_FIRST_LAST_DEFAULT, 200u};
+    if (const char* e = getenv("EO_MC_POLICY")) sscanf(e, "%d,%d,%d,%u", &p.full, &p.min_active, &p.first_last, &p.sleep_ns);
+    return p;
+  }();
+  mc_newton_kernel<ASSOC, NWARPS, DEPTH><<<(unsigned)ctx->sm_count, NWARPS * 32, smem, ctx->s_cmp>>>(k, P, ctx->stats, ctx->work_ctr, list, list_yl, pol);
   return EO_OK;
 }
 
