@@ -49,15 +49,29 @@ struct mc_ptrs {
   double* dlambda;
 };
 
+// max(*addr, v) for doubles of either sign with NON-RETURNING atomics (RED): non-negative doubles order like signed
+// integers (and beat every negative one), negative doubles order inversely to their unsigned bit patterns (and lose
+// against every non-negative one).  The issuing thread does not wait for the L2 round trip.
 __device__ __forceinline__ void mc_atomic_max_f64(double* addr, double v) {
   if (!(v == v)) return;  // NaN never becomes a maximum
-  unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
-  unsigned long long old = *a;
-  while (__longlong_as_double((long long)old) < v) {
-    const unsigned long long prev = atomicCAS(a, old, (unsigned long long)__double_as_longlong(v));
-    if (prev == old) break;
-    old = prev;
-  }
+  if (v >= 0.0)
+    atomicMax(reinterpret_cast<long long*>(addr), __double_as_longlong(v + 0.0));  // + 0.0: -0.0 -> +0.0
+  else
+    atomicMin(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+// warp-wide maximum of doubles (NaN lanes are ignored; -inf when every lane holds NaN) with two REDUX instructions on
+// an order-preserving 64-bit key instead of a ten-shuffle butterfly
+__device__ __forceinline__ double mc_warp_max_f64(double v) {
+  unsigned long long key = (unsigned long long)__double_as_longlong(v);
+  key = (key >> 63) ? ~key : (key | 0x8000000000000000ull);
+  if (!(v == v)) key = 0x000fffffffffffffull;  // key of -inf
+  const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+  const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+  unsigned long long m = ((unsigned long long)mh << 32) | ml;
+  m = (m >> 63) ? (m & 0x7fffffffffffffffull) : ~m;
+  return __longlong_as_double((long long)m);
 }
 
 __device__ __forceinline__ void mc_store_aux(const mc_ptrs& P, int64_t i, int32_t niter, double yielding,
@@ -442,48 +456,52 @@ __global__ void __launch_bounds__(256, 4) mc_trial_kernel(const mc_consts k, con
       plastic = true;  // NaN predicate -> plastic branch, like `yielding <= 0.0` being false
     }
   }
-  // ---- CTA-aggregated epilogue: ONE list reservation and one set of statistics atomics per CTA (a per-warp
-  //      atomicAdd on the single list counter would serialise 6 x 10^5 same-address atomics per 2 x 10^7 points)
+  // ---- CTA-aggregated epilogue: ONE list reservation per CTA (a per-warp atomicAdd on the single list counter would
+  //      serialise 6 x 10^5 same-address atomics per 2 x 10^7 points).  Only that one returning atomic sits between the
+  //      two barriers; the statistics go out afterwards as non-returning reductions.
   __shared__ unsigned int s_wbase[8];
   __shared__ double s_mf[8], s_mr[8];
   __shared__ int s_mi[8];
   const int warp = threadIdx.x >> 5;
   const unsigned pm = __ballot_sync(0xffffffffu, plastic);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    max_f = fmax(max_f, __shfl_xor_sync(0xffffffffu, max_f, o));
-    max_res = fmax(max_res, __shfl_xor_sync(0xffffffffu, max_res, o));
-    max_it = max(max_it, __shfl_xor_sync(0xffffffffu, max_it, o));
-  }
+  max_f = mc_warp_max_f64(max_f);
+  if (__any_sync(0xffffffffu, max_res != 0.0)) max_res = mc_warp_max_f64(max_res);  // exactly 0 for elastic points
+  max_it = __reduce_max_sync(0xffffffffu, max_it);
   if (lane == 0) s_wbase[warp] = __popc(pm), s_mf[warp] = max_f, s_mr[warp] = max_res, s_mi[warp] = max_it;
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned int total = 0;
-    double mf = -INFINITY, mr = 0.0;
-    int mi = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
       const unsigned int c = s_wbase[w];
       s_wbase[w] = total;
       total += c;
-      mf = fmax(mf, s_mf[w]), mr = fmax(mr, s_mr[w]), mi = max(mi, s_mi[w]);
     }
     const unsigned int base = total ? atomicAdd(ctr + MC_CTR_LIST, total) : 0u;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s_wbase[w] += base;
-    mc_atomic_max_f64(&stats->f_max, mf);
-    mc_atomic_max_f64(&stats->res_max, mr);
-    mc_atomic_max_f64(&stats->niter_max, (double)mi);
-    if (s_hist0) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->niter_hist[0]), (unsigned long long)s_hist0);
-    if (s_hist1) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->niter_hist[1]), (unsigned long long)s_hist1);
-    if (s_nonfinite) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_nonfinite), (unsigned long long)s_nonfinite);
-    if (blockIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_points), (unsigned long long)n);
   }
   __syncthreads();
   if (plastic) {
     const unsigned int pos = s_wbase[warp] + __popc(pm & ((1u << lane) - 1u));
     list[pos] = (int32_t)i;
     list_yl[pos] = yl;
+  }
+  if (threadIdx.x == 32) {  // a thread of another warp than the one that reserved the list space
+    // the maxima saturate after a few CTAs: look first (three independent loads), reduce only what raises a maximum
+    const double cf = *(volatile double*)&stats->f_max, cr = *(volatile double*)&stats->res_max,
+                 ci = *(volatile double*)&stats->niter_max;
+    double mf = -INFINITY, mr = 0.0;
+    int mi = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) mf = fmax(mf, s_mf[w]), mr = fmax(mr, s_mr[w]), mi = max(mi, s_mi[w]);
+    if (!(mf <= cf)) mc_atomic_max_f64(&stats->f_max, mf);
+    if (!(mr <= cr)) mc_atomic_max_f64(&stats->res_max, mr);
+    if (!((double)mi <= ci)) mc_atomic_max_f64(&stats->niter_max, (double)mi);
+    if (s_hist0) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->niter_hist[0]), (unsigned long long)s_hist0);
+    if (s_hist1) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->niter_hist[1]), (unsigned long long)s_hist1);
+    if (s_nonfinite) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_nonfinite), (unsigned long long)s_nonfinite);
+    if (blockIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_points), (unsigned long long)n);
   }
 }
 
