@@ -15,6 +15,21 @@
 #include <cmath>
 #include <cstdint>
 
+// The arithmetic type of the restatement.  Default double = the reference's float64 program.  The library is built a
+// second time with -DORACLE_REAL="long double" -DORACLE_SUFFIX=_ld (x87 extended precision, eps = 1.1e-19): the same
+// program evaluated ~2000x more accurately, used as the "exact" value when the rounding sensitivity of the reference
+// itself is audited near the corners of the Mohr-Coulomb hexagon (tests/test_mc_precision_cpu.py).
+#ifndef ORACLE_REAL
+#define ORACLE_REAL double
+#endif
+#ifndef ORACLE_SUFFIX
+#define ORACLE_SUFFIX
+#endif
+#define ORACLE_CAT2(a, b) a##b
+#define ORACLE_CAT(a, b) ORACLE_CAT2(a, b)
+#define ORACLE_NAME(base) ORACLE_CAT(base, ORACLE_SUFFIX)
+typedef ORACLE_REAL real;
+
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -31,7 +46,7 @@ struct Dual {
   Dual() : v(0.0) {
     for (int i = 0; i < N; ++i) d[i] = T(0.0);
   }
-  Dual(double c) : v(c) {  // NOLINT: implicit lift of a constant
+  Dual(real c) : v(c) {  // NOLINT: implicit lift of a constant
     for (int i = 0; i < N; ++i) d[i] = T(0.0);
   }
   explicit Dual(const T& val, int) : v(val) {
@@ -39,9 +54,9 @@ struct Dual {
   }
 };
 
-inline double primal(double x) { return x; }
+inline real primal(real x) { return x; }
 template <class T, int N>
-inline double primal(const Dual<T, N>& x) {
+inline real primal(const Dual<T, N>& x) {
   return primal(x.v);
 }
 
@@ -52,12 +67,12 @@ inline double primal(const Dual<T, N>& x) {
     BODY_DD return r;                                                           \
   }                                                                             \
   template <class T, int N>                                                     \
-  inline Dual<T, N> operator OP(const Dual<T, N>& a, double b) {                \
+  inline Dual<T, N> operator OP(const Dual<T, N>& a, real b) {                \
     Dual<T, N> r;                                                               \
     BODY_DS return r;                                                           \
   }                                                                             \
   template <class T, int N>                                                     \
-  inline Dual<T, N> operator OP(double a, const Dual<T, N>& b) {                \
+  inline Dual<T, N> operator OP(real a, const Dual<T, N>& b) {                \
     Dual<T, N> r;                                                               \
     BODY_SD return r;                                                           \
   }
@@ -84,12 +99,12 @@ inline Dual<T, N> operator-(const Dual<T, N>& a) {
   return r;
 }
 
-inline double ad_sqrt(double x) { return std::sqrt(x); }
-inline double ad_sin(double x) { return std::sin(x); }
-inline double ad_cos(double x) { return std::cos(x); }
-inline double ad_asin(double x) { return std::asin(x); }
-inline double ad_abs(double x) { return std::fabs(x); }
-inline double ad_clip(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+inline real ad_sqrt(real x) { return std::sqrt(x); }
+inline real ad_sin(real x) { return std::sin(x); }
+inline real ad_cos(real x) { return std::cos(x); }
+inline real ad_asin(real x) { return std::asin(x); }
+inline real ad_abs(real x) { return std::fabs(x); }
+inline real ad_clip(real x, real lo, real hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
 template <class T, int N>
 inline Dual<T, N> ad_sqrt(const Dual<T, N>& a) {
@@ -124,8 +139,8 @@ inline Dual<T, N> ad_asin(const Dual<T, N>& a) {
 }
 // clip(x, lo, hi): tangent passes inside the interval, is zero outside (jnp.clip, :293)
 template <class T, int N>
-inline Dual<T, N> ad_clip(const Dual<T, N>& a, double lo, double hi) {
-  const double p = primal(a);
+inline Dual<T, N> ad_clip(const Dual<T, N>& a, real lo, real hi) {
+  const real p = primal(a);
   if (p < lo) return Dual<T, N>(lo);
   if (p > hi) return Dual<T, N>(hi);
   return a;
@@ -134,21 +149,28 @@ inline Dual<T, N> ad_clip(const Dual<T, N>& a, double lo, double hi) {
 // ------------------------------------------------------------------------------------------
 // model
 // ------------------------------------------------------------------------------------------
-struct McParams {
+struct McParamsIO {  // as passed through the C interface
   double E, nu, c, phi, psi, theta_T, a;  // :110-116
   double tol;                             // :469
   int32_t Nitermax;                       // :469
 };
+struct McParams {
+  real E, nu, c, phi, psi, theta_T, a, tol;
+  int32_t Nitermax;
+  McParams() {}
+  McParams(const McParamsIO& q)  // NOLINT: the double parameter values are taken as exact
+      : E(q.E), nu(q.nu), c(q.c), phi(q.phi), psi(q.psi), theta_T(q.theta_T), a(q.a), tol(q.tol), Nitermax(q.Nitermax) {}
+};
 
 struct Consts {
-  double C[4][4];  // C_elas :407-415
-  double dev[4][4];
+  real C[4][4];  // C_elas :407-415
+  real dev[4][4];
   McParams p;
 };
 
 inline void make_consts(const McParams& p, Consts& k) {
-  const double lmbda = p.E * p.nu / ((1.0 + p.nu) * (1.0 - 2.0 * p.nu));  // :405
-  const double mu = p.E / (2.0 * (1.0 + p.nu));                           // :406
+  const real lmbda = p.E * p.nu / ((1.0 + p.nu) * (1.0 - 2.0 * p.nu));  // :405
+  const real mu = p.E / (2.0 * (1.0 + p.nu));                           // :406
   for (int i = 0; i < 4; ++i)
     for (int j = 0; j < 4; ++j) {
       k.C[i][j] = 0.0;
@@ -157,7 +179,7 @@ inline void make_consts(const McParams& p, Consts& k) {
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) {
       k.C[i][j] = (i == j) ? lmbda + 2 * mu : lmbda;
-      k.dev[i][j] = (i == j) ? 2.0 / 3.0 : -1.0 / 3.0;  // :352-360
+      k.dev[i][j] = (i == j) ? real(2.0) / real(3.0) : real(-1.0) / real(3.0);  // :352-360
     }
   k.C[3][3] = 2 * mu;
   k.dev[3][3] = 1.0;
@@ -166,18 +188,18 @@ inline void make_consts(const McParams& p, Consts& k) {
 
 // K(theta, angle) with the Abbo-Sloan rounding, :298-345.  sign(0) = +1 (:298-299).
 template <class T>
-inline T K_fun(const T& th, double angle, const McParams& p) {
-  const double tT = p.theta_T;
-  const double sa = std::sin(angle);
-  const double isq3 = 1.0 / std::sqrt(3.0);
+inline T K_fun(const T& th, real angle, const McParams& p) {
+  const real tT = p.theta_T;
+  const real sa = std::sin(angle);
+  const real isq3 = 1.0 / std::sqrt(real(3.0));
   if (std::fabs(primal(th)) > tT) {  // K_true :338-343
-    const double sg = primal(th) < 0.0 ? -1.0 : 1.0;
-    const double c1 = std::cos(tT) - isq3 * sa * std::sin(tT);                     // :302-303
-    const double c2 = sg * std::sin(tT) + isq3 * sa * std::cos(tT);                // :306-307
-    const double c3 = 18.0 * std::cos(3.0 * tT) * std::cos(3.0 * tT) * std::cos(3.0 * tT);  // :310
-    const double Cc = (-std::cos(3.0 * tT) * c1 - 3.0 * sg * std::sin(3.0 * tT) * c2) / c3;  // :313-316
-    const double Bc = (sg * std::sin(6.0 * tT) * c1 - 6.0 * std::cos(6.0 * tT) * c2) / c3;   // :319-322
-    const double Ac = -isq3 * sa * sg * std::sin(tT) - Bc * sg * std::sin(3 * tT) -
+    const real sg = primal(th) < 0.0 ? -1.0 : 1.0;
+    const real c1 = std::cos(tT) - isq3 * sa * std::sin(tT);                     // :302-303
+    const real c2 = sg * std::sin(tT) + isq3 * sa * std::cos(tT);                // :306-307
+    const real c3 = 18.0 * std::cos(3.0 * tT) * std::cos(3.0 * tT) * std::cos(3.0 * tT);  // :310
+    const real Cc = (-std::cos(3.0 * tT) * c1 - 3.0 * sg * std::sin(3.0 * tT) * c2) / c3;  // :313-316
+    const real Bc = (sg * std::sin(6.0 * tT) * c1 - 6.0 * std::cos(6.0 * tT) * c2) / c3;   // :319-322
+    const real Ac = -isq3 * sa * sg * std::sin(tT) - Bc * sg * std::sin(3 * tT) -
                       Cc * std::sin(3.0 * tT) * std::sin(3.0 * tT) + std::cos(tT);          // :325-331
     const T s3 = ad_sin(3.0 * th);
     return Ac + Bc * s3 + Cc * s3 * s3;
@@ -187,7 +209,7 @@ inline T K_fun(const T& th, double angle, const McParams& p) {
 
 // surface(sigma, angle), :364-374
 template <class T>
-inline T surface(const T sig[4], double angle, const Consts& k) {
+inline T surface(const T sig[4], real angle, const Consts& k) {
   const McParams& p = k.p;
   T s[4];
   for (int i = 0; i < 4; ++i) {
@@ -198,12 +220,12 @@ inline T surface(const T sig[4], double angle, const Consts& k) {
   const T I1 = sig[0] + sig[1] + sig[2];                                   // tr @ sigma :361,366
   const T J2 = 0.5 * (s[0] * s[0] + s[1] * s[1] + s[2] * s[2] + s[3] * s[3]);  // :286-287
   const T J3 = s[2] * (s[0] * s[1] - s[3] * s[3] / 2.0);                   // :282-283
-  T arg = -(3.0 * std::sqrt(3.0) * J3) / (2.0 * ad_sqrt(J2 * J2 * J2));    // :292
+  T arg = -(3.0 * std::sqrt(real(3.0)) * J3) / (2.0 * ad_sqrt(J2 * J2 * J2));    // :292
   arg = ad_clip(arg, -1.0, 1.0);                                           // :293
-  const T th = 1.0 / 3.0 * ad_asin(arg);                                   // :294
+  const T th = real(1.0) / real(3.0) * ad_asin(arg);                                   // :294
   const T K = K_fun(th, angle, p);
-  const double ag = p.a * std::tan(p.phi) / std::tan(angle);               // :348-349
-  const double sa = std::sin(angle);
+  const real ag = p.a * std::tan(p.phi) / std::tan(angle);               // :348-349
+  const real sa = std::sin(angle);
   return (I1 / 3.0 * sa) + ad_sqrt(J2 * K * K + ag * ag * sa * sa) - p.c * std::cos(angle);  // :368-374
 }
 
@@ -266,9 +288,9 @@ inline void solve5(T A[5][5], T b[5], T x[5]) {
   for (int i = 0; i < 5; ++i) piv[i] = i;
   for (int c = 0; c < 5; ++c) {
     int best = c;
-    double bv = std::fabs(primal(A[piv[c]][c]));
+    real bv = std::fabs(primal(A[piv[c]][c]));
     for (int r = c + 1; r < 5; ++r) {
-      const double v = std::fabs(primal(A[piv[r]][c]));
+      const real v = std::fabs(primal(A[piv[r]][c]));
       if (v > bv) {
         bv = v;
         best = r;
@@ -298,27 +320,27 @@ inline T norm5(const T r[5]) {
   return ad_sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3] + r[4] * r[4]);
 }
 
-// return_mapping, :474-533, on a generic scalar T (double: values only; Dual<double,4>: values
+// return_mapping, :474-533, on a generic scalar T (real: values only; Dual<real,4>: values
 // and d/d(deps) carried through the loop).
 template <class T>
 inline void return_mapping(const T deps[4], const T sn[4], const Consts& k, T sigma[4], int32_t& niter_out,
-                           double& yielding_out, double& norm_res_out, T& dlambda_out) {
+                           real& yielding_out, real& norm_res_out, T& dlambda_out) {
   // trial-state predicate :421-422 (value only: lax.cond predicates carry no tangent)
-  double trial[4];
+  real trial[4];
   for (int i = 0; i < 4; ++i) {
-    double acc = k.C[i][0] * primal(deps[0]);
+    real acc = k.C[i][0] * primal(deps[0]);
     for (int j = 1; j < 4; ++j) acc += k.C[i][j] * primal(deps[j]);
     trial[i] = primal(sn[i]) + acc;
   }
-  const double yielding = surface(trial, k.p.phi, k);
+  const real yielding = surface(trial, k.p.phi, k);
   const bool plastic = !(yielding <= 0.0);
 
   T y[5], res[5];
   for (int i = 0; i < 4; ++i) y[i] = sn[i];  // :496-498
   y[4] = T(0.0);
   residual(y, deps, sn, plastic, k, res);    // :500
-  const double norm0 = primal(norm5(res));   // :501
-  double nrm = norm0;
+  const real norm0 = primal(norm5(res));   // :501
+  real nrm = norm0;
   int32_t niter = 0;
   while ((nrm / norm0 > k.p.tol) && (niter < k.p.Nitermax)) {  // :503-505
     T J[5][5], rhs[5], dy[5];
@@ -339,39 +361,40 @@ inline void return_mapping(const T deps[4], const T sn[4], const Consts& k, T si
 
 void mc_point(const Consts& k, const double* deps, const double* sn, double* Ct, double* sig, int32_t* niter,
               double* yielding, double* norm_res, double* dlambda) {
-  typedef Dual<double, 4> D;  // jacfwd over deps, :555
+  typedef Dual<real, 4> D;  // jacfwd over deps, :555
   D de[4], s0[4], so[4], dl;
   for (int i = 0; i < 4; ++i) {
-    de[i] = D(deps[i]);
+    de[i] = D(real(deps[i]));
     de[i].d[i] = 1.0;
-    s0[i] = D(sn[i]);
+    s0[i] = D(real(sn[i]));
   }
   int32_t it;
-  double yl, nr;
+  real yl, nr;
   return_mapping(de, s0, k, so, it, yl, nr, dl);
   for (int i = 0; i < 4; ++i) {
-    sig[i] = so[i].v;
-    for (int j = 0; j < 4; ++j) Ct[4 * i + j] = so[i].d[j];
+    sig[i] = (double)so[i].v;
+    for (int j = 0; j < 4; ++j) Ct[4 * i + j] = (double)so[i].d[j];
   }
   *niter = it;
-  *yielding = yl;
-  *norm_res = nr;
-  *dlambda = dl.v;
+  *yielding = (double)yl;
+  *norm_res = (double)nr;
+  *dlambda = (double)dl.v;
 }
 
 }  // namespace
 
 extern "C" {
 
-typedef McParams oracle_mc_params;
+typedef McParamsIO oracle_mc_params;
 
 // Layouts as the reference returns them (:593): deps/sigma_n/sigma [n][4], C_tang [n][4][4];
-// aux outputs per point as in the aux tuple of :533.
-void oracle_mc_return_mapping(const oracle_mc_params* prm, const double* deps, const double* sigma_n, double* C_tang,
-                              double* sigma, int32_t* niter, double* yielding, double* norm_res, double* dlambda,
-                              int64_t n, int parallel) {
+// aux outputs per point as in the aux tuple of :533.  Exported as oracle_mc_return_mapping (real = double) and
+// oracle_mc_return_mapping_ld (real = long double, results rounded to double).
+void ORACLE_NAME(oracle_mc_return_mapping)(const oracle_mc_params* prm, const double* deps, const double* sigma_n,
+                                           double* C_tang, double* sigma, int32_t* niter, double* yielding,
+                                           double* norm_res, double* dlambda, int64_t n, int parallel) {
   Consts k;
-  make_consts(*prm, k);
+  make_consts(McParams(*prm), k);
 #pragma omp parallel for schedule(dynamic, 64) if (parallel)
   for (int64_t i = 0; i < n; ++i)
     mc_point(k, deps + 4 * i, sigma_n + 4 * i, C_tang + 16 * i, sigma + 4 * i, niter + i, yielding + i, norm_res + i,
@@ -379,22 +402,29 @@ void oracle_mc_return_mapping(const oracle_mc_params* prm, const double* deps, c
 }
 
 // Values only (no tangent): stress update used to generate stress paths.
-void oracle_mc_stress(const oracle_mc_params* prm, const double* deps, const double* sigma_n, double* sigma,
-                      int32_t* niter, double* yielding, int64_t n, int parallel) {
+void ORACLE_NAME(oracle_mc_stress)(const oracle_mc_params* prm, const double* deps, const double* sigma_n, double* sigma,
+                                   int32_t* niter, double* yielding, int64_t n, int parallel) {
   Consts k;
-  make_consts(*prm, k);
+  make_consts(McParams(*prm), k);
 #pragma omp parallel for schedule(dynamic, 64) if (parallel)
   for (int64_t i = 0; i < n; ++i) {
-    double nr, dl;
-    return_mapping<double>(deps + 4 * i, sigma_n + 4 * i, k, sigma + 4 * i, niter[i], yielding[i], nr, dl);
+    real de[4], sn[4], sg[4], nr, dl, yl;
+    for (int j = 0; j < 4; ++j) de[j] = deps[4 * i + j], sn[j] = sigma_n[4 * i + j];
+    return_mapping<real>(de, sn, k, sg, niter[i], yl, nr, dl);
+    for (int j = 0; j < 4; ++j) sigma[4 * i + j] = (double)sg[j];
+    yielding[i] = (double)yl;
   }
 }
 
 // f(sigma) and g-gradient, exposed for known-answer tests (f(sigma_returned) ~ 0 etc.)
-void oracle_mc_yield(const oracle_mc_params* prm, const double* sigma, double* f, int64_t n) {
+void ORACLE_NAME(oracle_mc_yield)(const oracle_mc_params* prm, const double* sigma, double* f, int64_t n) {
   Consts k;
-  make_consts(*prm, k);
-  for (int64_t i = 0; i < n; ++i) f[i] = surface(sigma + 4 * i, k.p.phi, k);
+  make_consts(McParams(*prm), k);
+  for (int64_t i = 0; i < n; ++i) {
+    real sg[4];
+    for (int j = 0; j < 4; ++j) sg[j] = sigma[4 * i + j];
+    f[i] = (double)surface(sg, k.p.phi, k);
+  }
 }
 
 }  // extern "C"

@@ -91,8 +91,10 @@ def _mc_prm(prm):
     return OracleMcParams(prm.E, prm.nu, prm.c, prm.phi, prm.psi, prm.theta_T, prm.a, prm.tol, prm.Nitermax)
 
 
-def mc_return_mapping(deps, sigma_n, prm, parallel: bool = False):
-    """C++ dual-number restatement of demo_mc:474-555.  Returns dict(C_tang, sigma, niter, yielding, norm_res, dlambda)."""
+def mc_return_mapping(deps, sigma_n, prm, parallel: bool = False, extended: bool = False):
+    """C++ dual-number restatement of demo_mc:474-555.  Returns dict(C_tang, sigma, niter, yielding, norm_res, dlambda).
+    extended=True: the same program evaluated in x87 extended precision (eps 1.1e-19) and rounded to double at the end -
+    the "exact" value for rounding audits."""
     lib = load()
     deps = np.ascontiguousarray(deps, dtype=np.float64).reshape(-1, 4)
     sigma_n = np.ascontiguousarray(sigma_n, dtype=np.float64).reshape(-1, 4)
@@ -100,9 +102,9 @@ def mc_return_mapping(deps, sigma_n, prm, parallel: bool = False):
     out = {"C_tang": np.empty((n, 4, 4)), "sigma": np.empty((n, 4)), "niter": np.empty(n, dtype=np.int32),
            "yielding": np.empty(n), "norm_res": np.empty(n), "dlambda": np.empty(n)}
     q = _mc_prm(prm)
-    lib.oracle_mc_return_mapping(C.byref(q), _p(deps), _p(sigma_n), _p(out["C_tang"]), _p(out["sigma"]),
-                                 _p(out["niter"]), _p(out["yielding"]), _p(out["norm_res"]), _p(out["dlambda"]),
-                                 C.c_int64(n), C.c_int(int(parallel)))
+    fn = lib.oracle_mc_return_mapping_ld if extended else lib.oracle_mc_return_mapping
+    fn(C.byref(q), _p(deps), _p(sigma_n), _p(out["C_tang"]), _p(out["sigma"]), _p(out["niter"]), _p(out["yielding"]),
+       _p(out["norm_res"]), _p(out["dlambda"]), C.c_int64(n), C.c_int(int(parallel)))
     return out
 
 

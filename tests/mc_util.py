@@ -16,40 +16,70 @@ def lode_arg(sig):
         return -(3 * np.sqrt(3) * J3) / (2 * np.sqrt(J2**3))
 
 
-def corner_points(ref, deps, sigma_n, prm, thresh=1e-6):
-    """Plastic points whose Lode angle is within ~0.01 degree of a corner of the Mohr-Coulomb hexagon
-    (1 - sin^2(3 theta) < 1e-6 at sigma_n, at the trial stress or at the returned stress).
+EPS = 2.220446049250313e-16
+# Rounding audit (tests/test_mc_precision_cpu.py): the reference's float64 program is evaluated once more
+# in x87 extended precision (oracle_mc_return_mapping_ld, eps 1.1e-19) and that value is taken as exact.  Measured on
+# 2 x 10^5 points of the demo's stress-path family and on the 2048-point golden:
+#   * the reference's OWN float64 evaluation (C++ restatement and the torch-executed source alike) is off by up to
+#     3.1 eps / w2 in the tangent and 4.9 eps / w2 in dlambda, w2 = 1 - sin^2(3 theta) (the reference differentiates
+#     sin(3 asin(x) / 3) as cos(3 theta) / sqrt(1 - x^2), demo_mc:292-294, :340-342) - 1.3e-10 at w2 < 1e-8;
+#   * the kernel arithmetic (sin 3 theta = x used directly) stays within 5e-14 of exact for w2 >= 1e-8 and 7.4e-12 below.
+# So: against the EXACT value every point is held to the flat north_star tolerance (check_mc_exact); against a float64
+# evaluation of the reference (goldens, oracle) a point is given the reference's own rounding bound on top of a
+# 1e-12 base - C_REF eps / w2 exceeds 1e-10 for about 0.5 % of a batch (returned stresses cluster at the corners).
+C_REF = 8.0
+RTOL_BASE = 1e-12
 
-    There the REFERENCE's own AD evaluates d sin(3 theta)/d arg as cos(3 theta)/sqrt(1 - arg^2) (asin followed
-    by sin, demo_mc:292-294, :340-342): a 0/0-type quotient whose relative rounding noise is eps/(1 - arg^2),
-    i.e. >= 1e-10 for these points.  Two correct IEEE evaluations of the reference's program (with and without
-    FMA contraction, different libm) already differ by that much, so such points are compared with the
-    tolerance scaled by that condition number (capped at 1e-6 relative); all other points at 1e-10.
-    Returned stresses cluster at the hexagon corners, so ~0.1 % of a batch is affected."""
-    w2 = 1.0 - lode_arg(ref["sigma"]) ** 2
+
+def lode_w2(ref_sigma, deps, sigma_n, prm):
+    """min over sigma_n, the trial stress and the returned stress of 1 - sin^2(3 theta)."""
+    w2 = 1.0 - lode_arg(ref_sigma) ** 2
     C = oc.elastic_stiffness(prm.lmbda, prm.mu)
     sigma_n = np.asarray(sigma_n).reshape(-1, 4)
     deps = np.asarray(deps).reshape(-1, 4)
     w2 = np.minimum(w2, 1.0 - lode_arg(sigma_n) ** 2)
     w2 = np.minimum(w2, 1.0 - lode_arg(sigma_n + deps @ C.T) ** 2)
-    w2 = np.where(np.isfinite(w2), np.maximum(w2, 1e-10), 1.0)
-    corner = (w2 < thresh) & (np.asarray(ref["yielding"]) > 0)
-    return corner, np.where(corner, thresh / w2, 1.0)
+    return np.where(np.isfinite(w2), np.maximum(w2, 1e-12), 1.0)
+
+
+def _compare(out, ref, tol_rows, keys=(("C_tang", 16), ("sigma", 4), ("dlambda", 1), ("yielding", 1))):
+    worst = {}
+    for k, w in keys:
+        a, b = np.asarray(out[k]).reshape(-1, w), np.asarray(ref[k]).reshape(-1, w)
+        scale = np.abs(b) + np.abs(b[np.isfinite(b)]).max()
+        bad = ~(np.abs(a - b) <= tol_rows[:, None] * scale) & ~(np.isnan(a) & np.isnan(b))
+        assert not bad.any(), (k, np.argwhere(bad)[:5], np.nanmax(np.abs(a - b) / scale))
+        with np.errstate(invalid="ignore"):
+            worst[k] = float(np.nanmax(np.abs(a - b) / scale)) if a.size else 0.0
+    return worst
 
 
 def check_mc(out, ref, deps, sigma_n, prm, rtol=RTOL):
-    """Flags and iteration counts bit-exact; tangent / stress / dlambda / yielding within rtol (relative to the
-    field's scale, corner points scaled as explained above); ||res|| (a converged, rounding-level quantity)
-    within an absolute 1e-10 of the stress scale."""
+    """`out` against a FLOAT64 evaluation of the reference (golden / oracle): flags and iteration counts bit-exact;
+    tangent / stress / dlambda / yielding within RTOL_BASE + C_REF eps / w2 of the field scale for plastic points (the
+    reference's own measured rounding bound, see above; < 1e-10 unless w2 < 1.8e-5), RTOL_BASE for elastic ones;
+    ||res|| (a converged, rounding-level quantity) within an absolute 1e-10 of the stress scale.  Returns the number
+    of points whose bound exceeds the north_star tolerance 1e-10."""
     assert np.array_equal(out["niter"], ref["niter"])
     assert np.array_equal(np.asarray(out["yielding"]) > 0, np.asarray(ref["yielding"]) > 0)
-    corner, scale = corner_points(ref, deps, sigma_n, prm)
-    assert corner.mean() < 2e-2 or corner.size < 200, corner.mean()
-    for k, w in (("C_tang", 16), ("sigma", 4), ("dlambda", 1), ("yielding", 1)):
-        a, b = np.asarray(out[k]).reshape(-1, w), np.asarray(ref[k]).reshape(-1, w)
-        tol = rtol * scale[:, None]
-        bad = ~(np.abs(a - b) <= tol * (np.abs(b) + np.abs(b[np.isfinite(b)]).max())) & ~(np.isnan(a) & np.isnan(b))
-        assert not bad.any(), (k, np.argwhere(bad)[:5], np.nanmax(np.abs(a - b)))
+    plastic = np.asarray(ref["yielding"]) > 0
+    w2 = lode_w2(ref["sigma"], deps, sigma_n, prm)
+    tol = np.where(plastic, RTOL_BASE + C_REF * EPS / w2, RTOL_BASE)
+    relaxed = tol > rtol
+    assert relaxed.mean() < 1e-2 or relaxed.size < 200, relaxed.mean()
+    _compare(out, ref, tol)
     smax = np.abs(np.asarray(ref["sigma"])[np.isfinite(ref["sigma"])]).max()
     np.testing.assert_allclose(out["norm_res"], ref["norm_res"], rtol=0, atol=1e-10 * smax)
-    return int(corner.sum())
+    return int(relaxed.sum())
+
+
+def check_mc_exact(out, deps, sigma_n, prm, rtol=RTOL):
+    """`out` against the reference program evaluated in extended precision (oracle, `extended=True`): flags and
+    iteration counts equal, tangent / stress / dlambda / yielding within the FLAT north_star tolerance at EVERY
+    point - no corner exception.  Returns the worst relative deviations per field."""
+    from oracle import native
+
+    ex = native.mc_return_mapping(deps, sigma_n, prm, parallel=True, extended=True)
+    assert np.array_equal(out["niter"], ex["niter"])
+    assert np.array_equal(np.asarray(out["yielding"]) > 0, ex["yielding"] > 0)
+    return _compare(out, ex, np.full(ex["niter"].shape[0], rtol))

@@ -14,7 +14,7 @@ import pytest
 
 from oracle import constitutive as oc
 from oracle import inputs, native
-from mc_util import check_mc
+from mc_util import check_mc, check_mc_exact
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 MC_PRM = oc.MohrCoulombParams()
@@ -38,10 +38,12 @@ def _mc(hc, deps, sn, prm):
     return out
 
 
-@pytest.mark.parametrize("name", ["mc_path_10x9.npz", "mc_rand_seed0_n96.npz"])
+@pytest.mark.parametrize("name", ["mc_path_10x9.npz", "mc_rand_seed0_n96.npz", "mc_rand_seed1_n2048.npz"])
 def test_mc_core_against_reference_golden(hc, golden_dir, name):
     g = np.load(os.path.join(golden_dir, name))
-    check_mc(_mc(hc, g["deps"], g["sigma_n"], MC_PRM), g, g["deps"], g["sigma_n"], MC_PRM)
+    o = _mc(hc, g["deps"], g["sigma_n"], MC_PRM)
+    check_mc(o, g, g["deps"], g["sigma_n"], MC_PRM)
+    check_mc_exact(o, g["deps"], g["sigma_n"], MC_PRM)  # flat 1e-10 at every point, corners included
 
 
 @pytest.mark.parametrize("psi_deg", [30, 10])
@@ -49,7 +51,9 @@ def test_mc_core_against_oracle(hc, psi_deg):
     prm = dataclasses.replace(MC_PRM, psi=psi_deg * np.pi / 180)
     step = lambda d, s: native.mc_stress(d, s, prm, parallel=True)[0]  # noqa: E731
     d, s = inputs.mc_batch(20_000, seed=3, stepper=step)
-    check_mc(_mc(hc, d, s, prm), native.mc_return_mapping(d, s, prm, parallel=True), d, s, prm)
+    o = _mc(hc, d, s, prm)
+    check_mc(o, native.mc_return_mapping(d, s, prm, parallel=True), d, s, prm)
+    check_mc_exact(o, d, s, prm)
 
 
 def test_mc_core_edge_semantics(hc):
