@@ -731,6 +731,9 @@ def run_gpu_arm(args):
     hbm_peak, hbm_src = _measured_peaks()
     peaks = {"hbm_gbs": hbm_peak, "hbm_source": hbm_src, "fp64_tflops": ctx.fp64_peak_tflops(),
              "fp32_tflops": ctx.fp32_peak_tflops(),
+             # by instruction form: all-register scalar FFMA and packed FFMA2 sit below the
+             # uniform-operand form the roofline fraction is quoted against
+             "fp32_tflops_ffma_3reg": ctx.fp32_peak_tflops(variant=1), "fp32_tflops_ffma2": ctx.fp32_peak_tflops(variant=2),
              "how": "FP64 / FP32: register-only DFMA / FFMA micro-benchmarks of this library (8 independent chains per thread, "
                     "all SMs, best of 3) run at the start of this bench"}
 

@@ -123,6 +123,7 @@ PROTOTYPES = {
     "eo_debug_counters": (C.c_int, [_vp, _vp]),
     "eo_fp64_peak": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double)]),
     "eo_fp32_peak": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double)]),
+    "eo_fp32_peak_variant": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "eo_stats_reset": (C.c_int, [_vp]),
     "eo_stats_read": (C.c_int, [_vp, C.POINTER(Stats)]),
     "eo_stats_device_ptr": (_vp, [_vp]),
@@ -155,6 +156,7 @@ PROTOTYPES = {
     "eo_isihara_destroy": (C.c_int, [_vp]),
     "eo_isihara_set_correction": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "eo_isihara_eval": (C.c_int, [_vp, _vp, _vp, _vp, _i64]),
+    "eo_isihara_eval_on_stream": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "eo_jit_create": (C.c_int, [_vp, C.POINTER(JitDesc), C.POINTER(_vp)]),
     "eo_jit_destroy": (C.c_int, [_vp]),
     "eo_jit_compile": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),

@@ -237,10 +237,14 @@ class Context:
         self.check(self._lib.eo_fp64_peak(self._h, int(iters), C.byref(t)))
         return float(t.value)
 
-    def fp32_peak_tflops(self, iters: int = 1 << 16) -> float:
-        """Measured FP32 FFMA throughput of this GPU (the roofline denominator of the Isihara network kernel)."""
+    def fp32_peak_tflops(self, iters: int = 1 << 16, variant: int | None = None) -> float:
+        """Measured FP32 FMA throughput of this GPU (the roofline denominator of the Isihara network kernel).
+        variant None / 0: scalar FFMA with uniform operands; 1: scalar FFMA, three register operands; 2: packed FFMA2."""
         t = C.c_double()
-        self.check(self._lib.eo_fp32_peak(self._h, int(iters), C.byref(t)))
+        if variant is None:
+            self.check(self._lib.eo_fp32_peak(self._h, int(iters), C.byref(t)))
+        else:
+            self.check(self._lib.eo_fp32_peak_variant(self._h, int(iters), int(variant), C.byref(t)))
         return float(t.value)
 
     # -------------------------------------------------------------- statistics

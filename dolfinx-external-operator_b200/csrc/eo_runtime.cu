@@ -65,6 +65,40 @@ __global__ void __launch_bounds__(256) eo_fp32_peak_kernel(float* out, int iters
   out[blockIdx.x * size_t(blockDim.x) + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
+// variant 1: every operand in a register that changes per chain (no constant-bank / immediate operand form)
+__global__ void __launch_bounds__(256) eo_fp32_peak3_kernel(float* out, int iters, float b0, float c0) {
+  float a[8], b[8], c[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = threadIdx.x + k, b[k] = b0 + 1e-7f * (threadIdx.x + k), c[k] = c0 * (k + 1);
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = fmaf(a[k], b[k], c[k]);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += a[k];
+  out[blockIdx.x * size_t(blockDim.x) + threadIdx.x] = s;
+}
+
+// variant 2: packed FFMA2 (fma.rn.f32x2), 8 independent chains of register pairs = 16 FMAs per trip
+__global__ void __launch_bounds__(256) eo_fp32_peak2x_kernel(float* out, int iters, float b0, float c0) {
+  float2 a[8], b[8], c[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    a[k] = make_float2(threadIdx.x + k, threadIdx.x + k + 0.5f);
+    b[k] = make_float2(b0 + 1e-7f * (threadIdx.x + k), b0 - 1e-7f * (threadIdx.x + k));
+    c[k] = make_float2(c0 * (k + 1), c0 * (k + 2));
+  }
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = __ffma2_rn(a[k], b[k], c[k]);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += a[k].x + a[k].y;
+  out[blockIdx.x * size_t(blockDim.x) + threadIdx.x] = s;
+}
+
 // out[k] = values[src[k]]: the non-contiguous coefficient assignment turned inside out (see eo_assign_gather)
 __global__ void __launch_bounds__(256) eo_gather_kernel(const double* __restrict__ values, const int64_t* __restrict__ src,
                                                         double* __restrict__ out, int64_t n_out) {
@@ -469,6 +503,35 @@ int eo_fp64_peak(eo_ctx* ctx, int iters, double* tflops) {
   cudaEventDestroy(e1);
   cudaFree(out);
   *tflops = 2.0 * 8.0 * double(iters) * double(grid) * block / (double(best) * 1e-3) / 1e12;
+  return EO_OK;
+}
+
+int eo_fp32_peak_variant(eo_ctx* ctx, int iters, int variant, double* tflops) {
+  EO_REQUIRE(ctx, ctx && tflops && iters > 0 && variant >= 0 && variant <= 2, "eo_fp32_peak_variant: bad argument");
+  EO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int grid = ctx->sm_count * 8, block = 256;
+  float* out = nullptr;
+  EO_CUDA(ctx, cudaMalloc(&out, size_t(grid) * block * sizeof(float)));
+  cudaEvent_t e0, e1;
+  EO_CUDA(ctx, cudaEventCreate(&e0));
+  EO_CUDA(ctx, cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {  // first repetition is the warm-up
+    EO_CUDA(ctx, cudaEventRecord(e0, ctx->s_cmp));
+    if (variant == 0) eo_fp32_peak_kernel<<<grid, block, 0, ctx->s_cmp>>>(out, iters, 0.999999f, 1e-6f);
+    else if (variant == 1) eo_fp32_peak3_kernel<<<grid, block, 0, ctx->s_cmp>>>(out, iters, 0.999999f, 1e-6f);
+    else eo_fp32_peak2x_kernel<<<grid, block, 0, ctx->s_cmp>>>(out, iters, 0.999999f, 1e-6f);
+    EO_CUDA(ctx, cudaEventRecord(e1, ctx->s_cmp));
+    EO_CUDA(ctx, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    EO_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  const double fma_per_trip = variant == 2 ? 16.0 : 8.0;
+  *tflops = 2.0 * fma_per_trip * double(iters) * double(grid) * block / (double(best) * 1e-3) / 1e12;
   return EO_OK;
 }
 

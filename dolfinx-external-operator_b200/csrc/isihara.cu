@@ -110,6 +110,29 @@ int eo_isihara_set_correction(eo_isihara* m, const double H_flat[4]) {
   return EO_OK;
 }
 
+static void isi_launch(eo_isihara* m, const double* F, double* dP, double* P, int64_t cnt, cudaStream_t stream) {
+  int64_t grid = (cnt + ISI_THREADS - 1) / ISI_THREADS;
+  const int64_t cap = int64_t(m->ctx->sm_count) * 2;  // persistent: one resident CTA per SM, grid-stride over the points
+  if (grid > cap) grid = cap;
+  isihara_kernel<<<(unsigned)grid, ISI_THREADS, ISI_SMEM, stream>>>(m->d_w, F, dP, P, cnt);
+  m->ctx->launches += 1;
+}
+
+int eo_isihara_eval_on_stream(eo_isihara* m, const double* F, double* dP, double* P, int64_t n, void* stream) {
+  if (!m) return EO_ERR_INVALID;
+  eo_ctx* ctx = m->ctx;
+  EO_REQUIRE(ctx, n >= 0, "eo_isihara_eval_on_stream: n < 0");
+  if (n == 0) return EO_OK;
+  EO_REQUIRE(ctx, F && dP && P, "eo_isihara_eval_on_stream: NULL array");
+  EO_REQUIRE(ctx, eo_is_device_ptr(F) && eo_is_device_ptr(dP) && eo_is_device_ptr(P),
+             "eo_isihara_eval_on_stream: arrays must be device memory (the caller's stream orders them)");
+  EO_REQUIRE(ctx, eo_aligned(F, 32) && eo_aligned(dP, 32) && eo_aligned(P, 32), "eo_isihara_eval_on_stream: arrays must be 32-byte aligned");
+  EO_CUDA(ctx, cudaSetDevice(ctx->device));
+  isi_launch(m, F, dP, P, n, (cudaStream_t)stream);
+  EO_CUDA(ctx, cudaGetLastError());
+  return EO_OK;
+}
+
 int eo_isihara_eval(eo_isihara* m, const double* F, double* dP, double* P, int64_t n) {
   if (!m) return EO_ERR_INVALID;
   eo_ctx* ctx = m->ctx;
@@ -121,12 +144,7 @@ int eo_isihara_eval(eo_isihara* m, const double* F, double* dP, double* P, int64
   return eo_run_streamed(ctx, args, 3, n, [&](void** a, int64_t cnt, int64_t) {
     for (int i = 0; i < 3; ++i)
       if (!eo_aligned(a[i], 32)) return eo_fail(ctx, EO_ERR_INVALID, "eo_isihara_eval: arrays must be 32-byte aligned");
-    int64_t grid = (cnt + ISI_THREADS - 1) / ISI_THREADS;
-    const int64_t cap = int64_t(ctx->sm_count) * 2;  // persistent: one resident CTA per SM, grid-stride over the points
-    if (grid > cap) grid = cap;
-    isihara_kernel<<<(unsigned)grid, ISI_THREADS, ISI_SMEM, ctx->s_cmp>>>(m->d_w, (const double*)a[0],
-                                                                                      (double*)a[1], (double*)a[2], cnt);
-    ctx->launches += 1;
+    isi_launch(m, (const double*)a[0], (double*)a[1], (double*)a[2], cnt, ctx->s_cmp);
     return (int)EO_OK;
   });
 }

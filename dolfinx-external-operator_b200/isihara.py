@@ -113,8 +113,8 @@ _TORCH_MODEL = None
 
 def register_torch_op(model: Isihara):
     """Define `torch.ops.eo.isihara_dP_dF(Tensor F) -> (Tensor dP, Tensor P)` for CUDA float64 tensors,
-    backed by `model` (zero copy; runs on the model's context stream and synchronises before returning so
-    that the result can be used on torch's current stream)."""
+    backed by `model`: zero copy, launched on torch's CURRENT stream (eo_isihara_eval_on_stream) - asynchronous and
+    ordered like any other torch op, no synchronisation on either side."""
     import torch
 
     global _TORCH_MODEL
@@ -132,10 +132,11 @@ def register_torch_op(model: Isihara):
         n = Fc.shape[0]
         dP = torch.empty((n, 4, 4), dtype=torch.float64, device=F.device)
         P = torch.empty((n, 4), dtype=torch.float64, device=F.device)
-        torch.cuda.current_stream(F.device).synchronize()  # F may still be being produced on torch's stream
         c = m.ctx
-        c.check(c.lib.eo_isihara_eval(m._h, Fc.data_ptr(), dP.data_ptr(), P.data_ptr(), n))
-        c.sync()
+        if F.device.index != c.device:
+            raise ValueError(f"eo::isihara_dP_dF: tensor on cuda:{F.device.index}, model context on cuda:{c.device}")
+        stream = torch.cuda.current_stream(F.device).cuda_stream
+        c.check(c.lib.eo_isihara_eval_on_stream(m._h, Fc.data_ptr(), dP.data_ptr(), P.data_ptr(), n, stream))
         return dP, P
 
     @isihara_dP_dF.register_fake

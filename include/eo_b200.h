@@ -121,6 +121,10 @@ int eo_debug_counters(eo_ctx* ctx, uint32_t* out);
 int eo_fp64_peak(eo_ctx* ctx, int iters, double* tflops);
 /* The same for FP32 FFMA: roofline denominator of the Isihara network kernel (float32 CUDA cores). */
 int eo_fp32_peak(eo_ctx* ctx, int iters, double* tflops);
+/* FP32 FMA throughput by instruction form: variant 0 = scalar FFMA with uniform multiplier / addend (what eo_fp32_peak
+ * runs), 1 = scalar FFMA with three per-chain register operands, 2 = packed FFMA2 (fma.rn.f32x2, two FMAs per
+ * instruction) with register-pair operands. */
+int eo_fp32_peak_variant(eo_ctx* ctx, int iters, int variant, double* tflops);
 
 /* ---------------------------------------------------------------- statistics
  * Device-resident record that every constitutive kernel accumulates into in its
@@ -393,6 +397,10 @@ int eo_isihara_set_correction(eo_isihara* m, const double H_flat[4]);
 /* F [n][4] = [F11, F12, F21, F22] (:263-266)  ->  dP [n][4][4] (dP_i/dF_j), P [n][4]; float64 in and out,
  * network arithmetic in float32 like the reference (results are float32-accurate).  Any-side pointers. */
 int eo_isihara_eval(eo_isihara* m, const double* F, double* dP, double* P, int64_t n);
+/* The same for device arrays on the CALLER's stream (cudaStream_t passed as void*; NULL = the legacy default stream):
+ * asynchronous, ordered only by that stream - what the torch custom op `eo::isihara_dP_dF` uses with torch's current
+ * stream, so that the op composes with the surrounding torch work without any synchronisation. */
+int eo_isihara_eval_on_stream(eo_isihara* m, const double* F, double* dP, double* P, int64_t n, void* stream);
 
 /* ---------------------------------------------------------------- generic run-time compiled models
  * replaces: any user `external_function(derivatives)(*operands)` (external_operator.py:432) that is not one
