@@ -45,6 +45,7 @@ struct eo_form {
   // bisection at the first eo_form_matrix after eo_form_set_pattern when memory allows; -1 = not in the pattern
   int32_t* pos = nullptr;
   unsigned* missing = nullptr;  // device counter of element entries the pattern does not hold
+  struct form_pipe* pipe = nullptr;  // chunk pipeline of the host-vector path (built at first use)
 };
 
 struct form_weights {
@@ -634,6 +635,168 @@ static int form_stage_x(eo_form* f, const double* x, const double** d_x) {
   return EO_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Host-vector path (u / x in host memory, b / y back to host memory): dependency-aware chunk pipeline.
+// The DOF vector is the only thing that crosses PCIe (about 11 B per point each way for P2 triangles), but a serial
+// H2D -> kernel -> D2H spends 88 % of its time in the two copies.  The cells are cut into K consecutive chunks and the
+// vector into P pieces; a small kernel records once per mesh which pieces every chunk reads / accumulates into.  Then
+//   * the pieces of u go up in the order of their FIRST use, chunk k starts as soon as the pieces it needs have landed,
+//   * a piece of b comes down as soon as the LAST chunk that adds to it has finished,
+// on three streams, so that the upload of later pieces, the kernels and the download of finished pieces overlap (the
+// link is full duplex).  With a numbering that has locality (structured, RCM, anything DOLFINx produces) this hides
+// the kernel and one of the two copies; with a random numbering every chunk touches every piece and the schedule
+// degenerates into the serial one - same results either way (to the rounding of the atomic scatter).
+// ------------------------------------------------------------------------------------------------------------
+#define FORM_PIPE_CHUNKS 16
+#define FORM_PIPE_PIECES 64
+
+struct form_pipe {
+  int K = 0, P = 0;
+  int64_t piece = 0;                    // doubles per piece
+  int64_t n_cells = 0;
+  std::vector<int64_t> cell_lo;         // K + 1 chunk boundaries
+  std::vector<int> h2d_order, d2h_order;
+  std::vector<int> h2d_upto, d2h_upto;  // per chunk: length of the prefix of *_order that belongs to chunks <= k
+  std::vector<cudaEvent_t> ev_in, ev_k;
+};
+
+__global__ void __launch_bounds__(256) form_touch_kernel(const int32_t* __restrict__ dofmap, int64_t n_cells, int nb, int bs,
+                                                         int64_t chunk_cells, int64_t piece, int words,
+                                                         unsigned int* __restrict__ bits) {
+  const int64_t j = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (j >= n_cells * nb) return;
+  const int64_t c = j / nb;
+  const int k = int(c / chunk_cells);
+  const int64_t d0 = int64_t(bs) * dofmap[j];
+  const int p0 = int(d0 / piece), p1 = int((d0 + bs - 1) / piece);
+  atomicOr(bits + size_t(k) * words + (p0 >> 5), 1u << (p0 & 31));
+  if (p1 != p0) atomicOr(bits + size_t(k) * words + (p1 >> 5), 1u << (p1 & 31));
+}
+
+static void form_pipe_free(form_pipe* pp) {
+  if (!pp) return;
+  for (cudaEvent_t e : pp->ev_in) cudaEventDestroy(e);
+  for (cudaEvent_t e : pp->ev_k) cudaEventDestroy(e);
+  delete pp;
+}
+
+static int form_pipe_build(eo_form* f, int64_t n_cells) {
+  eo_tab* t = f->tab;
+  eo_ctx* ctx = t->ctx;
+  form_pipe_free(f->pipe);
+  f->pipe = nullptr;
+  form_pipe* pp = new form_pipe();
+  const int64_t nd = int64_t(t->n_dofs) * t->T.bs;
+  pp->K = form_env("EO_FORM_PIPE_CHUNKS", FORM_PIPE_CHUNKS), pp->P = form_env("EO_FORM_PIPE_PIECES", FORM_PIPE_PIECES), pp->n_cells = n_cells;
+  if (pp->K < 1) pp->K = 1;
+  if (pp->P < 1) pp->P = 1;
+  pp->piece = ((nd + pp->P - 1) / pp->P + 3) / 4 * 4;  // 32-byte multiples
+  pp->P = int((nd + pp->piece - 1) / pp->piece);
+  const int64_t chunk_cells = (n_cells + pp->K - 1) / pp->K;
+  pp->K = int((n_cells + chunk_cells - 1) / chunk_cells);
+  for (int k = 0; k <= pp->K; ++k) pp->cell_lo.push_back(k * chunk_cells < n_cells ? k * chunk_cells : n_cells);
+  const int words = (pp->P + 31) / 32;
+  unsigned int* d_bits = nullptr;
+  std::vector<unsigned int> bits(size_t(pp->K) * words, 0u);
+  cudaError_t e = cudaMalloc(&d_bits, bits.size() * 4);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_bits, 0, bits.size() * 4, ctx->s_cmp);
+  if (e == cudaSuccess) {
+    const int64_t n = n_cells * t->T.nb;
+    form_touch_kernel<<<unsigned((n + 255) / 256), 256, 0, ctx->s_cmp>>>(t->dofmap, n_cells, t->T.nb, t->T.bs, chunk_cells,
+                                                                         pp->piece, words, d_bits);
+    e = cudaMemcpyAsync(bits.data(), d_bits, bits.size() * 4, cudaMemcpyDeviceToHost, ctx->s_cmp);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_cmp);
+  if (d_bits) cudaFree(d_bits);
+  if (e != cudaSuccess) {
+    delete pp;
+    return eo_fail(ctx, EO_ERR_CUDA, "eo_form: building the chunk pipeline: %s", cudaGetErrorString(e));
+  }
+  std::vector<int> first(pp->P, pp->K), last(pp->P, -1);
+  for (int k = 0; k < pp->K; ++k)
+    for (int q = 0; q < pp->P; ++q)
+      if (bits[size_t(k) * words + (q >> 5)] >> (q & 31) & 1u) {
+        if (first[q] > k) first[q] = k;
+        last[q] = k;
+      }
+  pp->h2d_upto.assign(pp->K, 0), pp->d2h_upto.assign(pp->K, 0);
+  for (int k = 0; k <= pp->K; ++k) {  // k == K: pieces no cell reads (uploaded last, nothing waits for them)
+    for (int q = 0; q < pp->P; ++q)
+      if (first[q] == k) pp->h2d_order.push_back(q);
+    if (k < pp->K) pp->h2d_upto[k] = int(pp->h2d_order.size());
+  }
+  for (int k = 0; k < pp->K; ++k) {
+    for (int q = 0; q < pp->P; ++q)
+      if (last[q] == k || (k == 0 && last[q] < 0)) pp->d2h_order.push_back(q);  // untouched pieces: zeros, after chunk 0
+    pp->d2h_upto[k] = int(pp->d2h_order.size());
+  }
+  pp->ev_in.resize(pp->K), pp->ev_k.resize(pp->K);
+  for (int k = 0; k < pp->K; ++k) {
+    cudaEventCreateWithFlags(&pp->ev_in[k], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&pp->ev_k[k], cudaEventDisableTiming);
+  }
+  f->pipe = pp;
+  return EO_OK;
+}
+
+static bool form_pipe_applies(eo_form* f, const void* in, const void* out, int accumulate, int64_t n_cells) {
+  static const bool enabled = form_env("EO_FORM_PIPE", 1) != 0;
+  return enabled && !accumulate && n_cells == f->tab->n_cells && n_cells >= (int64_t(1) << 17) && !eo_is_device_ptr(in) &&
+         !eo_is_device_ptr(out);
+}
+
+// launch(c0, c1, d_in, d_out) enqueues the kernel(s) for the cells [c0, c1) on ctx->s_cmp
+template <class Launch>
+static int form_pipelined(eo_form* f, const double* in_host, double* out_host, int64_t n_cells, Launch launch) {
+  eo_tab* t = f->tab;
+  eo_ctx* ctx = t->ctx;
+  if (!f->pipe || f->pipe->n_cells != n_cells) {
+    const int rc = form_pipe_build(f, n_cells);
+    if (rc != EO_OK) return rc;
+  }
+  form_pipe& pp = *f->pipe;
+  const int64_t nd = int64_t(t->n_dofs) * t->T.bs;
+  const size_t bytes = size_t(nd) * sizeof(double);
+  if (!t->u_stage[0]) EO_CUDA(ctx, cudaMalloc(&t->u_stage[0], bytes ? bytes : 8));
+  if (!f->y_stage) EO_CUDA(ctx, cudaMalloc(&f->y_stage, bytes ? bytes : 8));
+  double* d_in = t->u_stage[0];
+  double* d_out = f->y_stage;
+  auto piece_bytes = [&](int q) { return size_t((q + 1) * pp.piece <= nd ? pp.piece : nd - q * pp.piece) * sizeof(double); };
+  // the copy streams see everything queued on the compute stream so far
+  EO_CUDA(ctx, cudaEventRecord(ctx->ev_cmp[0], ctx->s_cmp));
+  EO_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_cmp[0], 0));
+  EO_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_cmp[0], 0));
+  EO_CUDA(ctx, cudaMemsetAsync(d_out, 0, bytes, ctx->s_cmp));
+  int up = 0, down = 0;
+  for (int k = 0; k < pp.K; ++k) {
+    for (; up < pp.h2d_upto[k]; ++up) {
+      const int q = pp.h2d_order[up];
+      EO_CUDA(ctx, cudaMemcpyAsync(d_in + q * pp.piece, in_host + q * pp.piece, piece_bytes(q), cudaMemcpyHostToDevice, ctx->s_in));
+    }
+    EO_CUDA(ctx, cudaEventRecord(pp.ev_in[k], ctx->s_in));
+    EO_CUDA(ctx, cudaStreamWaitEvent(ctx->s_cmp, pp.ev_in[k], 0));
+    if (pp.cell_lo[k + 1] > pp.cell_lo[k]) {
+      const int rc = launch(pp.cell_lo[k], pp.cell_lo[k + 1], (const double*)d_in, d_out);
+      if (rc != EO_OK) return rc;
+      EO_CUDA(ctx, cudaGetLastError());
+    }
+    EO_CUDA(ctx, cudaEventRecord(pp.ev_k[k], ctx->s_cmp));
+    EO_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, pp.ev_k[k], 0));
+    for (; down < pp.d2h_upto[k]; ++down) {
+      const int q = pp.d2h_order[down];
+      EO_CUDA(ctx, cudaMemcpyAsync(out_host + q * pp.piece, d_out + q * pp.piece, piece_bytes(q), cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+  }
+  for (; up < int(pp.h2d_order.size()); ++up) {  // pieces no cell reads: keep the staged copy complete
+    const int q = pp.h2d_order[up];
+    EO_CUDA(ctx, cudaMemcpyAsync(d_in + q * pp.piece, in_host + q * pp.piece, piece_bytes(q), cudaMemcpyHostToDevice, ctx->s_in));
+  }
+  EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_in));
+  EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_cmp));
+  EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
+  return EO_OK;
+}
+
 static int form_check_kind(eo_form* f, int kind, const char* what) {
   if (kind < 0 || kind > 3 || eo_tab_ncomp(f->tab, kind) <= 0)
     return eo_fail(f->tab->ctx, EO_ERR_INVALID, "%s: operand kind %d does not fit this element", what, kind);
@@ -656,6 +819,7 @@ int eo_form_create(eo_tab* tab, const double* weights, eo_form** out) {
 }
 
 int eo_form_destroy(eo_form* f) {
+  if (f) form_pipe_free(f->pipe), f->pipe = nullptr;
   if (!f) return EO_OK;
   cudaSetDevice(f->ctx->device);
   cudaStreamSynchronize(f->ctx->s_cmp);
@@ -716,36 +880,33 @@ int eo_form_action(eo_form* f, int kind_test, int kind_trial, const double* D, c
   EO_REQUIRE(ctx, x && y, "eo_form_action: NULL vector");
   EO_REQUIRE(ctx, n_cells == 0 || (D && eo_is_device_ptr(D)), "eo_form_action: the point values must be device memory");
   EO_CUDA(ctx, cudaSetDevice(ctx->device));
-  const double* d_x = nullptr;
-  rc = form_stage_x(f, x, &d_x);
-  if (rc != EO_OK) return rc;
-  double* d_y = nullptr;
-  rc = form_result(f, y, accumulate, &d_y);
-  if (rc != EO_OK) return rc;
-  EO_REQUIRE(ctx, d_x != d_y, "eo_form_action: x and y must not alias");
   const int kt = form_kind(kind_test), ki = form_kind(kind_trial);
-  if (n_cells > 0) {
-    form_weights W;
-    memcpy(W.w, f->w, sizeof(W.w));
+  form_weights W;
+  memcpy(W.w, f->w, sizeof(W.w));
+  const int64_t d_per_cell = int64_t(t->T.nq) * eo_tab_ncomp(t, kind_test) * eo_tab_ncomp(t, kind_trial);
+  // TMA-staged kernel for 4x4 tangents on 2-d vector fields: C_tang of the plasticity demos (Mandel strain both sides),
+  // dP/dF of the hyperelasticity demo (gradient both sides)   (EO_FORM_ACTION_TMA=0: register-path kernel, for A/B)
+  const bool tma = form_env("EO_FORM_ACTION_TMA", 1) && t->T.gdim == 2 && t->T.bs == 2 && t->T.nq == 3 && kt != 0 && ki != 0 &&
+                   eo_aligned(D, 32);
+  // the cells [c0, c1): every per-cell / per-point array is addressed relative to c0
+  auto launch = [&](int64_t c0, int64_t c1, const double* dx, double* dy) -> int {
+    const int64_t m = c1 - c0;
+    const double* Dc = D + c0 * d_per_cell;
     bool done = false;
-    // TMA-staged kernel for 4x4 tangents on 2-d vector fields: C_tang of the plasticity demos (Mandel strain both sides),
-    // dP/dF of the hyperelasticity demo (gradient both sides)   (EO_FORM_ACTION_TMA=0: register-path kernel, for A/B)
-    const bool tma = form_env("EO_FORM_ACTION_TMA", 1) && t->T.gdim == 2 && t->T.bs == 2 && t->T.nq == 3 && kt != 0 && ki != 0 &&
-                     eo_aligned(D, 32);
-    const unsigned gc = (unsigned)((n_cells + 127) / 128);
+    const unsigned gc = (unsigned)((m + 127) / 128);
 #define X(G, B, N)                                                                                                       \
   if (!done && t->T.gdim == G && t->T.bs == B && t->T.nb == N) {                                                         \
-    if (tma) {                                                                                                    \
+    const int32_t* dm = t->dofmap + c0 * N;                                                                              \
+    const int32_t* xd = t->x_dofmap + c0 * (G + 1);                                                                      \
+    if (tma) {                                                                                                           \
       const size_t sm = 128 + 128 * (3 * 128 + 16);                                                                      \
       auto kfn = form_action_tma_kernel<(G == 2 && B == 2 ? N : 3), 3>;                                                  \
       cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm));                                   \
-      kfn<<<gc, 128, sm, ctx->s_cmp>>>(t->T, W, kt, ki, t->dofmap, t->x_dofmap, t->x, D, d_x, n_cells, d_y);             \
+      kfn<<<gc, 128, sm, ctx->s_cmp>>>(t->T, W, kt, ki, dm, xd, t->x, Dc, dx, m, dy);                                    \
     } else if (t->T.nq == 3) {                                                                                           \
-      form_action_cell_kernel<G, B, N, 3><<<gc, 128, 0, ctx->s_cmp>>>(t->T, W, kt, ki, t->dofmap, t->x_dofmap, t->x, D,   \
-                                                                      d_x, n_cells, d_y);                                \
+      form_action_cell_kernel<G, B, N, 3><<<gc, 128, 0, ctx->s_cmp>>>(t->T, W, kt, ki, dm, xd, t->x, Dc, dx, m, dy);     \
     } else {                                                                                                             \
-      form_action_cell_kernel<G, B, N, 0><<<gc, 128, 0, ctx->s_cmp>>>(t->T, W, kt, ki, t->dofmap, t->x_dofmap, t->x, D,   \
-                                                                      d_x, n_cells, d_y);                                \
+      form_action_cell_kernel<G, B, N, 0><<<gc, 128, 0, ctx->s_cmp>>>(t->T, W, kt, ki, dm, xd, t->x, Dc, dx, m, dy);     \
     }                                                                                                                    \
     done = true;                                                                                                         \
   }
@@ -753,6 +914,19 @@ int eo_form_action(eo_form* f, int kind_test, int kind_trial, const double* D, c
 #undef X
     if (!done) return eo_fail(ctx, EO_ERR_UNSUPPORTED, "eo_form_action: no kernel for this element");
     ctx->launches += 1;
+    return EO_OK;
+  };
+  if (n_cells > 0 && form_pipe_applies(f, x, y, accumulate, n_cells)) return form_pipelined(f, x, y, n_cells, launch);
+  const double* d_x = nullptr;
+  rc = form_stage_x(f, x, &d_x);
+  if (rc != EO_OK) return rc;
+  double* d_y = nullptr;
+  rc = form_result(f, y, accumulate, &d_y);
+  if (rc != EO_OK) return rc;
+  EO_REQUIRE(ctx, d_x != d_y, "eo_form_action: x and y must not alias");
+  if (n_cells > 0) {
+    rc = launch(0, n_cells, d_x, d_y);
+    if (rc != EO_OK) return rc;
   }
   return form_finish(f, y, d_y);
 }
@@ -775,37 +949,42 @@ int eo_form_vm_step(eo_form* f, const eo_vm_params* prm, const double* u, const 
   EO_REQUIRE(ctx, eo_aligned(sigma_n, 32) && eo_aligned(C_tang, 32) && eo_aligned(sigma, 32),
              "eo_form_vm_step: arrays must be 32-byte aligned");
   EO_CUDA(ctx, cudaSetDevice(ctx->device));
-  const double* d_u = nullptr;
-  int rc = eo_tab_stage_u(t, u, &d_u);
-  if (rc != EO_OK) return rc;
-  double* d_b = nullptr;
-  rc = form_result(f, b, accumulate, &d_b);
-  if (rc != EO_OK) return rc;
-  if (n_cells > 0) {
-    const vm_consts q{prm->lmbda, prm->mu, prm->H, prm->sigma_0};
-    const unsigned grid = form_grid(ctx, t, n_cells);
-    form_weights W;
-    memcpy(W.w, f->w, sizeof(W.w));
-#define EO_STEP(N)                                                                                                        \
-  if (t->T.nb == N) {                                                                                                     \
-    if (exact) {                                                                                                          \
-      const size_t sm = form_smem(ctx, form_vm_step_kernel<N, true>, N * 2);                                              \
-      form_vm_step_kernel<N, true><<<grid, FORM_THREADS, sm, ctx->s_cmp>>>(t->T, W, q, t->dofmap, t->x_dofmap, t->x, d_u,  \
-                                                                           n_cells, sigma_n, p, C_tang, sigma, dp, d_b,   \
-                                                                           ctx->stats);                                   \
-    } else {                                                                                                              \
-      const size_t sm = form_smem(ctx, form_vm_step_kernel<N, false>, N * 2);                                             \
-      form_vm_step_kernel<N, false><<<grid, FORM_THREADS, sm, ctx->s_cmp>>>(t->T, W, q, t->dofmap, t->x_dofmap, t->x, d_u, \
-                                                                            n_cells, sigma_n, p, C_tang, sigma, dp, d_b,  \
-                                                                            ctx->stats);                                  \
-    }                                                                                                                     \
+  const vm_consts q{prm->lmbda, prm->mu, prm->H, prm->sigma_0};
+  form_weights W;
+  memcpy(W.w, f->w, sizeof(W.w));
+  // the cells [c0, c1): every per-cell / per-point array is addressed relative to c0
+  auto launch = [&](int64_t c0, int64_t c1, const double* du, double* db) -> int {
+    const int64_t m = c1 - c0, o = c0 * t->T.nq;
+    const unsigned grid = form_grid(ctx, t, m);
+#define EO_STEP(N)                                                                                                          \
+  if (t->T.nb == N) {                                                                                                       \
+    if (exact) {                                                                                                            \
+      const size_t sm = form_smem(ctx, form_vm_step_kernel<N, true>, N * 2);                                                \
+      form_vm_step_kernel<N, true><<<grid, FORM_THREADS, sm, ctx->s_cmp>>>(                                                 \
+          t->T, W, q, t->dofmap + c0 * N, t->x_dofmap + c0 * 3, t->x, du, m, sigma_n + 4 * o, p + o, C_tang + 16 * o,       \
+          sigma + 4 * o, dp + o, db, ctx->stats);                                                                           \
+    } else {                                                                                                                \
+      const size_t sm = form_smem(ctx, form_vm_step_kernel<N, false>, N * 2);                                               \
+      form_vm_step_kernel<N, false><<<grid, FORM_THREADS, sm, ctx->s_cmp>>>(                                                \
+          t->T, W, q, t->dofmap + c0 * N, t->x_dofmap + c0 * 3, t->x, du, m, sigma_n + 4 * o, p + o, C_tang + 16 * o,       \
+          sigma + 4 * o, dp + o, db, ctx->stats);                                                                           \
+    }                                                                                                                       \
   }
     EO_STEP(3)
     EO_STEP(6)
     EO_STEP(10)
 #undef EO_STEP
     ctx->launches += 1;
-  }
+    return EO_OK;
+  };
+  if (n_cells > 0 && form_pipe_applies(f, u, b, accumulate, n_cells)) return form_pipelined(f, u, b, n_cells, launch);
+  const double* d_u = nullptr;
+  int rc = eo_tab_stage_u(t, u, &d_u);
+  if (rc != EO_OK) return rc;
+  double* d_b = nullptr;
+  rc = form_result(f, b, accumulate, &d_b);
+  if (rc != EO_OK) return rc;
+  if (n_cells > 0) launch(0, n_cells, d_u, d_b);
   return form_finish(f, b, d_b);
 }
 
