@@ -958,9 +958,10 @@ def main():
                          "(torchrun's own parser rejects --n as an ambiguous abbreviation)")
     ap.add_argument("--e2e-n", type=float, default=1.5e7, help="quadrature points per GPU for the end-to-end leg")
     ap.add_argument("--state-layout", default="aos", choices=["aos", "soa"])
-    ap.add_argument("--mesh-order", default="structured", choices=["structured", "shuffled", "rcm"],
+    ap.add_argument("--mesh-order", default="structured", choices=["structured", "shuffled", "rcm", "morton"],
                     help="numbering of cells / dofs / nodes of the synthetic mesh (tab, fused, step, action): the row-major "
-                         "structured numbering, a random permutation, or reverse Cuthill-McKee of a shuffled mesh")
+                         "structured numbering, a random permutation, reverse Cuthill-McKee of a shuffled mesh, or a Z-order "
+                         "space-filling curve (cheap enough for 10^7 cells)")
     ap.add_argument("--cpu-sample", type=float, default=4e6)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--models", default="mc,heat,tab,fused,step,action,isihara",

@@ -152,7 +152,7 @@ def test_p2_tetrahedra_reproduce_quadratic_fields(hc):
     np.testing.assert_allclose(_hc_tab(hc, m, ot.DEF_GRAD, u, 3, 3, 9), F, rtol=0, atol=1e-12 * np.abs(F).max())
 
 
-@pytest.mark.parametrize("order", ["shuffled", "rcm"])
+@pytest.mark.parametrize("order", ["shuffled", "rcm", "morton"])
 def test_renumbered_mesh_is_the_same_mesh(order):
     """synthetic.renumber permutes cells / dofs / nodes consistently: the oracle returns the same per-cell values in the
     new cell order, and RCM restores locality (small dof spread per cell) where the shuffle destroys it."""
@@ -168,5 +168,5 @@ def test_renumbered_mesh_is_the_same_mesh(order):
     assert np.array_equal(b, a[r["cell_old"]])
     assert sorted(r["dof_new"]) == list(range(m["n_dofs"])) and sorted(r["cell_old"]) == list(range(m["dofmap"].shape[0]))
     spread = lambda d: (d.max(axis=1) - d.min(axis=1)).mean()  # noqa: E731
-    if order == "rcm":
+    if order in ("rcm", "morton"):
         assert spread(r["dofmap"]) < 0.5 * spread(syn.renumber(m, "shuffled", seed=2)["dofmap"])
