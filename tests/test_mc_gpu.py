@@ -120,6 +120,7 @@ def test_mc_demo_tracing_path(ctx):
     it, cnt = np.unique(o["niter"], return_counts=True)
     assert dict(zip(it.tolist(), cnt.tolist())) == {1: 276, 2: 99, 3: 57, 4: 15, 5: 3}
     _check(o, native.mc_return_mapping(d, s, PRM, parallel=True), d, s)
+    check_mc_exact(o, d, s, PRM)  # the path ends in the hexagon corners: flat 1e-10 against the exact value there too
     # returned plastic stresses lie on the yield surface
     pl = o["yielding"] > 0
     assert np.abs(native.mc_yield(o["sigma"][pl], PRM)).max() < 1e-6
