@@ -803,10 +803,11 @@ static int mc_launch_newton(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, c
 template <bool ASSOC>
 static int mc_launch_classes(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, int64_t n) {
   // EO_MC_CONFIG selects the CTA shape of pass 2 for A/B runs: 0 = 12 warps x 512 slots, 1 = 16 warps (128 registers) x
-  // 512 slots, 2 = 16 warps x 576 slots (associative flow rule only: 51 fields per slot do not fit otherwise)
+  // 512 slots, 2 = 16 warps x 576 slots, 3 = 12 warps x 576 slots (associative flow rule only: 51 fields per slot do not
+  // fit otherwise)
   static const int cfg = [] {
     const char* e = getenv("EO_MC_CONFIG");
-    return (e && *e >= '0' && *e <= '2') ? *e - '0' : MCN_DEFAULT_CONFIG;
+    return (e && *e >= '0' && *e <= '3') ? *e - '0' : MCN_DEFAULT_CONFIG;
   }();
   if (n > 2147483647LL) return eo_fail(ctx, EO_ERR_INVALID, "eo_mc_eval: n too large for one launch");
   void* sc = nullptr;
@@ -816,7 +817,8 @@ static int mc_launch_classes(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, 
   int32_t* list = reinterpret_cast<int32_t*>(sc);
   double* list_yl = reinterpret_cast<double*>(reinterpret_cast<char*>(sc) + yl_off);
   mc_trial_kernel<ASSOC><<<unsigned((n + 255) / 256), 256, 0, ctx->s_cmp>>>(k, P, n, ctx->stats, ctx->work_ctr, list, list_yl);
-  if (cfg == 2 && ASSOC) rc = mc_launch_newton<ASSOC, 16, ASSOC ? 18 : 16>(ctx, k, P, list, list_yl);
+  if (cfg == 3 && ASSOC) rc = mc_launch_newton<ASSOC, 12, ASSOC ? 18 : 16>(ctx, k, P, list, list_yl);
+  else if (cfg == 2 && ASSOC) rc = mc_launch_newton<ASSOC, 16, ASSOC ? 18 : 16>(ctx, k, P, list, list_yl);
   else if (cfg >= 1) rc = mc_launch_newton<ASSOC, 16, 16>(ctx, k, P, list, list_yl);
   else rc = mc_launch_newton<ASSOC, 12, 16>(ctx, k, P, list, list_yl);
   if (rc != EO_OK) return rc;
