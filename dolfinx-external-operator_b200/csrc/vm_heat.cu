@@ -10,6 +10,8 @@
 #include "eo_common.cuh"
 #include "vm_core.cuh"
 
+#include <cstdlib>
+
 // ------------------------------------------------------------------------------------------
 // von Mises                                   (reference: demo_plasticity_von_mises.py:307-326)
 // ------------------------------------------------------------------------------------------
@@ -72,6 +74,47 @@ __global__ void __launch_bounds__(256) vm_kernel(vm_consts q, const double* __re
     atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_points), (unsigned long long)n);
 }
 
+// SoA history with 256-bit accesses: a thread owns FOUR consecutive points, so component c of its points is one
+// 32-byte load from the SoA plane c (a warp instruction covers 1 KB of consecutive sectors, like the AoS kernel) and
+// the register file does the transposition for free.  Strain and tangent stay in the reference's AoS layout (one
+// 256-bit access per point and row).  Points are processed one after the other, the tangent leaves at once; only the
+// new stress and dp of the four points (20 doubles) are held for the SoA stores.  Needs n % 4 == 0 (32-byte aligned
+// planes); otherwise the 8-byte SoA kernel above runs.
+__global__ void __launch_bounds__(128) vm_soa4_kernel(vm_consts q, const double* __restrict__ deps,
+                                                      const double* __restrict__ sigma_n, const double* __restrict__ p,
+                                                      double* __restrict__ C_tang, double* __restrict__ sigma,
+                                                      double* __restrict__ dp_out, int64_t n, eo_stats* stats) {
+  const int64_t g = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;  // group of four points
+  int plastic = 0;
+  if (4 * g < n) {
+    const int64_t i0 = 4 * g;
+    const eo_d4 s0 = eo_ld256(sigma_n + i0), s1 = eo_ld256(sigma_n + n + i0), s2 = eo_ld256(sigma_n + 2 * n + i0),
+                s3 = eo_ld256(sigma_n + 3 * n + i0), pp = eo_ld256(p + i0);
+    const double sn[4][4] = {{s0.x, s1.x, s2.x, s3.x}, {s0.y, s1.y, s2.y, s3.y}, {s0.z, s1.z, s2.z, s3.z}, {s0.w, s1.w, s2.w, s3.w}};
+    const double pj[4] = {pp.x, pp.y, pp.z, pp.w};
+    double gs[4][4], dpj[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const eo_d4 e = eo_ld256(deps + 4 * (i0 + j));
+      vm_point_out o;
+      vm_point(q, e.x, e.y, e.z, e.w, sn[j][0], sn[j][1], sn[j][2], sn[j][3], pj[j], o);
+      plastic += o.dp > 0.0;
+      double* Ct = C_tang + 16 * (i0 + j);
+      eo_st256(Ct + 0, o.C[0], o.C[1], o.C[2], o.C[3]);
+      eo_st256(Ct + 4, o.C[4], o.C[5], o.C[6], o.C[7]);
+      eo_st256(Ct + 8, o.C[8], o.C[9], o.C[10], o.C[11]);
+      eo_st256(Ct + 12, o.C[12], o.C[13], o.C[14], o.C[15]);
+      gs[j][0] = o.g[0], gs[j][1] = o.g[1], gs[j][2] = o.g[2], gs[j][3] = o.g[3], dpj[j] = o.dp;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) eo_st256(sigma + c * n + i0, gs[0][c], gs[1][c], gs[2][c], gs[3][c]);
+    eo_st256(dp_out + i0, dpj[0], dpj[1], dpj[2], dpj[3]);
+  }
+  eo_block_sum_add(reinterpret_cast<unsigned long long*>(&stats->n_plastic), plastic);
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_points), (unsigned long long)n);
+}
+
 static int vm_launch(eo_ctx* ctx, const eo_vm_params* prm, const double* deps, const double* sigma_n, const double* p,
                      double* C_tang, double* sigma, double* dp, int64_t n, int layout) {
   vm_consts q{prm->lmbda, prm->mu, prm->H, prm->sigma_0};
@@ -81,7 +124,12 @@ static int vm_launch(eo_ctx* ctx, const eo_vm_params* prm, const double* deps, c
   const int64_t grid64 = (n + block - 1) / block;
   if (grid64 > 2147483647LL) return eo_fail(ctx, EO_ERR_INVALID, "eo_vm_eval: n too large for one launch");
   const unsigned grid = (unsigned)grid64;
-  if (layout == EO_LAYOUT_SOA) {
+  static const bool soa4 = [] { const char* e = getenv("EO_VM_SOA4"); return !(e && *e == '0'); }();
+  if (layout == EO_LAYOUT_SOA && soa4 && vec && n % 4 == 0 && eo_aligned(sigma_n, 32) && eo_aligned(sigma, 32) &&
+      eo_aligned(p, 32) && eo_aligned(dp, 32)) {
+    const int64_t groups = n / 4;
+    vm_soa4_kernel<<<(unsigned)((groups + 127) / 128), 128, 0, ctx->s_cmp>>>(q, deps, sigma_n, p, C_tang, sigma, dp, n, ctx->stats);
+  } else if (layout == EO_LAYOUT_SOA) {
     if (vec)
       vm_kernel<true, EO_LAYOUT_SOA><<<grid, block, 0, ctx->s_cmp>>>(q, deps, sigma_n, p, C_tang, sigma, dp, n, ctx->stats);
     else

@@ -104,16 +104,16 @@ def test_vm_host_pipeline_many_chunks_and_mixed_sides(ctx):
         ctx.set_chunk(1 << 20)
 
 
+@pytest.mark.parametrize("n", [3 * 4001, 4 * 3001])  # n % 4 == 0: the SoA layout takes the 4-points-per-thread kernel
 @pytest.mark.parametrize("layout", ["aos", "soa"])
-def test_vm_model_callable_resident_history_and_commit(ctx, layout):
-    n = 3 * 4001
+def test_vm_model_callable_resident_history_and_commit(ctx, layout, n):
     deps, sn, p = inputs.vm_batch(n, seed=2)
     vm = eo.VonMises(ctx=ctx, state_layout=layout)
     vm.set_history(sn, p)
     with pytest.raises(NotImplementedError):
         vm((0,))
     ctx.stats_reset()
-    Ct, sig, dp = vm((1,))(deps.reshape(-1, 3, 4))
+    Ct, sig, dp = vm((1,))(deps.reshape(-1, 1, 4))
     rC, rs, rdp = native.vm_return_mapping(deps, sn, p, PRM)
     assert Ct.shape == (16 * n,) and sig.shape == (4 * n,) and dp.shape == (n,)
     assert np.array_equal(Ct, rC.reshape(-1)) and np.array_equal(sig, rs.reshape(-1)) and np.array_equal(dp, rdp)
@@ -124,7 +124,7 @@ def test_vm_model_callable_resident_history_and_commit(ctx, layout):
     sn2, p2 = vm.get_history()
     assert np.array_equal(sn2, rs.reshape(-1)) and np.array_equal(p2, p + 1.0 * rdp)
     # second increment from the committed state
-    Ct_b, sig_b, dp_b = vm((1,))(deps.reshape(-1, 3, 4))
+    Ct_b, sig_b, dp_b = vm((1,))(deps.reshape(-1, 1, 4))
     rC2, rs2, rdp2 = native.vm_return_mapping(deps, rs, p + rdp, PRM)
     assert np.array_equal(sig_b, rs2.reshape(-1)) and np.array_equal(dp_b, rdp2) and np.array_equal(Ct_b, rC2.reshape(-1))
 
