@@ -80,6 +80,22 @@ __global__ void __launch_bounds__(256) eo_fp32_peak3_kernel(float* out, int iter
   out[blockIdx.x * size_t(blockDim.x) + threadIdx.x] = s;
 }
 
+// variant 3: one uniform operand (kernel parameter -> constant bank / uniform register), two per-chain registers:
+// acc = fma(z, w_uniform, acc) - the shape of a matrix-vector product whose weights are warp uniform
+__global__ void __launch_bounds__(256) eo_fp32_peak_u1_kernel(float* out, int iters, float b0, float c0) {
+  float a[8], z[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = threadIdx.x + k, z[k] = c0 * (k + 1) + 1e-7f * threadIdx.x;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = fmaf(z[k], b0, a[k]);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += a[k];
+  out[blockIdx.x * size_t(blockDim.x) + threadIdx.x] = s;
+}
+
 // variant 2: packed FFMA2 (fma.rn.f32x2), 8 independent chains of register pairs = 16 FMAs per trip
 __global__ void __launch_bounds__(256) eo_fp32_peak2x_kernel(float* out, int iters, float b0, float c0) {
   float2 a[8], b[8], c[8];
@@ -507,7 +523,7 @@ int eo_fp64_peak(eo_ctx* ctx, int iters, double* tflops) {
 }
 
 int eo_fp32_peak_variant(eo_ctx* ctx, int iters, int variant, double* tflops) {
-  EO_REQUIRE(ctx, ctx && tflops && iters > 0 && variant >= 0 && variant <= 2, "eo_fp32_peak_variant: bad argument");
+  EO_REQUIRE(ctx, ctx && tflops && iters > 0 && variant >= 0 && variant <= 3, "eo_fp32_peak_variant: bad argument");
   EO_CUDA(ctx, cudaSetDevice(ctx->device));
   const int grid = ctx->sm_count * 8, block = 256;
   float* out = nullptr;
@@ -520,6 +536,7 @@ int eo_fp32_peak_variant(eo_ctx* ctx, int iters, int variant, double* tflops) {
     EO_CUDA(ctx, cudaEventRecord(e0, ctx->s_cmp));
     if (variant == 0) eo_fp32_peak_kernel<<<grid, block, 0, ctx->s_cmp>>>(out, iters, 0.999999f, 1e-6f);
     else if (variant == 1) eo_fp32_peak3_kernel<<<grid, block, 0, ctx->s_cmp>>>(out, iters, 0.999999f, 1e-6f);
+    else if (variant == 3) eo_fp32_peak_u1_kernel<<<grid, block, 0, ctx->s_cmp>>>(out, iters, 0.999999f, 1e-6f);
     else eo_fp32_peak2x_kernel<<<grid, block, 0, ctx->s_cmp>>>(out, iters, 0.999999f, 1e-6f);
     EO_CUDA(ctx, cudaEventRecord(e1, ctx->s_cmp));
     EO_CUDA(ctx, cudaEventSynchronize(e1));

@@ -123,7 +123,8 @@ int eo_fp64_peak(eo_ctx* ctx, int iters, double* tflops);
 int eo_fp32_peak(eo_ctx* ctx, int iters, double* tflops);
 /* FP32 FMA throughput by instruction form: variant 0 = scalar FFMA with uniform multiplier / addend (what eo_fp32_peak
  * runs), 1 = scalar FFMA with three per-chain register operands, 2 = packed FFMA2 (fma.rn.f32x2, two FMAs per
- * instruction) with register-pair operands. */
+ * instruction) with register-pair operands, 3 = scalar FFMA with ONE uniform operand and two registers (the shape of a
+ * matrix-vector product with warp-uniform weights). */
 int eo_fp32_peak_variant(eo_ctx* ctx, int iters, int variant, double* tflops);
 
 /* ---------------------------------------------------------------- statistics
