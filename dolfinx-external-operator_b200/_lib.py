@@ -173,6 +173,7 @@ PROTOTYPES = {
     "eo_jit_compile_tabulated": (C.c_int, [_vp, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                            C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     "eo_mc_eval": (C.c_int, [_vp, C.POINTER(McParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
+    "eo_mc_eval_tabulated": (C.c_int, [_vp, C.POINTER(McParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "eo_mc_eval_scheme": (C.c_int, [_vp, C.POINTER(McParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_int]),
 }
 

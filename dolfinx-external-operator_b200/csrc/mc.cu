@@ -25,6 +25,8 @@
 // flushed once per CTA into the context's eo_stats record.
 #include "eo_common.cuh"
 #include "mc_core.cuh"
+#include "tab_core.cuh"
+#include "tab_handle.cuh"
 
 #define MC_THREADS 384   // 12 warps, one CTA per SM
 #define MC_NSLOTS 512    // state slots per CTA (power of two: ring-buffer arithmetic)
@@ -421,11 +423,32 @@ __global__ void __launch_bounds__(MC_THREADS, 1) mc_kernel(const mc_consts k, co
 // yield test (:421-422); elastic points are finished here, plastic points are appended (warp-aggregated) to a list
 // that mc_kernel<.., LISTED> works off.  The long dependent FP64 chain of the yield test (asin, sincos, sqrt) is
 // latency-bound at the 12 warps/SM of the persistent kernel; here 8x more warps hide it.
-template <bool ASSOC>
-__global__ void __launch_bounds__(256, 4) mc_trial_kernel(const mc_consts k, const mc_ptrs P, const int64_t n,
+// NB > 0: the strain increment is not read but TABULATED here - Mandel strain of the P1/P2/P3 vector field `src.u` at this
+// thread's point (cell = i / nq), like tab_vm_kernel - and, for plastic points only, stored next to the list entry
+// (`list_deps`), where pass 2 picks it up: the strain array of the whole mesh is never written (eo_mc_eval_tabulated).
+struct mc_tab_src {
+  const int32_t* dofmap;
+  const int32_t* x_dofmap;
+  const double* x;
+  const double* u;
+};
+
+template <bool ASSOC, int NB>
+__global__ void __launch_bounds__(256, NB > 0 ? 3 : 4) mc_trial_kernel(const mc_consts k, const mc_ptrs P, const int64_t n,
                                                        eo_stats* __restrict__ stats, unsigned int* ctr,
-                                                       int32_t* __restrict__ list, double* __restrict__ list_yl) {
+                                                       int32_t* __restrict__ list, double* __restrict__ list_yl,
+                                                       const tab_tables* __restrict__ T, const mc_tab_src src,
+                                                       double* __restrict__ list_deps) {
   __shared__ unsigned int s_hist0, s_hist1, s_histx, s_nonfinite;
+  __shared__ double s_dphi[NB > 0 ? EO_TAB_MAX_NQ : 1][2][NB > 0 ? NB : 1];
+  __shared__ double s_dpsi[2][3];
+  if (NB > 0) {
+    for (int t = threadIdx.x; t < T->nq * 2 * NB; t += blockDim.x) {
+      const int q = t / (2 * NB), kk = (t / NB) % 2, a = t % NB;
+      s_dphi[q][kk][a] = T->dphi[kk][q][a];
+    }
+    if (threadIdx.x < 6) s_dpsi[threadIdx.x / 3][threadIdx.x % 3] = T->dpsi[threadIdx.x / 3][threadIdx.x % 3];
+  }
   if (threadIdx.x == 0) s_hist0 = s_hist1 = s_histx = s_nonfinite = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -434,10 +457,49 @@ __global__ void __launch_bounds__(256, 4) mc_trial_kernel(const mc_consts k, con
   int max_it = 0;
   bool plastic = false;
   double yl = 0.0;
+  double de[4] = {0.0, 0.0, 0.0, 0.0};
   if (i < n) {
-    const eo_d4 e = eo_ld256(P.deps + 4 * i);
     const eo_d4 sg = eo_ld256(P.sigma_n + 4 * i);
-    const double de[4] = {e.x, e.y, e.z, e.w}, sn[4] = {sg.x, sg.y, sg.z, sg.w};
+    if (NB > 0) {
+      const int nq = T->nq;
+      const int64_t c = i / nq;
+      const int q = int(i - c * nq);
+      double w[NB > 0 ? NB : 1][2], xv[3][2], J[2][2], K[2][2];
+#pragma unroll
+      for (int a = 0; a < NB; ++a) {
+        const double2 v = __ldg(reinterpret_cast<const double2*>(src.u) + __ldg(src.dofmap + c * NB + a));
+        w[a][0] = v.x, w[a][1] = v.y;
+      }
+#pragma unroll
+      for (int v = 0; v < 3; ++v) {
+        const int64_t node = __ldg(src.x_dofmap + c * 3 + v);
+        xv[v][0] = __ldg(src.x + 3 * node), xv[v][1] = __ldg(src.x + 3 * node + 1);
+      }
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) J[a][b] = xv[0][a] * s_dpsi[b][0] + xv[1][a] * s_dpsi[b][1] + xv[2][a] * s_dpsi[b][2];
+      tab_inverse<2>(J, K);
+      double G[2][2], grad[2][2], val[2] = {0.0, 0.0};
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          double acc = 0.0;
+#pragma unroll
+          for (int a = 0; a < NB; ++a) acc += w[a][cc] * s_dphi[q][kk][a];
+          G[cc][kk] = acc;
+        }
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) grad[cc][j] = G[cc][0] * K[0][j] + G[cc][1] * K[1][j];
+      tab_operand<2, 2>(2, val, grad, de);
+    } else {
+      const eo_d4 e = eo_ld256(P.deps + 4 * i);
+      de[0] = e.x, de[1] = e.y, de[2] = e.z, de[3] = e.w;
+    }
+    const double sn[4] = {sg.x, sg.y, sg.z, sg.w};
     double Cde[4];
     yl = mc_trial(k, de, sn, Cde);
     max_f = yl;
@@ -486,6 +548,7 @@ __global__ void __launch_bounds__(256, 4) mc_trial_kernel(const mc_consts k, con
     const unsigned int pos = s_wbase[warp] + __popc(pm & ((1u << lane) - 1u));
     list[pos] = (int32_t)i;
     list_yl[pos] = yl;
+    if (NB > 0) eo_st256(list_deps + 4 * size_t(pos), de[0], de[1], de[2], de[3]);
   }
   if (threadIdx.x == 32) {  // a thread of another warp than the one that reserved the list space
     // the maxima saturate after a few CTAs: look first (three independent loads), reduce only what raises a maximum
@@ -534,7 +597,8 @@ struct mcn_policy {
 template <bool ASSOC, int NWARPS, int DEPTH>
 __global__ void __launch_bounds__(NWARPS * 32, 1) mc_newton_kernel(const mc_consts k, const mc_ptrs P, eo_stats* __restrict__ stats,
                                                                    unsigned int* ctr, const int32_t* __restrict__ list,
-                                                                   const double* __restrict__ list_yl, const mcn_policy pol) {
+                                                                   const double* __restrict__ list_yl, const mcn_policy pol,
+                                                                   const double* __restrict__ list_deps) {
   constexpr int NSLOT = 32 * DEPTH;
   constexpr unsigned ALL = DEPTH == 32 ? 0xffffffffu : ((1u << DEPTH) - 1u);
   const int64_t n = (int64_t)ctr[MC_CTR_LIST];
@@ -653,7 +717,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) mc_newton_kernel(const mc_cons
         const int64_t e = e0 + rank;
         const double yl = list_yl[e];
         const int i = list[e];
-        const eo_d4 de4 = eo_ld256(P.deps + 4 * (int64_t)i);
+        const eo_d4 de4 = list_deps ? eo_ld256(list_deps + 4 * e) : eo_ld256(P.deps + 4 * (int64_t)i);
         const eo_d4 sg = eo_ld256(P.sigma_n + 4 * (int64_t)i);
         const double de[4] = {de4.x, de4.y, de4.z, de4.w}, sn[4] = {sg.x, sg.y, sg.z, sg.w};
         double Cde[4];
@@ -773,7 +837,8 @@ static int mc_launch_queue(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, in
     if (rc != EO_OK) return rc;
     list = reinterpret_cast<int32_t*>(sc);
     list_yl = reinterpret_cast<double*>(reinterpret_cast<char*>(sc) + yl_off);
-    mc_trial_kernel<ASSOC><<<unsigned((n + 255) / 256), 256, 0, ctx->s_cmp>>>(k, P, n, ctx->stats, ctx->work_ctr, list, list_yl);
+    mc_trial_kernel<ASSOC, 0><<<unsigned((n + 255) / 256), 256, 0, ctx->s_cmp>>>(k, P, n, ctx->stats, ctx->work_ctr, list, list_yl,
+                                                                                   nullptr, mc_tab_src{}, nullptr);
     ctx->launches += 1;
     grid = (unsigned)ctx->sm_count;  // the list length is only known on the device
   }
@@ -783,7 +848,8 @@ static int mc_launch_queue(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, in
 
 // default scheme: pass 1 (mc_trial_kernel) + the lane-class Newton kernel over the plastic list
 template <bool ASSOC, int NWARPS, int DEPTH>
-static int mc_launch_newton(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, const int32_t* list, const double* list_yl) {
+static int mc_launch_newton(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, const int32_t* list, const double* list_yl,
+                            const double* list_deps) {
   const size_t smem = size_t(ASSOC ? MC_NF_ASSOC : MC_NF) * (32 * DEPTH) * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
@@ -796,12 +862,16 @@ static int mc_launch_newton(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, c
     if (const char* e = getenv("EO_MC_POLICY")) sscanf(e, "%d,%d,%d,%u", &p.full, &p.min_active, &p.first_last, &p.sleep_ns);
     return p;
   }();
-  mc_newton_kernel<ASSOC, NWARPS, DEPTH><<<(unsigned)ctx->sm_count, NWARPS * 32, smem, ctx->s_cmp>>>(k, P, ctx->stats, ctx->work_ctr, list, list_yl, pol);
+  mc_newton_kernel<ASSOC, NWARPS, DEPTH><<<(unsigned)ctx->sm_count, NWARPS * 32, smem, ctx->s_cmp>>>(k, P, ctx->stats, ctx->work_ctr, list, list_yl, pol,
+                                                                                                   list_deps);
   return EO_OK;
 }
 
+// default scheme: pass 1 (mc_trial_kernel) + the lane-class Newton kernel over the plastic list.  tab != nullptr: the
+// strain increment is tabulated inside pass 1 from the coefficient vector d_u (eo_mc_eval_tabulated).
 template <bool ASSOC>
-static int mc_launch_classes(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, int64_t n) {
+static int mc_launch_classes(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, int64_t n, eo_tab* tab = nullptr,
+                             const double* d_u = nullptr) {
   // EO_MC_CONFIG selects the CTA shape of pass 2 for A/B runs: 0 = 12 warps x 512 slots, 1 = 16 warps (128 registers) x
   // 512 slots, 2 = 16 warps x 576 slots, 3 = 12 warps x 576 slots (associative flow rule only: 51 fields per slot do not
   // fit otherwise)
@@ -812,15 +882,25 @@ static int mc_launch_classes(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, 
   if (n > 2147483647LL) return eo_fail(ctx, EO_ERR_INVALID, "eo_mc_eval: n too large for one launch");
   void* sc = nullptr;
   const size_t yl_off = (size_t(n) * 4 + 255) / 256 * 256;
-  int rc = eo_scratch(ctx, yl_off + size_t(n) * 8, &sc);
+  const size_t de_off = yl_off + (size_t(n) * 8 + 255) / 256 * 256;
+  int rc = eo_scratch(ctx, tab ? de_off + size_t(n) * 32 : yl_off + size_t(n) * 8, &sc);
   if (rc != EO_OK) return rc;
   int32_t* list = reinterpret_cast<int32_t*>(sc);
   double* list_yl = reinterpret_cast<double*>(reinterpret_cast<char*>(sc) + yl_off);
-  mc_trial_kernel<ASSOC><<<unsigned((n + 255) / 256), 256, 0, ctx->s_cmp>>>(k, P, n, ctx->stats, ctx->work_ctr, list, list_yl);
-  if (cfg == 3 && ASSOC) rc = mc_launch_newton<ASSOC, 12, ASSOC ? 18 : 16>(ctx, k, P, list, list_yl);
-  else if (cfg == 2 && ASSOC) rc = mc_launch_newton<ASSOC, 16, ASSOC ? 18 : 16>(ctx, k, P, list, list_yl);
-  else if (cfg >= 1) rc = mc_launch_newton<ASSOC, 16, 16>(ctx, k, P, list, list_yl);
-  else rc = mc_launch_newton<ASSOC, 12, 16>(ctx, k, P, list, list_yl);
+  double* list_deps = tab ? reinterpret_cast<double*>(reinterpret_cast<char*>(sc) + de_off) : nullptr;
+  const unsigned grid = unsigned((n + 255) / 256);
+  if (tab) {
+    const mc_tab_src src{tab->dofmap, tab->x_dofmap, tab->x, d_u};
+    if (tab->T.nb == 3) mc_trial_kernel<ASSOC, 3><<<grid, 256, 0, ctx->s_cmp>>>(k, P, n, ctx->stats, ctx->work_ctr, list, list_yl, tab->d_T, src, list_deps);
+    else if (tab->T.nb == 6) mc_trial_kernel<ASSOC, 6><<<grid, 256, 0, ctx->s_cmp>>>(k, P, n, ctx->stats, ctx->work_ctr, list, list_yl, tab->d_T, src, list_deps);
+    else mc_trial_kernel<ASSOC, 10><<<grid, 256, 0, ctx->s_cmp>>>(k, P, n, ctx->stats, ctx->work_ctr, list, list_yl, tab->d_T, src, list_deps);
+  } else {
+    mc_trial_kernel<ASSOC, 0><<<grid, 256, 0, ctx->s_cmp>>>(k, P, n, ctx->stats, ctx->work_ctr, list, list_yl, nullptr, mc_tab_src{}, nullptr);
+  }
+  if (cfg == 3 && ASSOC) rc = mc_launch_newton<ASSOC, 12, ASSOC ? 18 : 16>(ctx, k, P, list, list_yl, list_deps);
+  else if (cfg == 2 && ASSOC) rc = mc_launch_newton<ASSOC, 16, ASSOC ? 18 : 16>(ctx, k, P, list, list_yl, list_deps);
+  else if (cfg >= 1) rc = mc_launch_newton<ASSOC, 16, 16>(ctx, k, P, list, list_yl, list_deps);
+  else rc = mc_launch_newton<ASSOC, 12, 16>(ctx, k, P, list, list_yl, list_deps);
   if (rc != EO_OK) return rc;
   ctx->launches += 2;
   return EO_OK;
@@ -891,6 +971,38 @@ int eo_mc_eval_scheme(eo_ctx* ctx, const eo_mc_params* prm, const double* deps, 
               (int32_t*)a[4],      (double*)a[5],       (double*)a[6], (double*)a[7]};
     return mc_launch(ctx, k, P, m, scheme);
   });
+}
+
+int eo_mc_eval_tabulated(eo_ctx* ctx, const eo_mc_params* prm, eo_tab* tab, const double* u, const double* sigma_n,
+                         double* C_tang, double* sigma, int32_t* niter, double* yielding, double* norm_res, double* dlambda) {
+  EO_REQUIRE(ctx, ctx != nullptr, "eo_mc_eval_tabulated: ctx is NULL");
+  EO_REQUIRE(ctx, prm && tab, "eo_mc_eval_tabulated: NULL argument");
+  EO_REQUIRE(ctx, tab->ctx == ctx, "eo_mc_eval_tabulated: the tabulation handle lives on another context");
+  EO_REQUIRE(ctx, tab->T.gdim == 2 && tab->T.bs == 2 && (tab->T.nb == 3 || tab->T.nb == 6 || tab->T.nb == 10),
+             "eo_mc_eval_tabulated: needs a P1/P2/P3 vector field on triangles (plane-strain Mandel strain)");
+  EO_REQUIRE(ctx, prm->Nitermax >= 0 && prm->Nitermax <= 200, "eo_mc_eval_tabulated: Nitermax must be in [0, 200]");
+  const int64_t n = tab->n_cells * tab->T.nq;
+  if (n == 0) return EO_OK;
+  EO_REQUIRE(ctx, u && sigma_n && C_tang && sigma, "eo_mc_eval_tabulated: NULL array");
+  EO_REQUIRE(ctx, eo_is_device_ptr(sigma_n) && eo_is_device_ptr(C_tang) && eo_is_device_ptr(sigma) &&
+                      (!niter || eo_is_device_ptr(niter)) && (!yielding || eo_is_device_ptr(yielding)) &&
+                      (!norm_res || eo_is_device_ptr(norm_res)) && (!dlambda || eo_is_device_ptr(dlambda)),
+             "eo_mc_eval_tabulated: history and outputs must be device memory (the coefficient vector may be host memory)");
+  EO_REQUIRE(ctx, eo_aligned(sigma_n, 32) && eo_aligned(C_tang, 32) && eo_aligned(sigma, 32),
+             "eo_mc_eval_tabulated: arrays must be 32-byte aligned");
+  EO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const double* d_u = nullptr;
+  int rc = eo_tab_stage_u(tab, u, &d_u);
+  if (rc != EO_OK) return rc;
+  mc_params_in pin{prm->E, prm->nu, prm->c, prm->phi, prm->psi, prm->theta_T, prm->a, prm->tol, prm->Nitermax};
+  mc_consts k;
+  mc_make_consts(pin, k);
+  EO_CUDA(ctx, cudaMemsetAsync(ctx->work_ctr, 0, 256, ctx->s_cmp));
+  const mc_ptrs P{nullptr, sigma_n, C_tang, sigma, niter, yielding, norm_res, dlambda};
+  rc = k.assoc ? mc_launch_classes<true>(ctx, k, P, n, tab, d_u) : mc_launch_classes<false>(ctx, k, P, n, tab, d_u);
+  if (rc != EO_OK) return rc;
+  EO_CUDA(ctx, cudaGetLastError());
+  return EO_OK;
 }
 
 }  // extern "C"

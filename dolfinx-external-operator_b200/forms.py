@@ -136,8 +136,9 @@ class QuadratureForms:
     def mc_residual(self, mc, u=None, out=None, n_cells=None, accumulate=False, output="host"):
         """The Mohr-Coulomb counterpart of `vm_residual` (demo_plasticity_mohr_coulomb.py:679-688 + assemble_vector):
         Mandel strain of `u` -> local Newton return mapping (`mc`: a resident-history `MohrCoulomb`; tangent and stress
-        stay in HBM as `self.C_tang`, `mc.sigma_dev`) -> b = int sigma . eps(v) dx.  Three launches (tabulation, the
-        two-pass Mohr-Coulomb kernels, the stress integral): the model is FP64-pipe bound, fusing would not pay."""
+        stay in HBM as `self.C_tang`, `mc.sigma_dev`) -> b = int sigma . eps(v) dx.  The strain is tabulated inside
+        pass 1 of the Mohr-Coulomb kernels (`eo_mc_eval_tabulated`: kept only for the plastic points, never stored for
+        the mesh); the stress integral follows as its own launch because it needs both passes' stresses."""
         t = self.tab
         n = t.n_cells * t.nq
         if mc.n_qp is None:
@@ -147,12 +148,16 @@ class QuadratureForms:
         c = self.ctx
         if self.C_tang is None or self.C_tang.size != 16 * n:
             self.C_tang = c.empty((16 * n,))
-        if getattr(self, "_strain", None) is None or self._strain.size != 4 * n:
-            self._strain = c.empty((t.n_cells, t.nq, 4))
-        t.evaluate("mandel_strain", u, out=self._strain)
         c.stats_reset()
-        c.check(c.lib.eo_mc_eval(c.handle, C.byref(mc._prm), self._strain.ptr, mc.sigma_n_dev.ptr, self.C_tang.ptr,
-                                 mc.sigma_dev.ptr, None, None, None, None, n))
+        if type(t).__name__ == "Tabulator" and t.gdim == 2 and t.bs == 2 and t.nb in (3, 6, 10):
+            # strain tabulated inside pass 1 of the Mohr-Coulomb kernels: never stored
+            t.mc_fused(mc, u, C_tang=self.C_tang)
+        else:
+            if getattr(self, "_strain", None) is None or self._strain.size != 4 * n:
+                self._strain = c.empty((t.n_cells, t.nq, 4))
+            t.evaluate("mandel_strain", u, out=self._strain)
+            c.check(c.lib.eo_mc_eval(c.handle, C.byref(mc._prm), self._strain.ptr, mc.sigma_n_dev.ptr, self.C_tang.ptr,
+                                     mc.sigma_dev.ptr, None, None, None, None, n))
         return self.vector("mandel_strain", mc.sigma_dev, out=out, n_cells=n_cells, accumulate=accumulate, output=output)
 
     # ------------------------------------------------------------------ assembled matrix (CSR on the device)

@@ -174,6 +174,27 @@ class Tabulator:
         return C_tang
 
 
+    def mc_fused(self, mc, coefficient=None, C_tang: DeviceArray | None = None, aux: dict | None = None):
+        """Tabulate the Mandel strain and run the Mohr-Coulomb return mapping without ever storing the strain
+        (`eo_mc_eval_tabulated`: the strain is evaluated inside pass 1 and kept only for the plastic points).
+        History resident in `mc`; returns the tangent DeviceArray, the stress lands in `mc.sigma_dev`.  `aux`: optional
+        dict of device arrays niter (int32) / yielding / norm_res / dlambda."""
+        n = self.n_cells * self.nq
+        if mc.n_qp is None:
+            mc._alloc_state(n)
+        if mc.n_qp != n:
+            raise ValueError(f"mesh has {n} quadrature points, the resident history {mc.n_qp}")
+        c = self.ctx
+        if C_tang is None:
+            C_tang = c.empty((16 * n,))
+        u = self._coeff(coefficient)
+        a = aux or {}
+        c.check(c.lib.eo_mc_eval_tabulated(c.handle, C.byref(mc._prm), self._h, _ptr(u), mc.sigma_n_dev.ptr, C_tang.ptr,
+                                           mc.sigma_dev.ptr, _ptr(a.get("niter")), _ptr(a.get("yielding")),
+                                           _ptr(a.get("norm_res")), _ptr(a.get("dlambda"))))
+        return C_tang
+
+
 class LazyOperand:
     """An operand that has NOT been tabulated: (tabulator, kind, coefficient) for all cells.  `evaluate_operands`
     returns it for plans registered with output='lazy'; callables that can fuse the tabulation into their own kernel

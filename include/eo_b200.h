@@ -372,6 +372,15 @@ int eo_mc_eval_scheme(eo_ctx* ctx, const eo_mc_params* prm, const double* deps, 
                       double* C_tang, double* sigma, int32_t* niter, double* yielding, double* norm_res,
                       double* dlambda, int64_t n, int scheme);
 
+/* Fused hot path of the Mohr-Coulomb demo for all cells of `tab` (a P1/P2/P3 vector field on triangles): the Mandel
+ * strain of the coefficient vector u (any-side) is tabulated INSIDE pass 1 of the two-pass scheme and kept only for the
+ * plastic points (next to the list entry that pass 2 works off): the strain array of the mesh is never written.
+ * replaces: `evaluate_operands` + `C_tang_impl` of demo_plasticity_mohr_coulomb.py:679-688.  Point index = cell * nq + q;
+ * sigma_n, C_tang, sigma and the optional aux arrays are device memory; asynchronous on the ctx stream.  Same results as
+ * eo_tabulate -> eo_mc_eval up to the rounding of the strain (this translation unit contracts FMAs, tab.cu does not). */
+int eo_mc_eval_tabulated(eo_ctx* ctx, const eo_mc_params* prm, eo_tab* tab, const double* u, const double* sigma_n,
+                         double* C_tang, double* sigma, int32_t* niter, double* yielding, double* norm_res, double* dlambda);
+
 /* ---------------------------------------------------------------- Isihara ICNN hyperelasticity
  * replaces: `vectorized_stress_and_tangent` / `dP_dF_impl`, doc/demo/demo_hyperelasticity.py:429-456
  *           (network :242-307 with the state dict Isihara_noise=high.pth, corrections :362-381).

@@ -206,3 +206,40 @@ def test_mc_scratch_survives_l2_flush(ctx):
         ctx.check(ctx.lib.eo_dev_memset(ctx.handle, t.ptr, 0xFF, t.nbytes))
     _check(_abi(ctx, d[:15_000], s[:15_000]), {k: v[:15_000] for k, v in ref.items()}, d[:15_000], s[:15_000])
     ctx.sync()
+
+
+@pytest.mark.parametrize("degree", [1, 2])
+def test_mc_fused_with_tabulation(ctx, degree):
+    """eo_mc_eval_tabulated: the Mandel strain is tabulated inside pass 1 and never stored.  Same iteration counts and
+    flags as tabulate -> eo_mc_eval, values to the rounding of the strain (mc.cu contracts FMAs, tab.cu does not), and
+    within the tolerance of the oracle chain."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from dolfinx_external_operator_b200 import synthetic as syn
+    from mc_util import lode_w2
+    from oracle import tabulation as ot
+    from tab_util import tri_case
+
+    m = tri_case(nx=41, ny=37, degree=degree)
+    n = 3 * m["dofmap"].shape[0]
+    _, sn = inputs.mc_batch(n, seed=5, stepper=_stepper())
+    u = syn.smooth_displacement(m["dof_coords"], scale=2e-6, seed=3).reshape(-1)
+    tab = eo.Tabulator(dofmap=m["dofmap"], x_dofmap=m["x_dofmap"], x=m["x"], phi=m["phi"], dphi=m["dphi"], bs=2,
+                       n_dofs=m["n_dofs"], ctx=ctx)
+    mc_a, mc_b = eo.MohrCoulomb(ctx=ctx, n_qp=n), eo.MohrCoulomb(ctx=ctx, n_qp=n)
+    mc_a.set_history(sn)
+    mc_b.set_history(sn)
+    aux = {"niter": ctx.empty((n,), np.int32), "yielding": ctx.empty((n,)), "norm_res": ctx.empty((n,)), "dlambda": ctx.empty((n,))}
+    ctx.stats_reset()
+    Ct_f = tab.mc_fused(mc_a, u, aux=aux).to_host()
+    st = ctx.stats()
+    strain = tab.evaluate("mandel_strain", u, output="host").reshape(-1, 4)
+    two = _abi(ctx, strain, sn)
+    fused = {"C_tang": Ct_f.reshape(n, 4, 4), "sigma": mc_a.sigma_dev.to_host().reshape(n, 4), "niter": aux["niter"].to_host(),
+             "yielding": aux["yielding"].to_host(), "norm_res": aux["norm_res"].to_host(), "dlambda": aux["dlambda"].to_host()}
+    assert 0.05 < (two["yielding"] > 0).mean() < 0.95
+    _check(fused, two, strain, sn)
+    assert st["n_points"] == n and st["n_plastic"] == int((two["yielding"] > 0).sum())
+    ref = native.mc_return_mapping(ot.tabulate(ot.MANDEL_STRAIN, u, m["dofmap"], 2, m["x"], m["x_dofmap"], m["phi"], m["dphi"],
+                                               m["dpsi"]).reshape(-1, 4), sn, PRM, parallel=True)
+    _check(fused, ref, strain, sn)
