@@ -168,8 +168,10 @@ def test_vm_residual_step(ctx, exact):
            of.apply_action(ot.MANDEL_STRAIN, ot.MANDEL_STRAIN, Ct, x, W3, m["dofmap"], 2, m["n_dofs"], *_geo(m)))
 
 
-def test_mc_residual_step(ctx):
-    """Mohr-Coulomb: tabulate -> local Newton -> stress integral on the device vs the oracle chain (1e-10: Newton model)."""
+@pytest.mark.parametrize("fused", [False, True])
+def test_mc_residual_step(ctx, fused):
+    """Mohr-Coulomb: tabulate -> local Newton -> stress integral on the device vs the oracle chain (1e-10: Newton model);
+    fused=True: the strain is tabulated inside pass 1 of the Mohr-Coulomb kernels and never stored."""
     from oracle import native
 
     m = tri_case(nx=23, ny=17)
@@ -180,7 +182,7 @@ def test_mc_residual_step(ctx):
     u = syn.smooth_displacement(m["dof_coords"], scale=2e-6, seed=3).reshape(-1)
     mc = eo.MohrCoulomb(ctx=ctx, n_qp=n)
     mc.set_history(sigma_n)
-    b = forms.mc_residual(mc, u)
+    b = forms.mc_residual(mc, u, fused=fused)
     eps = ot.tabulate(ot.MANDEL_STRAIN, u, m["dofmap"], 2, *_geo(m)).reshape(-1, 4)
     ref = native.mc_return_mapping(eps, sigma_n, mprm, parallel=True)
     assert 0.05 < (np.asarray(ref["yielding"]) > 0).mean() < 0.95 and int(np.max(ref["niter"])) < 20
