@@ -549,17 +549,13 @@ EO_HD bool mc_stage(const mc_consts& k, int kind, const mc_slot& sl, int32_t& ni
       const double m[4] = {s[2] * s[1], s[2] * s[0], s[0] * s[1] - 0.5 * s[3] * s[3], -s[2] * s[3]};
       mc_dev(m, t);
     }
-    const double Gx = sl[MC_F_G + 0], Gy = sl[MC_F_G + 1], Gxx = sl[MC_F_G + 2], Gxy = sl[MC_F_G + 3],
-                 Gyy = sl[MC_F_G + 4];
+    const double Gx = sl[MC_F_G + 0], Gy = sl[MC_F_G + 1];
     double n[4], df[4];
     {
       const double h0 = k.g.sa * (1.0 / 3.0);
 #pragma unroll
       for (int i = 0; i < 4; ++i) n[i] = (i < 3 ? h0 : 0.0) + Gx * s[i] + Gy * t[i];
     }
-    double H[10];
-    mc_hess(s, t, Gx, Gy, Gxx, Gxy, Gyy, H);
-    double Hf[10];
     if (ASSOC) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) df[i] = n[i];
@@ -568,8 +564,44 @@ EO_HD bool mc_stage(const mc_consts& k, int kind, const mc_slot& sl, int32_t& ni
       const double h0 = k.f.sa * (1.0 / 3.0);
 #pragma unroll
       for (int i = 0; i < 4; ++i) df[i] = (i < 3 ? h0 : 0.0) + Fx * s[i] + Fy * t[i];
-      mc_hess(s, t, Fx, Fy, sl[MC_F_F + 2], sl[MC_F_F + 3], sl[MC_F_F + 4], Hf);
     }
+    double d[5];
+    if (kind == 1) {
+      // FIRST update: y0 = [sigma_n, 0], so dlambda = 0 and M = S + 0 Hess g = S EXACTLY (0 x finite = 0; where the
+      // Hessian is not finite - J2 = 0, clipped Lode argument - the gradient n is not finite either and poisons the
+      // update just like the reference's Jacobian does), M^{-1} = C_elas: no Hessian, no factorisation.  And Y0 = 0: the
+      // tangent right-hand sides are the unit vectors.
+      //   z = C n,  q = C df,  dlam = (df . rs + r_f) / (df . z),  dsig = rs - z dlam        (rs = -r_sigma, C S = I)
+      //   Y_sig[:, j] = C e_j - z yl_j,  Y_lam[j] = yl_j = q_j / (df . z)
+      double z[4], q_[4];
+      mc_Cmul(k, n, z);
+      if (ASSOC) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q_[i] = z[i];
+      } else {
+        mc_Cmul(k, df, q_);
+      }
+      const double idenom = 1.0 / mc_dot4(df, z);
+      const double rs[4] = {-sl[MC_F_R + 0], -sl[MC_F_R + 1], -sl[MC_F_R + 2], -sl[MC_F_R + 3]};
+      d[4] = (mc_dot4(df, rs) + sl[MC_F_R + 4]) * idenom;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) d[i] = rs[i] - z[i] * d[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double yl = q_[j] * idenom;
+        double e[4] = {0.0, 0.0, 0.0, 0.0}, Ce[4];
+        e[j] = 1.0;
+        mc_Cmul(k, e, Ce);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sl[MC_F_YY + 4 * i + j] = Ce[i] - z[i] * yl;
+        sl[MC_F_YY + 16 + j] = yl;
+      }
+    } else {
+    const double Gxx = sl[MC_F_G + 2], Gxy = sl[MC_F_G + 3], Gyy = sl[MC_F_G + 4];
+    double H[10];
+    mc_hess(s, t, Gx, Gy, Gxx, Gxy, Gyy, H);
+    double Hf[10];
+    if (!ASSOC) mc_hess(s, t, sl[MC_F_F + 0], sl[MC_F_F + 1], sl[MC_F_F + 2], sl[MC_F_F + 3], sl[MC_F_F + 4], Hf);
     // M = S + dl Hg (symmetric 4x4), z = M^{-1} n, q = M^{-1} df, denom = df . z     (see "linear algebra")
     const double dl = y[4];
     mc_ldl lf;
@@ -596,7 +628,6 @@ EO_HD bool mc_stage(const mc_consts& k, int kind, const mc_slot& sl, int32_t& ni
     }
     const double idenom = 1.0 / mc_dot4(df, z);
     // Newton step  J delta = -r                                                   (:511-512)
-    double d[5];
     {
       const double rs[4] = {-sl[MC_F_R + 0], -sl[MC_F_R + 1], -sl[MC_F_R + 2], -sl[MC_F_R + 3]};
       double w[4];
@@ -623,7 +654,7 @@ EO_HD bool mc_stage(const mc_consts& k, int kind, const mc_slot& sl, int32_t& ni
     } else {
       mc_symmul(Hf, d, Hfd);
     }
-    if (kind == 2) {  // Y0 = 0: the first update has no DJ term
+    {
       const double Gxxx = sl[MC_F_G + 5], Gxxy = sl[MC_F_G + 6], Gxyy = sl[MC_F_G + 7], Gyyy = sl[MC_F_G + 8];
       double db[4], Nb[4], p[4], q[4];
       mc_dev(d, db);
@@ -662,7 +693,7 @@ EO_HD bool mc_stage(const mc_consts& k, int kind, const mc_slot& sl, int32_t& ni
     for (int j = 0; j < 4; ++j) {
       double w[4] = {0.0, 0.0, 0.0, 0.0};
       double rho = 0.0;
-      if (kind == 2) {
+      {
         double a[4], Na[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) a[i] = sl[MC_F_YY + 4 * i + j];
@@ -679,6 +710,7 @@ EO_HD bool mc_stage(const mc_consts& k, int kind, const mc_slot& sl, int32_t& ni
       for (int i = 0; i < 4; ++i) sl[MC_F_YY + 4 * i + j] = w[i] - z[i] * yl;
       sl[MC_F_YY + 16 + j] = yl;
     }
+    }
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
       y[i] += d[i];  // :513
@@ -688,8 +720,15 @@ EO_HD bool mc_stage(const mc_consts& k, int kind, const mc_slot& sl, int32_t& ni
   }
 
   // --- residual at the (new) iterate and the loop test
+  // the update that follows the FIRST residual (kind 0 -> kind 1) needs the gradients only (dlambda = 0, Y0 = 0): first-
+  // order partials suffice there; every later update needs the partials up to order 3 (g) / 2 (f)
   mc_surf ug;
-  mc_surface<3>(k, k.g, y, ug);
+  if (kind == 0) {
+    mc_surface<1>(k, k.g, y, ug);
+    ug.G.xx = ug.G.xy = ug.G.yy = ug.G.xxx = ug.G.xxy = ug.G.xyy = ug.G.yyy = 0.0;
+  } else {
+    mc_surface<3>(k, k.g, y, ug);
+  }
   double n[4];
   mc_grad(k.g, ug, n);
   double fval;
@@ -697,7 +736,12 @@ EO_HD bool mc_stage(const mc_consts& k, int kind, const mc_slot& sl, int32_t& ni
     fval = ug.h;
   } else {
     mc_surf uf;
-    mc_surface<2>(k, k.f, y, uf);
+    if (kind == 0) {
+      mc_surface<1>(k, k.f, y, uf);
+      uf.G.xx = uf.G.xy = uf.G.yy = 0.0;
+    } else {
+      mc_surface<2>(k, k.f, y, uf);
+    }
     fval = uf.h;
     sl[MC_F_F + 0] = uf.G.x, sl[MC_F_F + 1] = uf.G.y, sl[MC_F_F + 2] = uf.G.xx, sl[MC_F_F + 3] = uf.G.xy,
                 sl[MC_F_F + 4] = uf.G.yy;
