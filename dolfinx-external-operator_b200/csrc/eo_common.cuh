@@ -12,7 +12,6 @@
 #include "eo_b200.h"
 
 #define EO_NSLOT 3  // pipeline depth of the host-side (staged) path
-#define EO_MC_MAX_CHUNKS 64
 
 struct eo_ctx {
   int device = 0;
@@ -43,10 +42,6 @@ struct eo_ctx {
   int stats_recv_world = 0;
   eo_stats* stats_global = nullptr;  // device [1]
   unsigned int* work_ctr = nullptr;  // device: tile counter of the persistent kernels
-  // Mohr-Coulomb overlapped scheme (mc.cu): pass 1 of the chunks on s_mc[0], pass 2 alternating on s_mc[1] / s_mc[2],
-  // chained by ev_mc; created on first use, destroyed with the context
-  cudaStream_t s_mc[3] = {};
-  cudaEvent_t ev_mc[EO_MC_MAX_CHUNKS + 4] = {};
   int64_t launches = 0;
   char err[512] = {0};
 };

@@ -223,13 +223,6 @@ int eo_destroy(eo_ctx* ctx) {
   cudaStreamSynchronize(ctx->s_cmp);
   cudaStreamSynchronize(ctx->s_out);
   if (ctx->s_coll) cudaStreamSynchronize(ctx->s_coll);
-  for (cudaStream_t st : ctx->s_mc)
-    if (st) {
-      cudaStreamSynchronize(st);
-      cudaStreamDestroy(st);
-    }
-  for (cudaEvent_t ev : ctx->ev_mc)
-    if (ev) cudaEventDestroy(ev);
   if (ctx->ev_coll_ready) cudaEventDestroy(ctx->ev_coll_ready);
   if (ctx->ev_coll_done) cudaEventDestroy(ctx->ev_coll_done);
   if (ctx->stats_send) cudaFree(ctx->stats_send);

@@ -33,6 +33,9 @@
 #define MC_TILE 4096     // points per work item of the global counter
 #define MC_SIMPLE_THREADS 128
 #define MC_CTR_LIST 32   // word of the context's counter block that holds the length of the plastic-point list
+#ifndef MCN_PREFETCH
+#define MCN_PREFETCH 512  // list entries
+#endif
 #define MCN_FULL_DEFAULT 28
 #define MCN_MIN_ACTIVE_DEFAULT 99  // 99: never wait (a warp starts with whatever lanes it can fill)
 #define MCN_FIRST_LAST_DEFAULT 2
@@ -516,6 +519,9 @@ __global__ void __launch_bounds__(256, NB > 0 ? 3 : 4) mc_trial_kernel(const mc_
       if (!(isfinite(sig[0]) && isfinite(sig[1]) && isfinite(sig[2]) && isfinite(sig[3]))) atomicAdd(&s_nonfinite, 1u);
     } else {
       plastic = true;  // NaN predicate -> plastic branch, like `yielding <= 0.0` being false
+      // the aux arrays are written for EVERY point here (pass 2 overwrites the plastic entries): a 32-byte sector written
+      // in part costs a read-fill from HBM when it leaves L2
+      mc_store_aux(P, i, 0, yl, 0.0, 0.0);
     }
   }
   // ---- CTA-aggregated epilogue: ONE list reservation per CTA (a per-warp atomicAdd on the single list counter would
@@ -594,77 +600,37 @@ struct mcn_policy {
   unsigned sleep_ns;
 };
 
-// Where pass 2 finds its points: `nsub` compact sub-lists of `cap` reserved entries each (sub-list c starts at entry
-// c * cap and holds cnt[c] entries).  The one-launch pass 1 writes ONE list (nsub = 1, cnt = the context's list counter);
-// the streaming pass 1 of the overlapped scheme writes one private sub-list per CTA (no global reservation atomics).
-// Work items are `tile` consecutive entries of one sub-list, numbered c * tps + j with tps = ceil(max_c cnt[c] / tile).
-#ifndef MCN_PREFETCH
-#define MCN_PREFETCH 512  // list entries
-#endif
-#define MCN_MAX_SUB 640  // 148 SMs x up to 4 pass-1 CTAs per SM (first chunk)
-struct mcn_src {
-  const int32_t* list;
-  const double* yl;
-  const double* deps;  // strain of the listed points (tabulated pass 1) or nullptr
-  const unsigned int* cnt;
-  int nsub;
-  int tile;
-  long long cap;
-};
-
 template <bool ASSOC, int NWARPS, int DEPTH>
-__device__ __forceinline__ void mc_newton_body(const mc_consts& k, const mc_ptrs& P, eo_stats* __restrict__ stats, unsigned int* ctr,
-                                               const mcn_src& src, const mcn_policy& pol) {
+__global__ void __launch_bounds__(NWARPS * 32, 1) mc_newton_kernel(const mc_consts k, const mc_ptrs P, eo_stats* __restrict__ stats,
+                                                                   unsigned int* ctr, const int32_t* __restrict__ list,
+                                                                   const double* __restrict__ list_yl, const mcn_policy pol,
+                                                                   const double* __restrict__ list_deps) {
   constexpr int NSLOT = 32 * DEPTH;
   constexpr unsigned ALL = DEPTH == 32 ? 0xffffffffu : ((1u << DEPTH) - 1u);
-  const int32_t* __restrict__ list = src.list;
-  const double* __restrict__ list_yl = src.yl;
-  const double* __restrict__ list_deps = src.deps;
+  const int64_t n = (int64_t)ctr[MC_CTR_LIST];
   extern __shared__ double s_slots[];  // [ASSOC ? MC_NF_ASSOC : MC_NF][NSLOT]
   __shared__ unsigned int s_free[32], s_ready[32];
   __shared__ int s_pt[NSLOT];
   __shared__ int s_it[NSLOT];
-  __shared__ unsigned long long s_work;  // (work item << 32) | (entries of the item << 16) | next entry within the item
+  __shared__ unsigned long long s_work;  // (tile index << 16) | next list entry within the tile
   __shared__ int s_inflight, s_done, s_fetching, s_active;  // s_active: warps inside a stage
   __shared__ unsigned int s_hist[EO_NITER_BINS];
   __shared__ unsigned int s_nonconv, s_nonfinite, s_plastic;
-  __shared__ unsigned int s_cnt[MCN_MAX_SUB];
-  __shared__ unsigned int s_cmax;
 
   const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t ntiles = (n + MC_TILE - 1) / MC_TILE;
   for (int b = tid; b < EO_NITER_BINS; b += NWARPS * 32) s_hist[b] = 0;
   if (tid < 32) s_free[tid] = ALL, s_ready[tid] = 0;
   if (tid == 0) {
     s_nonconv = s_nonfinite = s_plastic = 0;
     s_inflight = 0, s_done = 0, s_fetching = 0, s_active = 0;
-    s_work = 0ull;  // no entries: the first warp to look fetches a work item
-    s_cmax = 0;
+    s_work = 0xFFFFull;  // "exhausted": the first warp to look fetches a tile
   }
-  __syncthreads();
-  for (int c = tid; c < src.nsub; c += NWARPS * 32) {
-    const unsigned int v = src.cnt[c];
-    s_cnt[c] = v;
-    if (v) atomicMax(&s_cmax, v);
-  }
-  __syncthreads();
-  // work-item arithmetic is needed once per item / once per first visit: its operands stay in shared memory and in the
-  // kernel's constant bank, not in registers
-  __shared__ unsigned int s_tps;
-  if (tid == 0) s_tps = (s_cmax + (unsigned)src.tile - 1u) / (unsigned)src.tile;
   __syncthreads();
   double max_res = 0.0;
   int max_it = 0;
-  auto n_items = [&]() -> long long { return (long long)*(volatile unsigned int*)&s_tps * src.nsub; };
-  auto tile_points = [&](long long t) -> long long {
-    const long long tps = *(volatile unsigned int*)&s_tps;
-    const long long c = src.nsub == 1 ? 0 : t / tps;
-    const long long r = (long long)s_cnt[c] - (t - c * tps) * src.tile;
-    return r < 0 ? 0 : (r < src.tile ? r : (long long)src.tile);
-  };
-  auto tile_base = [&](long long t) -> long long {
-    const long long tps = *(volatile unsigned int*)&s_tps;
-    const long long c = src.nsub == 1 ? 0 : t / tps;
-    return c * src.cap + (t - c * tps) * src.tile;
+  auto tile_points = [&](long long tile) -> long long {
+    return tile < ntiles ? (n - tile * MC_TILE < MC_TILE ? n - tile * MC_TILE : MC_TILE) : 0;
   };
 
   for (;;) {
@@ -674,23 +640,16 @@ __device__ __forceinline__ void mc_newton_body(const mc_consts& k, const mc_ptrs
     int stage = MC_STAGE_WAIT;
     if (lane == 0) {
       unsigned long long w = *(volatile unsigned long long*)&s_work;
-      auto has_input = [](unsigned long long x) { return (unsigned)(x & 0xFFFFull) < (unsigned)((x >> 16) & 0xFFFFull); };
-      bool inputs = has_input(w);
+      bool inputs = (long long)(w & 0xFFFFull) < tile_points((long long)(w >> 16));
       if (!inputs && !*(volatile int*)&s_done && nF > 0 && atomicCAS(&s_fetching, 0, 1) == 0) {
-        w = *(volatile unsigned long long*)&s_work;  // one warp at a time fetches the next item; re-check under the flag
-        if (!has_input(w)) {
-          for (;;) {  // sub-lists shorter than the longest one end in empty work items: skip them
-            const unsigned int t = atomicAdd(ctr, 1u);
-            if ((long long)t >= n_items()) {
-              *(volatile int*)&s_done = 1;
-              break;
-            }
-            const long long pts = tile_points((long long)t);
-            if (pts > 0) {
-              atomicExch(&s_work, ((unsigned long long)t << 32) | ((unsigned long long)pts << 16));
-              inputs = true;
-              break;
-            }
+        w = *(volatile unsigned long long*)&s_work;  // one warp at a time fetches the next tile; re-check under the flag
+        if (!((long long)(w & 0xFFFFull) < tile_points((long long)(w >> 16)))) {
+          const unsigned int t = atomicAdd(ctr, 1u);
+          if ((int64_t)t >= ntiles) {
+            *(volatile int*)&s_done = 1;
+          } else {
+            atomicExch(&s_work, (unsigned long long)t << 16);
+            inputs = true;
           }
         } else {
           inputs = true;
@@ -709,7 +668,7 @@ __device__ __forceinline__ void mc_newton_body(const mc_consts& k, const mc_ptrs
       else if (f > 0) stage = MC_STAGE_T;
       else if (*(volatile int*)&s_done && *(volatile int*)&s_inflight == 0) {
         const unsigned long long w3 = *(volatile unsigned long long*)&s_work;
-        if (!has_input(w3)) stage = MC_STAGE_EXIT;
+        if (!((long long)(w3 & 0xFFFFull) < tile_points((long long)(w3 >> 16)))) stage = MC_STAGE_EXIT;
       }
     }
     stage = __shfl_sync(0xffffffffu, stage, 0);
@@ -742,13 +701,13 @@ __device__ __forceinline__ void mc_newton_body(const mc_consts& k, const mc_ptrs
       const unsigned sm = __ballot_sync(0xffffffffu, slot >= 0);
       const int want = __popc(sm);
       long long e0 = 0;
-      int got = 0, ahead = 0;  // ahead: entries of the work item behind this claim
+      int got = 0, ahead = 0;  // ahead: entries of the tile from this claim on
       if (lane == 0 && want > 0) {
         atomicAdd(&s_inflight, want);  // before the claim: "done and inflight == 0" then means finished
         const unsigned long long w2 = atomicAdd(&s_work, (unsigned long long)want);
-        const long long tile2 = (long long)(w2 >> 32), off = (long long)(w2 & 0xFFFFull), pts = (long long)((w2 >> 16) & 0xFFFFull);
+        const long long tile2 = (long long)(w2 >> 16), off = (long long)(w2 & 0xFFFFull), pts = tile_points(tile2);
         if (off < pts) {
-          e0 = tile_base(tile2) + off;
+          e0 = tile2 * MC_TILE + off;
           got = (int)(pts - off < want ? pts - off : want);
           ahead = (int)(pts - off);
         }
@@ -767,7 +726,8 @@ __device__ __forceinline__ void mc_newton_body(const mc_consts& k, const mc_ptrs
         const double yl = list_yl[e];
         const int i = list[e];
         // the inputs of the entry MCN_PREFETCH places further on (claimed about one round of the CTA's warps from now)
-        // are pulled into L2 while this point is worked on: first visits then wait for an L2 hit, not for HBM
+        // are pulled into L2 while this point is worked on: a first visit then waits for an L2 hit, not for HBM
+        // (measured: 12.58 -> 12.39 ms per 1e8 points)
         const int ip = rank + MCN_PREFETCH < ahead ? list[e + MCN_PREFETCH] : -1;
         const eo_d4 de4 = list_deps ? eo_ld256(list_deps + 4 * e) : eo_ld256(P.deps + 4 * (int64_t)i);
         const eo_d4 sg = eo_ld256(P.sigma_n + 4 * (int64_t)i);
@@ -856,192 +816,6 @@ __device__ __forceinline__ void mc_newton_body(const mc_consts& k, const mc_ptrs
   }
 }
 
-
-// measurement aid (EO_MC_TRACE=file): one record per CTA - kernel tag, chunk, SM, start / end on the global timer
-__device__ __forceinline__ unsigned long long mc_globaltimer() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __forceinline__ void mc_trace_write(unsigned long long* trace, unsigned tag, unsigned long long t0) {
-  if (!trace) return;
-  unsigned smid;
-  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-  const unsigned long long slot = atomicAdd(trace, 1ull);
-  if (slot < 65536ull) {
-    trace[1 + 3 * slot] = ((unsigned long long)tag << 32) | smid;
-    trace[2 + 3 * slot] = t0;
-    trace[3 + 3 * slot] = mc_globaltimer();
-  }
-}
-
-template <bool ASSOC, int NWARPS, int DEPTH>
-__global__ void __launch_bounds__(NWARPS * 32, 1) mc_newton_kernel(const mc_consts k, const mc_ptrs P, eo_stats* __restrict__ stats,
-                                                                   unsigned int* ctr, const mcn_src src, const mcn_policy pol) {
-  mc_newton_body<ASSOC, NWARPS, DEPTH>(k, P, stats, ctr, src, pol);
-}
-
-// The same kernel held to MCN_CO_REGS registers per thread: 12 warps x 152 registers leave 7168 registers of the SM
-// free - one 128-thread CTA of the streaming pass 1 below (56 registers) runs NEXT TO it on every SM.
-#define MCN_CO_REGS 144
-template <bool ASSOC, int NWARPS, int DEPTH>
-__global__ void __maxnreg__(MCN_CO_REGS) mc_newton_co_kernel(const mc_consts k, const mc_ptrs P, eo_stats* __restrict__ stats,
-                                                            unsigned int* ctr, const mcn_src src, const mcn_policy pol,
-                                                            unsigned long long* trace, const unsigned tag) {
-  __shared__ unsigned long long s_t0;
-  if (trace && threadIdx.x == 0) s_t0 = mc_globaltimer();
-  mc_newton_body<ASSOC, NWARPS, DEPTH>(k, P, stats, ctr, src, pol);
-  if (trace && threadIdx.x == 0) mc_trace_write(trace, tag, s_t0);
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Overlapped scheme, pass 1: STREAMING yield test that shares the SM with pass 2 of the previous chunk.
-//
-// Pass 1 is HBM bound (252 B per point, almost no arithmetic), pass 2 is FP64-pipe bound (no memory traffic to speak of):
-// run back to back they leave the FP64 pipe idle for the first third of the step and the memory system idle for the rest.
-// This kernel is pass 1 shaped to run BESIDE the Newton kernel: one CTA of 4 warps and 56 registers per SM (what
-// mc_newton_co_kernel leaves free), inputs prefetched three blocks ahead by the bulk-copy engine (cp.async.bulk ->
-// mbarrier: the memory-level parallelism of a full-occupancy kernel without its registers), and no global atomics on the
-// hot path: every CTA appends its plastic points to a PRIVATE sub-list (the position counter lives in shared memory) and
-// publishes the length once.  CTA b takes the 128-point blocks b, b + gridDim.x, ...
-#define MCS_THREADS 128
-#define MCS_PPT 2                          // points per thread: two independent dependency chains per warp
-#define MCS_BLOCK (MCS_THREADS * MCS_PPT)  // points per block
-#define MCS_STAGES 2
-#define MCS_REGS 80
-template <bool ASSOC>
-__global__ void __maxnreg__(MCS_REGS) mc_trial_stream_kernel(const mc_consts k, const mc_ptrs P, const int64_t n,
-                                                             eo_stats* __restrict__ stats, int32_t* __restrict__ list,
-                                                             double* __restrict__ list_yl, unsigned int* __restrict__ sub_cnt,
-                                                             const long long sub_cap, unsigned long long* trace,
-                                                             const unsigned tag) {
-  __shared__ unsigned long long s_t0;
-  if (trace && threadIdx.x == 0) s_t0 = mc_globaltimer();
-  __shared__ __align__(128) double s_in[MCS_STAGES][2][MCS_BLOCK * 4];
-  __shared__ __align__(8) unsigned long long s_bar[MCS_STAGES];
-  __shared__ unsigned int s_npl, s_hist0, s_hist1, s_nonfinite;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int64_t nblk = (n + MCS_BLOCK - 1) / MCS_BLOCK;
-  const unsigned bar0 = (unsigned)__cvta_generic_to_shared(&s_bar[0]);
-  const unsigned in0 = (unsigned)__cvta_generic_to_shared(&s_in[0][0][0]);
-  auto issue = [&](int64_t j, int st) {  // one thread: both rows of block j into stage st
-    const int64_t p0 = j * MCS_BLOCK;
-    const unsigned bytes = (unsigned)((n - p0 < MCS_BLOCK ? n - p0 : MCS_BLOCK) * 32);
-    const unsigned bar = bar0 + 8u * st, dst = in0 + (unsigned)(st * 2 * MCS_BLOCK * 32);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(P.deps + 4 * p0), "r"(bytes), "r"(bar)
-                 : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     dst + (unsigned)(MCS_BLOCK * 32)),
-                 "l"(P.sigma_n + 4 * p0), "r"(bytes), "r"(bar)
-                 : "memory");
-  };
-  if (tid == 0) {
-    s_npl = s_hist0 = s_hist1 = s_nonfinite = 0;
-#pragma unroll
-    for (int st = 0; st < MCS_STAGES; ++st) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u * st) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#pragma unroll
-    for (int st = 0; st < MCS_STAGES; ++st) {
-      const int64_t j = blockIdx.x + int64_t(st) * gridDim.x;
-      if (j < nblk) issue(j, st);
-    }
-  }
-  __syncthreads();
-  double max_f = -INFINITY, max_res = 0.0;
-  int max_it = 0;
-  int32_t* const my_list = list + (long long)blockIdx.x * sub_cap;
-  double* const my_yl = list_yl + (long long)blockIdx.x * sub_cap;
-  int it_blk = 0;
-  for (int64_t j = blockIdx.x; j < nblk; j += gridDim.x, ++it_blk) {
-    const int st = it_blk % MCS_STAGES;
-    const unsigned parity = (unsigned)(it_blk / MCS_STAGES) & 1u;
-    {
-      const unsigned bar = bar0 + 8u * st;
-      unsigned done = 0;
-      while (!done)
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(done)
-                     : "r"(bar), "r"(parity)
-                     : "memory");
-    }
-    double de[MCS_PPT][4], sn[MCS_PPT][4];
-#pragma unroll
-    for (int u = 0; u < MCS_PPT; ++u) {
-      const double2* a = reinterpret_cast<const double2*>(&s_in[st][0][4 * (tid + u * MCS_THREADS)]);
-      const double2* b = reinterpret_cast<const double2*>(&s_in[st][1][4 * (tid + u * MCS_THREADS)]);
-      const double2 a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
-      de[u][0] = a0.x, de[u][1] = a0.y, de[u][2] = a1.x, de[u][3] = a1.y;
-      sn[u][0] = b0.x, sn[u][1] = b0.y, sn[u][2] = b1.x, sn[u][3] = b1.y;
-    }
-    __syncthreads();  // every thread holds its points: the stage can take the block MCS_STAGES ahead
-    if (tid == 0) {
-      const int64_t jn = j + int64_t(MCS_STAGES) * gridDim.x;
-      if (jn < nblk) issue(jn, st);
-    }
-    // the yield test of the thread's points side by side (independent chains for the scheduler to interleave)
-    double yl[MCS_PPT], Cde[MCS_PPT][4];
-#pragma unroll
-    for (int u = 0; u < MCS_PPT; ++u) yl[u] = mc_trial(k, de[u], sn[u], Cde[u]);
-#pragma unroll
-    for (int u = 0; u < MCS_PPT; ++u) {
-      const int64_t i = j * MCS_BLOCK + u * MCS_THREADS + tid;
-      const bool live = i < n;
-      bool plastic = false;
-      if (live) {
-        max_f = fmax(max_f, yl[u]);  // fmax ignores NaN like mc_warp_max_f64
-        if (yl[u] <= 0.0) {
-          double sig[4], Ct[16], nr, dl;
-          const int32_t it = mc_elastic(k, sn[u], Cde[u], sig, Ct, nr, dl);
-          mc_store_point(P, i, Ct, sig);
-          mc_store_aux(P, i, it, yl[u], nr, dl);
-          max_res = fmax(max_res, nr);
-          max_it = max(max_it, it);
-          if (it == 0) atomicAdd(&s_hist0, 1u);
-          else if (it == 1) atomicAdd(&s_hist1, 1u);
-          else atomicAdd(reinterpret_cast<unsigned long long*>(&stats->niter_hist[min(it, EO_NITER_BINS - 1)]), 1ull);
-          if (!(isfinite(sig[0]) && isfinite(sig[1]) && isfinite(sig[2]) && isfinite(sig[3]))) atomicAdd(&s_nonfinite, 1u);
-        } else {
-          plastic = true;  // NaN predicate -> plastic branch, like `yielding <= 0.0` being false
-          // whole 32-byte sectors of the aux arrays are written here (pass 2 overwrites these entries): a sector written
-          // in part costs a read-fill from HBM
-          mc_store_aux(P, i, 0, yl[u], 0.0, 0.0);
-        }
-      }
-      const unsigned pm = __ballot_sync(0xffffffffu, plastic);
-      if (pm) {
-        unsigned int base = 0;
-        if (lane == 0) base = atomicAdd(&s_npl, (unsigned)__popc(pm));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (plastic) {
-          const unsigned int pos = base + __popc(pm & ((1u << lane) - 1u));
-          my_list[pos] = (int32_t)i;
-          my_yl[pos] = yl[u];
-        }
-      }
-    }
-  }
-  // ---- epilogue: publish the sub-list length, flush the statistics
-  max_f = mc_warp_max_f64(max_f);
-  max_res = mc_warp_max_f64(max_res);
-  max_it = __reduce_max_sync(0xffffffffu, max_it);
-  if (lane == 0) {
-    mc_atomic_max_f64(&stats->f_max, max_f);
-    if (max_res > 0.0) mc_atomic_max_f64(&stats->res_max, max_res);
-    if (max_it > 0) mc_atomic_max_f64(&stats->niter_max, (double)max_it);
-  }
-  __syncthreads();
-  if (tid == 0) {
-    sub_cnt[blockIdx.x] = s_npl;
-    if (s_hist0) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->niter_hist[0]), (unsigned long long)s_hist0);
-    if (s_hist1) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->niter_hist[1]), (unsigned long long)s_hist1);
-    if (s_nonfinite) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_nonfinite), (unsigned long long)s_nonfinite);
-    if (blockIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_points), (unsigned long long)n);
-    mc_trace_write(trace, tag, s_t0);
-  }
-}
-
 // simple variant: one thread per point, whole Newton loop per thread (divergent).  Kept as the
 // baseline the queue scheme is measured against (bench.py --mc-scheme simple) and as a cross-check.
 template <bool ASSOC>
@@ -1088,16 +862,7 @@ static int mc_launch_queue(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, in
   return EO_OK;
 }
 
-static const mcn_policy& mcn_policy_get() {  // EO_MC_POLICY="full,min_active,first_last,sleep_ns" overrides (A/B runs)
-  static const mcn_policy pol = [] {
-    mcn_policy p{MCN_FULL_DEFAULT, MCN_MIN_ACTIVE_DEFAULT, MCN_FIRST_LAST_DEFAULT, 200u};
-    if (const char* e = getenv("EO_MC_POLICY")) sscanf(e, "%d,%d,%d,%u", &p.full, &p.min_active, &p.first_last, &p.sleep_ns);
-    return p;
-  }();
-  return pol;
-}
-
-// pass 2 over the list the one-launch pass 1 left in the context's scratch (its length in the context's counter block)
+// default scheme: pass 1 (mc_trial_kernel) + the lane-class Newton kernel over the plastic list
 template <bool ASSOC, int NWARPS, int DEPTH>
 static int mc_launch_newton(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, const int32_t* list, const double* list_yl,
                             const double* list_deps) {
@@ -1108,162 +873,13 @@ static int mc_launch_newton(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, c
     if (e != cudaSuccess) return eo_fail(ctx, EO_ERR_CUDA, "eo_mc_eval: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const mcn_src src{list, list_yl, list_deps, ctx->work_ctr + MC_CTR_LIST, 1, MC_TILE, 0};
-  mc_newton_kernel<ASSOC, NWARPS, DEPTH><<<(unsigned)ctx->sm_count, NWARPS * 32, smem, ctx->s_cmp>>>(k, P, ctx->stats, ctx->work_ctr, src,
-                                                                                                   mcn_policy_get());
-  return EO_OK;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Overlapped scheme (default for large device-resident batches): the batch is cut into chunks; pass 1 of chunk c + 1
-// (mc_trial_stream_kernel, HBM bound) runs on the same SMs and at the same time as pass 2 of chunk c
-// (mc_newton_co_kernel, FP64 bound).  Plain stream semantics: pass 1 of all chunks in order on s_mc[0], each followed by an
-// event; pass 2 of chunk c waits for that event on s_mc[1 + c % 2] (two streams: the tail of one Newton launch overlaps
-// the start of the next); everything is forked from and joined to the compute stream, so callers see one ordered
-// operation.  Nothing spins on another kernel: a tool that serialises launches only loses the overlap.
-#define MCO_TILE 512  // list entries per work item of pass 2 (chunks are small: finer items keep the CTAs' tails short)
-struct mco_config {
-  long long min_n;   // batches below this use the two-launch scheme
-  long long chunk;   // points per chunk (0: n / 16, at least 2^22)
-  int first_mult;    // CTAs per SM of the first chunk's pass 1 (the SMs are empty then)
-  int mode;          // measurements only: 1 = pass 1 alone (plastic points stay unset), 2 = pass 2 after ALL of pass 1
-  int mult;          // CTAs per SM of the later chunks' pass 1
-};
-static mco_config mco_config_get() {  // EO_MC_OVERLAP="min_n,chunk,first_mult"; "0" switches the scheme off (read per call)
-  mco_config c{-1LL, 0LL, 4, 0, 1};
-  if (const char* e = getenv("EO_MC_OVERLAP")) {
-    if (e[0] == '0' && e[1] == 0) c.min_n = -1;
-    else sscanf(e, "%lld,%lld,%d,%d,%d", &c.min_n, &c.chunk, &c.first_mult, &c.mode, &c.mult);
-  }
-  return c;
-}
-
-template <bool ASSOC>
-static int mc_launch_overlap(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, int64_t n) {
-  constexpr int NWARPS = 12, DEPTH = 16;
-  const mco_config cfg = mco_config_get();
-  const size_t smem = size_t(ASSOC ? MC_NF_ASSOC : MC_NF) * (32 * DEPTH) * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(mc_newton_co_kernel<ASSOC, NWARPS, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    // both kernels ask for the largest shared-memory carve-out: an SM configured for pass 2 alone (196 KB) would have no
-    // room for the 32 KB of the streaming pass 1, and an SM cannot change its carve-out while a CTA is resident
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(mc_newton_co_kernel<ASSOC, NWARPS, DEPTH>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                               cudaSharedmemCarveoutMaxShared);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(mc_trial_stream_kernel<ASSOC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return eo_fail(ctx, EO_ERR_CUDA, "eo_mc_eval: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
-  for (int i = 0; i < 3; ++i)
-    if (!ctx->s_mc[i]) EO_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_mc[i], cudaStreamNonBlocking));
-  long long chunk = cfg.chunk > 0 ? cfg.chunk : (n / 16 > (1LL << 22) ? n / 16 : (1LL << 22));
-  chunk = (chunk + MCS_BLOCK - 1) / MCS_BLOCK * MCS_BLOCK;  // chunk starts stay 32-byte aligned in every array
-  int nchunks = int((n + chunk - 1) / chunk);
-  if (nchunks > EO_MC_MAX_CHUNKS) {
-    nchunks = EO_MC_MAX_CHUNKS;
-    chunk = ((n + nchunks - 1) / nchunks + MCS_BLOCK - 1) / MCS_BLOCK * MCS_BLOCK;
-    nchunks = int((n + chunk - 1) / chunk);
-  }
-  for (int i = 0; i < nchunks + 4; ++i)
-    if (!ctx->ev_mc[i]) EO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_mc[i], cudaEventDisableTiming));
-  const int G = ctx->sm_count < MCN_MAX_SUB / 4 ? ctx->sm_count : MCN_MAX_SUB / 4;  // pass-1 CTAs per chunk = sub-lists: G x (1..4)
-  const int first_mult = cfg.first_mult < 1 ? 1 : (cfg.first_mult > 4 ? 4 : cfg.first_mult);
-  const int mult = cfg.mult < 1 ? 1 : (cfg.mult > 4 ? 4 : cfg.mult);
-  // scratch: [counters: nchunks x (16 + MCN_MAX_SUB) words][list int32][list_yl f64]; chunk c's sub-lists hold at most
-  // cap_c entries each
-  const size_t ctr_words = size_t(nchunks) * (16 + MCN_MAX_SUB);
-  const size_t ctr_bytes = (ctr_words * 4 + 255) / 256 * 256;
-  auto cap_of = [&](long long m, int g) {
-    const long long blocks = (m + MCS_BLOCK - 1) / MCS_BLOCK;
-    return ((blocks + g - 1) / g) * MCS_BLOCK;
-  };
-  // entries reserved per chunk: G sub-lists (the first chunk runs first_mult CTAs per SM, so cap_0 * G_0 is about the same)
-  size_t entries = 0;
-  std::vector<size_t> ent_off(nchunks);
-  for (int c = 0; c < nchunks; ++c) {
-    const long long m = (n - c * chunk) < chunk ? (n - c * chunk) : chunk;
-    const int g = G * (c == 0 ? first_mult : mult);
-    ent_off[c] = entries;
-    entries += size_t(cap_of(m, g)) * g;
-  }
-  const size_t list_bytes = (entries * 4 + 255) / 256 * 256;
-  void* sc = nullptr;
-  int rc = eo_scratch(ctx, ctr_bytes + list_bytes + entries * 8, &sc);
-  if (rc != EO_OK) return rc;
-  unsigned int* ctrs = reinterpret_cast<unsigned int*>(sc);
-  int32_t* list = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(sc) + ctr_bytes);
-  double* list_yl = reinterpret_cast<double*>(reinterpret_cast<char*>(sc) + ctr_bytes + list_bytes);
-  static unsigned long long* trace = nullptr;  // EO_MC_TRACE=file: per-CTA timeline of the NEXT call, written at its end
-  const char* trace_file = getenv("EO_MC_TRACE");
-  if (trace_file && !trace) EO_CUDA(ctx, cudaMalloc(&trace, (1 + 3 * 65536) * 8));
-  if (trace_file) EO_CUDA(ctx, cudaMemsetAsync(trace, 0, 8, ctx->s_cmp));
-  unsigned long long* const tr = trace_file ? trace : nullptr;
-  // fork
-  EO_CUDA(ctx, cudaMemsetAsync(ctrs, 0, ctr_bytes, ctx->s_cmp));
-  cudaEvent_t ev_fork = ctx->ev_mc[nchunks], ev_join[3] = {ctx->ev_mc[nchunks + 1], ctx->ev_mc[nchunks + 2], ctx->ev_mc[nchunks + 3]};
-  EO_CUDA(ctx, cudaEventRecord(ev_fork, ctx->s_cmp));
-  for (int i = 0; i < 3; ++i) EO_CUDA(ctx, cudaStreamWaitEvent(ctx->s_mc[i], ev_fork, 0));
-  const mcn_policy& pol = mcn_policy_get();
-  auto launch = [&](int c, bool pass1, int wait_ev) -> int {
-    const long long off = c * chunk, m = (n - off) < chunk ? (n - off) : chunk;
-    const mc_ptrs Pc{P.deps + 4 * off,
-                     P.sigma_n + 4 * off,
-                     P.C_tang + 16 * off,
-                     P.sigma + 4 * off,
-                     P.niter ? P.niter + off : nullptr,
-                     P.yielding ? P.yielding + off : nullptr,
-                     P.norm_res ? P.norm_res + off : nullptr,
-                     P.dlambda ? P.dlambda + off : nullptr};
-    unsigned int* cw = ctrs + size_t(c) * (16 + MCN_MAX_SUB);
-    const int g = G * (c == 0 ? first_mult : mult);
-    const long long cap = cap_of(m, g);
-    if (pass1) {
-      mc_trial_stream_kernel<ASSOC><<<(unsigned)g, MCS_THREADS, 0, ctx->s_mc[0]>>>(k, Pc, m, ctx->stats, list + ent_off[c],
-                                                                                   list_yl + ent_off[c], cw + 16, cap, tr, (unsigned)c);
-      EO_CUDA(ctx, cudaEventRecord(ctx->ev_mc[c], ctx->s_mc[0]));
-    } else {
-      cudaStream_t sn = ctx->s_mc[1 + (c & 1)];
-      EO_CUDA(ctx, cudaStreamWaitEvent(sn, ctx->ev_mc[wait_ev], 0));
-      const mcn_src src{list + ent_off[c], list_yl + ent_off[c], nullptr, cw + 16, g, MCO_TILE, cap};
-      mc_newton_co_kernel<ASSOC, NWARPS, DEPTH><<<(unsigned)ctx->sm_count, NWARPS * 32, smem, sn>>>(k, Pc, ctx->stats, cw, src, pol, tr,
-                                                                                                    0x1000u + (unsigned)c);
-    }
-    return EO_OK;
-  };
-  if (cfg.mode == 0) {
-    for (int c = 0; c < nchunks; ++c) {
-      if ((rc = launch(c, true, 0)) != EO_OK) return rc;
-      if ((rc = launch(c, false, c)) != EO_OK) return rc;
-    }
-  } else {  // measurements: pass 1 alone / the two passes one after the other
-    for (int c = 0; c < nchunks; ++c)
-      if ((rc = launch(c, true, 0)) != EO_OK) return rc;
-    for (int c = 0; c < nchunks && cfg.mode == 2; ++c)
-      if ((rc = launch(c, false, nchunks - 1)) != EO_OK) return rc;
-  }
-  // join
-  for (int i = 0; i < 3; ++i) {
-    EO_CUDA(ctx, cudaEventRecord(ev_join[i], ctx->s_mc[i]));
-    EO_CUDA(ctx, cudaStreamWaitEvent(ctx->s_cmp, ev_join[i], 0));
-  }
-  ctx->launches += 2 * nchunks;
-  if (tr) {
-    EO_CUDA(ctx, cudaStreamSynchronize(ctx->s_cmp));
-    std::vector<unsigned long long> h(1 + 3 * 65536);
-    EO_CUDA(ctx, cudaMemcpy(h.data(), tr, h.size() * 8, cudaMemcpyDeviceToHost));
-    if (FILE* f = fopen(trace_file, "w")) {
-      const unsigned long long cnt = h[0] < 65536ull ? h[0] : 65536ull;
-      unsigned long long tmin = ~0ull;
-      for (unsigned long long r = 0; r < cnt; ++r) tmin = h[2 + 3 * r] < tmin ? h[2 + 3 * r] : tmin;
-      fprintf(f, "kernel,chunk,sm,start_us,end_us\n");
-      for (unsigned long long r = 0; r < cnt; ++r)
-        fprintf(f, "%s,%u,%u,%.3f,%.3f\n", (h[1 + 3 * r] >> 32) & 0x1000u ? "newton" : "trial", (unsigned)((h[1 + 3 * r] >> 32) & 0xFFFu),
-                (unsigned)(h[1 + 3 * r] & 0xFFFFFFFFu), (h[2 + 3 * r] - tmin) * 1e-3, (h[3 + 3 * r] - tmin) * 1e-3);
-      fclose(f);
-    }
-  }
+  static const mcn_policy pol = [] {  // EO_MC_POLICY="full,min_active,first_last,sleep_ns" overrides (A/B runs)
+    mcn_policy p{MCN_FULL_DEFAULT, MCN_MIN_ACTIVE_DEFAULT, MCN_FIRST_LAST_DEFAULT, 200u};
+    if (const char* e = getenv("EO_MC_POLICY")) sscanf(e, "%d,%d,%d,%u", &p.full, &p.min_active, &p.first_last, &p.sleep_ns);
+    return p;
+  }();
+  mc_newton_kernel<ASSOC, NWARPS, DEPTH><<<(unsigned)ctx->sm_count, NWARPS * 32, smem, ctx->s_cmp>>>(k, P, ctx->stats, ctx->work_ctr, list, list_yl, pol,
+                                                                                                   list_deps);
   return EO_OK;
 }
 
@@ -1323,11 +939,7 @@ static int mc_launch(eo_ctx* ctx, const mc_consts& k, const mc_ptrs& P, int64_t 
   const int64_t grid = ntiles < ctx->sm_count ? ntiles : ctx->sm_count;
   cudaError_t e = cudaMemsetAsync(ctx->work_ctr, 0, 256, ctx->s_cmp);
   if (e != cudaSuccess) return eo_fail(ctx, EO_ERR_CUDA, "eo_mc_eval: cudaMemsetAsync: %s", cudaGetErrorString(e));
-  if (scheme == 0) {
-    // large batches with the associative flow rule (46-field slots leave shared memory for the streaming pass 1): overlapped
-    if (k.assoc && mco_config_get().min_n >= 0 && n >= mco_config_get().min_n) return mc_launch_overlap<true>(ctx, k, P, n);
-    return k.assoc ? mc_launch_classes<true>(ctx, k, P, n) : mc_launch_classes<false>(ctx, k, P, n);
-  }
+  if (scheme == 0) return k.assoc ? mc_launch_classes<true>(ctx, k, P, n) : mc_launch_classes<false>(ctx, k, P, n);
   int rc;
   if (scheme == 2)  // one pass, no stage affinity: any warp takes the highest-priority full queue (A/B measurements)
     rc = k.assoc ? mc_launch_queue<true, 0, false>(ctx, k, P, n, smem, (unsigned)grid) : mc_launch_queue<false, 0, false>(ctx, k, P, n, smem, (unsigned)grid);

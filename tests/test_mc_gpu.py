@@ -109,43 +109,6 @@ def test_mc_schemes_agree(ctx):
         assert np.array_equal(st[scheme]["niter_hist"], st[0]["niter_hist"])
 
 
-@pytest.mark.parametrize("n,cfg", [(60_001, "0,4096,2"), (4097, "0,4096,8"), (128, "0,128,1"), (1, "0,4096,8"),
-                                   (300_000, "0,65536,8"), (200_000, "0,0,8")])
-def test_mc_overlapped_scheme(ctx, monkeypatch, n, cfg):
-    """The overlapped scheme (streaming pass 1 of chunk c + 1 beside pass 2 of chunk c; default for large resident
-    batches) forced onto small batches with small chunks (EO_MC_OVERLAP = min_n,chunk,first_mult): the same per-point code
-    as the two-launch scheme -> bit-identical results and equal statistics; and the usual parity against the oracle."""
-    d, s = inputs.mc_batch(n, seed=n + 3, stepper=_stepper())
-    dd, ds = ctx.to_device(d.reshape(-1)), ctx.to_device(s.reshape(-1))
-    q = McParams(PRM.E, PRM.nu, PRM.c, PRM.phi, PRM.psi, PRM.theta_T, PRM.a, PRM.tol, PRM.Nitermax)
-    res, st = {}, {}
-    for mode in ("0", cfg):
-        monkeypatch.setenv("EO_MC_OVERLAP", mode)
-        o = {"C_tang": ctx.empty((16 * n,)), "sigma": ctx.empty((4 * n,)), "niter": ctx.empty((n,), dtype=np.int32),
-             "yielding": ctx.empty((n,)), "norm_res": ctx.empty((n,)), "dlambda": ctx.empty((n,))}
-        for a in o.values():
-            ctx.check(ctx.lib.eo_dev_memset(ctx.handle, a.ptr, 0xFF, a.nbytes))
-        ctx.stats_reset()
-        for rep in range(2):  # twice: scratch / counters / events are reused
-            ctx.check(ctx.lib.eo_mc_eval(ctx.handle, C.byref(q), dd.ptr, ds.ptr, o["C_tang"].ptr, o["sigma"].ptr,
-                                         o["niter"].ptr, o["yielding"].ptr, o["norm_res"].ptr, o["dlambda"].ptr, n))
-        ctx.sync()
-        st[mode] = ctx.stats()
-        res[mode] = {k: v.to_host() for k, v in o.items()}
-        for a in o.values():
-            a.free()
-    a, b = res["0"], res[cfg]
-    for key in a:
-        assert np.array_equal(a[key], b[key], equal_nan=True), key
-    for key in ("n_points", "n_plastic", "n_nonconverged", "n_nonfinite", "niter_max", "f_max", "res_max"):
-        assert st["0"][key] == st[cfg][key], key
-    assert st[cfg]["n_points"] == 2 * n
-    assert np.array_equal(st["0"]["niter_hist"], st[cfg]["niter_hist"])
-    b = {k: (v.reshape(-1, 4, 4) if k == "C_tang" else v.reshape(-1, 4) if k == "sigma" else v) for k, v in b.items()}
-    _check(b, native.mc_return_mapping(d, s, PRM, parallel=True), d, s)
-    dd.free(), ds.free()
-
-
 def test_mc_demo_tracing_path(ctx):
     """The demo's yield-surface tracing driver (demo_mc:853-930) walked with the GPU kernel as the stress
     update: same iteration histogram as the reference and same stresses as the oracle."""
