@@ -25,16 +25,16 @@ static void isi_compact(const isi_weights& w, isi_weights_c& c) {
   memcpy(c.H, w.H, sizeof c.H);
 }
 
-#define ISI_THREADS 256  // one CTA per SM: 19 KB of weights + 192 KB of activation scratch
-#define ISI_SMEM (sizeof(isi_weights_c) + size_t(ISI_NH) * ISI_THREADS * 3 * sizeof(float))
+#define ISI_THREADS 384  // one CTA per SM (12 warps, 168 registers): 19 KB of weights + 192 KB of activation scratch
+#define ISI_SMEM (sizeof(isi_weights_c) + size_t(ISI_NH) * ISI_THREADS * 2 * sizeof(float))
 
-__global__ void __launch_bounds__(ISI_THREADS) isihara_kernel(const isi_weights_c* __restrict__ gw,
+__global__ void __launch_bounds__(ISI_THREADS, 1) isihara_kernel(const isi_weights_c* __restrict__ gw,
                                                               const double* __restrict__ F, double* __restrict__ dP,
                                                               double* __restrict__ P, int64_t n) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   isi_weights_c& W = *reinterpret_cast<isi_weights_c*>(s_raw);
-  // layer-1 activation scratch: [unit][thread][phi, phi', phi''] - consecutive threads are 3 words apart: conflict free
-  float* zs = reinterpret_cast<float*>(s_raw + sizeof(isi_weights_c)) + 3 * threadIdx.x;
+  // layer-1 activation scratch: [unit][thread][u, w] - consecutive threads are 2 words apart: one 64-bit access per unit
+  float* zs = reinterpret_cast<float*>(s_raw + sizeof(isi_weights_c)) + 2 * threadIdx.x;
   {
     const int nw = int(sizeof(isi_weights_c) / 16);
     const float4* src = reinterpret_cast<const float4*>(gw);
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(ISI_THREADS) isihara_kernel(const isi_weights_
     const eo_d4 f = eo_ld256(F + 4 * i);
     const double Fv[4] = {f.x, f.y, f.z, f.w};
     double Pv[4], T[16];
-    isi_point(W, Fv, Pv, T, zs, 3 * ISI_THREADS);
+    isi_point(W, Fv, Pv, T, zs, 2 * ISI_THREADS);
     double* o = dP + 16 * i;
     eo_st256(o + 0, T[0], T[1], T[2], T[3]);
     eo_st256(o + 4, T[4], T[5], T[6], T[7]);

@@ -52,6 +52,10 @@ struct isi_weights_c {
   double H[4];
 };
 
+struct __attribute__((aligned(8))) isi_f2 {
+  float x, y;
+};
+
 // softplus and the activation phi(a) = softplus(a)^2 / 12 with its first two derivatives, float32.
 // torch.nn.functional.softplus is log1p(exp(a)), linear above the threshold 20.  Evaluated here in the symmetric form
 //     t = exp(-|a|) in (0, 1],   softplus(a) = max(a, 0) + log1p(t),   sigmoid(a) = (a >= 0 ? 1 : t) / (1 + t)
@@ -62,7 +66,7 @@ struct isi_weights_c {
 // product a log2(e), which moves softplus by at most 0.28 x 2^-23; lg2.approx is within 2^-22 absolute on (1, 2], i.e.
 // softplus within 1.7e-7 absolute where it is read from the SFU (t >= 2^-7), and the series t - t^2/2 + t^3/3 (error
 // < 1e-9) is used below.  Measured against the reference golden: tests/isi_util.py.
-EO_ISI_HD void isi_phi(float a, float& p0, float& p1, float& p2) {
+EO_ISI_HD void isi_softplus(float a, float& sp, float& sg) {
 #if defined(__CUDA_ARCH__)
   float t, lg, r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fabsf(a) * -1.4426950408889634f));
@@ -75,21 +79,29 @@ EO_ISI_HD void isi_phi(float a, float& p0, float& p1, float& p2) {
   const float t = expf(-fabsf(a));
   const float l1p = log1pf(t), r = 1.0f / (1.0f + t);
 #endif
-  const float sp = fmaxf(a, 0.0f) + l1p;
-  const float sg = (a >= 0.0f ? 1.0f : t) * r;  // sigmoid = d softplus / da
-  const float sg1 = sg * (1.0f - sg);           // d sigmoid / da
+  sp = fmaxf(a, 0.0f) + l1p;
+  sg = (a >= 0.0f ? 1.0f : t) * r;  // sigmoid = d softplus / da
+}
+EO_ISI_HD void isi_phi(float a, float& p0, float& p1, float& p2) {
+  float sp, sg;
+  isi_softplus(a, sp, sg);
+  const float sg1 = sg * (1.0f - sg);  // d sigmoid / da
   p0 = sp * sp * (1.0f / 12.0f);
   p1 = sp * sg * (1.0f / 6.0f);
   p2 = (sg * sg + sp * sg1) * (1.0f / 6.0f);
 }
+// The layer-1 activations are kept between the passes as TWO floats per unit, u = softplus / sqrt(12) and
+// w = sigmoid / sqrt(3) (512 bytes of scratch per point instead of 768: 12 instead of 8 warps per SM), from which
+//     phi = u^2,   phi' = u w,   phi'' = w^2 / 2 + phi' (1 - sqrt(3) w)
+// cost one or two multiplications where they are used.
+#define ISI_C_U 0.28867513459481287f  // 1 / sqrt(12)
+#define ISI_C_W 0.57735026918962584f  // 1 / sqrt(3)
+#define ISI_SQRT3 1.7320508075688772f
 
 // Two float32 FMAs in one instruction: sm_100's packed FFMA2 (fma.rn.f32x2).  A three-register scalar FFMA issues
 // every second cycle per SM sub-partition on Blackwell (B300_MICROARCH.md: rt_SMSP = 2), i.e. 64 FMA/clk/SM; the packed
 // form carries two FMAs at the same issue cost and so reaches the 128 FMA/clk/SM of the pipe.  Each half is an IEEE
 // fma: bit-identical to two scalar FFMAs.  Host build: plain multiply-add.
-struct isi_f2 {
-  float x, y;
-};
 EO_ISI_HD isi_f2 isi_fma2(isi_f2 a, isi_f2 b, isi_f2 c) {
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
   const float2 r = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y));
@@ -101,9 +113,9 @@ EO_ISI_HD isi_f2 isi_fma2(isi_f2 a, isi_f2 b, isi_f2 c) {
 
 // y(x), dy/dx (3), d2y/dx2 (6: xx, xy, xz, yy, yz, zz) of the network, float32.
 // `W` may live in shared memory (device) or anywhere (host).  `zs` is per-point scratch for the layer-1
-// activations (phi, phi', phi'' of the 64 units, computed ONCE): element (i, c) at zs[i * zstride + c], c = 0..2
-// - shared memory on the device (12-byte cells, consecutive threads 3 words apart: conflict free), a local array on
-// the host.  WT: isi_weights or isi_weights_c.
+// activations ((u, w) of the 64 units, see above, computed ONCE): the 8-byte cell of unit i at zs + i * zstride
+// (8-byte aligned) - shared memory on the device (consecutive threads 2 words apart: one 64-bit access per unit, no
+// bank conflicts), a local array on the host.  WT: isi_weights or isi_weights_c.
 template <class WT>
 EO_ISI_HD void isi_network(const WT& W, const float x[3], float* zs, int zstride, float& y, float gx[3],
                            float hx[6]) {
@@ -115,10 +127,9 @@ EO_ISI_HD void isi_network(const WT& W, const float x[3], float* zs, int zstride
 #pragma unroll 4
   for (int i = 0; i < ISI_NH; ++i) {
     const float a1 = W.A1[i][0] * x[0] + W.A1[i][1] * x[1] + W.A1[i][2] * x[2] + W.A1[i][3];
-    float p0, p1, p2;
-    isi_phi(a1, p0, p1, p2);
-    float* z = zs + i * zstride;
-    z[0] = p0, z[1] = p1, z[2] = p2;
+    float sp, sg;
+    isi_softplus(a1, sp, sg);
+    *reinterpret_cast<isi_f2*>(zs + i * zstride) = isi_f2{sp * ISI_C_U, sg * ISI_C_W};
   }
   // ---- pass A: a2_j and d_j = da2_j/dx for blocks of 16 outputs (64 accumulators in registers, paired along j for
   //      the packed FMA); weights read as W2T[i][jb .. jb+15]: contiguous, four 128-bit broadcasts per 32 FFMA2
@@ -136,9 +147,9 @@ EO_ISI_HD void isi_network(const WT& W, const float x[3], float* zs, int zstride
     }
 #pragma unroll 2
     for (int i = 0; i < ISI_NH; ++i) {
-      const float* z = zs + i * zstride;
-      const float p1 = z[1];
-      const float z0 = z[0], z1 = p1 * W.A1[i][0], z2 = p1 * W.A1[i][1], z3 = p1 * W.A1[i][2];
+      const isi_f2 uw = *reinterpret_cast<const isi_f2*>(zs + i * zstride);
+      const float p1 = uw.x * uw.y;
+      const float z0 = uw.x * uw.x, z1 = p1 * W.A1[i][0], z2 = p1 * W.A1[i][1], z3 = p1 * W.A1[i][2];
       const isi_f2 zz[4] = {{z0, z0}, {z1, z1}, {z2, z2}, {z3, z3}};
 #pragma unroll
       for (int m = 0; m < 8; ++m) {
@@ -172,8 +183,8 @@ EO_ISI_HD void isi_network(const WT& W, const float x[3], float* zs, int zstride
 #pragma unroll
     for (int j = 0; j < ISI_NH; j += 2) v2 = isi_fma2(isi_f2{W.W2T[i][j], W.W2T[i][j + 1]}, isi_f2{g[j], g[j + 1]}, v2);
     const float v = v2.x + v2.y;
-    const float* z = zs + i * zstride;
-    const float p1 = z[1], p2 = z[2];
+    const isi_f2 uw = *reinterpret_cast<const isi_f2*>(zs + i * zstride);
+    const float p1 = uw.x * uw.y, p2 = fmaf(0.5f * uw.y, uw.y, p1 * fmaf(-ISI_SQRT3, uw.y, 1.0f));
     const float A0 = W.A1[i][0], A1 = W.A1[i][1], A2 = W.A1[i][2];
     const float t1 = p1 * v, t2 = p2 * v;
     G0 += A0 * t1, G1 += A1 * t1, G2 += A2 * t1;
@@ -230,15 +241,30 @@ EO_ISI_HD isi_jet isi_compose(const isi_jet& u, double f0, double f1, double f2)
     for (int j = i; j < 4; ++j) r.h[ISI_SYM(i, j)] = f2 * u.g[i] * u.g[j] + f1 * u.h[ISI_SYM(i, j)];
   return r;
 }
-EO_ISI_HD isi_jet isi_pow(const isi_jet& u, double p) {
-  const double f0 = pow(u.v, p);
+// u^p with the value f0 = pow(u.v, p) supplied by the caller
+EO_ISI_HD isi_jet isi_pow(const isi_jet& u, double p, double f0) {
   return isi_compose(u, f0, p * f0 / u.v, p * (p - 1.0) * f0 / (u.v * u.v));
 }
 
 // One point: F = [F11, F12, F21, F22] (:263-266)  ->  P (4), tangent dP_i/dF_j (row-major 4x4)
-// zs / zstride: scratch for isi_network (3 * ISI_NH floats per point when zstride = 3)
+// zs / zstride: scratch for isi_network (2 * ISI_NH floats per point when zstride = 2), 8-byte aligned
 template <class WT>
 EO_ISI_HD void isi_point(const WT& W, const double F[4], double P[4], double dP[16], float* zs, int zstride) {
+  // features (:269-283) as plain values first: the 2nd-order jets (42 doubles) are built AFTER the network so that they
+  // do not occupy registers while it runs; the three powers of I3 are computed once and handed on
+  double pw[3];
+  float x[3];
+  {
+    const double C11 = F[0] * F[0] + F[2] * F[2], C12 = F[0] * F[1] + F[2] * F[3], C22 = F[1] * F[1] + F[3] * F[3];
+    const double C1221 = C12 * C12, C1122 = C11 * C22;
+    const double I1 = (C11 + C22) + 1.0, I2 = ((C11 + C22) - C1221) + C1122, I3 = C1122 - C1221;
+    pw[0] = pow(I3, -1.0 / 3.0), pw[1] = pow(I3, -2.0 / 3.0), pw[2] = pow(I3, 0.5);
+    const double Jm1 = pw[2] - 1.0;
+    x[0] = (float)(I1 * pw[0] - 3.0), x[1] = (float)(I2 * pw[1] - 3.0), x[2] = (float)(Jm1 * Jm1);
+  }
+  // network in float32 (:286)
+  float y, gx[3], hx[6];
+  isi_network(W, x, zs, zstride, y, gx, hx);
   const isi_jet F11 = isi_var(F[0], 0), F12 = isi_var(F[1], 1), F21 = isi_var(F[2], 2), F22 = isi_var(F[3], 3);
   // right Cauchy-Green tensor and invariants (:269-277)
   const isi_jet C11 = isi_add(isi_mul(F11, F11), isi_mul(F21, F21));
@@ -251,17 +277,13 @@ EO_ISI_HD void isi_point(const WT& W, const double F[4], double P[4], double dP[
   const isi_jet I3 = isi_add(C1122, C1221, -1.0);
   // features (:280-283)
   isi_jet X[3];
-  X[0] = isi_addc(isi_mul(I1, isi_pow(I3, -1.0 / 3.0)), -3.0);
-  X[1] = isi_addc(isi_mul(I2, isi_pow(I3, -2.0 / 3.0)), -3.0);
+  X[0] = isi_addc(isi_mul(I1, isi_pow(I3, -1.0 / 3.0, pw[0])), -3.0);
+  X[1] = isi_addc(isi_mul(I2, isi_pow(I3, -2.0 / 3.0, pw[1])), -3.0);
   {
-    const isi_jet J = isi_pow(I3, 0.5);
+    const isi_jet J = isi_pow(I3, 0.5, pw[2]);
     const isi_jet Jm1 = isi_addc(J, -1.0);
     X[2] = isi_mul(Jm1, Jm1);
   }
-  // network in float32 (:286)
-  const float x[3] = {(float)X[0].v, (float)X[1].v, (float)X[2].v};
-  float y, gx[3], hx[6];
-  isi_network(W, x, zs, zstride, y, gx, hx);
   const double Wx[3] = {(double)gx[0], (double)gx[1], (double)gx[2]};
   const double Wxx[3][3] = {{(double)hx[0], (double)hx[1], (double)hx[2]},
                             {(double)hx[1], (double)hx[3], (double)hx[4]},

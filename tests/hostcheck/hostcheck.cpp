@@ -105,8 +105,8 @@ int hostcheck_form(int gdim, int bs, int nb, int nq, int kind_test, int kind_tri
 void hostcheck_isihara(const isi_weights* w, const double* F, double* dP, double* P, int64_t n) {
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < n; ++i) {
-    float zs[3 * ISI_NH];
-    isi_point(*w, F + 4 * i, P + 4 * i, dP + 16 * i, zs, 3);
+    alignas(8) float zs[2 * ISI_NH];
+    isi_point(*w, F + 4 * i, P + 4 * i, dP + 16 * i, zs, 2);
   }
 }
 
