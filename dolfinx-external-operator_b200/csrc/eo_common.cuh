@@ -216,6 +216,37 @@ __device__ __forceinline__ void eo_st64(double* p, double x) {
   asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(x) : "memory");
 }
 
+// 4x4 tangents of the four consecutive points of a lane quad (lanes 4k..4k+3), stored as WHOLE 128-byte lines:
+// a warp-wide 256-bit store of per-thread 128-byte records touches 32 different lines per instruction (32 L1
+// wavefronts; four instructions per tangent), which is what bounds the fused kernels, not HBM.  The quad swaps rows
+// with a two-stage butterfly (2 x 16 SHFL.32) so that lane r holds row r of all four points; instruction j then
+// writes point j's full line from the four lanes of the quad: 8 lines per instruction.  The values are untouched.
+// Must be called by all 32 lanes; `C_quad` = address of the tangent of the quad's FIRST point, `n_valid` = how many
+// of the quad's points exist (0..4).
+__device__ __forceinline__ void eo_st_tangent_quad(double* C_quad, int n_valid, double C[16]) {
+  unsigned lane;
+  asm("mov.u32 %0, %%laneid;" : "=r"(lane));
+  const bool b2 = lane & 2u, b1 = lane & 1u;
+#pragma unroll
+  for (int s = 0; s < 2; ++s)  // rows (s, s + 2) <-> lanes (q, q ^ 2)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double got = __shfl_xor_sync(0xffffffffu, b2 ? C[4 * s + k] : C[4 * (s + 2) + k], 2);
+      if (b2) C[4 * s + k] = got; else C[4 * (s + 2) + k] = got;
+    }
+#pragma unroll
+  for (int s = 0; s < 4; s += 2)  // rows (s, s + 1) <-> lanes (q, q ^ 1)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double got = __shfl_xor_sync(0xffffffffu, b1 ? C[4 * s + k] : C[4 * (s + 1) + k], 1);
+      if (b1) C[4 * s + k] = got; else C[4 * (s + 1) + k] = got;
+    }
+  double* row = C_quad + 4 * (lane & 3u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (j < n_valid) eo_st256(row + 16 * j, C[4 * j + 0], C[4 * j + 1], C[4 * j + 2], C[4 * j + 3]);
+}
+
 // block-wide sum of per-thread counts (grid-stride kernels: a thread may have counted several points)
 __device__ __forceinline__ void eo_block_sum_add(unsigned long long* dst, int count) {
   __shared__ int s_sum;

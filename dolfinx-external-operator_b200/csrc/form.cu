@@ -66,23 +66,24 @@ __device__ __forceinline__ double form_geometry(const tab_tables& T, const int32
   return form_geometry_xv<GDIM>(T, xv, K);
 }
 
+// the same from the per-cell cache of the handle when it exists (eo_tab_geometry; warp-uniform branch): one 256-bit and one
+// 64-bit load instead of 3 + 6 dependent ones and the division
+__device__ __forceinline__ double form_cell_geometry(const tab_tables& T, const int32_t* __restrict__ x_dofmap,
+                                                     const double* __restrict__ x, const double* __restrict__ geoK,
+                                                     const double* __restrict__ geoD, int64_t c, double K[2][2]) {
+  if (geoK) {
+    const eo_d4 k = eo_ld256(geoK + 4 * c);
+    K[0][0] = k.x, K[0][1] = k.y, K[1][0] = k.z, K[1][1] = k.w;
+    return eo_ld64(geoD + c);
+  }
+  return form_geometry<2>(T, x_dofmap, x, c, K);
+}
+
 // the cell's coefficients through the dofmap (read-only path; neighbouring cells / points share nodes: L1/L2 hits)
 template <int BS, int NB>
 __device__ __forceinline__ void form_gather(const int32_t* __restrict__ dofmap, const double* __restrict__ u, int64_t c,
                                             double w[NB][BS]) {
-  int32_t idx[NB];
-#pragma unroll
-  for (int a = 0; a < NB; ++a) idx[a] = __ldg(dofmap + c * NB + a);
-#pragma unroll
-  for (int a = 0; a < NB; ++a) {
-    if constexpr (BS == 2) {
-      const double2 v = __ldg(reinterpret_cast<const double2*>(u) + idx[a]);
-      w[a][0] = v.x, w[a][1] = v.y;
-    } else {
-#pragma unroll
-      for (int k = 0; k < BS; ++k) w[a][k] = __ldg(u + int64_t(BS) * idx[a] + k);
-    }
-  }
+  tab_gather<BS, NB>(dofmap, u, c, w);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -341,7 +342,8 @@ __global__ void __launch_bounds__(128) form_action_tma_kernel(const __grid_const
                                                               const __grid_constant__ form_weights W, int kind_test,
                                                               int kind_trial, const int32_t* __restrict__ dofmap,
                                                               const int32_t* __restrict__ x_dofmap,
-                                                              const double* __restrict__ x, const double* __restrict__ D,
+                                                              const double* __restrict__ x, const double* __restrict__ geoK,
+                                                              const double* __restrict__ geoD, const double* __restrict__ D,
                                                               const double* __restrict__ xin, int64_t n_cells,
                                                               double* __restrict__ y) {
   extern __shared__ __align__(128) unsigned char form_smem_raw[];
@@ -365,7 +367,7 @@ __global__ void __launch_bounds__(128) form_action_tma_kernel(const __grid_const
   double K[2][2], w[NB][2], adet = 0.0;
   int32_t idx[NB];
   if (c < n_cells) {
-    adet = form_geometry<2>(T, x_dofmap, x, c, K);
+    adet = form_cell_geometry(T, x_dofmap, x, geoK, geoD, c, K);
 #pragma unroll
     for (int a = 0; a < NB; ++a) idx[a] = __ldg(dofmap + c * NB + a);
 #pragma unroll
@@ -416,9 +418,9 @@ template <int NB, bool EXACT>
 __global__ void __launch_bounds__(FORM_THREADS, 3) form_vm_step_kernel(
     const __grid_constant__ tab_tables T, const __grid_constant__ form_weights W, const vm_consts vq,
     const int32_t* __restrict__ dofmap, const int32_t* __restrict__ x_dofmap, const double* __restrict__ x,
-    const double* __restrict__ u, int64_t n_cells, const double* __restrict__ sigma_n, const double* __restrict__ p,
-    double* __restrict__ C_tang, double* __restrict__ sigma, double* __restrict__ dp_out, double* __restrict__ b,
-    eo_stats* stats) {
+    const double* __restrict__ u, const double* __restrict__ geoK, const double* __restrict__ geoD, int64_t n_cells,
+    const double* __restrict__ sigma_n, const double* __restrict__ p, double* __restrict__ C_tang,
+    double* __restrict__ sigma, double* __restrict__ dp_out, double* __restrict__ b, eo_stats* stats) {
   extern __shared__ double s_fe[];
   __shared__ form_tabs<2, NB> S;
   form_stage_tables<2, NB>(T, S);
@@ -435,7 +437,7 @@ __global__ void __launch_bounds__(FORM_THREADS, 3) form_vm_step_kernel(
       const double pi = eo_ld64(p + i);
       double w[NB][2];
       form_gather<2, NB>(dofmap, u, t.c, w);
-      scale = W.w[t.q] * form_geometry<2>(T, x_dofmap, x, t.c, K);
+      scale = W.w[t.q] * form_cell_geometry(T, x_dofmap, x, geoK, geoD, t.c, K);
       double val[2] = {0.0, 0.0}, grad[2][2], e[4];
       form_point<2, 2, NB>(S, w, K, t.q, false, true, val, grad);
       tab_operand<2, 2>(2, val, grad, e);
@@ -888,6 +890,10 @@ int eo_form_action(eo_form* f, int kind_test, int kind_trial, const double* D, c
   // dP/dF of the hyperelasticity demo (gradient both sides)   (EO_FORM_ACTION_TMA=0: register-path kernel, for A/B)
   const bool tma = form_env("EO_FORM_ACTION_TMA", 1) && t->T.gdim == 2 && t->T.bs == 2 && t->T.nq == 3 && kt != 0 && ki != 0 &&
                    eo_aligned(D, 32);
+  if (tma && n_cells > 0) {
+    const int grc = eo_tab_geometry(t);
+    if (grc != EO_OK) return grc;
+  }
   // the cells [c0, c1): every per-cell / per-point array is addressed relative to c0
   auto launch = [&](int64_t c0, int64_t c1, const double* dx, double* dy) -> int {
     const int64_t m = c1 - c0;
@@ -902,7 +908,8 @@ int eo_form_action(eo_form* f, int kind_test, int kind_trial, const double* D, c
       const size_t sm = 128 + 128 * (3 * 128 + 16);                                                                      \
       auto kfn = form_action_tma_kernel<(G == 2 && B == 2 ? N : 3), 3>;                                                  \
       cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm));                                   \
-      kfn<<<gc, 128, sm, ctx->s_cmp>>>(t->T, W, kt, ki, dm, xd, t->x, Dc, dx, m, dy);                                    \
+      kfn<<<gc, 128, sm, ctx->s_cmp>>>(t->T, W, kt, ki, dm, xd, t->x, t->geoK ? t->geoK + 4 * c0 : nullptr,              \
+                                       t->geoK ? t->geoD + c0 : nullptr, Dc, dx, m, dy);                                 \
     } else if (t->T.nq == 3) {                                                                                           \
       form_action_cell_kernel<G, B, N, 3><<<gc, 128, 0, ctx->s_cmp>>>(t->T, W, kt, ki, dm, xd, t->x, Dc, dx, m, dy);     \
     } else {                                                                                                             \
@@ -952,28 +959,32 @@ int eo_form_vm_step(eo_form* f, const eo_vm_params* prm, const double* u, const 
   const vm_consts q{prm->lmbda, prm->mu, prm->H, prm->sigma_0};
   form_weights W;
   memcpy(W.w, f->w, sizeof(W.w));
+  if (n_cells > 0) {
+    const int grc = eo_tab_geometry(t);
+    if (grc != EO_OK) return grc;
+  }
   // the cells [c0, c1): every per-cell / per-point array is addressed relative to c0
   auto launch = [&](int64_t c0, int64_t c1, const double* du, double* db) -> int {
     const int64_t m = c1 - c0, o = c0 * t->T.nq;
     const unsigned grid = form_grid(ctx, t, m);
-#define EO_STEP(N)                                                                                                          \
-  if (t->T.nb == N) {                                                                                                       \
-    if (exact) {                                                                                                            \
-      const size_t sm = form_smem(ctx, form_vm_step_kernel<N, true>, N * 2);                                                \
-      form_vm_step_kernel<N, true><<<grid, FORM_THREADS, sm, ctx->s_cmp>>>(                                                 \
-          t->T, W, q, t->dofmap + c0 * N, t->x_dofmap + c0 * 3, t->x, du, m, sigma_n + 4 * o, p + o, C_tang + 16 * o,       \
-          sigma + 4 * o, dp + o, db, ctx->stats);                                                                           \
-    } else {                                                                                                                \
-      const size_t sm = form_smem(ctx, form_vm_step_kernel<N, false>, N * 2);                                               \
-      form_vm_step_kernel<N, false><<<grid, FORM_THREADS, sm, ctx->s_cmp>>>(                                                \
-          t->T, W, q, t->dofmap + c0 * N, t->x_dofmap + c0 * 3, t->x, du, m, sigma_n + 4 * o, p + o, C_tang + 16 * o,       \
-          sigma + 4 * o, dp + o, db, ctx->stats);                                                                           \
-    }                                                                                                                       \
+#define EO_STEP_ARGS(N)                                                                                              \
+  t->T, W, q, t->dofmap + c0 * N, t->x_dofmap + c0 * 3, t->x, du, t->geoK ? t->geoK + 4 * c0 : nullptr,                \
+      t->geoK ? t->geoD + c0 : nullptr, m, sigma_n + 4 * o, p + o, C_tang + 16 * o, sigma + 4 * o, dp + o, db, ctx->stats
+#define EO_STEP_X(N, X)                                                                                              \
+  if (bool(exact) == X) {                                                                                            \
+    const size_t sm = form_smem(ctx, form_vm_step_kernel<N, X>, N * 2);                                              \
+    form_vm_step_kernel<N, X><<<grid, FORM_THREADS, sm, ctx->s_cmp>>>(EO_STEP_ARGS(N));                              \
+  }
+#define EO_STEP(N)                                                                                                   \
+  if (t->T.nb == N) {                                                                                                \
+    EO_STEP_X(N, true) else EO_STEP_X(N, false)                                                                      \
   }
     EO_STEP(3)
     EO_STEP(6)
     EO_STEP(10)
 #undef EO_STEP
+#undef EO_STEP_X
+#undef EO_STEP_ARGS
     ctx->launches += 1;
     return EO_OK;
   };

@@ -207,14 +207,18 @@ struct isi_jet {
 EO_ISI_HD isi_jet isi_var(double val, int k) {
   isi_jet r;
   r.v = val;
+#pragma unroll
   for (int i = 0; i < 4; ++i) r.g[i] = (i == k) ? 1.0 : 0.0;
+#pragma unroll
   for (int i = 0; i < 10; ++i) r.h[i] = 0.0;
   return r;
 }
 EO_ISI_HD isi_jet isi_add(const isi_jet& a, const isi_jet& b, double sb = 1.0) {
   isi_jet r;
   r.v = a.v + sb * b.v;
+#pragma unroll
   for (int i = 0; i < 4; ++i) r.g[i] = a.g[i] + sb * b.g[i];
+#pragma unroll
   for (int i = 0; i < 10; ++i) r.h[i] = a.h[i] + sb * b.h[i];
   return r;
 }
@@ -226,8 +230,11 @@ EO_ISI_HD isi_jet isi_addc(const isi_jet& a, double c) {
 EO_ISI_HD isi_jet isi_mul(const isi_jet& a, const isi_jet& b) {
   isi_jet r;
   r.v = a.v * b.v;
+#pragma unroll
   for (int i = 0; i < 4; ++i) r.g[i] = a.g[i] * b.v + a.v * b.g[i];
+#pragma unroll
   for (int i = 0; i < 4; ++i)
+#pragma unroll
     for (int j = i; j < 4; ++j)
       r.h[ISI_SYM(i, j)] = a.h[ISI_SYM(i, j)] * b.v + a.v * b.h[ISI_SYM(i, j)] + a.g[i] * b.g[j] + a.g[j] * b.g[i];
   return r;
@@ -236,8 +243,11 @@ EO_ISI_HD isi_jet isi_mul(const isi_jet& a, const isi_jet& b) {
 EO_ISI_HD isi_jet isi_compose(const isi_jet& u, double f0, double f1, double f2) {
   isi_jet r;
   r.v = f0;
+#pragma unroll
   for (int i = 0; i < 4; ++i) r.g[i] = f1 * u.g[i];
+#pragma unroll
   for (int i = 0; i < 4; ++i)
+#pragma unroll
     for (int j = i; j < 4; ++j) r.h[ISI_SYM(i, j)] = f2 * u.g[i] * u.g[j] + f1 * u.h[ISI_SYM(i, j)];
   return r;
 }
@@ -289,16 +299,22 @@ EO_ISI_HD void isi_point(const WT& W, const double F[4], double P[4], double dP[
                             {(double)hx[1], (double)hx[3], (double)hx[4]},
                             {(double)hx[2], (double)hx[4], (double)hx[5]}};
   // chain rule to F, then the corrections P += F @ H, dP += H^T with H the 4x4 block matrix of :368-376
+#pragma unroll
   for (int i = 0; i < 4; ++i) {
     double acc = 0.0;
+#pragma unroll
     for (int k = 0; k < 3; ++k) acc += Wx[k] * X[k].g[i];
     P[i] = acc;
   }
+#pragma unroll
   for (int i = 0; i < 4; ++i)
+#pragma unroll
     for (int j = 0; j < 4; ++j) {
       double acc = 0.0;
+#pragma unroll
       for (int k = 0; k < 3; ++k) {
         acc += Wx[k] * X[k].h[ISI_SYM(i, j)];
+#pragma unroll
         for (int l = 0; l < 3; ++l) acc += Wxx[k][l] * X[k].g[i] * X[l].g[j];
       }
       dP[4 * i + j] = acc;

@@ -18,6 +18,9 @@
 #include "tab_core.cuh"
 #include "tab_handle.cuh"
 #include "vm_core.cuh"
+#include "form_core.cuh"
+
+#include <cstdlib>
 
 #ifndef TAB_FUSED_WAVES
 #define TAB_FUSED_WAVES 8
@@ -50,18 +53,57 @@ __global__ void __launch_bounds__(128) tab_kernel(const __grid_constant__ tab_ta
   }
 }
 
+// K = J^-1 and |det J| of every cell, once per handle: exactly the values tab_geometry / form_geometry_xv give the
+// kernels that compute them per point (same statements, this file and form.cu are compiled with -fmad=false)
+__global__ void __launch_bounds__(256) tab_geometry_kernel(const __grid_constant__ tab_tables T,
+                                                           const int32_t* __restrict__ x_dofmap,
+                                                           const double* __restrict__ x, int64_t n_cells,
+                                                           double* __restrict__ geoK, double* __restrict__ geoD) {
+  const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (c >= n_cells) return;
+  double xv[3][2], K[2][2];
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    const int32_t node = __ldg(x_dofmap + c * 3 + v);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) xv[v][i] = __ldg(x + 3 * int64_t(node) + i);
+  }
+  const double adet = form_geometry_xv<2>(T, xv, K);
+  eo_st256(geoK + 4 * c, K[0][0], K[0][1], K[1][0], K[1][1]);
+  eo_st64(geoD + c, adet);
+}
+
+int eo_tab_geometry(eo_tab* t) {
+  static const bool on = [] { const char* e = getenv("EO_GEOM_CACHE"); return !(e && *e == '0'); }();
+  if (!on || t->geoK || t->T.gdim != 2 || t->n_cells == 0) return EO_OK;
+  eo_ctx* ctx = t->ctx;
+  double *k = nullptr, *d = nullptr;
+  if (cudaMalloc(&k, size_t(t->n_cells) * 32) != cudaSuccess || cudaMalloc(&d, size_t(t->n_cells) * 8) != cudaSuccess) {
+    cudaGetLastError();  // no room for the cache: the kernels compute the geometry per point
+    if (k) cudaFree(k);
+    return EO_OK;
+  }
+  tab_geometry_kernel<<<unsigned((t->n_cells + 255) / 256), 256, 0, ctx->s_cmp>>>(t->T, t->x_dofmap, t->x, t->n_cells, k, d);
+  EO_CUDA(ctx, cudaGetLastError());
+  t->geoK = k, t->geoD = d;
+  return EO_OK;
+}
+
 // tabulate the Mandel strain and feed it to the von Mises radial return.
 // Mapping: one thread per QUADRATURE POINT (cell = i / nq), so that the per-point streams (history in, tangent /
 // stress / dp out) are accessed exactly like in vm_kernel - consecutive threads, consecutive 32-byte records.
 // The nq threads of a cell gather the same coefficients (same sectors: one L1 request) and each contracts them
 // with the derivative-table row of its own point, staged in shared memory (the row index is not warp uniform,
 // which the constant bank would serialise).
-template <int NB, int NQ, bool EXACT>  // NQ > 0: evaluation points per cell known at compile time (cheap index split)
+// QUAD: the tangent leaves as whole 128-byte lines (eo_st_tangent_quad); all 32 lanes stay in the loop, lanes past the
+// end recompute the last point and store nothing.
+template <int NB, int NQ, bool EXACT, bool QUAD>  // NQ > 0: evaluation points per cell known at compile time (cheap index split)
 __global__ void __launch_bounds__(256, 4) tab_vm_kernel(const __grid_constant__ tab_tables T, const vm_consts vq,
                                                      const int32_t* __restrict__ dofmap,
                                                      const int32_t* __restrict__ x_dofmap, const double* __restrict__ x,
-                                                     const double* __restrict__ u, int64_t n_points,
-                                                     const double* __restrict__ sigma_n, const double* __restrict__ p,
+                                                     const double* __restrict__ u, const double* __restrict__ geoK,
+                                                     int64_t n_points, const double* __restrict__ sigma_n,
+                                                     const double* __restrict__ p,
                                                      double* __restrict__ C_tang, double* __restrict__ sigma,
                                                      double* __restrict__ dp_out, double* __restrict__ strain_out,
                                                      eo_stats* stats) {
@@ -73,7 +115,10 @@ __global__ void __launch_bounds__(256, 4) tab_vm_kernel(const __grid_constant__ 
   __syncthreads();
   // grid-stride over 256-point tiles: the table staging and its barrier are paid once per CTA, not once per tile
   int plastic = 0;
-  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n_points; i += int64_t(gridDim.x) * blockDim.x) {
+  for (int64_t i0 = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; (QUAD ? (i0 & ~int64_t(31)) : i0) < n_points;
+       i0 += int64_t(gridDim.x) * blockDim.x) {
+    const bool live = !QUAD || i0 < n_points;
+    const int64_t i = live ? i0 : n_points - 1;
     int64_t c;
     int q;
     if (NQ > 0) {
@@ -91,7 +136,13 @@ __global__ void __launch_bounds__(256, 4) tab_vm_kernel(const __grid_constant__ 
     const eo_d4 s = eo_ld256(sigma_n + 4 * i);
     const double pi = eo_ld64(p + i);
     double w[NB][2], K[2][2];
-    tab_load_cell<2, 2, NB>(T, dofmap, x_dofmap, x, u, c, w, K);
+    if (geoK) {  // warp uniform
+      const eo_d4 k = eo_ld256(geoK + 4 * c);
+      K[0][0] = k.x, K[0][1] = k.y, K[1][0] = k.z, K[1][1] = k.w;
+      tab_gather<2, NB>(dofmap, u, c, w);
+    } else {
+      tab_load_cell<2, 2, NB>(T, dofmap, x_dofmap, x, u, c, w, K);
+    }
     double G[2][2], grad[2][2], val[2] = {0.0, 0.0}, e[4];
 #pragma unroll
     for (int cc = 0; cc < 2; ++cc)
@@ -112,12 +163,19 @@ __global__ void __launch_bounds__(256, 4) tab_vm_kernel(const __grid_constant__ 
       vm_point(vq, e[0], e[1], e[2], e[3], s.x, s.y, s.z, s.w, pi, o);
     else
       vm_point_fast(vq, e[0], e[1], e[2], e[3], s.x, s.y, s.z, s.w, pi, o);
+    if (QUAD) {
+      const int64_t iq = i0 & ~int64_t(3);  // first point of the lane quad
+      const int64_t left = n_points - iq;
+      eo_st_tangent_quad(C_tang + 16 * iq, left >= 4 ? 4 : (left > 0 ? int(left) : 0), o.C);
+      if (!live) continue;
+    } else {
+      double* Ct = C_tang + 16 * i;
+      eo_st256(Ct + 0, o.C[0], o.C[1], o.C[2], o.C[3]);
+      eo_st256(Ct + 4, o.C[4], o.C[5], o.C[6], o.C[7]);
+      eo_st256(Ct + 8, o.C[8], o.C[9], o.C[10], o.C[11]);
+      eo_st256(Ct + 12, o.C[12], o.C[13], o.C[14], o.C[15]);
+    }
     plastic += o.dp > 0.0;
-    double* Ct = C_tang + 16 * i;
-    eo_st256(Ct + 0, o.C[0], o.C[1], o.C[2], o.C[3]);
-    eo_st256(Ct + 4, o.C[4], o.C[5], o.C[6], o.C[7]);
-    eo_st256(Ct + 8, o.C[8], o.C[9], o.C[10], o.C[11]);
-    eo_st256(Ct + 12, o.C[12], o.C[13], o.C[14], o.C[15]);
     eo_st256(sigma + 4 * i, o.g[0], o.g[1], o.g[2], o.g[3]);
     eo_st64(dp_out + i, o.dp);
     if (strain_out) eo_st256(strain_out + 4 * i, e[0], e[1], e[2], e[3]);
@@ -249,6 +307,8 @@ int eo_tab_destroy(eo_tab* t) {
   for (double* s : t->u_stage)
     if (s) cudaFree(s);
   if (t->cells_stage) cudaFree(t->cells_stage);
+  if (t->geoK) cudaFree(t->geoK);
+  if (t->geoD) cudaFree(t->geoD);
   delete t;
   return EO_OK;
 }
@@ -328,14 +388,27 @@ int eo_tab_vm_fused(eo_tab* t, const eo_vm_params* prm, const double* u, const d
   const double* d_u = nullptr;
   int rc = eo_tab_stage_u(t, u, &d_u);
   if (rc != EO_OK) return rc;
+  rc = eo_tab_geometry(t);
+  if (rc != EO_OK) return rc;
   const vm_consts q{prm->lmbda, prm->mu, prm->H, prm->sigma_0};
   const int64_t n_points = t->n_cells * t->T.nq;
   const int64_t tiles = (n_points + 255) / 256;
   const int64_t cap = int64_t(ctx->sm_count) * 4 * TAB_FUSED_WAVES;  // 4 resident CTAs per SM x a few waves each
   const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
-#define EO_FUSED_LAUNCH(N, Q, X)                                                                                         \
-  tab_vm_kernel<N, Q, X><<<grid, 256, 0, ctx->s_cmp>>>(t->T, q, t->dofmap, t->x_dofmap, t->x, d_u, n_points, sigma_n, p, \
-                                                       C_tang, sigma, dp, strain, ctx->stats)
+  // EO_QUAD_STORE=0: per-thread 128-byte tangent records (A/B; same values)
+  static const bool quad_env = [] { const char* e = getenv("EO_QUAD_STORE"); return !(e && *e == '0'); }();
+  const bool quad = quad_env && eo_aligned(C_tang, 128);
+#define EO_FUSED_LAUNCH(N, Q, X)                                                                                          \
+  do {                                                                                                                    \
+    if (quad)                                                                                                             \
+      tab_vm_kernel<N, Q, X, true><<<grid, 256, 0, ctx->s_cmp>>>(t->T, q, t->dofmap, t->x_dofmap, t->x, d_u, t->geoK,     \
+                                                                 n_points, sigma_n, p, C_tang, sigma, dp, strain,         \
+                                                                 ctx->stats);                                             \
+    else                                                                                                                  \
+      tab_vm_kernel<N, Q, X, false><<<grid, 256, 0, ctx->s_cmp>>>(t->T, q, t->dofmap, t->x_dofmap, t->x, d_u, t->geoK,    \
+                                                                  n_points, sigma_n, p, C_tang, sigma, dp, strain,        \
+                                                                  ctx->stats);                                            \
+  } while (0)
 #define EO_FUSED_CASE(N)                          \
   if (t->T.nb == N) {                             \
     if (t->T.nq == 3 && exact) EO_FUSED_LAUNCH(N, 3, true);   \

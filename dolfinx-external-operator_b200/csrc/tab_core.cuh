@@ -157,15 +157,25 @@ EO_TAB_HD void tab_operand(int kind, const double val[BS], const double grad[BS]
 }
 
 #if defined(__CUDACC__) || defined(__CUDACC_RTC__)
-// gather the cell's coefficients and inverse Jacobian (read-only path; neighbouring cells share nodes: L1/L2 hits)
-template <int GDIM, int BS, int NB>
-__device__ __forceinline__ void tab_load_cell(const tab_tables& T, const int32_t* __restrict__ dofmap,
-                                              const int32_t* __restrict__ x_dofmap, const double* __restrict__ x,
-                                              const double* __restrict__ u, int64_t c, double w[NB][BS],
-                                              double K[GDIM][GDIM]) {
-  int32_t idx[NB];
+// the cell's row of the dofmap (NB even: rows are 8-byte aligned, two indices per load)
+template <int NB>
+__device__ __forceinline__ void tab_load_idx(const int32_t* __restrict__ dofmap, int64_t c, int32_t idx[NB]) {
+  if constexpr (NB % 2 == 0) {
+    const int2* row = reinterpret_cast<const int2*>(dofmap + c * NB);
 #pragma unroll
-  for (int a = 0; a < NB; ++a) idx[a] = __ldg(dofmap + c * NB + a);
+    for (int a = 0; a < NB / 2; ++a) {
+      const int2 v = __ldg(row + a);
+      idx[2 * a] = v.x, idx[2 * a + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int a = 0; a < NB; ++a) idx[a] = __ldg(dofmap + c * NB + a);
+  }
+}
+
+// the coefficients of the dofs idx[] (blocked layout)
+template <int BS, int NB>
+__device__ __forceinline__ void tab_gather_idx(const double* __restrict__ u, const int32_t idx[NB], double w[NB][BS]) {
 #pragma unroll
   for (int a = 0; a < NB; ++a) {
     if constexpr (BS == 2) {
@@ -176,6 +186,23 @@ __device__ __forceinline__ void tab_load_cell(const tab_tables& T, const int32_t
       for (int k = 0; k < BS; ++k) w[a][k] = __ldg(u + int64_t(BS) * idx[a] + k);
     }
   }
+}
+
+template <int BS, int NB>
+__device__ __forceinline__ void tab_gather(const int32_t* __restrict__ dofmap, const double* __restrict__ u, int64_t c,
+                                           double w[NB][BS]) {
+  int32_t idx[NB];
+  tab_load_idx<NB>(dofmap, c, idx);
+  tab_gather_idx<BS, NB>(u, idx, w);
+}
+
+// gather the cell's coefficients and inverse Jacobian (read-only path; neighbouring cells share nodes: L1/L2 hits)
+template <int GDIM, int BS, int NB>
+__device__ __forceinline__ void tab_load_cell(const tab_tables& T, const int32_t* __restrict__ dofmap,
+                                              const int32_t* __restrict__ x_dofmap, const double* __restrict__ x,
+                                              const double* __restrict__ u, int64_t c, double w[NB][BS],
+                                              double K[GDIM][GDIM]) {
+  tab_gather<BS, NB>(dofmap, u, c, w);
   double xv[GDIM + 1][GDIM];
 #pragma unroll
   for (int v = 0; v < GDIM + 1; ++v) {

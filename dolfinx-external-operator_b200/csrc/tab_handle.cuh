@@ -15,7 +15,15 @@ struct eo_tab {
   double* u_stage[EO_JIT_MAX_ARGS] = {};         // device staging copies of host coefficient vectors, one per operand slot
   int32_t* cells_stage = nullptr;                // device staging copy of a host entity list
   size_t cells_stage_n = 0;
+  // per-cell geometry, computed once per handle (the coordinates are fixed at creation): inverse Jacobian, row-major
+  // [n_cells][4] (2-d meshes), and |det J| [n_cells]; built at the first fused / residual-step launch
+  double* geoK = nullptr;
+  double* geoD = nullptr;
 };
+
+// builds t->geoK / t->geoD if the handle qualifies (2-d affine cells) and EO_GEOM_CACHE is not 0; leaves them NULL
+// otherwise (not an error: the kernels then compute the geometry per point from x_dofmap / x)
+int eo_tab_geometry(eo_tab* t);
 
 // device pointer for a coefficient vector given on either side (host vectors are copied into t->u_stage[slot];
 // calls that tabulate several operands on one handle in ONE launch give every operand its own slot)
