@@ -218,6 +218,8 @@ __global__ void __launch_bounds__(128) form_vector_cell_kernel(const __grid_cons
                                                                const int32_t* __restrict__ dofmap,
                                                                const int32_t* __restrict__ x_dofmap,
                                                                const double* __restrict__ x,
+                                                               const double* __restrict__ geoK,
+                                                               const double* __restrict__ geoD,
                                                                const double* __restrict__ coef, int64_t n_cells,
                                                                double* __restrict__ b) {
   const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
@@ -225,8 +227,11 @@ __global__ void __launch_bounds__(128) form_vector_cell_kernel(const __grid_cons
   const int ncomp = tab_ncomp(kind, BS, GDIM);
   const bool vec4 = ncomp == 4 && (reinterpret_cast<uintptr_t>(coef) % 32) == 0;
   const double* s_ptr = coef + c * int64_t(T.nq) * ncomp;
-  double K[GDIM][GDIM];
-  const double adet = form_geometry<GDIM>(T, x_dofmap, x, c, K);
+  double K[GDIM][GDIM], adet;
+  if constexpr (GDIM == 2)
+    adet = form_cell_geometry(T, x_dofmap, x, geoK, geoD, c, K);
+  else
+    adet = form_geometry<GDIM>(T, x_dofmap, x, c, K);
   int32_t idx[NB];
 #pragma unroll
   for (int a = 0; a < NB; ++a) idx[a] = __ldg(dofmap + c * NB + a);
@@ -851,13 +856,15 @@ int eo_form_vector(eo_form* f, int kind_test, const double* coef, int64_t n_cell
   if (rc != EO_OK) return rc;
   const int kind = form_kind(kind_test);
   if (n_cells > 0) {
+    const int grc = eo_tab_geometry(t);
+    if (grc != EO_OK) return grc;
     form_weights W;
     memcpy(W.w, f->w, sizeof(W.w));
     bool done = false;
 #define X(G, B, N)                                                                                                     \
   if (!done && t->T.gdim == G && t->T.bs == B && t->T.nb == N) {                                                       \
     form_vector_cell_kernel<G, B, N><<<(unsigned)((n_cells + 127) / 128), 128, 0, ctx->s_cmp>>>(                       \
-        t->T, W, kind, t->dofmap, t->x_dofmap, t->x, coef, n_cells, d_b);                                              \
+        t->T, W, kind, t->dofmap, t->x_dofmap, t->x, t->geoK, t->geoD, coef, n_cells, d_b);                            \
     done = true;                                                                                                       \
   }
     EO_FORM_CASES(X)

@@ -31,13 +31,23 @@ template <int GDIM, int BS, int NB>
 __global__ void __launch_bounds__(128) tab_kernel(const __grid_constant__ tab_tables T, int kind,
                                                   const int32_t* __restrict__ dofmap,
                                                   const int32_t* __restrict__ x_dofmap, const double* __restrict__ x,
-                                                  const double* __restrict__ u, const int32_t* __restrict__ cells,
-                                                  int64_t n_cells, double* __restrict__ out) {
+                                                  const double* __restrict__ u, const double* __restrict__ geoK,
+                                                  const int32_t* __restrict__ cells, int64_t n_cells,
+                                                  double* __restrict__ out) {
   const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (i >= n_cells) return;
   const int64_t c = cells ? int64_t(cells[i]) : i;
   double w[NB][BS], K[GDIM][GDIM];
-  tab_load_cell<GDIM, BS, NB>(T, dofmap, x_dofmap, x, u, c, w, K);
+  bool cached = false;
+  if constexpr (GDIM == 2) {
+    if (geoK) {  // the handle's per-cell inverse Jacobians (eo_tab_geometry): the same values, one load
+      const eo_d4 k = eo_ld256(geoK + 4 * c);
+      K[0][0] = k.x, K[0][1] = k.y, K[1][0] = k.z, K[1][1] = k.w;
+      tab_gather<BS, NB>(dofmap, u, c, w);
+      cached = true;
+    }
+  }
+  if (!cached) tab_load_cell<GDIM, BS, NB>(T, dofmap, x_dofmap, x, u, c, w, K);
   const int ncomp = tab_ncomp(kind, BS, GDIM);
   const bool vec4 = ncomp == 4 && (reinterpret_cast<uintptr_t>(out) % 32) == 0;
   double* o = out + i * int64_t(T.nq) * ncomp;
@@ -188,11 +198,15 @@ __global__ void __launch_bounds__(256, 4) tab_vm_kernel(const __grid_constant__ 
 template <int GDIM, int BS, int NB>
 static void tab_launch_t(eo_tab* t, int kind, const double* u, const int32_t* cells, int64_t n, double* out) {
   const unsigned grid = (unsigned)((n + 127) / 128);
-  tab_kernel<GDIM, BS, NB><<<grid, 128, 0, t->ctx->s_cmp>>>(t->T, kind, t->dofmap, t->x_dofmap, t->x, u, cells, n, out);
+  tab_kernel<GDIM, BS, NB><<<grid, 128, 0, t->ctx->s_cmp>>>(t->T, kind, t->dofmap, t->x_dofmap, t->x, u, t->geoK, cells, n, out);
 }
 
 static int tab_launch(eo_tab* t, int kind, const double* u, const int32_t* cells, int64_t n, double* out) {
   const int g = t->T.gdim, b = t->T.bs, nb = t->T.nb;
+  if (kind != 0 && n > 0) {  // gradients need K: cache it on the handle at the first use
+    const int grc = eo_tab_geometry(t);
+    if (grc != EO_OK) return grc;
+  }
 #define EO_TAB_CASE(G, B, N)                      \
   if (g == G && b == B && nb == N) {              \
     tab_launch_t<G, B, N>(t, kind, u, cells, n, out); \

@@ -1,7 +1,25 @@
+"""Key metrics of one `ncu --page raw --csv` export (tools/prof_kernel.sh): python tools/ncu_keys.py TAG_raw.csv"""
 import csv, sys
 rows = list(csv.reader(open(sys.argv[1])))
 hdr, units, vals = rows[0], rows[1], rows[2]
-keys = ["gpu__time_duration.sum","sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active","sm__warps_active.avg.pct_of_peak_sustained_active","smsp__inst_executed.sum","smsp__issue_active.avg.pct_of_peak_sustained_active","smsp__thread_inst_executed_per_inst_executed.ratio","smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed","smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed","smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed","sm__cycles_elapsed.max","l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum","l1tex__data_pipe_lsu_wavefronts_mem_shared.sum","smsp__sass_inst_executed_op_local_ld.sum","smsp__sass_inst_executed_op_local_st.sum","dram__bytes_read.sum","dram__bytes_write.sum","launch__registers_per_thread"]
-for i,h in enumerate(hdr):
-    if h in keys or ("issue_stalled" in h and "per_issue_active" in h and float(vals[i] or 0) > 0.1):
-        print(h, units[i], vals[i])
+keys = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed",
+        "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed",
+        "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed", "sm__cycles_elapsed.max",
+        "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_ld.sum",
+        "l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_st.sum", "l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_red.sum",
+        "l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "smsp__sass_inst_executed_op_local_ld.sum", "smsp__sass_inst_executed_op_local_st.sum", "dram__bytes_read.sum",
+        "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed"]
+for i, h in enumerate(hdr):
+    stall = "issue_stalled" in h and "per_issue_active" in h
+    if h in keys or stall:
+        try:
+            if stall and float(vals[i] or 0) <= 0.1:
+                continue
+        except ValueError:
+            pass
+        print(h, units[i], vals[i][:110])
