@@ -693,6 +693,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) mc_newton_kernel(const mc_cons
         }
       }
     }
+    // acquire side of the hand-over (the release side is the fence before the atomicOr on s_ready below): the slot's
+    // fields are read only after the claim.  compute-sanitizer's racecheck models barriers only and still lists these
+    // slot accesses as hazards (profiles/r2_sanitizer.md).
+    __threadfence_block();
     int kind0 = 2, kind1 = 2;
     if (stage == MC_STAGE_T) {
       // ---------------------------------------------------------------- stage F: claim list entries for the lanes that
