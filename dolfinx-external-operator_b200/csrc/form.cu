@@ -468,6 +468,73 @@ __global__ void __launch_bounds__(FORM_THREADS, 3) form_vm_step_kernel(
     atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_points), (unsigned long long)(n_cells * T.nq));
 }
 
+// The same step with ONE THREAD PER CELL for three points per cell (the demos' degree-2 rule, P1 / P2 triangles): dofmap
+// row, cached geometry, coefficient gather and the history of the cell's three points are requested up front; the points
+// are then processed one after the other with the element tables as constant-bank operands (the point index is a
+// compile-time constant), each point's tangent / stress / dp leaving at once (three consecutive records per thread: whole
+// sectors), and the element vector accumulates in registers - no shared memory, no barriers, nb*bs REDs per cell, 35 %
+// fewer instructions than the per-point mapping.  168 registers, 12 warps per SM, persistent grid-stride loop (the
+// block-wide sum of the plastic counts, one barrier, is paid once per CTA).  Per-point arithmetic is that of the kernel
+// above, statement for statement (bit-identical per-point results).  Measured per 1e8 points on the row-major numbered
+// mesh: 5.18-5.21 ms against 5.55-5.60 for the per-point kernel (128 registers / 16 warps: 5.71, spills; L2 prefetch of the
+// next cell's streams: 5.29; a register-free cp.async pipeline of the next cell's inputs through shared memory: 5.40) - but
+// on the Z-order numbered mesh (the locality real meshes have) 6.47 against 5.54 ms: a warp's 32 cells spread every gather
+// instruction over more lines than the per-point warp's 11 cells.  Hence OPT-IN (EO_STEP_CELL=1), not the default
+// (profiles/r2_rejected_variants.md).
+#define FORM_CELL_THREADS 128
+template <int NB, bool EXACT>
+__global__ void __launch_bounds__(FORM_CELL_THREADS, 3) form_vm_step_cell_kernel(
+    const __grid_constant__ tab_tables T, const __grid_constant__ form_weights W, const vm_consts vq,
+    const int32_t* __restrict__ dofmap, const int32_t* __restrict__ x_dofmap, const double* __restrict__ x,
+    const double* __restrict__ u, const double* __restrict__ geoK, const double* __restrict__ geoD, int64_t n_cells,
+    const double* __restrict__ sigma_n, const double* __restrict__ p, double* __restrict__ C_tang,
+    double* __restrict__ sigma, double* __restrict__ dp_out, double* __restrict__ b, eo_stats* stats) {
+  int plastic = 0;
+  for (int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; c < n_cells; c += int64_t(gridDim.x) * blockDim.x) {
+    int32_t idx[NB];
+    tab_load_idx<NB>(dofmap, c, idx);
+    const int64_t i0 = 3 * c;
+    eo_d4 sn[3];
+    double pn[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) sn[q] = eo_ld256(sigma_n + 4 * (i0 + q)), pn[q] = eo_ld64(p + i0 + q);
+    double w[NB][2], K[2][2], fe[NB][2];
+    const double adet = form_cell_geometry(T, x_dofmap, x, geoK, geoD, c, K);
+    tab_gather_idx<2, NB>(u, idx, w);
+#pragma unroll
+    for (int a = 0; a < NB; ++a) fe[a][0] = 0.0, fe[a][1] = 0.0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      double val[2] = {0.0, 0.0}, grad[2][2], e[4];
+      tab_point<2, 2, NB>(T, w, K, q, false, true, val, grad);
+      tab_operand<2, 2>(2, val, grad, e);
+      vm_point_out o;
+      if (EXACT)
+        vm_point(vq, e[0], e[1], e[2], e[3], sn[q].x, sn[q].y, sn[q].z, sn[q].w, pn[q], o);
+      else
+        vm_point_fast(vq, e[0], e[1], e[2], e[3], sn[q].x, sn[q].y, sn[q].z, sn[q].w, pn[q], o);
+      plastic += o.dp > 0.0;
+      double* Ct = C_tang + 16 * (i0 + q);
+      eo_st256(Ct + 0, o.C[0], o.C[1], o.C[2], o.C[3]);
+      eo_st256(Ct + 4, o.C[4], o.C[5], o.C[6], o.C[7]);
+      eo_st256(Ct + 8, o.C[8], o.C[9], o.C[10], o.C[11]);
+      eo_st256(Ct + 12, o.C[12], o.C[13], o.C[14], o.C[15]);
+      eo_st256(sigma + 4 * (i0 + q), o.g[0], o.g[1], o.g[2], o.g[3]);
+      eo_st64(dp_out + i0 + q, o.dp);
+      double Vs[2], Gs[2][2];
+      form_cotangent<2, 2>(2, o.g, Vs, Gs);
+      form_accumulate<2, 2, NB>(T, 2, q, W.w[q] * adet, Vs, Gs, K, fe);
+    }
+#pragma unroll
+    for (int a = 0; a < NB; ++a)
+#pragma unroll
+      for (int k = 0; k < 2; ++k) atomicAdd(b + 2 * int64_t(idx[a]) + k, fe[a][k]);
+  }
+  eo_block_sum_add(reinterpret_cast<unsigned long long*>(&stats->n_plastic), plastic);
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_points), (unsigned long long)(n_cells * 3));
+}
+
 // position of (row, col) in the CSR values by bisection in the sorted row, or -1
 __device__ __forceinline__ int32_t form_csr_find(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
                                                  int32_t grow, int32_t gcol) {
@@ -970,6 +1037,10 @@ int eo_form_vm_step(eo_form* f, const eo_vm_params* prm, const double* u, const 
     const int grc = eo_tab_geometry(t);
     if (grc != EO_OK) return grc;
   }
+  // EO_STEP_CELL=1: one thread per cell (three points per cell on P1 / P2 triangles).  Opt-in: 7 % faster than the per-point
+  // kernel on a row-major numbered mesh, 15 % slower on a Z-order numbered one (header of form_vm_step_cell_kernel)
+  static const bool cell_env = [] { const char* e = getenv("EO_STEP_CELL"); return e && *e == '1'; }();
+  const bool cellwise = cell_env && t->T.nq == 3 && (t->T.nb == 3 || t->T.nb == 6);
   // the cells [c0, c1): every per-cell / per-point array is addressed relative to c0
   auto launch = [&](int64_t c0, int64_t c1, const double* du, double* db) -> int {
     const int64_t m = c1 - c0, o = c0 * t->T.nq;
@@ -986,6 +1057,16 @@ int eo_form_vm_step(eo_form* f, const eo_vm_params* prm, const double* u, const 
   if (t->T.nb == N) {                                                                                                \
     EO_STEP_X(N, true) else EO_STEP_X(N, false)                                                                      \
   }
+    if (cellwise) {
+      const int64_t tiles_c = (m + FORM_CELL_THREADS - 1) / FORM_CELL_THREADS, cap_c = int64_t(ctx->sm_count) * 3 * FORM_WAVES;
+      const unsigned gridc = (unsigned)(tiles_c < cap_c ? tiles_c : cap_c);
+#define EO_STEP_CELL(N, X) \
+  if (t->T.nb == N && bool(exact) == X) form_vm_step_cell_kernel<N, X><<<gridc, FORM_CELL_THREADS, 0, ctx->s_cmp>>>(EO_STEP_ARGS(N));
+      EO_STEP_CELL(3, true) EO_STEP_CELL(3, false) EO_STEP_CELL(6, true) EO_STEP_CELL(6, false)
+#undef EO_STEP_CELL
+      ctx->launches += 1;
+      return EO_OK;
+    }
     EO_STEP(3)
     EO_STEP(6)
     EO_STEP(10)
