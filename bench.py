@@ -47,18 +47,21 @@ sys.path.insert(0, ROOT)
 
 BYTES_PER_QP = {"vm": 240, "jitvm": 240, "jitfused": 235, "jitvm3d": 448, "heat": 88, "mc": 252, "tab": 176.0 / 3.0, "fused": 235, "isihara": 192,
                 # device-side consumers (csrc/form.cu): + read-modify-write of the DOF vector (2 nodes x 2 x 8 B per cell, twice)
-                "step": 235 + 64.0 / 3.0, "action": 128 + 80.0 / 3.0 + 64.0 / 3.0}
+                "step": 235 + 64.0 / 3.0, "action": 128 + 80.0 / 3.0 + 64.0 / 3.0,
+                # the same with the von Mises tangent kept as 6 numbers per point (48 instead of 128 B)
+                "step6": 235 - 80 + 64.0 / 3.0, "action6": 48 + 80.0 / 3.0 + 64.0 / 3.0}
 # per P2-triangle cell: dofmap 24 + x_dofmap 12 + 6 gathered dofs x 16 + 3 gathered vertices x 16 = 180 B (vs 80 B unique)
 _CELL_GATHER = (24 + 12 + 96 + 48) / 3.0
 GATHERED_BYTES_PER_QP = {"tab": _CELL_GATHER + 32, "fused": _CELL_GATHER + 40 + 168, "jitfused": _CELL_GATHER + 40 + 168,
-                         "step": _CELL_GATHER + 40 + 168 + 12 * 16 / 3.0, "action": _CELL_GATHER + 128 + 12 * 16 / 3.0}
+                         "step": _CELL_GATHER + 40 + 168 + 12 * 16 / 3.0, "action": _CELL_GATHER + 128 + 12 * 16 / 3.0,
+                         "step6": _CELL_GATHER + 40 + 88 + 12 * 16 / 3.0, "action6": _CELL_GATHER + 48 + 12 * 16 / 3.0}
 # ALGORITHMIC FP64 work of the Mohr-Coulomb path per point for the demo stress-path family (34 % plastic points, 2-5
 # Newton iterations): 2 x DFMA + DADD + DMUL thread instructions counted by ncu: yield test 245 +
 # Newton / tangent recursion 1768.  Fixed: a faster kernel that needs fewer instructions does not shrink it.
 MC_FLOPS_PER_QP = 2014.0
 # FP32 FMAs of the Isihara network per point: five 64x64 matrix-vector products + the 3->64 / 64->1 layers (isihara_core.cuh)
 ISIHARA_FMA_PER_QP = 5 * 64 * 64 + 64 * 16
-MESH_MODELS = ("tab", "fused", "jitfused", "step", "action")
+MESH_MODELS = ("tab", "fused", "jitfused", "step", "action", "step6", "action6")
 METRIC = "quadrature points per second (stress + consistent tangent + internal state)"
 
 
@@ -220,7 +223,8 @@ def cpu_tab_rate(model: str, min_seconds: float, nxy: int = 800):
     _, sn, p = syn.vm_batch(nq, seed=0)
     W3 = el.triangle_quadrature_weights(2)
     prm = oc.VonMisesParams()
-    mode = {"tab": "tab", "fused": "fused", "jitfused": "fused", "step": "step", "action": "action"}[model]
+    mode = {"tab": "tab", "fused": "fused", "jitfused": "fused", "step": "step", "action": "action", "step6": "step",
+            "action6": "action"}[model]
     Ct0 = native.forms_p2_cells("fused", m, W3, u, prm, sn, p)[0] if mode == "action" else None
 
     def fn():
@@ -270,7 +274,7 @@ def run_reference_arm(args):
     native.build()
     native.use_all_cores()
     cores = native.num_threads()
-    if args.model in ("tab", "fused", "step", "action", "isihara"):
+    if args.model in ("tab", "fused", "step", "action", "step6", "action6", "isihara"):
         r = cpu_tab_rate(args.model, 5.0) if args.model != "isihara" else cpu_isihara_rate(8192, 5.0)
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "QP/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
@@ -354,6 +358,11 @@ WORKLOADS = {
             "3 quadrature points per triangle",
     "action": "matrix-free tangent action y = J x with J = int (C_tang epsilon(u_hat)) . epsilon(v) dx, tangent resident "
               "in HBM (what a Krylov method needs from assemble_matrix); P2 vector field, 3 points per triangle",
+    "step6": "the residual step with the von Mises tangent kept in FACTORED form for the device-side consumers (6 numbers per "
+             "point: C_t = C_elas - cn v v^T - cd dev; 48 instead of 128 B per point written): eo_form_vm_step_factored; "
+             "stress, dp, statistics and b identical to `step`",
+    "action6": "the matrix-free tangent action with C_t rebuilt in registers from the factored tangent (48 instead of 128 B "
+               "per point read): eo_form_action_vm_factored; agrees with `action` to rounding",
 }
 
 
@@ -518,6 +527,13 @@ def build_workload(model, ctx, eo, inputs, n, rank, args, mesh=None):
                 w.keep.append(d_b)
                 if model == "step":
                     w.step = lambda: forms.vm_residual(vm, d_u, out=d_b, exact=args.fused_exact)
+                elif model == "step6":
+                    w.step = lambda: forms.vm_residual(vm, d_u, out=d_b, exact=args.fused_exact, tangent="factored")
+                elif model == "action6":
+                    forms.vm_residual(vm, d_u, out=d_b, exact=args.fused_exact, tangent="factored")  # fills forms.T6
+                    d_y = ctx.empty((2 * tab.n_dofs,))
+                    w.keep.append(d_y)
+                    w.step = lambda: forms.vm_action(d_u, out=d_y)
                 else:
                     forms.vm_residual(vm, d_u, out=d_b, exact=args.fused_exact)  # fills forms.C_tang
                     d_y = ctx.empty((2 * tab.n_dofs,))
@@ -640,7 +656,7 @@ def models_block(ctx, eo, inputs, args, rank, world, peaks, barrier, max_over_ra
                  "kernel_ms_max_over_ranks": time_steps.kernel_ms_max,
                  "ms_per_step": total_ms / K, "value": world * wl.n * K / (total_ms * 1e-3), "unit": "QP/s",
                  "gpu_launches": int(launches), "roofline": roofline_for(name, wl.n, km, peaks, _traffic(name, wl.n))}
-        if name in ("mc", "fused", "step"):
+        if name in ("mc", "fused", "step", "step6"):
             entry.update(_stats_cfg(name, stats))
         entry.update(wl.cfg)
         if rank == 0 and world == 1 and args.models_cpu_seconds > 0:
@@ -765,7 +781,7 @@ def run_gpu_arm(args):
         want_points = sum(l["n_points"] for l in loc)
         want_plastic = sum(l["n_plastic"] for l in loc)
         want_hist = np.sum([np.asarray(l["niter_hist"], dtype=np.int64) for l in loc], axis=0)
-        counted = model in ("vm", "mc", "fused", "step")
+        counted = model in ("vm", "mc", "fused", "step", "step6")
         ok = (gstats["n_points"] == want_points and gstats["n_plastic"] == want_plastic
               and np.array_equal(gstats["niter_hist"], want_hist)
               and _same(gstats["f_max"], _nanmax(l["f_max"] for l in loc))
@@ -854,7 +870,7 @@ def run_gpu_arm(args):
                    bound="PCIe device-to-host: the result is 168-188 B per point, the kernel needs < 10 % of the step")
         d_tmp.free()
         del m_e, call, out, deps_h, flat
-    if model in ("step", "action"):
+    if model in ("step", "action", "step6", "action6"):
         # end to end through QuadratureForms with HOST vectors: only DOF vectors cross the link
         tab, forms, vm = wl.mesh.tab, wl.mesh.forms, wl.vm
         nd = 2 * tab.n_dofs
@@ -863,6 +879,12 @@ def run_gpu_arm(args):
         if model == "step":
             call = lambda: forms.vm_residual(vm, u_h, out=b_h, exact=args.fused_exact)  # noqa: E731
             api = "QuadratureForms.vm_residual(vm, u_host, out=b_host): eo_form_vm_step, history / tangent resident in HBM"
+        elif model == "step6":
+            call = lambda: forms.vm_residual(vm, u_h, out=b_h, exact=args.fused_exact, tangent="factored")  # noqa: E731
+            api = "QuadratureForms.vm_residual(vm, u_host, out=b_host, tangent='factored'): eo_form_vm_step_factored"
+        elif model == "action6":
+            call = lambda: forms.vm_action(u_h, out=b_h)  # noqa: E731
+            api = "QuadratureForms.vm_action(x_host, out=y_host): eo_form_action_vm_factored"
         else:
             call = lambda: forms.action("mandel_strain", "mandel_strain", forms.C_tang, u_h, out=b_h)  # noqa: E731
             api = "QuadratureForms.action(..., C_tang_resident, x_host, out=y_host): eo_form_action"
@@ -954,7 +976,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--model", default="vm", choices=["vm", "heat", "mc", "tab", "fused", "isihara", "jitvm", "jitfused", "jitvm3d", "step", "action"])
+    ap.add_argument("--model", default="vm", choices=["vm", "heat", "mc", "tab", "fused", "isihara", "jitvm", "jitfused", "jitvm3d", "step", "action", "step6", "action6"])
     ap.add_argument("--fused-exact", action="store_true")
     ap.add_argument("--mc-scheme", default="classes", choices=["classes", "simple", "queue-noaffinity", "queue-onepass", "ring"])
     ap.add_argument("--n", "--qp-per-gpu", dest="n", type=float, default=1e8,
@@ -968,7 +990,7 @@ def main():
                          "space-filling curve (cheap enough for 10^7 cells)")
     ap.add_argument("--cpu-sample", type=float, default=4e6)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
-    ap.add_argument("--models", default="mc,heat,tab,fused,step,action,isihara",
+    ap.add_argument("--models", default="mc,heat,tab,fused,step,action,step6,action6,isihara",
                     help="vm (default) line: comma-separated legs of the `models` block ('' = none)")
     ap.add_argument("--models-steps", type=int, default=5)
     ap.add_argument("--models-cpu-seconds", type=float, default=2.0)

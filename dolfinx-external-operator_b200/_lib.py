@@ -145,6 +145,9 @@ PROTOTYPES = {
     "eo_form_vector": (C.c_int, [_vp, C.c_int, _vp, _i64, _vp, C.c_int]),
     "eo_form_action": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _i64, _vp, C.c_int]),
     "eo_form_vm_step": (C.c_int, [_vp, C.POINTER(VmParams), _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, C.c_int, C.c_int]),
+    "eo_form_vm_step_factored": (C.c_int, [_vp, C.POINTER(VmParams), _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, C.c_int, C.c_int]),
+    "eo_form_action_vm_factored": (C.c_int, [_vp, C.POINTER(VmParams), _vp, _vp, _i64, _vp, C.c_int]),
+    "eo_vm_expand_tangent": (C.c_int, [_vp, C.POINTER(VmParams), _vp, _vp, _i64, C.c_int]),
     "eo_form_set_pattern": (C.c_int, [_vp, _vp, _vp, _i64]),
     "eo_form_nnz": (_i64, [_vp]),
     "eo_form_matrix": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _i64, _vp, C.c_int]),

@@ -414,12 +414,105 @@ __global__ void __launch_bounds__(128) form_action_tma_kernel(const __grid_const
     for (int k = 0; k < 2; ++k) atomicAdd(y + 2 * int64_t(idx[a]) + k, fe[a][k]);
 }
 
+// Tangent action from the FACTORED von Mises tangent (6 doubles per point: v[4], cn, cd - vm_core.cuh): the shape of
+// form_action_tma_kernel with 144 instead of 384 bytes per cell through the TMA unit (row stride 144 B = 9 x 16: the 16-byte
+// reads of 8 consecutive lanes cover all 32 banks without padding) and tau = C_t e rebuilt in registers
+// (vm_factored_apply).  Mandel strain on both sides, three points per cell.  96 instead of 176 algorithmic bytes per point.
+// 78 registers, 6 CTAs per SM; forcing 8 / 7 CTAs (64 / 72 registers, spills) or letting ptxas use 106 registers: 2.31 / 2.10 /
+// 2.11 ms against 1.90 ms per 1e8 points.
+template <int NB>
+__global__ void __launch_bounds__(128) form_action_vm6_kernel(const __grid_constant__ tab_tables T,
+                                                              const __grid_constant__ form_weights W, const vm_consts vq,
+                                                              const int32_t* __restrict__ dofmap,
+                                                              const int32_t* __restrict__ x_dofmap,
+                                                              const double* __restrict__ x, const double* __restrict__ geoK,
+                                                              const double* __restrict__ geoD, const double* __restrict__ T6,
+                                                              const double* __restrict__ xin, int64_t n_cells,
+                                                              double* __restrict__ y) {
+  extern __shared__ __align__(128) unsigned char form_smem_raw[];
+  constexpr unsigned CELL_B = 3 * 48, ROW_B = CELL_B;
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(form_smem_raw);
+  const unsigned rows = bar + 128;
+  const int64_t c0 = blockIdx.x * int64_t(128);
+  const int64_t c = c0 + threadIdx.x;
+  const unsigned cells_here = (unsigned)((n_cells - c0) < 128 ? (n_cells - c0) : 128);
+  if (threadIdx.x == 0) {  // the transaction count is armed before any copy can complete
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(cells_here * CELL_B) : "memory");
+  }
+  __syncthreads();
+  if (c < n_cells)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     rows + threadIdx.x * ROW_B),
+                 "l"(T6 + c * int64_t(18)), "r"(CELL_B), "r"(bar)
+                 : "memory");
+  double K[2][2], w[NB][2], adet = 0.0;
+  int32_t idx[NB];
+  if (c < n_cells) {
+    adet = form_cell_geometry(T, x_dofmap, x, geoK, geoD, c, K);
+    tab_load_idx<NB>(dofmap, c, idx);
+    tab_gather_idx<2, NB>(xin, idx, w);
+  }
+  unsigned done = 0;
+  while (!done)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done)
+                 : "r"(bar)
+                 : "memory");
+  if (c >= n_cells) return;
+  double fe[NB][2];
+#pragma unroll
+  for (int a = 0; a < NB; ++a) fe[a][0] = 0.0, fe[a][1] = 0.0;
+  const unsigned my = rows + threadIdx.x * ROW_B;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    double val[2] = {0.0, 0.0}, grad[2][2], e[4], tau[4], f[6];
+    tab_point<2, 2, NB, true>(T, w, K, q, false, true, val, grad);
+    tab_operand<2, 2>(2, val, grad, e);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(f[2 * r]), "=d"(f[2 * r + 1]) : "r"(my + q * 48 + r * 16));
+    vm_factored_apply(vq, f, f[4], f[5], e, tau);
+    double Vs[2], Gs[2][2];
+    form_cotangent<2, 2>(2, tau, Vs, Gs);
+    form_accumulate<2, 2, NB, true>(T, 2, q, W.w[q] * adet, Vs, Gs, K, fe);
+  }
+#pragma unroll
+  for (int a = 0; a < NB; ++a)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) atomicAdd(y + 2 * int64_t(idx[a]) + k, fe[a][k]);
+}
+
+// factored tangent -> the reference's (n, 4, 4) layout, by the statements of vm_point / vm_point_fast (bit-identical to what
+// the un-factored kernels store)
+template <bool EXACT>
+__global__ void __launch_bounds__(256) vm_expand_kernel(const vm_consts vq, const double* __restrict__ T6, int64_t n,
+                                                        double* __restrict__ C_tang) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const double2 a = eo_ld128(T6 + 6 * i), b2 = eo_ld128(T6 + 6 * i + 2), cc = eo_ld128(T6 + 6 * i + 4);
+  const double v[4] = {a.x, a.y, b2.x, b2.y};
+  double C[16];
+  if (EXACT)
+    vm_tangent_exact(vq, v, cc.x, cc.y, C);
+  else
+    vm_tangent_fast(vq, v, cc.x, cc.y, C);
+  double* Ct = C_tang + 16 * i;
+  eo_st256(Ct + 0, C[0], C[1], C[2], C[3]);
+  eo_st256(Ct + 4, C[4], C[5], C[6], C[7]);
+  eo_st256(Ct + 8, C[8], C[9], C[10], C[11]);
+  eo_st256(Ct + 12, C[12], C[13], C[14], C[15]);
+}
+
 // One Newton residual evaluation of the von Mises problem without leaving the device:
 // Mandel strain of u -> radial return (C_tang, sigma, dp stored for the tangent action / the history commit)
 // -> b += int sigma . epsilon(v) dx.  The per-point arithmetic and its results are those of eo_tab_vm_fused.
 // (A per-cell variant with TMA bulk stores of tangent and stress - the analogue of form_action_tma_kernel - was measured
 // slower, 6.6 vs 5.8 ms per 1e8 points: 160 registers leave 12 warps per SM for the division-heavy radial return.)
-template <int NB, bool EXACT>
+// FACT: the tangent is stored in its factored form (v[4], cn, cd: 48 instead of 128 bytes per point, vm_core.cuh) for
+// eo_form_action_vm_factored; `C_tang` then points at that [n_points][6] array.
+template <int NB, bool EXACT, bool FACT>
 __global__ void __launch_bounds__(FORM_THREADS, 3) form_vm_step_kernel(
     const __grid_constant__ tab_tables T, const __grid_constant__ form_weights W, const vm_consts vq,
     const int32_t* __restrict__ dofmap, const int32_t* __restrict__ x_dofmap, const double* __restrict__ x,
@@ -452,11 +545,18 @@ __global__ void __launch_bounds__(FORM_THREADS, 3) form_vm_step_kernel(
       else
         vm_point_fast(vq, e[0], e[1], e[2], e[3], s.x, s.y, s.z, s.w, pi, o);
       plastic += o.dp > 0.0;
-      double* Ct = C_tang + 16 * i;
-      eo_st256(Ct + 0, o.C[0], o.C[1], o.C[2], o.C[3]);
-      eo_st256(Ct + 4, o.C[4], o.C[5], o.C[6], o.C[7]);
-      eo_st256(Ct + 8, o.C[8], o.C[9], o.C[10], o.C[11]);
-      eo_st256(Ct + 12, o.C[12], o.C[13], o.C[14], o.C[15]);
+      if (FACT) {
+        double* Tf = C_tang + 6 * i;
+        eo_st128(Tf + 0, o.v[0], o.v[1]);
+        eo_st128(Tf + 2, o.v[2], o.v[3]);
+        eo_st128(Tf + 4, o.cn, o.cd);
+      } else {
+        double* Ct = C_tang + 16 * i;
+        eo_st256(Ct + 0, o.C[0], o.C[1], o.C[2], o.C[3]);
+        eo_st256(Ct + 4, o.C[4], o.C[5], o.C[6], o.C[7]);
+        eo_st256(Ct + 8, o.C[8], o.C[9], o.C[10], o.C[11]);
+        eo_st256(Ct + 12, o.C[12], o.C[13], o.C[14], o.C[15]);
+      }
       eo_st256(sigma + 4 * i, o.g[0], o.g[1], o.g[2], o.g[3]);
       eo_st64(dp_out + i, o.dp);
       g[0] = o.g[0], g[1] = o.g[1], g[2] = o.g[2], g[3] = o.g[3];
@@ -1012,8 +1112,10 @@ int eo_form_action(eo_form* f, int kind_test, int kind_trial, const double* D, c
   return form_finish(f, y, d_y);
 }
 
-int eo_form_vm_step(eo_form* f, const eo_vm_params* prm, const double* u, const double* sigma_n, const double* p,
-                    double* C_tang, double* sigma, double* dp, int64_t n_cells, double* b, int accumulate, int exact) {
+// fact == 0: C_tang is the (n, 4, 4) tangent; fact == 1: the factored tangent, 6 doubles per point
+static int form_vm_step_impl(eo_form* f, const eo_vm_params* prm, const double* u, const double* sigma_n, const double* p,
+                             double* C_tang, double* sigma, double* dp, int64_t n_cells, double* b, int accumulate,
+                             int exact, int fact) {
   if (!f) return EO_ERR_INVALID;
   eo_tab* t = f->tab;
   eo_ctx* ctx = t->ctx;
@@ -1027,12 +1129,13 @@ int eo_form_vm_step(eo_form* f, const eo_vm_params* prm, const double* u, const 
   EO_REQUIRE(ctx, n_cells == 0 || (eo_is_device_ptr(sigma_n) && eo_is_device_ptr(p) && eo_is_device_ptr(C_tang) &&
                                    eo_is_device_ptr(sigma) && eo_is_device_ptr(dp)),
              "eo_form_vm_step: history and point outputs must be device memory (u and b may be host memory)");
-  EO_REQUIRE(ctx, eo_aligned(sigma_n, 32) && eo_aligned(C_tang, 32) && eo_aligned(sigma, 32),
-             "eo_form_vm_step: arrays must be 32-byte aligned");
+  EO_REQUIRE(ctx, eo_aligned(sigma_n, 32) && eo_aligned(C_tang, fact ? 16 : 32) && eo_aligned(sigma, 32),
+             "eo_form_vm_step: arrays must be 32-byte aligned (the factored tangent: 16)");
   EO_CUDA(ctx, cudaSetDevice(ctx->device));
   const vm_consts q{prm->lmbda, prm->mu, prm->H, prm->sigma_0};
   form_weights W;
   memcpy(W.w, f->w, sizeof(W.w));
+  const int tw = fact ? 6 : 16;  // doubles per point of the tangent array
   if (n_cells > 0) {
     const int grc = eo_tab_geometry(t);
     if (grc != EO_OK) return grc;
@@ -1040,22 +1143,22 @@ int eo_form_vm_step(eo_form* f, const eo_vm_params* prm, const double* u, const 
   // EO_STEP_CELL=1: one thread per cell (three points per cell on P1 / P2 triangles).  Opt-in: 7 % faster than the per-point
   // kernel on a row-major numbered mesh, 15 % slower on a Z-order numbered one (header of form_vm_step_cell_kernel)
   static const bool cell_env = [] { const char* e = getenv("EO_STEP_CELL"); return e && *e == '1'; }();
-  const bool cellwise = cell_env && t->T.nq == 3 && (t->T.nb == 3 || t->T.nb == 6);
+  const bool cellwise = cell_env && !fact && t->T.nq == 3 && (t->T.nb == 3 || t->T.nb == 6);
   // the cells [c0, c1): every per-cell / per-point array is addressed relative to c0
   auto launch = [&](int64_t c0, int64_t c1, const double* du, double* db) -> int {
     const int64_t m = c1 - c0, o = c0 * t->T.nq;
     const unsigned grid = form_grid(ctx, t, m);
 #define EO_STEP_ARGS(N)                                                                                              \
   t->T, W, q, t->dofmap + c0 * N, t->x_dofmap + c0 * 3, t->x, du, t->geoK ? t->geoK + 4 * c0 : nullptr,                \
-      t->geoK ? t->geoD + c0 : nullptr, m, sigma_n + 4 * o, p + o, C_tang + 16 * o, sigma + 4 * o, dp + o, db, ctx->stats
-#define EO_STEP_X(N, X)                                                                                              \
-  if (bool(exact) == X) {                                                                                            \
-    const size_t sm = form_smem(ctx, form_vm_step_kernel<N, X>, N * 2);                                              \
-    form_vm_step_kernel<N, X><<<grid, FORM_THREADS, sm, ctx->s_cmp>>>(EO_STEP_ARGS(N));                              \
+      t->geoK ? t->geoD + c0 : nullptr, m, sigma_n + 4 * o, p + o, C_tang + tw * o, sigma + 4 * o, dp + o, db, ctx->stats
+#define EO_STEP_X(N, X, F)                                                                                           \
+  if (bool(exact) == X && bool(fact) == F) {                                                                         \
+    const size_t sm = form_smem(ctx, form_vm_step_kernel<N, X, F>, N * 2);                                           \
+    form_vm_step_kernel<N, X, F><<<grid, FORM_THREADS, sm, ctx->s_cmp>>>(EO_STEP_ARGS(N));                           \
   }
 #define EO_STEP(N)                                                                                                   \
   if (t->T.nb == N) {                                                                                                \
-    EO_STEP_X(N, true) else EO_STEP_X(N, false)                                                                      \
+    EO_STEP_X(N, true, false) else EO_STEP_X(N, false, false) else EO_STEP_X(N, true, true) else EO_STEP_X(N, false, true) \
   }
     if (cellwise) {
       const int64_t tiles_c = (m + FORM_CELL_THREADS - 1) / FORM_CELL_THREADS, cap_c = int64_t(ctx->sm_count) * 3 * FORM_WAVES;
@@ -1085,6 +1188,83 @@ int eo_form_vm_step(eo_form* f, const eo_vm_params* prm, const double* u, const 
   if (rc != EO_OK) return rc;
   if (n_cells > 0) launch(0, n_cells, d_u, d_b);
   return form_finish(f, b, d_b);
+}
+
+int eo_form_vm_step(eo_form* f, const eo_vm_params* prm, const double* u, const double* sigma_n, const double* p,
+                    double* C_tang, double* sigma, double* dp, int64_t n_cells, double* b, int accumulate, int exact) {
+  return form_vm_step_impl(f, prm, u, sigma_n, p, C_tang, sigma, dp, n_cells, b, accumulate, exact, 0);
+}
+
+int eo_form_vm_step_factored(eo_form* f, const eo_vm_params* prm, const double* u, const double* sigma_n, const double* p,
+                             double* T6, double* sigma, double* dp, int64_t n_cells, double* b, int accumulate, int exact) {
+  return form_vm_step_impl(f, prm, u, sigma_n, p, T6, sigma, dp, n_cells, b, accumulate, exact, 1);
+}
+
+int eo_form_action_vm_factored(eo_form* f, const eo_vm_params* prm, const double* T6, const double* x, int64_t n_cells,
+                               double* y, int accumulate) {
+  if (!f) return EO_ERR_INVALID;
+  eo_tab* t = f->tab;
+  eo_ctx* ctx = t->ctx;
+  EO_REQUIRE(ctx, prm != nullptr, "eo_form_action_vm_factored: prm is NULL");
+  EO_REQUIRE(ctx, t->T.gdim == 2 && t->T.bs == 2 && t->T.nq == 3 && (t->T.nb == 3 || t->T.nb == 6 || t->T.nb == 10),
+             "eo_form_action_vm_factored: P1/P2/P3 vector triangles with three points per cell only");
+  if (n_cells < 0) n_cells = t->n_cells;
+  EO_REQUIRE(ctx, n_cells <= t->n_cells, "eo_form_action_vm_factored: more cells requested than the mesh has");
+  EO_REQUIRE(ctx, x && y, "eo_form_action_vm_factored: NULL vector");
+  EO_REQUIRE(ctx, n_cells == 0 || (T6 && eo_is_device_ptr(T6) && eo_aligned(T6, 16)),
+             "eo_form_action_vm_factored: the factored tangent must be 16-byte aligned device memory");
+  EO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const vm_consts q{prm->lmbda, prm->mu, prm->H, prm->sigma_0};
+  form_weights W;
+  memcpy(W.w, f->w, sizeof(W.w));
+  if (n_cells > 0) {
+    const int grc = eo_tab_geometry(t);
+    if (grc != EO_OK) return grc;
+  }
+  auto launch = [&](int64_t c0, int64_t c1, const double* dx, double* dy) -> int {
+    const int64_t m = c1 - c0;
+    const unsigned gc = (unsigned)((m + 127) / 128);
+    const size_t sm = 128 + 128 * (3 * 48);
+#define EO_ACT6(N)                                                                                                      \
+  if (t->T.nb == N)                                                                                                     \
+    form_action_vm6_kernel<N><<<gc, 128, sm, ctx->s_cmp>>>(t->T, W, q, t->dofmap + c0 * N, t->x_dofmap + c0 * 3, t->x,   \
+                                                           t->geoK ? t->geoK + 4 * c0 : nullptr,                        \
+                                                           t->geoK ? t->geoD + c0 : nullptr, T6 + 18 * c0, dx, m, dy);
+    EO_ACT6(3) EO_ACT6(6) EO_ACT6(10)
+#undef EO_ACT6
+    ctx->launches += 1;
+    return EO_OK;
+  };
+  if (n_cells > 0 && form_pipe_applies(f, x, y, accumulate, n_cells)) return form_pipelined(f, x, y, n_cells, launch);
+  const double* d_x = nullptr;
+  int rc = form_stage_x(f, x, &d_x);
+  if (rc != EO_OK) return rc;
+  double* d_y = nullptr;
+  rc = form_result(f, y, accumulate, &d_y);
+  if (rc != EO_OK) return rc;
+  EO_REQUIRE(ctx, d_x != d_y, "eo_form_action_vm_factored: x and y must not alias");
+  if (n_cells > 0) {
+    rc = launch(0, n_cells, d_x, d_y);
+    if (rc != EO_OK) return rc;
+  }
+  return form_finish(f, y, d_y);
+}
+
+int eo_vm_expand_tangent(eo_ctx* ctx, const eo_vm_params* prm, const double* T6, double* C_tang, int64_t n, int exact) {
+  if (!ctx) return EO_ERR_INVALID;
+  EO_REQUIRE(ctx, prm != nullptr, "eo_vm_expand_tangent: prm is NULL");
+  EO_REQUIRE(ctx, n >= 0, "eo_vm_expand_tangent: negative n");
+  if (n == 0) return EO_OK;
+  EO_REQUIRE(ctx, T6 && C_tang && eo_is_device_ptr(T6) && eo_is_device_ptr(C_tang) && eo_aligned(T6, 16) && eo_aligned(C_tang, 32),
+             "eo_vm_expand_tangent: device arrays, 16- / 32-byte aligned");
+  EO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const vm_consts q{prm->lmbda, prm->mu, prm->H, prm->sigma_0};
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  if (exact) vm_expand_kernel<true><<<grid, 256, 0, ctx->s_cmp>>>(q, T6, n, C_tang);
+  else vm_expand_kernel<false><<<grid, 256, 0, ctx->s_cmp>>>(q, T6, n, C_tang);
+  ctx->launches += 1;
+  EO_CUDA(ctx, cudaGetLastError());
+  return EO_OK;
 }
 
 int eo_form_set_pattern(eo_form* f, const int32_t* row_ptr, const int32_t* col, int64_t nnz) {

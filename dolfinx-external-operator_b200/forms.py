@@ -112,10 +112,16 @@ class QuadratureForms:
                                      int(bool(accumulate))))
         return out
 
-    def vm_residual(self, vm, u=None, out=None, n_cells=None, accumulate=False, exact=False, output="host"):
+    def vm_residual(self, vm, u=None, out=None, n_cells=None, accumulate=False, exact=False, output="host",
+                    tangent="full"):
         """Constitutive update of the von Mises demo + residual in ONE kernel: the Mandel strain of `u` (default: the
         tabulator's coefficient) goes through the radial return (`vm`: a resident-history `VonMises`), tangent /
-        stress / dp stay in HBM (`self.C_tang`, `vm.sigma_dev`, `vm.dp_dev`) and b = int sigma . eps(v) dx comes back."""
+        stress / dp stay in HBM (`self.C_tang`, `vm.sigma_dev`, `vm.dp_dev`) and b = int sigma . eps(v) dx comes back.
+        tangent="factored": the tangent is kept as 6 numbers per point (`self.T6`: v, cn, cd with
+        C_t = C_elas - cn v v^T - cd dev) for `vm_action` - 48 instead of 128 bytes per point; `expand_tangent()` gives
+        the reference's (n, 4, 4) array when an assembler needs it."""
+        if tangent not in ("full", "factored"):
+            raise ValueError("tangent must be 'full' or 'factored'")
         t = self.tab
         n = t.n_cells * t.nq
         if vm.n_qp is None:
@@ -123,14 +129,48 @@ class QuadratureForms:
         if vm.n_qp != n:
             raise ValueError(f"mesh has {n} quadrature points, the resident history {vm.n_qp}")
         c = self.ctx
-        if self.C_tang is None or self.C_tang.size != 16 * n:
-            self.C_tang = c.empty((16 * n,))
         u = t._coeff(u)
         out = self._vec_out(out, output)
         prm = VmParams(vm.lmbda, vm.mu, vm.H, vm.sigma_0)
+        if tangent == "factored":
+            if getattr(self, "T6", None) is None or self.T6.size != 6 * n:
+                self.T6 = c.empty((6 * n,))
+            self._T6_prm, self._T6_exact = prm, bool(exact)
+            c.check(c.lib.eo_form_vm_step_factored(self._h, C.byref(prm), _ptr(u), vm.sigma_n_dev.ptr, vm.p_dev.ptr,
+                                                   self.T6.ptr, vm.sigma_dev.ptr, vm.dp_dev.ptr, self._cells(n_cells),
+                                                   _ptr(out), int(bool(accumulate)), int(bool(exact))))
+            return out
+        if self.C_tang is None or self.C_tang.size != 16 * n:
+            self.C_tang = c.empty((16 * n,))
         c.check(c.lib.eo_form_vm_step(self._h, C.byref(prm), _ptr(u), vm.sigma_n_dev.ptr, vm.p_dev.ptr, self.C_tang.ptr,
                                       vm.sigma_dev.ptr, vm.dp_dev.ptr, self._cells(n_cells), _ptr(out),
                                       int(bool(accumulate)), int(bool(exact))))
+        return out
+
+    def vm_action(self, x, out=None, n_cells=None, accumulate=False, output="host"):
+        """y = J x with the factored tangent of the last `vm_residual(..., tangent="factored")`: the matrix-free form of
+        `assemble_matrix(J)` with J = inner(C_t eps(u_hat), eps(v)) dx (demo_plasticity_von_mises.py:390-398)."""
+        if getattr(self, "T6", None) is None:
+            raise RuntimeError("vm_action needs vm_residual(..., tangent='factored') first")
+        x = self._vec_in(x)
+        out = self._vec_out(out, output)
+        c = self.ctx
+        c.check(c.lib.eo_form_action_vm_factored(self._h, C.byref(self._T6_prm), self.T6.ptr, _ptr(x), self._cells(n_cells),
+                                                 _ptr(out), int(bool(accumulate))))
+        return out
+
+    def expand_tangent(self, out: DeviceArray = None):
+        """The factored tangent as the reference's (n, 4, 4) array on the device (bit-identical to what
+        `vm_residual(tangent="full")` stores with the same `exact` flag)."""
+        if getattr(self, "T6", None) is None:
+            raise RuntimeError("expand_tangent needs vm_residual(..., tangent='factored') first")
+        c = self.ctx
+        n = self.T6.size // 6
+        if out is None:
+            if self.C_tang is None or self.C_tang.size != 16 * n:
+                self.C_tang = c.empty((16 * n,))
+            out = self.C_tang
+        c.check(c.lib.eo_vm_expand_tangent(c.handle, C.byref(self._T6_prm), self.T6.ptr, out.ptr, n, int(self._T6_exact)))
         return out
 
     def mc_residual(self, mc, u=None, out=None, n_cells=None, accumulate=False, output="host", fused=False):

@@ -291,6 +291,21 @@ int eo_form_action(eo_form* form, int kind_test, int kind_trial, const double* D
  * eo_form_action / eo_commit_history) -> b (+)= int sigma . epsilon(v) dx.  One kernel; u, b any-side. */
 int eo_form_vm_step(eo_form* form, const eo_vm_params* prm, const double* u, const double* sigma_n, const double* p,
                     double* C_tang, double* sigma, double* dp, int64_t n_cells, double* b, int accumulate, int exact);
+/* The same step with the consistent tangent kept in FACTORED form for the device-side consumers: T6[n_points][6] =
+ * (v0, v1, v2, v3, cn, cd) with C_t = C_elas - cn v v^T - cd dev, v = n_elas f+ / f (demo_vm:317),
+ * cn = 3 mu (3 mu / (3 mu + H) - beta) (:323), cd = 2 mu beta (:324): 48 instead of 128 bytes per point written here and
+ * read by every tangent action (the reference's (n, 4, 4) array is what DOLFINx's assembler needs, not what a matrix-free
+ * Krylov method needs).  Stress, dp, statistics and b are those of eo_form_vm_step.  T6: 16-byte aligned device memory. */
+int eo_form_vm_step_factored(eo_form* form, const eo_vm_params* prm, const double* u, const double* sigma_n, const double* p,
+                             double* T6, double* sigma, double* dp, int64_t n_cells, double* b, int accumulate, int exact);
+/* y (+)= A x, A = assemble_matrix(inner(C_t epsilon(u_hat), epsilon(v)) dx) (demo_vm:390-398) with C_t rebuilt from T6 in
+ * registers (three points per cell, P1/P2/P3 vector triangles).  Agrees with eo_form_action on the expanded tangent to
+ * rounding. */
+int eo_form_action_vm_factored(eo_form* form, const eo_vm_params* prm, const double* T6, const double* x, int64_t n_cells,
+                               double* y, int accumulate);
+/* T6 -> C_tang[n][4][4], by the statements of the un-factored kernels (exact != 0: the reference's statement sequence,
+ * else the symmetric / FMA form of the default fused kernels): bit-identical to what eo_form_vm_step stores. */
+int eo_vm_expand_tangent(eo_ctx* ctx, const eo_vm_params* prm, const double* T6, double* C_tang, int64_t n, int exact);
 /* CSR pattern of the assembled matrix over scalar dofs (row = bs * node + comp): host arrays row_ptr[bs*n_dofs + 1],
  * col[nnz] (strictly increasing within a row - what `fem.create_sparsity_pattern` + finalize gives); validated and
  * uploaded once.  eo_form_matrix then adds every element matrix into vals[nnz] (device memory). */

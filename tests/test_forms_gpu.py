@@ -399,3 +399,56 @@ def test_host_vector_pipeline_equals_device_path(ctx, order):
     y_d = forms2.action("mandel_strain", "mandel_strain", forms2.C_tang, ctx.to_device(x), output="device").to_host()
     _close(y_h, y_d)
     assert ctx.stats()["n_points"] >= n
+
+
+@pytest.mark.parametrize("exact", [False, True])
+@pytest.mark.parametrize("degree", [1, 2])
+def test_vm_factored_tangent(ctx, exact, degree):
+    """Device-side consumers with the von Mises tangent kept as 6 numbers per point (v, cn, cd): the residual, stress, dp and
+    statistics are those of the ordinary step bit for bit, the expanded factors are the ordinary tangent bit for bit, and
+    the tangent action rebuilt from the factors agrees with the action on the full tangent and with the oracle."""
+    m = tri_case(nx=37, ny=23, degree=degree)
+    tab, forms = _mk(ctx, m, 2)
+    n = m["dofmap"].shape[0] * 3
+    rng = np.random.default_rng(17)
+    sigma_n, p = rng.normal(0.0, 100.0, (n, 4)), np.abs(rng.normal(0.0, 1e-3, n))
+    u = syn.smooth_displacement(m["dof_coords"], scale=6e-4, seed=4).reshape(-1)
+    vm = eo.VonMises(ctx=ctx, n_qp=n)
+    vm.set_history(sigma_n, p)
+    b_full = forms.vm_residual(vm, u, exact=exact)
+    Ct, sig, dp = forms.C_tang.to_host(), vm.sigma_dev.to_host(), vm.dp_dev.to_host()
+    assert 0.2 < (dp > 0).mean() < 0.8
+    vm2 = eo.VonMises(ctx=ctx, n_qp=n)
+    vm2.set_history(sigma_n, p)
+    ctx.stats_reset()
+    b_fact = forms.vm_residual(vm2, u, exact=exact, tangent="factored")
+    st = ctx.stats()
+    assert st["n_points"] == n and st["n_plastic"] == int((dp > 0).sum())
+    assert np.array_equal(sig, vm2.sigma_dev.to_host()) and np.array_equal(dp, vm2.dp_dev.to_host())
+    _close(b_fact, b_full, 1e-13)
+    # the factors: elastic points carry v = 0 and cd = 0; expanded, they are the stored tangent
+    T6 = forms.T6.to_host().reshape(n, 6)
+    assert np.all(T6[dp == 0, :4] == 0.0) and np.all(T6[dp == 0, 5] == 0.0)
+    assert np.array_equal(forms.expand_tangent(ctx.empty((16 * n,))).to_host(), Ct)
+    # the action from the factors == the action on the full tangent == the oracle
+    x = rng.normal(size=u.size)
+    y_fact = forms.vm_action(x)
+    y_full = forms.action("mandel_strain", "mandel_strain", forms.C_tang, x)
+    _close(y_fact, y_full, 1e-12)
+    _close(y_fact, of.apply_action(ot.MANDEL_STRAIN, ot.MANDEL_STRAIN, Ct, x, W3, m["dofmap"], 2, m["n_dofs"], *_geo(m)))
+    # host vectors through the chunk pipeline and device-resident vectors give the same action
+    d_x, d_y = ctx.to_device(x), ctx.empty((u.size,))
+    forms.vm_action(d_x, out=d_y)
+    _close(d_y.to_host(), y_fact, 1e-13)
+    # accumulate: y += J x
+    y2 = forms.vm_action(x, out=y_fact.copy(), accumulate=True)
+    _close(y2, 2.0 * y_fact, 1e-13)
+
+
+def test_vm_factored_errors(ctx):
+    m = tri_case()
+    tab, forms = _mk(ctx, m, 2)
+    with pytest.raises(RuntimeError):
+        forms.vm_action(np.zeros(2 * m["n_dofs"]))
+    with pytest.raises(ValueError):
+        forms.vm_residual(eo.VonMises(ctx=ctx, n_qp=m["dofmap"].shape[0] * 3), np.zeros(2 * m["n_dofs"]), tangent="packed")
