@@ -86,6 +86,26 @@ __device__ __forceinline__ void form_gather(const int32_t* __restrict__ dofmap, 
   tab_gather<BS, NB>(dofmap, u, c, w);
 }
 
+// Scatter of one cell's element vector per thread (block size 2) by lane PAIRS: the even lane adds component 0 and the odd
+// lane component 1 of the SAME node in the same instruction - first for the even lane's cell, then for the odd lane's - so
+// that a RED instruction touches 16 aligned 16-byte chunks instead of 32 scattered 8-byte words.  With one RED per lane
+// and entry, a Z-order numbered mesh spent 2.5x the L1 wavefronts on the scatter that a row-major numbered one does
+// (ncu: 14.7 M against 5.8 M per 2e7 points in the per-cell residual step, which lost 15 % there; with pairs it is level).
+// All 32 lanes must call; `active` = this lane has a cell.
+template <int NB>
+__device__ __forceinline__ void form_scatter_pairs(double* __restrict__ y, const int32_t idx[NB], const double fe[NB][2],
+                                                   bool active) {
+  const bool odd = threadIdx.x & 1u;
+  const bool pact = __shfl_xor_sync(0xffffffffu, int(active), 1) != 0;
+#pragma unroll
+  for (int a = 0; a < NB; ++a) {
+    const double recv = __shfl_xor_sync(0xffffffffu, odd ? fe[a][0] : fe[a][1], 1);  // the partner's share for MY component
+    const int32_t pidx = __shfl_xor_sync(0xffffffffu, idx[a], 1);
+    if (odd ? pact : active) atomicAdd(y + 2 * int64_t(odd ? pidx : idx[a]) + (odd ? 1 : 0), odd ? recv : fe[a][0]);
+    if (odd ? active : pact) atomicAdd(y + 2 * int64_t(odd ? idx[a] : pidx) + (odd ? 1 : 0), odd ? fe[a][1] : recv);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Mapping of the fused residual step: one thread per QUADRATURE POINT, a CTA of FORM_THREADS threads covers
 // FORM_THREADS / nq consecutive cells (a cell never straddles CTAs).  The per-point streams (stress 32 B, tangent
@@ -223,24 +243,29 @@ __global__ void __launch_bounds__(128) form_vector_cell_kernel(const __grid_cons
                                                                const double* __restrict__ coef, int64_t n_cells,
                                                                double* __restrict__ b) {
   const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-  if (c >= n_cells) return;
+  const bool active = c < n_cells;  // block size 2: every lane stays for the pairwise scatter
+  if (BS != 2 && !active) return;
   const int ncomp = tab_ncomp(kind, BS, GDIM);
   const bool vec4 = ncomp == 4 && (reinterpret_cast<uintptr_t>(coef) % 32) == 0;
   const double* s_ptr = coef + c * int64_t(T.nq) * ncomp;
-  double K[GDIM][GDIM], adet;
-  if constexpr (GDIM == 2)
-    adet = form_cell_geometry(T, x_dofmap, x, geoK, geoD, c, K);
-  else
-    adet = form_geometry<GDIM>(T, x_dofmap, x, c, K);
+  double K[GDIM][GDIM], adet = 0.0;
   int32_t idx[NB];
-#pragma unroll
-  for (int a = 0; a < NB; ++a) idx[a] = __ldg(dofmap + c * NB + a);
   double fe[NB][BS];
 #pragma unroll
-  for (int a = 0; a < NB; ++a)
+  for (int a = 0; a < NB; ++a) {
+    idx[a] = 0;
 #pragma unroll
     for (int k = 0; k < BS; ++k) fe[a][k] = 0.0;
-  for (int q = 0; q < T.nq; ++q) {
+  }
+  if (active) {
+    if constexpr (GDIM == 2)
+      adet = form_cell_geometry(T, x_dofmap, x, geoK, geoD, c, K);
+    else
+      adet = form_geometry<GDIM>(T, x_dofmap, x, c, K);
+#pragma unroll
+    for (int a = 0; a < NB; ++a) idx[a] = __ldg(dofmap + c * NB + a);
+  }
+  for (int q = 0; active && q < T.nq; ++q) {
     double s[BS * GDIM > 4 ? BS * GDIM : 4];
     if (vec4) {
       const eo_d4 v = eo_ld256(s_ptr + 4 * q);
@@ -252,10 +277,14 @@ __global__ void __launch_bounds__(128) form_vector_cell_kernel(const __grid_cons
     form_cotangent<GDIM, BS>(kind, s, Vs, Gs);
     form_accumulate<GDIM, BS, NB, true>(T, kind, q, W.w[q] * adet, Vs, Gs, K, fe);
   }
+  if constexpr (BS == 2) {
+    form_scatter_pairs<NB>(b, idx, fe, active);
+  } else {
 #pragma unroll
-  for (int a = 0; a < NB; ++a)
+    for (int a = 0; a < NB; ++a)
 #pragma unroll
-    for (int k = 0; k < BS; ++k) atomicAdd(b + int64_t(BS) * idx[a] + k, fe[a][k]);
+      for (int k = 0; k < BS; ++k) atomicAdd(b + int64_t(BS) * idx[a] + k, fe[a][k]);
+  }
 }
 
 // y += sum_q w_q |det J| B_test,q^T ( D[c][q] (B_trial,q x) ),   D row-major (ncomp_test, ncomp_trial) per point.
@@ -371,6 +400,8 @@ __global__ void __launch_bounds__(128) form_action_tma_kernel(const __grid_const
                  : "memory");
   double K[2][2], w[NB][2], adet = 0.0;
   int32_t idx[NB];
+#pragma unroll
+  for (int a = 0; a < NB; ++a) idx[a] = 0;
   if (c < n_cells) {
     adet = form_cell_geometry(T, x_dofmap, x, geoK, geoD, c, K);
 #pragma unroll
@@ -387,11 +418,12 @@ __global__ void __launch_bounds__(128) form_action_tma_kernel(const __grid_const
                  : "=r"(done)
                  : "r"(bar)
                  : "memory");
-  if (c >= n_cells) return;
+  const bool active = c < n_cells;  // every lane stays for the pairwise scatter
   double fe[NB][2];
 #pragma unroll
   for (int a = 0; a < NB; ++a) fe[a][0] = 0.0, fe[a][1] = 0.0;
   const unsigned my = rows + threadIdx.x * ROW_B;
+  if (active)
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
     double val[2] = {0.0, 0.0}, grad[2][2], e[4], tau[4];
@@ -408,10 +440,7 @@ __global__ void __launch_bounds__(128) form_action_tma_kernel(const __grid_const
     form_cotangent<2, 2>(kind_test, tau, Vs, Gs);
     form_accumulate<2, 2, NB, true>(T, kind_test, q, W.w[q] * adet, Vs, Gs, K, fe);
   }
-#pragma unroll
-  for (int a = 0; a < NB; ++a)
-#pragma unroll
-    for (int k = 0; k < 2; ++k) atomicAdd(y + 2 * int64_t(idx[a]) + k, fe[a][k]);
+  form_scatter_pairs<NB>(y, idx, fe, active);
 }
 
 // Tangent action from the FACTORED von Mises tangent (6 doubles per point: v[4], cn, cd - vm_core.cuh): the shape of
@@ -449,6 +478,8 @@ __global__ void __launch_bounds__(128) form_action_vm6_kernel(const __grid_const
                  : "memory");
   double K[2][2], w[NB][2], adet = 0.0;
   int32_t idx[NB];
+#pragma unroll
+  for (int a = 0; a < NB; ++a) idx[a] = 0;
   if (c < n_cells) {
     adet = form_cell_geometry(T, x_dofmap, x, geoK, geoD, c, K);
     tab_load_idx<NB>(dofmap, c, idx);
@@ -460,11 +491,12 @@ __global__ void __launch_bounds__(128) form_action_vm6_kernel(const __grid_const
                  : "=r"(done)
                  : "r"(bar)
                  : "memory");
-  if (c >= n_cells) return;
+  const bool active = c < n_cells;  // every lane stays for the pairwise scatter
   double fe[NB][2];
 #pragma unroll
   for (int a = 0; a < NB; ++a) fe[a][0] = 0.0, fe[a][1] = 0.0;
   const unsigned my = rows + threadIdx.x * ROW_B;
+  if (active)
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
     double val[2] = {0.0, 0.0}, grad[2][2], e[4], tau[4], f[6];
@@ -478,10 +510,7 @@ __global__ void __launch_bounds__(128) form_action_vm6_kernel(const __grid_const
     form_cotangent<2, 2>(2, tau, Vs, Gs);
     form_accumulate<2, 2, NB, true>(T, 2, q, W.w[q] * adet, Vs, Gs, K, fe);
   }
-#pragma unroll
-  for (int a = 0; a < NB; ++a)
-#pragma unroll
-    for (int k = 0; k < 2; ++k) atomicAdd(y + 2 * int64_t(idx[a]) + k, fe[a][k]);
+  form_scatter_pairs<NB>(y, idx, fe, active);
 }
 
 // factored tangent -> the reference's (n, 4, 4) layout, by the statements of vm_point / vm_point_fast (bit-identical to what
@@ -575,14 +604,14 @@ __global__ void __launch_bounds__(FORM_THREADS, 3) form_vm_step_kernel(
 // sectors), and the element vector accumulates in registers - no shared memory, no barriers, nb*bs REDs per cell, 35 %
 // fewer instructions than the per-point mapping.  168 registers, 12 warps per SM, persistent grid-stride loop (the
 // block-wide sum of the plastic counts, one barrier, is paid once per CTA).  Per-point arithmetic is that of the kernel
-// above, statement for statement (bit-identical per-point results).  Measured per 1e8 points on the row-major numbered
-// mesh: 5.18-5.21 ms against 5.55-5.60 for the per-point kernel (128 registers / 16 warps: 5.71, spills; L2 prefetch of the
-// next cell's streams: 5.29; a register-free cp.async pipeline of the next cell's inputs through shared memory: 5.40) - but
-// on the Z-order numbered mesh (the locality real meshes have) 6.47 against 5.54 ms: a warp's 32 cells spread every gather
-// instruction over more lines than the per-point warp's 11 cells.  Hence OPT-IN (EO_STEP_CELL=1), not the default
-// (profiles/r2_rejected_variants.md).
+// above, statement for statement (bit-identical per-point results).  Measured per 1e8 points: 5.03 ms against 5.60 for the
+// per-point kernel on the row-major numbered mesh, 5.50 against 5.52 on the Z-order numbered one (2 % ahead on RCM, 1 %
+// behind on a randomly shuffled numbering) - with the element vector scattered by lane pairs (form_scatter_pairs); with
+// one RED per lane and entry this mapping lost 15 % on the Z-order numbering.  Variants measured slower: 128 registers /
+// 16 warps (5.71, spills), L2 prefetch of the next cell's streams (5.29), a register-free cp.async pipeline of the next
+// cell's inputs through shared memory (5.40) - profiles/r2_rejected_variants.md.
 #define FORM_CELL_THREADS 128
-template <int NB, bool EXACT>
+template <int NB, bool EXACT, bool FACT>  // FACT: the tangent stored as its 6 factors (see form_vm_step_kernel)
 __global__ void __launch_bounds__(FORM_CELL_THREADS, 3) form_vm_step_cell_kernel(
     const __grid_constant__ tab_tables T, const __grid_constant__ form_weights W, const vm_consts vq,
     const int32_t* __restrict__ dofmap, const int32_t* __restrict__ x_dofmap, const double* __restrict__ x,
@@ -590,19 +619,24 @@ __global__ void __launch_bounds__(FORM_CELL_THREADS, 3) form_vm_step_cell_kernel
     const double* __restrict__ sigma_n, const double* __restrict__ p, double* __restrict__ C_tang,
     double* __restrict__ sigma, double* __restrict__ dp_out, double* __restrict__ b, eo_stats* stats) {
   int plastic = 0;
-  for (int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; c < n_cells; c += int64_t(gridDim.x) * blockDim.x) {
+  // the loop condition is warp uniform (the lanes of a pair exchange contributions in the scatter); lanes past the end idle
+  for (int64_t cw = blockIdx.x * int64_t(blockDim.x) + (threadIdx.x & ~31u); cw < n_cells; cw += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t c = cw + (threadIdx.x & 31u);
+    const bool active = c < n_cells;
     int32_t idx[NB];
+    double fe[NB][2];
+#pragma unroll
+    for (int a = 0; a < NB; ++a) idx[a] = 0, fe[a][0] = 0.0, fe[a][1] = 0.0;
+    if (active) {
     tab_load_idx<NB>(dofmap, c, idx);
     const int64_t i0 = 3 * c;
     eo_d4 sn[3];
     double pn[3];
 #pragma unroll
     for (int q = 0; q < 3; ++q) sn[q] = eo_ld256(sigma_n + 4 * (i0 + q)), pn[q] = eo_ld64(p + i0 + q);
-    double w[NB][2], K[2][2], fe[NB][2];
+    double w[NB][2], K[2][2];
     const double adet = form_cell_geometry(T, x_dofmap, x, geoK, geoD, c, K);
     tab_gather_idx<2, NB>(u, idx, w);
-#pragma unroll
-    for (int a = 0; a < NB; ++a) fe[a][0] = 0.0, fe[a][1] = 0.0;
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
       double val[2] = {0.0, 0.0}, grad[2][2], e[4];
@@ -614,21 +648,26 @@ __global__ void __launch_bounds__(FORM_CELL_THREADS, 3) form_vm_step_cell_kernel
       else
         vm_point_fast(vq, e[0], e[1], e[2], e[3], sn[q].x, sn[q].y, sn[q].z, sn[q].w, pn[q], o);
       plastic += o.dp > 0.0;
-      double* Ct = C_tang + 16 * (i0 + q);
-      eo_st256(Ct + 0, o.C[0], o.C[1], o.C[2], o.C[3]);
-      eo_st256(Ct + 4, o.C[4], o.C[5], o.C[6], o.C[7]);
-      eo_st256(Ct + 8, o.C[8], o.C[9], o.C[10], o.C[11]);
-      eo_st256(Ct + 12, o.C[12], o.C[13], o.C[14], o.C[15]);
+      if (FACT) {
+        double* Tf = C_tang + 6 * (i0 + q);
+        eo_st128(Tf + 0, o.v[0], o.v[1]);
+        eo_st128(Tf + 2, o.v[2], o.v[3]);
+        eo_st128(Tf + 4, o.cn, o.cd);
+      } else {
+        double* Ct = C_tang + 16 * (i0 + q);
+        eo_st256(Ct + 0, o.C[0], o.C[1], o.C[2], o.C[3]);
+        eo_st256(Ct + 4, o.C[4], o.C[5], o.C[6], o.C[7]);
+        eo_st256(Ct + 8, o.C[8], o.C[9], o.C[10], o.C[11]);
+        eo_st256(Ct + 12, o.C[12], o.C[13], o.C[14], o.C[15]);
+      }
       eo_st256(sigma + 4 * (i0 + q), o.g[0], o.g[1], o.g[2], o.g[3]);
       eo_st64(dp_out + i0 + q, o.dp);
       double Vs[2], Gs[2][2];
       form_cotangent<2, 2>(2, o.g, Vs, Gs);
       form_accumulate<2, 2, NB>(T, 2, q, W.w[q] * adet, Vs, Gs, K, fe);
     }
-#pragma unroll
-    for (int a = 0; a < NB; ++a)
-#pragma unroll
-      for (int k = 0; k < 2; ++k) atomicAdd(b + 2 * int64_t(idx[a]) + k, fe[a][k]);
+    }
+    form_scatter_pairs<NB>(b, idx, fe, active);
   }
   eo_block_sum_add(reinterpret_cast<unsigned long long*>(&stats->n_plastic), plastic);
   if (blockIdx.x == 0 && threadIdx.x == 0)
@@ -1140,10 +1179,9 @@ static int form_vm_step_impl(eo_form* f, const eo_vm_params* prm, const double* 
     const int grc = eo_tab_geometry(t);
     if (grc != EO_OK) return grc;
   }
-  // EO_STEP_CELL=1: one thread per cell (three points per cell on P1 / P2 triangles).  Opt-in: 7 % faster than the per-point
-  // kernel on a row-major numbered mesh, 15 % slower on a Z-order numbered one (header of form_vm_step_cell_kernel)
-  static const bool cell_env = [] { const char* e = getenv("EO_STEP_CELL"); return e && *e == '1'; }();
-  const bool cellwise = cell_env && !fact && t->T.nq == 3 && (t->T.nb == 3 || t->T.nb == 6);
+  // three points per cell on P1 / P2 triangles: one thread per cell (EO_STEP_CELL=0: the per-point kernel, for A/B)
+  static const bool cell_env = [] { const char* e = getenv("EO_STEP_CELL"); return !(e && *e == '0'); }();
+  const bool cellwise = cell_env && t->T.nq == 3 && (t->T.nb == 3 || t->T.nb == 6);
   // the cells [c0, c1): every per-cell / per-point array is addressed relative to c0
   auto launch = [&](int64_t c0, int64_t c1, const double* du, double* db) -> int {
     const int64_t m = c1 - c0, o = c0 * t->T.nq;
@@ -1163,8 +1201,11 @@ static int form_vm_step_impl(eo_form* f, const eo_vm_params* prm, const double* 
     if (cellwise) {
       const int64_t tiles_c = (m + FORM_CELL_THREADS - 1) / FORM_CELL_THREADS, cap_c = int64_t(ctx->sm_count) * 3 * FORM_WAVES;
       const unsigned gridc = (unsigned)(tiles_c < cap_c ? tiles_c : cap_c);
-#define EO_STEP_CELL(N, X) \
-  if (t->T.nb == N && bool(exact) == X) form_vm_step_cell_kernel<N, X><<<gridc, FORM_CELL_THREADS, 0, ctx->s_cmp>>>(EO_STEP_ARGS(N));
+#define EO_STEP_CELL(N, X)                                                                                              \
+  if (t->T.nb == N && bool(exact) == X) {                                                                               \
+    if (fact) form_vm_step_cell_kernel<N, X, true><<<gridc, FORM_CELL_THREADS, 0, ctx->s_cmp>>>(EO_STEP_ARGS(N));       \
+    else form_vm_step_cell_kernel<N, X, false><<<gridc, FORM_CELL_THREADS, 0, ctx->s_cmp>>>(EO_STEP_ARGS(N));           \
+  }
       EO_STEP_CELL(3, true) EO_STEP_CELL(3, false) EO_STEP_CELL(6, true) EO_STEP_CELL(6, false)
 #undef EO_STEP_CELL
       ctx->launches += 1;

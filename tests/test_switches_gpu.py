@@ -1,8 +1,8 @@
 """The per-cell geometry cache of the tabulation handle (`eo_tab_geometry`), the whole-line tangent stores of the fused
 kernel (`eo_st_tangent_quad`) and the one-thread-per-cell mapping of the residual step (`form_vm_step_cell_kernel`) change
 how values are fetched, stored and scheduled, never the values: processes run with the switches flipped (EO_GEOM_CACHE=0,
-EO_QUAD_STORE=0 - the round-1 code paths; EO_STEP_CELL=1 - the opt-in mapping) must reproduce the default results BIT FOR
-BIT for every per-point array; the scattered integrals (atomic adds in arbitrary order) agree to 1e-13 of their scale."""
+EO_QUAD_STORE=0, EO_STEP_CELL=0 - the round-1 code paths) must reproduce the default results BIT FOR BIT for every
+per-point array; the scattered integrals (atomic adds in arbitrary order) agree to 1e-13 of their scale."""
 
 import os
 import subprocess
@@ -26,8 +26,8 @@ def _run(tmp_path, name, **env):
 def test_geometry_cache_and_quad_stores_do_not_change_results(tmp_path):
     ref = _run(tmp_path, "default")
     for name, env in (("nocache", {"EO_GEOM_CACHE": "0"}), ("noquad", {"EO_QUAD_STORE": "0"}),
-                      ("percell", {"EO_STEP_CELL": "1"}),
-                      ("round1", {"EO_GEOM_CACHE": "0", "EO_QUAD_STORE": "0"})):
+                      ("perpoint", {"EO_STEP_CELL": "0"}),
+                      ("round1", {"EO_GEOM_CACHE": "0", "EO_QUAD_STORE": "0", "EO_STEP_CELL": "0"})):
         got = _run(tmp_path, name, **env)
         assert sorted(got.files) == sorted(ref.files)
         for k in ref.files:

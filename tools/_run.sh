@@ -1,4 +1,5 @@
-python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-python bench.py > gpurun_out/r2i_bench_default.json 2> gpurun_out/r2i_bench_default.err; tail -c 300 gpurun_out/r2i_bench_default.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/r2i_default_cmd_launches.csv python bench.py --steps 3 --warmup 3 > gpurun_out/r2i_default_cmd.log 2>&1
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+python -m pytest tests/test_forms_gpu.py tests/test_switches_gpu.py -x -q -m gpu 2>&1 | tail -2
+run() { python bench.py --model $M --steps 10 --warmup 3 --cpu-seconds 0 --e2e-n 0 $X 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$M', '$X', d['ms_per_step'], d['roofline']['frac'], d['value'])"; }
+M=step6; for X in "--n 1e8" "--mesh-order morton --n 1e8"; do run; EO_STEP_CELL=0 run; done
