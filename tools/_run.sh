@@ -1,5 +1,5 @@
-python -m pytest tests/test_forms_gpu.py tests/test_switches_gpu.py -x -q -m gpu 2>&1 | tail -2
-run() { python bench.py --model $M --steps 10 --warmup 3 --cpu-seconds 0 --e2e-n 0 $X 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$M', '$X', d['ms_per_step'], d['roofline']['frac'], d['value'])"; }
-M=step6; for X in "--n 1e8" "--mesh-order morton --n 1e8"; do run; EO_STEP_CELL=0 run; done
+SKIP=4 bash tools/prof_kernel.sh step form_vm_step_cell 1e8 r2l_step
+SKIP=4 bash tools/prof_kernel.sh action form_action_tma 1e8 r2l_action
+SKIP=4 bash tools/prof_kernel.sh action6 form_action_vm6 1e8 r2l_action6
+rm -f gpurun_out/r2l_*.ncu-rep
+ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/r2l_default_cmd_launches.csv python bench.py --steps 3 --warmup 3 > gpurun_out/r2l_default_cmd.log 2>&1
