@@ -4,6 +4,14 @@
 // compiled with -fmad=false so that the results are the plain IEEE sequence of the reference's statements.
 #pragma once
 
+// host/device header: the CUDA kernels and the CPU test harness (tests/hostcheck/) compile the same source
+#if defined(__CUDACC__)
+#define EO_VM_HD __device__ __forceinline__
+#else
+#include <cmath>
+#define EO_VM_HD inline
+#endif
+
 struct vm_consts {
   double l, m, H, s0;
 };
@@ -18,7 +26,7 @@ struct vm_point_out {
 };
 
 // C_t from its factors, the reference's statement sequence (:323-326 with C_elas, dev written out)
-__device__ __forceinline__ void vm_tangent_exact(const vm_consts& q, const double v[4], double cn, double cd, double C[16]) {
+EO_VM_HD void vm_tangent_exact(const vm_consts& q, const double v[4], double cn, double cd, double C[16]) {
   const double l = q.l, m = q.m;
   const double l2m = l + 2.0 * m;
   const double third = 1.0 / 3.0;
@@ -35,7 +43,7 @@ __device__ __forceinline__ void vm_tangent_exact(const vm_consts& q, const doubl
 }
 
 // the same with the symmetry used and explicit FMAs (vm_point_fast)
-__device__ __forceinline__ void vm_tangent_fast(const vm_consts& q, const double v[4], double cn, double cd, double C[16]) {
+EO_VM_HD void vm_tangent_fast(const vm_consts& q, const double v[4], double cn, double cd, double C[16]) {
   const double l = q.l, m = q.m;
   const double l2m = l + 2.0 * m;
   const double third = 1.0 / 3.0;
@@ -54,7 +62,7 @@ __device__ __forceinline__ void vm_tangent_fast(const vm_consts& q, const double
 }
 
 // tau = C_t e straight from the factors (device-side consumers: 48 instead of 128 bytes per point)
-__device__ __forceinline__ void vm_factored_apply(const vm_consts& q, const double v[4], double cn, double cd,
+EO_VM_HD void vm_factored_apply(const vm_consts& q, const double v[4], double cn, double cd,
                                                   const double e[4], double tau[4]) {
   const double l = q.l, m = q.m;
   const double dD = (l + 2.0 * m) - cd * (2.0 / 3.0), dO = l + cd * (1.0 / 3.0);
@@ -65,7 +73,7 @@ __device__ __forceinline__ void vm_factored_apply(const vm_consts& q, const doub
   tau[3] = fma(-ve, v[3], (2.0 * m - cd) * e[3]);
 }
 
-__device__ __forceinline__ void vm_point(const vm_consts& q, double e0, double e1, double e2, double e3, double n0,
+EO_VM_HD void vm_point(const vm_consts& q, double e0, double e1, double e2, double e3, double n0,
                                          double n1, double n2, double n3, double pi, vm_point_out& o) {
   const double l = q.l, m = q.m, H = q.H;
   const double l2m = l + 2.0 * m;
@@ -103,7 +111,7 @@ __device__ __forceinline__ void vm_point(const vm_consts& q, double e0, double e
 // downstream algebra uses two divisions instead of nine (n = s * (f+ / (sigma_eq f))), a precomputed
 // 1/(3 mu + H), the symmetry of the tangent and explicit FMAs.  Results agree with vm_point to a few ulp
 // (tests: rtol 1e-12); elastic points still give dp = 0, sigma = sigma_trial and C_t = C_elas exactly.
-__device__ __forceinline__ void vm_point_fast(const vm_consts& q, double e0, double e1, double e2, double e3, double n0,
+EO_VM_HD void vm_point_fast(const vm_consts& q, double e0, double e1, double e2, double e3, double n0,
                                               double n1, double n2, double n3, double pi, vm_point_out& o) {
   const double l = q.l, m = q.m, H = q.H;
   const double l2m = l + 2.0 * m;

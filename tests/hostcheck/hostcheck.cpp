@@ -6,6 +6,7 @@
 #include "tab_core.cuh"
 #include "form_core.cuh"
 #include "isihara_core.cuh"
+#include "vm_core.cuh"
 
 template <int GDIM, int BS, int NB>
 static void tab_cells(const tab_tables& T, int kind, const int32_t* dofmap, const int32_t* x_dofmap, const double* x,
@@ -100,6 +101,27 @@ int hostcheck_form(int gdim, int bs, int nb, int nq, int kind_test, int kind_tri
   else if (gdim == 3 && bs == 1 && nb == 10) form_cells<3, 1, 10>(T, weights, kind_test, kind_trial, dofmap, x_dofmap, xg, D, x, n_cells, y);
   else return -1;
   return 0;
+}
+
+// von Mises radial return of vm_core.cuh: exact != 0 = the reference's statement sequence (vm_point), else the
+// few-division / FMA form (vm_point_fast).  T6[n][6] = the tangent's factors (v, cn, cd); tau[n][4] = vm_factored_apply of
+// those factors on e_probe[n][4]
+void hostcheck_vm(double lmbda, double mu, double H, double sigma_0, const double* deps, const double* sigma_n, const double* p,
+                  int64_t n, int exact, double* C_tang, double* sigma, double* dp, double* T6, const double* e_probe,
+                  double* tau) {
+  const vm_consts q{lmbda, mu, H, sigma_0};
+  for (int64_t i = 0; i < n; ++i) {
+    vm_point_out o;
+    const double *e = deps + 4 * i, *s = sigma_n + 4 * i;
+    if (exact)
+      vm_point(q, e[0], e[1], e[2], e[3], s[0], s[1], s[2], s[3], p[i], o);
+    else
+      vm_point_fast(q, e[0], e[1], e[2], e[3], s[0], s[1], s[2], s[3], p[i], o);
+    for (int k = 0; k < 16; ++k) C_tang[16 * i + k] = o.C[k];
+    for (int k = 0; k < 4; ++k) sigma[4 * i + k] = o.g[k], T6[6 * i + k] = o.v[k];
+    dp[i] = o.dp, T6[6 * i + 4] = o.cn, T6[6 * i + 5] = o.cd;
+    vm_factored_apply(q, o.v, o.cn, o.cd, e_probe + 4 * i, tau + 4 * i);
+  }
 }
 
 void hostcheck_isihara(const isi_weights* w, const double* F, double* dP, double* P, int64_t n) {

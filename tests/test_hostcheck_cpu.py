@@ -63,3 +63,43 @@ def test_mc_core_edge_semantics(hc):
     assert list(o["niter"]) == [0, 0, 0] == list(r["niter"])
     assert np.array_equal(o["sigma"], r["sigma"])
     assert np.array_equal(np.isnan(o["C_tang"]), np.isnan(r["C_tang"]))
+
+
+@pytest.mark.parametrize("batch", ["mixed", "elastic", "plastic"])
+@pytest.mark.parametrize("exact", [True, False])
+def test_vm_core_and_factored_tangent(hc, golden_dir, exact, batch):
+    """vm_core.cuh on the host: both forms reproduce the golden made by the reference's own Numba kernel (flags exactly,
+    values to 1e-12), the exact statement sequence is bit-identical to the C oracle; the tangent's factors (v, cn, cd) rebuild
+    C_t = C_elas - cn v v^T - cd dev, and vm_factored_apply(e) == C_t e (what the factored tangent action computes)."""
+    g = np.load(os.path.join(golden_dir, "vm_seed0_n1026.npz"))
+    deps, sn, p = (np.ascontiguousarray(g[f"{batch}_{k}"], dtype=np.float64) for k in ("deps", "sigma_n", "p"))
+    n = p.size
+    prm = oc.VonMisesParams()
+    rng = np.random.default_rng(3)
+    e = rng.normal(size=(n, 4))
+    out = {k: np.empty(s) for k, s in (("C", (n, 4, 4)), ("sig", (n, 4)), ("dp", n), ("T6", (n, 6)), ("tau", (n, 4)))}
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    hc.hostcheck_vm(C.c_double(prm.lmbda), C.c_double(prm.mu), C.c_double(prm.H), C.c_double(prm.sigma_0), ptr(deps), ptr(sn),
+                    ptr(p), C.c_int64(n), C.c_int(int(exact)), ptr(out["C"]), ptr(out["sig"]), ptr(out["dp"]), ptr(out["T6"]),
+                    ptr(e), ptr(out["tau"]))
+    gC, gs, gdp = g[f"{batch}_C_tang"].reshape(n, 4, 4), g[f"{batch}_sigma"].reshape(n, 4), g[f"{batch}_dp"].reshape(n)
+    assert np.array_equal(out["dp"] > 0, gdp > 0)
+    if batch == "mixed":
+        assert 0.2 < (gdp > 0).mean() < 0.8
+    for a, b in ((out["C"], gC), (out["sig"], gs), (out["dp"], gdp)):  # the golden itself: rounding (Numba / NumPy order)
+        assert np.abs(a - b).max() <= 1e-12 * max(np.abs(b).max(), 1e-300)
+    if exact:  # same statement order as the non-contracting C oracle: identical bits (what the GPU kernel is held to)
+        rC, rs, rdp = native.vm_return_mapping(deps, sn, p, prm)
+        assert np.array_equal(out["C"], rC.reshape(n, 4, 4)) and np.array_equal(out["sig"], rs.reshape(n, 4))
+        assert np.array_equal(out["dp"], np.asarray(rdp).reshape(n))
+    # the factors
+    v, cn, cd = out["T6"][:, :4], out["T6"][:, 4], out["T6"][:, 5]
+    el = gdp == 0
+    assert np.all(v[el] == 0.0) and np.all(cd[el] == 0.0)
+    l, m = prm.lmbda, prm.mu
+    Cel = np.array([[l + 2 * m, l, l, 0], [l, l + 2 * m, l, 0], [l, l, l + 2 * m, 0], [0, 0, 0, 2 * m]])
+    dev = np.eye(4) - np.outer([1, 1, 1, 0], [1, 1, 1, 0]) / 3.0
+    Cr = Cel[None] - cn[:, None, None] * v[:, :, None] * v[:, None, :] - cd[:, None, None] * dev[None]
+    assert np.abs(Cr - out["C"]).max() <= 1e-13 * np.abs(out["C"]).max()
+    tau_ref = np.einsum("nij,nj->ni", out["C"], e)
+    assert np.abs(out["tau"] - tau_ref).max() <= 1e-12 * np.abs(tau_ref).max()
