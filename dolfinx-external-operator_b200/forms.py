@@ -179,9 +179,8 @@ class QuadratureForms:
         stay in HBM as `self.C_tang`, `mc.sigma_dev`) -> b = int sigma . eps(v) dx.  Default: three launches
         (tabulation, the two-pass Mohr-Coulomb kernels, the stress integral - it needs both passes' stresses).
         fused=True tabulates the strain inside pass 1 (`eo_mc_eval_tabulated`: kept only for the plastic points, the
-        32 B/point strain array of the mesh is never allocated); measured 3.30 against 3.07 ms per 2e7 points - the
-        gather makes the latency-bound pass 1 slower than the strain round trip costs, so it is a memory, not a time
-        saving."""
+        32 B/point strain array of the mesh is never allocated); measured 2.85 ms per 2e7 points either way with the
+        final kernels (3.30 against 3.07 earlier in round 2), so it is a memory, not a time saving."""
         t = self.tab
         n = t.n_cells * t.nq
         if mc.n_qp is None:
