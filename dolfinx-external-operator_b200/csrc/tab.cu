@@ -85,12 +85,14 @@ __global__ void __launch_bounds__(256) tab_geometry_kernel(const __grid_constant
 
 int eo_tab_geometry(eo_tab* t) {
   static const bool on = [] { const char* e = getenv("EO_GEOM_CACHE"); return !(e && *e == '0'); }();
-  if (!on || t->geoK || t->T.gdim != 2 || t->n_cells == 0) return EO_OK;
+  if (!on || t->geoK || t->geo_failed || t->T.gdim != 2 || t->n_cells == 0) return EO_OK;
   eo_ctx* ctx = t->ctx;
+  EO_CUDA(ctx, cudaSetDevice(ctx->device));
   double *k = nullptr, *d = nullptr;
   if (cudaMalloc(&k, size_t(t->n_cells) * 32) != cudaSuccess || cudaMalloc(&d, size_t(t->n_cells) * 8) != cudaSuccess) {
-    cudaGetLastError();  // no room for the cache: the kernels compute the geometry per point
+    cudaGetLastError();  // no room for the cache: the kernels compute the geometry per point (not tried again)
     if (k) cudaFree(k);
+    t->geo_failed = true;
     return EO_OK;
   }
   tab_geometry_kernel<<<unsigned((t->n_cells + 255) / 256), 256, 0, ctx->s_cmp>>>(t->T, t->x_dofmap, t->x, t->n_cells, k, d);

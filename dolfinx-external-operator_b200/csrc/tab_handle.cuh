@@ -19,6 +19,7 @@ struct eo_tab {
   // [n_cells][4] (2-d meshes), and |det J| [n_cells]; built at the first fused / residual-step launch
   double* geoK = nullptr;
   double* geoD = nullptr;
+  bool geo_failed = false;  // the allocation did not fit once: the kernels compute the geometry per point
 };
 
 // builds t->geoK / t->geoD if the handle qualifies (2-d affine cells) and EO_GEOM_CACHE is not 0; leaves them NULL
